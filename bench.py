@@ -1,0 +1,323 @@
+#!/usr/bin/env python
+"""bench.py — NBNXM short-range nonbonded force step on B200 (driver contract in the task prompt).
+
+  python bench.py [--gpus N] [--steps K] [--warmup W] [--workload NAME] [--impl reference]
+
+A "step" is one pass of the hot path over the synthetic water box named in config.workload:
+clear outputs -> force(+energy) kernel on the dynamically pruned list -> rolling prune on the reference's
+schedule (every 2nd step, numParts = nstlistPrune/2) -> pack forces (float4 -> float3), with coordinates
+already resident in HBM.  `value` = useful pair interactions per second, the quantity
+`gmx nonbonded-benchmark` prints (N/2 (rho 4/3 pi rc^3 + 1) pairs per step,
+src/gromacs/nbnxm/benchmark/bench_setup.cpp:332-337).  `e2e` is the same metric through the public API
+with host buffers (H2D of xq and D2H of forces + energies inside the timed region).  `roofline` reports
+the force kernel alone against the measured FP32-FMA peak using the reference's flop model
+(src/gromacs/gmxlib/nrnb.cpp:92-112) on the pairs the kernel actually evaluates.
+
+--impl reference times the UNMODIFIED reference's CPU SIMD kernel (oracle/_ref/bench_ref, linked against
+the reference's own libgromacs) on the host cores for the same workload.
+"""
+import argparse
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+METRIC = "useful_pair_interactions_per_s"
+UNIT = "Gpairs/s"
+DEFAULT_WORKLOAD = "water96k_fswitch"
+REF_VDW = {"cut": "cut", "fswitch": "fswitch", "pswitch": "pswitch", "ljpme": "ljpme"}
+
+
+def host_cores():
+    try:
+        return len(os.sched_getaffinity(0))
+    except Exception:
+        return os.cpu_count() or 1
+
+
+def run_reference_cpu(cfg, natoms_k, budget_s=20.0, threads=None):
+    """Time the reference's SIMD kernel on a bounded number of iterations (about budget_s of CPU work)."""
+    exe = os.path.join(ROOT, "oracle", "_ref", "bench_ref")
+    threads = threads or host_cores()
+    if not os.path.exists(exe):
+        return None
+    base = [exe, "--size", str(natoms_k), "--rc", str(cfg["rc"]), "--vdw", REF_VDW[cfg["vdw"]],
+            "--energy", "1" if cfg["energy"] else "0", "--nt", str(threads)]
+    env = dict(os.environ, OMP_NUM_THREADS=str(threads), OMP_PROC_BIND="close", OMP_PLACES="cores")
+
+    def call(iters, warm):
+        out = subprocess.run(base + ["--iter", str(iters), "--warmup", str(warm)], env=env, check=True,
+                             capture_output=True, text=True).stdout.strip().splitlines()[-1]
+        return json.loads(out)
+    probe = call(2, 1)
+    iters = int(max(3, min(2000, budget_s / max(probe["sec_per_iter"], 1e-6))))
+    res = call(iters, 2)
+    res["threads"] = threads
+    return res
+
+
+def run_port_cpu(wl, plist, budget_s=15.0, threads=None):
+    """Fallback CPU baseline: the oracle's float32 OpenMP port on a slice of the sci entries."""
+    import numpy as np
+    from oracle import oracle_py as O
+    threads = threads or host_cores()
+    p = O.OrcParams()
+    for name, _ in wl.params._fields_:
+        if hasattr(p, name):
+            setattr(p, name, getattr(wl.params, name))
+    p.ntypes = wl.nbat.numTypes
+    nsci = plist.sci.shape[0]
+    sample = max(1, min(nsci, 64 * threads))
+    while True:
+        t0 = time.perf_counter()
+        _, _, n = O.forces_f32_omp(p, plist.sci[:sample], plist.cjPacked, plist.excl, wl.nbat.xq, wl.nbat.type,
+                                   wl.nbat.lj_comb, wl.nbat.nbfp, wl.nbat.nbfp_comb, wl.nbat.shift_vec,
+                                   calc_energy=wl.cfg["energy"], nthreads=threads)
+        dt = time.perf_counter() - t0
+        if dt > 0.3 * budget_s or sample == nsci:
+            break
+        sample = min(nsci, sample * 4)
+    return dict(sec=dt, computed_pairs=n, sample_sci=sample, nsci=nsci, threads=threads)
+
+
+class ClockSampler:
+    """nvidia-smi clocks / throttle reasons during the timed region (B200_PROFILING.md)."""
+    Q = ("clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,"
+         "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,"
+         "clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, index):
+        self.index, self.rows, self.proc = index, [], None
+
+    def start(self):
+        try:
+            self.proc = subprocess.Popen(["nvidia-smi", "-i", str(self.index), "--query-gpu=" + self.Q,
+                                          "--format=csv,noheader,nounits", "-lms", "100"],
+                                         stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+            self.thread = threading.Thread(target=self._read, daemon=True)
+            self.thread.start()
+        except Exception:
+            self.proc = None
+
+    def _read(self):
+        for line in self.proc.stdout:
+            self.rows.append([c.strip() for c in line.split(",")])
+
+    def stop(self):
+        if not self.proc:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+        self.proc.terminate()
+        try:
+            self.proc.wait(timeout=2)
+        except Exception:
+            self.proc.kill()
+        sm, smax, reasons = [], None, set()
+        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        for r in self.rows:
+            try:
+                sm.append(float(r[0]))
+                smax = float(r[1])
+                for n, v in zip(names, r[3:7]):
+                    if v.lower().startswith("active"):
+                        reasons.add(n)
+            except Exception:
+                pass
+        sm.sort()
+        return {"sm_mhz": sm[len(sm) // 2] if sm else None, "sm_max_mhz": smax, "reasons": sorted(reasons),
+                "samples": len(sm)}
+
+
+def reference_arm(args):
+    """--impl reference: the reference's own CPU kernels on the host cores, rank 0 only."""
+    if int(os.environ.get("RANK", "0")) != 0:
+        return
+    from gromacs_b200.workload import CONFIGS
+    import math
+    cfg = CONFIGS[args.workload]
+    res = run_reference_cpu(cfg, cfg["k"], budget_s=max(5.0, min(60.0, 6.0 * args.steps)))
+    if res is None:
+        print(json.dumps({"impl": "reference", "unavailable": "oracle/_ref/bench_ref is not built (needs the reference sources)"}))
+        return
+    value = res["useful_pairs"] / res["sec_per_iter"] * 1e-9
+    line = {
+        "impl": "reference", "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": args.gpus, "steps": res["iters"],
+        "warmup": 2, "ms_per_step": res["sec_per_iter"] * 1e3, "higher_is_better": True, "scaling": "strong",
+        "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+        "config": {"workload": args.workload, "natoms": int(res["natoms"]), "rc_nm": cfg["rc"], "vdw": cfg["vdw"],
+                   "energy_every_step": cfg["energy"],
+                   "note": "reference SIMD 4xM kernel (AVX2_256 build), its own CPU pair list with rlist = rc"},
+        "cpu_baseline": {"value": value, "unit": UNIT, "cores": res["threads"], "kind": "reference",
+                         "sample": "%d iterations of the full %d-atom system" % (res["iters"], int(res["natoms"]))},
+        "e2e": {"value": value, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+    }
+    print(json.dumps(line))
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=50)
+    ap.add_argument("--warmup", type=int, default=5)
+    ap.add_argument("--workload", default=None)
+    ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-l2-flush", action="store_true")
+    args = ap.parse_args()
+    if args.workload is None:
+        args.workload = DEFAULT_WORKLOAD if args.gpus == 1 else "water1536k"
+    if args.impl == "reference":
+        return reference_arm(args)
+
+    import numpy as np
+    import torch
+    from gromacs_b200 import LOCAL, NbnxmGpu, StepWorkload
+    from gromacs_b200.nbnxm import measure_fp32_peak
+    from gromacs_b200.workload import make_workload
+
+    rank = int(os.environ.get("RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    local_rank = int(os.environ.get("LOCAL_RANK", "0"))
+    if world > 1:
+        from gromacs_b200.multigpu import bench_multi_gpu
+        return bench_multi_gpu(args, rank, world, local_rank)
+    if args.gpus != 1:
+        sys.exit("launch multi-GPU runs with torch.distributed.run (one rank per GPU)")
+
+    torch.cuda.set_device(local_rank)
+    wl = make_workload(args.workload)
+    cfg, nbat = wl.cfg, wl.nbat
+    energy = cfg["energy"]
+    sw = StepWorkload(computeEnergy=energy, computeVirial=energy, useGpuFBufferOps=True)
+    # pinned host buffers, like the reference's HostAllocationPolicy
+    xq_pin = torch.empty((nbat.numAtoms(), 4), dtype=torch.float32).pin_memory()
+    xq_pin.numpy()[:] = nbat.xq
+    nbat.xq = xq_pin.numpy()
+    f_pin = torch.zeros((nbat.numAtoms(), 3), dtype=torch.float32).pin_memory()
+    nbat.f = f_pin.numpy()
+
+    nb = NbnxmGpu(wl.params, nbat, device=local_rank)
+    plist = wl.pairlist(min_sci=nb.gpu_min_ci_balanced())
+    nb.gpu_init_atomdata(nbat)
+    nb.gpu_init_pairlist(plist, LOCAL)
+    nb.setupGpuShortRangeWork(LOCAL)
+    nb.gpu_upload_shiftvec(nbat)
+    nb.gpu_copy_xq_to_gpu(nbat, LOCAL)
+    local_stream = torch.cuda.ExternalStream(nb.streams()[0])
+    num_parts = 3          # nstlistPrune 6 -> numRollingPruningParts = nstlistPrune / 2 (pairlist_tuning.cpp:685)
+    flush = None if args.no_l2_flush else torch.empty(256 << 20, dtype=torch.uint8, device="cuda")
+
+    def step(i, host_io):
+        if host_io:
+            nb.gpu_copy_xq_to_gpu(nbat, LOCAL)
+        nb.gpu_clear_outputs(computeVirial=energy)
+        nb.gpu_launch_kernel(sw, LOCAL)
+        if cfg["dynamic_pruning"] and i % 2 == 1:     # isDynamicPruningStepGpu, pairlistsets.h:108-115
+            nb.gpu_launch_kernel_pruneonly(LOCAL, num_parts)
+        sw.useGpuFBufferOps = not host_io
+        nb.gpu_launch_cpyback(nbat, sw, LOCAL)
+        if host_io:
+            return nb.gpu_wait_finish_task(sw, LOCAL)
+
+    # search step + first-pass prune + a full rolling cycle, untimed
+    nb.set_pair_counting(True)
+    step(0, False)
+    nb.gpu_wait_finish_task(sw, LOCAL)
+    pairs_first = nb.get_pair_count(LOCAL)
+    for i in range(max(args.warmup, 2 * num_parts)):
+        step(i, False)
+    nb.gpu_wait_finish_task(sw, LOCAL)
+    nb.get_pair_count(LOCAL)
+    step(0, False)
+    nb.gpu_wait_finish_task(sw, LOCAL)
+    computed_pairs = nb.get_pair_count(LOCAL)       # pairs one force launch evaluates on the pruned list
+    nb.set_pair_counting(False)
+
+    def timed_run(host_io):
+        ev = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)) for _ in range(args.steps)]
+        torch.cuda.synchronize()
+        l0 = nb.launch_count()
+        t0 = time.perf_counter()
+        for i in range(args.steps):
+            if flush is not None:
+                with torch.cuda.stream(local_stream):
+                    flush.zero_()
+            ev[i][0].record(local_stream)
+            step(i, host_io)
+            ev[i][1].record(local_stream)
+        nb.gpu_wait_finish_task(sw, LOCAL)
+        torch.cuda.synchronize()
+        wall = time.perf_counter() - t0
+        ms = [a.elapsed_time(b) for a, b in ev]
+        return sum(ms) / len(ms), nb.launch_count() - l0, wall
+
+    for i in range(args.warmup):
+        step(i, False)
+    clocks = ClockSampler(local_rank)
+    clocks.start()
+    ms_step, launches, _ = timed_run(False)
+    clock_rec = clocks.stop()
+
+    # force kernel alone (dominant kernel): library-side CUDA events around each launch
+    nb.gpu_reset_timings()
+    nb.set_timing(True)
+    timed_run(False)
+    t = nb.gpu_get_timings()
+    nb.set_timing(False)
+    k_ms = t.force_ms[0][1 if energy else 0] / max(1, t.force_count[0][1 if energy else 0])
+    prune_ms = t.rolling_prune_ms / max(1, t.rolling_prune_count)
+    fp32_peak = measure_fp32_peak(local_rank)
+    achieved = computed_pairs * wl.flops_per_pair / (k_ms * 1e-3) * 1e-12
+
+    # end to end through the public API with host buffers
+    for i in range(args.warmup):
+        step(i, True)
+    ms_e2e, _, _ = timed_run(True)
+
+    value = wl.useful_pairs / (ms_step * 1e-3) * 1e-9
+    line = {
+        "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": 1, "steps": args.steps, "warmup": args.warmup,
+        "ms_per_step": ms_step, "higher_is_better": True, "scaling": "strong", "vs_baseline": None, "dtype": "f32",
+        "data": "synthetic",
+        "config": {"workload": args.workload, "natoms": wl.box.natoms, "rc_nm": cfg["rc"], "vdw": cfg["vdw"],
+                   "elec": "ewald_analytical", "energy_every_step": energy, "rlist_outer_nm": cfg["rlist_outer"],
+                   "rlist_inner_nm": cfg["rlist_inner"], "rolling_prune_parts": num_parts,
+                   "nsci": int(plist.sci.shape[0]), "ncj_packed": int(plist.cjPacked.shape[0]),
+                   "l2": "256 MiB flush between steps, outside the per-step CUDA-event intervals" if flush is not None else "no flush",
+                   "timing": "mean of per-step CUDA-event intervals on the library's local stream"},
+        "us_per_force_step": ms_step * 1e3,
+        "computed_pairs_per_step": computed_pairs,
+        "computed_gpairs_per_s": computed_pairs / (ms_step * 1e-3) * 1e-9,
+        "unpruned_pairs_first_step": pairs_first,
+        "gpu_launches": launches,
+        "clocks": clock_rec,
+        "e2e": {"value": wl.useful_pairs / (ms_e2e * 1e-3) * 1e-9, "unit": UNIT, "ms_per_step": ms_e2e,
+                "h2d_bytes_per_step": int(nbat.numAtoms() * 16),
+                "d2h_bytes_per_step": int(nbat.numAtoms() * 12 + (16 + 45 * 24 if energy else 0))},
+        "roofline": {"bound": "fp32_fma", "achieved": achieved, "peak": fp32_peak, "unit": "TFLOP/s",
+                     "frac": achieved / fp32_peak, "traffic": None,
+                     "kernel": "nbnxm_force_kernel", "kernel_us": k_ms * 1e3, "rolling_prune_us": prune_ms * 1e3,
+                     "flops_per_pair": wl.flops_per_pair,
+                     "peak_source": "measured live: pure-FFMA kernel (nbnxm_b200_measure_fp32_peak); nominal 148 SM x 128 x 2 x 1.965 GHz = 74.45"},
+    }
+    if not args.no_cpu_baseline:
+        res = run_reference_cpu(cfg, cfg["k"], budget_s=15.0)
+        if res is not None:
+            line["cpu_baseline"] = {"value": res["useful_pairs"] / res["sec_per_iter"] * 1e-9, "unit": UNIT,
+                                    "cores": res["threads"], "kind": "reference",
+                                    "sample": "%d iterations of the reference SIMD 4xM kernel on the full system" % res["iters"]}
+        else:
+            r = run_port_cpu(wl, plist)
+            frac = r["computed_pairs"] / max(1, pairs_first)
+            line["cpu_baseline"] = {"value": wl.useful_pairs * frac / r["sec"] * 1e-9, "unit": UNIT, "cores": r["threads"],
+                                    "kind": "port", "sample": "%d of %d sci entries" % (r["sample_sci"], r["nsci"])}
+    nb.gpu_free()
+    print(json.dumps(line))
+
+
+if __name__ == "__main__":
+    main()

@@ -1,0 +1,951 @@
+/* C-ABI implementation of nbnxm_b200 (include/nbnxm_b200.h): device-memory management, stream /
+ * event protocol and kernel launch logic.  It plays the role of the reference's
+ * src/gromacs/nbnxm/nbnxm_gpu_data_mgmt.cpp (buffers, H2D/D2H, events),
+ * src/gromacs/nbnxm/cuda/nbnxm_cuda.cu (launch logic :516-786) and
+ * src/gromacs/nbnxm/gpu_common.h (task completion :141-431), behind plain C entry points.
+ * There is no CPU path: every entry point needs a CUDA device.
+ */
+#include <cstdarg>
+#include <cstdio>
+#include <cstring>
+
+#include <vector>
+
+#include "nbnxm_device.cuh"
+#include "nbnxm_force_kernel.cuh"
+
+namespace nbb
+{
+void launch_prune(bool fresh, const AtomDataDev& ad, const ParamsDev& p, const PairlistDev& pl, int numParts, cudaStream_t stream);
+void launch_sci_sort(const PairlistDev& pl, cudaStream_t stream);
+void launch_x_to_nbat_x(float4* xq, const float* x, const int* atomIndex, int first, int n, cudaStream_t s);
+void launch_f4_to_f3(const float4* f4, float* f3, int first, int n, cudaStream_t s);
+void launch_pack_xq(const float4* xq, const int* index, int n, const float* shift, float4* out, cudaStream_t s);
+void launch_copy4(const float4* in, float4* out, int n, cudaStream_t s);
+void launch_unpack_add_f(float4* f4, const int* index, int n, const float4* in, cudaStream_t s);
+
+ForceKernelPtr select_force_kernel(int elec, int vdw, bool energy, bool prune)
+{
+    switch (elec)
+    {
+        case NBNXM_B200_ELEC_CUT: return select_force_kernel_elec<NBNXM_B200_ELEC_CUT>(vdw, energy, prune);
+        case NBNXM_B200_ELEC_RF: return select_force_kernel_elec<NBNXM_B200_ELEC_RF>(vdw, energy, prune);
+        case NBNXM_B200_ELEC_EWALD_TAB: return select_force_kernel_elec<NBNXM_B200_ELEC_EWALD_TAB>(vdw, energy, prune);
+        case NBNXM_B200_ELEC_EWALD_TAB_TWIN: return select_force_kernel_elec<NBNXM_B200_ELEC_EWALD_TAB_TWIN>(vdw, energy, prune);
+        case NBNXM_B200_ELEC_EWALD_ANA: return select_force_kernel_elec<NBNXM_B200_ELEC_EWALD_ANA>(vdw, energy, prune);
+        case NBNXM_B200_ELEC_EWALD_ANA_TWIN: return select_force_kernel_elec<NBNXM_B200_ELEC_EWALD_ANA_TWIN>(vdw, energy, prune);
+        default: return nullptr;
+    }
+}
+} // namespace nbb
+
+using namespace nbb;
+
+namespace
+{
+
+thread_local char g_lastError[512] = "";
+
+int fail(const char* fmt, ...)
+{
+    va_list ap;
+    va_start(ap, fmt);
+    vsnprintf(g_lastError, sizeof(g_lastError), fmt, ap);
+    va_end(ap);
+    return 1;
+}
+
+#define CU(call)                                                                                      \
+    do                                                                                                \
+    {                                                                                                 \
+        cudaError_t e_ = (call);                                                                      \
+        if (e_ != cudaSuccess)                                                                        \
+        {                                                                                             \
+            return fail("%s:%d %s failed: %s", __FILE__, __LINE__, #call, cudaGetErrorString(e_));    \
+        }                                                                                             \
+    } while (0)
+
+template<typename T>
+struct DevBuf
+{
+    T*     p     = nullptr;
+    size_t n     = 0;
+    size_t alloc = 0;
+    /* grow-only reallocation with 20 % slack, contents are not preserved
+     * (reallocateDeviceBuffer, src/gromacs/gpu_utils/devicebuffer.h) */
+    cudaError_t reserve(size_t count)
+    {
+        n = count;
+        if (count <= alloc)
+        {
+            return cudaSuccess;
+        }
+        if (p)
+        {
+            cudaFree(p);
+            p = nullptr;
+        }
+        alloc         = count + count / 5 + 64;
+        cudaError_t e = cudaMalloc(&p, alloc * sizeof(T));
+        if (e != cudaSuccess)
+        {
+            alloc = 0;
+            n     = 0;
+        }
+        return e;
+    }
+    void release()
+    {
+        if (p) cudaFree(p);
+        p     = nullptr;
+        n     = 0;
+        alloc = 0;
+    }
+};
+
+struct PairList
+{
+    DevBuf<nbnxm_b200_sci_t>       sci, sciSorted;
+    DevBuf<int>                    sciCount, sciHistogram, sciOffset, rollingPart;
+    DevBuf<nbnxm_b200_cj_packed_t> cjPacked;
+    DevBuf<unsigned int>           imaskOuter;
+    DevBuf<nbnxm_b200_excl_t>      excl;
+    DevBuf<unsigned long long>     pairCount;
+    int                            numSci               = 0;
+    int                            naCi                 = -1;
+    bool                           haveFreshList        = false;
+    int                            rollingNumParts      = 0;
+    bool                           didPrune             = false;
+    bool                           didRollingPrune      = false;
+
+    PairlistDev dev(bool counting) const
+    {
+        PairlistDev d;
+        d.sci          = sci.p;
+        d.sciSorted    = sciSorted.p;
+        d.sciCount     = sciCount.p;
+        d.sciHistogram = sciHistogram.p;
+        d.sciOffset    = sciOffset.p;
+        d.cjPacked     = cjPacked.p;
+        d.imaskOuter   = imaskOuter.p;
+        d.excl         = excl.p;
+        d.rollingPart  = rollingPart.p;
+        d.pairCount    = counting ? pairCount.p : nullptr;
+        d.numSci       = numSci;
+        return d;
+    }
+};
+
+struct TimedRegion
+{
+    cudaEvent_t start, stop;
+    int         kind; /* 0..3 force[prune][energy], 4 prune, 5 rolling prune, 6 xq h2d, 7 f d2h, 8 pairlist h2d */
+};
+
+} // namespace
+
+struct nbnxm_b200
+{
+    int                 device = 0;
+    cudaStream_t        stream[2]    = { nullptr, nullptr };
+    bool                ownStream[2] = { false, false };
+    bool                localAndNonlocal = false;
+    nbnxm_b200_params_t params{};
+    int                 numTypes = 0;
+    int                 numSMs   = 0;
+
+    DevBuf<float4> xq, f4;
+    DevBuf<float>  f3;
+    DevBuf<int>    atomType;
+    DevBuf<float2> ljComb;
+    DevBuf<float>  shiftVec;
+    DevBuf<double> fshift, energy;
+    DevBuf<float2> nbfp, nbfpComb;
+    DevBuf<float>  coulombTab;
+    bool           shiftVecUploaded = false;
+    int            natoms = 0, natomsLocal = 0;
+
+    /* x buffer ops (one entry per grid) */
+    struct XGrid
+    {
+        int first = 0, n = 0;
+    };
+    std::vector<XGrid> xgrids;
+    DevBuf<int>        atomIndex;
+
+    PairList plist[2];
+    bool     haveWork[2] = { false, false };
+
+    double* h_fshift = nullptr; /* pinned staging, NBStagingData (gpu_types_common.h:142) */
+    double* h_energy = nullptr;
+
+    cudaEvent_t nonlocalDone = nullptr, localH2DDone = nullptr;
+
+    bool                     doTiming = false;
+    std::vector<TimedRegion> regions;
+    nbnxm_b200_timings_t     timings{};
+    bool                     pairCounting = false;
+    long long                launches     = 0;
+
+    ParamsDev   pd{};
+    AtomDataDev ad() const
+    {
+        AtomDataDev a;
+        a.xq       = xq.p;
+        a.f4       = f4.p;
+        a.atomType = atomType.p;
+        a.ljComb   = ljComb.p;
+        a.shiftVec = shiftVec.p;
+        a.fshift   = fshift.p;
+        a.energy   = energy.p;
+        a.numTypes = numTypes;
+        return a;
+    }
+};
+
+namespace
+{
+
+void fillParamsDev(nbnxm_b200* nb)
+{
+    const nbnxm_b200_params_t& s = nb->params;
+    ParamsDev&                 d = nb->pd;
+    d.epsfac = s.epsfac; d.c_rf = s.c_rf; d.two_k_rf = s.two_k_rf; d.ewald_beta = s.ewald_beta;
+    d.sh_ewald = s.sh_ewald; d.sh_lj_ewald = s.sh_lj_ewald; d.ewaldcoeff_lj = s.ewaldcoeff_lj;
+    d.rcoulomb_sq = s.rcoulomb_sq; d.rvdw_sq = s.rvdw_sq; d.rvdw_switch = s.rvdw_switch;
+    d.rlist_outer_sq = s.rlist_outer_sq; d.rlist_inner_sq = s.rlist_inner_sq;
+    d.disp_c2 = s.disp_c2; d.disp_c3 = s.disp_c3; d.disp_cpot = s.disp_cpot;
+    d.rep_c2 = s.rep_c2; d.rep_c3 = s.rep_c3; d.rep_cpot = s.rep_cpot;
+    d.sw_c3 = s.sw_c3; d.sw_c4 = s.sw_c4; d.sw_c5 = s.sw_c5;
+    d.coulomb_tab_scale = s.coulomb_tab_scale;
+    d.nbfp       = nb->nbfp.p;
+    d.nbfpComb   = nb->nbfpComb.p;
+    d.coulombTab = nb->coulombTab.p;
+}
+
+bool usesLjComb(int vdw) { return vdw == NBNXM_B200_VDW_CUT_COMB_GEOM || vdw == NBNXM_B200_VDW_CUT_COMB_LB; }
+
+/* getGpuAtomRange, src/gromacs/nbnxm/gpu_common_utils.h:72-91 */
+int atomRange(const nbnxm_b200* nb, int aloc, int* begin, int* count)
+{
+    switch (aloc)
+    {
+        case 0: *begin = 0; *count = nb->natomsLocal; return 0;
+        case 1: *begin = nb->natomsLocal; *count = nb->natoms - nb->natomsLocal; return 0;
+        case 2: *begin = 0; *count = nb->natoms; return 0;
+        default: return fail("invalid atom locality %d", aloc);
+    }
+}
+
+void beginRegion(nbnxm_b200* nb, int kind, cudaStream_t s)
+{
+    if (!nb->doTiming) return;
+    TimedRegion r;
+    cudaEventCreate(&r.start);
+    cudaEventCreate(&r.stop);
+    r.kind = kind;
+    cudaEventRecord(r.start, s);
+    nb->regions.push_back(r);
+}
+void endRegion(nbnxm_b200* nb, cudaStream_t s)
+{
+    if (!nb->doTiming) return;
+    cudaEventRecord(nb->regions.back().stop, s);
+}
+
+int collectTimings(nbnxm_b200* nb)
+{
+    for (TimedRegion& r : nb->regions)
+    {
+        CU(cudaEventSynchronize(r.stop));
+        float ms = 0;
+        CU(cudaEventElapsedTime(&ms, r.start, r.stop));
+        nbnxm_b200_timings_t& t = nb->timings;
+        switch (r.kind)
+        {
+            case 0: case 1: case 2: case 3:
+                t.force_ms[(r.kind >> 1) & 1][r.kind & 1] += ms;
+                t.force_count[(r.kind >> 1) & 1][r.kind & 1]++;
+                break;
+            case 4: t.prune_ms += ms; t.prune_count++; break;
+            case 5: t.rolling_prune_ms += ms; t.rolling_prune_count++; break;
+            case 6: t.xq_h2d_ms += ms; break;
+            case 7: t.f_d2h_ms += ms; break;
+            case 8: t.pairlist_h2d_ms += ms; break;
+        }
+        cudaEventDestroy(r.start);
+        cudaEventDestroy(r.stop);
+    }
+    nb->regions.clear();
+    return 0;
+}
+
+/* canSkipNonbondedWork, src/gromacs/nbnxm/gpu_common_utils.h:60 */
+bool canSkipNonbondedWork(const nbnxm_b200* nb, int iloc) { return iloc == 1 && nb->plist[iloc].numSci == 0; }
+
+} // namespace
+
+extern "C" {
+
+const char* nbnxm_b200_last_error(void) { return g_lastError; }
+
+int nbnxm_b200_init(nbnxm_b200_t** out, int device, const nbnxm_b200_params_t* params, int ntypes, const float* nbfp,
+                    const float* nbfp_comb, const float* coulomb_tab, int coulomb_tab_size, int local_and_nonlocal,
+                    void* local_stream, void* nonlocal_stream)
+{
+    if (!out || !params || !nbfp || ntypes <= 0) return fail("nbnxm_b200_init: null argument");
+    int ndev = 0;
+    if (cudaGetDeviceCount(&ndev) != cudaSuccess || ndev == 0)
+    {
+        return fail("nbnxm_b200_init: no CUDA device available (this library has no CPU fallback)");
+    }
+    CU(cudaSetDevice(device));
+    cudaDeviceProp prop;
+    CU(cudaGetDeviceProperties(&prop, device));
+    if (prop.major < 10)
+    {
+        return fail("nbnxm_b200_init: device %d is sm_%d%d; this library is built for sm_100a only", device, prop.major, prop.minor);
+    }
+    nbnxm_b200* nb       = new nbnxm_b200();
+    nb->device           = device;
+    nb->numSMs           = prop.multiProcessorCount;
+    nb->localAndNonlocal = local_and_nonlocal != 0;
+    nb->params           = *params;
+    nb->numTypes         = ntypes;
+    if (local_stream)
+    {
+        nb->stream[0] = static_cast<cudaStream_t>(local_stream);
+    }
+    else
+    {
+        CU(cudaStreamCreateWithFlags(&nb->stream[0], cudaStreamNonBlocking));
+        nb->ownStream[0] = true;
+    }
+    if (nb->localAndNonlocal)
+    {
+        if (nonlocal_stream)
+        {
+            nb->stream[1] = static_cast<cudaStream_t>(nonlocal_stream);
+        }
+        else
+        {
+            /* non-local work is on the critical path of the halo exchange: highest priority,
+             * as in the reference's DeviceStreamManager */
+            int lo = 0, hi = 0;
+            CU(cudaDeviceGetStreamPriorityRange(&lo, &hi));
+            CU(cudaStreamCreateWithPriority(&nb->stream[1], cudaStreamNonBlocking, hi));
+            nb->ownStream[1] = true;
+        }
+    }
+    else
+    {
+        nb->stream[1] = nb->stream[0];
+    }
+    CU(cudaEventCreateWithFlags(&nb->nonlocalDone, cudaEventDisableTiming));
+    CU(cudaEventCreateWithFlags(&nb->localH2DDone, cudaEventDisableTiming));
+    CU(cudaMallocHost(&nb->h_fshift, sizeof(double) * 3 * c_numShiftVectors));
+    CU(cudaMallocHost(&nb->h_energy, sizeof(double) * 2));
+
+    CU(nb->nbfp.reserve(size_t(ntypes) * ntypes));
+    CU(cudaMemcpyAsync(nb->nbfp.p, nbfp, sizeof(float2) * ntypes * ntypes, cudaMemcpyHostToDevice, nb->stream[0]));
+    CU(nb->nbfpComb.reserve(ntypes));
+    if (nbfp_comb)
+    {
+        CU(cudaMemcpyAsync(nb->nbfpComb.p, nbfp_comb, sizeof(float2) * ntypes, cudaMemcpyHostToDevice, nb->stream[0]));
+    }
+    else
+    {
+        CU(cudaMemsetAsync(nb->nbfpComb.p, 0, sizeof(float2) * ntypes, nb->stream[0]));
+    }
+    if (coulomb_tab && coulomb_tab_size > 0)
+    {
+        CU(nb->coulombTab.reserve(coulomb_tab_size));
+        CU(cudaMemcpyAsync(nb->coulombTab.p, coulomb_tab, sizeof(float) * coulomb_tab_size, cudaMemcpyHostToDevice, nb->stream[0]));
+    }
+    /* initAtomdataFirst, nbnxm_gpu_data_mgmt.cpp:322 */
+    CU(nb->shiftVec.reserve(3 * c_numShiftVectors));
+    CU(nb->fshift.reserve(3 * c_numShiftVectors));
+    CU(nb->energy.reserve(2));
+    CU(cudaMemsetAsync(nb->fshift.p, 0, sizeof(double) * 3 * c_numShiftVectors, nb->stream[0]));
+    CU(cudaMemsetAsync(nb->energy.p, 0, sizeof(double) * 2, nb->stream[0]));
+    for (int l = 0; l < 2; l++)
+    {
+        CU(nb->plist[l].pairCount.reserve(1));
+        CU(cudaMemsetAsync(nb->plist[l].pairCount.p, 0, sizeof(unsigned long long), nb->stream[0]));
+    }
+    CU(cudaStreamSynchronize(nb->stream[0]));
+    fillParamsDev(nb);
+    *out = nb;
+    return 0;
+}
+
+int nbnxm_b200_free(nbnxm_b200_t* nb)
+{
+    if (!nb) return 0;
+    cudaSetDevice(nb->device);
+    cudaDeviceSynchronize();
+    collectTimings(nb);
+    nb->xq.release(); nb->f4.release(); nb->f3.release(); nb->atomType.release(); nb->ljComb.release();
+    nb->shiftVec.release(); nb->fshift.release(); nb->energy.release(); nb->nbfp.release();
+    nb->nbfpComb.release(); nb->coulombTab.release(); nb->atomIndex.release();
+    for (PairList& pl : nb->plist)
+    {
+        pl.sci.release(); pl.sciSorted.release(); pl.sciCount.release(); pl.sciHistogram.release();
+        pl.sciOffset.release(); pl.rollingPart.release(); pl.cjPacked.release(); pl.imaskOuter.release();
+        pl.excl.release(); pl.pairCount.release();
+    }
+    if (nb->h_fshift) cudaFreeHost(nb->h_fshift);
+    if (nb->h_energy) cudaFreeHost(nb->h_energy);
+    if (nb->nonlocalDone) cudaEventDestroy(nb->nonlocalDone);
+    if (nb->localH2DDone) cudaEventDestroy(nb->localH2DDone);
+    if (nb->ownStream[0]) cudaStreamDestroy(nb->stream[0]);
+    if (nb->ownStream[1]) cudaStreamDestroy(nb->stream[1]);
+    delete nb;
+    return 0;
+}
+
+int nbnxm_b200_update_params(nbnxm_b200_t* nb, const nbnxm_b200_params_t* params, const float* coulomb_tab, int coulomb_tab_size)
+{
+    if (!nb || !params) return fail("nbnxm_b200_update_params: null argument");
+    CU(cudaSetDevice(nb->device));
+    if (params->elec_type != nb->params.elec_type && !(params->elec_type >= 2 && nb->params.elec_type >= 2))
+    {
+        return fail("nbnxm_b200_update_params: the electrostatics family cannot change");
+    }
+    nb->params = *params;
+    if (coulomb_tab && coulomb_tab_size > 0)
+    {
+        CU(cudaStreamSynchronize(nb->stream[0]));
+        CU(cudaStreamSynchronize(nb->stream[1]));
+        CU(nb->coulombTab.reserve(coulomb_tab_size));
+        CU(cudaMemcpyAsync(nb->coulombTab.p, coulomb_tab, sizeof(float) * coulomb_tab_size, cudaMemcpyHostToDevice, nb->stream[0]));
+    }
+    fillParamsDev(nb);
+    return 0;
+}
+
+int nbnxm_b200_init_pairlist(nbnxm_b200_t* nb, int iloc, const nbnxm_b200_sci_t* sci, int nsci,
+                             const nbnxm_b200_cj_packed_t* cj_packed, int ncj_packed, const nbnxm_b200_excl_t* excl,
+                             int nexcl, int na_ci)
+{
+    if (!nb || iloc < 0 || iloc > 1) return fail("nbnxm_b200_init_pairlist: bad argument");
+    if (nsci < 0 || ncj_packed < 0 || nexcl < 0) return fail("nbnxm_b200_init_pairlist: negative size");
+    if (na_ci != c_clusterSize) return fail("nbnxm_b200_init_pairlist: cluster size %d unsupported (need 8)", na_ci);
+    CU(cudaSetDevice(nb->device));
+    PairList&    pl = nb->plist[iloc];
+    cudaStream_t st = nb->stream[iloc];
+    if (pl.naCi >= 0 && pl.naCi != na_ci)
+    {
+        return fail("In init_plist: the #atoms per cluster has changed (from %d to %d)", pl.naCi, na_ci);
+    }
+    pl.naCi = na_ci;
+    /* buffers may still be in use by the previous list's kernels */
+    CU(cudaStreamSynchronize(st));
+    beginRegion(nb, 8, st);
+    pl.numSci = nsci;
+    CU(pl.sci.reserve(nsci));
+    CU(pl.sciSorted.reserve(nsci));
+    CU(pl.sciCount.reserve(nsci));
+    CU(pl.rollingPart.reserve(nsci));
+    CU(pl.sciHistogram.reserve(c_sciHistogramSize + 1));
+    CU(pl.sciOffset.reserve(c_sciHistogramSize));
+    CU(pl.cjPacked.reserve(ncj_packed));
+    CU(pl.imaskOuter.reserve(size_t(ncj_packed) * 2));
+    CU(pl.excl.reserve(nexcl > 0 ? nexcl : 1));
+    if (nsci > 0)
+    {
+        CU(cudaMemcpyAsync(pl.sci.p, sci, sizeof(*sci) * nsci, cudaMemcpyHostToDevice, st));
+        CU(cudaMemcpyAsync(pl.sciSorted.p, sci, sizeof(*sci) * nsci, cudaMemcpyHostToDevice, st));
+        CU(cudaMemsetAsync(pl.rollingPart.p, 0, sizeof(int) * nsci, st));
+        CU(cudaMemsetAsync(pl.sciCount.p, 0, sizeof(int) * nsci, st));
+    }
+    CU(cudaMemsetAsync(pl.sciHistogram.p, 0, sizeof(int) * (c_sciHistogramSize + 1), st));
+    if (ncj_packed > 0)
+    {
+        CU(cudaMemcpyAsync(pl.cjPacked.p, cj_packed, sizeof(*cj_packed) * ncj_packed, cudaMemcpyHostToDevice, st));
+        CU(cudaMemsetAsync(pl.imaskOuter.p, 0, sizeof(unsigned int) * 2 * ncj_packed, st));
+    }
+    if (nexcl > 0)
+    {
+        CU(cudaMemcpyAsync(pl.excl.p, excl, sizeof(*excl) * nexcl, cudaMemcpyHostToDevice, st));
+    }
+    endRegion(nb, st);
+    pl.haveFreshList   = true;
+    pl.didPrune        = false;
+    pl.didRollingPrune = false;
+    pl.rollingNumParts = 0;
+    return 0;
+}
+
+int nbnxm_b200_init_atomdata(nbnxm_b200_t* nb, int natoms, int natoms_local, const int* atom_type, const float* lj_comb)
+{
+    if (!nb || natoms < 0 || natoms_local < 0 || natoms_local > natoms) return fail("nbnxm_b200_init_atomdata: bad argument");
+    if (natoms % (c_clusterSize * c_superClusterSize) != 0 && natoms % c_clusterSize != 0)
+    {
+        return fail("nbnxm_b200_init_atomdata: natoms (%d) must be a multiple of the cluster size", natoms);
+    }
+    const bool comb = usesLjComb(nb->params.vdw_type);
+    if (comb && !lj_comb) return fail("nbnxm_b200_init_atomdata: this VdW flavor needs lj_comb");
+    if (!comb && !atom_type) return fail("nbnxm_b200_init_atomdata: this VdW flavor needs atom types");
+    CU(cudaSetDevice(nb->device));
+    cudaStream_t st = nb->stream[0];
+    const bool   realloc = size_t(natoms) > nb->xq.alloc;
+    if (realloc)
+    {
+        CU(cudaStreamSynchronize(nb->stream[0]));
+        CU(cudaStreamSynchronize(nb->stream[1]));
+    }
+    CU(nb->xq.reserve(natoms));
+    CU(nb->f4.reserve(natoms));
+    CU(nb->f3.reserve(size_t(natoms) * 3));
+    CU(nb->atomType.reserve(natoms));
+    CU(nb->ljComb.reserve(natoms));
+    if (realloc && natoms > 0)
+    {
+        CU(cudaMemsetAsync(nb->f4.p, 0, sizeof(float4) * nb->f4.alloc, st));
+        CU(cudaMemsetAsync(nb->xq.p, 0, sizeof(float4) * nb->xq.alloc, st));
+    }
+    nb->natoms      = natoms;
+    nb->natomsLocal = natoms_local;
+    if (natoms > 0)
+    {
+        if (atom_type) CU(cudaMemcpyAsync(nb->atomType.p, atom_type, sizeof(int) * natoms, cudaMemcpyHostToDevice, st));
+        if (lj_comb) CU(cudaMemcpyAsync(nb->ljComb.p, lj_comb, sizeof(float2) * natoms, cudaMemcpyHostToDevice, st));
+    }
+    return 0;
+}
+
+int nbnxm_b200_upload_shiftvec(nbnxm_b200_t* nb, const float* shift_vec, int dynamic_box)
+{
+    if (!nb || !shift_vec) return fail("nbnxm_b200_upload_shiftvec: null argument");
+    CU(cudaSetDevice(nb->device));
+    /* only if we have a dynamic box or it was never uploaded (nbnxm_gpu_data_mgmt.cpp:719-737) */
+    if (dynamic_box || !nb->shiftVecUploaded)
+    {
+        CU(cudaMemcpyAsync(nb->shiftVec.p, shift_vec, sizeof(float) * 3 * c_numShiftVectors, cudaMemcpyHostToDevice, nb->stream[0]));
+        nb->shiftVecUploaded = true;
+    }
+    return 0;
+}
+
+int nbnxm_b200_copy_xq_to_gpu(nbnxm_b200_t* nb, int aloc, const float* xq)
+{
+    if (!nb || !xq) return fail("nbnxm_b200_copy_xq_to_gpu: null argument");
+    if (aloc != 0 && aloc != 1) return fail("nbnxm_b200_copy_xq_to_gpu: locality must be Local or NonLocal");
+    CU(cudaSetDevice(nb->device));
+    int begin, count;
+    if (atomRange(nb, aloc, &begin, &count)) return 1;
+    cudaStream_t st = nb->stream[aloc];
+    /* skip the non-local copy if there is no non-local work (nbnxm_gpu_data_mgmt.cpp:1498-1516) */
+    if (aloc == 1 && !nb->haveWork[1] && nb->plist[1].numSci == 0)
+    {
+        nb->plist[1].haveFreshList = false;
+        return 0;
+    }
+    beginRegion(nb, 6, st);
+    if (count > 0)
+    {
+        CU(cudaMemcpyAsync(nb->xq.p + begin, xq + 4 * size_t(begin), sizeof(float4) * count, cudaMemcpyHostToDevice, st));
+    }
+    endRegion(nb, st);
+    if (aloc == 0) nbnxm_b200_insert_nonlocal_dependency(nb, 0);
+    return 0;
+}
+
+int nbnxm_b200_insert_nonlocal_dependency(nbnxm_b200_t* nb, int iloc)
+{
+    if (!nb) return fail("null handle");
+    /* nbnxmInsertNonlocalGpuDependency, nbnxm_gpu_data_mgmt.cpp:1464-1487 */
+    if (nb->localAndNonlocal)
+    {
+        if (iloc == 0)
+        {
+            CU(cudaEventRecord(nb->localH2DDone, nb->stream[0]));
+        }
+        else
+        {
+            CU(cudaStreamWaitEvent(nb->stream[1], nb->localH2DDone, 0));
+        }
+    }
+    return 0;
+}
+
+int nbnxm_b200_init_x_to_nbat_x(nbnxm_b200_t* nb, int grid, int ngrids, const int* atom_index, int natoms_nbat,
+                                const int* /*cxy_na*/, const int* /*cxy_ind*/, int /*ncolumns*/, int /*num_atoms_per_cell*/,
+                                int atom_offset)
+{
+    if (!nb || !atom_index || grid < 0 || grid >= ngrids) return fail("nbnxm_b200_init_x_to_nbat_x: bad argument");
+    CU(cudaSetDevice(nb->device));
+    if (grid == 0)
+    {
+        nb->xgrids.assign(ngrids, nbnxm_b200::XGrid());
+        if (size_t(nb->natoms) > nb->atomIndex.alloc)
+        {
+            CU(cudaStreamSynchronize(nb->stream[0]));
+            CU(cudaStreamSynchronize(nb->stream[1]));
+        }
+        CU(nb->atomIndex.reserve(nb->natoms));
+    }
+    if (atom_offset < 0 || atom_offset + natoms_nbat > nb->natoms)
+    {
+        return fail("nbnxm_b200_init_x_to_nbat_x: grid range [%d, %d) outside the %d nbat atoms", atom_offset, atom_offset + natoms_nbat, nb->natoms);
+    }
+    nb->xgrids[grid].first = atom_offset;
+    nb->xgrids[grid].n     = natoms_nbat;
+    /* the reference launches one thread per cell slot from the column tables; with the atom-index
+     * array already holding -1 for filler slots one thread per nbat slot is equivalent */
+    CU(cudaMemcpyAsync(nb->atomIndex.p + atom_offset, atom_index, sizeof(int) * natoms_nbat, cudaMemcpyHostToDevice, nb->stream[0]));
+    return 0;
+}
+
+int nbnxm_b200_x_to_nbat_x(nbnxm_b200_t* nb, const float* d_x, void* x_ready_event, int aloc)
+{
+    if (!nb || !d_x) return fail("nbnxm_b200_x_to_nbat_x: null argument");
+    if (nb->xgrids.empty()) return fail("nbnxm_b200_x_to_nbat_x: call nbnxm_b200_init_x_to_nbat_x first");
+    CU(cudaSetDevice(nb->device));
+    cudaStream_t st = nb->stream[aloc == 1 ? 1 : 0];
+    if (x_ready_event) CU(cudaStreamWaitEvent(st, static_cast<cudaEvent_t>(x_ready_event), 0));
+    /* grid 0 holds the local atoms, grids 1.. the non-local zones (nbnxm_gpu_buffer_ops.cpp:59-92) */
+    const int g0 = (aloc == 1) ? 1 : 0;
+    const int g1 = (aloc == 0) ? 1 : int(nb->xgrids.size());
+    for (int g = g0; g < g1; g++)
+    {
+        launch_x_to_nbat_x(nb->xq.p, d_x, nb->atomIndex.p, nb->xgrids[g].first, nb->xgrids[g].n, st);
+        nb->launches++;
+    }
+    CU(cudaGetLastError());
+    if (aloc == 0) nbnxm_b200_insert_nonlocal_dependency(nb, 0);
+    return 0;
+}
+
+int nbnxm_b200_launch_kernel_pruneonly(nbnxm_b200_t* nb, int iloc, int num_parts)
+{
+    if (!nb || iloc < 0 || iloc > 1 || num_parts < 1) return fail("nbnxm_b200_launch_kernel_pruneonly: bad argument");
+    CU(cudaSetDevice(nb->device));
+    PairList&    pl = nb->plist[iloc];
+    cudaStream_t st = nb->stream[iloc];
+    if (pl.haveFreshList)
+    {
+        if (num_parts != 1) return fail("With first pruning we expect 1 part");
+        pl.rollingNumParts = 0;
+    }
+    else
+    {
+        if (pl.rollingNumParts == 0)
+        {
+            pl.rollingNumParts = num_parts;
+        }
+        else if (num_parts != pl.rollingNumParts)
+        {
+            return fail("It is not allowed to change numParts in between list generation steps");
+        }
+    }
+    const int numSciInPartMax = (pl.numSci + num_parts - 1) / num_parts;
+    if (numSciInPartMax <= 0)
+    {
+        pl.haveFreshList = false;
+        return 0;
+    }
+    beginRegion(nb, pl.haveFreshList ? 4 : 5, st);
+    launch_prune(pl.haveFreshList, nb->ad(), nb->pd, pl.dev(false), num_parts, st);
+    nb->launches++;
+    if (pl.haveFreshList)
+    {
+        launch_sci_sort(pl.dev(false), st);
+        nb->launches += 2;
+        pl.haveFreshList = false;
+        pl.didPrune      = true;
+    }
+    else
+    {
+        pl.didRollingPrune = true;
+    }
+    endRegion(nb, st);
+    CU(cudaGetLastError());
+    return 0;
+}
+
+int nbnxm_b200_launch_kernel(nbnxm_b200_t* nb, int iloc, int compute_energy, int compute_virial)
+{
+    if (!nb || iloc < 0 || iloc > 1) return fail("nbnxm_b200_launch_kernel: bad argument");
+    CU(cudaSetDevice(nb->device));
+    PairList&    pl = nb->plist[iloc];
+    cudaStream_t st = nb->stream[iloc];
+    if (canSkipNonbondedWork(nb, iloc))
+    {
+        pl.haveFreshList = false;
+        return 0;
+    }
+    if (nb->params.use_dynamic_pruning && pl.haveFreshList)
+    {
+        if (nbnxm_b200_launch_kernel_pruneonly(nb, iloc, 1)) return 1;
+    }
+    if (pl.numSci == 0)
+    {
+        return 0;
+    }
+    if (!nb->shiftVecUploaded) return fail("nbnxm_b200_launch_kernel: shift vectors were never uploaded");
+    const bool     doPrune = pl.haveFreshList && !pl.didPrune;
+    ForceKernelPtr kernel  = select_force_kernel(nb->params.elec_type, nb->params.vdw_type, compute_energy != 0, doPrune);
+    if (!kernel)
+    {
+        return fail("nbnxm_b200_launch_kernel: no kernel for elec_type %d vdw_type %d", nb->params.elec_type, nb->params.vdw_type);
+    }
+    beginRegion(nb, (doPrune ? 2 : 0) + (compute_energy ? 1 : 0), st);
+    const int blocks = (pl.numSci + c_forceWarpsPerBlock - 1) / c_forceWarpsPerBlock;
+    kernel<<<blocks, c_forceThreads, 0, st>>>(nb->ad(), nb->pd, pl.dev(nb->pairCounting), compute_virial != 0);
+    nb->launches++;
+    if (doPrune)
+    {
+        launch_sci_sort(pl.dev(false), st);
+        nb->launches += 2;
+        pl.didPrune      = true;
+        pl.haveFreshList = false;
+    }
+    endRegion(nb, st);
+    CU(cudaGetLastError());
+    return 0;
+}
+
+int nbnxm_b200_launch_cpyback(nbnxm_b200_t* nb, int aloc, float* f, int compute_energy, int compute_virial, int use_gpu_f_buffer_ops)
+{
+    if (!nb) return fail("null handle");
+    if (aloc != 0 && aloc != 1) return fail("nbnxm_b200_launch_cpyback: locality must be Local or NonLocal");
+    if (!use_gpu_f_buffer_ops && !f) return fail("nbnxm_b200_launch_cpyback: null force buffer");
+    CU(cudaSetDevice(nb->device));
+    const int    iloc = aloc;
+    cudaStream_t st   = nb->stream[iloc];
+    /* don't launch non-local copy-back if there was no non-local work to do */
+    if (aloc == 1 && !nb->haveWork[1] && nb->plist[1].numSci == 0)
+    {
+        return 0;
+    }
+    int begin, count;
+    if (atomRange(nb, aloc, &begin, &count)) return 1;
+    /* the non-local kernel also writes forces of local atoms: the local copy-back has to wait for it
+     * (nbnxm_gpu_data_mgmt.cpp:1313-1346) */
+    if (aloc == 0 && nb->localAndNonlocal && (nb->haveWork[1] || nb->plist[1].numSci > 0))
+    {
+        CU(cudaStreamWaitEvent(st, nb->nonlocalDone, 0));
+    }
+    beginRegion(nb, 7, st);
+    launch_f4_to_f3(nb->f4.p, nb->f3.p, begin, count, st);
+    nb->launches++;
+    if (!use_gpu_f_buffer_ops && count > 0)
+    {
+        CU(cudaMemcpyAsync(f + 3 * size_t(begin), nb->f3.p + 3 * size_t(begin), sizeof(float) * 3 * count, cudaMemcpyDeviceToHost, st));
+    }
+    if (aloc == 1 && nb->localAndNonlocal)
+    {
+        CU(cudaEventRecord(nb->nonlocalDone, st));
+    }
+    if (aloc == 0)
+    {
+        if (compute_virial)
+        {
+            CU(cudaMemcpyAsync(nb->h_fshift, nb->fshift.p, sizeof(double) * 3 * c_numShiftVectors, cudaMemcpyDeviceToHost, st));
+        }
+        if (compute_energy)
+        {
+            CU(cudaMemcpyAsync(nb->h_energy, nb->energy.p, sizeof(double) * 2, cudaMemcpyDeviceToHost, st));
+        }
+    }
+    endRegion(nb, st);
+    CU(cudaGetLastError());
+    return 0;
+}
+
+static int finishTask(nbnxm_b200_t* nb, int aloc, int compute_energy, int compute_virial, float* e_lj, float* e_el, float* fshift)
+{
+    /* gpu_reduce_staged_outputs, gpu_common.h:141-171: only the local stream carries energies */
+    if (aloc == 0)
+    {
+        if (compute_energy)
+        {
+            if (e_lj) *e_lj += static_cast<float>(nb->h_energy[0]);
+            if (e_el) *e_el += static_cast<float>(nb->h_energy[1]);
+        }
+        if (compute_virial && fshift)
+        {
+            for (int i = 0; i < 3 * c_numShiftVectors; i++) fshift[i] += static_cast<float>(nb->h_fshift[i]);
+        }
+    }
+    PairList& pl       = nb->plist[aloc];
+    pl.haveFreshList   = false;
+    pl.didPrune        = false;
+    pl.didRollingPrune = false;
+    return 0;
+}
+
+int nbnxm_b200_try_finish_task(nbnxm_b200_t* nb, int aloc, int compute_energy, int compute_virial, float* e_lj, float* e_el,
+                               float* fshift, int* done)
+{
+    if (!nb || !done) return fail("nbnxm_b200_try_finish_task: null argument");
+    if (aloc != 0 && aloc != 1) return fail("nbnxm_b200_try_finish_task: locality must be Local or NonLocal");
+    CU(cudaSetDevice(nb->device));
+    cudaError_t q = cudaStreamQuery(nb->stream[aloc]);
+    if (q == cudaErrorNotReady)
+    {
+        *done = 0;
+        return 0;
+    }
+    CU(q);
+    *done = 1;
+    return finishTask(nb, aloc, compute_energy, compute_virial, e_lj, e_el, fshift);
+}
+
+int nbnxm_b200_wait_finish_task(nbnxm_b200_t* nb, int aloc, int compute_energy, int compute_virial, float* e_lj, float* e_el, float* fshift)
+{
+    if (!nb) return fail("null handle");
+    if (aloc != 0 && aloc != 1) return fail("nbnxm_b200_wait_finish_task: locality must be Local or NonLocal");
+    CU(cudaSetDevice(nb->device));
+    CU(cudaStreamSynchronize(nb->stream[aloc]));
+    return finishTask(nb, aloc, compute_energy, compute_virial, e_lj, e_el, fshift);
+}
+
+int nbnxm_b200_clear_outputs(nbnxm_b200_t* nb, int compute_virial)
+{
+    if (!nb) return fail("null handle");
+    CU(cudaSetDevice(nb->device));
+    cudaStream_t st = nb->stream[0];
+    if (nb->natoms > 0) CU(cudaMemsetAsync(nb->f4.p, 0, sizeof(float4) * nb->natoms, st));
+    if (compute_virial)
+    {
+        CU(cudaMemsetAsync(nb->fshift.p, 0, sizeof(double) * 3 * c_numShiftVectors, st));
+        CU(cudaMemsetAsync(nb->energy.p, 0, sizeof(double) * 2, st));
+    }
+    return 0;
+}
+
+int nbnxm_b200_setup_short_range_work(nbnxm_b200_t* nb, int iloc, int have_bonded_work)
+{
+    if (!nb || iloc < 0 || iloc > 1) return fail("bad argument");
+    nb->haveWork[iloc] = (nb->plist[iloc].numSci > 0) || have_bonded_work;
+    return 0;
+}
+int nbnxm_b200_have_short_range_work(const nbnxm_b200_t* nb, int iloc) { return (nb && iloc >= 0 && iloc <= 1) ? nb->haveWork[iloc] : 0; }
+
+int nbnxm_b200_min_ci_balanced(const nbnxm_b200_t* nb)
+{
+    /* enough sci entries for two full waves of the one-warp-per-entry force kernel at 16 warps/SM
+     * (the reference uses 61 x #SM 64-thread blocks, cuda/nbnxm_cuda_data_mgmt.cu:95-130) */
+    return nb ? 32 * nb->numSMs : 0;
+}
+int nbnxm_b200_is_kernel_ewald_analytical(const nbnxm_b200_t* nb)
+{
+    return nb && (nb->params.elec_type == NBNXM_B200_ELEC_EWALD_ANA || nb->params.elec_type == NBNXM_B200_ELEC_EWALD_ANA_TWIN);
+}
+
+int nbnxm_b200_set_timing(nbnxm_b200_t* nb, int enable)
+{
+    if (!nb) return fail("null handle");
+    nb->doTiming = enable != 0;
+    return 0;
+}
+int nbnxm_b200_get_timings(nbnxm_b200_t* nb, nbnxm_b200_timings_t* out)
+{
+    if (!nb || !out) return fail("null argument");
+    CU(cudaSetDevice(nb->device));
+    if (collectTimings(nb)) return 1;
+    *out = nb->timings;
+    return 0;
+}
+int nbnxm_b200_reset_timings(nbnxm_b200_t* nb)
+{
+    if (!nb) return fail("null handle");
+    CU(cudaSetDevice(nb->device));
+    if (collectTimings(nb)) return 1;
+    memset(&nb->timings, 0, sizeof(nb->timings));
+    return 0;
+}
+
+int nbnxm_b200_get_device_buffers(nbnxm_b200_t* nb, float** d_xq, float** d_f, int* natoms)
+{
+    if (!nb) return fail("null handle");
+    if (d_xq) *d_xq = reinterpret_cast<float*>(nb->xq.p);
+    if (d_f) *d_f = nb->f3.p;
+    if (natoms) *natoms = nb->natoms;
+    return 0;
+}
+int nbnxm_b200_get_streams(nbnxm_b200_t* nb, void** local_stream, void** nonlocal_stream)
+{
+    if (!nb) return fail("null handle");
+    if (local_stream) *local_stream = nb->stream[0];
+    if (nonlocal_stream) *nonlocal_stream = nb->stream[1];
+    return 0;
+}
+
+int nbnxm_b200_download_pairlist(nbnxm_b200_t* nb, int iloc, nbnxm_b200_cj_packed_t* cj_packed, unsigned int* imask_outer,
+                                 nbnxm_b200_sci_t* sci_sorted, int* sci_count, int* rolling_part)
+{
+    if (!nb || iloc < 0 || iloc > 1) return fail("bad argument");
+    CU(cudaSetDevice(nb->device));
+    PairList& pl = nb->plist[iloc];
+    CU(cudaStreamSynchronize(nb->stream[iloc]));
+    if (cj_packed && pl.cjPacked.n) CU(cudaMemcpy(cj_packed, pl.cjPacked.p, sizeof(*cj_packed) * pl.cjPacked.n, cudaMemcpyDeviceToHost));
+    if (imask_outer && pl.imaskOuter.n) CU(cudaMemcpy(imask_outer, pl.imaskOuter.p, sizeof(unsigned) * pl.imaskOuter.n, cudaMemcpyDeviceToHost));
+    if (sci_sorted && pl.numSci) CU(cudaMemcpy(sci_sorted, pl.sciSorted.p, sizeof(*sci_sorted) * pl.numSci, cudaMemcpyDeviceToHost));
+    if (sci_count && pl.numSci) CU(cudaMemcpy(sci_count, pl.sciCount.p, sizeof(int) * pl.numSci, cudaMemcpyDeviceToHost));
+    if (rolling_part && pl.numSci) CU(cudaMemcpy(rolling_part, pl.rollingPart.p, sizeof(int) * pl.numSci, cudaMemcpyDeviceToHost));
+    return 0;
+}
+
+int nbnxm_b200_set_pair_counting(nbnxm_b200_t* nb, int enable)
+{
+    if (!nb) return fail("null handle");
+    CU(cudaSetDevice(nb->device));
+    nb->pairCounting = enable != 0;
+    for (int l = 0; l < 2; l++) CU(cudaMemsetAsync(nb->plist[l].pairCount.p, 0, sizeof(unsigned long long), nb->stream[l]));
+    return 0;
+}
+int nbnxm_b200_get_pair_count(nbnxm_b200_t* nb, int iloc, long long* npairs)
+{
+    if (!nb || !npairs || iloc < 0 || iloc > 1) return fail("bad argument");
+    CU(cudaSetDevice(nb->device));
+    CU(cudaStreamSynchronize(nb->stream[iloc]));
+    unsigned long long v = 0;
+    CU(cudaMemcpy(&v, nb->plist[iloc].pairCount.p, sizeof(v), cudaMemcpyDeviceToHost));
+    CU(cudaMemset(nb->plist[iloc].pairCount.p, 0, sizeof(v)));
+    *npairs = static_cast<long long>(v);
+    return 0;
+}
+long long nbnxm_b200_launch_count(const nbnxm_b200_t* nb) { return nb ? nb->launches : 0; }
+
+int nbnxm_b200_pack_xq(nbnxm_b200_t* nb, const int* d_index, int n, const float* shift3, float* d_send, void* stream)
+{
+    if (!nb || (n > 0 && (!d_index || !d_send || !shift3))) return fail("nbnxm_b200_pack_xq: null argument");
+    CU(cudaSetDevice(nb->device));
+    launch_pack_xq(nb->xq.p, d_index, n, shift3, reinterpret_cast<float4*>(d_send), stream ? static_cast<cudaStream_t>(stream) : nb->stream[1]);
+    nb->launches++;
+    CU(cudaGetLastError());
+    return 0;
+}
+int nbnxm_b200_unpack_xq(nbnxm_b200_t* nb, int first, int n, const float* d_recv, void* stream)
+{
+    if (!nb || first < 0 || first + n > nb->natoms) return fail("nbnxm_b200_unpack_xq: range outside atom data");
+    CU(cudaSetDevice(nb->device));
+    launch_copy4(reinterpret_cast<const float4*>(d_recv), nb->xq.p + first, n, stream ? static_cast<cudaStream_t>(stream) : nb->stream[1]);
+    nb->launches++;
+    CU(cudaGetLastError());
+    return 0;
+}
+int nbnxm_b200_pack_f(nbnxm_b200_t* nb, int first, int n, float* d_send, void* stream)
+{
+    if (!nb || first < 0 || first + n > nb->natoms) return fail("nbnxm_b200_pack_f: range outside atom data");
+    CU(cudaSetDevice(nb->device));
+    launch_copy4(nb->f4.p + first, reinterpret_cast<float4*>(d_send), n, stream ? static_cast<cudaStream_t>(stream) : nb->stream[1]);
+    nb->launches++;
+    CU(cudaGetLastError());
+    return 0;
+}
+int nbnxm_b200_unpack_add_f(nbnxm_b200_t* nb, const int* d_index, int n, const float* d_recv, void* stream)
+{
+    if (!nb || (n > 0 && (!d_index || !d_recv))) return fail("nbnxm_b200_unpack_add_f: null argument");
+    CU(cudaSetDevice(nb->device));
+    launch_unpack_add_f(nb->f4.p, d_index, n, reinterpret_cast<const float4*>(d_recv), stream ? static_cast<cudaStream_t>(stream) : nb->stream[0]);
+    nb->launches++;
+    CU(cudaGetLastError());
+    return 0;
+}
+
+} // extern "C"

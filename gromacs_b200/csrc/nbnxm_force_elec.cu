@@ -1,0 +1,40 @@
+/* Instantiates the force kernels of one electrostatics type (compile with -DNBNXM_ELEC=<0..5>);
+ * the reference builds the same flavor matrix with macros in
+ * src/gromacs/nbnxm/cuda/nbnxm_cuda_kernels.cuh and looks kernels up through four function-pointer
+ * tables (src/gromacs/nbnxm/cuda/nbnxm_cuda.cu:169-440). */
+#include "nbnxm_force_kernel.cuh"
+
+#ifndef NBNXM_ELEC
+#    error "compile with -DNBNXM_ELEC=<electrostatics type>"
+#endif
+
+namespace nbb
+{
+
+template<int VDW>
+static ForceKernelPtr pick(bool energy, bool prune)
+{
+    if (energy)
+    {
+        return prune ? nbnxm_force_kernel<NBNXM_ELEC, VDW, true, true> : nbnxm_force_kernel<NBNXM_ELEC, VDW, true, false>;
+    }
+    return prune ? nbnxm_force_kernel<NBNXM_ELEC, VDW, false, true> : nbnxm_force_kernel<NBNXM_ELEC, VDW, false, false>;
+}
+
+template<>
+ForceKernelPtr select_force_kernel_elec<NBNXM_ELEC>(int vdw, bool energy, bool prune)
+{
+    switch (vdw)
+    {
+        case NBNXM_B200_VDW_CUT: return pick<NBNXM_B200_VDW_CUT>(energy, prune);
+        case NBNXM_B200_VDW_CUT_COMB_GEOM: return pick<NBNXM_B200_VDW_CUT_COMB_GEOM>(energy, prune);
+        case NBNXM_B200_VDW_CUT_COMB_LB: return pick<NBNXM_B200_VDW_CUT_COMB_LB>(energy, prune);
+        case NBNXM_B200_VDW_FSWITCH: return pick<NBNXM_B200_VDW_FSWITCH>(energy, prune);
+        case NBNXM_B200_VDW_PSWITCH: return pick<NBNXM_B200_VDW_PSWITCH>(energy, prune);
+        case NBNXM_B200_VDW_EWALD_GEOM: return pick<NBNXM_B200_VDW_EWALD_GEOM>(energy, prune);
+        case NBNXM_B200_VDW_EWALD_LB: return pick<NBNXM_B200_VDW_EWALD_LB>(energy, prune);
+        default: return nullptr;
+    }
+}
+
+} // namespace nbb

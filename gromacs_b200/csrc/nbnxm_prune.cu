@@ -1,0 +1,227 @@
+/* Pair-list pruning and sci sorting kernels of the nbnxm_b200 path.
+ *
+ * prune kernel  : replaces nbnxm_kernel_prune_cuda<haveFreshList>
+ *                 (src/gromacs/nbnxm/cuda/nbnxm_cuda_kernel_pruneonly.cuh:109-346)
+ * histogram scan: replaces cub::DeviceScan::ExclusiveSum (cuda/nbnxm_cuda_data_mgmt.cu:135-165)
+ * bucket sort   : replaces nbnxmKernelBucketSciSort (cuda/nbnxm_cuda_kernel_sci_sort.cuh:67-90)
+ *
+ * Mask semantics are the reference's, bit for bit: for every (cjPacked, half w, j-cluster jm,
+ * i-cluster ci) a bit survives the outer prune iff any of its 8 x 4 atom pairs has
+ * r2 < rlistOuter^2 and is set in the inner mask iff any pair has r2 < rlistInner^2, with
+ * xi = float(x_i + shift) and r2 = fma(dz,dz, fma(dy,dy, dx*dx)).
+ *
+ * Work decomposition: one warp per sci entry; lane = il + 8*jl holds the 8 shifted i-atoms
+ * (il of every i-cluster) in registers and tests j-atoms jl (half 0) and jl+4 (half 1), so both
+ * halves are pruned by the same warp with two warp votes per cluster pair.
+ */
+#include "nbnxm_device.cuh"
+
+namespace nbb
+{
+
+constexpr int c_pruneWarpsPerBlock = 4;
+
+template<bool FRESH>
+__global__ void __launch_bounds__(c_pruneWarpsPerBlock * 32)
+        nbnxm_prune_kernel(const AtomDataDev ad, const ParamsDev p, const PairlistDev pl, const int numParts)
+{
+    constexpr unsigned c_full = 0xffffffffu;
+    const int          lane   = threadIdx.x & 31;
+    const int          il     = lane & 7;
+    const int          jl     = lane >> 3;
+    const int          unit   = blockIdx.x * c_pruneWarpsPerBlock + (threadIdx.x >> 5);
+
+    const int numUnitsMax = (pl.numSci + numParts - 1) / numParts;
+    if (unit >= numUnitsMax)
+    {
+        return;
+    }
+    /* rolling part index lives on the device, one copy per work unit, so consecutive launches need
+     * no host bookkeeping (same idea as pruneonly.cuh:123-131) */
+    const int part = pl.rollingPart[unit];
+    __syncwarp();
+    if (lane == 0)
+    {
+        pl.rollingPart[unit] = (part + 1) % numParts;
+    }
+    const int numSciInPart = (pl.numSci - part + numParts - 1) / numParts;
+    if (unit >= numSciInPart)
+    {
+        return;
+    }
+    const int              sciIdx = unit * numParts + part;
+    const nbnxm_b200_sci_t s      = FRESH ? pl.sci[sciIdx] : pl.sciSorted[sciIdx];
+
+    const float shx = ad.shiftVec[3 * s.shift], shy = ad.shiftVec[3 * s.shift + 1], shz = ad.shiftVec[3 * s.shift + 2];
+    float       xi[c_superClusterSize], yi[c_superClusterSize], zi[c_superClusterSize];
+#pragma unroll
+    for (int ci = 0; ci < c_superClusterSize; ci++)
+    {
+        const float4 v = ad.xq[(s.sci * c_superClusterSize + ci) * c_clusterSize + il];
+        xi[ci]         = __fadd_rn(v.x, shx);
+        yi[ci]         = __fadd_rn(v.y, shy);
+        zi[ci]         = __fadd_rn(v.z, shz);
+    }
+    const float rlistOuter2 = p.rlist_outer_sq;
+    const float rlistInner2 = p.rlist_inner_sq;
+    int         count       = 0;
+
+    for (int jp = s.cj_packed_begin; jp < s.cj_packed_end; jp++)
+    {
+        const int4 cjv = *reinterpret_cast<const int4*>(pl.cjPacked[jp].cj);
+        unsigned   full0, full1, check0, check1, new0, new1;
+        if (FRESH)
+        {
+            full0  = pl.cjPacked[jp].imei[0].imask;
+            full1  = pl.cjPacked[jp].imei[1].imask;
+            check0 = full0;
+            check1 = full1;
+            new0   = 0u;
+            new1   = 0u;
+        }
+        else
+        {
+            const uint2 o = *reinterpret_cast<const uint2*>(pl.imaskOuter + 2 * jp);
+            full0         = o.x;
+            full1         = o.y;
+            new0          = pl.cjPacked[jp].imei[0].imask;
+            new1          = pl.cjPacked[jp].imei[1].imask;
+            check0        = new0 ^ full0;
+            check1        = new1 ^ full1;
+        }
+        const unsigned checkAny = check0 | check1;
+        if (checkAny == 0u)
+        {
+            continue;
+        }
+        const int cjs[4] = { cjv.x, cjv.y, cjv.z, cjv.w };
+#pragma unroll
+        for (int jm = 0; jm < c_jGroupSize; jm++)
+        {
+            if (checkAny & (0xffu << (jm * 8)))
+            {
+                const int    aj0 = cjs[jm] * c_clusterSize + jl;
+                const float4 xj0 = ad.xq[aj0];
+                const float4 xj1 = ad.xq[aj0 + 4];
+#pragma unroll
+                for (int ci = 0; ci < c_superClusterSize; ci++)
+                {
+                    const unsigned bit = 1u << (jm * 8 + ci);
+                    if (checkAny & bit)
+                    {
+                        const float r20 = norm2_fma(__fsub_rn(xi[ci], xj0.x), __fsub_rn(yi[ci], xj0.y), __fsub_rn(zi[ci], xj0.z));
+                        const float r21 = norm2_fma(__fsub_rn(xi[ci], xj1.x), __fsub_rn(yi[ci], xj1.y), __fsub_rn(zi[ci], xj1.z));
+                        if (check0 & bit)
+                        {
+                            if (FRESH && !__any_sync(c_full, r20 < rlistOuter2)) full0 &= ~bit;
+                            if (__any_sync(c_full, r20 < rlistInner2)) new0 |= bit;
+                        }
+                        if (check1 & bit)
+                        {
+                            if (FRESH && !__any_sync(c_full, r21 < rlistOuter2)) full1 &= ~bit;
+                            if (__any_sync(c_full, r21 < rlistInner2)) new1 |= bit;
+                        }
+                    }
+                }
+            }
+        }
+        if (lane == 0)
+        {
+            /* like the reference, a half whose check mask is empty is left untouched */
+            if (FRESH)
+            {
+                if (check0) pl.imaskOuter[2 * jp] = full0;
+                if (check1) pl.imaskOuter[2 * jp + 1] = full1;
+            }
+            if (check0) pl.cjPacked[jp].imei[0].imask = new0;
+            if (check1) pl.cjPacked[jp].imei[1].imask = new1;
+        }
+        if (FRESH)
+        {
+            count += (check0 ? __popc(new0) : 0) + (check1 ? __popc(new1) : 0);
+        }
+    }
+    if (FRESH && lane == 0)
+    {
+        const int index = max(c_sciHistogramSize - count - 1, 0);
+        atomicAdd(pl.sciHistogram + index, 1);
+        pl.sciCount[sciIdx] = index;
+    }
+}
+
+/* exclusive prefix sum of the 8192-bin histogram, one CTA */
+__global__ void __launch_bounds__(1024) nbnxm_sci_histogram_scan_kernel(const int* __restrict__ histogram, int* __restrict__ offset)
+{
+    constexpr int perThread = c_sciHistogramSize / 1024;
+    __shared__ int warpSums[32];
+    const int      t = threadIdx.x;
+    int            v[perThread];
+    int            sum = 0;
+#pragma unroll
+    for (int i = 0; i < perThread; i++)
+    {
+        v[i] = histogram[t * perThread + i];
+        sum += v[i];
+    }
+    int incl = sum;
+#pragma unroll
+    for (int m = 1; m < 32; m <<= 1)
+    {
+        const int n = __shfl_up_sync(0xffffffffu, incl, m);
+        if ((t & 31) >= m) incl += n;
+    }
+    if ((t & 31) == 31) warpSums[t >> 5] = incl;
+    __syncthreads();
+    if (t < 32)
+    {
+        int w = warpSums[t];
+#pragma unroll
+        for (int m = 1; m < 32; m <<= 1)
+        {
+            const int n = __shfl_up_sync(0xffffffffu, w, m);
+            if (t >= m) w += n;
+        }
+        warpSums[t] = w;
+    }
+    __syncthreads();
+    int base = incl - sum + ((t >> 5) > 0 ? warpSums[(t >> 5) - 1] : 0);
+#pragma unroll
+    for (int i = 0; i < perThread; i++)
+    {
+        offset[t * perThread + i] = base;
+        base += v[i];
+    }
+}
+
+__global__ void __launch_bounds__(256) nbnxm_sci_bucket_sort_kernel(const PairlistDev pl)
+{
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i < pl.numSci)
+    {
+        const nbnxm_b200_sci_t s   = pl.sci[i];
+        const int              pos = atomicAdd(pl.sciOffset + pl.sciCount[i], 1);
+        pl.sciSorted[pos]          = s;
+    }
+}
+
+void launch_prune(bool fresh, const AtomDataDev& ad, const ParamsDev& p, const PairlistDev& pl, int numParts, cudaStream_t stream)
+{
+    const int units  = (pl.numSci + numParts - 1) / numParts;
+    const int blocks = (units + c_pruneWarpsPerBlock - 1) / c_pruneWarpsPerBlock;
+    if (fresh)
+    {
+        nbnxm_prune_kernel<true><<<blocks, c_pruneWarpsPerBlock * 32, 0, stream>>>(ad, p, pl, numParts);
+    }
+    else
+    {
+        nbnxm_prune_kernel<false><<<blocks, c_pruneWarpsPerBlock * 32, 0, stream>>>(ad, p, pl, numParts);
+    }
+}
+
+void launch_sci_sort(const PairlistDev& pl, cudaStream_t stream)
+{
+    nbnxm_sci_histogram_scan_kernel<<<1, 1024, 0, stream>>>(pl.sciHistogram, pl.sciOffset);
+    nbnxm_sci_bucket_sort_kernel<<<(pl.numSci + 255) / 256, 256, 0, stream>>>(pl);
+}
+
+} // namespace nbb

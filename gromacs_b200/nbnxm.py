@@ -1,0 +1,338 @@
+"""Host-side mirror of the reference's NBNXM GPU-backend interface, over the C ABI.
+
+`NbnxmGpu` stands for the reference's `NbnxmGpu` object and its methods carry the names of the free
+functions in src/gromacs/nbnxm/nbnxm_gpu.h:68-313 and src/gromacs/nbnxm/gpu_data_mgmt.h:66-181
+(`gpu_init_pairlist`, `gpu_copy_xq_to_gpu`, `gpu_launch_kernel`, ...), with the same argument meaning
+and the same error behaviour (a failed call raises, it never falls back to a CPU path).
+
+The library (gromacs_b200/libnbnxm_b200.so) is plain C ABI (include/nbnxm_b200.h); nothing here
+touches torch.  The GPU work is entirely inside the library.
+"""
+import ctypes as C
+import os
+from dataclasses import dataclass, field
+
+import numpy as np
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+_LIB_PATH = os.path.join(_HERE, "libnbnxm_b200.so")
+
+LOCAL, NONLOCAL, ALL = 0, 1, 2
+
+ELEC_TYPES = {"Cut": 0, "RF": 1, "EwaldTab": 2, "EwaldTabTwin": 3, "EwaldAna": 4, "EwaldAnaTwin": 5}
+VDW_TYPES = {"Cut": 0, "CutCombGeom": 1, "CutCombLB": 2, "FSwitch": 3, "PSwitch": 4, "EwaldGeom": 5, "EwaldLB": 6}
+
+# every symbol include/nbnxm_b200.h declares
+EXPORTED_SYMBOLS = [
+    "nbnxm_b200_last_error", "nbnxm_b200_init", "nbnxm_b200_free", "nbnxm_b200_update_params",
+    "nbnxm_b200_init_pairlist", "nbnxm_b200_init_atomdata", "nbnxm_b200_upload_shiftvec",
+    "nbnxm_b200_copy_xq_to_gpu", "nbnxm_b200_init_x_to_nbat_x", "nbnxm_b200_x_to_nbat_x",
+    "nbnxm_b200_launch_kernel", "nbnxm_b200_launch_kernel_pruneonly", "nbnxm_b200_launch_cpyback",
+    "nbnxm_b200_try_finish_task", "nbnxm_b200_wait_finish_task", "nbnxm_b200_clear_outputs",
+    "nbnxm_b200_insert_nonlocal_dependency", "nbnxm_b200_setup_short_range_work",
+    "nbnxm_b200_have_short_range_work", "nbnxm_b200_min_ci_balanced",
+    "nbnxm_b200_is_kernel_ewald_analytical", "nbnxm_b200_get_timings", "nbnxm_b200_reset_timings",
+    "nbnxm_b200_set_timing", "nbnxm_b200_get_device_buffers", "nbnxm_b200_get_streams",
+    "nbnxm_b200_download_pairlist", "nbnxm_b200_set_pair_counting", "nbnxm_b200_get_pair_count",
+    "nbnxm_b200_launch_count", "nbnxm_b200_pack_xq", "nbnxm_b200_unpack_xq", "nbnxm_b200_pack_f",
+    "nbnxm_b200_unpack_add_f", "nbnxm_b200_measure_fp32_peak",
+]
+
+
+class NbnxmError(RuntimeError):
+    """Raised where the reference would gmx_fatal / GMX_THROW."""
+
+
+class Params(C.Structure):
+    """nbnxm_b200_params_t: the scalar part of NBParamGpu (gpu_types_common.h:222-262)."""
+    _fields_ = [("elec_type", C.c_int), ("vdw_type", C.c_int)] + [
+        (n, C.c_float) for n in (
+            "epsfac", "c_rf", "two_k_rf", "ewald_beta", "sh_ewald", "sh_lj_ewald", "ewaldcoeff_lj",
+            "rcoulomb_sq", "rvdw_sq", "rvdw_switch", "rlist_outer_sq", "rlist_inner_sq",
+            "disp_c2", "disp_c3", "disp_cpot", "rep_c2", "rep_c3", "rep_cpot",
+            "sw_c3", "sw_c4", "sw_c5", "coulomb_tab_scale")] + [("use_dynamic_pruning", C.c_int)]
+
+
+class Timings(C.Structure):
+    _fields_ = [("force_ms", (C.c_double * 2) * 2), ("force_count", (C.c_int * 2) * 2),
+                ("prune_ms", C.c_double), ("rolling_prune_ms", C.c_double),
+                ("prune_count", C.c_int), ("rolling_prune_count", C.c_int),
+                ("xq_h2d_ms", C.c_double), ("f_d2h_ms", C.c_double), ("pairlist_h2d_ms", C.c_double)]
+
+
+_lib = None
+
+
+def load_library():
+    """Load libnbnxm_b200.so; fails loudly when the CUDA extension has not been built."""
+    global _lib
+    if _lib is None:
+        if not os.path.exists(_LIB_PATH):
+            raise NbnxmError(
+                "%s is missing: build it with `make -C gromacs_b200/csrc` (there is no CPU fallback)" % _LIB_PATH)
+        lib = C.CDLL(_LIB_PATH)
+        lib.nbnxm_b200_last_error.restype = C.c_char_p
+        lib.nbnxm_b200_launch_count.restype = C.c_longlong
+        lib.nbnxm_b200_launch_count.argtypes = [C.c_void_p]
+        _lib = lib
+    return _lib
+
+
+def measure_fp32_peak(device=0):
+    """Pure-FFMA throughput of the device in TFLOP/s (roofline denominator of the force kernel)."""
+    v = C.c_double(0)
+    if load_library().nbnxm_b200_measure_fp32_peak(C.c_int(device), C.byref(v)):
+        raise NbnxmError("nbnxm_b200_measure_fp32_peak failed (no CUDA device?)")
+    return v.value
+
+
+def _ptr(a, ctype):
+    return None if a is None else a.ctypes.data_as(C.POINTER(ctype))
+
+
+def _f32(a):
+    return None if a is None else np.ascontiguousarray(a, dtype=np.float32)
+
+
+def _i32(a):
+    return None if a is None else np.ascontiguousarray(a, dtype=np.int32)
+
+
+@dataclass
+class StepWorkload:
+    """The fields of gmx::StepWorkload this path reads (mdtypes/simulation_workload.h:63-111)."""
+    computeForces: bool = True
+    computeEnergy: bool = False
+    computeVirial: bool = False
+    useGpuFBufferOps: bool = False
+
+
+@dataclass
+class PairlistGpu:
+    """NbnxmPairlistGpu as plain arrays (pairlist.h:335): sci int32[n,4], cjPacked uint32[n,8], excl uint32[n,32]."""
+    sci: np.ndarray
+    cjPacked: np.ndarray
+    excl: np.ndarray
+    na_ci: int = 8
+    rlist: float = 0.0
+
+    def __post_init__(self):
+        self.sci = np.ascontiguousarray(self.sci, np.int32).reshape(-1, 4)
+        self.cjPacked = np.ascontiguousarray(self.cjPacked, np.uint32).reshape(-1, 8)
+        self.excl = np.ascontiguousarray(self.excl, np.uint32).reshape(-1, 32)
+
+
+@dataclass
+class AtomData:
+    """The parts of nbnxm_atomdata_t this path reads/writes (atomdata.h:184-375)."""
+    xq: np.ndarray                      # x(): float32[natoms,4], XYZQ
+    type: np.ndarray = None             # params().type
+    lj_comb: np.ndarray = None          # params().lj_comb float32[natoms,2]
+    nbfp: np.ndarray = None             # params().nbfp float32[ntypes*ntypes,2] (6*C6, 12*C12)
+    nbfp_comb: np.ndarray = None        # params().nbfp_comb float32[ntypes,2]
+    numTypes: int = 0
+    shift_vec: np.ndarray = None        # float32[45,3]
+    numLocalAtoms: int = -1
+    f: np.ndarray = field(default=None)  # outputBuffer(0).f float32[natoms,3]
+
+    def numAtoms(self):
+        return int(self.xq.shape[0])
+
+    def __post_init__(self):
+        self.xq = _f32(self.xq).reshape(-1, 4)
+        if self.numLocalAtoms < 0:
+            self.numLocalAtoms = self.numAtoms()
+        if self.f is None:
+            self.f = np.zeros((self.numAtoms(), 3), np.float32)
+
+
+class NbnxmGpu:
+    """One per rank and device, like the reference's NbnxmGpu (cuda/nbnxm_cuda_types.h:69)."""
+
+    def __init__(self, params: Params, nbat: AtomData, device=0, bLocalAndNonlocal=False,
+                 coulomb_tab=None, local_stream=None, nonlocal_stream=None):
+        """gpu_init (nbnxm_gpu_data_mgmt.cpp:637)."""
+        self._lib = load_library()
+        self._h = C.c_void_p()
+        self.params = params
+        nbfp = _f32(nbat.nbfp)
+        nbfp_comb = _f32(nbat.nbfp_comb) if nbat.nbfp_comb is not None and np.size(nbat.nbfp_comb) else None
+        tab = _f32(coulomb_tab)
+        self._check(self._lib.nbnxm_b200_init(
+            C.byref(self._h), C.c_int(device), C.byref(params), C.c_int(nbat.numTypes), _ptr(nbfp, C.c_float),
+            _ptr(nbfp_comb, C.c_float), _ptr(tab, C.c_float), C.c_int(0 if tab is None else tab.size),
+            C.c_int(int(bLocalAndNonlocal)), C.c_void_p(local_stream), C.c_void_p(nonlocal_stream)))
+        self._keep = []   # host buffers with async copies in flight
+
+    # ---- plumbing -------------------------------------------------------------------------
+    def _check(self, status):
+        if status != 0:
+            raise NbnxmError(self._lib.nbnxm_b200_last_error().decode())
+
+    def gpu_free(self):
+        if self._h:
+            self._lib.nbnxm_b200_free(self._h)
+            self._h = C.c_void_p()
+
+    def __del__(self):
+        try:
+            self.gpu_free()
+        except Exception:
+            pass
+
+    # ---- search-step functions --------------------------------------------------------------
+    def gpu_init_pairlist(self, h_plist: PairlistGpu, iloc=LOCAL):
+        self._check(self._lib.nbnxm_b200_init_pairlist(
+            self._h, C.c_int(iloc), _ptr(h_plist.sci, C.c_int), C.c_int(h_plist.sci.shape[0]),
+            _ptr(h_plist.cjPacked, C.c_uint32), C.c_int(h_plist.cjPacked.shape[0]),
+            _ptr(h_plist.excl, C.c_uint32), C.c_int(h_plist.excl.shape[0]), C.c_int(h_plist.na_ci)))
+        self._numSci = getattr(self, "_numSci", {})
+        self._numSci[iloc] = h_plist.sci.shape[0]
+        self._ncj = getattr(self, "_ncj", {})
+        self._ncj[iloc] = h_plist.cjPacked.shape[0]
+
+    def gpu_init_atomdata(self, nbat: AtomData):
+        t = _i32(nbat.type)
+        lj = _f32(nbat.lj_comb) if nbat.lj_comb is not None and np.size(nbat.lj_comb) >= 2 * nbat.numAtoms() else None
+        self._natoms = nbat.numAtoms()
+        self._check(self._lib.nbnxm_b200_init_atomdata(
+            self._h, C.c_int(nbat.numAtoms()), C.c_int(nbat.numLocalAtoms), _ptr(t, C.c_int), _ptr(lj, C.c_float)))
+
+    def gpu_upload_shiftvec(self, nbat: AtomData, bDynamicBox=True):
+        sv = _f32(nbat.shift_vec)
+        self._check(self._lib.nbnxm_b200_upload_shiftvec(self._h, _ptr(sv, C.c_float), C.c_int(int(bDynamicBox))))
+
+    def setupGpuShortRangeWork(self, iloc=LOCAL, haveBondedWork=False):
+        self._check(self._lib.nbnxm_b200_setup_short_range_work(self._h, C.c_int(iloc), C.c_int(int(haveBondedWork))))
+
+    def haveGpuShortRangeWork(self, iloc=LOCAL):
+        return bool(self._lib.nbnxm_b200_have_short_range_work(self._h, C.c_int(iloc)))
+
+    def nbnxm_gpu_init_x_to_nbat_x(self, atom_index, atom_offset=0, grid=0, ngrids=1):
+        ai = _i32(atom_index)
+        self._check(self._lib.nbnxm_b200_init_x_to_nbat_x(
+            self._h, C.c_int(grid), C.c_int(ngrids), _ptr(ai, C.c_int), C.c_int(ai.shape[0]), None, None,
+            C.c_int(0), C.c_int(64), C.c_int(atom_offset)))
+
+    # ---- per-step functions -------------------------------------------------------------------
+    def gpu_copy_xq_to_gpu(self, nbat: AtomData, aloc=LOCAL):
+        self._keep.append(nbat.xq)
+        self._check(self._lib.nbnxm_b200_copy_xq_to_gpu(self._h, C.c_int(aloc), _ptr(nbat.xq, C.c_float)))
+
+    def nbnxm_gpu_x_to_nbat_x(self, d_x_ptr, xReadyOnDevice=None, aloc=LOCAL):
+        self._check(self._lib.nbnxm_b200_x_to_nbat_x(self._h, C.c_void_p(d_x_ptr), C.c_void_p(xReadyOnDevice), C.c_int(aloc)))
+
+    def gpu_launch_kernel(self, stepWork: StepWorkload, iloc=LOCAL):
+        self._check(self._lib.nbnxm_b200_launch_kernel(
+            self._h, C.c_int(iloc), C.c_int(int(stepWork.computeEnergy)), C.c_int(int(stepWork.computeVirial))))
+
+    def gpu_launch_kernel_pruneonly(self, iloc=LOCAL, numParts=1):
+        self._check(self._lib.nbnxm_b200_launch_kernel_pruneonly(self._h, C.c_int(iloc), C.c_int(numParts)))
+
+    def gpu_launch_cpyback(self, nbat: AtomData, stepWork: StepWorkload, aloc=LOCAL):
+        self._keep.append(nbat.f)
+        self._check(self._lib.nbnxm_b200_launch_cpyback(
+            self._h, C.c_int(aloc), _ptr(nbat.f, C.c_float), C.c_int(int(stepWork.computeEnergy)),
+            C.c_int(int(stepWork.computeVirial)), C.c_int(int(stepWork.useGpuFBufferOps))))
+
+    def gpu_wait_finish_task(self, stepWork: StepWorkload, aloc=LOCAL, shiftForces=None):
+        """Returns (e_lj, e_el) added by this task; shift forces are added into shiftForces[45,3]."""
+        e_lj, e_el = C.c_float(0), C.c_float(0)
+        fs = np.zeros((45, 3), np.float32)
+        self._check(self._lib.nbnxm_b200_wait_finish_task(
+            self._h, C.c_int(aloc), C.c_int(int(stepWork.computeEnergy)), C.c_int(int(stepWork.computeVirial)),
+            C.byref(e_lj), C.byref(e_el), _ptr(fs, C.c_float)))
+        if shiftForces is not None:
+            shiftForces += fs
+        self._keep.clear()
+        return e_lj.value, e_el.value
+
+    def gpu_try_finish_task(self, stepWork: StepWorkload, aloc=LOCAL, shiftForces=None):
+        e_lj, e_el, done = C.c_float(0), C.c_float(0), C.c_int(0)
+        fs = np.zeros((45, 3), np.float32)
+        self._check(self._lib.nbnxm_b200_try_finish_task(
+            self._h, C.c_int(aloc), C.c_int(int(stepWork.computeEnergy)), C.c_int(int(stepWork.computeVirial)),
+            C.byref(e_lj), C.byref(e_el), _ptr(fs, C.c_float), C.byref(done)))
+        if done.value and shiftForces is not None:
+            shiftForces += fs
+        return bool(done.value), e_lj.value, e_el.value
+
+    def gpu_clear_outputs(self, computeVirial=True):
+        self._check(self._lib.nbnxm_b200_clear_outputs(self._h, C.c_int(int(computeVirial))))
+
+    def nbnxmInsertNonlocalGpuDependency(self, iloc):
+        self._check(self._lib.nbnxm_b200_insert_nonlocal_dependency(self._h, C.c_int(iloc)))
+
+    # ---- queries --------------------------------------------------------------------------------
+    def gpu_min_ci_balanced(self):
+        return int(self._lib.nbnxm_b200_min_ci_balanced(self._h))
+
+    def gpu_is_kernel_ewald_analytical(self):
+        return bool(self._lib.nbnxm_b200_is_kernel_ewald_analytical(self._h))
+
+    def gpu_pme_loadbal_update_param(self, params: Params, coulomb_tab=None):
+        tab = _f32(coulomb_tab)
+        self._check(self._lib.nbnxm_b200_update_params(
+            self._h, C.byref(params), _ptr(tab, C.c_float), C.c_int(0 if tab is None else tab.size)))
+        self.params = params
+
+    def set_timing(self, enable=True):
+        self._check(self._lib.nbnxm_b200_set_timing(self._h, C.c_int(int(enable))))
+
+    def gpu_get_timings(self):
+        t = Timings()
+        self._check(self._lib.nbnxm_b200_get_timings(self._h, C.byref(t)))
+        return t
+
+    def gpu_reset_timings(self):
+        self._check(self._lib.nbnxm_b200_reset_timings(self._h))
+
+    def device_buffers(self):
+        """(d_xq, d_f, natoms): raw device addresses of the float4 coordinates and float3 forces."""
+        xq, f, n = C.c_void_p(), C.c_void_p(), C.c_int()
+        self._check(self._lib.nbnxm_b200_get_device_buffers(self._h, C.byref(xq), C.byref(f), C.byref(n)))
+        return xq.value, f.value, n.value
+
+    def streams(self):
+        a, b = C.c_void_p(), C.c_void_p()
+        self._check(self._lib.nbnxm_b200_get_streams(self._h, C.byref(a), C.byref(b)))
+        return a.value, b.value
+
+    def download_pairlist(self, iloc=LOCAL):
+        """(cjPacked uint32[n,8], imask_outer uint32[2n], sciSorted int32[nsci,4], sciCount int32[nsci], rollingPart)."""
+        nsci, ncj = self._numSci[iloc], self._ncj[iloc]
+        cj = np.zeros((ncj, 8), np.uint32)
+        im = np.zeros(2 * ncj, np.uint32)
+        ss = np.zeros((nsci, 4), np.int32)
+        sc = np.zeros(nsci, np.int32)
+        rp = np.zeros(nsci, np.int32)
+        self._check(self._lib.nbnxm_b200_download_pairlist(
+            self._h, C.c_int(iloc), _ptr(cj, C.c_uint32), _ptr(im, C.c_uint32), _ptr(ss, C.c_int),
+            _ptr(sc, C.c_int), _ptr(rp, C.c_int)))
+        return cj, im, ss, sc, rp
+
+    def set_pair_counting(self, enable=True):
+        self._check(self._lib.nbnxm_b200_set_pair_counting(self._h, C.c_int(int(enable))))
+
+    def get_pair_count(self, iloc=LOCAL):
+        v = C.c_longlong(0)
+        self._check(self._lib.nbnxm_b200_get_pair_count(self._h, C.c_int(iloc), C.byref(v)))
+        return v.value
+
+    def launch_count(self):
+        return int(self._lib.nbnxm_b200_launch_count(self._h))
+
+    # ---- halo helpers (x-slab decomposition) -------------------------------------------------------
+    def pack_xq(self, d_index_ptr, n, shift3, d_send_ptr, stream=None):
+        sh = _f32(shift3)
+        self._check(self._lib.nbnxm_b200_pack_xq(self._h, C.c_void_p(d_index_ptr), C.c_int(n), _ptr(sh, C.c_float),
+                                                C.c_void_p(d_send_ptr), C.c_void_p(stream)))
+
+    def unpack_xq(self, first, n, d_recv_ptr, stream=None):
+        self._check(self._lib.nbnxm_b200_unpack_xq(self._h, C.c_int(first), C.c_int(n), C.c_void_p(d_recv_ptr), C.c_void_p(stream)))
+
+    def pack_f(self, first, n, d_send_ptr, stream=None):
+        self._check(self._lib.nbnxm_b200_pack_f(self._h, C.c_int(first), C.c_int(n), C.c_void_p(d_send_ptr), C.c_void_p(stream)))
+
+    def unpack_add_f(self, d_index_ptr, n, d_recv_ptr, stream=None):
+        self._check(self._lib.nbnxm_b200_unpack_add_f(self._h, C.c_void_p(d_index_ptr), C.c_int(n), C.c_void_p(d_recv_ptr), C.c_void_p(stream)))

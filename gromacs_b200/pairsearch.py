@@ -1,0 +1,96 @@
+"""Host-side grid + GPU-layout pair-list construction (include/nbnxm_b200_search.h), the caller side of the
+force path: mirrors nonbonded_verlet_t::putAtomsOnGrid / setAtomProperties / constructPairlist
+(src/gromacs/nbnxm/nbnxm.cpp:78, atomdata.cpp:1107, pairlist.cpp:4056)."""
+import ctypes as C
+import os
+
+import numpy as np
+
+from .nbnxm import AtomData, NbnxmError, PairlistGpu, load_library
+
+SEARCH_SYMBOLS = [
+    "nbnxm_b200_grid_create", "nbnxm_b200_grid_free", "nbnxm_b200_grid_info", "nbnxm_b200_grid_get_order",
+    "nbnxm_b200_grid_fill_atomdata", "nbnxm_b200_pairlist_build", "nbnxm_b200_pairlist_sizes",
+    "nbnxm_b200_pairlist_copy",
+]
+
+
+def _p(a, ct):
+    return None if a is None else a.ctypes.data_as(C.POINTER(ct))
+
+
+class Grid:
+    """One pair-search grid over a rectangular periodic box (Grid / GridSet of the reference)."""
+
+    def __init__(self, box, x, nthreads=None):
+        self._lib = load_library()
+        self._g = C.c_void_p()
+        self.nthreads = nthreads or min(os.cpu_count() or 1, 64)
+        self.box = np.ascontiguousarray(box, np.float32)
+        x = np.ascontiguousarray(x, np.float32)
+        self.natoms = x.shape[0]
+        if self._lib.nbnxm_b200_grid_create(C.byref(self._g), _p(self.box, C.c_float), C.c_int(self.natoms),
+                                            _p(x, C.c_float), C.c_int(self.nthreads)):
+            raise NbnxmError("nbnxm_b200_grid_create failed")
+        n, nb, ncx, ncy = C.c_int(), C.c_int(), C.c_int(), C.c_int()
+        self._lib.nbnxm_b200_grid_info(self._g, C.byref(n), C.byref(nb), C.byref(ncx), C.byref(ncy))
+        self.natoms_nbat, self.nbins, self.ncx, self.ncy = n.value, nb.value, ncx.value, ncy.value
+        self.atom_index = np.zeros(self.natoms_nbat, np.int32)
+        self.first_bin_of_column = np.zeros(self.ncx * self.ncy + 1, np.int32)
+        self._lib.nbnxm_b200_grid_get_order(self._g, _p(self.atom_index, C.c_int), _p(self.first_bin_of_column, C.c_int))
+
+    def __del__(self):
+        try:
+            if self._g:
+                self._lib.nbnxm_b200_grid_free(self._g)
+                self._g = C.c_void_p()
+        except Exception:
+            pass
+
+    def atomdata(self, x, q, atom_type, nbfp, ntypes, nbfp_comb=None, lj_comb_per_type=None, shift_vec=None):
+        """Build the nbnxm_atomdata_t contents in grid order (fillers: x = -1e6, q = 0, type = ntypes-1)."""
+        x = np.ascontiguousarray(x, np.float32)
+        q = np.ascontiguousarray(q, np.float32)
+        t = np.ascontiguousarray(atom_type, np.int32)
+        xq = np.zeros((self.natoms_nbat, 4), np.float32)
+        tn = np.zeros(self.natoms_nbat, np.int32)
+        ljt = None if lj_comb_per_type is None else np.ascontiguousarray(lj_comb_per_type, np.float32)
+        lj = None if ljt is None else np.zeros((self.natoms_nbat, 2), np.float32)
+        if self._lib.nbnxm_b200_grid_fill_atomdata(self._g, _p(x, C.c_float), _p(q, C.c_float), _p(t, C.c_int),
+                                                   C.c_int(ntypes), _p(ljt, C.c_float), _p(xq, C.c_float),
+                                                   _p(tn, C.c_int), _p(lj, C.c_float)):
+            raise NbnxmError("nbnxm_b200_grid_fill_atomdata failed")
+        return AtomData(xq=xq, type=tn, lj_comb=lj, nbfp=nbfp, nbfp_comb=nbfp_comb, numTypes=ntypes,
+                        shift_vec=shift_vec if shift_vec is not None else shift_vectors(self.box))
+
+    def pairlist(self, rlist, excl_index=None, excl_atoms=None, min_sci=0, bins=None, j_bins=None,
+                 inter_zone=False, required_tx=0):
+        """constructPairlist for the GPU layout; returns a PairlistGpu. bins / j_bins: (begin, end) bin ranges."""
+        b0, b1 = bins if bins is not None else (0, self.nbins)
+        j0, j1 = j_bins if j_bins is not None else (0, self.nbins)
+        ei = None if excl_index is None else np.ascontiguousarray(excl_index, np.int32)
+        ea = None if excl_atoms is None else np.ascontiguousarray(excl_atoms, np.int32)
+        if self._lib.nbnxm_b200_pairlist_build(self._g, C.c_float(rlist), _p(ei, C.c_int), _p(ea, C.c_int),
+                                               C.c_int(min_sci), C.c_int(b0), C.c_int(b1), C.c_int(j0), C.c_int(j1),
+                                               C.c_int(int(inter_zone)), C.c_int(required_tx), C.c_int(self.nthreads)):
+            raise NbnxmError("nbnxm_b200_pairlist_build failed (rlist must be < half the box)")
+        nsci, ncj, nex, ncp = C.c_int(), C.c_int(), C.c_int(), C.c_longlong()
+        self._lib.nbnxm_b200_pairlist_sizes(self._g, C.byref(nsci), C.byref(ncj), C.byref(nex), C.byref(ncp))
+        sci = np.zeros((nsci.value, 4), np.int32)
+        cjp = np.zeros((ncj.value, 8), np.uint32)
+        excl = np.zeros((nex.value, 32), np.uint32)
+        self._lib.nbnxm_b200_pairlist_copy(self._g, _p(sci, C.c_int), _p(cjp, C.c_uint32), _p(excl, C.c_uint32))
+        pl = PairlistGpu(sci=sci, cjPacked=cjp, excl=excl, na_ci=8, rlist=rlist)
+        pl.nci_tot = ncp.value
+        return pl
+
+
+def shift_vectors(box):
+    """calc_shifts for a rectangular box (src/gromacs/pbcutil/pbc.cpp): 45 vectors, index
+    ((z+1)*3 + (y+1))*5 + (x+2), central = 22 (pbcutil/ishift.h:43-56)."""
+    sv = np.zeros((45, 3), np.float32)
+    for z in (-1, 0, 1):
+        for y in (-1, 0, 1):
+            for x in (-2, -1, 0, 1, 2):
+                sv[((z + 1) * 3 + (y + 1)) * 5 + (x + 2)] = (x * box[0], y * box[1], z * box[2])
+    return sv

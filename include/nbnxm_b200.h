@@ -1,0 +1,212 @@
+/* nbnxm_b200 — C ABI of the Blackwell-native NBNXM short-range nonbonded path.
+ *
+ * One opaque handle (nbnxm_b200_t) stands for the reference's `NbnxmGpu`
+ * (src/gromacs/nbnxm/cuda/nbnxm_cuda_types.h:69).  Every entry point replaces one free function
+ * of the reference's GPU-backend boundary, src/gromacs/nbnxm/nbnxm_gpu.h:68-313 and
+ * src/gromacs/nbnxm/gpu_data_mgmt.h:66-181; the function it replaces is cited on each declaration.
+ *
+ * Conventions
+ *  - plain pointers and sizes only; host pointers unless a name starts with d_.
+ *  - every function returns 0 on success, non-zero on failure; nbnxm_b200_last_error() returns the
+ *    message.  (The reference's functions do not return errors, they gmx_fatal(); the C++ shim in
+ *    gromacs_b200/gmx_shim turns a non-zero status into gmx_fatal to keep that convention.)
+ *  - there is no CPU fallback: without a usable sm_100 device nbnxm_b200_init fails.
+ *  - iloc / aloc: 0 = Local, 1 = NonLocal (gmx::InteractionLocality / AtomLocality,
+ *    src/gromacs/mdtypes/locality.h); aloc 2 = All where the reference allows it.
+ *  - all work is stream-ordered on the handle's local / non-local streams like the reference
+ *    (nbnxm_cuda_types.h:112); host buffers passed to async copies must stay alive until
+ *    nbnxm_b200_wait_finish_task (pinned memory recommended, cf. HostAllocationPolicy).
+ */
+#ifndef NBNXM_B200_H
+#define NBNXM_B200_H
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+typedef struct nbnxm_b200 nbnxm_b200_t;
+
+/* gmx::ElecType / gmx::VdwType, src/gromacs/nbnxm/nbnxm_enums.h:73-110 (same numbering) */
+enum nbnxm_b200_elec_type
+{
+    NBNXM_B200_ELEC_CUT            = 0,
+    NBNXM_B200_ELEC_RF             = 1,
+    NBNXM_B200_ELEC_EWALD_TAB      = 2,
+    NBNXM_B200_ELEC_EWALD_TAB_TWIN = 3,
+    NBNXM_B200_ELEC_EWALD_ANA      = 4,
+    NBNXM_B200_ELEC_EWALD_ANA_TWIN = 5
+};
+enum nbnxm_b200_vdw_type
+{
+    NBNXM_B200_VDW_CUT           = 0,
+    NBNXM_B200_VDW_CUT_COMB_GEOM = 1,
+    NBNXM_B200_VDW_CUT_COMB_LB   = 2,
+    NBNXM_B200_VDW_FSWITCH       = 3,
+    NBNXM_B200_VDW_PSWITCH       = 4,
+    NBNXM_B200_VDW_EWALD_GEOM    = 5,
+    NBNXM_B200_VDW_EWALD_LB      = 6
+};
+
+/* Scalar part of gmx::NBParamGpu (src/gromacs/nbnxm/gpu_types_common.h:222-262), i.e. what
+ * set_cutoff_parameters / initNbparam derive from interaction_const_t and PairlistParams
+ * (src/gromacs/nbnxm/nbnxm_gpu_data_mgmt.cpp:218-240, 462-520). */
+typedef struct
+{
+    int   elec_type; /* nbnxm_b200_elec_type */
+    int   vdw_type;  /* nbnxm_b200_vdw_type */
+    float epsfac;
+    float c_rf;
+    float two_k_rf;
+    float ewald_beta;
+    float sh_ewald;
+    float sh_lj_ewald;
+    float ewaldcoeff_lj;
+    float rcoulomb_sq;
+    float rvdw_sq;
+    float rvdw_switch;
+    float rlist_outer_sq;
+    float rlist_inner_sq;
+    float disp_c2, disp_c3, disp_cpot; /* shift_consts_t dispersion_shift */
+    float rep_c2, rep_c3, rep_cpot;    /* shift_consts_t repulsion_shift  */
+    float sw_c3, sw_c4, sw_c5;         /* switch_consts_t vdw_switch      */
+    float coulomb_tab_scale;
+    int   use_dynamic_pruning;
+} nbnxm_b200_params_t;
+
+/* Byte-identical to nbnxm_sci_t / nbnxm_cj_packed_t / nbnxm_excl_t, src/gromacs/nbnxm/pairlist.h:189-287 */
+typedef struct
+{
+    int sci, shift, cj_packed_begin, cj_packed_end;
+} nbnxm_b200_sci_t;
+typedef struct
+{
+    int cj[4];
+    struct
+    {
+        unsigned int imask;
+        int          excl_ind;
+    } imei[2];
+} nbnxm_b200_cj_packed_t;
+typedef struct
+{
+    unsigned int pair[32];
+} nbnxm_b200_excl_t;
+
+/* gmx_wallclock_gpu_nbnxm_t, src/gromacs/timing/include/gromacs/timing/gpu_timing.h:80-92 (ms, counts) */
+typedef struct
+{
+    double force_ms[2][2]; /* [prune?][energy?] */
+    int    force_count[2][2];
+    double prune_ms, rolling_prune_ms;
+    int    prune_count, rolling_prune_count;
+    double xq_h2d_ms, f_d2h_ms, pairlist_h2d_ms;
+} nbnxm_b200_timings_t;
+
+const char* nbnxm_b200_last_error(void);
+
+/* gpu_init, nbnxm_gpu_data_mgmt.cpp:637.  nbfp: ntypes*ntypes (6*C6, 12*C12) pairs; nbfp_comb: ntypes
+ * pairs or NULL; coulomb_tab: F*r table (EwaldCorrectionTables::tableF) or NULL.
+ * local_stream / nonlocal_stream: cudaStream_t to run on, or NULL to let the library create them. */
+int nbnxm_b200_init(nbnxm_b200_t** nb, int device, const nbnxm_b200_params_t* params, int ntypes,
+                    const float* nbfp, const float* nbfp_comb, const float* coulomb_tab, int coulomb_tab_size,
+                    int local_and_nonlocal, void* local_stream, void* nonlocal_stream);
+/* gpu_free, nbnxm_gpu_data_mgmt.cpp:1724 */
+int nbnxm_b200_free(nbnxm_b200_t* nb);
+/* gpu_pme_loadbal_update_param, nbnxm_gpu_data_mgmt.cpp:701 */
+int nbnxm_b200_update_params(nbnxm_b200_t* nb, const nbnxm_b200_params_t* params, const float* coulomb_tab,
+                             int coulomb_tab_size);
+
+/* gpu_init_pairlist, nbnxm_gpu_data_mgmt.cpp:739 */
+int nbnxm_b200_init_pairlist(nbnxm_b200_t* nb, int iloc, const nbnxm_b200_sci_t* sci, int nsci,
+                             const nbnxm_b200_cj_packed_t* cj_packed, int ncj_packed,
+                             const nbnxm_b200_excl_t* excl, int nexcl, int na_ci);
+/* gpu_init_atomdata, nbnxm_gpu_data_mgmt.cpp:1006.  atom_type and/or lj_comb (natoms float pairs)
+ * as the flavor needs (types for Cut/FSwitch/PSwitch/Ewald*, lj_comb for CutComb*). */
+int nbnxm_b200_init_atomdata(nbnxm_b200_t* nb, int natoms, int natoms_local, const int* atom_type,
+                             const float* lj_comb);
+/* gpu_upload_shiftvec, nbnxm_gpu_data_mgmt.cpp:719.  shift_vec: 45 x 3 floats */
+int nbnxm_b200_upload_shiftvec(nbnxm_b200_t* nb, const float* shift_vec, int dynamic_box);
+/* gpu_copy_xq_to_gpu, nbnxm_gpu_data_mgmt.cpp:1489.  xq: natoms x 4 floats (nbat->x(), XYZQ) */
+int nbnxm_b200_copy_xq_to_gpu(nbnxm_b200_t* nb, int aloc, const float* xq);
+/* nbnxm_gpu_init_x_to_nbat_x, nbnxm_gpu_data_mgmt.cpp:1605.  One grid per call:
+ * atom_index[natoms_nbat] (nbat slot -> rvec index, -1 for fillers), cells packed with
+ * num_atoms_per_cell atoms; cxy_na / cxy_ind: per column atom count / first cell (ncolumns, ncolumns+1). */
+int nbnxm_b200_init_x_to_nbat_x(nbnxm_b200_t* nb, int grid, int ngrids, const int* atom_index, int natoms_nbat,
+                                const int* cxy_na, const int* cxy_ind, int ncolumns, int num_atoms_per_cell,
+                                int atom_offset);
+/* nbnxm_gpu_x_to_nbat_x, nbnxm_gpu_buffer_ops.cpp:59 / cuda/nbnxm_gpu_buffer_ops_internal.cu:73.
+ * d_x: device rvec coordinates; x_ready_event: cudaEvent_t or NULL. */
+int nbnxm_b200_x_to_nbat_x(nbnxm_b200_t* nb, const float* d_x, void* x_ready_event, int aloc);
+
+/* gpu_launch_kernel, cuda/nbnxm_cuda.cu:516 */
+int nbnxm_b200_launch_kernel(nbnxm_b200_t* nb, int iloc, int compute_energy, int compute_virial);
+/* gpu_launch_kernel_pruneonly, cuda/nbnxm_cuda.cu:660 */
+int nbnxm_b200_launch_kernel_pruneonly(nbnxm_b200_t* nb, int iloc, int num_parts);
+/* gpu_launch_cpyback, nbnxm_gpu_data_mgmt.cpp:1268.  f: natoms x 3 floats (nbat order, XYZ) */
+int nbnxm_b200_launch_cpyback(nbnxm_b200_t* nb, int aloc, float* f, int compute_energy, int compute_virial,
+                              int use_gpu_f_buffer_ops);
+/* gpu_try_finish_task / gpu_wait_finish_task, gpu_common.h:290 / :394.  Adds the staged energies and
+ * shift forces (45 x 3) into e_lj, e_el, fshift for aloc == Local, like gpu_reduce_staged_outputs
+ * (gpu_common.h:141).  *done = 1 when the task completed (always for wait). */
+int nbnxm_b200_try_finish_task(nbnxm_b200_t* nb, int aloc, int compute_energy, int compute_virial,
+                               float* e_lj, float* e_el, float* fshift, int* done);
+int nbnxm_b200_wait_finish_task(nbnxm_b200_t* nb, int aloc, int compute_energy, int compute_virial,
+                                float* e_lj, float* e_el, float* fshift);
+/* gpu_clear_outputs, nbnxm_gpu_data_mgmt.cpp:1197 */
+int nbnxm_b200_clear_outputs(nbnxm_b200_t* nb, int compute_virial);
+/* nbnxmInsertNonlocalGpuDependency, nbnxm_gpu_data_mgmt.cpp:1464 */
+int nbnxm_b200_insert_nonlocal_dependency(nbnxm_b200_t* nb, int iloc);
+/* setupGpuShortRangeWorkLow / haveGpuShortRangeWork, nbnxm_gpu_data_mgmt.cpp:1244 / :1257 */
+int nbnxm_b200_setup_short_range_work(nbnxm_b200_t* nb, int iloc, int have_bonded_work);
+int nbnxm_b200_have_short_range_work(const nbnxm_b200_t* nb, int iloc);
+/* gpu_min_ci_balanced, cuda/nbnxm_cuda_data_mgmt.cu:122 */
+int nbnxm_b200_min_ci_balanced(const nbnxm_b200_t* nb);
+/* gpu_is_kernel_ewald_analytical, nbnxm_gpu_data_mgmt.cpp:1238 */
+int nbnxm_b200_is_kernel_ewald_analytical(const nbnxm_b200_t* nb);
+/* gpu_get_timings / gpu_reset_timings, nbnxm_gpu_data_mgmt.cpp:1224 / :1230 */
+int nbnxm_b200_get_timings(nbnxm_b200_t* nb, nbnxm_b200_timings_t* out);
+int nbnxm_b200_reset_timings(nbnxm_b200_t* nb);
+int nbnxm_b200_set_timing(nbnxm_b200_t* nb, int enable);
+
+/* gpu_get_f / gpuGetNBAtomData, nbnxm_gpu_data_mgmt.cpp:1829 / :1823: device views.
+ * d_f is float3-packed (natoms x 3), valid after nbnxm_b200_launch_cpyback's reduction stage
+ * (use_gpu_f_buffer_ops = 1 keeps it on the device); d_xq is float4. */
+int nbnxm_b200_get_device_buffers(nbnxm_b200_t* nb, float** d_xq, float** d_f, int* natoms);
+/* streams the handle runs on (cudaStream_t), for callers that order their own work against it */
+int nbnxm_b200_get_streams(nbnxm_b200_t* nb, void** local_stream, void** nonlocal_stream);
+
+/* ---- inspection helpers (the reference reads the same data back in
+ * GpuPairlistTest, src/gromacs/nbnxm/tests/pairlist.cpp:236) ---- */
+/* copies the device cjPacked array (with pruned imasks), the outer-pruned imask array (2 per cjPacked),
+ * sciSorted and the per-sci histogram index back to the host; any pointer may be NULL. */
+int nbnxm_b200_download_pairlist(nbnxm_b200_t* nb, int iloc, nbnxm_b200_cj_packed_t* cj_packed,
+                                 unsigned int* imask_outer, nbnxm_b200_sci_t* sci_sorted, int* sci_count,
+                                 int* rolling_part);
+/* number of atom pairs the last force launch on iloc evaluated (32 per set imask bit), counted on the
+ * device when counting is enabled with nbnxm_b200_set_pair_counting */
+int nbnxm_b200_set_pair_counting(nbnxm_b200_t* nb, int enable);
+int nbnxm_b200_get_pair_count(nbnxm_b200_t* nb, int iloc, long long* npairs);
+/* number of kernels this handle launched since init (for bench.py's gpu_launches) */
+long long nbnxm_b200_launch_count(const nbnxm_b200_t* nb);
+
+/* measured FP32 FMA peak of the device in TFLOP/s (pure-FFMA kernel, best of 5): the roofline denominator */
+int nbnxm_b200_measure_fp32_peak(int device, double* tflops);
+
+/* ---- x-slab halo exchange helpers (the reference's pack / unpack kernels,
+ * src/gromacs/domdec/gpuhaloexchange_impl_gpu.cu:82-137); the transport (NCCL send/recv) is the caller's ---- */
+/* d_send[i] = xq[index[i]] (+ shift on xyz); index on device */
+int nbnxm_b200_pack_xq(nbnxm_b200_t* nb, const int* d_index, int n, const float* shift3, float* d_send, void* stream);
+/* xq[first + i] = d_recv[i] */
+int nbnxm_b200_unpack_xq(nbnxm_b200_t* nb, int first, int n, const float* d_recv, void* stream);
+/* d_send[i] = f[first + i] (float4), then zeroes nothing */
+int nbnxm_b200_pack_f(nbnxm_b200_t* nb, int first, int n, float* d_send, void* stream);
+/* f[index[i]] += d_recv[i] */
+int nbnxm_b200_unpack_add_f(nbnxm_b200_t* nb, const int* d_index, int n, const float* d_recv, void* stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* NBNXM_B200_H */

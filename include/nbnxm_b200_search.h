@@ -1,0 +1,63 @@
+/* nbnxm_b200_search — host-side grid binning and GPU-layout pair-list construction (C ABI).
+ *
+ * This is the caller side of the force path ("next" row of the scope table): it produces exactly the
+ * inputs the reference hands to gpu_init_atomdata / gpu_init_pairlist, in the reference's formats:
+ *   - atoms sorted into columns / 64-atom bins / 2x2x2 clusters of 8 (Grid::putOnGrid and
+ *     sortCellsGpuGeometry, src/gromacs/nbnxm/grid.cpp:1612, :1169),
+ *   - nbnxm_sci_t / nbnxm_cj_packed_t / nbnxm_excl_t arrays (src/gromacs/nbnxm/pairlist.h:189-287) with the
+ *     mask conventions of src/gromacs/nbnxm/pairlist.cpp:651-688 (self/Newton exclusions), :1561-1660
+ *     (topology exclusions), :1769-1879 (splitting of long i-entries for load balance).
+ * It is an independent implementation (bounding-box search over a column grid, OpenMP over i-bins); the
+ * list it builds is not entry-for-entry the reference's list (any list that covers all pairs within
+ * rlist exactly once is valid), which tests/test_pairsearch.py verifies against brute force.
+ * Rectangular boxes only.
+ */
+#ifndef NBNXM_B200_SEARCH_H
+#define NBNXM_B200_SEARCH_H
+
+#include "nbnxm_b200.h"
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+typedef struct nbnxm_b200_grid nbnxm_b200_grid_t;
+
+/* nonbonded_verlet_t::putAtomsOnGrid (src/gromacs/nbnxm/nbnxm.cpp:78): bins natoms atoms (x: natoms x 3,
+ * inside the rectangular box [0, box)) and sorts them into nbat order. */
+int nbnxm_b200_grid_create(nbnxm_b200_grid_t** grid, const float* box, int natoms, const float* x, int nthreads);
+int nbnxm_b200_grid_free(nbnxm_b200_grid_t* grid);
+/* number of nbat slots (atoms padded to whole 64-atom bins) and bins, grid columns along x and y */
+int nbnxm_b200_grid_info(const nbnxm_b200_grid_t* grid, int* natoms_nbat, int* nbins, int* ncx, int* ncy);
+/* atom_index[natoms_nbat]: nbat slot -> atom (-1 = filler) (GridSet::atomIndices);
+ * first_bin_of_column[ncx*ncy + 1] (Grid::cellToBin_) */
+int nbnxm_b200_grid_get_order(const nbnxm_b200_grid_t* grid, int* atom_index, int* first_bin_of_column);
+/* nbnxm_atomdata_t::copy x / setAtomProperties (src/gromacs/nbnxm/atomdata.cpp:159-280, :1107): fills
+ * xq[natoms_nbat*4] (fillers at -1e6 with q = 0), type[natoms_nbat] (fillers get ntypes-1) and, when
+ * lj_comb_per_type != NULL (ntypes x 2), lj_comb[natoms_nbat*2]. Any output may be NULL. */
+int nbnxm_b200_grid_fill_atomdata(const nbnxm_b200_grid_t* grid, const float* x, const float* q, const int* type,
+                                  int ntypes, const float* lj_comb_per_type, float* xq, int* type_nbat,
+                                  float* lj_comb);
+
+/* nonbonded_verlet_t::constructPairlist (src/gromacs/nbnxm/pairlist.cpp:4056) for the GPU layout.
+ * excl_index/excl_atoms: topology exclusions as CSR in atom order (may be NULL).
+ * min_sci: split i-entries so that at least about this many are produced (gpu_min_ci_balanced); 0 = no split.
+ * bin_begin/bin_end: only i-bins in [bin_begin, bin_end) get i-entries; j_bin_lo/j_bin_hi restrict the
+ * j-clusters to bins in [j_bin_lo, j_bin_hi); pass 0, nbins, 0, nbins for the whole system.
+ * inter_zone = 0: i and j ranges are the same zone: half-shell rule (backward PBC shifts only, j >= i on the
+ *   central shift), like an intra-grid list of the reference (pairlist.cpp:3063-3067, 3226-3229).
+ * inter_zone = 1: i bins are a home x-slab and j bins its +x neighbour slab (halo): every pair is listed
+ *   once for all y/z shifts and only the x shift `required_tx` (0, or -1 across the periodic boundary),
+ *   like the reference's inter-zone lists of the eighth-shell scheme (domdec/domdec_zones.cpp:55-83). */
+int nbnxm_b200_pairlist_build(nbnxm_b200_grid_t* grid, float rlist, const int* excl_index, const int* excl_atoms,
+                              int min_sci, int bin_begin, int bin_end, int j_bin_lo, int j_bin_hi, int inter_zone,
+                              int required_tx, int nthreads);
+int nbnxm_b200_pairlist_sizes(const nbnxm_b200_grid_t* grid, int* nsci, int* ncj_packed, int* nexcl,
+                              long long* ncluster_pairs);
+int nbnxm_b200_pairlist_copy(const nbnxm_b200_grid_t* grid, nbnxm_b200_sci_t* sci, nbnxm_b200_cj_packed_t* cj_packed,
+                             nbnxm_b200_excl_t* excl);
+
+#ifdef __cplusplus
+}
+#endif
+#endif

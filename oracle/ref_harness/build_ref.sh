@@ -30,4 +30,10 @@ INC="$INC -isystem $REF/src/external/thread_mpi/include -isystem $REF/src/extern
 /usr/bin/g++ -O2 -std=c++17 -mavx2 -mfma -fopenmp -DGMX_DOUBLE=0 -DHAVE_CONFIG_H $INC \
     "$HERE/dump_nbnxm.cpp" "$REF/src/gromacs/nbnxm/tests/testsystem.cpp" \
     -L"$BLD/lib" -lgromacs -Wl,-rpath,"$BLD/lib" -o "$OUT/dump_nbnxm"
-echo "built $OUT/dump_nbnxm"
+/usr/bin/g++ -O2 -std=c++17 -mavx2 -mfma -fopenmp -DGMX_DOUBLE=0 -DHAVE_CONFIG_H $INC \
+    "$HERE/bench_ref.cpp" -L"$BLD/lib" -lgromacs -Wl,-rpath,'$ORIGIN/lib' -o "$OUT/bench_ref"
+# the timing harness travels to the GPU box with the reference's shared libraries beside it
+mkdir -p "$OUT/lib"
+cp -L "$BLD/lib/libgromacs.so.12" "$BLD/lib/libmuparser.so.2" "$OUT/lib/"
+strip --strip-unneeded "$OUT/lib/libgromacs.so.12" || true
+echo "built $OUT/dump_nbnxm $OUT/bench_ref"

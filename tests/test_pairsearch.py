@@ -1,0 +1,94 @@
+"""CPU tests of the host-side grid + pair-list builder (gromacs_b200/csrc/pairsearch.cpp): the lists it
+produces, walked by the oracle, must give the brute-force forces (every pair within the cut-off exactly
+once, exclusion and diagonal masks right), also when i-entries are split and when the system is cut
+into x-slabs with one-sided halos."""
+import numpy as np
+import pytest
+
+from util import load_golden, oracle_params, relrms
+
+
+def build(d, rlist, **kw):
+    from gromacs_b200.pairsearch import Grid
+    grid = Grid(d["sys_box"], d["sys_x"], nthreads=2)
+    nt = int(d["nbat_ntypes"][0])
+    nbat = grid.atomdata(d["sys_x"], d["sys_q"], d["sys_type"], d["nbat_nbfp"], nt, nbfp_comb=d["nbat_nbfp_comb"])
+    return grid, nbat
+
+
+def walk(oracle, p, nbat, plists, natoms, atom_index):
+    f = np.zeros((nbat.numAtoms(), 3))
+    e = np.zeros(2)
+    npairs = 0
+    for pl in plists:
+        fi, _, ei, n = oracle.forces(p, pl.sci, pl.cjPacked, pl.excl, nbat.xq, nbat.type,
+                                     np.zeros((nbat.numAtoms(), 2), np.float32), nbat.nbfp, nbat.nbfp_comb, nbat.shift_vec)
+        f += fi
+        e += ei
+        npairs += n
+    return oracle.nbat_to_atom_order(f, atom_index, natoms), e, npairs
+
+
+@pytest.mark.parametrize("case,rlist,min_sci", [("test243_ewald_cutnone", 0.9, 0), ("test243_ewald_cutnone", 0.93, 60),
+                                                ("bench1_ewald_cutnone", 1.0, 0), ("bench1_ewald_cutnone", 1.05, 500),
+                                                ("bench1_ewald_ljpmegeom", 0.95, 0)])
+def test_own_pairlist_covers_all_pairs_once(oracle, case, rlist, min_sci):
+    d = load_golden(case)
+    p = oracle_params(oracle, d)
+    grid, nbat = build(d, rlist)
+    pl = grid.pairlist(rlist, d["sys_excl_index"], d["sys_excl_atoms"], min_sci=min_sci)
+    n = d["sys_x"].shape[0]
+    assert grid.natoms_nbat % 64 == 0 and sorted(grid.atom_index[grid.atom_index >= 0].tolist()) == list(range(n))
+    # format invariants the kernels rely on
+    assert np.array_equal(pl.cjPacked[:, 4], pl.cjPacked[:, 6])            # both halves start identical
+    assert np.all(pl.excl[0] == 0xffffffff)
+    assert pl.sci[:, 2].min() >= 0 and pl.sci[:, 3].max() <= pl.cjPacked.shape[0]
+    if min_sci:
+        assert pl.sci.shape[0] >= min_sci // 2
+    f, e, npairs = walk(oracle, p, nbat, [pl], n, grid.atom_index)
+    fb, eb = oracle.brute_force(p, d["sys_x"], d["sys_q"], d["sys_type"], d["nbat_nbfp"], d["nbat_nbfp_comb"],
+                                d["sys_box"], d["sys_excl_index"], d["sys_excl_atoms"])
+    assert relrms(f, fb) < 1e-6
+    assert abs(e[0] - eb[0]) < 1e-6 * abs(eb[0]) + 1e-6 and abs(e[1] - eb[1]) < 1e-6 * abs(eb[1])
+    # and the same forces as the reference's own list for these coordinates
+    fr, _, er, npairs_ref = oracle.forces(p, d["pl_sci"], d["pl_cjPacked"], d["pl_excl"], d["nbat_xq"], d["nbat_type"],
+                                          d["nbat_lj_comb"], d["nbat_nbfp"], d["nbat_nbfp_comb"], d["shift_vec"])
+    fr = oracle.nbat_to_atom_order(fr, d["nbat_atom_index"], n)
+    assert relrms(f, fr) < 1e-6
+    if abs(rlist - float(d["rlist"][0])) < 1e-6:
+        # list quality: not more than 15 % larger than the reference's list at the same rlist
+        assert npairs < 1.15 * npairs_ref, (npairs, npairs_ref)
+
+
+@pytest.mark.parametrize("nslabs", [2, 3])
+def test_x_slab_lists_partition_the_pairs(oracle, nslabs):
+    """local (home x home) + non-local (home x +x-neighbour halo) lists over all slabs = the whole system."""
+    from gromacs_b200.slabs import slab_bin_ranges
+    d = load_golden("bench1_ewald_cutnone")
+    # a wider box so that 3 slabs are each wider than rlist: stack the unit box 4x along x
+    x = np.concatenate([d["sys_x"] + np.array([i * d["sys_box"][0], 0, 0], np.float32) for i in range(4)])
+    n0 = d["sys_x"].shape[0]
+    box = d["sys_box"] * np.array([4, 1, 1], np.float32)
+    q = np.tile(d["sys_q"], 4)
+    t = np.tile(d["sys_type"], 4)
+    ei = np.concatenate([d["sys_excl_index"][:-1] + i * d["sys_excl_atoms"].shape[0] for i in range(4)]
+                        + [[4 * d["sys_excl_atoms"].shape[0]]]).astype(np.int32)
+    ea = np.concatenate([d["sys_excl_atoms"] + i * n0 for i in range(4)]).astype(np.int32)
+    dd = dict(d)
+    dd.update(sys_x=x, sys_box=box, sys_q=q, sys_type=t)
+    rlist = 1.0
+    p = oracle_params(oracle, d)
+    grid, nbat = build(dd, rlist)
+    whole = grid.pairlist(rlist, ei, ea)
+    f_ref, e_ref, n_ref = walk(oracle, p, nbat, [whole], x.shape[0], grid.atom_index)
+    lists = []
+    for r in range(nslabs):
+        home, halo, tx = slab_bin_ranges(grid, nslabs, r, rlist)
+        lists.append(grid.pairlist(rlist, ei, ea, bins=home, j_bins=home))
+        lists.append(grid.pairlist(rlist, ei, ea, bins=home, j_bins=halo, inter_zone=True, required_tx=tx))
+        # the halo is a contiguous range of whole columns of the next slab
+        assert halo[0] < halo[1]
+    f, e, n = walk(oracle, p, nbat, lists, x.shape[0], grid.atom_index)
+    # (x + shift) is rounded to float per image, so a pair seen from the other side differs by ~1e-7
+    assert relrms(f, f_ref) < 1e-6
+    assert abs(e[1] - e_ref[1]) < 1e-7 * abs(e_ref[1])
