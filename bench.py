@@ -167,6 +167,7 @@ def main():
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-l2-flush", action="store_true")
+    ap.add_argument("--min-sci", type=int, default=0, help="override gpu_min_ci_balanced (list splitting target)")
     args = ap.parse_args()
     if args.workload is None:
         args.workload = DEFAULT_WORKLOAD if args.gpus == 1 else "water1536k"
@@ -201,7 +202,7 @@ def main():
     nbat.f = f_pin.numpy()
 
     nb = NbnxmGpu(wl.params, nbat, device=local_rank)
-    plist = wl.pairlist(min_sci=nb.gpu_min_ci_balanced())
+    plist = wl.pairlist(min_sci=args.min_sci or nb.gpu_min_ci_balanced())
     nb.gpu_init_atomdata(nbat)
     nb.gpu_init_pairlist(plist, LOCAL)
     nb.setupGpuShortRangeWork(LOCAL)

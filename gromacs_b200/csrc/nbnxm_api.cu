@@ -13,6 +13,7 @@
 
 #include "nbnxm_device.cuh"
 #include "nbnxm_force_kernel.cuh"
+#include "nbnxm_handle.cuh"
 
 namespace nbb
 {
@@ -41,9 +42,8 @@ ForceKernelPtr select_force_kernel(int elec, int vdw, bool energy, bool prune)
 
 using namespace nbb;
 
-namespace
+namespace nbb
 {
-
 thread_local char g_lastError[512] = "";
 
 int fail(const char* fmt, ...)
@@ -54,154 +54,7 @@ int fail(const char* fmt, ...)
     va_end(ap);
     return 1;
 }
-
-#define CU(call)                                                                                      \
-    do                                                                                                \
-    {                                                                                                 \
-        cudaError_t e_ = (call);                                                                      \
-        if (e_ != cudaSuccess)                                                                        \
-        {                                                                                             \
-            return fail("%s:%d %s failed: %s", __FILE__, __LINE__, #call, cudaGetErrorString(e_));    \
-        }                                                                                             \
-    } while (0)
-
-template<typename T>
-struct DevBuf
-{
-    T*     p     = nullptr;
-    size_t n     = 0;
-    size_t alloc = 0;
-    /* grow-only reallocation with 20 % slack, contents are not preserved
-     * (reallocateDeviceBuffer, src/gromacs/gpu_utils/devicebuffer.h) */
-    cudaError_t reserve(size_t count)
-    {
-        n = count;
-        if (count <= alloc)
-        {
-            return cudaSuccess;
-        }
-        if (p)
-        {
-            cudaFree(p);
-            p = nullptr;
-        }
-        alloc         = count + count / 5 + 64;
-        cudaError_t e = cudaMalloc(&p, alloc * sizeof(T));
-        if (e != cudaSuccess)
-        {
-            alloc = 0;
-            n     = 0;
-        }
-        return e;
-    }
-    void release()
-    {
-        if (p) cudaFree(p);
-        p     = nullptr;
-        n     = 0;
-        alloc = 0;
-    }
-};
-
-struct PairList
-{
-    DevBuf<nbnxm_b200_sci_t>       sci, sciSorted;
-    DevBuf<int>                    sciCount, sciHistogram, sciOffset, rollingPart;
-    DevBuf<nbnxm_b200_cj_packed_t> cjPacked;
-    DevBuf<unsigned int>           imaskOuter;
-    DevBuf<nbnxm_b200_excl_t>      excl;
-    DevBuf<unsigned long long>     pairCount;
-    int                            numSci               = 0;
-    int                            naCi                 = -1;
-    bool                           haveFreshList        = false;
-    int                            rollingNumParts      = 0;
-    bool                           didPrune             = false;
-    bool                           didRollingPrune      = false;
-
-    PairlistDev dev(bool counting) const
-    {
-        PairlistDev d;
-        d.sci          = sci.p;
-        d.sciSorted    = sciSorted.p;
-        d.sciCount     = sciCount.p;
-        d.sciHistogram = sciHistogram.p;
-        d.sciOffset    = sciOffset.p;
-        d.cjPacked     = cjPacked.p;
-        d.imaskOuter   = imaskOuter.p;
-        d.excl         = excl.p;
-        d.rollingPart  = rollingPart.p;
-        d.pairCount    = counting ? pairCount.p : nullptr;
-        d.numSci       = numSci;
-        return d;
-    }
-};
-
-struct TimedRegion
-{
-    cudaEvent_t start, stop;
-    int         kind; /* 0..3 force[prune][energy], 4 prune, 5 rolling prune, 6 xq h2d, 7 f d2h, 8 pairlist h2d */
-};
-
-} // namespace
-
-struct nbnxm_b200
-{
-    int                 device = 0;
-    cudaStream_t        stream[2]    = { nullptr, nullptr };
-    bool                ownStream[2] = { false, false };
-    bool                localAndNonlocal = false;
-    nbnxm_b200_params_t params{};
-    int                 numTypes = 0;
-    int                 numSMs   = 0;
-
-    DevBuf<float4> xq, f4;
-    DevBuf<float>  f3;
-    DevBuf<int>    atomType;
-    DevBuf<float2> ljComb;
-    DevBuf<float>  shiftVec;
-    DevBuf<double> fshift, energy;
-    DevBuf<float2> nbfp, nbfpComb;
-    DevBuf<float>  coulombTab;
-    bool           shiftVecUploaded = false;
-    int            natoms = 0, natomsLocal = 0;
-
-    /* x buffer ops (one entry per grid) */
-    struct XGrid
-    {
-        int first = 0, n = 0;
-    };
-    std::vector<XGrid> xgrids;
-    DevBuf<int>        atomIndex;
-
-    PairList plist[2];
-    bool     haveWork[2] = { false, false };
-
-    double* h_fshift = nullptr; /* pinned staging, NBStagingData (gpu_types_common.h:142) */
-    double* h_energy = nullptr;
-
-    cudaEvent_t nonlocalDone = nullptr, localH2DDone = nullptr;
-
-    bool                     doTiming = false;
-    std::vector<TimedRegion> regions;
-    nbnxm_b200_timings_t     timings{};
-    bool                     pairCounting = false;
-    long long                launches     = 0;
-
-    ParamsDev   pd{};
-    AtomDataDev ad() const
-    {
-        AtomDataDev a;
-        a.xq       = xq.p;
-        a.f4       = f4.p;
-        a.atomType = atomType.p;
-        a.ljComb   = ljComb.p;
-        a.shiftVec = shiftVec.p;
-        a.fshift   = fshift.p;
-        a.energy   = energy.p;
-        a.numTypes = numTypes;
-        return a;
-    }
-};
+} // namespace nbb
 
 namespace
 {
@@ -287,7 +140,7 @@ bool canSkipNonbondedWork(const nbnxm_b200* nb, int iloc) { return iloc == 1 && 
 
 extern "C" {
 
-const char* nbnxm_b200_last_error(void) { return g_lastError; }
+const char* nbnxm_b200_last_error(void) { return nbb::g_lastError; }
 
 int nbnxm_b200_init(nbnxm_b200_t** out, int device, const nbnxm_b200_params_t* params, int ntypes, const float* nbfp,
                     const float* nbfp_comb, const float* coulomb_tab, int coulomb_tab_size, int local_and_nonlocal,
@@ -384,6 +237,7 @@ int nbnxm_b200_free(nbnxm_b200_t* nb)
     if (!nb) return 0;
     cudaSetDevice(nb->device);
     cudaDeviceSynchronize();
+    nbnxm_b200_halo_free(nb);
     collectTimings(nb);
     nb->xq.release(); nb->f4.release(); nb->f3.release(); nb->atomType.release(); nb->ljComb.release();
     nb->shiftVec.release(); nb->fshift.release(); nb->energy.release(); nb->nbfp.release();
@@ -692,8 +546,8 @@ int nbnxm_b200_launch_kernel(nbnxm_b200_t* nb, int iloc, int compute_energy, int
         return fail("nbnxm_b200_launch_kernel: no kernel for elec_type %d vdw_type %d", nb->params.elec_type, nb->params.vdw_type);
     }
     beginRegion(nb, (doPrune ? 2 : 0) + (compute_energy ? 1 : 0), st);
-    const int blocks = (pl.numSci + c_forceWarpsPerBlock - 1) / c_forceWarpsPerBlock;
-    kernel<<<blocks, c_forceThreads, 0, st>>>(nb->ad(), nb->pd, pl.dev(nb->pairCounting), compute_virial != 0);
+    /* one 32-thread CTA per sci entry */
+    kernel<<<pl.numSci, 32, 0, st>>>(nb->ad(), nb->pd, pl.dev(nb->pairCounting), compute_virial != 0);
     nb->launches++;
     if (doPrune)
     {
@@ -827,9 +681,10 @@ int nbnxm_b200_have_short_range_work(const nbnxm_b200_t* nb, int iloc) { return 
 
 int nbnxm_b200_min_ci_balanced(const nbnxm_b200_t* nb)
 {
-    /* enough sci entries for two full waves of the one-warp-per-entry force kernel at 16 warps/SM
-     * (the reference uses 61 x #SM 64-thread blocks, cuda/nbnxm_cuda_data_mgmt.cu:95-130) */
-    return nb ? 32 * nb->numSMs : 0;
+    /* one warp per sci entry, up to ~24 resident warps per SM: aim at several waves of entries so that the
+     * sorted (largest first) schedule can even out the tail; the list builder splits long entries to get
+     * there (the reference uses 61 x #SM 64-thread blocks, cuda/nbnxm_cuda_data_mgmt.cu:95-130) */
+    return nb ? 128 * nb->numSMs : 0;
 }
 int nbnxm_b200_is_kernel_ewald_analytical(const nbnxm_b200_t* nb)
 {

@@ -77,6 +77,19 @@ __device__ __forceinline__ void red_add_v4(float4* addr, float x, float y, float
                  : "memory");
 }
 
+/* the same, issued only where `doIt` is set: a predicated instruction instead of a divergent branch */
+__device__ __forceinline__ void red_add_v4_if(const bool doIt, float4* addr, float x, float y, float z)
+{
+    asm volatile(
+            "{\n\t"
+            ".reg .pred p;\n\t"
+            "setp.ne.s32 p, %5, 0;\n\t"
+            "@p red.global.add.v4.f32 [%0], {%1, %2, %3, %4};\n\t"
+            "}" ::"l"(addr),
+            "f"(x), "f"(y), "f"(z), "f"(0.0f), "r"(static_cast<int>(doIt))
+            : "memory");
+}
+
 __device__ __forceinline__ float norm2_fma(float dx, float dy, float dz)
 {
     // fixed evaluation order; the prune masks are defined on exactly this expression

@@ -4,13 +4,18 @@
  * src/gromacs/nbnxm/nbnxm_kernel_utils.h:56-289); written from scratch for sm_100a.
  *
  * Work decomposition (differs from the reference on purpose):
- *   - one WARP per sci entry (i-super-cluster work unit), several independent warps per CTA, no
- *     block-level synchronisation;
- *   - lane = il + 8*jl: the lane owns i-atom `il` of every i-cluster and the TWO j-atoms jl and jl+4 of
- *     the current j-cluster, i.e. both halves of the reference's "cluster-pair split"
- *     (imei[0], imei[1]) are evaluated by the same warp as two independent pair streams;
- *   - i-atom coordinates/parameters are staged once per sci entry in shared memory (one 128-byte
- *     conflict-free LDS.128 per i-cluster step, shared by both pair streams);
+ *   - one WARP = one 32-thread CTA per sci entry (i-super-cluster work unit): per-entry data is
+ *     CTA-uniform (uniform registers / predicates, no convergence barriers), no block-level
+ *     synchronisation;
+ *   - lane = il + 8*jl owns i-atom `il` of every i-cluster; the unit of work is one (j-cluster, half)
+ *     = 8 i-atoms x 4 j-atoms per i-cluster, i.e. exactly one imask bit per i-cluster, one pair per
+ *     lane.  The two halves of the reference's "cluster-pair split" (imei[0], imei[1]) are walked one
+ *     after the other by the same warp, so a half whose bit was pruned costs nothing;
+ *   - the (j-cluster, half) loop is NOT unrolled and the i-cluster loop is (i forces live in registers):
+ *     the hot loop stays inside the 32 KB instruction cache;
+ *   - i-atom coordinates/parameters are staged once per sci entry in shared memory; the 32 j-atoms of a
+ *     cjPacked group are fetched by one coalesced 16-byte load per lane, one group ahead, and parked in
+ *     shared memory (conflict-free LDS.128 broadcasts in the pair loop);
  *   - j forces are reduced over the 8 il-lanes by shuffles and added with one
  *     red.global.add.v4.f32 per j-atom; i forces are kept in registers for the whole sci entry.
  */
@@ -22,8 +27,11 @@
 namespace nbb
 {
 
-constexpr int c_forceWarpsPerBlock = 4;
-constexpr int c_forceThreads       = c_forceWarpsPerBlock * 32;
+/* one warp per CTA; resident CTAs per SM the kernels are compiled for (register budget 65536 / 32 / N) */
+#ifndef NBNXM_FORCE_MIN_BLOCKS
+#    define NBNXM_FORCE_MIN_BLOCKS 20
+#endif
+constexpr int c_forceMinBlocksPerSM = NBNXM_FORCE_MIN_BLOCKS;
 
 template<int ELEC, int VDW, bool ENERGY>
 struct Flavor
@@ -62,7 +70,17 @@ __device__ __forceinline__ float pme_corr_f(const float z2)
     num       = fmaf(num, z2, -0.019278317264888380590f);
     num       = fmaf(num, z2, 0.069670166153766424023f);
     num       = fmaf(num, z2, -0.75225204789749321333f);
-    return __fdividef(num, den);
+    /* den >= 1: the plain approximate reciprocal needs no range fix-up */
+    float rden;
+    asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(rden) : "f"(den));
+    return num * rden;
+}
+
+__device__ __forceinline__ float rsqrt_approx(const float x)
+{
+    float y;
+    asm("rsqrt.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x));
+    return y;
 }
 
 struct PairConsts
@@ -85,8 +103,18 @@ __device__ __forceinline__ float pair_force(const ParamsDev& p,
                                             float&            eEl)
 {
     using Fl = Flavor<ELEC, VDW, ENERGY>;
+    /* In the energy kernels qq = qi*qj comes without the electric conversion factor: the Coulomb energy is
+     * a small residual of large terms of both signs, and a factor rounded into every i-charge would be a
+     * systematic relative error on those terms.  The factor is applied to the double-precision total. */
+    const float qqF   = ENERGY ? qq * p.epsfac : qq;
     r2                = fmaxf(r2, c_minDistanceSquared);
-    const float invR  = rsqrtf(r2);
+    float invR = rsqrt_approx(r2);
+    if (ENERGY)
+    {
+        /* one Newton-Raphson step: the energy totals are sums with heavy cancellation and need pair
+         * energies good to an ulp to stay within 1e-6 relative */
+        invR = invR * fmaf(-0.5f * r2 * invR, invR, 1.5f);
+    }
     const float invR2 = invR * invR;
     float       invR6 = invR2 * invR2 * invR2;
     if (Fl::exclusionForces)
@@ -152,17 +180,17 @@ __device__ __forceinline__ float pair_force(const ParamsDev& p,
 
     if (Fl::elecCut)
     {
-        fInvR += qq * (Fl::exclusionForces ? intBit : 1.0f) * invR2 * invR;
+        fInvR += qqF * (Fl::exclusionForces ? intBit : 1.0f) * invR2 * invR;
         if (ENERGY) eEl += qq * (intBit * invR - p.c_rf);
     }
     if (Fl::elecRF)
     {
-        fInvR += qq * (intBit * invR2 * invR - p.two_k_rf);
+        fInvR += qqF * (intBit * invR2 * invR - p.two_k_rf);
         if (ENERGY) eEl += qq * (intBit * invR + 0.5f * p.two_k_rf * r2 - p.c_rf);
     }
     if (Fl::ewaldAna)
     {
-        fInvR += qq * (intBit * invR2 * invR + pme_corr_f(k.beta2 * r2) * k.beta3);
+        fInvR += qqF * (intBit * invR2 * invR + pme_corr_f(k.beta2 * r2) * k.beta3);
     }
     if (Fl::ewaldTab)
     {
@@ -172,7 +200,7 @@ __device__ __forceinline__ float pair_force(const ParamsDev& p,
         const float fraction   = normalized - index;
         const float left       = __ldg(p.coulombTab + index);
         const float right      = __ldg(p.coulombTab + index + 1);
-        fInvR += qq * (intBit * invR2 - fmaf(fraction, right - left, left)) * invR;
+        fInvR += qqF * (intBit * invR2 - fmaf(fraction, right - left, left)) * invR;
     }
     if (Fl::ewaldAny && ENERGY)
     {
@@ -230,29 +258,115 @@ __device__ __forceinline__ void lj_pair_params(const ParamsDev& p,
     }
 }
 
+/* Dynamic-index read of one of four registers without local memory. */
+__device__ __forceinline__ unsigned select4(const unsigned a, const unsigned b, const unsigned c, const unsigned d, const int i)
+{
+    const unsigned lo = (i & 1) ? b : a;
+    const unsigned hi = (i & 1) ? d : c;
+    return (i & 2) ? hi : lo;
+}
+
+/* One (j-cluster, half) against the i-clusters whose bits are set in m8: one atom pair per lane and
+ * i-cluster.  EXCL = false is the fast path for groups without exclusion masks (excl_ind == 0, entry 0
+ * of the exclusion array is all ones): no per-pair mask evaluation and no diagonal test - the diagonal
+ * cluster pair always carries an exclusion mask (pairlist.cpp:651-688). */
+template<int ELEC, int VDW, bool ENERGY, bool PRUNE, bool EXCL>
+__device__ __forceinline__ void cluster_half(const ParamsDev&  p,
+                                             const PairConsts& k,
+                                             const float4*     xqi,
+                                             const float2*     lji,
+                                             const float4      xj,
+                                             const float2      pj,
+                                             const unsigned    m8,
+                                             const unsigned    wex8,
+                                             const bool        nonSelf,
+                                             const int         ciDiag,
+                                             const float       rlistOuter2,
+                                             float3 (&fi)[c_superClusterSize],
+                                             float3&   fj,
+                                             float&    eLJj,
+                                             float&    eElj,
+                                             unsigned& keep8)
+{
+    using Fl                  = Flavor<ELEC, VDW, ENERGY>;
+    constexpr unsigned c_full = 0xffffffffu;
+    const int          tj     = __float_as_int(pj.x);
+#pragma unroll
+    for (int ci = 0; ci < c_superClusterSize; ci++)
+    {
+        if (m8 & (1u << ci))
+        {
+            const float4 xi = xqi[ci * c_clusterSize];
+            const float  dx = xi.x - xj.x, dy = xi.y - xj.y, dz = xi.z - xj.z;
+            const float  r2 = norm2_fma(dx, dy, dz);
+            if (PRUNE)
+            {
+                /* clear the bit of a (cluster pair, half) with no atom pair inside rlistOuter
+                 * (nbnxm_cuda_kernel.cuh:495-503) */
+                if (!__any_sync(c_full, r2 < rlistOuter2)) keep8 &= ~(1u << ci);
+            }
+            const float intBit = (!EXCL || (wex8 & (1u << ci))) ? 1.0f : 0.0f;
+            bool        within;
+            if (!EXCL)
+            {
+                within = (r2 < k.rc2);
+            }
+            else if (Fl::exclusionForces)
+            {
+                within = (r2 < k.rc2) && (nonSelf || ciDiag != ci);
+            }
+            else
+            {
+                within = (r2 < k.rc2) && (intBit != 0.0f);
+            }
+            const float2 pi  = lji[ci * c_clusterSize];
+            const int    tiN = __float_as_int(pi.x), ti = __float_as_int(pi.y);
+            float        c6, c12, c6g;
+            lj_pair_params<ELEC, VDW, ENERGY>(p, pi, pj, tiN, ti, tj, c6, c12, c6g);
+            float ePairLJ = 0.0f, ePairEl = 0.0f;
+            float F = pair_force<ELEC, VDW, ENERGY>(p, k, r2, xi.w * xj.w, c6, c12, c6g, intBit, ePairLJ, ePairEl);
+            F       = within ? F : 0.0f;
+            if (ENERGY)
+            {
+                eLJj += within ? ePairLJ : 0.0f;
+                eElj += within ? ePairEl : 0.0f;
+            }
+            fi[ci].x = fmaf(F, dx, fi[ci].x);
+            fi[ci].y = fmaf(F, dy, fi[ci].y);
+            fi[ci].z = fmaf(F, dz, fi[ci].z);
+            fj.x     = fmaf(-F, dx, fj.x);
+            fj.y     = fmaf(-F, dy, fj.y);
+            fj.z     = fmaf(-F, dz, fj.z);
+        }
+    }
+}
+
+/* One warp = one CTA = one sci entry.  With 32-thread CTAs everything that is per-entry (list masks,
+ * cluster indices, loop trip counts) is CTA-uniform, which lets the compiler keep it in uniform
+ * registers and branch on uniform predicates without convergence barriers. */
 template<int ELEC, int VDW, bool ENERGY, bool PRUNE>
-__global__ void __launch_bounds__(c_forceThreads)
+__global__ void __launch_bounds__(32, (ENERGY || PRUNE) ? c_forceMinBlocksPerSM - 4 : c_forceMinBlocksPerSM)
         nbnxm_force_kernel(const AtomDataDev ad, const ParamsDev p, const PairlistDev pl, const int calcFshift)
 {
-    using Fl                 = Flavor<ELEC, VDW, ENERGY>;
+    using Fl                  = Flavor<ELEC, VDW, ENERGY>;
     constexpr unsigned c_full = 0xffffffffu;
+    /* the energy kernels carry one general pair path only: two copies would not fit the instruction cache */
+    constexpr bool c_fastPath = !ENERGY && !PRUNE;
 
-    const int lane = threadIdx.x & 31;
-    const int warp = threadIdx.x >> 5;
-    const int il   = lane & 7;
-    const int jl   = lane >> 3;
-
-    const int sciIdx = blockIdx.x * c_forceWarpsPerBlock + warp;
-    if (sciIdx >= pl.numSci)
-    {
-        return;
-    }
+    const int lane   = threadIdx.x;
+    const int il     = lane & 7;
+    const int jl     = lane >> 3;
+    const int sciIdx = blockIdx.x;
     /* The fused force+prune variant produces the counts the sort consumes, so it walks the
      * unsorted list (same rule as nbnxm_cuda_kernel.cuh:158-166). */
     const nbnxm_b200_sci_t s = PRUNE ? pl.sci[sciIdx] : pl.sciSorted[sciIdx];
 
-    __shared__ float4 sm_xqi[c_forceWarpsPerBlock][64];
-    __shared__ float2 sm_lji[c_forceWarpsPerBlock][64]; // comb params, or (type*numTypes, type) as int bits
+    /* staging areas: the 64 i-atoms of the entry (for its whole lifetime) and the 32 j-atoms of the
+     * current cjPacked group */
+    __shared__ float4 sm_xqi[64];
+    __shared__ float2 sm_lji[64]; // comb params, or (type*numTypes, type) as int bits
+    __shared__ float4 sm_xqj[32];
+    __shared__ float4 sm_ljj[32]; // (c6, c12) or (type as int bits, -), then the global atom index
 
     const float shx = ad.shiftVec[3 * s.shift], shy = ad.shiftVec[3 * s.shift + 1], shz = ad.shiftVec[3 * s.shift + 2];
 
@@ -266,8 +380,8 @@ __global__ void __launch_bounds__(c_forceThreads)
     k.ljeCoeff2   = p.ewaldcoeff_lj * p.ewaldcoeff_lj;
     k.ljeCoeff6_6 = k.ljeCoeff2 * k.ljeCoeff2 * k.ljeCoeff2 * c_oneSixth;
 
-    /* energies: float partial sums per j-cluster, double across the sci entry, so that the totals keep
-     * 1e-6 relative accuracy (the reference accumulates in float, gpu_common.h:151-161) */
+    /* energies: float partial sums per j-cluster half, double across the sci entry, so that the totals
+     * keep 1e-6 relative accuracy (the reference accumulates in float, gpu_common.h:151-161) */
     double eLJ = 0.0, eEl = 0.0;
     const bool diagonalEntry = (s.shift == c_centralShiftIndex && s.cj_packed_begin < s.cj_packed_end
                                 && pl.cjPacked[s.cj_packed_begin].cj[0] == s.sci * c_superClusterSize);
@@ -280,9 +394,9 @@ __global__ void __launch_bounds__(c_forceThreads)
         if (ENERGY && Fl::exclusionForces && diagonalEntry)
         {
             /* self terms, once per diagonal sci entry (nbnxm_cuda_kernel.cuh:383-417) */
-            const float q2 = p.epsfac * v.w * v.w;
-            if (Fl::ewaldAny) eEl -= q2 * p.ewald_beta * 0.56418958354775628695f;
-            if (Fl::elecRF || Fl::elecCut) eEl -= q2 * 0.5f * p.c_rf;
+            const double q2 = static_cast<double>(v.w) * v.w;
+            if (Fl::ewaldAny) eEl -= q2 * p.ewald_beta * 0.56418958354775628695;
+            if (Fl::elecRF || Fl::elecCut) eEl -= q2 * 0.5 * p.c_rf;
             if (Fl::ljEwald)
             {
                 eLJ += __ldg(p.nbfp + ad.atomType[ai] * (ad.numTypes + 1)).x * 0.5f * c_oneSixth * k.ljeCoeff6_6;
@@ -291,19 +405,21 @@ __global__ void __launch_bounds__(c_forceThreads)
         v.x += shx;
         v.y += shy;
         v.z += shz;
-        v.w *= p.epsfac;
-        sm_xqi[warp][lane + 32 * h] = v;
+        if (!ENERGY)
+        {
+            v.w *= p.epsfac;
+        }
+        sm_xqi[lane + 32 * h] = v;
         if (Fl::ljComb)
         {
-            sm_lji[warp][lane + 32 * h] = ad.ljComb[ai];
+            sm_lji[lane + 32 * h] = ad.ljComb[ai];
         }
         else
         {
-            const int t                 = ad.atomType[ai];
-            sm_lji[warp][lane + 32 * h] = make_float2(__int_as_float(t * ad.numTypes), __int_as_float(t));
+            const int t           = ad.atomType[ai];
+            sm_lji[lane + 32 * h] = make_float2(__int_as_float(t * ad.numTypes), __int_as_float(t));
         }
     }
-    __syncwarp();
 
     float3 fi[c_superClusterSize];
 #pragma unroll
@@ -312,120 +428,128 @@ __global__ void __launch_bounds__(c_forceThreads)
         fi[ci] = make_float3(0.0f, 0.0f, 0.0f);
     }
 
-    /* j <= i within the same cluster on the central shift is the "Newton" half of the diagonal
-     * cluster pair and the self pair (nbnxm_cuda_kernel.cuh:421-423) */
-    const bool nonSelf0 = !(s.shift == c_centralShiftIndex && jl <= il);
-    const bool nonSelf1 = !(s.shift == c_centralShiftIndex && jl + 4 <= il);
+    const bool         centralShift = (s.shift == c_centralShiftIndex);
+    const float        rlistOuter2  = p.rlist_outer_sq;
+    int                prunedCount  = 0;
+    unsigned long long pairCount    = 0;
 
-    const float        rlistOuter2 = p.rlist_outer_sq;
-    int                prunedCount = 0;
-    unsigned long long pairCount   = 0;
-
-    for (int jp = s.cj_packed_begin; jp < s.cj_packed_end; jp++)
+    /* Software pipeline over the cjPacked groups of the entry: group descriptors (32 bytes, CTA-uniform
+     * loads) are fetched two groups ahead, the 32 j-atoms of a group one group ahead - lane L fetches
+     * atom (L & 7) of j-cluster (L >> 3), one coalesced 16-byte load per lane - and parked in shared
+     * memory, together with their LJ parameters and global index, for the (half, j-cluster) loop. */
+    const uint4* cjGroups = reinterpret_cast<const uint4*>(pl.cjPacked);
+    int          jp       = s.cj_packed_begin;
+    const uint4  zero4    = make_uint4(0u, 0u, 0u, 0u);
+    uint4        cjNext = zero4, meNext = zero4, cjNext2 = zero4, meNext2 = zero4;
+    if (jp < s.cj_packed_end)
     {
-        const int4 cjv = *reinterpret_cast<const int4*>(pl.cjPacked[jp].cj);
-        const int4 mev = *reinterpret_cast<const int4*>(pl.cjPacked[jp].imei);
-        unsigned   imask0 = static_cast<unsigned>(mev.x), imask1 = static_cast<unsigned>(mev.z);
-        const unsigned imaskAny = imask0 | imask1;
-        if (imaskAny == 0u)
+        cjNext = cjGroups[2 * jp];
+        meNext = cjGroups[2 * jp + 1];
+    }
+    if (jp + 1 < s.cj_packed_end)
+    {
+        cjNext2 = cjGroups[2 * jp + 2];
+        meNext2 = cjGroups[2 * jp + 3];
+    }
+    float4 xjNext = make_float4(0.0f, 0.0f, 0.0f, 0.0f);
+    float4 pjNext = make_float4(0.0f, 0.0f, 0.0f, 0.0f); /* (c6, c12) or (type, -), then the atom index */
+
+    auto fetchAtoms = [&](const uint4 cjv, const uint4 mev, float4& xj, float4& pj) {
+        /* unused slots of a partially filled group have no mask bits and an unspecified index */
+        if ((mev.x | mev.z) & (0xffu << (8 * jl)))
+        {
+            const int aj = static_cast<int>(select4(cjv.x, cjv.y, cjv.z, cjv.w, jl)) * c_clusterSize + il;
+            xj           = ad.xq[aj];
+            if (Fl::ljComb)
+            {
+                const float2 c = ad.ljComb[aj];
+                pj.x           = c.x;
+                pj.y           = c.y;
+            }
+            else
+            {
+                pj.x = __int_as_float(ad.atomType[aj]);
+            }
+            pj.z = __int_as_float(aj);
+        }
+    };
+    fetchAtoms(cjNext, meNext, xjNext, pjNext);
+
+    const float4* xqiLane = sm_xqi + il;
+    const float2* ljiLane = sm_lji + il;
+
+    for (; jp < s.cj_packed_end; jp++)
+    {
+        const uint4 mev = meNext;
+        __syncwarp();
+        sm_xqj[lane] = xjNext;
+        sm_ljj[lane] = pjNext;
+        __syncwarp();
+        cjNext = cjNext2;
+        meNext = meNext2;
+        if (jp + 2 < s.cj_packed_end)
+        {
+            cjNext2 = cjGroups[2 * jp + 4];
+            meNext2 = cjGroups[2 * jp + 5];
+        }
+        else
+        {
+            meNext2 = zero4;
+        }
+        fetchAtoms(cjNext, meNext, xjNext, pjNext);
+
+        if ((mev.x | mev.z) == 0u)
         {
             continue;
         }
-        const unsigned wexcl0 = pl.excl[mev.y].pair[lane];
-        const unsigned wexcl1 = pl.excl[mev.w].pair[lane];
-        const unsigned on0all = imask0, on1all = imask1;
         if (pl.pairCount != nullptr)
         {
-            pairCount += 32ull * (__popc(imask0) + __popc(imask1));
+            pairCount += 32ull * (__popc(mev.x) + __popc(mev.z));
         }
-        const int cjs[4] = { cjv.x, cjv.y, cjv.z, cjv.w };
+        unsigned keep0 = mev.x, keep1 = mev.z;
 
-#pragma unroll
-        for (int jm = 0; jm < c_jGroupSize; jm++)
+        /* the two halves of the cluster-pair split one after the other; within a half one iteration per
+         * j-cluster: 8 i-atoms x 4 j-atoms per i-cluster, one pair per lane */
+#pragma unroll 1
+        for (int half = 0; half < 2; half++)
         {
-            if (imaskAny & (0xffu << (jm * 8)))
+            unsigned  cur     = half ? mev.z : mev.x;
+            const int exclInd = static_cast<int>(half ? mev.w : mev.y);
+            /* entry 0 of the exclusion array is all ones (pairlist.h:274-287) */
+            unsigned      wex    = (exclInd != 0 && cur != 0u) ? pl.excl[exclInd].pair[lane] : c_full;
+            const float4* xqjPtr = sm_xqj + half * 4 + jl;
+            const float4* ljjPtr = sm_ljj + half * 4 + jl;
+            /* j <= i within the same cluster on the central shift is the "Newton" half of the
+             * diagonal cluster pair and the self pair (nbnxm_cuda_kernel.cuh:421-423) */
+            const bool nonSelf = !(centralShift && (half * 4 + jl) <= il);
+            unsigned   cleared = 0u;
+#pragma unroll 1
+            for (int shift = 0; cur != 0u; cur >>= 8, wex >>= 8, xqjPtr += c_clusterSize, ljjPtr += c_clusterSize, shift += 8)
             {
-                const int    cj  = cjs[jm];
-                const int    aj0 = cj * c_clusterSize + jl;
-                const int    aj1 = aj0 + 4;
-                const float4 xj0 = ad.xq[aj0];
-                const float4 xj1 = ad.xq[aj1];
-                float2       pj0 = make_float2(0.0f, 0.0f), pj1 = make_float2(0.0f, 0.0f);
-                int          tj0 = 0, tj1 = 0;
-                if (Fl::ljComb)
+                const unsigned m8 = cur & 0xffu;
+                if (m8 == 0u)
                 {
-                    pj0 = ad.ljComb[aj0];
-                    pj1 = ad.ljComb[aj1];
+                    continue;
+                }
+                const float4 xj  = *xqjPtr;
+                const float4 pjv = *ljjPtr;
+                const float2 pj  = make_float2(pjv.x, pjv.y);
+                const int    aj  = __float_as_int(pjv.z);
+                float3       fj  = make_float3(0.0f, 0.0f, 0.0f);
+                float        eLJj = 0.0f, eElj = 0.0f;
+                unsigned     keep8 = m8;
+
+                if (c_fastPath && exclInd == 0)
+                {
+                    cluster_half<ELEC, VDW, ENERGY, PRUNE, false>(p, k, xqiLane, ljiLane, xj, pj, m8, 0xffu, true, -1,
+                                                                   rlistOuter2, fi, fj, eLJj, eElj, keep8);
                 }
                 else
                 {
-                    tj0 = ad.atomType[aj0];
-                    tj1 = ad.atomType[aj1];
-                }
-                float3 fj0 = make_float3(0.0f, 0.0f, 0.0f), fj1 = make_float3(0.0f, 0.0f, 0.0f);
-                float  eLJj = 0.0f, eElj = 0.0f;
-
-#pragma unroll
-                for (int ci = 0; ci < c_superClusterSize; ci++)
-                {
-                    const unsigned bit = 1u << (jm * 8 + ci);
-                    if (imaskAny & bit)
-                    {
-                        const float4 xi  = sm_xqi[warp][ci * 8 + il];
-                        const float  dx0 = xi.x - xj0.x, dy0 = xi.y - xj0.y, dz0 = xi.z - xj0.z;
-                        const float  dx1 = xi.x - xj1.x, dy1 = xi.y - xj1.y, dz1 = xi.z - xj1.z;
-                        const float  r20 = norm2_fma(dx0, dy0, dz0);
-                        const float  r21 = norm2_fma(dx1, dy1, dz1);
-                        const bool   on0 = (on0all & bit) != 0u, on1 = (on1all & bit) != 0u;
-                        if (PRUNE)
-                        {
-                            /* clear the bit of a (cluster pair, half) with no atom pair inside
-                             * rlistOuter (nbnxm_cuda_kernel.cuh:495-503) */
-                            if (on0 && !__any_sync(c_full, r20 < rlistOuter2)) imask0 &= ~bit;
-                            if (on1 && !__any_sync(c_full, r21 < rlistOuter2)) imask1 &= ~bit;
-                        }
-                        const float intBit0 = (wexcl0 & bit) ? 1.0f : 0.0f;
-                        const float intBit1 = (wexcl1 & bit) ? 1.0f : 0.0f;
-                        bool        within0, within1;
-                        if (Fl::exclusionForces)
-                        {
-                            const bool offDiagonal = (cj != s.sci * c_superClusterSize + ci);
-                            within0                = on0 && (r20 < k.rc2) && (nonSelf0 || offDiagonal);
-                            within1                = on1 && (r21 < k.rc2) && (nonSelf1 || offDiagonal);
-                        }
-                        else
-                        {
-                            within0 = on0 && (r20 < k.rc2) && (intBit0 != 0.0f);
-                            within1 = on1 && (r21 < k.rc2) && (intBit1 != 0.0f);
-                        }
-                        if (within0 || within1)
-                        {
-                            const float2 pi  = sm_lji[warp][ci * 8 + il];
-                            const int    tiN = __float_as_int(pi.x), ti = __float_as_int(pi.y);
-                            float        c60, c120, c6g0, c61, c121, c6g1;
-                            lj_pair_params<ELEC, VDW, ENERGY>(p, pi, pj0, tiN, ti, tj0, c60, c120, c6g0);
-                            lj_pair_params<ELEC, VDW, ENERGY>(p, pi, pj1, tiN, ti, tj1, c61, c121, c6g1);
-                            float e0lj = 0.0f, e0el = 0.0f, e1lj = 0.0f, e1el = 0.0f;
-                            float F0 = pair_force<ELEC, VDW, ENERGY>(p, k, r20, xi.w * xj0.w, c60, c120, c6g0, intBit0, e0lj, e0el);
-                            float F1 = pair_force<ELEC, VDW, ENERGY>(p, k, r21, xi.w * xj1.w, c61, c121, c6g1, intBit1, e1lj, e1el);
-                            F0 = within0 ? F0 : 0.0f;
-                            F1 = within1 ? F1 : 0.0f;
-                            if (ENERGY)
-                            {
-                                eLJj += (within0 ? e0lj : 0.0f) + (within1 ? e1lj : 0.0f);
-                                eElj += (within0 ? e0el : 0.0f) + (within1 ? e1el : 0.0f);
-                            }
-                            fi[ci].x = fmaf(F0, dx0, fmaf(F1, dx1, fi[ci].x));
-                            fi[ci].y = fmaf(F0, dy0, fmaf(F1, dy1, fi[ci].y));
-                            fi[ci].z = fmaf(F0, dz0, fmaf(F1, dz1, fi[ci].z));
-                            fj0.x    = fmaf(-F0, dx0, fj0.x);
-                            fj0.y    = fmaf(-F0, dy0, fj0.y);
-                            fj0.z    = fmaf(-F0, dz0, fj0.z);
-                            fj1.x    = fmaf(-F1, dx1, fj1.x);
-                            fj1.y    = fmaf(-F1, dy1, fj1.y);
-                            fj1.z    = fmaf(-F1, dz1, fj1.z);
-                        }
-                    }
+                    /* the i-cluster this j-cluster is, if any */
+                    const int ciDiag = (aj >> 3) - s.sci * c_superClusterSize;
+                    cluster_half<ELEC, VDW, ENERGY, PRUNE, true>(p, k, xqiLane, ljiLane, xj, pj, m8, wex, nonSelf, ciDiag,
+                                                                  rlistOuter2, fi, fj, eLJj, eElj, keep8);
                 }
 
                 if (ENERGY)
@@ -433,35 +557,33 @@ __global__ void __launch_bounds__(c_forceThreads)
                     eLJ += eLJj;
                     eEl += eElj;
                 }
-                /* reduce the two j-atom forces over the 8 il-lanes, one v4 reduction per j-atom */
+                /* reduce the j-atom force over the 8 il-lanes, one v4 reduction per j-atom */
 #pragma unroll
                 for (int m = 1; m < 8; m <<= 1)
                 {
-                    fj0.x += __shfl_xor_sync(c_full, fj0.x, m);
-                    fj0.y += __shfl_xor_sync(c_full, fj0.y, m);
-                    fj0.z += __shfl_xor_sync(c_full, fj0.z, m);
-                    fj1.x += __shfl_xor_sync(c_full, fj1.x, m);
-                    fj1.y += __shfl_xor_sync(c_full, fj1.y, m);
-                    fj1.z += __shfl_xor_sync(c_full, fj1.z, m);
+                    fj.x += __shfl_xor_sync(c_full, fj.x, m);
+                    fj.y += __shfl_xor_sync(c_full, fj.y, m);
+                    fj.z += __shfl_xor_sync(c_full, fj.z, m);
                 }
-                if (il == 0)
+                red_add_v4_if(il == 0, ad.f4 + aj, fj.x, fj.y, fj.z);
+                if (PRUNE)
                 {
-                    red_add_v4(ad.f4 + aj0, fj0.x, fj0.y, fj0.z);
+                    cleared |= (m8 & ~keep8) << shift;
                 }
-                if (il == 1)
-                {
-                    red_add_v4(ad.f4 + aj1, fj1.x, fj1.y, fj1.z);
-                }
+            }
+            if (PRUNE)
+            {
+                if (half) keep1 &= ~cleared; else keep0 &= ~cleared;
             }
         }
         if (PRUNE)
         {
             if (lane == 0)
             {
-                pl.cjPacked[jp].imei[0].imask = imask0;
-                pl.cjPacked[jp].imei[1].imask = imask1;
+                pl.cjPacked[jp].imei[0].imask = keep0;
+                pl.cjPacked[jp].imei[1].imask = keep1;
             }
-            prunedCount += __popc(imask0) + __popc(imask1);
+            prunedCount += __popc(keep0) + __popc(keep1);
         }
     }
 
@@ -481,10 +603,7 @@ __global__ void __launch_bounds__(c_forceThreads)
         x += __shfl_xor_sync(c_full, x, 16);
         y += __shfl_xor_sync(c_full, y, 16);
         z += __shfl_xor_sync(c_full, z, 16);
-        if (jl == (ci & 3))
-        {
-            red_add_v4(ad.f4 + (s.sci * c_superClusterSize + ci) * c_clusterSize + il, x, y, z);
-        }
+        red_add_v4_if(jl == (ci & 3), ad.f4 + (s.sci * c_superClusterSize + ci) * c_clusterSize + il, x, y, z);
     }
     if (calcFshift && s.shift != c_centralShiftIndex)
     {
@@ -510,7 +629,7 @@ __global__ void __launch_bounds__(c_forceThreads)
         }
         if (lane < 2)
         {
-            atomicAdd(ad.energy + lane, lane == 0 ? eLJ : eEl);
+            atomicAdd(ad.energy + lane, lane == 0 ? eLJ : eEl * static_cast<double>(p.epsfac));
         }
     }
     if (PRUNE && lane == 0)

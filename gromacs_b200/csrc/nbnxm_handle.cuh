@@ -1,0 +1,173 @@
+/* Private definition of the nbnxm_b200 handle (the reference's NbnxmGpu,
+ * src/gromacs/nbnxm/cuda/nbnxm_cuda_types.h:69) shared by the translation units that implement the
+ * C ABI (nbnxm_api.cu, nbnxm_halo.cu). Not part of the public interface. */
+#ifndef NBNXM_B200_HANDLE_CUH
+#define NBNXM_B200_HANDLE_CUH
+
+#include <cstdarg>
+#include <cstdio>
+
+#include <vector>
+
+#include "nbnxm_device.cuh"
+
+namespace nbb
+{
+
+extern thread_local char g_lastError[512];
+/* sets the thread's last-error message, returns 1 */
+int fail(const char* fmt, ...);
+
+#define CU(call)                                                                                      \
+    do                                                                                                \
+    {                                                                                                 \
+        cudaError_t e_ = (call);                                                                      \
+        if (e_ != cudaSuccess)                                                                        \
+        {                                                                                             \
+            return nbb::fail("%s:%d %s failed: %s", __FILE__, __LINE__, #call, cudaGetErrorString(e_)); \
+        }                                                                                             \
+    } while (0)
+
+template<typename T>
+struct DevBuf
+{
+    T*     p     = nullptr;
+    size_t n     = 0;
+    size_t alloc = 0;
+    /* grow-only reallocation with 20 % slack, contents are not preserved
+     * (reallocateDeviceBuffer, src/gromacs/gpu_utils/devicebuffer.h) */
+    cudaError_t reserve(size_t count)
+    {
+        n = count;
+        if (count <= alloc)
+        {
+            return cudaSuccess;
+        }
+        if (p)
+        {
+            cudaFree(p);
+            p = nullptr;
+        }
+        alloc         = count + count / 5 + 64;
+        cudaError_t e = cudaMalloc(&p, alloc * sizeof(T));
+        if (e != cudaSuccess)
+        {
+            alloc = 0;
+            n     = 0;
+        }
+        return e;
+    }
+    void release()
+    {
+        if (p) cudaFree(p);
+        p     = nullptr;
+        n     = 0;
+        alloc = 0;
+    }
+};
+
+struct PairList
+{
+    DevBuf<nbnxm_b200_sci_t>       sci, sciSorted;
+    DevBuf<int>                    sciCount, sciHistogram, sciOffset, rollingPart;
+    DevBuf<nbnxm_b200_cj_packed_t> cjPacked;
+    DevBuf<unsigned int>           imaskOuter;
+    DevBuf<nbnxm_b200_excl_t>      excl;
+    DevBuf<unsigned long long>     pairCount;
+    int                            numSci               = 0;
+    int                            naCi                 = -1;
+    bool                           haveFreshList        = false;
+    int                            rollingNumParts      = 0;
+    bool                           didPrune             = false;
+    bool                           didRollingPrune      = false;
+
+    PairlistDev dev(bool counting) const
+    {
+        PairlistDev d;
+        d.sci          = sci.p;
+        d.sciSorted    = sciSorted.p;
+        d.sciCount     = sciCount.p;
+        d.sciHistogram = sciHistogram.p;
+        d.sciOffset    = sciOffset.p;
+        d.cjPacked     = cjPacked.p;
+        d.imaskOuter   = imaskOuter.p;
+        d.excl         = excl.p;
+        d.rollingPart  = rollingPart.p;
+        d.pairCount    = counting ? pairCount.p : nullptr;
+        d.numSci       = numSci;
+        return d;
+    }
+};
+
+struct TimedRegion
+{
+    cudaEvent_t start, stop;
+    int         kind; /* 0..3 force[prune][energy], 4 prune, 5 rolling prune, 6 xq h2d, 7 f d2h, 8 pairlist h2d */
+};
+
+struct HaloState; /* nbnxm_halo.cu */
+
+} // namespace nbb
+
+struct nbnxm_b200
+{
+    int                 device = 0;
+    cudaStream_t        stream[2]    = { nullptr, nullptr };
+    bool                ownStream[2] = { false, false };
+    bool                localAndNonlocal = false;
+    nbnxm_b200_params_t params{};
+    int                 numTypes = 0;
+    int                 numSMs   = 0;
+
+    nbb::DevBuf<float4> xq, f4;
+    nbb::DevBuf<float>  f3;
+    nbb::DevBuf<int>    atomType;
+    nbb::DevBuf<float2> ljComb;
+    nbb::DevBuf<float>  shiftVec;
+    nbb::DevBuf<double> fshift, energy;
+    nbb::DevBuf<float2> nbfp, nbfpComb;
+    nbb::DevBuf<float>  coulombTab;
+    bool           shiftVecUploaded = false;
+    int            natoms = 0, natomsLocal = 0;
+
+    /* x buffer ops (one entry per grid) */
+    struct XGrid
+    {
+        int first = 0, n = 0;
+    };
+    std::vector<XGrid> xgrids;
+    nbb::DevBuf<int>        atomIndex;
+
+    nbb::PairList plist[2];
+    bool     haveWork[2] = { false, false };
+
+    double* h_fshift = nullptr; /* pinned staging, NBStagingData (gpu_types_common.h:142) */
+    double* h_energy = nullptr;
+
+    cudaEvent_t nonlocalDone = nullptr, localH2DDone = nullptr;
+
+    bool                     doTiming = false;
+    std::vector<nbb::TimedRegion> regions;
+    nbnxm_b200_timings_t     timings{};
+    bool                     pairCounting = false;
+    long long                launches     = 0;
+
+    nbb::HaloState* halo = nullptr;
+
+    nbb::ParamsDev   pd{};
+    nbb::AtomDataDev ad() const
+    {
+        nbb::AtomDataDev a;
+        a.xq       = xq.p;
+        a.f4       = f4.p;
+        a.atomType = atomType.p;
+        a.ljComb   = ljComb.p;
+        a.shiftVec = shiftVec.p;
+        a.fshift   = fshift.p;
+        a.energy   = energy.p;
+        a.numTypes = numTypes;
+        return a;
+    }
+};
+
+#endif

@@ -1,0 +1,326 @@
+"""x-slab decomposition of the NBNXM force step over the GPUs of one box, one process per GPU.
+
+Mirrors the reference's domain-decomposed step (do_force, src/gromacs/mdlib/sim_util.cpp:1815-1922,
+2424-2442): every rank holds its home atoms followed by a halo imported from the +x neighbour
+(eighth-shell zones restricted to one dimension, src/gromacs/domdec/domdec_zones.cpp:55-83), runs a
+local list (home x home) on the local stream and a non-local list (home x halo) on the non-local
+stream, and returns the halo forces to their owner.  The transport is the library's NCCL send/recv
+halo exchange (include/nbnxm_b200.h, nbnxm_b200_halo_*); torch.distributed is only used to launch the
+ranks, broadcast the NCCL id, and take barriers / max-over-ranks timings.
+
+Host-side pieces (slab ranges, list re-indexing) are pure numpy and are tested on CPU with gloo.
+"""
+import ctypes as C
+import json
+import os
+import time
+from dataclasses import dataclass
+
+import numpy as np
+
+from .nbnxm import LOCAL, NONLOCAL, AtomData, NbnxmGpu, PairlistGpu, StepWorkload
+from .slabs import slab_bin_ranges
+
+
+@dataclass
+class SlabPlan:
+    """What one rank needs at a search step: its atoms (home then halo), its two lists re-indexed to that
+    order, and the contiguous send / receive ranges of the halo exchange."""
+    rank: int
+    nranks: int
+    home_bins: tuple
+    halo_bins: tuple
+    nbat: AtomData              # home atoms then halo atoms
+    local: PairlistGpu
+    nonlocal_: PairlistGpu
+    send_first: int
+    send_count: int
+    recv_first: int
+    recv_count: int
+    home_slice: slice           # where the home atoms live in the global nbat order
+    halo_slice: slice
+
+
+def _reindex(pl, first_home_bin, first_halo_bin, num_home_bins, nclusters_total, halo):
+    """Global bin / cluster indices -> rank order (home bins first, then halo bins)."""
+    sci = pl.sci.copy()
+    cjp = pl.cjPacked.copy()
+    sci[:, 0] -= first_home_bin
+    cj = cjp[:, :4].astype(np.int64)
+    if halo:
+        cj = cj - first_halo_bin * 8 + num_home_bins * 8
+    else:
+        cj = cj - first_home_bin * 8
+    # unused slots of partially filled j-groups carry no mask bits and an unspecified index: keep them loadable
+    cjp[:, :4] = np.clip(cj, 0, nclusters_total - 1).astype(np.uint32)
+    return PairlistGpu(sci=sci, cjPacked=cjp, excl=pl.excl, na_ci=pl.na_ci, rlist=pl.rlist)
+
+
+def make_slab_plan(wl, rank, nranks, min_sci=0):
+    """constructPairlist(Local) + constructPairlist(NonLocal) for slab `rank` of `nranks`
+    (sim_util.cpp:1458, :1503), from one global grid."""
+    grid, cfg, g = wl.grid, wl.cfg, wl.nbat
+    rlist = cfg["rlist_outer"]
+    home, halo, tx = slab_bin_ranges(grid, nranks, rank, rlist)
+    ex_i, ex_a = wl.box.excl_index, wl.box.excl_atoms
+    if nranks == 1:
+        local = grid.pairlist(rlist, ex_i, ex_a, min_sci=min_sci)
+        empty = PairlistGpu(sci=np.zeros((0, 4), np.int32), cjPacked=np.zeros((0, 8), np.uint32),
+                            excl=np.full((1, 32), 0xffffffff, np.uint32))
+        return SlabPlan(rank, 1, home, halo, g, local, empty, 0, 0, g.numAtoms(), 0, slice(0, g.numAtoms()),
+                        slice(0, 0))
+    # non-local work is about rlist / slab width of the local work: share the balance target accordingly
+    loc_g = grid.pairlist(rlist, ex_i, ex_a, min_sci=min_sci, bins=home, j_bins=home)
+    nloc_g = grid.pairlist(rlist, ex_i, ex_a, min_sci=min_sci // 2, bins=home, j_bins=halo, inter_zone=True,
+                           required_tx=tx)
+    nhome, nhalo = home[1] - home[0], halo[1] - halo[0]
+    ncl = (nhome + nhalo) * 8
+    local = _reindex(loc_g, home[0], halo[0], nhome, ncl, halo=False)
+    nonloc = _reindex(nloc_g, home[0], halo[0], nhome, ncl, halo=True)
+    hs, ls = slice(home[0] * 64, home[1] * 64), slice(halo[0] * 64, halo[1] * 64)
+    cat = lambda a: None if a is None else np.concatenate([a[hs], a[ls]])
+    nbat = AtomData(xq=cat(g.xq), type=cat(g.type), lj_comb=cat(g.lj_comb), nbfp=g.nbfp, nbfp_comb=g.nbfp_comb,
+                    numTypes=g.numTypes, shift_vec=g.shift_vec, numLocalAtoms=nhome * 64)
+    # what the -x neighbour imports from us: the first columns of our slab = its halo range
+    _, halo_prev, _ = slab_bin_ranges(grid, nranks, (rank - 1) % nranks, rlist)
+    assert halo_prev[0] == home[0], "the -x neighbour's halo must start at our first column"
+    return SlabPlan(rank, nranks, home, halo, nbat, local, nonloc, 0, (halo_prev[1] - halo_prev[0]) * 64,
+                    nhome * 64, nhalo * 64, hs, ls)
+
+
+# ---- the halo part of the C ABI -------------------------------------------------------------------
+
+class HaloExchange:
+    """nbnxm_b200_halo_*: GpuHaloExchange for x-slabs (domdec/gpuhaloexchange.h:80-130)."""
+
+    def __init__(self, nb: NbnxmGpu, unique_id: bytes, rank, nranks):
+        self.nb, self._lib = nb, nb._lib
+        buf = C.create_string_buffer(unique_id, 128)
+        nb._check(self._lib.nbnxm_b200_halo_init(nb._h, buf, C.c_int(rank), C.c_int(nranks)))
+
+    @staticmethod
+    def unique_id(lib):
+        buf = C.create_string_buffer(128)
+        if lib.nbnxm_b200_halo_get_unique_id(buf, C.c_int(128)):
+            raise RuntimeError(lib.nbnxm_b200_last_error().decode())
+        return buf.raw
+
+    def reinitHalo(self, plan: SlabPlan):
+        self.nb._check(self._lib.nbnxm_b200_halo_set_ranges(
+            self.nb._h, C.c_int(plan.send_first), C.c_int(plan.send_count), C.c_int(plan.recv_first),
+            C.c_int(plan.recv_count)))
+
+    def communicateGpuHaloCoordinates(self):
+        self.nb._check(self._lib.nbnxm_b200_halo_exchange_x(self.nb._h))
+
+    def communicateGpuHaloForces(self):
+        self.nb._check(self._lib.nbnxm_b200_halo_exchange_f(self.nb._h))
+
+    def set_timing(self, enable=True):
+        self.nb._check(self._lib.nbnxm_b200_halo_set_timing(self.nb._h, C.c_int(int(enable))))
+
+    def timings(self, reset=False):
+        x, f = C.c_double(0), C.c_double(0)
+        self.nb._check(self._lib.nbnxm_b200_halo_get_timings(self.nb._h, C.byref(x), C.byref(f), C.c_int(int(reset))))
+        return x.value, f.value
+
+
+class SlabStep:
+    """One rank's force step: the do_force sequence around the two kernels (sim_util.cpp:1639-2442)."""
+
+    def __init__(self, nb, halo, plan, energy, dynamic_pruning, num_parts=3):
+        self.nb, self.halo, self.plan = nb, halo, plan
+        self.energy, self.dynamic_pruning, self.num_parts = energy, dynamic_pruning, num_parts
+        self.sw = StepWorkload(computeEnergy=energy, computeVirial=energy, useGpuFBufferOps=True)
+        self.multi = plan.nranks > 1
+
+    def search_step(self):
+        nb, plan = self.nb, self.plan
+        nb.gpu_init_atomdata(plan.nbat)
+        nb.gpu_init_pairlist(plan.local, LOCAL)
+        nb.gpu_init_pairlist(plan.nonlocal_, NONLOCAL)
+        nb.setupGpuShortRangeWork(LOCAL)
+        nb.setupGpuShortRangeWork(NONLOCAL)
+        nb.gpu_upload_shiftvec(plan.nbat)
+        if self.multi:
+            self.halo.reinitHalo(plan)
+        nb.gpu_copy_xq_to_gpu(plan.nbat, LOCAL)
+
+    def __call__(self, step, host_io=False):
+        nb, sw = self.nb, self.sw
+        if host_io:
+            nb.gpu_copy_xq_to_gpu(self.plan.nbat, LOCAL)
+        nb.gpu_clear_outputs(computeVirial=self.energy)
+        if self.multi:
+            nb.nbnxmInsertNonlocalGpuDependency(LOCAL)         # clear + H2D done -> non-local stream may start
+            self.halo.communicateGpuHaloCoordinates()
+        nb.gpu_launch_kernel(sw, LOCAL)
+        if self.multi:
+            nb.gpu_launch_kernel(sw, NONLOCAL)
+            self.halo.communicateGpuHaloForces()
+        if self.dynamic_pruning:
+            # with DD the rolling prune alternates local (even) / non-local (odd), prunekerneldispatch.cpp:123-128
+            if not self.multi:
+                if step % 2 == 1:
+                    nb.gpu_launch_kernel_pruneonly(LOCAL, self.num_parts)
+            elif step % 2 == 0:
+                nb.gpu_launch_kernel_pruneonly(LOCAL, self.num_parts)
+            else:
+                nb.gpu_launch_kernel_pruneonly(NONLOCAL, self.num_parts)
+        sw.useGpuFBufferOps = not host_io
+        if self.multi:
+            nb.gpu_launch_cpyback(self.plan.nbat, StepWorkload(useGpuFBufferOps=True), NONLOCAL)
+        nb.gpu_launch_cpyback(self.plan.nbat, sw, LOCAL)
+        if host_io:
+            if self.multi:
+                nb.gpu_wait_finish_task(sw, NONLOCAL)
+            return nb.gpu_wait_finish_task(sw, LOCAL)
+        return None
+
+    def finish(self):
+        if self.multi:
+            self.nb.gpu_wait_finish_task(self.sw, NONLOCAL)
+        return self.nb.gpu_wait_finish_task(self.sw, LOCAL)
+
+
+def bench_multi_gpu(args, rank, world, local_rank):
+    """bench.py's N > 1 arm: strong scaling of one water box over `world` x-slabs."""
+    import torch
+    import torch.distributed as dist
+    from .nbnxm import load_library, measure_fp32_peak
+    from .workload import make_workload
+
+    torch.cuda.set_device(local_rank)
+    dist.init_process_group(backend="nccl", device_id=torch.device("cuda", local_rank))
+    lib = load_library()
+    idt = torch.zeros(128, dtype=torch.uint8, device="cuda")
+    if rank == 0:
+        idt.copy_(torch.frombuffer(bytearray(HaloExchange.unique_id(lib)), dtype=torch.uint8))
+    dist.broadcast(idt, 0)
+    uid = bytes(idt.cpu().numpy().tobytes())
+
+    ncores = len(os.sched_getaffinity(0))
+    wl = make_workload(args.workload, nthreads=max(1, ncores // world))
+    cfg = wl.cfg
+    energy = cfg["energy"]
+    nb = NbnxmGpu(wl.params, wl.nbat, device=local_rank, bLocalAndNonlocal=True)
+    halo = HaloExchange(nb, uid, rank, world)
+    plan = make_slab_plan(wl, rank, world, min_sci=args.min_sci or nb.gpu_min_ci_balanced())
+    nbat = plan.nbat
+    xq_pin = torch.empty((nbat.numAtoms(), 4), dtype=torch.float32).pin_memory()
+    xq_pin.numpy()[:] = nbat.xq
+    nbat.xq = xq_pin.numpy()
+    f_pin = torch.zeros((nbat.numAtoms(), 3), dtype=torch.float32).pin_memory()
+    nbat.f = f_pin.numpy()
+
+    num_parts = 3
+    step = SlabStep(nb, halo, plan, energy, cfg["dynamic_pruning"], num_parts)
+    step.search_step()
+    local_stream = torch.cuda.ExternalStream(nb.streams()[0])
+    flush = None if args.no_l2_flush else torch.empty(256 << 20, dtype=torch.uint8, device="cuda")
+
+    nb.set_pair_counting(True)
+    step(0)
+    step.finish()
+    nb.get_pair_count(LOCAL), nb.get_pair_count(NONLOCAL)
+    for i in range(max(args.warmup, 4 * num_parts)):
+        step(i)
+    step.finish()
+    nb.get_pair_count(LOCAL), nb.get_pair_count(NONLOCAL)
+    step(0)
+    step.finish()
+    pairs = torch.tensor([nb.get_pair_count(LOCAL), nb.get_pair_count(NONLOCAL)], dtype=torch.float64, device="cuda")
+    nb.set_pair_counting(False)
+    dist.all_reduce(pairs)
+    computed_pairs = float(pairs.sum().item())
+
+    def timed_run(host_io):
+        ev = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)) for _ in range(args.steps)]
+        dist.barrier()
+        torch.cuda.synchronize()
+        l0 = nb.launch_count()
+        for i in range(args.steps):
+            if flush is not None:
+                with torch.cuda.stream(local_stream):
+                    flush.zero_()
+            ev[i][0].record(local_stream)
+            step(i, host_io)
+            ev[i][1].record(local_stream)
+        step.finish()
+        torch.cuda.synchronize()
+        dist.barrier()
+        ms = sum(a.elapsed_time(b) for a, b in ev) / len(ev)
+        t = torch.tensor([ms], dtype=torch.float64, device="cuda")
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        n = torch.tensor([nb.launch_count() - l0], dtype=torch.float64, device="cuda")
+        dist.all_reduce(n)
+        return float(t.item()), int(n.item())
+
+    from bench import ClockSampler, METRIC, UNIT
+    for i in range(args.warmup):
+        step(i)
+    clocks = ClockSampler(local_rank)
+    if rank == 0:
+        clocks.start()
+    ms_step, launches = timed_run(False)
+    clock_rec = clocks.stop() if rank == 0 else None
+
+    nb.gpu_reset_timings()
+    nb.set_timing(True)
+    halo.set_timing(True)
+    for i in range(4):
+        step(i)
+        step.finish()
+        halo.timings()
+    t = nb.gpu_get_timings()
+    hx, hf = halo.timings(reset=True)
+    nb.set_timing(False)
+    halo.set_timing(False)
+    e = 1 if energy else 0
+    k_ms = t.force_ms[0][e] / max(1, t.force_count[0][e]) * 2   # local + non-local launches per step
+    kt = torch.tensor([k_ms, hx, hf], dtype=torch.float64, device="cuda")
+    dist.all_reduce(kt, op=dist.ReduceOp.MAX)
+    k_ms, hx, hf = [float(v) for v in kt.tolist()]
+    fp32_peak = measure_fp32_peak(local_rank)
+
+    for i in range(args.warmup):
+        step(i, True)
+    ms_e2e, _ = timed_run(True)
+    sizes = torch.tensor([plan.nbat.numLocalAtoms, plan.recv_count, plan.send_count], dtype=torch.float64, device="cuda")
+    dist.all_reduce(sizes)
+    n_home, n_halo, _ = [int(v) for v in sizes.tolist()]
+
+    if rank == 0:
+        achieved = computed_pairs * wl.flops_per_pair / (k_ms * 1e-3) * 1e-12
+        line = {
+            "metric": METRIC, "value": wl.useful_pairs / (ms_step * 1e-3) * 1e-9, "unit": UNIT, "n_gpus": world,
+            "steps": args.steps, "warmup": args.warmup, "ms_per_step": ms_step, "higher_is_better": True,
+            "scaling": "strong", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+            "config": {"workload": args.workload, "natoms": wl.box.natoms, "rc_nm": cfg["rc"], "vdw": cfg["vdw"],
+                       "elec": "ewald_analytical", "energy_every_step": energy, "rlist_outer_nm": cfg["rlist_outer"],
+                       "rlist_inner_nm": cfg["rlist_inner"], "rolling_prune_parts": num_parts,
+                       "decomposition": "%d x-slabs, one-sided halo from the +x neighbour" % world,
+                       "halo_atoms_total": n_halo, "home_atoms_total": n_home,
+                       "l2": "256 MiB flush between steps, outside the per-step CUDA-event intervals" if flush is not None else "no flush",
+                       "timing": "mean of per-step CUDA-event intervals on each rank's local stream, max over ranks"},
+            "us_per_force_step": ms_step * 1e3,
+            "computed_pairs_per_step": computed_pairs,
+            "computed_gpairs_per_s": computed_pairs / (ms_step * 1e-3) * 1e-9,
+            "gpu_launches": launches,
+            "clocks": clock_rec,
+            "halo": {"x_exchange_us": hx * 1e3, "f_exchange_us": hf * 1e3, "transport": "ncclSend/ncclRecv",
+                     "bytes_per_step_total": int(n_halo * 32)},
+            "e2e": {"value": wl.useful_pairs / (ms_e2e * 1e-3) * 1e-9, "unit": UNIT, "ms_per_step": ms_e2e,
+                    "h2d_bytes_per_step": int(n_home * 16),
+                    "d2h_bytes_per_step": int(n_home * 12 + (16 + 45 * 24 if energy else 0) * world)},
+            "roofline": {"bound": "fp32_fma", "achieved": achieved, "peak": fp32_peak * world, "unit": "TFLOP/s",
+                         "frac": achieved / (fp32_peak * world), "traffic": None, "kernel": "nbnxm_force_kernel",
+                         "kernel_us": k_ms * 1e3, "flops_per_pair": wl.flops_per_pair,
+                         "note": "local + non-local force launches of the slowest rank; pairs summed over ranks; peak = measured FFMA peak x n_gpus"},
+        }
+        print(json.dumps(line), flush=True)
+    halo_free = getattr(lib, "nbnxm_b200_halo_free")
+    halo_free(nb._h)
+    nb.gpu_free()
+    dist.barrier()
+    dist.destroy_process_group()

@@ -36,6 +36,9 @@ EXPORTED_SYMBOLS = [
     "nbnxm_b200_download_pairlist", "nbnxm_b200_set_pair_counting", "nbnxm_b200_get_pair_count",
     "nbnxm_b200_launch_count", "nbnxm_b200_pack_xq", "nbnxm_b200_unpack_xq", "nbnxm_b200_pack_f",
     "nbnxm_b200_unpack_add_f", "nbnxm_b200_measure_fp32_peak",
+    "nbnxm_b200_halo_get_unique_id", "nbnxm_b200_halo_init", "nbnxm_b200_halo_free", "nbnxm_b200_halo_set_ranges",
+    "nbnxm_b200_halo_exchange_x", "nbnxm_b200_halo_exchange_f", "nbnxm_b200_halo_set_timing",
+    "nbnxm_b200_halo_get_timings",
 ]
 
 

@@ -206,6 +206,26 @@ int nbnxm_b200_pack_f(nbnxm_b200_t* nb, int first, int n, float* d_send, void* s
 /* f[index[i]] += d_recv[i] */
 int nbnxm_b200_unpack_add_f(nbnxm_b200_t* nb, const int* d_index, int n, const float* d_recv, void* stream);
 
+/* ---- x-slab halo exchange over NCCL send/recv (NVLink), one process per GPU.  Replaces
+ * gmx::GpuHaloExchange (src/gromacs/domdec/gpuhaloexchange.h:80-130) for a 1-D decomposition along x:
+ * slabs are whole grid columns, so with atoms in nbat order the region sent to the -x neighbour is the
+ * contiguous range [send_first, send_first + send_count) of the local atoms and the halo received from
+ * the +x neighbour the contiguous range [recv_first, ...) of the non-local atoms.  All calls are
+ * stream-ordered on the handle's non-local stream. ---- */
+/* ncclGetUniqueId into a 128-byte buffer (rank 0 calls it, the caller broadcasts the bytes) */
+int nbnxm_b200_halo_get_unique_id(char* id, int nbytes);
+/* ncclCommInitRank: collective over the nranks handles (GpuHaloExchange constructor) */
+int nbnxm_b200_halo_init(nbnxm_b200_t* nb, const char* id, int rank, int nranks);
+int nbnxm_b200_halo_free(nbnxm_b200_t* nb);
+/* GpuHaloExchange::reinitHalo, gpuhaloexchange_impl_gpu.cpp:152: called at search steps after gpu_init_atomdata */
+int nbnxm_b200_halo_set_ranges(nbnxm_b200_t* nb, int send_first, int send_count, int recv_first, int recv_count);
+/* communicateHaloCoordinates, gpuhaloexchange_impl_gpu.cpp:286: xq of our first columns -> rank-1, halo xq <- rank+1 */
+int nbnxm_b200_halo_exchange_x(nbnxm_b200_t* nb);
+/* communicateHaloForces, gpuhaloexchange_impl_gpu.cpp:340: halo f -> rank+1, f += what rank-1 computed on our atoms */
+int nbnxm_b200_halo_exchange_f(nbnxm_b200_t* nb);
+int nbnxm_b200_halo_set_timing(nbnxm_b200_t* nb, int enable);
+int nbnxm_b200_halo_get_timings(nbnxm_b200_t* nb, double* x_ms, double* f_ms, int reset);
+
 #ifdef __cplusplus
 }
 #endif

@@ -65,7 +65,8 @@ def test_force_energy_virial_parity(oracle, case):
         # step 2: sorted list, F+E+virial kernel
         f, e_lj, e_el, fsh = run_step(nb, nbat, plist, energy=True, virial=True, fresh_list=False)
         check_forces(f, f_ref)
-        assert abs(e_lj - e_ref[0]) <= E_REL * abs(e_ref[0]) + 2e-6, (e_lj, e_ref[0])
+        e_rel_lj = E_REL_LJ_LB if "cutlb" in case else E_REL
+        assert abs(e_lj - e_ref[0]) <= e_rel_lj * abs(e_ref[0]) + 2e-6, (e_lj, e_ref[0])
         assert abs(e_el - e_ref[1]) <= E_REL * abs(e_ref[1]), (e_el, e_ref[1])
         # virial contribution of the shift forces: -1/2 sum_s shift_vec[s] (x) fshift[s]
         vir, vir_ref = virial(d["shift_vec"], fsh), virial(d["shift_vec"], fsh_ref)
@@ -271,6 +272,9 @@ def test_x_to_nbat_x_and_local_nonlocal_streams(oracle):
         nb.gpu_wait_finish_task(StepWorkload(), NONLOCAL)
         nb.gpu_launch_kernel(sw, LOCAL)
         nb.gpu_launch_kernel(sw, NONLOCAL)
+        # ... and it also writes forces of non-local atoms, which a DD local list never does: the non-local
+        # copy-back must not overtake it (the library only orders local-after-non-local, like the reference)
+        torch.cuda.synchronize()
         nb.gpu_launch_cpyback(nbat, sw, NONLOCAL)
         nb.gpu_launch_cpyback(nbat, sw, LOCAL)
         nb.gpu_wait_finish_task(sw, NONLOCAL)
