@@ -1,0 +1,440 @@
+/* Reference-side binding of libnbnxm_b200: the free functions of the reference's NBNXM GPU-backend
+ * boundary (src/gromacs/nbnxm/nbnxm_gpu.h:68-313, src/gromacs/nbnxm/gpu_data_mgmt.h:66-181) implemented on
+ * top of the C ABI in include/nbnxm_b200.h.
+ *
+ * This file is what a maintainer adds to the reference tree INSTEAD of
+ *   src/gromacs/nbnxm/nbnxm_gpu_data_mgmt.cpp, src/gromacs/nbnxm/cuda/nbnxm_cuda.cu,
+ *   src/gromacs/nbnxm/cuda/nbnxm_cuda_data_mgmt.cu, src/gromacs/nbnxm/cuda/nbnxm_cuda_kernel_*.cu,
+ *   src/gromacs/nbnxm/cuda/nbnxm_gpu_buffer_ops_internal.cu
+ * in a GMX_GPU=CUDA build, linking libnbnxm_b200.so.  It is compiled against the reference's headers, so it
+ * cannot be built without the reference tree (INTEGRATION.md has the recipe).  Everything above it - the
+ * callers in nonbonded_verlet_t, init_nb_verlet and do_force - stays untouched.
+ *
+ * Conventions kept from the reference: these functions do not return errors; a non-zero status from the C
+ * ABI becomes gmx_fatal, as CUDA errors do there (CU_RET_ERR).
+ */
+#include "gmxpre.h"
+
+#include <optional>
+#include <vector>
+
+#include "gromacs/gpu_utils/device_stream_manager.h"
+#include "gromacs/gpu_utils/devicebuffer_datatype.h"
+#include "gromacs/gpu_utils/gpu_utils.h"
+#include "gromacs/gpu_utils/gpueventsynchronizer.h"
+#include "gromacs/hardware/device_information.h"
+#include "gromacs/mdtypes/enerdata.h"
+#include "gromacs/mdtypes/interaction_const.h"
+#include "gromacs/mdtypes/locality.h"
+#include "gromacs/mdtypes/simulation_workload.h"
+#include "gromacs/nbnxm/atomdata.h"
+#include "gromacs/nbnxm/gpu_data_mgmt.h"
+#include "gromacs/nbnxm/gridset.h"
+#include "gromacs/nbnxm/nbnxm.h"
+#include "gromacs/nbnxm/nbnxm_enums.h"
+#include "gromacs/nbnxm/nbnxm_gpu.h"
+#include "gromacs/nbnxm/pairlist.h"
+#include "gromacs/nbnxm/pairlistparams.h"
+#include "gromacs/nbnxm/pairlistsets.h"
+#include "gromacs/nbnxm/grid.h"
+#include "gromacs/tables/forcetable.h"
+#include "gromacs/timing/gpu_timing.h"
+#include "gromacs/timing/wallcycle.h"
+#include "gromacs/utility/fatalerror.h"
+
+#include "nbnxm_b200.h"
+
+namespace gmx
+{
+
+/* The reference's callers only ever hold a pointer to this type (nonbonded_verlet_t::gpuNbv_,
+ * src/gromacs/nbnxm/nbnxm.h:501); its definition belongs to the backend. */
+struct NbnxmGpu
+{
+    nbnxm_b200_t*             handle = nullptr;
+    bool                      useLjCombRule = false;
+    /* the reference's streams the library runs on (owned by the DeviceStreamManager) */
+    const DeviceStream* deviceStreams[2] = { nullptr, nullptr };
+    gmx_wallclock_gpu_nbnxm_t timings;
+};
+
+namespace
+{
+
+void check(int status, const char* what)
+{
+    if (status != 0)
+    {
+        gmx_fatal(FARGS, "%s failed: %s", what, nbnxm_b200_last_error());
+    }
+}
+
+int toInt(InteractionLocality l)
+{
+    return l == InteractionLocality::Local ? 0 : 1;
+}
+int toInt(AtomLocality l)
+{
+    return l == AtomLocality::Local ? 0 : (l == AtomLocality::NonLocal ? 1 : 2);
+}
+
+/* nbnxmGpuPickVdwKernelType + nbnxmGpuPickElectrostaticsKernelType + set_cutoff_parameters,
+ * src/gromacs/nbnxm/nbnxm_gpu_data_mgmt.cpp:168-240, 368-460.  Analytical Ewald is the reference's choice on
+ * every NVIDIA device except CC 7.0 / 8.0, so it is the choice on sm_100. */
+nbnxm_b200_params_t makeParams(const interaction_const_t& ic, const PairlistParams& listParams, LJCombinationRule ljComb)
+{
+    nbnxm_b200_params_t p{};
+    const bool          twin = (ic.coulomb.cutoff != ic.vdw.cutoff);
+    if (ic.coulomb.type == CoulombInteractionType::Cut)
+    {
+        p.elec_type = NBNXM_B200_ELEC_CUT;
+    }
+    else if (usingRF(ic.coulomb.type))
+    {
+        p.elec_type = NBNXM_B200_ELEC_RF;
+    }
+    else if (usingPme(ic.coulomb.type) || ic.coulomb.type == CoulombInteractionType::Ewald)
+    {
+        p.elec_type = twin ? NBNXM_B200_ELEC_EWALD_ANA_TWIN : NBNXM_B200_ELEC_EWALD_ANA;
+    }
+    else
+    {
+        gmx_fatal(FARGS, "The requested electrostatics type is not implemented in the GPU accelerated kernels");
+    }
+    if (ic.vdw.type == VanDerWaalsType::Cut)
+    {
+        switch (ic.vdw.modifier)
+        {
+            case InteractionModifiers::None:
+            case InteractionModifiers::PotShift:
+                p.vdw_type = (ljComb == LJCombinationRule::None)        ? NBNXM_B200_VDW_CUT
+                             : (ljComb == LJCombinationRule::Geometric) ? NBNXM_B200_VDW_CUT_COMB_GEOM
+                                                                        : NBNXM_B200_VDW_CUT_COMB_LB;
+                break;
+            case InteractionModifiers::ForceSwitch: p.vdw_type = NBNXM_B200_VDW_FSWITCH; break;
+            case InteractionModifiers::PotSwitch: p.vdw_type = NBNXM_B200_VDW_PSWITCH; break;
+            default: gmx_fatal(FARGS, "The requested VdW interaction modifier is not implemented in the GPU accelerated kernels");
+        }
+    }
+    else if (ic.vdw.type == VanDerWaalsType::Pme)
+    {
+        p.vdw_type = (ic.vdw.pmeCombinationRule == LongRangeVdW::Geom) ? NBNXM_B200_VDW_EWALD_GEOM : NBNXM_B200_VDW_EWALD_LB;
+    }
+    else
+    {
+        gmx_fatal(FARGS, "The requested VdW type is not implemented in the GPU accelerated kernels");
+    }
+    p.epsfac              = ic.coulomb.epsfac;
+    p.c_rf                = ic.coulomb.reactionFieldShift;
+    p.two_k_rf            = 2.0 * ic.coulomb.reactionFieldCoefficient;
+    p.ewald_beta          = ic.coulomb.ewaldCoeff;
+    p.sh_ewald            = ic.coulomb.ewaldShift;
+    p.sh_lj_ewald         = ic.vdw.ewaldShift;
+    p.ewaldcoeff_lj       = ic.vdw.ewaldCoeff;
+    p.rcoulomb_sq         = ic.coulomb.cutoff * ic.coulomb.cutoff;
+    p.rvdw_sq             = ic.vdw.cutoff * ic.vdw.cutoff;
+    p.rvdw_switch         = ic.vdw.switchDistance;
+    p.rlist_outer_sq      = listParams.rlistOuter * listParams.rlistOuter;
+    p.rlist_inner_sq      = listParams.rlistInner * listParams.rlistInner;
+    p.disp_c2             = ic.vdw.dispersionShift.c2;
+    p.disp_c3             = ic.vdw.dispersionShift.c3;
+    p.disp_cpot           = ic.vdw.dispersionShift.cpot;
+    p.rep_c2              = ic.vdw.repulsionShift.c2;
+    p.rep_c3              = ic.vdw.repulsionShift.c3;
+    p.rep_cpot            = ic.vdw.repulsionShift.cpot;
+    p.sw_c3               = ic.vdw.switchConstants.c3;
+    p.sw_c4               = ic.vdw.switchConstants.c4;
+    p.sw_c5               = ic.vdw.switchConstants.c5;
+    p.coulomb_tab_scale   = ic.coulombEwaldTables ? ic.coulombEwaldTables->scale : 0.0F;
+    p.use_dynamic_pruning = listParams.useDynamicPruning ? 1 : 0;
+    return p;
+}
+
+} // namespace
+
+NbnxmGpu* gpu_init(const DeviceStreamManager& deviceStreamManager,
+                   const interaction_const_t* ic,
+                   const PairlistParams&      listParams,
+                   const nbnxm_atomdata_t*    nbat,
+                   bool                       bLocalAndNonlocal,
+                   const std::optional<size_t> nLambda)
+{
+    if (nLambda.has_value())
+    {
+        gmx_fatal(FARGS, "Perturbed (FEP) nonbonded kernels are not part of the nbnxm_b200 backend");
+    }
+    auto*                      nb     = new NbnxmGpu();
+    const auto&                params = nbat->params();
+    const nbnxm_b200_params_t  p      = makeParams(*ic, listParams, params.ljCombinationRule);
+    nb->useLjCombRule = (p.vdw_type == NBNXM_B200_VDW_CUT_COMB_GEOM || p.vdw_type == NBNXM_B200_VDW_CUT_COMB_LB);
+    const float* tab     = ic->coulombEwaldTables ? ic->coulombEwaldTables->tableF.data() : nullptr;
+    const int    tabSize = ic->coulombEwaldTables ? static_cast<int>(ic->coulombEwaldTables->tableF.size()) : 0;
+    /* run on the reference's own streams so that its event protocol with PME / bonded / update work holds */
+    nb->deviceStreams[0] = &deviceStreamManager.stream(DeviceStreamType::NonBondedLocal);
+    nb->deviceStreams[1] = bLocalAndNonlocal ? &deviceStreamManager.stream(DeviceStreamType::NonBondedNonLocal)
+                                             : nb->deviceStreams[0];
+    void* localStream    = nb->deviceStreams[0]->stream();
+    void* nonLocalStream = bLocalAndNonlocal ? nb->deviceStreams[1]->stream() : nullptr;
+    check(nbnxm_b200_init(&nb->handle,
+                          deviceStreamManager.deviceInfo().id,
+                          &p,
+                          params.numTypes,
+                          params.nbfp.data(),
+                          params.nbfp_comb.empty() ? nullptr : params.nbfp_comb.data(),
+                          tab,
+                          tabSize,
+                          bLocalAndNonlocal ? 1 : 0,
+                          localStream,
+                          nonLocalStream),
+          "nbnxm_b200_init");
+    return nb;
+}
+
+void gpu_free(NbnxmGpu* nb)
+{
+    if (nb != nullptr)
+    {
+        nbnxm_b200_free(nb->handle);
+        delete nb;
+    }
+}
+
+void gpu_init_pairlist(NbnxmGpu* nb, const NbnxmPairlistGpu* h_nblist, InteractionLocality iloc)
+{
+    static_assert(sizeof(nbnxm_sci_t) == sizeof(nbnxm_b200_sci_t), "sci layout");
+    static_assert(sizeof(nbnxm_cj_packed_t) == sizeof(nbnxm_b200_cj_packed_t), "cjPacked layout");
+    static_assert(sizeof(nbnxm_excl_t) == sizeof(nbnxm_b200_excl_t), "excl layout");
+    check(nbnxm_b200_init_pairlist(nb->handle,
+                                   toInt(iloc),
+                                   reinterpret_cast<const nbnxm_b200_sci_t*>(h_nblist->sci.data()),
+                                   static_cast<int>(h_nblist->sci.size()),
+                                   reinterpret_cast<const nbnxm_b200_cj_packed_t*>(h_nblist->cjPacked.list_.data()),
+                                   static_cast<int>(h_nblist->cjPacked.size()),
+                                   reinterpret_cast<const nbnxm_b200_excl_t*>(h_nblist->excl.data()),
+                                   static_cast<int>(h_nblist->excl.size()),
+                                   h_nblist->na_ci),
+          "nbnxm_b200_init_pairlist");
+}
+
+void gpu_init_atomdata(NbnxmGpu* nb, const nbnxm_atomdata_t* nbat)
+{
+    const auto& params = nbat->params();
+    check(nbnxm_b200_init_atomdata(nb->handle,
+                                   nbat->numAtoms(),
+                                   nbat->numLocalAtoms(),
+                                   nb->useLjCombRule ? nullptr : params.type.data(),
+                                   nb->useLjCombRule ? params.lj_comb.data() : nullptr),
+          "nbnxm_b200_init_atomdata");
+}
+
+void gpu_upload_shiftvec(NbnxmGpu* nb, const nbnxm_atomdata_t* nbatom)
+{
+    check(nbnxm_b200_upload_shiftvec(nb->handle, reinterpret_cast<const float*>(nbatom->shift_vec.data()), nbatom->bDynamicBox ? 1 : 0),
+          "nbnxm_b200_upload_shiftvec");
+}
+
+void gpu_copy_xq_to_gpu(NbnxmGpu* nb, const nbnxm_atomdata_t* nbdata, AtomLocality aloc)
+{
+    check(nbnxm_b200_copy_xq_to_gpu(nb->handle, toInt(aloc), nbdata->x().data()), "nbnxm_b200_copy_xq_to_gpu");
+}
+
+void gpu_launch_kernel(NbnxmGpu* nb, const StepWorkload& stepWork, InteractionLocality iloc)
+{
+    check(nbnxm_b200_launch_kernel(nb->handle, toInt(iloc), stepWork.computeEnergy ? 1 : 0, stepWork.computeVirial ? 1 : 0),
+          "nbnxm_b200_launch_kernel");
+}
+
+void gpu_launch_kernel_pruneonly(NbnxmGpu* nb, InteractionLocality iloc, int numParts)
+{
+    check(nbnxm_b200_launch_kernel_pruneonly(nb->handle, toInt(iloc), numParts), "nbnxm_b200_launch_kernel_pruneonly");
+}
+
+void gpu_launch_cpyback(NbnxmGpu* nb, nbnxm_atomdata_t* nbatom, const StepWorkload& stepWork, AtomLocality aloc)
+{
+    check(nbnxm_b200_launch_cpyback(nb->handle,
+                                    toInt(aloc),
+                                    nbatom->outputBuffer(0).f.data(),
+                                    stepWork.computeEnergy ? 1 : 0,
+                                    stepWork.computeVirial ? 1 : 0,
+                                    stepWork.useGpuFBufferOps ? 1 : 0),
+          "nbnxm_b200_launch_cpyback");
+}
+
+bool gpu_try_finish_task(NbnxmGpu*           nb,
+                         const StepWorkload& stepWork,
+                         AtomLocality        aloc,
+                         real*               e_lj,
+                         real*               e_el,
+                         double* /*dvdl_lj*/,
+                         double* /*dvdl_el*/,
+                         ArrayRef<RVec> shiftForces,
+                         ForeignLambdaTerms* /*foreign_term*/,
+                         GpuTaskCompletion completionKind)
+{
+    float* fshift = shiftForces.empty() ? nullptr : reinterpret_cast<float*>(shiftForces.data());
+    if (completionKind == GpuTaskCompletion::Check)
+    {
+        int done = 0;
+        check(nbnxm_b200_try_finish_task(nb->handle, toInt(aloc), stepWork.computeEnergy, stepWork.computeVirial, e_lj, e_el, fshift, &done),
+              "nbnxm_b200_try_finish_task");
+        return done != 0;
+    }
+    check(nbnxm_b200_wait_finish_task(nb->handle, toInt(aloc), stepWork.computeEnergy, stepWork.computeVirial, e_lj, e_el, fshift),
+          "nbnxm_b200_wait_finish_task");
+    return true;
+}
+
+float gpu_wait_finish_task(NbnxmGpu*           nb,
+                           const StepWorkload& stepWork,
+                           AtomLocality        aloc,
+                           const bool /*haveSoftCore*/,
+                           gmx_enerdata_t* enerd,
+                           ArrayRef<RVec>  shiftForces,
+                           gmx_wallcycle*  wcycle)
+{
+    auto cycleCounter = (aloc == AtomLocality::Local) ? WallCycleCounter::WaitGpuNbL : WallCycleCounter::WaitGpuNbNL;
+    wallcycle_start(wcycle, cycleCounter);
+    gpu_try_finish_task(nb,
+                        stepWork,
+                        aloc,
+                        enerd->grpp.energyGroupPairTerms[NonBondedEnergyTerms::LJSR].data(),
+                        enerd->grpp.energyGroupPairTerms[NonBondedEnergyTerms::CoulombSR].data(),
+                        nullptr,
+                        nullptr,
+                        shiftForces,
+                        nullptr,
+                        GpuTaskCompletion::Wait);
+    return static_cast<float>(wallcycle_stop(wcycle, cycleCounter));
+}
+
+void gpu_clear_outputs(NbnxmGpu* nb, bool computeVirial)
+{
+    check(nbnxm_b200_clear_outputs(nb->handle, computeVirial ? 1 : 0), "nbnxm_b200_clear_outputs");
+}
+
+void nbnxmInsertNonlocalGpuDependency(NbnxmGpu* nb, InteractionLocality interactionLocality)
+{
+    check(nbnxm_b200_insert_nonlocal_dependency(nb->handle, toInt(interactionLocality)), "nbnxm_b200_insert_nonlocal_dependency");
+}
+
+void setupGpuShortRangeWorkLow(NbnxmGpu* nb, const ListedForcesGpu* listedForcesGpu, InteractionLocality iLocality)
+{
+    const bool haveBonded = (listedForcesGpu != nullptr); /* the reference asks listedForcesGpu->haveInteractions() */
+    check(nbnxm_b200_setup_short_range_work(nb->handle, toInt(iLocality), haveBonded ? 1 : 0), "nbnxm_b200_setup_short_range_work");
+}
+
+bool haveGpuShortRangeWork(const NbnxmGpu* nb, InteractionLocality interactionLocality)
+{
+    return nbnxm_b200_have_short_range_work(nb->handle, toInt(interactionLocality)) != 0;
+}
+
+void nbnxm_gpu_init_x_to_nbat_x(const GridSet& gridSet, NbnxmGpu* gpu_nbv)
+{
+    const int numGrids = static_cast<int>(gridSet.grids().size());
+    for (int g = 0; g < numGrids; g++)
+    {
+        const Grid& grid        = gridSet.grid(g);
+        const int   atomOffset  = grid.firstAtomInCell(0); /* first nbat slot of this grid */
+        const int   numNbatAtoms = grid.atomIndexEnd() - atomOffset;
+        check(nbnxm_b200_init_x_to_nbat_x(gpu_nbv->handle,
+                                          g,
+                                          numGrids,
+                                          gridSet.atomIndices().data() + atomOffset,
+                                          numNbatAtoms,
+                                          grid.numAtomsPerCell().data(),
+                                          grid.cellToBin().data(),
+                                          grid.numCells(),
+                                          grid.numAtomsPerBin(),
+                                          atomOffset),
+              "nbnxm_b200_init_x_to_nbat_x");
+    }
+}
+
+void nbnxm_gpu_x_to_nbat_x(NbnxmGpu* gpu_nbv, DeviceBuffer<RVec> d_x, GpuEventSynchronizer* xReadyOnDevice, AtomLocality locality)
+{
+    /* the library runs on the reference's own streams, so the reference's event object can enqueue the wait */
+    if (xReadyOnDevice != nullptr)
+    {
+        xReadyOnDevice->enqueueWaitEvent(*gpu_nbv->deviceStreams[locality == AtomLocality::NonLocal ? 1 : 0]);
+    }
+    check(nbnxm_b200_x_to_nbat_x(gpu_nbv->handle, reinterpret_cast<const float*>(d_x), nullptr, toInt(locality)),
+          "nbnxm_b200_x_to_nbat_x");
+}
+
+int gpu_min_ci_balanced(NbnxmGpu* nb)
+{
+    return nb != nullptr ? nbnxm_b200_min_ci_balanced(nb->handle) : 0;
+}
+
+bool gpu_is_kernel_ewald_analytical(const NbnxmGpu* nb)
+{
+    return nbnxm_b200_is_kernel_ewald_analytical(nb->handle) != 0;
+}
+
+DeviceBuffer<RVec> gpu_get_f(NbnxmGpu* nb)
+{
+    float* d_f = nullptr;
+    nbnxm_b200_get_device_buffers(nb->handle, nullptr, &d_f, nullptr);
+    return reinterpret_cast<DeviceBuffer<RVec>>(d_f);
+}
+
+gmx_wallclock_gpu_nbnxm_t* gpu_get_timings(NbnxmGpu* nb)
+{
+    if (nb == nullptr)
+    {
+        return nullptr;
+    }
+    nbnxm_b200_timings_t t;
+    check(nbnxm_b200_get_timings(nb->handle, &t), "nbnxm_b200_get_timings");
+    for (int prune = 0; prune < 2; prune++)
+    {
+        for (int energy = 0; energy < 2; energy++)
+        {
+            nb->timings.ktime[prune][energy].t = t.force_ms[prune][energy];
+            nb->timings.ktime[prune][energy].c = t.force_count[prune][energy];
+        }
+    }
+    nb->timings.pruneTime.t        = t.prune_ms;
+    nb->timings.pruneTime.c        = t.prune_count;
+    nb->timings.dynamicPruneTime.t = t.rolling_prune_ms;
+    nb->timings.dynamicPruneTime.c = t.rolling_prune_count;
+    nb->timings.nb_h2d_t           = t.xq_h2d_ms;
+    nb->timings.nb_d2h_t           = t.f_d2h_ms;
+    nb->timings.pl_h2d_t           = t.pairlist_h2d_ms;
+    return &nb->timings;
+}
+
+void gpu_reset_timings(nonbonded_verlet_t* nbv)
+{
+    if (nbv != nullptr && nbv->gpuNbv() != nullptr)
+    {
+        check(nbnxm_b200_reset_timings(nbv->gpuNbv()->handle), "nbnxm_b200_reset_timings");
+    }
+}
+
+void gpu_pme_loadbal_update_param(nonbonded_verlet_t* nbv, const interaction_const_t& ic)
+{
+    if (nbv == nullptr || !nbv->useGpu())
+    {
+        return;
+    }
+    NbnxmGpu*                 nb = nbv->gpuNbv();
+    const nbnxm_b200_params_t p  = makeParams(ic, nbv->pairlistSets().params(), nbv->nbat().params().ljCombinationRule);
+    const float* tab     = ic.coulombEwaldTables ? ic.coulombEwaldTables->tableF.data() : nullptr;
+    const int    tabSize = ic.coulombEwaldTables ? static_cast<int>(ic.coulombEwaldTables->tableF.size()) : 0;
+    check(nbnxm_b200_update_params(nb->handle, &p, tab, tabSize), "nbnxm_b200_update_params");
+}
+
+/* Perturbed-interaction (FEP) kernels work on atom-pair lists and are a separate backend piece
+ * (src/gromacs/nbnxm/cuda/nbfe_cuda.cu); not part of this path. */
+void copy_gpu_fepparams(NbnxmGpu*, bool, float, float, int, float, float, float, float, int,
+                        const EnumerationArray<FreeEnergyPerturbationCouplingType, std::vector<double>>&)
+{
+    gmx_fatal(FARGS, "Perturbed (FEP) nonbonded kernels are not part of the nbnxm_b200 backend");
+}
+void gpu_init_feppairlist(NbnxmGpu*, const AtomPairlist&, InteractionLocality, ArrayRef<const int>)
+{
+    gmx_fatal(FARGS, "Perturbed (FEP) nonbonded kernels are not part of the nbnxm_b200 backend");
+}
+
+} // namespace gmx

@@ -1,0 +1,93 @@
+"""Multi-GPU parity (needs >= 2 GPUs on the box; skipped otherwise): the x-slab step with the NCCL halo exchange
+of the library, one process per GPU, against the oracle on the whole system."""
+import os
+import socket
+
+import numpy as np
+import pytest
+
+pytestmark = pytest.mark.gpu
+
+
+def _free_port():
+    s = socket.socket()
+    s.bind(("127.0.0.1", 0))
+    port = s.getsockname()[1]
+    s.close()
+    return port
+
+
+def _worker(rank, world, port, out):
+    import torch
+    import torch.distributed as dist
+    os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port))
+    torch.cuda.set_device(rank)
+    dist.init_process_group("nccl", rank=rank, world_size=world, device_id=torch.device("cuda", rank))
+    try:
+        from gromacs_b200 import NbnxmGpu
+        from gromacs_b200.multigpu import HaloExchange, SlabStep, make_slab_plan
+        from gromacs_b200.nbnxm import load_library
+        from gromacs_b200.workload import make_workload
+        lib = load_library()
+        idt = torch.zeros(128, dtype=torch.uint8, device="cuda")
+        if rank == 0:
+            idt.copy_(torch.frombuffer(bytearray(HaloExchange.unique_id(lib)), dtype=torch.uint8))
+        dist.broadcast(idt, 0)
+        wl = make_workload("water48k_test", nthreads=4)
+        nb = NbnxmGpu(wl.params, wl.nbat, device=rank, bLocalAndNonlocal=True)
+        halo = HaloExchange(nb, idt.cpu().numpy().tobytes(), rank, world)
+        plan = make_slab_plan(wl, rank, world, min_sci=2000)
+        # the halo part of the host coordinates is never uploaded: it has to arrive through the exchange
+        plan.nbat.xq[plan.recv_first:] = 0
+        step = SlabStep(nb, halo, plan, energy=True, dynamic_pruning=False)
+        step.search_step()
+        results = []
+        for i in range(3):
+            e_lj, e_el = step(i, host_io=True)
+            results.append((plan.nbat.f[:plan.nbat.numLocalAtoms].astype(np.float64).copy(), e_lj, e_el))
+        parts = [None] * world
+        dist.all_gather_object(parts, (plan.home_slice.start, results))
+        lib.nbnxm_b200_halo_free(nb._h)
+        nb.gpu_free()
+        if rank == 0:
+            out.put(parts)
+    finally:
+        dist.destroy_process_group()
+
+
+@pytest.mark.parametrize("world", [2, 4])
+def test_x_slab_step_matches_oracle(oracle, world):
+    import torch
+    if torch.cuda.device_count() < world:
+        pytest.skip("needs %d GPUs" % world)
+    import torch.multiprocessing as mp
+    from gromacs_b200.workload import make_workload
+    ctx = mp.get_context("spawn")
+    out = ctx.Queue()
+    port = _free_port()
+    procs = [ctx.Process(target=_worker, args=(r, world, port, out)) for r in range(world)]
+    for pr in procs:
+        pr.start()
+    parts = out.get(timeout=600)
+    for pr in procs:
+        pr.join(120)
+        assert pr.exitcode == 0
+    wl = make_workload("water48k_test", nthreads=4)
+    p = oracle.OrcParams()
+    for name, _ in wl.params._fields_:
+        if hasattr(p, name):
+            setattr(p, name, getattr(wl.params, name))
+    p.ntypes = wl.nbat.numTypes
+    whole, g = wl.pairlist(), wl.nbat
+    f_ref, _, e_ref, _ = oracle.forces(p, whole.sci, whole.cjPacked, whole.excl, g.xq, g.type, g.lj_comb, g.nbfp,
+                                       g.nbfp_comb, g.shift_vec)
+    for i in range(3):
+        f = np.zeros_like(f_ref)
+        e = np.zeros(2)
+        for start, results in parts:
+            fpart, e_lj, e_el = results[i]
+            f[start:start + fpart.shape[0]] += fpart
+            e += (e_lj, e_el)
+        assert np.sqrt(((f - f_ref) ** 2).sum() / (f_ref ** 2).sum()) <= 5e-6
+        assert np.abs(f - f_ref).max() <= 1e-4 * np.abs(f_ref).max()
+        assert abs(e[1] - e_ref[1]) <= 2e-6 * abs(e_ref[1]), (e, e_ref)
