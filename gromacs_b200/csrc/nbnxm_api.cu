@@ -19,6 +19,7 @@ namespace nbb
 {
 void launch_prune(bool fresh, const AtomDataDev& ad, const ParamsDev& p, const PairlistDev& pl, int numParts, cudaStream_t stream);
 void launch_sci_sort(const PairlistDev& pl, cudaStream_t stream);
+void launch_count_pairs(const PairlistDev& pl, cudaStream_t stream);
 void launch_x_to_nbat_x(float4* xq, const float* x, const int* atomIndex, int first, int n, cudaStream_t s);
 void launch_f4_to_f3(const float4* f4, float* f3, int first, int n, cudaStream_t s);
 void launch_pack_xq(const float4* xq, const int* index, int n, const float* shift, float4* out, cudaStream_t s);
@@ -71,6 +72,22 @@ void fillParamsDev(nbnxm_b200* nb)
     d.rep_c2 = s.rep_c2; d.rep_c3 = s.rep_c3; d.rep_cpot = s.rep_cpot;
     d.sw_c3 = s.sw_c3; d.sw_c4 = s.sw_c4; d.sw_c5 = s.sw_c5;
     d.coulomb_tab_scale = s.coulomb_tab_scale;
+    {
+        /* pmeCorrF coefficients (src/gromacs/nbnxm/nbnxm_kernel_utils.h:216-250), powers of beta folded in */
+        const double cn[7] = { -0.75225204789749321333, 0.069670166153766424023, -0.019278317264888380590,
+                               0.0010054721316683106153, -0.000053401640219807709149, 1.4703624142580877519e-6,
+                               -1.7357322914161492954e-8 };
+        const double cd[5] = { 1.0, 0.50736591960530292870, 0.11583842382862377919, 0.014866955030185295499,
+                               0.0011193462567257629232 };
+        const double b = s.ewald_beta, b2 = b * b;
+        double       pw = 1.0;
+        for (int k = 0; k < 7; k++)
+        {
+            d.pmeNum[k] = static_cast<float>(cn[k] * pw * b2 * b);
+            if (k < 5) d.pmeDen[k] = static_cast<float>(cd[k] * pw);
+            pw *= b2;
+        }
+    }
     d.nbfp       = nb->nbfp.p;
     d.nbfpComb   = nb->nbfpComb.p;
     d.coulombTab = nb->coulombTab.p;
@@ -546,8 +563,14 @@ int nbnxm_b200_launch_kernel(nbnxm_b200_t* nb, int iloc, int compute_energy, int
         return fail("nbnxm_b200_launch_kernel: no kernel for elec_type %d vdw_type %d", nb->params.elec_type, nb->params.vdw_type);
     }
     beginRegion(nb, (doPrune ? 2 : 0) + (compute_energy ? 1 : 0), st);
+    if (nb->pairCounting)
+    {
+        /* diagnostics: the pairs this launch is about to evaluate (masks as the force kernel will read them) */
+        launch_count_pairs(pl.dev(true), st);
+        nb->launches++;
+    }
     /* one 32-thread CTA per sci entry */
-    kernel<<<pl.numSci, 32, 0, st>>>(nb->ad(), nb->pd, pl.dev(nb->pairCounting), compute_virial != 0);
+    kernel<<<pl.numSci, 32, 0, st>>>(nb->ad(), nb->pd, pl.dev(false), compute_virial != 0);
     nb->launches++;
     if (doPrune)
     {

@@ -51,6 +51,8 @@ struct ParamsDev
     float rcoulomb_sq, rvdw_sq, rvdw_switch, rlist_outer_sq, rlist_inner_sq;
     float disp_c2, disp_c3, disp_cpot, rep_c2, rep_c3, rep_cpot, sw_c3, sw_c4, sw_c5;
     float coulomb_tab_scale;
+    /* pmeCorrF coefficients with beta folded in: num[k] = cn_k beta^(2k+3), den[k] = cd_k beta^(2k) */
+    float pmeNum[7], pmeDen[5];
     const float2* nbfp;
     const float2* nbfpComb;
     const float*  coulombTab;

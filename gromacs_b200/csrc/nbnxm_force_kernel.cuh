@@ -54,26 +54,34 @@ struct Flavor
     static constexpr bool exclusionForces = ewaldAny || elecRF || ljEwald || (elecCut && ENERGY);
 };
 
-/* (2/sqrt(pi) z exp(-z^2) - erf(z)) / z^3 as a rational minimax approximation in z^2; the
- * coefficients are the ones the reference uses in pmeCorrF (nbnxm_kernel_utils.h:216-250). */
-__device__ __forceinline__ float pme_corr_f(const float z2)
+/* beta^3 (2/sqrt(pi) z exp(-z^2) - erf(z)) / z^3 with z = beta r as a rational minimax approximation in r^2.
+ * The coefficients are the reference's pmeCorrF ones (nbnxm_kernel_utils.h:216-250) with the powers of beta
+ * folded in on the host (ParamsDev::pmeNum / pmeDen, fillParamsDev): they sit in the constant bank and feed
+ * the FFMAs directly, which saves the z^2 = beta^2 r^2 and the * beta^3 multiplications of every pair. */
+__device__ __forceinline__ float pme_corr_f_beta3(const ParamsDev& p, const float r2)
 {
-    float den = 0.0011193462567257629232f;
-    den       = fmaf(den, z2, 0.014866955030185295499f);
-    den       = fmaf(den, z2, 0.11583842382862377919f);
-    den       = fmaf(den, z2, 0.50736591960530292870f);
-    den       = fmaf(den, z2, 1.0f);
-    float num = -1.7357322914161492954e-8f;
-    num       = fmaf(num, z2, 1.4703624142580877519e-6f);
-    num       = fmaf(num, z2, -0.000053401640219807709149f);
-    num       = fmaf(num, z2, 0.0010054721316683106153f);
-    num       = fmaf(num, z2, -0.019278317264888380590f);
-    num       = fmaf(num, z2, 0.069670166153766424023f);
-    num       = fmaf(num, z2, -0.75225204789749321333f);
+    float den = fmaf(p.pmeDen[4], r2, p.pmeDen[3]);
+    den       = fmaf(den, r2, p.pmeDen[2]);
+    den       = fmaf(den, r2, p.pmeDen[1]);
+    den       = fmaf(den, r2, 1.0f);
+    float num = fmaf(p.pmeNum[6], r2, p.pmeNum[5]);
+    num       = fmaf(num, r2, p.pmeNum[4]);
+    num       = fmaf(num, r2, p.pmeNum[3]);
+    num       = fmaf(num, r2, p.pmeNum[2]);
+    num       = fmaf(num, r2, p.pmeNum[1]);
+    num       = fmaf(num, r2, p.pmeNum[0]);
     /* den >= 1: the plain approximate reciprocal needs no range fix-up */
     float rden;
     asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(rden) : "f"(den));
     return num * rden;
+}
+
+/* Dynamic-index read of one of four registers without local memory. */
+__device__ __forceinline__ unsigned select4(const unsigned a, const unsigned b, const unsigned c, const unsigned d, const int i)
+{
+    const unsigned lo = (i & 1) ? b : a;
+    const unsigned hi = (i & 1) ? d : c;
+    return (i & 2) ? hi : lo;
 }
 
 __device__ __forceinline__ float rsqrt_approx(const float x)
@@ -190,7 +198,7 @@ __device__ __forceinline__ float pair_force(const ParamsDev& p,
     }
     if (Fl::ewaldAna)
     {
-        fInvR += qqF * (intBit * invR2 * invR + pme_corr_f(k.beta2 * r2) * k.beta3);
+        fInvR += qqF * (intBit * invR2 * invR + pme_corr_f_beta3(p, r2));
     }
     if (Fl::ewaldTab)
     {
@@ -256,14 +264,6 @@ __device__ __forceinline__ void lj_pair_params(const ParamsDev& p,
             c6grid = epsilon * sigma2 * sigma2 * sigma2;
         }
     }
-}
-
-/* Dynamic-index read of one of four registers without local memory. */
-__device__ __forceinline__ unsigned select4(const unsigned a, const unsigned b, const unsigned c, const unsigned d, const int i)
-{
-    const unsigned lo = (i & 1) ? b : a;
-    const unsigned hi = (i & 1) ? d : c;
-    return (i & 2) ? hi : lo;
 }
 
 /* One (j-cluster, half) against the i-clusters whose bits are set in m8: one atom pair per lane and
@@ -367,6 +367,10 @@ __global__ void __launch_bounds__(32, (ENERGY || PRUNE) ? c_forceMinBlocksPerSM 
     __shared__ float2 sm_lji[64]; // comb params, or (type*numTypes, type) as int bits
     __shared__ float4 sm_xqj[32];
     __shared__ float4 sm_ljj[32]; // (c6, c12) or (type as int bits, -), then the global atom index
+    /* per-lane partial j forces of the current group: [j-atom slot][il ^ (slot & 7)] so that both the stores
+     * (8 different 16-byte columns of one row per quarter warp) and the column sums (8 different columns per
+     * quarter warp) are bank-conflict free */
+    __shared__ __align__(128) float4 sm_fj[32 * c_clusterSize];
 
     const float shx = ad.shiftVec[3 * s.shift], shy = ad.shiftVec[3 * s.shift + 1], shz = ad.shiftVec[3 * s.shift + 2];
 
@@ -431,7 +435,6 @@ __global__ void __launch_bounds__(32, (ENERGY || PRUNE) ? c_forceMinBlocksPerSM 
     const bool         centralShift = (s.shift == c_centralShiftIndex);
     const float        rlistOuter2  = p.rlist_outer_sq;
     int                prunedCount  = 0;
-    unsigned long long pairCount    = 0;
 
     /* Software pipeline over the cjPacked groups of the entry: group descriptors (32 bytes, CTA-uniform
      * loads) are fetched two groups ahead, the 32 j-atoms of a group one group ahead - lane L fetches
@@ -480,7 +483,8 @@ __global__ void __launch_bounds__(32, (ENERGY || PRUNE) ? c_forceMinBlocksPerSM 
 
     for (; jp < s.cj_packed_end; jp++)
     {
-        const uint4 mev = meNext;
+        const uint4 mev   = meNext;
+        const int   ajOwn = __float_as_int(pjNext.z); /* the atom this lane fetched for the group */
         __syncwarp();
         sm_xqj[lane] = xjNext;
         sm_ljj[lane] = pjNext;
@@ -501,10 +505,6 @@ __global__ void __launch_bounds__(32, (ENERGY || PRUNE) ? c_forceMinBlocksPerSM 
         if ((mev.x | mev.z) == 0u)
         {
             continue;
-        }
-        if (pl.pairCount != nullptr)
-        {
-            pairCount += 32ull * (__popc(mev.x) + __popc(mev.z));
         }
         unsigned keep0 = mev.x, keep1 = mev.z;
 
@@ -557,15 +557,11 @@ __global__ void __launch_bounds__(32, (ENERGY || PRUNE) ? c_forceMinBlocksPerSM 
                     eLJ += eLJj;
                     eEl += eElj;
                 }
-                /* reduce the j-atom force over the 8 il-lanes, one v4 reduction per j-atom */
-#pragma unroll
-                for (int m = 1; m < 8; m <<= 1)
+                /* park the lane's partial j force; the group's 32 j-atoms are reduced together below */
                 {
-                    fj.x += __shfl_xor_sync(c_full, fj.x, m);
-                    fj.y += __shfl_xor_sync(c_full, fj.y, m);
-                    fj.z += __shfl_xor_sync(c_full, fj.z, m);
+                    const int slot = static_cast<int>(xqjPtr - sm_xqj);
+                    sm_fj[slot * c_clusterSize + (il ^ (slot & 7))] = make_float4(fj.x, fj.y, fj.z, 0.0f);
                 }
-                red_add_v4_if(il == 0, ad.f4 + aj, fj.x, fj.y, fj.z);
                 if (PRUNE)
                 {
                     cleared |= (m8 & ~keep8) << shift;
@@ -574,6 +570,28 @@ __global__ void __launch_bounds__(32, (ENERGY || PRUNE) ? c_forceMinBlocksPerSM 
             if (PRUNE)
             {
                 if (half) keep1 &= ~cleared; else keep0 &= ~cleared;
+            }
+        }
+        /* j forces of the group: lane L sums the 8 partial forces of j-atom slot L (j-cluster L >> 3, atom
+         * L & 7, i.e. half (L >> 2) & 1) and adds them with ONE v4 reduction; slots of halves that were not
+         * visited hold stale data and are skipped */
+        __syncwarp();
+        {
+            const unsigned visited = (((lane >> 2) & 1) ? mev.z : mev.x) & (0xffu << (8 * (lane >> 3)));
+            if (visited != 0u)
+            {
+                const float4* col = sm_fj + lane * c_clusterSize;
+                const float4  v0  = col[il];
+                float         sx = v0.x, sy = v0.y, sz = v0.z;
+#pragma unroll
+                for (int kx = 1; kx < c_clusterSize; kx++)
+                {
+                    const float4 v = col[kx ^ il];
+                    sx += v.x;
+                    sy += v.y;
+                    sz += v.z;
+                }
+                red_add_v4(ad.f4 + ajOwn, sx, sy, sz);
             }
         }
         if (PRUNE)
@@ -638,10 +656,6 @@ __global__ void __launch_bounds__(32, (ENERGY || PRUNE) ? c_forceMinBlocksPerSM 
         const int index = max(c_sciHistogramSize - prunedCount - 1, 0);
         atomicAdd(pl.sciHistogram + index, 1);
         pl.sciCount[sciIdx] = index;
-    }
-    if (pl.pairCount != nullptr && lane == 0)
-    {
-        atomicAdd(pl.pairCount, pairCount);
     }
 }
 

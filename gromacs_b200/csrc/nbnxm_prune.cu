@@ -204,6 +204,38 @@ __global__ void __launch_bounds__(256) nbnxm_sci_bucket_sort_kernel(const Pairli
     }
 }
 
+/* diagnostics: 32 atom pairs per set imask bit over the cjPacked ranges of all sci entries */
+__global__ void __launch_bounds__(256) nbnxm_count_pairs_kernel(const PairlistDev pl)
+{
+    const int          i = blockIdx.x * blockDim.x + threadIdx.x;
+    unsigned long long n = 0;
+    if (i < pl.numSci)
+    {
+        const nbnxm_b200_sci_t s = pl.sci[i];
+        for (int jp = s.cj_packed_begin; jp < s.cj_packed_end; jp++)
+        {
+            n += 32ull * (__popc(pl.cjPacked[jp].imei[0].imask) + __popc(pl.cjPacked[jp].imei[1].imask));
+        }
+    }
+#pragma unroll
+    for (int m = 16; m > 0; m >>= 1)
+    {
+        n += __shfl_xor_sync(0xffffffffu, n, m);
+    }
+    if ((threadIdx.x & 31) == 0 && n != 0)
+    {
+        atomicAdd(pl.pairCount, n);
+    }
+}
+
+void launch_count_pairs(const PairlistDev& pl, cudaStream_t stream)
+{
+    if (pl.numSci > 0 && pl.pairCount != nullptr)
+    {
+        nbnxm_count_pairs_kernel<<<(pl.numSci + 255) / 256, 256, 0, stream>>>(pl);
+    }
+}
+
 void launch_prune(bool fresh, const AtomDataDev& ad, const ParamsDev& p, const PairlistDev& pl, int numParts, cudaStream_t stream)
 {
     const int units  = (pl.numSci + numParts - 1) / numParts;
