@@ -569,6 +569,12 @@ int nbnxm_b200_launch_kernel(nbnxm_b200_t* nb, int iloc, int compute_energy, int
         launch_count_pairs(pl.dev(true), st);
         nb->launches++;
     }
+    if (nb->carveoutSet.insert(reinterpret_cast<const void*>(kernel)).second)
+    {
+        /* 2.5 - 6.5 KB of shared memory per 32-thread CTA and up to 21 CTAs per SM: ask for the large carve-out */
+        CU(cudaFuncSetAttribute(reinterpret_cast<const void*>(kernel), cudaFuncAttributePreferredSharedMemoryCarveout,
+                                cudaSharedmemCarveoutMaxShared));
+    }
     /* one 32-thread CTA per sci entry */
     kernel<<<pl.numSci, 32, 0, st>>>(nb->ad(), nb->pd, pl.dev(false), compute_virial != 0);
     nb->launches++;

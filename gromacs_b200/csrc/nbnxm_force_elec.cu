@@ -2,7 +2,10 @@
  * the reference builds the same flavor matrix with macros in
  * src/gromacs/nbnxm/cuda/nbnxm_cuda_kernels.cuh and looks kernels up through four function-pointer
  * tables (src/gromacs/nbnxm/cuda/nbnxm_cuda.cu:169-440). */
+#include <cstdlib>
+
 #include "nbnxm_force_kernel.cuh"
+#include "nbnxm_force_kernel_packed.cuh"
 
 #ifndef NBNXM_ELEC
 #    error "compile with -DNBNXM_ELEC=<electrostatics type>"
@@ -11,9 +14,30 @@
 namespace nbb
 {
 
+/* the packed-FP32 kernel where the flavor has one (no fused prune); NBNXM_B200_SCALAR_KERNEL=1
+ * forces the scalar kernel, for A/B measurements */
+template<int VDW, bool AVAILABLE = PackedFlavor<NBNXM_ELEC, VDW>::available>
+struct PackedPick
+{
+    static ForceKernelPtr get(bool) { return nullptr; }
+};
+template<int VDW>
+struct PackedPick<VDW, true>
+{
+    static ForceKernelPtr get(bool energy)
+    {
+        return energy ? nbnxm_force_kernel_packed<NBNXM_ELEC, VDW, true> : nbnxm_force_kernel_packed<NBNXM_ELEC, VDW, false>;
+    }
+};
+
 template<int VDW>
 static ForceKernelPtr pick(bool energy, bool prune)
 {
+    const bool scalarOnly = (std::getenv("NBNXM_B200_SCALAR_KERNEL") != nullptr);
+    if (!prune && !scalarOnly && PackedPick<VDW>::get(energy) != nullptr)
+    {
+        return PackedPick<VDW>::get(energy);
+    }
     if (energy)
     {
         return prune ? nbnxm_force_kernel<NBNXM_ELEC, VDW, true, true> : nbnxm_force_kernel<NBNXM_ELEC, VDW, true, false>;

@@ -7,6 +7,7 @@
 #include <cstdarg>
 #include <cstdio>
 
+#include <set>
 #include <vector>
 
 #include "nbnxm_device.cuh"
@@ -153,6 +154,7 @@ struct nbnxm_b200
     long long                launches     = 0;
 
     nbb::HaloState* halo = nullptr;
+    std::set<const void*> carveoutSet; /* kernels whose shared-memory carve-out preference was set */
 
     nbb::ParamsDev   pd{};
     nbb::AtomDataDev ad() const

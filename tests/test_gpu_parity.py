@@ -48,8 +48,19 @@ def check_forces(f, ref):
     assert maxrel(f, ref) <= F_MAXREL, maxrel(f, ref)
 
 
+@pytest.fixture(params=["packed", "scalar"])
+def kernel_variant(request, monkeypatch):
+    """Force-only launches use the packed-FP32 (FFMA2) kernel where the flavor has one; NBNXM_B200_SCALAR_KERNEL
+    selects the scalar kernel instead (read at every launch), so both are checked against the oracle."""
+    if request.param == "scalar":
+        monkeypatch.setenv("NBNXM_B200_SCALAR_KERNEL", "1")
+    else:
+        monkeypatch.delenv("NBNXM_B200_SCALAR_KERNEL", raising=False)
+    return request.param
+
+
 @pytest.mark.parametrize("case", golden_cases())
-def test_force_energy_virial_parity(oracle, case):
+def test_force_energy_virial_parity(oracle, case, kernel_variant):
     from gromacs_b200 import NbnxmGpu
     d = load_golden(case)
     nbat, plist = product_inputs(d)
