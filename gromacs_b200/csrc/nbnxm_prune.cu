@@ -10,8 +10,8 @@
  * r2 < rlistOuter^2 and is set in the inner mask iff any pair has r2 < rlistInner^2, with
  * xi = float(x_i + shift) and r2 = fma(dz,dz, fma(dy,dy, dx*dx)).
  *
- * Work decomposition: one warp per sci entry; lane = il + 8*jl holds the 8 shifted i-atoms
- * (il of every i-cluster) in registers and tests j-atoms jl (half 0) and jl+4 (half 1), so both
+ * Work decomposition: one warp (= one 32-thread CTA) per sci entry; lane = il + 8*jl holds the 8 shifted
+ * i-atoms (il of every i-cluster) in registers and tests j-atoms jl (half 0) and jl+4 (half 1), so both
  * halves are pruned by the same warp with two warp votes per cluster pair.
  */
 #include "nbnxm_device.cuh"
@@ -19,23 +19,18 @@
 namespace nbb
 {
 
-constexpr int c_pruneWarpsPerBlock = 4;
-
+/* One warp = one 32-thread CTA = one sci entry, like the force kernel: list masks and trip counts are
+ * CTA-uniform.  Only the i-cluster loop is unrolled (the shifted i-atoms live in registers); the j-cluster loop
+ * is not, which keeps the kernel inside the instruction cache. */
 template<bool FRESH>
-__global__ void __launch_bounds__(c_pruneWarpsPerBlock * 32)
-        nbnxm_prune_kernel(const AtomDataDev ad, const ParamsDev p, const PairlistDev pl, const int numParts)
+__global__ void __launch_bounds__(32) nbnxm_prune_kernel(const AtomDataDev ad, const ParamsDev p, const PairlistDev pl, const int numParts)
 {
     constexpr unsigned c_full = 0xffffffffu;
-    const int          lane   = threadIdx.x & 31;
+    const int          lane   = threadIdx.x;
     const int          il     = lane & 7;
     const int          jl     = lane >> 3;
-    const int          unit   = blockIdx.x * c_pruneWarpsPerBlock + (threadIdx.x >> 5);
+    const int          unit   = blockIdx.x;
 
-    const int numUnitsMax = (pl.numSci + numParts - 1) / numParts;
-    if (unit >= numUnitsMax)
-    {
-        return;
-    }
     /* rolling part index lives on the device, one copy per work unit, so consecutive launches need
      * no host bookkeeping (same idea as pruneonly.cuh:123-131) */
     const int part = pl.rollingPart[unit];
@@ -66,65 +61,108 @@ __global__ void __launch_bounds__(c_pruneWarpsPerBlock * 32)
     const float rlistInner2 = p.rlist_inner_sq;
     int         count       = 0;
 
-    for (int jp = s.cj_packed_begin; jp < s.cj_packed_end; jp++)
-    {
-        const int4 cjv = *reinterpret_cast<const int4*>(pl.cjPacked[jp].cj);
-        unsigned   full0, full1, check0, check1, new0, new1;
+    /* the 32 j-atoms of a cjPacked group are fetched by one coalesced 16-byte load per lane (lane L: atom
+     * L & 7 of j-cluster L >> 3), one group ahead of use, and parked in shared memory */
+    __shared__ float4 sm_xqj[32];
+    const uint4*      cjGroups = reinterpret_cast<const uint4*>(pl.cjPacked);
+    const uint2*      outerMasks = reinterpret_cast<const uint2*>(pl.imaskOuter);
+
+    auto checkMasks = [&](const int jpx, uint4& cjv, unsigned& full0, unsigned& full1, unsigned& new0, unsigned& new1) {
+        cjv             = cjGroups[2 * jpx];
+        const uint4 mev = cjGroups[2 * jpx + 1];
         if (FRESH)
         {
-            full0  = pl.cjPacked[jp].imei[0].imask;
-            full1  = pl.cjPacked[jp].imei[1].imask;
-            check0 = full0;
-            check1 = full1;
-            new0   = 0u;
-            new1   = 0u;
+            full0 = mev.x;
+            full1 = mev.z;
+            new0  = 0u;
+            new1  = 0u;
         }
         else
         {
-            const uint2 o = *reinterpret_cast<const uint2*>(pl.imaskOuter + 2 * jp);
+            const uint2 o = outerMasks[jpx];
             full0         = o.x;
             full1         = o.y;
-            new0          = pl.cjPacked[jp].imei[0].imask;
-            new1          = pl.cjPacked[jp].imei[1].imask;
-            check0        = new0 ^ full0;
-            check1        = new1 ^ full1;
+            new0          = mev.x;
+            new1          = mev.z;
         }
-        const unsigned checkAny = check0 | check1;
-        if (checkAny == 0u)
+    };
+    auto fetchAtom = [&](const uint4 cjv, const unsigned checkAny, float4& xj) {
+        if (checkAny & (0xffu << (8 * jl)))
+        {
+            const int cj = static_cast<int>(jl == 0 ? cjv.x : (jl == 1 ? cjv.y : (jl == 2 ? cjv.z : cjv.w)));
+            xj           = ad.xq[cj * c_clusterSize + il];
+        }
+    };
+
+    uint4    cjNext = make_uint4(0u, 0u, 0u, 0u);
+    unsigned full0N = 0u, full1N = 0u, new0N = 0u, new1N = 0u;
+    float4   xjNext = make_float4(0.0f, 0.0f, 0.0f, 0.0f);
+    int      jp     = s.cj_packed_begin;
+    if (jp < s.cj_packed_end)
+    {
+        checkMasks(jp, cjNext, full0N, full1N, new0N, new1N);
+        fetchAtom(cjNext, FRESH ? (full0N | full1N) : ((new0N ^ full0N) | (new1N ^ full1N)), xjNext);
+    }
+    for (; jp < s.cj_packed_end; jp++)
+    {
+        unsigned       full0 = full0N, full1 = full1N, new0 = new0N, new1 = new1N;
+        const unsigned check0 = FRESH ? full0 : (new0 ^ full0);
+        const unsigned check1 = FRESH ? full1 : (new1 ^ full1);
+        __syncwarp();
+        sm_xqj[lane] = xjNext;
+        __syncwarp();
+        if (jp + 1 < s.cj_packed_end)
+        {
+            checkMasks(jp + 1, cjNext, full0N, full1N, new0N, new1N);
+            fetchAtom(cjNext, FRESH ? (full0N | full1N) : ((new0N ^ full0N) | (new1N ^ full1N)), xjNext);
+        }
+        if ((check0 | check1) == 0u)
         {
             continue;
         }
-        const int cjs[4] = { cjv.x, cjv.y, cjv.z, cjv.w };
-#pragma unroll
-        for (int jm = 0; jm < c_jGroupSize; jm++)
+        /* one iteration per j-cluster with anything left to check; both halves in the same pass */
+        unsigned      c0 = check0, c1 = check1;
+        unsigned      clear0 = 0u, clear1 = 0u, set0 = 0u, set1 = 0u; /* outer bits to clear, inner bits to set */
+        const float4* xjPtr = sm_xqj + jl;
+#pragma unroll 1
+        for (int shift = 0; (c0 | c1) != 0u; shift += 8, c0 >>= 8, c1 >>= 8, xjPtr += c_clusterSize)
         {
-            if (checkAny & (0xffu << (jm * 8)))
+            const unsigned m0 = c0 & 0xffu, m1 = c1 & 0xffu;
+            if ((m0 | m1) == 0u)
             {
-                const int    aj0 = cjs[jm] * c_clusterSize + jl;
-                const float4 xj0 = ad.xq[aj0];
-                const float4 xj1 = ad.xq[aj0 + 4];
+                continue;
+            }
+            const float4 xj0 = xjPtr[0];
+            const float4 xj1 = xjPtr[4];
+            unsigned     out0 = 0u, out1 = 0u, in0 = 0u, in1 = 0u; /* cluster pairs with a pair inside rlistOuter / rlistInner */
 #pragma unroll
-                for (int ci = 0; ci < c_superClusterSize; ci++)
+            for (int ci = 0; ci < c_superClusterSize; ci++)
+            {
+                if ((m0 | m1) & (1u << ci))
                 {
-                    const unsigned bit = 1u << (jm * 8 + ci);
-                    if (checkAny & bit)
+                    const float r20 = norm2_fma(__fsub_rn(xi[ci], xj0.x), __fsub_rn(yi[ci], xj0.y), __fsub_rn(zi[ci], xj0.z));
+                    const float r21 = norm2_fma(__fsub_rn(xi[ci], xj1.x), __fsub_rn(yi[ci], xj1.y), __fsub_rn(zi[ci], xj1.z));
+                    if (FRESH)
                     {
-                        const float r20 = norm2_fma(__fsub_rn(xi[ci], xj0.x), __fsub_rn(yi[ci], xj0.y), __fsub_rn(zi[ci], xj0.z));
-                        const float r21 = norm2_fma(__fsub_rn(xi[ci], xj1.x), __fsub_rn(yi[ci], xj1.y), __fsub_rn(zi[ci], xj1.z));
-                        if (check0 & bit)
-                        {
-                            if (FRESH && !__any_sync(c_full, r20 < rlistOuter2)) full0 &= ~bit;
-                            if (__any_sync(c_full, r20 < rlistInner2)) new0 |= bit;
-                        }
-                        if (check1 & bit)
-                        {
-                            if (FRESH && !__any_sync(c_full, r21 < rlistOuter2)) full1 &= ~bit;
-                            if (__any_sync(c_full, r21 < rlistInner2)) new1 |= bit;
-                        }
+                        if (__any_sync(c_full, r20 < rlistOuter2)) out0 |= 1u << ci;
+                        if (__any_sync(c_full, r21 < rlistOuter2)) out1 |= 1u << ci;
                     }
+                    if (__any_sync(c_full, r20 < rlistInner2)) in0 |= 1u << ci;
+                    if (__any_sync(c_full, r21 < rlistInner2)) in1 |= 1u << ci;
                 }
             }
+            if (FRESH)
+            {
+                clear0 |= (m0 & ~out0) << shift;
+                clear1 |= (m1 & ~out1) << shift;
+            }
+            set0 |= (m0 & in0) << shift;
+            set1 |= (m1 & in1) << shift;
         }
+        full0 &= ~clear0;
+        full1 &= ~clear1;
+        new0 |= set0;
+        new1 |= set1;
         if (lane == 0)
         {
             /* like the reference, a half whose check mask is empty is left untouched */
@@ -238,15 +276,14 @@ void launch_count_pairs(const PairlistDev& pl, cudaStream_t stream)
 
 void launch_prune(bool fresh, const AtomDataDev& ad, const ParamsDev& p, const PairlistDev& pl, int numParts, cudaStream_t stream)
 {
-    const int units  = (pl.numSci + numParts - 1) / numParts;
-    const int blocks = (units + c_pruneWarpsPerBlock - 1) / c_pruneWarpsPerBlock;
+    const int units = (pl.numSci + numParts - 1) / numParts;
     if (fresh)
     {
-        nbnxm_prune_kernel<true><<<blocks, c_pruneWarpsPerBlock * 32, 0, stream>>>(ad, p, pl, numParts);
+        nbnxm_prune_kernel<true><<<units, 32, 0, stream>>>(ad, p, pl, numParts);
     }
     else
     {
-        nbnxm_prune_kernel<false><<<blocks, c_pruneWarpsPerBlock * 32, 0, stream>>>(ad, p, pl, numParts);
+        nbnxm_prune_kernel<false><<<units, 32, 0, stream>>>(ad, p, pl, numParts);
     }
 }
 
