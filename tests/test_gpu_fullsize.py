@@ -1,0 +1,88 @@
+"""GPU tests at BASELINE.json's benchmark sizes: the 96k-atom box against the double-precision oracle on the
+whole list, and the 1.5M-atom box through size-independent properties (Newton's third law, pruning does not
+change forces, packed and scalar kernels agree, a sub-list against the oracle)."""
+import numpy as np
+import pytest
+
+from util import relrms
+
+pytestmark = pytest.mark.gpu
+
+
+def orc_params(oracle, wl):
+    p = oracle.OrcParams()
+    for name, _ in wl.params._fields_:
+        if hasattr(p, name):
+            setattr(p, name, getattr(wl.params, name))
+    p.ntypes = wl.nbat.numTypes
+    return p
+
+
+def gpu_forces(wl, plist, energy, dynamic_pruning=None, rolling_steps=0):
+    from gromacs_b200 import LOCAL, NbnxmGpu, StepWorkload
+    import copy
+    params = copy.copy(wl.params)
+    if dynamic_pruning is not None:
+        params.use_dynamic_pruning = int(dynamic_pruning)
+    nbat = wl.nbat
+    nb = NbnxmGpu(params, nbat)
+    try:
+        sw = StepWorkload(computeEnergy=energy, computeVirial=energy)
+        nb.gpu_init_atomdata(nbat)
+        nb.gpu_init_pairlist(plist, LOCAL)
+        nb.setupGpuShortRangeWork(LOCAL)
+        nb.gpu_upload_shiftvec(nbat)
+        nb.gpu_copy_xq_to_gpu(nbat, LOCAL)
+        e = (0.0, 0.0)
+        for step in range(1 + rolling_steps):
+            nb.gpu_clear_outputs(True)
+            nb.gpu_launch_kernel(sw, LOCAL)
+            if step > 0 and params.use_dynamic_pruning:
+                nb.gpu_launch_kernel_pruneonly(LOCAL, 3)
+            nb.gpu_launch_cpyback(nbat, sw, LOCAL)
+            e = nb.gpu_wait_finish_task(sw, LOCAL)
+        return nbat.f.astype(np.float64).copy(), e
+    finally:
+        nb.gpu_free()
+
+
+def test_96k_force_switch_box_matches_oracle(oracle):
+    """BASELINE configs[1]: 96 000 atoms, rc 1.0, Ewald + LJ force-switch, F+E; whole list through the oracle."""
+    from gromacs_b200.workload import make_workload
+    wl = make_workload("water96k_fswitch")
+    plist = wl.pairlist(min_sci=4000)
+    g = wl.nbat
+    f_ref, _, e_ref, _ = oracle.forces(orc_params(oracle, wl), plist.sci, plist.cjPacked, plist.excl, g.xq, g.type,
+                                       np.zeros((g.numAtoms(), 2), np.float32), g.nbfp, g.nbfp_comb, g.shift_vec)
+    f, (e_lj, e_el) = gpu_forces(wl, plist, energy=True, rolling_steps=6)
+    assert relrms(f, f_ref) <= 5e-6
+    assert np.abs(f - f_ref).max() <= 1e-4 * np.abs(f_ref).max()
+    assert abs(e_el - e_ref[1]) <= 1e-6 * abs(e_ref[1]), (e_el, e_ref[1])
+    assert abs(e_lj - e_ref[0]) <= 1e-6 * abs(e_ref[0]), (e_lj, e_ref[0])
+
+
+def test_1536k_box_properties(oracle, monkeypatch):
+    """BASELINE configs[3] at full size."""
+    from gromacs_b200.workload import make_workload
+    from gromacs_b200 import PairlistGpu
+    wl = make_workload("water1536k")
+    plist = wl.pairlist(min_sci=18944)
+    # dynamic pruning + a full rolling cycle vs. the unpruned outer list: pruning only drops pairs beyond rc
+    f_pruned, _ = gpu_forces(wl, plist, energy=False, dynamic_pruning=True, rolling_steps=6)
+    f_outer, _ = gpu_forces(wl, plist, energy=False, dynamic_pruning=False)
+    assert relrms(f_pruned, f_outer) <= 2e-6
+    # Newton's third law: the forces sum to zero up to float32 accumulation noise
+    scale = np.abs(f_pruned).sum(0)
+    assert np.all(np.abs(f_pruned.sum(0)) <= 1e-6 * scale), (f_pruned.sum(0), scale)
+    # packed (FFMA2) and scalar kernels are two evaluations of the same pairs
+    monkeypatch.setenv("NBNXM_B200_SCALAR_KERNEL", "1")
+    f_scalar, _ = gpu_forces(wl, plist, energy=False, dynamic_pruning=True, rolling_steps=2)
+    monkeypatch.delenv("NBNXM_B200_SCALAR_KERNEL")
+    assert relrms(f_pruned, f_scalar) <= 2e-6
+    # a sub-list (every 40th sci entry) against the float32 oracle port on the same entries
+    sub = PairlistGpu(sci=plist.sci[::40], cjPacked=plist.cjPacked, excl=plist.excl)
+    g = wl.nbat
+    f32, _, _ = oracle.forces_f32_omp(orc_params(oracle, wl), sub.sci, sub.cjPacked, sub.excl, g.xq, g.type, g.lj_comb, g.nbfp,
+                                      g.nbfp_comb, g.shift_vec, nthreads=8)
+    f_sub, _ = gpu_forces(wl, sub, energy=False, dynamic_pruning=False)
+    assert relrms(f_sub, f32.astype(np.float64)) <= 5e-6
