@@ -26,16 +26,16 @@ void launch_pack_xq(const float4* xq, const int* index, int n, const float* shif
 void launch_copy4(const float4* in, float4* out, int n, cudaStream_t s);
 void launch_unpack_add_f(float4* f4, const int* index, int n, const float4* in, cudaStream_t s);
 
-ForceKernelPtr select_force_kernel(int elec, int vdw, bool energy, bool prune)
+ForceKernelPtr select_force_kernel(int elec, int vdw, bool energy, bool prune, int numTypes)
 {
     switch (elec)
     {
-        case NBNXM_B200_ELEC_CUT: return select_force_kernel_elec<NBNXM_B200_ELEC_CUT>(vdw, energy, prune);
-        case NBNXM_B200_ELEC_RF: return select_force_kernel_elec<NBNXM_B200_ELEC_RF>(vdw, energy, prune);
-        case NBNXM_B200_ELEC_EWALD_TAB: return select_force_kernel_elec<NBNXM_B200_ELEC_EWALD_TAB>(vdw, energy, prune);
-        case NBNXM_B200_ELEC_EWALD_TAB_TWIN: return select_force_kernel_elec<NBNXM_B200_ELEC_EWALD_TAB_TWIN>(vdw, energy, prune);
-        case NBNXM_B200_ELEC_EWALD_ANA: return select_force_kernel_elec<NBNXM_B200_ELEC_EWALD_ANA>(vdw, energy, prune);
-        case NBNXM_B200_ELEC_EWALD_ANA_TWIN: return select_force_kernel_elec<NBNXM_B200_ELEC_EWALD_ANA_TWIN>(vdw, energy, prune);
+        case NBNXM_B200_ELEC_CUT: return select_force_kernel_elec<NBNXM_B200_ELEC_CUT>(vdw, energy, prune, numTypes);
+        case NBNXM_B200_ELEC_RF: return select_force_kernel_elec<NBNXM_B200_ELEC_RF>(vdw, energy, prune, numTypes);
+        case NBNXM_B200_ELEC_EWALD_TAB: return select_force_kernel_elec<NBNXM_B200_ELEC_EWALD_TAB>(vdw, energy, prune, numTypes);
+        case NBNXM_B200_ELEC_EWALD_TAB_TWIN: return select_force_kernel_elec<NBNXM_B200_ELEC_EWALD_TAB_TWIN>(vdw, energy, prune, numTypes);
+        case NBNXM_B200_ELEC_EWALD_ANA: return select_force_kernel_elec<NBNXM_B200_ELEC_EWALD_ANA>(vdw, energy, prune, numTypes);
+        case NBNXM_B200_ELEC_EWALD_ANA_TWIN: return select_force_kernel_elec<NBNXM_B200_ELEC_EWALD_ANA_TWIN>(vdw, energy, prune, numTypes);
         default: return nullptr;
     }
 }
@@ -60,7 +60,7 @@ int fail(const char* fmt, ...)
 namespace
 {
 
-void fillParamsDev(nbnxm_b200* nb)
+int fillParamsDev(nbnxm_b200* nb)
 {
     const nbnxm_b200_params_t& s = nb->params;
     ParamsDev&                 d = nb->pd;
@@ -91,6 +91,20 @@ void fillParamsDev(nbnxm_b200* nb)
     d.nbfp       = nb->nbfp.p;
     d.nbfpComb   = nb->nbfpComb.p;
     d.coulombTab = nb->coulombTab.p;
+    {
+        /* the packed kernel reads its pair-body constants from global memory (nbnxm_force_kernel_packed.cuh);
+         * kernels of earlier steps may still be reading the previous values */
+        float h[13];
+        h[0] = d.rcoulomb_sq;
+        for (int k = 0; k < 7; k++) h[1 + k] = d.pmeNum[k];
+        for (int k = 0; k < 5; k++) h[8 + k] = d.pmeDen[k];
+        CU(nb->packedConsts.reserve(16));
+        if (nb->stream[0]) CU(cudaStreamSynchronize(nb->stream[0]));
+        if (nb->stream[1]) CU(cudaStreamSynchronize(nb->stream[1]));
+        CU(cudaMemcpy(nb->packedConsts.p, h, sizeof(h), cudaMemcpyHostToDevice));
+        d.packedConsts = nb->packedConsts.p;
+    }
+    return 0;
 }
 
 bool usesLjComb(int vdw) { return vdw == NBNXM_B200_VDW_CUT_COMB_GEOM || vdw == NBNXM_B200_VDW_CUT_COMB_LB; }
@@ -244,7 +258,7 @@ int nbnxm_b200_init(nbnxm_b200_t** out, int device, const nbnxm_b200_params_t* p
         CU(cudaMemsetAsync(nb->plist[l].pairCount.p, 0, sizeof(unsigned long long), nb->stream[0]));
     }
     CU(cudaStreamSynchronize(nb->stream[0]));
-    fillParamsDev(nb);
+    if (fillParamsDev(nb)) return 1;
     *out = nb;
     return 0;
 }
@@ -258,7 +272,7 @@ int nbnxm_b200_free(nbnxm_b200_t* nb)
     collectTimings(nb);
     nb->xq.release(); nb->f4.release(); nb->f3.release(); nb->atomType.release(); nb->ljComb.release();
     nb->shiftVec.release(); nb->fshift.release(); nb->energy.release(); nb->nbfp.release();
-    nb->nbfpComb.release(); nb->coulombTab.release(); nb->atomIndex.release();
+    nb->nbfpComb.release(); nb->coulombTab.release(); nb->atomIndex.release(); nb->packedConsts.release();
     for (PairList& pl : nb->plist)
     {
         pl.sci.release(); pl.sciSorted.release(); pl.sciCount.release(); pl.sciHistogram.release();
@@ -291,8 +305,7 @@ int nbnxm_b200_update_params(nbnxm_b200_t* nb, const nbnxm_b200_params_t* params
         CU(nb->coulombTab.reserve(coulomb_tab_size));
         CU(cudaMemcpyAsync(nb->coulombTab.p, coulomb_tab, sizeof(float) * coulomb_tab_size, cudaMemcpyHostToDevice, nb->stream[0]));
     }
-    fillParamsDev(nb);
-    return 0;
+    return fillParamsDev(nb);
 }
 
 int nbnxm_b200_init_pairlist(nbnxm_b200_t* nb, int iloc, const nbnxm_b200_sci_t* sci, int nsci,
@@ -557,7 +570,7 @@ int nbnxm_b200_launch_kernel(nbnxm_b200_t* nb, int iloc, int compute_energy, int
     }
     if (!nb->shiftVecUploaded) return fail("nbnxm_b200_launch_kernel: shift vectors were never uploaded");
     const bool     doPrune = pl.haveFreshList && !pl.didPrune;
-    ForceKernelPtr kernel  = select_force_kernel(nb->params.elec_type, nb->params.vdw_type, compute_energy != 0, doPrune);
+    ForceKernelPtr kernel  = select_force_kernel(nb->params.elec_type, nb->params.vdw_type, compute_energy != 0, doPrune, nb->numTypes);
     if (!kernel)
     {
         return fail("nbnxm_b200_launch_kernel: no kernel for elec_type %d vdw_type %d", nb->params.elec_type, nb->params.vdw_type);

@@ -56,6 +56,8 @@ struct ParamsDev
     const float2* nbfp;
     const float2* nbfpComb;
     const float*  coulombTab;
+    /* device copy of {rcoulomb_sq, pmeNum[7], pmeDen[5]} for the packed kernel (nbnxm_force_kernel_packed.cuh) */
+    const float*  packedConsts;
 };
 
 struct PairlistDev

@@ -31,10 +31,12 @@ struct PackedPick<VDW, true>
 };
 
 template<int VDW>
-static ForceKernelPtr pick(bool energy, bool prune)
+static ForceKernelPtr pick(bool energy, bool prune, int numTypes)
 {
     const bool scalarOnly = (std::getenv("NBNXM_B200_SCALAR_KERNEL") != nullptr);
-    if (!prune && !scalarOnly && PackedPick<VDW>::get(energy) != nullptr)
+    /* the packed kernel stages the type table of the flavors that use one in shared memory */
+    const bool typesFit = !PackedFlavor<NBNXM_ELEC, VDW>::typeTable || numTypes <= c_packedMaxTypes;
+    if (!prune && !scalarOnly && typesFit && PackedPick<VDW>::get(energy) != nullptr)
     {
         return PackedPick<VDW>::get(energy);
     }
@@ -46,17 +48,17 @@ static ForceKernelPtr pick(bool energy, bool prune)
 }
 
 template<>
-ForceKernelPtr select_force_kernel_elec<NBNXM_ELEC>(int vdw, bool energy, bool prune)
+ForceKernelPtr select_force_kernel_elec<NBNXM_ELEC>(int vdw, bool energy, bool prune, int numTypes)
 {
     switch (vdw)
     {
-        case NBNXM_B200_VDW_CUT: return pick<NBNXM_B200_VDW_CUT>(energy, prune);
-        case NBNXM_B200_VDW_CUT_COMB_GEOM: return pick<NBNXM_B200_VDW_CUT_COMB_GEOM>(energy, prune);
-        case NBNXM_B200_VDW_CUT_COMB_LB: return pick<NBNXM_B200_VDW_CUT_COMB_LB>(energy, prune);
-        case NBNXM_B200_VDW_FSWITCH: return pick<NBNXM_B200_VDW_FSWITCH>(energy, prune);
-        case NBNXM_B200_VDW_PSWITCH: return pick<NBNXM_B200_VDW_PSWITCH>(energy, prune);
-        case NBNXM_B200_VDW_EWALD_GEOM: return pick<NBNXM_B200_VDW_EWALD_GEOM>(energy, prune);
-        case NBNXM_B200_VDW_EWALD_LB: return pick<NBNXM_B200_VDW_EWALD_LB>(energy, prune);
+        case NBNXM_B200_VDW_CUT: return pick<NBNXM_B200_VDW_CUT>(energy, prune, numTypes);
+        case NBNXM_B200_VDW_CUT_COMB_GEOM: return pick<NBNXM_B200_VDW_CUT_COMB_GEOM>(energy, prune, numTypes);
+        case NBNXM_B200_VDW_CUT_COMB_LB: return pick<NBNXM_B200_VDW_CUT_COMB_LB>(energy, prune, numTypes);
+        case NBNXM_B200_VDW_FSWITCH: return pick<NBNXM_B200_VDW_FSWITCH>(energy, prune, numTypes);
+        case NBNXM_B200_VDW_PSWITCH: return pick<NBNXM_B200_VDW_PSWITCH>(energy, prune, numTypes);
+        case NBNXM_B200_VDW_EWALD_GEOM: return pick<NBNXM_B200_VDW_EWALD_GEOM>(energy, prune, numTypes);
+        case NBNXM_B200_VDW_EWALD_LB: return pick<NBNXM_B200_VDW_EWALD_LB>(energy, prune, numTypes);
         default: return nullptr;
     }
 }

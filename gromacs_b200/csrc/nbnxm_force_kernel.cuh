@@ -663,9 +663,9 @@ typedef void (*ForceKernelPtr)(const AtomDataDev, const ParamsDev, const Pairlis
 
 /* one translation unit per electrostatics type instantiates its 7 x 2 x 2 kernels */
 template<int ELEC>
-ForceKernelPtr select_force_kernel_elec(int vdw, bool energy, bool prune);
+ForceKernelPtr select_force_kernel_elec(int vdw, bool energy, bool prune, int numTypes);
 
-ForceKernelPtr select_force_kernel(int elec, int vdw, bool energy, bool prune);
+ForceKernelPtr select_force_kernel(int elec, int vdw, bool energy, bool prune, int numTypes);
 
 } // namespace nbb
 

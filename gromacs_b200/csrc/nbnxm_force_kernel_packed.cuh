@@ -1,17 +1,27 @@
-/* Packed-FP32 (FFMA2 / FMUL2 / FADD2) force-only kernel of the nbnxm_b200 path.
+/* Packed-FP32 (FFMA2 / FMUL2 / FADD2) force kernel of the nbnxm_b200 path, force-only and force+energy.
  *
- * sm_100a can issue one instruction that does two FP32 FMAs on a 64-bit register pair (PTX
- * fma.rn.f32x2, SASS FFMA2; scalar registers, immediates and negations broadcast as operands for free).
- * It has the FLOP throughput of FFMA but half its issue-slot cost (profiles/microbench/fp32_peak.cu), and the
- * scalar kernel is issue bound, not FMA-pipe bound.  So this kernel evaluates the TWO halves of a cluster
- * pair - j-atoms jl and jl+4 of a j-cluster against the same i-atom - as one packed pair stream: every
- * quantity of the pair physics is a (half 0, half 1) register pair.  A cluster pair of which only one half
- * survived pruning (about one in six) runs with the other half masked off.
+ * On sm_100a the FP32 pipe retires one warp-wide FFMA per scheduler per clock, i.e. the FP32 peak IS the issue
+ * peak: every instruction that is not an FMA takes a slot away from it (profiles/r01d_force_packed.txt,
+ * profiles/microbench).  This kernel is therefore built around the instruction count per atom pair:
+ *   - the two halves of a cluster pair (j-atoms jl and jl+4 against the same i-atom) are one packed pair stream
+ *     (fma.rn.f32x2): ALU, MUFU-feeding, shared-memory and control instructions are shared by two pairs.  A
+ *     cluster pair of which only one half survived pruning (about one in four) runs a scalar body on that half
+ *     in the force-only kernel, so a pruned half costs nothing;
+ *   - the pair force is evaluated as W = (F/r) r^2 (one multiplication by r^-2 at the end, no r^-3), the Ewald
+ *     correction polynomial runs on r^2 with the powers of beta folded into its coefficients, and the r^2 = 0
+ *     guard of filler atoms is an additive 1e-12 inside the first FMA instead of a max;
+ *   - the path with exclusion masks is chosen per (j-cluster, i-cluster) from a warp-wide OR of the mask words,
+ *     not per cjPacked group, and is one non-unrolled loop: about 3 % of the cluster pairs of a water box carry
+ *     exclusions, but 28 % of the groups do;
+ *   - per-group bookkeeping is kept small: every lane loads the j-cluster index it needs itself, the lane-dependent
+ *     shared-memory offsets are computed once (and kept from being re-derived from the thread index in every
+ *     body), partial j forces are parked without sign change in rows padded to 9 float4 (conflict-free without a
+ *     swizzle) and reduced once per group.
  *
- * Same list walk, staging and reductions as nbnxm_force_kernel (nbnxm_force_kernel.cuh), which remains the
- * kernel for the energy and fused-prune variants and for the flavors that need per-pair table look-ups or
- * expf (tabulated Ewald, LJ-PME).  Physics from src/gromacs/nbnxm/nbnxm_kernel_utils.h:56-289 and
- * src/gromacs/nbnxm/cuda/nbnxm_cuda_kernel.cuh:505-660.
+ * Same list walk and reductions as nbnxm_force_kernel (nbnxm_force_kernel.cuh), which remains the kernel for the
+ * fused-prune variant, for the flavors that need per-pair table look-ups or expf (tabulated Ewald, LJ-PME) and for
+ * type-table flavors with more than c_packedMaxTypes atom types.  Physics from
+ * src/gromacs/nbnxm/nbnxm_kernel_utils.h:56-289 and src/gromacs/nbnxm/cuda/nbnxm_cuda_kernel.cuh:505-660.
  */
 #ifndef NBNXM_B200_FORCE_KERNEL_PACKED_CUH
 #define NBNXM_B200_FORCE_KERNEL_PACKED_CUH
@@ -21,18 +31,22 @@
 namespace nbb
 {
 
-/* resident CTAs per SM the packed kernel is compiled for: two pair streams per lane want ~120 registers (ptxas rematerialises addresses in every pair body below that) */
+/* resident CTAs (= warps) per SM the kernels are compiled for */
 #ifndef NBNXM_PACKED_MIN_BLOCKS
-#    define NBNXM_PACKED_MIN_BLOCKS 14
+#    define NBNXM_PACKED_MIN_BLOCKS 20
 #endif
-constexpr int c_packedMinBlocksPerSM = NBNXM_PACKED_MIN_BLOCKS;
-/* i-force accumulators: packed (half 0, half 1) pairs (48 registers, 3 FFMA2 per pair body) or scalars (24
- * registers, 6 FFMA) */
-#ifndef NBNXM_PACKED_FI
-#    define NBNXM_PACKED_FI 1
+#ifndef NBNXM_PACKED_MIN_BLOCKS_ENERGY
+#    define NBNXM_PACKED_MIN_BLOCKS_ENERGY 16
 #endif
+/* type-table flavors keep nbfp in shared memory: at most this many atom types */
+constexpr int c_packedMaxTypes = 8;
+/* added to r^2 in the force-only path without exclusions: keeps r^-6 finite for coinciding filler atoms
+ * (whose parameters are zero) and is below half an ulp of any r^2 > 2e-5 nm^2 */
+constexpr float c_r2Guard = 1.0e-12f;
 
 typedef unsigned long long f32x2; /* (lo, hi) = (half 0, half 1) */
+
+#pragma nv_diag_suppress 550 /* the unused half of an unpacked register pair */
 
 __device__ __forceinline__ f32x2 pk(const float lo, const float hi)
 {
@@ -40,46 +54,81 @@ __device__ __forceinline__ f32x2 pk(const float lo, const float hi)
     asm("mov.b64 %0, {%1, %2};" : "=l"(r) : "f"(lo), "f"(hi));
     return r;
 }
-__device__ __forceinline__ f32x2 bc(const float a)
-{
-    return pk(a, a);
-}
 __device__ __forceinline__ float lo(const f32x2 v)
 {
     float a, b;
     asm("mov.b64 {%0, %1}, %2;" : "=f"(a), "=f"(b) : "l"(v));
+    (void)b;
     return a;
 }
 __device__ __forceinline__ float hi(const f32x2 v)
 {
     float a, b;
     asm("mov.b64 {%0, %1}, %2;" : "=f"(a), "=f"(b) : "l"(v));
+    (void)a;
     return b;
 }
-__device__ __forceinline__ f32x2 fma2(const f32x2 a, const f32x2 b, const f32x2 c)
+
+/* The pair physics is written once for V = f32x2 (two pairs per lane) and V = float (one pair). */
+__device__ __forceinline__ f32x2 vfma(const f32x2 a, const f32x2 b, const f32x2 c)
 {
     f32x2 d;
     asm("fma.rn.f32x2 %0, %1, %2, %3;" : "=l"(d) : "l"(a), "l"(b), "l"(c));
     return d;
 }
-__device__ __forceinline__ f32x2 mul2(const f32x2 a, const f32x2 b)
+__device__ __forceinline__ f32x2 vmul(const f32x2 a, const f32x2 b)
 {
     f32x2 d;
     asm("mul.rn.f32x2 %0, %1, %2;" : "=l"(d) : "l"(a), "l"(b));
     return d;
 }
-__device__ __forceinline__ f32x2 add2(const f32x2 a, const f32x2 b)
+__device__ __forceinline__ f32x2 vadd(const f32x2 a, const f32x2 b)
 {
     f32x2 d;
     asm("add.rn.f32x2 %0, %1, %2;" : "=l"(d) : "l"(a), "l"(b));
     return d;
 }
-__device__ __forceinline__ f32x2 sub2(const f32x2 a, const f32x2 b)
+__device__ __forceinline__ f32x2 vsub(const f32x2 a, const f32x2 b)
 {
     f32x2 d;
     asm("sub.rn.f32x2 %0, %1, %2;" : "=l"(d) : "l"(a), "l"(b));
     return d;
 }
+__device__ __forceinline__ float vfma(const float a, const float b, const float c) { return fmaf(a, b, c); }
+__device__ __forceinline__ float vmul(const float a, const float b) { return a * b; }
+__device__ __forceinline__ float vadd(const float a, const float b) { return a + b; }
+__device__ __forceinline__ float vsub(const float a, const float b) { return a - b; }
+
+template<typename V>
+__device__ __forceinline__ V vbc(const float a);
+template<>
+__device__ __forceinline__ f32x2 vbc<f32x2>(const float a) { return pk(a, a); }
+template<>
+__device__ __forceinline__ float vbc<float>(const float a) { return a; }
+
+__device__ __forceinline__ float rcp_approx(const float x)
+{
+    float y;
+    asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x));
+    return y;
+}
+__device__ __forceinline__ float ex2_approx(const float x)
+{
+    float y;
+    asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x));
+    return y;
+}
+__device__ __forceinline__ float vrsqrt(const float x) { return rsqrt_approx(x); }
+__device__ __forceinline__ f32x2 vrsqrt(const f32x2 x) { return pk(rsqrt_approx(lo(x)), rsqrt_approx(hi(x))); }
+__device__ __forceinline__ float vrcp(const float x) { return rcp_approx(x); }
+__device__ __forceinline__ f32x2 vrcp(const f32x2 x) { return pk(rcp_approx(lo(x)), rcp_approx(hi(x))); }
+__device__ __forceinline__ float vex2(const float x) { return ex2_approx(x); }
+__device__ __forceinline__ f32x2 vex2(const f32x2 x) { return pk(ex2_approx(lo(x)), ex2_approx(hi(x))); }
+__device__ __forceinline__ float vmax0(const float x) { return fmaxf(x, 0.0f); }
+__device__ __forceinline__ f32x2 vmax0(const f32x2 x) { return pk(fmaxf(lo(x), 0.0f), fmaxf(hi(x), 0.0f)); }
+/* 1 where x < c, else 0 */
+__device__ __forceinline__ float vless(const float x, const float c) { return x < c ? 1.0f : 0.0f; }
+__device__ __forceinline__ f32x2 vless(const f32x2 x, const float c) { return pk(lo(x) < c ? 1.0f : 0.0f, hi(x) < c ? 1.0f : 0.0f); }
 
 /* flavors the packed kernel covers */
 template<int ELEC, int VDW>
@@ -87,326 +136,453 @@ struct PackedFlavor
 {
     using Fl                        = Flavor<ELEC, VDW, false>;
     static constexpr bool available = !Fl::ewaldTab && !Fl::ljEwald;
+    /* LJ parameters from the type table (staged in shared memory) instead of per-atom combination parameters */
+    static constexpr bool typeTable = !Fl::ljComb;
 };
 
-/* beta^3 pmeCorrF(beta^2 r^2) for both halves (coefficients: nbnxm_kernel_utils.h:216-250) */
-__device__ __forceinline__ f32x2 pme_corr_f_packed(const f32x2 z2)
+/* erfc(x), x >= 0: t P(t) form with t = 1 / (1 + x/2), P a degree-9 fit of erfc(x) exp(x^2) (relative fit error
+ * 2.6e-9 on [0, 3.6]; in float32 about 3e-7 absolute, like erfcf), times exp(-x^2) with the rounding error of x^2
+ * compensated.  15 FP32 operations and 2 MUFU per value, against ~55 instructions for erfcf. */
+template<typename V>
+__device__ __forceinline__ V erfc_poly(const V x)
 {
-    f32x2 den = fma2(z2, bc(0.0011193462567257629232f), bc(0.014866955030185295499f));
-    den       = fma2(den, z2, bc(0.11583842382862377919f));
-    den       = fma2(den, z2, bc(0.50736591960530292870f));
-    den       = fma2(den, z2, bc(1.0f));
-    f32x2 num = fma2(z2, bc(-1.7357322914161492954e-8f), bc(1.4703624142580877519e-6f));
-    num       = fma2(num, z2, bc(-0.000053401640219807709149f));
-    num       = fma2(num, z2, bc(0.0010054721316683106153f));
-    num       = fma2(num, z2, bc(-0.019278317264888380590f));
-    num       = fma2(num, z2, bc(0.069670166153766424023f));
-    num       = fma2(num, z2, bc(-0.75225204789749321333f));
-    float r0, r1;
-    asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(r0) : "f"(lo(den)));
-    asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(r1) : "f"(hi(den)));
-    return mul2(num, pk(r0, r1));
+    const V t = vrcp(vfma(x, vbc<V>(0.5f), vbc<V>(1.0f)));
+    V       q = vfma(t, vbc<V>(-1.744380291e-02f), vbc<V>(4.996527726e-02f));
+    q         = vfma(q, t, vbc<V>(8.959100685e-02f));
+    q         = vfma(q, t, vbc<V>(-5.334397185e-01f));
+    q         = vfma(q, t, vbc<V>(6.932961627e-01f));
+    q         = vfma(q, t, vbc<V>(-2.149867186e-01f));
+    q         = vfma(q, t, vbc<V>(4.016416182e-01f));
+    q         = vfma(q, t, vbc<V>(2.443820402e-01f));
+    q         = vfma(q, t, vbc<V>(2.873080888e-01f));
+    q         = vfma(q, t, vbc<V>(-3.139566102e-04f));
+    const V x2hi = vmul(x, x);
+    const V x2lo = vfma(x, x, vsub(vbc<V>(0.0f), x2hi));
+    V       e    = vex2(vmul(x2hi, vbc<V>(-1.4426950408889634f)));
+    e            = vfma(vsub(vbc<V>(0.0f), e), x2lo, e);
+    return vmul(q, e);
 }
 
-/* erfc(x), x >= 0, for both halves: t P(t) form with t = 1 / (1 + x/2), P a degree-9 fit of erfc(x) exp(x^2)
- * (relative fit error 2.6e-9 on [0, 3.6]; in float32 about 3e-7 absolute, like erfcf), times exp(-x^2) with the
- * rounding error of x^2 compensated.  15 packed FP32 operations and 4 MUFU for two values, against ~55
- * instructions per value for erfcf. */
-__device__ __forceinline__ f32x2 erfc_packed(const f32x2 x)
+/* constants of the pair bodies that are the same for every pair of a launch (uniform registers) */
+struct PackedConsts
 {
-    const f32x2 d = fma2(x, bc(0.5f), bc(1.0f));
-    float       t0, t1;
-    asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(t0) : "f"(lo(d)));
-    asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(t1) : "f"(hi(d)));
-    const f32x2 t = pk(t0, t1);
-    f32x2       q = fma2(t, bc(-1.744380291e-02f), bc(4.996527726e-02f));
-    q             = fma2(q, t, bc(8.959100685e-02f));
-    q             = fma2(q, t, bc(-5.334397185e-01f));
-    q             = fma2(q, t, bc(6.932961627e-01f));
-    q             = fma2(q, t, bc(-2.149867186e-01f));
-    q             = fma2(q, t, bc(4.016416182e-01f));
-    q             = fma2(q, t, bc(2.443820402e-01f));
-    q             = fma2(q, t, bc(2.873080888e-01f));
-    q             = fma2(q, t, bc(-3.139566102e-04f));
-    const f32x2 x2hi = mul2(x, x);
-    const f32x2 x2lo = fma2(x, x, sub2(bc(0.0f), x2hi));
-    const f32x2 arg  = mul2(x2hi, bc(-1.4426950408889634f));
-    float       e0, e1;
-    asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(e0) : "f"(lo(arg)));
-    asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(e1) : "f"(hi(arg)));
-    f32x2 e = pk(e0, e1);
-    e       = fma2(sub2(bc(0.0f), e), x2lo, e);
-    return mul2(q, e);
-}
+    float rc2, rvdw2, beta, epsfac;
+    float num[7], den[5]; /* pmeCorrF with beta folded in: beta^3 pmeCorrF(beta^2 r^2) = num(r^2) / den(r^2) */
+};
 
-/* F/r of the two pairs (not yet masked). c6n = -6*C6, c12 = 12*C12, qq = epsfac*qi*qj; intBit = 1/0 per
- * half, only read when EXCL. r2 already clamped to c_minDistanceSquared. */
-template<int ELEC, int VDW, bool ENERGY, bool EXCL>
-__device__ __forceinline__ f32x2 pair_force_packed(const ParamsDev&  p,
-                                                   const PairConsts& k,
-                                                   const f32x2       r2,
-                                                   const f32x2       qq,
-                                                   const f32x2       c6n,
-                                                   const f32x2       c12,
-                                                   const f32x2       intBit,
-                                                   f32x2&            eLJout,
-                                                   f32x2&            eElout)
+/* W = (F/r) r^2 and r^-2 of one pair (V = float) or two (V = f32x2); F/r = W r^-2 is left to the caller, which
+ * masks it.  c6n = -6*C6, c12 = 12*C12, qq = qi*qj (with epsfac unless ENERGY); intBit = 1/0, only read when EXCL.
+ * r2 already guarded against 0. */
+template<typename V, int ELEC, int VDW, bool ENERGY, bool EXCL>
+__device__ __forceinline__ V pair_w(const ParamsDev&    p,
+                                    const PackedConsts& k,
+                                    const V             r2,
+                                    const V             qq,
+                                    const V             c6n,
+                                    const V             c12,
+                                    const V             intBit,
+                                    V&                  invR2out,
+                                    V&                  eLJout,
+                                    V&                  eElout)
 {
-    using Fl   = Flavor<ELEC, VDW, ENERGY>;
-    f32x2 invR = pk(rsqrt_approx(lo(r2)), rsqrt_approx(hi(r2)));
+    using Fl = Flavor<ELEC, VDW, ENERGY>;
+    V invR   = vrsqrt(r2);
     if (ENERGY)
     {
         /* one Newton-Raphson step, see pair_force(); qq comes without epsfac in the energy kernels */
-        invR = mul2(invR, fma2(mul2(mul2(r2, bc(-0.5f)), invR), invR, bc(1.5f)));
+        invR = vmul(invR, vfma(vmul(vmul(r2, vbc<V>(-0.5f)), invR), invR, vbc<V>(1.5f)));
     }
-    const f32x2 qqF   = ENERGY ? mul2(qq, bc(p.epsfac)) : qq;
-    const f32x2 invR2 = mul2(invR, invR);
-    f32x2       invR6 = mul2(mul2(invR2, invR2), invR2);
+    const V qqF   = ENERGY ? vmul(qq, vbc<V>(k.epsfac)) : qq;
+    const V invR2 = vmul(invR, invR);
+    V       invR6 = vmul(vmul(invR2, invR2), invR2);
     if (EXCL && Fl::exclusionForces)
     {
-        invR6 = mul2(invR6, intBit);
+        invR6 = vmul(invR6, intBit);
     }
-    /* invR6 (c12 invR6 - c6) invR2 */
-    f32x2 fInvR = mul2(mul2(invR6, fma2(c12, invR6, c6n)), invR2);
-    f32x2 eLJ   = 0ull;
+    /* LJ: invR6 (c12 invR6 - c6) */
+    V W   = vmul(invR6, vfma(c12, invR6, c6n));
+    V eLJ = vbc<V>(0.0f);
     if (ENERGY || Fl::ljPSwitch)
     {
         /* c12 (invR6^2 + rep.cpot) / 12 - c6 (invR6 + disp.cpot) / 6 */
-        eLJ = fma2(mul2(c12, bc(c_oneTwelfth)), fma2(invR6, invR6, bc(p.rep_cpot)),
-                   mul2(mul2(c6n, bc(c_oneSixth)), add2(invR6, bc(p.disp_cpot))));
+        eLJ = vfma(vmul(c12, vbc<V>(c_oneTwelfth)), vfma(invR6, invR6, vbc<V>(p.rep_cpot)),
+                   vmul(vmul(c6n, vbc<V>(c_oneSixth)), vadd(invR6, vbc<V>(p.disp_cpot))));
         if (EXCL && Fl::exclusionForces)
         {
-            eLJ = mul2(eLJ, intBit);
+            eLJ = vmul(eLJ, intBit);
         }
+    }
+    V r = vbc<V>(0.0f);
+    if (Fl::ljFSwitch || Fl::ljPSwitch || (Fl::ewaldAna && ENERGY))
+    {
+        r = vmul(r2, invR);
     }
     if (Fl::ljFSwitch || Fl::ljPSwitch)
     {
-        const f32x2 r     = mul2(r2, invR);
-        const f32x2 rswRaw = sub2(r, bc(p.rvdw_switch));
-        const f32x2 rsw   = pk(fmaxf(lo(rswRaw), 0.0f), fmaxf(hi(rswRaw), 0.0f));
+        const V rsw = vmax0(vsub(r, vbc<V>(p.rvdw_switch)));
         if (Fl::ljFSwitch)
         {
-            /* (-c6 (d2 + d3 rsw) + c12 (r2 + r3 rsw)) rsw^2 / r */
-            const f32x2 disp = fma2(rsw, bc(p.disp_c3), bc(p.disp_c2));
-            const f32x2 rep  = fma2(rsw, bc(p.rep_c3), bc(p.rep_c2));
-            const f32x2 t    = fma2(c12, rep, mul2(c6n, disp));
-            const f32x2 rsw2 = mul2(rsw, rsw);
-            fInvR            = fma2(mul2(t, rsw2), invR, fInvR);
+            /* F/r += (-c6 (d2 + d3 rsw) + c12 (r2 + r3 rsw)) rsw^2 / r, i.e. W += (...) rsw^2 r */
+            const V disp = vfma(rsw, vbc<V>(p.disp_c3), vbc<V>(p.disp_c2));
+            const V rep  = vfma(rsw, vbc<V>(p.rep_c3), vbc<V>(p.rep_c2));
+            const V t    = vfma(c12, rep, vmul(c6n, disp));
+            const V rsw2 = vmul(rsw, rsw);
+            W            = vfma(vmul(t, rsw2), r, W);
             if (ENERGY)
             {
                 /* (c6 (d2/3 + d3/4 rsw) - c12 (r2/3 + r3/4 rsw)) rsw^3, with c6n = -c6 */
-                const f32x2 dispE = fma2(rsw, bc(p.disp_c3 * 0.25f), bc(p.disp_c2 * (1.0f / 3.0f)));
-                const f32x2 repE  = fma2(rsw, bc(p.rep_c3 * 0.25f), bc(p.rep_c2 * (1.0f / 3.0f)));
-                const f32x2 u     = fma2(c12, repE, mul2(c6n, dispE));
-                eLJ               = fma2(sub2(bc(0.0f), u), mul2(rsw2, rsw), eLJ);
+                const V dispE = vfma(rsw, vbc<V>(p.disp_c3 * 0.25f), vbc<V>(p.disp_c2 * (1.0f / 3.0f)));
+                const V repE  = vfma(rsw, vbc<V>(p.rep_c3 * 0.25f), vbc<V>(p.rep_c2 * (1.0f / 3.0f)));
+                const V u     = vfma(c12, repE, vmul(c6n, dispE));
+                eLJ           = vfma(vsub(vbc<V>(0.0f), u), vmul(rsw2, rsw), eLJ);
             }
         }
         else
         {
             /* potential switch needs the pair energy even in the force-only kernel */
-            const f32x2 rsw2 = mul2(rsw, rsw);
-            const f32x2 sw   = fma2(mul2(rsw2, rsw), fma2(fma2(rsw, bc(p.sw_c5), bc(p.sw_c4)), rsw, bc(p.sw_c3)), bc(1.0f));
-            const f32x2 dsw  = mul2(rsw2, fma2(fma2(rsw, bc(5.0f * p.sw_c5), bc(4.0f * p.sw_c4)), rsw, bc(3.0f * p.sw_c3)));
-            /* fInvR sw - invR eLJ dsw (rsw = 0 gives sw = 1, dsw = 0) */
-            fInvR = fma2(fInvR, sw, mul2(mul2(invR, eLJ), sub2(bc(0.0f), dsw)));
-            eLJ   = mul2(eLJ, sw);
+            const V rsw2 = vmul(rsw, rsw);
+            const V sw   = vfma(vmul(rsw2, rsw), vfma(vfma(rsw, vbc<V>(p.sw_c5), vbc<V>(p.sw_c4)), rsw, vbc<V>(p.sw_c3)), vbc<V>(1.0f));
+            const V dsw  = vmul(rsw2, vfma(vfma(rsw, vbc<V>(5.0f * p.sw_c5), vbc<V>(4.0f * p.sw_c4)), rsw, vbc<V>(3.0f * p.sw_c3)));
+            /* F/r = F/r sw - eLJ dsw / r, i.e. W = W sw - r eLJ dsw (rsw = 0 gives sw = 1, dsw = 0) */
+            W   = vfma(W, sw, vmul(vmul(r, eLJ), vsub(vbc<V>(0.0f), dsw)));
+            eLJ = vmul(eLJ, sw);
         }
     }
     if (Fl::vdwCutoffCheck)
     {
-        const f32x2 inRange = pk(lo(r2) < k.rvdw2 ? 1.0f : 0.0f, hi(r2) < k.rvdw2 ? 1.0f : 0.0f);
-        fInvR               = mul2(fInvR, inRange);
-        eLJ                 = mul2(eLJ, inRange);
+        const V inRange = vless(r2, k.rvdw2);
+        W               = vmul(W, inRange);
+        eLJ             = vmul(eLJ, inRange);
     }
     eLJout = eLJ;
-    f32x2 invR3 = mul2(invR2, invR);
-    if (EXCL && Fl::exclusionForces)
-    {
-        invR3 = mul2(invR3, intBit);
-    }
-    /* intBit * invR for the energies */
-    const f32x2 invRi = (EXCL) ? mul2(invR, intBit) : invR;
-    f32x2       eEl   = 0ull;
+    /* intBit * invR: the plain Coulomb part of excluded pairs is absent */
+    const V invRi = (EXCL && (Fl::exclusionForces || ENERGY)) ? vmul(invR, intBit) : invR;
+    V       eEl   = vbc<V>(0.0f);
     if (Fl::elecCut)
     {
-        fInvR = fma2(qqF, invR3, fInvR);
-        if (ENERGY) eEl = mul2(qq, sub2(invRi, bc(p.c_rf)));
+        W = vfma(qqF, invRi, W);
+        if (ENERGY) eEl = vmul(qq, vsub(invRi, vbc<V>(p.c_rf)));
     }
     if (Fl::elecRF)
     {
-        fInvR = fma2(qqF, sub2(invR3, bc(p.two_k_rf)), fInvR);
-        if (ENERGY) eEl = mul2(qq, add2(invRi, fma2(r2, bc(0.5f * p.two_k_rf), bc(-p.c_rf))));
+        /* F/r += qq (invR3 - 2k), i.e. W += qq (invR - 2k r2) */
+        W = vfma(qqF, vfma(r2, vbc<V>(-p.two_k_rf), invRi), W);
+        if (ENERGY) eEl = vmul(qq, vadd(invRi, vfma(r2, vbc<V>(0.5f * p.two_k_rf), vbc<V>(-p.c_rf))));
     }
     if (Fl::ewaldAna)
     {
-        const f32x2 corr = pme_corr_f_packed(mul2(r2, bc(k.beta2)));
-        fInvR            = fma2(qqF, fma2(corr, bc(k.beta3), invR3), fInvR);
+        /* F/r += qq (invR3 + beta^3 pmeCorrF(beta^2 r2)), i.e. W += qq (invR + r2 num(r2) / den(r2)) */
+        V den = vfma(r2, vbc<V>(k.den[4]), vbc<V>(k.den[3]));
+        den   = vfma(den, r2, vbc<V>(k.den[2]));
+        den   = vfma(den, r2, vbc<V>(k.den[1]));
+        den   = vfma(den, r2, vbc<V>(1.0f));
+        V num = vfma(r2, vbc<V>(k.num[6]), vbc<V>(k.num[5]));
+        num   = vfma(num, r2, vbc<V>(k.num[4]));
+        num   = vfma(num, r2, vbc<V>(k.num[3]));
+        num   = vfma(num, r2, vbc<V>(k.num[2]));
+        num   = vfma(num, r2, vbc<V>(k.num[1]));
+        num   = vfma(num, r2, vbc<V>(k.num[0]));
+        /* den >= 1: the plain approximate reciprocal needs no range fix-up */
+        const V corr = vmul(num, vrcp(den));
+        W            = vfma(qqF, vfma(corr, r2, invRi), W);
         if (ENERGY)
         {
             /* qq (invR (erfc(beta r) - (1 - intBit)) - intBit sh_ewald); excluded pairs get -erf(beta r)/r */
-            const f32x2 ec = erfc_packed(mul2(mul2(r2, invR), bc(k.beta)));
+            const V ec = erfc_poly(vmul(r, vbc<V>(k.beta)));
             if (EXCL)
             {
-                eEl = mul2(qq, fma2(invR, add2(ec, sub2(intBit, bc(1.0f))), mul2(intBit, bc(-p.sh_ewald))));
+                eEl = vmul(qq, vfma(invR, vadd(ec, vsub(intBit, vbc<V>(1.0f))), vmul(intBit, vbc<V>(-p.sh_ewald))));
             }
             else
             {
-                eEl = mul2(qq, fma2(invR, ec, bc(-p.sh_ewald)));
+                eEl = vmul(qq, vfma(invR, ec, vbc<V>(-p.sh_ewald)));
             }
         }
     }
-    eElout = eEl;
-    return fInvR;
+    eElout   = eEl;
+    invR2out = invR2;
+    return W;
 }
 
-#if NBNXM_PACKED_FI
-typedef f32x2 FiAcc;
-__device__ __forceinline__ void fi_add(FiAcc& acc, const f32x2 F, const f32x2 d) { acc = fma2(F, d, acc); }
-__device__ __forceinline__ float fi_total(const FiAcc acc) { return lo(acc) + hi(acc); }
-__device__ __forceinline__ FiAcc fi_zero() { return 0ull; }
-#else
-typedef float FiAcc;
-__device__ __forceinline__ void fi_add(FiAcc& acc, const f32x2 F, const f32x2 d) { acc = fmaf(lo(F), lo(d), fmaf(hi(F), hi(d), acc)); }
-__device__ __forceinline__ float fi_total(const FiAcc acc) { return acc; }
-__device__ __forceinline__ FiAcc fi_zero() { return 0.0f; }
-#endif
+constexpr int c_fjRow = 9; /* float4 per j-atom slot in PackedShared::fj: 8 partial forces + 1 of padding */
 
-/* One j-cluster (both halves) against the i-clusters whose bits are set in mAny = m0 | m1. */
-template<int ELEC, int VDW, bool ENERGY, bool EXCL>
-__device__ __forceinline__ void cluster_pair_packed(const ParamsDev&  p,
-                                                    const PairConsts& k,
-                                                    const float4*     xqi,
-                                                    const float2*     lji,
-                                                    const f32x2       xj,
-                                                    const f32x2       yj,
-                                                    const f32x2       zj,
-                                                    const f32x2       qj,
-                                                    const f32x2       ljj0, /* (c6, c12 comb) or types as int bits */
-                                                    const f32x2       ljj1,
-                                                    const unsigned    m0,
-                                                    const unsigned    m1,
-                                                    const unsigned    wex0,
-                                                    const unsigned    wex1,
-                                                    const bool        nonSelf0,
-                                                    const bool        nonSelf1,
-                                                    const int         ciDiag,
-                                                    FiAcc (&fi)[c_superClusterSize][3],
-                                                    f32x2 (&fj)[3],
-                                                    f32x2& eLJacc,
-                                                    f32x2& eElacc)
+/* shared memory of one CTA (= one warp = one sci entry) */
+struct PackedShared
 {
-    using Fl            = Flavor<ELEC, VDW, ENERGY>;
-    const unsigned mAny = m0 | m1;
-#pragma unroll
-    for (int ci = 0; ci < c_superClusterSize; ci++)
+    float4 xqi[64];  /* i-atoms: shifted coordinates, charge (times epsfac in the force-only kernel) */
+    float4 lji[64];  /* i-atoms: (c6, c12, -, -) combination parameters or (type * numTypes as int bits, -, -, -); same
+                        16-byte stride as xqi so that one lane offset addresses both */
+    /* j-atoms of the current cjPacked group as (half 0, half 1) pairs: entry u = 4*jm + jl holds atoms jl and jl+4
+     * of j-cluster jm */
+    float4 jxy[16];  /* xA xB yA yB */
+    float4 jzq[16];  /* zA zB qA qB */
+    float4 jlj[16];  /* c6A c6B c12A c12B, or typeA typeB - - */
+    /* per-lane partial j forces of the current group: [j-atom slot][il], rows padded to 9 float4 so that both the
+     * stores (8 consecutive float4 of one row per quarter warp) and the row sums (8 rows, same column, per
+     * quarter warp) are bank-conflict free with plain offsets */
+    float4 fj[32 * c_fjRow];
+    /* type table, -6*C6 and 12*C12 */
+    float nbC6n[c_packedMaxTypes * c_packedMaxTypes];
+    float nbC12[c_packedMaxTypes * c_packedMaxTypes];
+};
+
+/* j-atoms of one j-cluster as this lane sees them: atoms jl (lo) and jl+4 (hi) */
+struct PackedJ
+{
+    f32x2 x, y, z, q, lj0, lj1;
+};
+
+/* scalar partial j forces of the current j-cluster: atoms jl (A) and jl+4 (B) */
+struct FjAcc
+{
+    float xA, yA, zA, xB, yB, zB;
+};
+
+/* LJ parameters of two pairs: c6n = -6*C6, c12 = 12*C12 */
+template<int ELEC, int VDW>
+__device__ __forceinline__ void lj_params_packed(const PackedShared& sm, const float4 pi, const PackedJ& j, f32x2& c6n, f32x2& c12)
+{
+    using Fl = Flavor<ELEC, VDW, false>;
+    if (Fl::ljCombGeom)
     {
-        if (mAny & (1u << ci))
+        c6n = vmul(pk(-pi.x, -pi.x), j.lj0);
+        c12 = vmul(pk(pi.y, pi.y), j.lj1);
+    }
+    else if (Fl::ljCombLB)
+    {
+        const f32x2 sigma  = vadd(pk(pi.x, pi.x), j.lj0);
+        const f32x2 eps    = vmul(pk(pi.y, pi.y), j.lj1);
+        const f32x2 sigma2 = vmul(sigma, sigma);
+        const f32x2 sigma6 = vmul(vmul(sigma2, sigma2), sigma2);
+        const f32x2 c6     = vmul(eps, sigma6);
+        c12                = vmul(c6, sigma6);
+        c6n                = vsub(pk(0.0f, 0.0f), c6);
+    }
+    else
+    {
+        const int tiN = __float_as_int(pi.x);
+        const int ia = tiN + __float_as_int(lo(j.lj0)), ib = tiN + __float_as_int(hi(j.lj0));
+        c6n          = pk(sm.nbC6n[ia], sm.nbC6n[ib]);
+        c12          = pk(sm.nbC12[ia], sm.nbC12[ib]);
+    }
+}
+
+/* One (i-cluster, j-cluster) pair with BOTH halves in the list and no exclusion masks, force only: the hot body. */
+template<int ELEC, int VDW>
+__device__ __forceinline__ void body_both(const ParamsDev&    p,
+                                          const PackedConsts& k,
+                                          const PackedShared& sm,
+                                          const float4        xi,
+                                          const float4        pi,
+                                          const PackedJ&      j,
+                                          float (&fi)[3],
+                                          FjAcc& fj)
+{
+    const f32x2 dx = vsub(pk(xi.x, xi.x), j.x), dy = vsub(pk(xi.y, xi.y), j.y), dz = vsub(pk(xi.z, xi.z), j.z);
+    f32x2       r2;
+    if (Flavor<ELEC, VDW, false>::ljPSwitch)
+    {
+        /* the potential switch evaluates r^-12 also in the force-only kernel: the reference's clamp keeps it finite */
+        r2 = vfma(dz, dz, vfma(dy, dy, vmul(dx, dx)));
+        r2 = pk(fmaxf(lo(r2), c_minDistanceSquared), fmaxf(hi(r2), c_minDistanceSquared));
+    }
+    else
+    {
+        r2 = vfma(dz, dz, vfma(dy, dy, vfma(dx, dx, pk(c_r2Guard, c_r2Guard))));
+    }
+    f32x2 c6n, c12;
+    lj_params_packed<ELEC, VDW>(sm, pi, j, c6n, c12);
+    f32x2       invR2, e0, e1;
+    const f32x2 W  = pair_w<f32x2, ELEC, VDW, false, false>(p, k, r2, vmul(pk(xi.w, xi.w), j.q), c6n, c12, 0ull, invR2, e0, e1);
+    const f32x2 F  = vmul(W, invR2);
+    const float F0 = (lo(r2) < k.rc2) ? lo(F) : 0.0f;
+    const float F1 = (hi(r2) < k.rc2) ? hi(F) : 0.0f;
+    fi[0]          = fmaf(F0, lo(dx), fmaf(F1, hi(dx), fi[0]));
+    fi[1]          = fmaf(F0, lo(dy), fmaf(F1, hi(dy), fi[1]));
+    fi[2]          = fmaf(F0, lo(dz), fmaf(F1, hi(dz), fi[2]));
+    fj.xA          = fmaf(F0, lo(dx), fj.xA);
+    fj.yA          = fmaf(F0, lo(dy), fj.yA);
+    fj.zA          = fmaf(F0, lo(dz), fj.zA);
+    fj.xB          = fmaf(F1, hi(dx), fj.xB);
+    fj.yB          = fmaf(F1, hi(dy), fj.yB);
+    fj.zB          = fmaf(F1, hi(dz), fj.zB);
+}
+
+/* One (i-cluster, j-cluster) pair with only half HALF in the list and no exclusion masks, force only: a scalar pair
+ * body on that half's j-atom, so that a pruned half costs nothing. */
+template<int ELEC, int VDW, int HALF>
+__device__ __forceinline__ void body_single(const ParamsDev&    p,
+                                            const PackedConsts& k,
+                                            const PackedShared& sm,
+                                            const float4        xi,
+                                            const float4        pi,
+                                            const PackedJ&      j,
+                                            float (&fi)[3],
+                                            FjAcc& fj)
+{
+    using Fl       = Flavor<ELEC, VDW, false>;
+    const float xj = HALF ? hi(j.x) : lo(j.x), yj = HALF ? hi(j.y) : lo(j.y), zj = HALF ? hi(j.z) : lo(j.z);
+    const float qj = HALF ? hi(j.q) : lo(j.q), l0 = HALF ? hi(j.lj0) : lo(j.lj0), l1 = HALF ? hi(j.lj1) : lo(j.lj1);
+    const float dx = xi.x - xj, dy = xi.y - yj, dz = xi.z - zj;
+    const float r2 = Fl::ljPSwitch ? fmaxf(fmaf(dz, dz, fmaf(dy, dy, dx * dx)), c_minDistanceSquared)
+                                   : fmaf(dz, dz, fmaf(dy, dy, fmaf(dx, dx, c_r2Guard)));
+    float       c6n, c12;
+    if (Fl::ljCombGeom)
+    {
+        c6n = -pi.x * l0;
+        c12 = pi.y * l1;
+    }
+    else if (Fl::ljCombLB)
+    {
+        const float sigma = pi.x + l0, eps = pi.y * l1, sigma2 = sigma * sigma, sigma6 = sigma2 * sigma2 * sigma2;
+        const float c6 = eps * sigma6;
+        c12 = c6 * sigma6;
+        c6n = -c6;
+    }
+    else
+    {
+        const int ia = __float_as_int(pi.x) + __float_as_int(l0);
+        c6n          = sm.nbC6n[ia];
+        c12          = sm.nbC12[ia];
+    }
+    float       invR2, e0, e1;
+    const float W = pair_w<float, ELEC, VDW, false, false>(p, k, r2, xi.w * qj, c6n, c12, 0.0f, invR2, e0, e1);
+    const float F = (r2 < k.rc2) ? W * invR2 : 0.0f;
+    fi[0]         = fmaf(F, dx, fi[0]);
+    fi[1]         = fmaf(F, dy, fi[1]);
+    fi[2]         = fmaf(F, dz, fi[2]);
+    if (HALF)
+    {
+        fj.xB = fmaf(F, dx, fj.xB);
+        fj.yB = fmaf(F, dy, fj.yB);
+        fj.zB = fmaf(F, dz, fj.zB);
+    }
+    else
+    {
+        fj.xA = fmaf(F, dx, fj.xA);
+        fj.yA = fmaf(F, dy, fj.yA);
+        fj.zA = fmaf(F, dz, fj.zA);
+    }
+}
+
+/* One (i-cluster, j-cluster) pair, general: list mask bits per half, optional exclusion masks, optional energies.
+ * Returns the masked F/r of the two pairs and the distance vectors. */
+template<int ELEC, int VDW, bool ENERGY, bool EXCL>
+__device__ __forceinline__ f32x2 body_general(const ParamsDev&    p,
+                                              const PackedConsts& k,
+                                              const PackedShared& sm,
+                                              const float4        xi,
+                                              const float4        pi,
+                                              const PackedJ&      j,
+                                              const bool          m0, /* list mask bits of the two halves */
+                                              const bool          m1,
+                                              const bool          i0, /* exclusion mask bits (EXCL only) */
+                                              const bool          i1,
+                                              const bool          self0, /* pair gets no exclusion correction (EXCL only) */
+                                              const bool          self1,
+                                              f32x2&              dx,
+                                              f32x2&              dy,
+                                              f32x2&              dz,
+                                              f32x2&              eLJacc,
+                                              f32x2&              eElacc)
+{
+    using Fl = Flavor<ELEC, VDW, ENERGY>;
+    dx       = vsub(pk(xi.x, xi.x), j.x);
+    dy       = vsub(pk(xi.y, xi.y), j.y);
+    dz       = vsub(pk(xi.z, xi.z), j.z);
+    const f32x2 r2 = vfma(dz, dz, vfma(dy, dy, vmul(dx, dx)));
+    bool        w0 = m0 && (lo(r2) < k.rc2);
+    bool        w1 = m1 && (hi(r2) < k.rc2);
+    f32x2       intBit = pk(1.0f, 1.0f);
+    if (EXCL)
+    {
+        intBit = pk(i0 ? 1.0f : 0.0f, i1 ? 1.0f : 0.0f);
+        if (Fl::exclusionForces)
         {
-            const float4 xi = xqi[ci * c_clusterSize];
-            const f32x2  dx = sub2(bc(xi.x), xj), dy = sub2(bc(xi.y), yj), dz = sub2(bc(xi.z), zj);
-            const f32x2  r2 = fma2(dz, dz, fma2(dy, dy, mul2(dx, dx)));
-            bool         w0 = (m0 & (1u << ci)) && (lo(r2) < k.rc2);
-            bool         w1 = (m1 & (1u << ci)) && (hi(r2) < k.rc2);
-            f32x2        intBit = bc(1.0f);
-            if (EXCL)
-            {
-                const bool i0 = (wex0 & (1u << ci)) != 0u, i1 = (wex1 & (1u << ci)) != 0u;
-                intBit        = pk(i0 ? 1.0f : 0.0f, i1 ? 1.0f : 0.0f);
-                if (Fl::exclusionForces)
-                {
-                    const bool offDiagonal = (ciDiag != ci);
-                    w0                     = w0 && (nonSelf0 || offDiagonal);
-                    w1                     = w1 && (nonSelf1 || offDiagonal);
-                }
-                else
-                {
-                    w0 = w0 && i0;
-                    w1 = w1 && i1;
-                }
-            }
-            const float2 pi = lji[ci * c_clusterSize];
-            f32x2        c6n, c12;
-            if (Fl::ljCombGeom)
-            {
-                c6n = mul2(bc(-pi.x), ljj0);
-                c12 = mul2(bc(pi.y), ljj1);
-            }
-            else if (Fl::ljCombLB)
-            {
-                const f32x2 sigma  = add2(bc(pi.x), ljj0);
-                const f32x2 eps    = mul2(bc(pi.y), ljj1);
-                const f32x2 sigma2 = mul2(sigma, sigma);
-                const f32x2 sigma6 = mul2(mul2(sigma2, sigma2), sigma2);
-                const f32x2 c6     = mul2(eps, sigma6);
-                c12                = mul2(c6, sigma6);
-                c6n                = sub2(bc(0.0f), c6);
-            }
-            else
-            {
-                const int    tiN = __float_as_int(pi.x);
-                const float2 a   = __ldg(p.nbfp + tiN + __float_as_int(lo(ljj0)));
-                const float2 b   = __ldg(p.nbfp + tiN + __float_as_int(hi(ljj0)));
-                c6n              = pk(-a.x, -b.x);
-                c12              = pk(a.y, b.y);
-            }
-            const f32x2 r2c = pk(fmaxf(lo(r2), c_minDistanceSquared), fmaxf(hi(r2), c_minDistanceSquared));
-            f32x2       ePairLJ, ePairEl;
-            f32x2       F = pair_force_packed<ELEC, VDW, ENERGY, EXCL>(p, k, r2c, mul2(bc(xi.w), qj), c6n, c12, intBit, ePairLJ, ePairEl);
-            F             = pk(w0 ? lo(F) : 0.0f, w1 ? hi(F) : 0.0f);
-            if (ENERGY)
-            {
-                eLJacc = add2(eLJacc, pk(w0 ? lo(ePairLJ) : 0.0f, w1 ? hi(ePairLJ) : 0.0f));
-                eElacc = add2(eElacc, pk(w0 ? lo(ePairEl) : 0.0f, w1 ? hi(ePairEl) : 0.0f));
-            }
-            fi_add(fi[ci][0], F, dx);
-            fi_add(fi[ci][1], F, dy);
-            fi_add(fi[ci][2], F, dz);
-            fj[0]           = fma2(F, dx, fj[0]);
-            fj[1]           = fma2(F, dy, fj[1]);
-            fj[2]           = fma2(F, dz, fj[2]);
+            w0 = w0 && !self0;
+            w1 = w1 && !self1;
+        }
+        else
+        {
+            w0 = w0 && i0;
+            w1 = w1 && i1;
         }
     }
+    f32x2 c6n, c12;
+    lj_params_packed<ELEC, VDW>(sm, pi, j, c6n, c12);
+    const f32x2 r2c = pk(fmaxf(lo(r2), c_minDistanceSquared), fmaxf(hi(r2), c_minDistanceSquared));
+    f32x2       invR2, ePairLJ, ePairEl;
+    const f32x2 W = pair_w<f32x2, ELEC, VDW, ENERGY, EXCL>(p, k, r2c, vmul(pk(xi.w, xi.w), j.q), c6n, c12, intBit, invR2, ePairLJ, ePairEl);
+    const f32x2 F = vmul(W, invR2);
+    if (ENERGY)
+    {
+        eLJacc = vadd(eLJacc, pk(w0 ? lo(ePairLJ) : 0.0f, w1 ? hi(ePairLJ) : 0.0f));
+        eElacc = vadd(eElacc, pk(w0 ? lo(ePairEl) : 0.0f, w1 ? hi(ePairEl) : 0.0f));
+    }
+    return pk(w0 ? lo(F) : 0.0f, w1 ? hi(F) : 0.0f);
 }
 
 template<int ELEC, int VDW, bool ENERGY>
-__global__ void __launch_bounds__(32, ENERGY ? c_packedMinBlocksPerSM - 2 : c_packedMinBlocksPerSM)
+__global__ void __launch_bounds__(32, ENERGY ? NBNXM_PACKED_MIN_BLOCKS_ENERGY : NBNXM_PACKED_MIN_BLOCKS)
         nbnxm_force_kernel_packed(const AtomDataDev ad, const ParamsDev p, const PairlistDev pl, const int calcFshift)
 {
-    using Fl                  = Flavor<ELEC, VDW, ENERGY>;
-    constexpr unsigned c_full = 0xffffffffu;
+    using Fl                   = Flavor<ELEC, VDW, ENERGY>;
+    constexpr unsigned c_full  = 0xffffffffu;
+    constexpr bool     c_types = PackedFlavor<ELEC, VDW>::typeTable;
 
-    const int lane   = threadIdx.x;
-    const int il     = lane & 7;
-    const int jl     = lane >> 3;
-    const int sciIdx = blockIdx.x;
-    const nbnxm_b200_sci_t s = pl.sciSorted[sciIdx];
+    const int lane = threadIdx.x;
+    const int il   = lane & 7;
+    const int jl   = lane >> 3;
+    const nbnxm_b200_sci_t s = pl.sciSorted[blockIdx.x];
 
-    /* i-atoms of the entry; j-atoms of the current group as (half 0, half 1) pairs: entry u = 4*jm + jl holds
-     * atoms jl and jl+4 of j-cluster jm */
-    __shared__ float4 sm_xqi[64];
-    __shared__ float2 sm_lji[64];
-    __shared__ float4 sm_jxy[16]; /* xA xB yA yB */
-    __shared__ float4 sm_jzq[16]; /* zA zB qA qB */
-    __shared__ float4 sm_jlj[16]; /* c6A c6B c12A c12B, or typeA typeB - - */
-    __shared__ __align__(128) float4 sm_fj[32 * c_clusterSize];
+    __shared__ PackedShared sm;
 
     const float shx = ad.shiftVec[3 * s.shift], shy = ad.shiftVec[3 * s.shift + 1], shz = ad.shiftVec[3 * s.shift + 2];
 
-    PairConsts k;
-    k.rc2         = p.rcoulomb_sq;
-    k.rcoulomb    = sqrtf(p.rcoulomb_sq);
-    k.rvdw2       = p.rvdw_sq;
-    k.beta        = p.ewald_beta;
-    k.beta2       = p.ewald_beta * p.ewald_beta;
-    k.beta3       = k.beta2 * p.ewald_beta;
-    k.ljeCoeff2   = 0.0f;
-    k.ljeCoeff6_6 = 0.0f;
+    /* The constants of the pair bodies come from global memory, not from the kernel parameters: values loaded
+     * from the constant bank are re-loaded by ptxas in every pair body (FFMA2 takes no constant-bank operand),
+     * a dozen instructions per body; loaded values stay in (uniform) registers. */
+    PackedConsts k;
+    k.rc2    = __ldg(p.packedConsts + 0);
+    k.rvdw2  = p.rvdw_sq;
+    k.beta   = p.ewald_beta;
+    k.epsfac = p.epsfac;
+    if (Fl::ewaldAna)
+    {
+#pragma unroll
+        for (int n = 0; n < 7; n++) k.num[n] = __ldg(p.packedConsts + 1 + n);
+#pragma unroll
+        for (int n = 1; n < 5; n++) k.den[n] = __ldg(p.packedConsts + 8 + n);
+    }
+
+    /* Lane-dependent shared-memory byte offsets, passed through a shuffle: ptxas would otherwise re-derive each of
+     * them from the thread index (S2R, shifts, masks) in front of every use instead of keeping a register. */
+    /* i-atom il of i-cluster 0 in xqi / lji */
+    const int iOff = __shfl_sync(c_full, il, lane);
+    /* this lane's entry of j-cluster 0 in jxy / jzq / jlj */
+    const int jOff0 = __shfl_sync(c_full, jl, lane);
+    /* where it parks its partial j forces: slot = 8*jm + jl (half 1: + 4), column il */
+    const int parkOff = __shfl_sync(c_full, jl * c_fjRow + il, lane);
+    /* the j-atom slot it reduces (the atom it fetched) */
+    const int sumOff = __shfl_sync(c_full, lane * c_fjRow, lane);
+    /* where it stages the atom it fetched (lane = 8*jm + atom, atom = 4*half + jl'): float index into jxy/jzq/jlj */
+    const int stageOff = __shfl_sync(c_full, ((lane >> 3) * 4 + (lane & 3)) * 4 + ((lane >> 2) & 1), lane);
 
     /* energies: float partial sums per j-cluster, double across the sci entry (see nbnxm_force_kernel) */
     double     eLJ = 0.0, eEl = 0.0;
     const bool diagonalEntry = (s.shift == c_centralShiftIndex && s.cj_packed_begin < s.cj_packed_end
                                 && pl.cjPacked[s.cj_packed_begin].cj[0] == s.sci * c_superClusterSize);
 
+    if (c_types)
+    {
+        const int nt2 = ad.numTypes * ad.numTypes;
+        for (int n = lane; n < nt2; n += 32)
+        {
+            const float2 c = __ldg(p.nbfp + n);
+            sm.nbC6n[n]    = -c.x;
+            sm.nbC12[n]    = c.y;
+        }
+    }
 #pragma unroll
     for (int h = 0; h < 2; h++)
     {
@@ -426,50 +602,56 @@ __global__ void __launch_bounds__(32, ENERGY ? c_packedMinBlocksPerSM - 2 : c_pa
         {
             v.w *= p.epsfac;
         }
-        sm_xqi[lane + 32 * h] = v;
+        sm.xqi[lane + 32 * h] = v;
         if (Fl::ljComb)
         {
-            sm_lji[lane + 32 * h] = ad.ljComb[ai];
+            const float2 c        = ad.ljComb[ai];
+            sm.lji[lane + 32 * h] = make_float4(c.x, c.y, 0.0f, 0.0f);
         }
         else
         {
-            const int t           = ad.atomType[ai];
-            sm_lji[lane + 32 * h] = make_float2(__int_as_float(t * ad.numTypes), __int_as_float(t));
+            sm.lji[lane + 32 * h] = make_float4(__int_as_float(ad.atomType[ai] * ad.numTypes), 0.0f, 0.0f, 0.0f);
         }
     }
 
-    FiAcc fi[c_superClusterSize][3];
+    float fi[c_superClusterSize][3];
 #pragma unroll
     for (int ci = 0; ci < c_superClusterSize; ci++)
     {
-        fi[ci][0] = fi[ci][1] = fi[ci][2] = fi_zero();
+        fi[ci][0] = fi[ci][1] = fi[ci][2] = 0.0f;
     }
 
     const bool centralShift = (s.shift == c_centralShiftIndex);
 
-    /* same software pipeline as nbnxm_force_kernel: descriptors two groups ahead, atoms one group ahead */
+    /* Software pipeline over the cjPacked groups: the two (imask, excl_ind) words of a group (one 16-byte load, the
+     * same address in all lanes) and the j-cluster index a lane fetches an atom of are loaded two groups ahead, the
+     * atom itself - lane L fetches atom (L & 7) of j-cluster (L >> 3), one coalesced 16-byte load per lane - one
+     * group ahead. */
     const uint4* cjGroups = reinterpret_cast<const uint4*>(pl.cjPacked);
+    const int*   cjInts   = reinterpret_cast<const int*>(pl.cjPacked);
     int          jp       = s.cj_packed_begin;
     const uint4  zero4    = make_uint4(0u, 0u, 0u, 0u);
-    uint4        cjNext = zero4, meNext = zero4, cjNext2 = zero4, meNext2 = zero4;
+    uint4        meNext = zero4, meNext2 = zero4;
+    int          cjNext = 0, cjNext2 = 0;
     if (jp < s.cj_packed_end)
     {
-        cjNext = cjGroups[2 * jp];
         meNext = cjGroups[2 * jp + 1];
+        cjNext = cjInts[8 * jp + jl];
     }
     if (jp + 1 < s.cj_packed_end)
     {
-        cjNext2 = cjGroups[2 * jp + 2];
         meNext2 = cjGroups[2 * jp + 3];
+        cjNext2 = cjInts[8 * jp + 8 + jl];
     }
     float4 xjNext = make_float4(0.0f, 0.0f, 0.0f, 0.0f);
     float2 pjNext = make_float2(0.0f, 0.0f);
     int    ajNext = 0;
 
-    auto fetchAtoms = [&](const uint4 cjv, const uint4 mev, float4& xj, float2& pj, int& ajOut) {
+    auto fetchAtoms = [&](const int cj, const uint4 mev, float4& xj, float2& pj, int& ajOut) {
+        /* unused slots of a partially filled group have no mask bits and an unspecified index */
         if ((mev.x | mev.z) & (0xffu << (8 * jl)))
         {
-            const int aj = static_cast<int>(select4(cjv.x, cjv.y, cjv.z, cjv.w, jl)) * c_clusterSize + il;
+            const int aj = cj * c_clusterSize + il;
             xj           = ad.xq[aj];
             if (Fl::ljComb)
             {
@@ -484,18 +666,20 @@ __global__ void __launch_bounds__(32, ENERGY ? c_packedMinBlocksPerSM - 2 : c_pa
     };
     fetchAtoms(cjNext, meNext, xjNext, pjNext, ajNext);
 
-    const float4* xqiLane = sm_xqi + il;
-    const float2* ljiLane = sm_lji + il;
-    /* where this lane parks the atom it fetched: lane = 8*jm + atom, atom = 4*half + jl' */
-    float* const stageXY = reinterpret_cast<float*>(sm_jxy + ((lane >> 3) * 4 + (lane & 3))) + ((lane >> 2) & 1);
-    float* const stageZQ = reinterpret_cast<float*>(sm_jzq + ((lane >> 3) * 4 + (lane & 3))) + ((lane >> 2) & 1);
-    float* const stageLJ = reinterpret_cast<float*>(sm_jlj + ((lane >> 3) * 4 + (lane & 3))) + ((lane >> 2) & 1);
-    const bool    nonSelf0 = !(centralShift && jl <= il);
-    const bool    nonSelf1 = !(centralShift && (jl + 4) <= il);
+    float* const  stageXY = reinterpret_cast<float*>(sm.jxy) + stageOff;
+    float* const  stageZQ = reinterpret_cast<float*>(sm.jzq) + stageOff;
+    float* const  stageLJ = reinterpret_cast<float*>(sm.jlj) + stageOff;
+    const float4* xqiLane = sm.xqi + iOff;
+    const float4* ljiLane = sm.lji + iOff;
+    const float4* fjSum   = sm.fj + sumOff;
+    /* j <= i within the same cluster on the central shift: the "Newton" half of the diagonal cluster pair and the
+     * self pair (nbnxm_cuda_kernel.cuh:421-423) */
+    const bool selfLo = centralShift && jl <= il;
+    const bool selfHi = centralShift && (jl + 4) <= il;
 
     for (; jp < s.cj_packed_end; jp++)
     {
-        const uint4 cjv = cjNext, mev = meNext;
+        const uint4 mev   = meNext;
         const int   ajOwn = ajNext;
         __syncwarp();
         stageXY[0] = xjNext.x;
@@ -503,14 +687,17 @@ __global__ void __launch_bounds__(32, ENERGY ? c_packedMinBlocksPerSM - 2 : c_pa
         stageZQ[0] = xjNext.z;
         stageZQ[2] = xjNext.w;
         stageLJ[0] = pjNext.x;
-        stageLJ[2] = pjNext.y;
+        if (Fl::ljComb)
+        {
+            stageLJ[2] = pjNext.y;
+        }
         __syncwarp();
-        cjNext = cjNext2;
         meNext = meNext2;
+        cjNext = cjNext2;
         if (jp + 2 < s.cj_packed_end)
         {
-            cjNext2 = cjGroups[2 * jp + 4];
             meNext2 = cjGroups[2 * jp + 5];
+            cjNext2 = cjInts[8 * jp + 16 + jl];
         }
         else
         {
@@ -523,90 +710,173 @@ __global__ void __launch_bounds__(32, ENERGY ? c_packedMinBlocksPerSM - 2 : c_pa
         {
             continue;
         }
-        const int exclInd0 = static_cast<int>(mev.y), exclInd1 = static_cast<int>(mev.w);
-        /* entry 0 of the exclusion array is all ones (pairlist.h:274-287) */
-        unsigned  wex0 = (exclInd0 != 0) ? pl.excl[exclInd0].pair[lane] : c_full;
-        unsigned  wex1 = (exclInd1 != 0) ? pl.excl[exclInd1].pair[lane] : c_full;
-        /* the energy kernel carries the general pair path only: two copies would not fit the instruction cache */
-        const bool haveExcl = ENERGY || (exclInd0 | exclInd1) != 0;
+        /* exclusion masks: entry 0 of the exclusion array is all ones (pairlist.h:274-287).  curEx gets the bits of
+         * the (j-cluster, i-cluster) pairs in which any atom pair of either half is excluded. */
+        unsigned wex0 = c_full, wex1 = c_full, curEx = 0u;
+        if ((mev.y | mev.w) != 0u)
+        {
+            if (mev.y != 0u) wex0 = pl.excl[mev.y].pair[lane];
+            if (mev.w != 0u) wex1 = pl.excl[mev.w].pair[lane];
+            curEx = __reduce_or_sync(c_full, ~(wex0 & wex1));
+        }
 
-        const float4* jxy  = sm_jxy + jl;
-        const float4* jzq  = sm_jzq + jl;
-        const float4* jlj  = sm_jlj + jl;
-        int           slot = jl; /* j-atom slot of half 0; half 1 is slot + 4 */
 #pragma unroll 1
-        for (int jm = 0; (cur0 | cur1) != 0u;
-             jm++, cur0 >>= 8, cur1 >>= 8, wex0 >>= 8, wex1 >>= 8, jxy += 4, jzq += 4, jlj += 4, slot += c_clusterSize)
+        for (int jm = 0; (cur0 | cur1) != 0u; jm++, cur0 >>= 8, cur1 >>= 8, curEx >>= 8, wex0 >>= 8, wex1 >>= 8)
         {
             const unsigned m0 = cur0 & 0xffu, m1 = cur1 & 0xffu;
             if ((m0 | m1) == 0u)
             {
                 continue;
             }
-            const float4 xy = *jxy, zq = *jzq, lj = *jlj;
-            const f32x2  xj = pk(xy.x, xy.y), yj = pk(xy.z, xy.w), zj = pk(zq.x, zq.y), qj = pk(zq.z, zq.w);
-            const f32x2  ljj0 = pk(lj.x, lj.y), ljj1 = pk(lj.z, lj.w);
-            f32x2        fj[3] = { 0ull, 0ull, 0ull };
-            f32x2        eLJj = 0ull, eElj = 0ull;
-            if (!haveExcl)
+            const float4 xy = sm.jxy[jOff0 + 4 * jm];
+            const float4 zq = sm.jzq[jOff0 + 4 * jm];
+            const float4 lj = sm.jlj[jOff0 + 4 * jm];
+            PackedJ      j;
+            j.x   = pk(xy.x, xy.y);
+            j.y   = pk(xy.z, xy.w);
+            j.z   = pk(zq.x, zq.y);
+            j.q   = pk(zq.z, zq.w);
+            j.lj0 = pk(lj.x, lj.y);
+            j.lj1 = pk(lj.z, lj.w);
+            FjAcc fj = { 0.0f, 0.0f, 0.0f, 0.0f, 0.0f, 0.0f };
+            f32x2 eLJj = 0ull, eElj = 0ull;
+            const unsigned mFast = (m0 | m1) & ~curEx;
+            if (!ENERGY)
             {
-                cluster_pair_packed<ELEC, VDW, ENERGY, false>(p, k, xqiLane, ljiLane, xj, yj, zj, qj, ljj0, ljj1, m0, m1, 0xffu,
-                                                              0xffu, true, true, -1, fi, fj, eLJj, eElj);
+                const unsigned mBoth = m0 & m1;
+#pragma unroll
+                for (int ci = 0; ci < c_superClusterSize; ci++)
+                {
+                    if (mFast & (1u << ci))
+                    {
+                        const float4 xi = xqiLane[ci * c_clusterSize];
+                        const float4 pi = ljiLane[ci * c_clusterSize];
+                        if (mBoth & (1u << ci))
+                        {
+                            body_both<ELEC, VDW>(p, k, sm, xi, pi, j, fi[ci], fj);
+                        }
+                        else if (m0 & (1u << ci))
+                        {
+                            body_single<ELEC, VDW, 0>(p, k, sm, xi, pi, j, fi[ci], fj);
+                        }
+                        else
+                        {
+                            body_single<ELEC, VDW, 1>(p, k, sm, xi, pi, j, fi[ci], fj);
+                        }
+                    }
+                }
             }
             else
             {
-                const int cj     = static_cast<int>(select4(cjv.x, cjv.y, cjv.z, cjv.w, jm));
-                const int ciDiag = cj - s.sci * c_superClusterSize;
-                cluster_pair_packed<ELEC, VDW, ENERGY, true>(p, k, xqiLane, ljiLane, xj, yj, zj, qj, ljj0, ljj1, m0, m1, wex0,
-                                                             wex1, nonSelf0, nonSelf1, ciDiag, fi, fj, eLJj, eElj);
+#pragma unroll
+                for (int ci = 0; ci < c_superClusterSize; ci++)
+                {
+                    if (mFast & (1u << ci))
+                    {
+                        const float4 xi = xqiLane[ci * c_clusterSize];
+                        const float4 pi = ljiLane[ci * c_clusterSize];
+                        f32x2        dx, dy, dz;
+                        const f32x2  F = body_general<ELEC, VDW, ENERGY, false>(p, k, sm, xi, pi, j, (m0 & (1u << ci)) != 0u,
+                                                                               (m1 & (1u << ci)) != 0u, true, true, false, false,
+                                                                               dx, dy, dz, eLJj, eElj);
+                        fi[ci][0] = fmaf(lo(F), lo(dx), fmaf(hi(F), hi(dx), fi[ci][0]));
+                        fi[ci][1] = fmaf(lo(F), lo(dy), fmaf(hi(F), hi(dy), fi[ci][1]));
+                        fi[ci][2] = fmaf(lo(F), lo(dz), fmaf(hi(F), hi(dz), fi[ci][2]));
+                        fj.xA     = fmaf(lo(F), lo(dx), fj.xA);
+                        fj.yA     = fmaf(lo(F), lo(dy), fj.yA);
+                        fj.zA     = fmaf(lo(F), lo(dz), fj.zA);
+                        fj.xB     = fmaf(hi(F), hi(dx), fj.xB);
+                        fj.yB     = fmaf(hi(F), hi(dy), fj.yB);
+                        fj.zB     = fmaf(hi(F), hi(dz), fj.zB);
+                    }
+                }
+            }
+            /* the few cluster pairs with exclusion masks: one loop body for all i-clusters, own accumulators */
+            unsigned mEx = (m0 | m1) & curEx;
+            if (mEx != 0u)
+            {
+                /* the i-cluster this j-cluster is, if any */
+                const int ciDiag = cjInts[8 * jp + jm] - s.sci * c_superClusterSize;
+                f32x2     gx = 0ull, gy = 0ull, gz = 0ull;
+#pragma unroll 1
+                for (; mEx != 0u; mEx &= mEx - 1u)
+                {
+                    const int    ci = __ffs(mEx) - 1;
+                    const float4 xi = xqiLane[ci * c_clusterSize];
+                    const float4 pi = ljiLane[ci * c_clusterSize];
+                    const bool   onDiagonal = (ciDiag == ci);
+                    f32x2        dx, dy, dz;
+                    const f32x2  F = body_general<ELEC, VDW, ENERGY, true>(
+                            p, k, sm, xi, pi, j, ((m0 >> ci) & 1u) != 0u, ((m1 >> ci) & 1u) != 0u, ((wex0 >> ci) & 1u) != 0u,
+                            ((wex1 >> ci) & 1u) != 0u, onDiagonal && selfLo, onDiagonal && selfHi, dx, dy, dz, eLJj, eElj);
+                    const float fx = fmaf(lo(F), lo(dx), hi(F) * hi(dx));
+                    const float fy = fmaf(lo(F), lo(dy), hi(F) * hi(dy));
+                    const float fz = fmaf(lo(F), lo(dz), hi(F) * hi(dz));
+#pragma unroll
+                    for (int c = 0; c < c_superClusterSize; c++)
+                    {
+                        const bool hit = (c == ci);
+                        fi[c][0] += hit ? fx : 0.0f;
+                        fi[c][1] += hit ? fy : 0.0f;
+                        fi[c][2] += hit ? fz : 0.0f;
+                    }
+                    gx = vfma(F, dx, gx);
+                    gy = vfma(F, dy, gy);
+                    gz = vfma(F, dz, gz);
+                }
+                fj.xA += lo(gx);
+                fj.yA += lo(gy);
+                fj.zA += lo(gz);
+                fj.xB += hi(gx);
+                fj.yB += hi(gy);
+                fj.zB += hi(gz);
             }
             if (ENERGY)
             {
                 eLJ += lo(eLJj) + hi(eLJj);
                 eEl += lo(eElj) + hi(eElj);
             }
-            /* park the partial j forces (sign: the j-atom gets -F d) */
+            /* park the partial j forces (sum of F d: the j-atom gets minus that, applied after the reduction) */
+            float4* const park = sm.fj + parkOff + jm * (c_clusterSize * c_fjRow);
             if (m0 != 0u)
             {
-                sm_fj[slot * c_clusterSize + (il ^ (slot & 7))] = make_float4(-lo(fj[0]), -lo(fj[1]), -lo(fj[2]), 0.0f);
+                park[0] = make_float4(fj.xA, fj.yA, fj.zA, 0.0f);
             }
             if (m1 != 0u)
             {
-                const int slot1                                     = slot + 4;
-                sm_fj[slot1 * c_clusterSize + (il ^ (slot1 & 7))] = make_float4(-hi(fj[0]), -hi(fj[1]), -hi(fj[2]), 0.0f);
+                park[4 * c_fjRow] = make_float4(fj.xB, fj.yB, fj.zB, 0.0f);
             }
         }
 
-        /* j forces of the group: lane L sums the 8 partial forces of j-atom slot L and adds them with one
-         * v4 reduction; slots of halves that were not visited hold stale data and are skipped */
+        /* j forces of the group: lane L sums the 8 partial forces of j-atom slot L (the atom it fetched) and adds
+         * them with one v4 reduction; slots of halves that were not visited hold stale data and are skipped */
         __syncwarp();
         {
             const unsigned visited = (((lane >> 2) & 1) ? mev.z : mev.x) & (0xffu << (8 * (lane >> 3)));
             if (visited != 0u)
             {
-                const float4* col = sm_fj + lane * c_clusterSize;
-                const float4  v0  = col[il];
-                float         sx = v0.x, sy = v0.y, sz = v0.z;
+                const float4 v0 = fjSum[0];
+                float        sx = v0.x, sy = v0.y, sz = v0.z;
 #pragma unroll
                 for (int kx = 1; kx < c_clusterSize; kx++)
                 {
-                    const float4 v = col[kx ^ il];
+                    const float4 v = fjSum[kx];
                     sx += v.x;
                     sy += v.y;
                     sz += v.z;
                 }
-                red_add_v4(ad.f4 + ajOwn, sx, sy, sz);
+                red_add_v4(ad.f4 + ajOwn, -sx, -sy, -sz);
             }
         }
     }
 
-    /* i forces: add the two halves, reduce over the 4 jl-lanes, one v4 reduction per i-atom; shift force from
-     * the per-lane partial sums (central shift skipped, nbnxm_cuda_kernel.cuh:697-717) */
+    /* i forces: reduce over the 4 jl-lanes, one v4 reduction per i-atom; shift force from the per-lane partial
+     * sums (central shift skipped, nbnxm_cuda_kernel.cuh:697-717) */
     float fsx = 0.0f, fsy = 0.0f, fsz = 0.0f;
 #pragma unroll
     for (int ci = 0; ci < c_superClusterSize; ci++)
     {
-        float x = fi_total(fi[ci][0]), y = fi_total(fi[ci][1]), z = fi_total(fi[ci][2]);
+        float x = fi[ci][0], y = fi[ci][1], z = fi[ci][2];
         fsx += x;
         fsy += y;
         fsz += z;

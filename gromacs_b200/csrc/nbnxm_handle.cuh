@@ -128,6 +128,7 @@ struct nbnxm_b200
     nbb::DevBuf<double> fshift, energy;
     nbb::DevBuf<float2> nbfp, nbfpComb;
     nbb::DevBuf<float>  coulombTab;
+    nbb::DevBuf<float>  packedConsts; /* ParamsDev::packedConsts */
     bool           shiftVecUploaded = false;
     int            natoms = 0, natomsLocal = 0;
 
