@@ -304,6 +304,7 @@ __device__ __forceinline__ V pair_w(const ParamsDev&    p,
     return W;
 }
 
+constexpr int c_descChunk = 64; /* cjPacked groups staged in shared memory at a time */
 constexpr int c_fjRow = 9; /* float4 per j-atom slot in PackedShared::fj: 8 partial forces + 1 of padding */
 
 /* shared memory of one CTA (= one warp = one sci entry) */
@@ -324,6 +325,8 @@ struct PackedShared
     /* type table, -6*C6 and 12*C12 */
     float nbC6n[c_packedMaxTypes * c_packedMaxTypes];
     float nbC12[c_packedMaxTypes * c_packedMaxTypes];
+    /* the cjPacked groups of the current chunk of the sci entry, as in the list: cj[4], (imask, excl_ind) x 2 */
+    uint4 desc[2 * c_descChunk];
 };
 
 /* j-atoms of one j-cluster as this lane sees them: atoms jl (lo) and jl+4 (hi) */
@@ -340,7 +343,7 @@ struct FjAcc
 
 /* LJ parameters of two pairs: c6n = -6*C6, c12 = 12*C12 */
 template<int ELEC, int VDW>
-__device__ __forceinline__ void lj_params_packed(const PackedShared& sm, const float4 pi, const PackedJ& j, f32x2& c6n, f32x2& c12)
+__device__ __forceinline__ void lj_params_packed(const PackedShared& sm, const float2 pi, const PackedJ& j, f32x2& c6n, f32x2& c12)
 {
     using Fl = Flavor<ELEC, VDW, false>;
     if (Fl::ljCombGeom)
@@ -373,7 +376,7 @@ __device__ __forceinline__ void body_both(const ParamsDev&    p,
                                           const PackedConsts& k,
                                           const PackedShared& sm,
                                           const float4        xi,
-                                          const float4        pi,
+                                          const float2        pi,
                                           const PackedJ&      j,
                                           float (&fi)[3],
                                           FjAcc& fj)
@@ -415,7 +418,7 @@ __device__ __forceinline__ void body_single(const ParamsDev&    p,
                                             const PackedConsts& k,
                                             const PackedShared& sm,
                                             const float4        xi,
-                                            const float4        pi,
+                                            const float2        pi,
                                             const PackedJ&      j,
                                             float (&fi)[3],
                                             FjAcc& fj)
@@ -472,7 +475,7 @@ __device__ __forceinline__ f32x2 body_general(const ParamsDev&    p,
                                               const PackedConsts& k,
                                               const PackedShared& sm,
                                               const float4        xi,
-                                              const float4        pi,
+                                              const float2        pi,
                                               const PackedJ&      j,
                                               const bool          m0, /* list mask bits of the two halves */
                                               const bool          m1,
@@ -522,6 +525,50 @@ __device__ __forceinline__ f32x2 body_general(const ParamsDev&    p,
     return pk(w0 ? lo(F) : 0.0f, w1 ? hi(F) : 0.0f);
 }
 
+/* 32-bit shared-memory addresses and explicit ld/st.shared: with generic pointers into the shared struct ptxas
+ * re-derives the shared window base (S2UR SR_CgaCtaId, ULEA) and the lane offsets in front of the accesses of every
+ * loop iteration. */
+__device__ __forceinline__ unsigned smem_u32(const void* p)
+{
+    return static_cast<unsigned>(__cvta_generic_to_shared(p));
+}
+__device__ __forceinline__ float4 lds128(const unsigned a)
+{
+    float4 v;
+    asm volatile("ld.shared.v4.f32 {%0, %1, %2, %3}, [%4];" : "=f"(v.x), "=f"(v.y), "=f"(v.z), "=f"(v.w) : "r"(a) : "memory");
+    return v;
+}
+__device__ __forceinline__ uint4 lds128u(const unsigned a)
+{
+    uint4 v;
+    asm volatile("ld.shared.v4.u32 {%0, %1, %2, %3}, [%4];" : "=r"(v.x), "=r"(v.y), "=r"(v.z), "=r"(v.w) : "r"(a) : "memory");
+    return v;
+}
+__device__ __forceinline__ float2 lds64(const unsigned a)
+{
+    float2 v;
+    asm volatile("ld.shared.v2.f32 {%0, %1}, [%2];" : "=f"(v.x), "=f"(v.y) : "r"(a) : "memory");
+    return v;
+}
+__device__ __forceinline__ int lds32i(const unsigned a)
+{
+    int v;
+    asm volatile("ld.shared.u32 %0, [%1];" : "=r"(v) : "r"(a) : "memory");
+    return v;
+}
+__device__ __forceinline__ void sts128(const unsigned a, const float x, const float y, const float z, const float w)
+{
+    asm volatile("st.shared.v4.f32 [%0], {%1, %2, %3, %4};" ::"r"(a), "f"(x), "f"(y), "f"(z), "f"(w) : "memory");
+}
+__device__ __forceinline__ void sts128u(const unsigned a, const uint4 v)
+{
+    asm volatile("st.shared.v4.u32 [%0], {%1, %2, %3, %4};" ::"r"(a), "r"(v.x), "r"(v.y), "r"(v.z), "r"(v.w) : "memory");
+}
+__device__ __forceinline__ void sts32(const unsigned a, const float x)
+{
+    asm volatile("st.shared.f32 [%0], %1;" ::"r"(a), "f"(x) : "memory");
+}
+
 template<int ELEC, int VDW, bool ENERGY>
 __global__ void __launch_bounds__(32, ENERGY ? NBNXM_PACKED_MIN_BLOCKS_ENERGY : NBNXM_PACKED_MIN_BLOCKS)
         nbnxm_force_kernel_packed(const AtomDataDev ad, const ParamsDev p, const PairlistDev pl, const int calcFshift)
@@ -555,18 +602,25 @@ __global__ void __launch_bounds__(32, ENERGY ? NBNXM_PACKED_MIN_BLOCKS_ENERGY : 
         for (int n = 1; n < 5; n++) k.den[n] = __ldg(p.packedConsts + 8 + n);
     }
 
-    /* Lane-dependent shared-memory byte offsets, passed through a shuffle: ptxas would otherwise re-derive each of
+    /* Lane-dependent shared-memory addresses, passed through a shuffle: ptxas would otherwise re-derive each of
      * them from the thread index (S2R, shifts, masks) in front of every use instead of keeping a register. */
-    /* i-atom il of i-cluster 0 in xqi / lji */
-    const int iOff = __shfl_sync(c_full, il, lane);
-    /* this lane's entry of j-cluster 0 in jxy / jzq / jlj */
-    const int jOff0 = __shfl_sync(c_full, jl, lane);
-    /* where it parks its partial j forces: slot = 8*jm + jl (half 1: + 4), column il */
-    const int parkOff = __shfl_sync(c_full, jl * c_fjRow + il, lane);
+    /* i-atom il of i-cluster 0 in xqi (lji: + sizeof(xqi)) */
+    const unsigned xqiAddr = __shfl_sync(c_full, smem_u32(sm.xqi + il), lane);
+    constexpr unsigned c_ljiFromXqi = sizeof(float4) * 64;
+    /* this lane's entry of j-cluster 0 in jxy (jzq: + 256, jlj: + 512) */
+    const unsigned jAddr0 = __shfl_sync(c_full, smem_u32(sm.jxy + jl), lane);
+    /* where it parks its partial j forces of j-cluster 0: slot jl (half 1: slot jl + 4), column il */
+    const unsigned parkAddr0 = __shfl_sync(c_full, smem_u32(sm.fj + jl * c_fjRow + il), lane);
     /* the j-atom slot it reduces (the atom it fetched) */
-    const int sumOff = __shfl_sync(c_full, lane * c_fjRow, lane);
-    /* where it stages the atom it fetched (lane = 8*jm + atom, atom = 4*half + jl'): float index into jxy/jzq/jlj */
-    const int stageOff = __shfl_sync(c_full, ((lane >> 3) * 4 + (lane & 3)) * 4 + ((lane >> 2) & 1), lane);
+    const unsigned sumAddr = __shfl_sync(c_full, smem_u32(sm.fj + lane * c_fjRow), lane);
+    /* where it stages the atom it fetched (lane = 8*jm + atom, atom = 4*half + jl'): a float of jxy (+8: y; jzq, jlj alike) */
+    const unsigned stageAddr =
+            __shfl_sync(c_full, smem_u32(reinterpret_cast<float*>(sm.jxy) + ((lane >> 3) * 4 + (lane & 3)) * 4 + ((lane >> 2) & 1)), lane);
+    /* the cjPacked groups of the current chunk: cj[4], then (imask, excl_ind) x 2 */
+    const unsigned descAddr = __shfl_sync(c_full, smem_u32(sm.desc), lane);
+    const unsigned cjAddr   = __shfl_sync(c_full, smem_u32(reinterpret_cast<int*>(sm.desc) + jl), lane);
+    /* this lane's word of an exclusion mask entry */
+    const unsigned exclLane = __shfl_sync(c_full, lane, lane);
 
     /* energies: float partial sums per j-cluster, double across the sci entry (see nbnxm_force_kernel) */
     double     eLJ = 0.0, eEl = 0.0;
@@ -622,250 +676,245 @@ __global__ void __launch_bounds__(32, ENERGY ? NBNXM_PACKED_MIN_BLOCKS_ENERGY : 
     }
 
     const bool centralShift = (s.shift == c_centralShiftIndex);
-
-    /* Software pipeline over the cjPacked groups: the two (imask, excl_ind) words of a group (one 16-byte load, the
-     * same address in all lanes) and the j-cluster index a lane fetches an atom of are loaded two groups ahead, the
-     * atom itself - lane L fetches atom (L & 7) of j-cluster (L >> 3), one coalesced 16-byte load per lane - one
-     * group ahead. */
-    const uint4* cjGroups = reinterpret_cast<const uint4*>(pl.cjPacked);
-    const int*   cjInts   = reinterpret_cast<const int*>(pl.cjPacked);
-    int          jp       = s.cj_packed_begin;
-    const uint4  zero4    = make_uint4(0u, 0u, 0u, 0u);
-    uint4        meNext = zero4, meNext2 = zero4;
-    int          cjNext = 0, cjNext2 = 0;
-    if (jp < s.cj_packed_end)
-    {
-        meNext = cjGroups[2 * jp + 1];
-        cjNext = cjInts[8 * jp + jl];
-    }
-    if (jp + 1 < s.cj_packed_end)
-    {
-        meNext2 = cjGroups[2 * jp + 3];
-        cjNext2 = cjInts[8 * jp + 8 + jl];
-    }
-    float4 xjNext = make_float4(0.0f, 0.0f, 0.0f, 0.0f);
-    float2 pjNext = make_float2(0.0f, 0.0f);
-    int    ajNext = 0;
-
-    auto fetchAtoms = [&](const int cj, const uint4 mev, float4& xj, float2& pj, int& ajOut) {
-        /* unused slots of a partially filled group have no mask bits and an unspecified index */
-        if ((mev.x | mev.z) & (0xffu << (8 * jl)))
-        {
-            const int aj = cj * c_clusterSize + il;
-            xj           = ad.xq[aj];
-            if (Fl::ljComb)
-            {
-                pj = ad.ljComb[aj];
-            }
-            else
-            {
-                pj.x = __int_as_float(ad.atomType[aj]);
-            }
-            ajOut = aj;
-        }
-    };
-    fetchAtoms(cjNext, meNext, xjNext, pjNext, ajNext);
-
-    float* const  stageXY = reinterpret_cast<float*>(sm.jxy) + stageOff;
-    float* const  stageZQ = reinterpret_cast<float*>(sm.jzq) + stageOff;
-    float* const  stageLJ = reinterpret_cast<float*>(sm.jlj) + stageOff;
-    const float4* xqiLane = sm.xqi + iOff;
-    const float4* ljiLane = sm.lji + iOff;
-    const float4* fjSum   = sm.fj + sumOff;
     /* j <= i within the same cluster on the central shift: the "Newton" half of the diagonal cluster pair and the
      * self pair (nbnxm_cuda_kernel.cuh:421-423) */
     const bool selfLo = centralShift && jl <= il;
     const bool selfHi = centralShift && (jl + 4) <= il;
 
-    for (; jp < s.cj_packed_end; jp++)
+    const uint4* cjGroups = reinterpret_cast<const uint4*>(pl.cjPacked);
+
+    /* The cjPacked groups of the entry are staged in shared memory c_descChunk at a time (coalesced 16-byte loads),
+     * so that masks and j-cluster indices of the coming groups are a shared-memory read away.  Within a chunk the
+     * 32 j-atoms of a group - lane L fetches atom (L & 7) of j-cluster (L >> 3), one coalesced 16-byte load per lane -
+     * and the exclusion mask words are fetched one group ahead. */
+    for (int chunkBegin = s.cj_packed_begin; chunkBegin < s.cj_packed_end; chunkBegin += c_descChunk)
     {
-        const uint4 mev   = meNext;
-        const int   ajOwn = ajNext;
+        const int numInChunk = min(c_descChunk, s.cj_packed_end - chunkBegin);
         __syncwarp();
-        stageXY[0] = xjNext.x;
-        stageXY[2] = xjNext.y;
-        stageZQ[0] = xjNext.z;
-        stageZQ[2] = xjNext.w;
-        stageLJ[0] = pjNext.x;
-        if (Fl::ljComb)
+        for (int t = lane; t < 2 * numInChunk; t += 32)
         {
-            stageLJ[2] = pjNext.y;
+            sts128u(descAddr + 16 * t, cjGroups[2 * chunkBegin + t]);
         }
         __syncwarp();
-        meNext = meNext2;
-        cjNext = cjNext2;
-        if (jp + 2 < s.cj_packed_end)
-        {
-            meNext2 = cjGroups[2 * jp + 5];
-            cjNext2 = cjInts[8 * jp + 16 + jl];
-        }
-        else
-        {
-            meNext2 = zero4;
-        }
-        fetchAtoms(cjNext, meNext, xjNext, pjNext, ajNext);
 
-        unsigned cur0 = mev.x, cur1 = mev.z;
-        if ((cur0 | cur1) == 0u)
-        {
-            continue;
-        }
-        /* exclusion masks: entry 0 of the exclusion array is all ones (pairlist.h:274-287).  curEx gets the bits of
-         * the (j-cluster, i-cluster) pairs in which any atom pair of either half is excluded. */
-        unsigned wex0 = c_full, wex1 = c_full, curEx = 0u;
-        if ((mev.y | mev.w) != 0u)
-        {
-            if (mev.y != 0u) wex0 = pl.excl[mev.y].pair[lane];
-            if (mev.w != 0u) wex1 = pl.excl[mev.w].pair[lane];
-            curEx = __reduce_or_sync(c_full, ~(wex0 & wex1));
-        }
+        float4   xjNext = make_float4(0.0f, 0.0f, 0.0f, 0.0f);
+        float2   pjNext = make_float2(0.0f, 0.0f);
+        unsigned wex0Next = c_full, wex1Next = c_full;
+        auto     fetchGroup = [&](const int g) {
+            const uint4 me = lds128u(descAddr + 32 * g + 16);
+            /* unused slots of a partially filled group have no mask bits and an unspecified index */
+            if ((me.x | me.z) & (0xffu << (8 * jl)))
+            {
+                const int aj = lds32i(cjAddr + 32 * g) * c_clusterSize + il;
+                xjNext       = ad.xq[aj];
+                if (Fl::ljComb)
+                {
+                    pjNext = ad.ljComb[aj];
+                }
+                else
+                {
+                    pjNext.x = __int_as_float(ad.atomType[aj]);
+                }
+            }
+            /* entry 0 of the exclusion array is all ones (pairlist.h:274-287) */
+            wex0Next = c_full;
+            wex1Next = c_full;
+            if (me.y != 0u) wex0Next = pl.excl[me.y].pair[exclLane];
+            if (me.w != 0u) wex1Next = pl.excl[me.w].pair[exclLane];
+        };
+        fetchGroup(0);
 
-#pragma unroll 1
-        for (int jm = 0; (cur0 | cur1) != 0u; jm++, cur0 >>= 8, cur1 >>= 8, curEx >>= 8, wex0 >>= 8, wex1 >>= 8)
+        for (int g = 0; g < numInChunk; g++)
         {
-            const unsigned m0 = cur0 & 0xffu, m1 = cur1 & 0xffu;
-            if ((m0 | m1) == 0u)
+            const uint4    mev   = lds128u(descAddr + 32 * g + 16);
+            const unsigned wex0 = wex0Next, wex1 = wex1Next;
+            __syncwarp();
+            sts32(stageAddr, xjNext.x);
+            sts32(stageAddr + 8, xjNext.y);
+            sts32(stageAddr + 256, xjNext.z);
+            sts32(stageAddr + 256 + 8, xjNext.w);
+            sts32(stageAddr + 512, pjNext.x);
+            if (Fl::ljComb)
+            {
+                sts32(stageAddr + 512 + 8, pjNext.y);
+            }
+            __syncwarp();
+            if (g + 1 < numInChunk)
+            {
+                fetchGroup(g + 1);
+            }
+
+            unsigned cur0 = mev.x, cur1 = mev.z;
+            if ((cur0 | cur1) == 0u)
             {
                 continue;
             }
-            const float4 xy = sm.jxy[jOff0 + 4 * jm];
-            const float4 zq = sm.jzq[jOff0 + 4 * jm];
-            const float4 lj = sm.jlj[jOff0 + 4 * jm];
-            PackedJ      j;
-            j.x   = pk(xy.x, xy.y);
-            j.y   = pk(xy.z, xy.w);
-            j.z   = pk(zq.x, zq.y);
-            j.q   = pk(zq.z, zq.w);
-            j.lj0 = pk(lj.x, lj.y);
-            j.lj1 = pk(lj.z, lj.w);
-            FjAcc fj = { 0.0f, 0.0f, 0.0f, 0.0f, 0.0f, 0.0f };
-            f32x2 eLJj = 0ull, eElj = 0ull;
-            const unsigned mFast = (m0 | m1) & ~curEx;
-            if (!ENERGY)
+            /* curEx gets the bits of the (j-cluster, i-cluster) pairs in which any atom pair of either half is excluded */
+            unsigned curEx = 0u;
+            if ((mev.y | mev.w) != 0u)
             {
-                const unsigned mBoth = m0 & m1;
-#pragma unroll
-                for (int ci = 0; ci < c_superClusterSize; ci++)
-                {
-                    if (mFast & (1u << ci))
-                    {
-                        const float4 xi = xqiLane[ci * c_clusterSize];
-                        const float4 pi = ljiLane[ci * c_clusterSize];
-                        if (mBoth & (1u << ci))
-                        {
-                            body_both<ELEC, VDW>(p, k, sm, xi, pi, j, fi[ci], fj);
-                        }
-                        else if (m0 & (1u << ci))
-                        {
-                            body_single<ELEC, VDW, 0>(p, k, sm, xi, pi, j, fi[ci], fj);
-                        }
-                        else
-                        {
-                            body_single<ELEC, VDW, 1>(p, k, sm, xi, pi, j, fi[ci], fj);
-                        }
-                    }
-                }
+                curEx = __reduce_or_sync(c_full, ~(wex0 & wex1));
             }
-            else
-            {
-#pragma unroll
-                for (int ci = 0; ci < c_superClusterSize; ci++)
-                {
-                    if (mFast & (1u << ci))
-                    {
-                        const float4 xi = xqiLane[ci * c_clusterSize];
-                        const float4 pi = ljiLane[ci * c_clusterSize];
-                        f32x2        dx, dy, dz;
-                        const f32x2  F = body_general<ELEC, VDW, ENERGY, false>(p, k, sm, xi, pi, j, (m0 & (1u << ci)) != 0u,
-                                                                               (m1 & (1u << ci)) != 0u, true, true, false, false,
-                                                                               dx, dy, dz, eLJj, eElj);
-                        fi[ci][0] = fmaf(lo(F), lo(dx), fmaf(hi(F), hi(dx), fi[ci][0]));
-                        fi[ci][1] = fmaf(lo(F), lo(dy), fmaf(hi(F), hi(dy), fi[ci][1]));
-                        fi[ci][2] = fmaf(lo(F), lo(dz), fmaf(hi(F), hi(dz), fi[ci][2]));
-                        fj.xA     = fmaf(lo(F), lo(dx), fj.xA);
-                        fj.yA     = fmaf(lo(F), lo(dy), fj.yA);
-                        fj.zA     = fmaf(lo(F), lo(dz), fj.zA);
-                        fj.xB     = fmaf(hi(F), hi(dx), fj.xB);
-                        fj.yB     = fmaf(hi(F), hi(dy), fj.yB);
-                        fj.zB     = fmaf(hi(F), hi(dz), fj.zB);
-                    }
-                }
-            }
-            /* the few cluster pairs with exclusion masks: one loop body for all i-clusters, own accumulators */
-            unsigned mEx = (m0 | m1) & curEx;
-            if (mEx != 0u)
-            {
-                /* the i-cluster this j-cluster is, if any */
-                const int ciDiag = cjInts[8 * jp + jm] - s.sci * c_superClusterSize;
-                f32x2     gx = 0ull, gy = 0ull, gz = 0ull;
-#pragma unroll 1
-                for (; mEx != 0u; mEx &= mEx - 1u)
-                {
-                    const int    ci = __ffs(mEx) - 1;
-                    const float4 xi = xqiLane[ci * c_clusterSize];
-                    const float4 pi = ljiLane[ci * c_clusterSize];
-                    const bool   onDiagonal = (ciDiag == ci);
-                    f32x2        dx, dy, dz;
-                    const f32x2  F = body_general<ELEC, VDW, ENERGY, true>(
-                            p, k, sm, xi, pi, j, ((m0 >> ci) & 1u) != 0u, ((m1 >> ci) & 1u) != 0u, ((wex0 >> ci) & 1u) != 0u,
-                            ((wex1 >> ci) & 1u) != 0u, onDiagonal && selfLo, onDiagonal && selfHi, dx, dy, dz, eLJj, eElj);
-                    const float fx = fmaf(lo(F), lo(dx), hi(F) * hi(dx));
-                    const float fy = fmaf(lo(F), lo(dy), hi(F) * hi(dy));
-                    const float fz = fmaf(lo(F), lo(dz), hi(F) * hi(dz));
-#pragma unroll
-                    for (int c = 0; c < c_superClusterSize; c++)
-                    {
-                        const bool hit = (c == ci);
-                        fi[c][0] += hit ? fx : 0.0f;
-                        fi[c][1] += hit ? fy : 0.0f;
-                        fi[c][2] += hit ? fz : 0.0f;
-                    }
-                    gx = vfma(F, dx, gx);
-                    gy = vfma(F, dy, gy);
-                    gz = vfma(F, dz, gz);
-                }
-                fj.xA += lo(gx);
-                fj.yA += lo(gy);
-                fj.zA += lo(gz);
-                fj.xB += hi(gx);
-                fj.yB += hi(gy);
-                fj.zB += hi(gz);
-            }
-            if (ENERGY)
-            {
-                eLJ += lo(eLJj) + hi(eLJj);
-                eEl += lo(eElj) + hi(eElj);
-            }
-            /* park the partial j forces (sum of F d: the j-atom gets minus that, applied after the reduction) */
-            float4* const park = sm.fj + parkOff + jm * (c_clusterSize * c_fjRow);
-            if (m0 != 0u)
-            {
-                park[0] = make_float4(fj.xA, fj.yA, fj.zA, 0.0f);
-            }
-            if (m1 != 0u)
-            {
-                park[4 * c_fjRow] = make_float4(fj.xB, fj.yB, fj.zB, 0.0f);
-            }
-        }
 
-        /* j forces of the group: lane L sums the 8 partial forces of j-atom slot L (the atom it fetched) and adds
-         * them with one v4 reduction; slots of halves that were not visited hold stale data and are skipped */
-        __syncwarp();
-        {
-            const unsigned visited = (((lane >> 2) & 1) ? mev.z : mev.x) & (0xffu << (8 * (lane >> 3)));
-            if (visited != 0u)
+            unsigned jAddr = jAddr0, parkAddr = parkAddr0;
+#pragma unroll 1
+            for (int jm = 0; (cur0 | cur1) != 0u;
+                 jm++, cur0 >>= 8, cur1 >>= 8, curEx >>= 8, jAddr += 64, parkAddr += 16 * c_clusterSize * c_fjRow)
             {
-                const float4 v0 = fjSum[0];
-                float        sx = v0.x, sy = v0.y, sz = v0.z;
-#pragma unroll
-                for (int kx = 1; kx < c_clusterSize; kx++)
+                const unsigned m0 = cur0 & 0xffu, m1 = cur1 & 0xffu;
+                if ((m0 | m1) == 0u)
                 {
-                    const float4 v = fjSum[kx];
-                    sx += v.x;
-                    sy += v.y;
-                    sz += v.z;
+                    continue;
                 }
-                red_add_v4(ad.f4 + ajOwn, -sx, -sy, -sz);
+                const float4 xy = lds128(jAddr), zq = lds128(jAddr + 256), lj = lds128(jAddr + 512);
+                PackedJ      j;
+                j.x   = pk(xy.x, xy.y);
+                j.y   = pk(xy.z, xy.w);
+                j.z   = pk(zq.x, zq.y);
+                j.q   = pk(zq.z, zq.w);
+                j.lj0 = pk(lj.x, lj.y);
+                j.lj1 = pk(lj.z, lj.w);
+                FjAcc fj = { 0.0f, 0.0f, 0.0f, 0.0f, 0.0f, 0.0f };
+                f32x2 eLJj = 0ull, eElj = 0ull;
+                const unsigned mFast = (m0 | m1) & ~curEx;
+                if (!ENERGY)
+                {
+                    const unsigned mBoth = m0 & m1;
+#pragma unroll
+                    for (int ci = 0; ci < c_superClusterSize; ci++)
+                    {
+                        if (mFast & (1u << ci))
+                        {
+                            const float4 xi = lds128(xqiAddr + ci * (16 * c_clusterSize));
+                            const float2 pi = lds64(xqiAddr + c_ljiFromXqi + ci * (16 * c_clusterSize));
+                            if (mBoth & (1u << ci))
+                            {
+                                body_both<ELEC, VDW>(p, k, sm, xi, pi, j, fi[ci], fj);
+                            }
+                            else if (m0 & (1u << ci))
+                            {
+                                body_single<ELEC, VDW, 0>(p, k, sm, xi, pi, j, fi[ci], fj);
+                            }
+                            else
+                            {
+                                body_single<ELEC, VDW, 1>(p, k, sm, xi, pi, j, fi[ci], fj);
+                            }
+                        }
+                    }
+                }
+                else
+                {
+#pragma unroll
+                    for (int ci = 0; ci < c_superClusterSize; ci++)
+                    {
+                        if (mFast & (1u << ci))
+                        {
+                            const float4 xi = lds128(xqiAddr + ci * (16 * c_clusterSize));
+                            const float2 pi = lds64(xqiAddr + c_ljiFromXqi + ci * (16 * c_clusterSize));
+                            f32x2        dx, dy, dz;
+                            const f32x2  F = body_general<ELEC, VDW, ENERGY, false>(p, k, sm, xi, pi, j, (m0 & (1u << ci)) != 0u,
+                                                                                   (m1 & (1u << ci)) != 0u, true, true, false,
+                                                                                   false, dx, dy, dz, eLJj, eElj);
+                            fi[ci][0] = fmaf(lo(F), lo(dx), fmaf(hi(F), hi(dx), fi[ci][0]));
+                            fi[ci][1] = fmaf(lo(F), lo(dy), fmaf(hi(F), hi(dy), fi[ci][1]));
+                            fi[ci][2] = fmaf(lo(F), lo(dz), fmaf(hi(F), hi(dz), fi[ci][2]));
+                            fj.xA     = fmaf(lo(F), lo(dx), fj.xA);
+                            fj.yA     = fmaf(lo(F), lo(dy), fj.yA);
+                            fj.zA     = fmaf(lo(F), lo(dz), fj.zA);
+                            fj.xB     = fmaf(hi(F), hi(dx), fj.xB);
+                            fj.yB     = fmaf(hi(F), hi(dy), fj.yB);
+                            fj.zB     = fmaf(hi(F), hi(dz), fj.zB);
+                        }
+                    }
+                }
+                /* the few cluster pairs with exclusion masks: one loop body for all i-clusters, own accumulators */
+                unsigned mEx = (m0 | m1) & curEx;
+                if (mEx != 0u)
+                {
+                    /* the i-cluster this j-cluster is, if any */
+                    const int ciDiag = lds32i(descAddr + 32 * g + 4 * jm) - s.sci * c_superClusterSize;
+                    f32x2     gx = 0ull, gy = 0ull, gz = 0ull;
+#pragma unroll 1
+                    for (; mEx != 0u; mEx &= mEx - 1u)
+                    {
+                        const int    ci = __ffs(mEx) - 1;
+                        const float4 xi = lds128(xqiAddr + ci * (16 * c_clusterSize));
+                        const float2 pi = lds64(xqiAddr + c_ljiFromXqi + ci * (16 * c_clusterSize));
+                        const bool   onDiagonal = (ciDiag == ci);
+                        const int    bit        = 8 * jm + ci;
+                        f32x2        dx, dy, dz;
+                        const f32x2  F = body_general<ELEC, VDW, ENERGY, true>(
+                                p, k, sm, xi, pi, j, ((m0 >> ci) & 1u) != 0u, ((m1 >> ci) & 1u) != 0u, ((wex0 >> bit) & 1u) != 0u,
+                                ((wex1 >> bit) & 1u) != 0u, onDiagonal && selfLo, onDiagonal && selfHi, dx, dy, dz, eLJj, eElj);
+                        const float fx = fmaf(lo(F), lo(dx), hi(F) * hi(dx));
+                        const float fy = fmaf(lo(F), lo(dy), hi(F) * hi(dy));
+                        const float fz = fmaf(lo(F), lo(dz), hi(F) * hi(dz));
+                        switch (ci)
+                        {
+#define NBNXM_FI_CASE(c) \
+    case c:              \
+        fi[c][0] += fx;  \
+        fi[c][1] += fy;  \
+        fi[c][2] += fz;  \
+        break;
+                            NBNXM_FI_CASE(0)
+                            NBNXM_FI_CASE(1)
+                            NBNXM_FI_CASE(2)
+                            NBNXM_FI_CASE(3)
+                            NBNXM_FI_CASE(4)
+                            NBNXM_FI_CASE(5)
+                            NBNXM_FI_CASE(6)
+                            NBNXM_FI_CASE(7)
+#undef NBNXM_FI_CASE
+                        }
+                        gx = vfma(F, dx, gx);
+                        gy = vfma(F, dy, gy);
+                        gz = vfma(F, dz, gz);
+                    }
+                    fj.xA += lo(gx);
+                    fj.yA += lo(gy);
+                    fj.zA += lo(gz);
+                    fj.xB += hi(gx);
+                    fj.yB += hi(gy);
+                    fj.zB += hi(gz);
+                }
+                if (ENERGY)
+                {
+                    eLJ += lo(eLJj) + hi(eLJj);
+                    eEl += lo(eElj) + hi(eElj);
+                }
+                /* park the partial j forces (sum of F d: the j-atom gets minus that, applied after the reduction) */
+                if (m0 != 0u)
+                {
+                    sts128(parkAddr, fj.xA, fj.yA, fj.zA, 0.0f);
+                }
+                if (m1 != 0u)
+                {
+                    sts128(parkAddr + 16 * 4 * c_fjRow, fj.xB, fj.yB, fj.zB, 0.0f);
+                }
+            }
+
+            /* j forces of the group: lane L sums the 8 partial forces of j-atom slot L (the atom it fetched) and adds
+             * them with one v4 reduction; slots of halves that were not visited hold stale data and are skipped */
+            __syncwarp();
+            {
+                const unsigned visited = (((lane >> 2) & 1) ? mev.z : mev.x) & (0xffu << (8 * (lane >> 3)));
+                if (visited != 0u)
+                {
+                    const float4 v0 = lds128(sumAddr);
+                    float        sx = v0.x, sy = v0.y, sz = v0.z;
+#pragma unroll
+                    for (int kx = 1; kx < c_clusterSize; kx++)
+                    {
+                        const float4 v = lds128(sumAddr + 16 * kx);
+                        sx += v.x;
+                        sy += v.y;
+                        sz += v.z;
+                    }
+                    /* the atom this lane fetched for the group */
+                    const int ajOwn = lds32i(cjAddr + 32 * g) * c_clusterSize + il;
+                    red_add_v4(ad.f4 + ajOwn, -sx, -sy, -sz);
+                }
             }
         }
     }
