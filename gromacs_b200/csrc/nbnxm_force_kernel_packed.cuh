@@ -582,7 +582,7 @@ __global__ void __launch_bounds__(32, ENERGY ? NBNXM_PACKED_MIN_BLOCKS_ENERGY : 
     const int jl   = lane >> 3;
     const nbnxm_b200_sci_t s = pl.sciSorted[blockIdx.x];
 
-    __shared__ PackedShared sm;
+    __shared__ __align__(128) PackedShared sm;
 
     const float shx = ad.shiftVec[3 * s.shift], shy = ad.shiftVec[3 * s.shift + 1], shz = ad.shiftVec[3 * s.shift + 2];
 
@@ -618,9 +618,10 @@ __global__ void __launch_bounds__(32, ENERGY ? NBNXM_PACKED_MIN_BLOCKS_ENERGY : 
             __shfl_sync(c_full, smem_u32(reinterpret_cast<float*>(sm.jxy) + ((lane >> 3) * 4 + (lane & 3)) * 4 + ((lane >> 2) & 1)), lane);
     /* the cjPacked groups of the current chunk: cj[4], then (imask, excl_ind) x 2 */
     const unsigned descAddr = __shfl_sync(c_full, smem_u32(sm.desc), lane);
-    const unsigned cjAddr   = __shfl_sync(c_full, smem_u32(reinterpret_cast<int*>(sm.desc) + jl), lane);
-    /* this lane's word of an exclusion mask entry */
-    const unsigned exclLane = __shfl_sync(c_full, lane, lane);
+    /* il and jl can be read back from the low bits of these addresses (the struct is 128-byte aligned): cheaper than
+     * holding them in registers for the few places that need them */
+#define NBNXM_IL_FROM_ADDR ((xqiAddr >> 4) & 7u)
+#define NBNXM_JL_FROM_ADDR ((jAddr0 >> 4) & 3u)
 
     /* energies: float partial sums per j-cluster, double across the sci entry (see nbnxm_force_kernel) */
     double     eLJ = 0.0, eEl = 0.0;
@@ -676,10 +677,6 @@ __global__ void __launch_bounds__(32, ENERGY ? NBNXM_PACKED_MIN_BLOCKS_ENERGY : 
     }
 
     const bool centralShift = (s.shift == c_centralShiftIndex);
-    /* j <= i within the same cluster on the central shift: the "Newton" half of the diagonal cluster pair and the
-     * self pair (nbnxm_cuda_kernel.cuh:421-423) */
-    const bool selfLo = centralShift && jl <= il;
-    const bool selfHi = centralShift && (jl + 4) <= il;
 
     const uint4* cjGroups = reinterpret_cast<const uint4*>(pl.cjPacked);
 
@@ -700,12 +697,14 @@ __global__ void __launch_bounds__(32, ENERGY ? NBNXM_PACKED_MIN_BLOCKS_ENERGY : 
         float4   xjNext = make_float4(0.0f, 0.0f, 0.0f, 0.0f);
         float2   pjNext = make_float2(0.0f, 0.0f);
         unsigned wex0Next = c_full, wex1Next = c_full;
+        bool     fetchedNext = false;
         auto     fetchGroup = [&](const int g) {
             const uint4 me = lds128u(descAddr + 32 * g + 16);
             /* unused slots of a partially filled group have no mask bits and an unspecified index */
-            if ((me.x | me.z) & (0xffu << (8 * jl)))
+            fetchedNext = (((me.x | me.z) >> (8u * NBNXM_JL_FROM_ADDR)) & 0xffu) != 0u;
+            if (fetchedNext)
             {
-                const int aj = lds32i(cjAddr + 32 * g) * c_clusterSize + il;
+                const int aj = lds32i(descAddr + 32 * g + 4u * NBNXM_JL_FROM_ADDR) * c_clusterSize + NBNXM_IL_FROM_ADDR;
                 xjNext       = ad.xq[aj];
                 if (Fl::ljComb)
                 {
@@ -719,8 +718,12 @@ __global__ void __launch_bounds__(32, ENERGY ? NBNXM_PACKED_MIN_BLOCKS_ENERGY : 
             /* entry 0 of the exclusion array is all ones (pairlist.h:274-287) */
             wex0Next = c_full;
             wex1Next = c_full;
-            if (me.y != 0u) wex0Next = pl.excl[me.y].pair[exclLane];
-            if (me.w != 0u) wex1Next = pl.excl[me.w].pair[exclLane];
+            if ((me.y | me.w) != 0u)
+            {
+                const unsigned exclLane = 8u * NBNXM_JL_FROM_ADDR + NBNXM_IL_FROM_ADDR;
+                if (me.y != 0u) wex0Next = pl.excl[me.y].pair[exclLane];
+                if (me.w != 0u) wex1Next = pl.excl[me.w].pair[exclLane];
+            }
         };
         fetchGroup(0);
 
@@ -728,6 +731,7 @@ __global__ void __launch_bounds__(32, ENERGY ? NBNXM_PACKED_MIN_BLOCKS_ENERGY : 
         {
             const uint4    mev   = lds128u(descAddr + 32 * g + 16);
             const unsigned wex0 = wex0Next, wex1 = wex1Next;
+            const bool     fetched = fetchedNext;
             __syncwarp();
             sts32(stageAddr, xjNext.x);
             sts32(stageAddr + 8, xjNext.y);
@@ -833,7 +837,11 @@ __global__ void __launch_bounds__(32, ENERGY ? NBNXM_PACKED_MIN_BLOCKS_ENERGY : 
                 {
                     /* the i-cluster this j-cluster is, if any */
                     const int ciDiag = lds32i(descAddr + 32 * g + 4 * jm) - s.sci * c_superClusterSize;
-                    f32x2     gx = 0ull, gy = 0ull, gz = 0ull;
+                    /* j <= i within the same cluster on the central shift: the "Newton" half of the diagonal cluster
+                     * pair and the self pair (nbnxm_cuda_kernel.cuh:421-423) */
+                    const bool selfLo = centralShift && NBNXM_JL_FROM_ADDR <= NBNXM_IL_FROM_ADDR;
+                    const bool selfHi = centralShift && (NBNXM_JL_FROM_ADDR + 4u) <= NBNXM_IL_FROM_ADDR;
+                    f32x2      gx = 0ull, gy = 0ull, gz = 0ull;
 #pragma unroll 1
                     for (; mEx != 0u; mEx &= mEx - 1u)
                     {
@@ -883,23 +891,17 @@ __global__ void __launch_bounds__(32, ENERGY ? NBNXM_PACKED_MIN_BLOCKS_ENERGY : 
                     eLJ += lo(eLJj) + hi(eLJj);
                     eEl += lo(eElj) + hi(eElj);
                 }
-                /* park the partial j forces (sum of F d: the j-atom gets minus that, applied after the reduction) */
-                if (m0 != 0u)
-                {
-                    sts128(parkAddr, fj.xA, fj.yA, fj.zA, 0.0f);
-                }
-                if (m1 != 0u)
-                {
-                    sts128(parkAddr + 16 * 4 * c_fjRow, fj.xB, fj.yB, fj.zB, 0.0f);
-                }
+                /* park the partial j forces of both halves (sum of F d: the j-atom gets minus that, applied after the
+                 * reduction); a half without list bits parks zeros */
+                sts128(parkAddr, fj.xA, fj.yA, fj.zA, 0.0f);
+                sts128(parkAddr + 16 * 4 * c_fjRow, fj.xB, fj.yB, fj.zB, 0.0f);
             }
 
             /* j forces of the group: lane L sums the 8 partial forces of j-atom slot L (the atom it fetched) and adds
-             * them with one v4 reduction; slots of halves that were not visited hold stale data and are skipped */
+             * them with one v4 reduction; slots of j-clusters that were not visited hold stale data and are skipped */
             __syncwarp();
             {
-                const unsigned visited = (((lane >> 2) & 1) ? mev.z : mev.x) & (0xffu << (8 * (lane >> 3)));
-                if (visited != 0u)
+                if (fetched)
                 {
                     const float4 v0 = lds128(sumAddr);
                     float        sx = v0.x, sy = v0.y, sz = v0.z;
@@ -912,7 +914,7 @@ __global__ void __launch_bounds__(32, ENERGY ? NBNXM_PACKED_MIN_BLOCKS_ENERGY : 
                         sz += v.z;
                     }
                     /* the atom this lane fetched for the group */
-                    const int ajOwn = lds32i(cjAddr + 32 * g) * c_clusterSize + il;
+                    const int ajOwn = lds32i(descAddr + 32 * g + 4u * NBNXM_JL_FROM_ADDR) * c_clusterSize + NBNXM_IL_FROM_ADDR;
                     red_add_v4(ad.f4 + ajOwn, -sx, -sy, -sz);
                 }
             }
@@ -965,6 +967,9 @@ __global__ void __launch_bounds__(32, ENERGY ? NBNXM_PACKED_MIN_BLOCKS_ENERGY : 
         }
     }
 }
+
+#undef NBNXM_IL_FROM_ADDR
+#undef NBNXM_JL_FROM_ADDR
 
 } // namespace nbb
 
