@@ -94,11 +94,19 @@ int fillParamsDev(nbnxm_b200* nb)
     {
         /* the packed kernel reads its pair-body constants from global memory (nbnxm_force_kernel_packed.cuh);
          * kernels of earlier steps may still be reading the previous values */
-        float h[13];
-        h[0] = d.rcoulomb_sq;
-        for (int k = 0; k < 7; k++) h[1 + k] = d.pmeNum[k];
-        for (int k = 0; k < 5; k++) h[8 + k] = d.pmeDen[k];
-        CU(nb->packedConsts.reserve(16));
+        float h[pcCount] = {};
+        h[pcRc2] = d.rcoulomb_sq;
+        for (int k = 0; k < 7; k++) h[pcNum0 + k] = d.pmeNum[k];
+        for (int k = 0; k < 5; k++) h[pcDen0 + k] = d.pmeDen[k];
+        h[pcRvdw2] = d.rvdw_sq; h[pcBeta] = d.ewald_beta; h[pcEpsfac] = d.epsfac; h[pcRvdwSwitch] = d.rvdw_switch;
+        h[pcDispC2] = d.disp_c2; h[pcDispC3] = d.disp_c3; h[pcRepC2] = d.rep_c2; h[pcRepC3] = d.rep_c3;
+        h[pcDispC2Third] = d.disp_c2 * (1.0f / 3.0f); h[pcDispC3Quarter] = d.disp_c3 * 0.25f;
+        h[pcRepC2Third] = d.rep_c2 * (1.0f / 3.0f); h[pcRepC3Quarter] = d.rep_c3 * 0.25f;
+        h[pcDispCpot] = d.disp_cpot; h[pcRepCpot] = d.rep_cpot;
+        h[pcSwC3] = d.sw_c3; h[pcSwC4] = d.sw_c4; h[pcSwC5] = d.sw_c5;
+        h[pcSwC3x3] = 3.0f * d.sw_c3; h[pcSwC4x4] = 4.0f * d.sw_c4; h[pcSwC5x5] = 5.0f * d.sw_c5;
+        h[pcCrf] = d.c_rf; h[pcTwoKrf] = d.two_k_rf; h[pcHalfTwoKrf] = 0.5f * d.two_k_rf; h[pcShEwald] = d.sh_ewald;
+        CU(nb->packedConsts.reserve(pcCount));
         if (nb->stream[0]) CU(cudaStreamSynchronize(nb->stream[0]));
         if (nb->stream[1]) CU(cudaStreamSynchronize(nb->stream[1]));
         CU(cudaMemcpy(nb->packedConsts.p, h, sizeof(h), cudaMemcpyHostToDevice));

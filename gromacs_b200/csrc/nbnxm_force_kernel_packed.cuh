@@ -43,6 +43,8 @@ constexpr int c_packedMaxTypes = 8;
 /* added to r^2 in the force-only path without exclusions: keeps r^-6 finite for coinciding filler atoms
  * (whose parameters are zero) and is below half an ulp of any r^2 > 2e-5 nm^2 */
 constexpr float c_r2Guard = 1.0e-12f;
+/* upper clamp of r^2 in the bodies that mask by multiplication (nm^2) */
+constexpr float c_maxDistanceSquared = 1.0e4f;
 
 typedef unsigned long long f32x2; /* (lo, hi) = (half 0, half 1) */
 
@@ -156,19 +158,82 @@ __device__ __forceinline__ V erfc_poly(const V x)
     q         = vfma(q, t, vbc<V>(2.443820402e-01f));
     q         = vfma(q, t, vbc<V>(2.873080888e-01f));
     q         = vfma(q, t, vbc<V>(-3.139566102e-04f));
-    const V x2hi = vmul(x, x);
-    const V x2lo = vfma(x, x, vsub(vbc<V>(0.0f), x2hi));
-    V       e    = vex2(vmul(x2hi, vbc<V>(-1.4426950408889634f)));
-    e            = vfma(vsub(vbc<V>(0.0f), e), x2lo, e);
+    /* exp(-x^2) with the rounding error of x^2 compensated: h = fl(x^2), nl = h - x^2 exactly, e (1 + nl) */
+    const V nx = vmul(x, vbc<V>(-1.0f));
+    const V h  = vmul(x, x);
+    const V nl = vfma(nx, x, h);
+    V       e  = vex2(vmul(h, vbc<V>(-1.4426950408889634f)));
+    e          = vfma(e, nl, e);
     return vmul(q, e);
 }
 
-/* constants of the pair bodies that are the same for every pair of a launch (uniform registers) */
+/* Constants of the pair bodies that are the same for every pair of a launch.  The kernel loads them from a small
+ * global-memory array (ParamsDev::packedConsts, filled by fillParamsDev), not from the kernel parameters: values
+ * read from the constant bank are re-loaded by ptxas in front of every use (FFMA2 takes no constant-bank operand),
+ * a dozen instructions per pair body, while loaded values stay in uniform registers. */
 struct PackedConsts
 {
     float rc2, rvdw2, beta, epsfac;
     float num[7], den[5]; /* pmeCorrF with beta folded in: beta^3 pmeCorrF(beta^2 r^2) = num(r^2) / den(r^2) */
+    float rvdw_switch, disp_c2, disp_c3, rep_c2, rep_c3, disp_c2_3, disp_c3_4, rep_c2_3, rep_c3_4, disp_cpot, rep_cpot;
+    float sw_c3, sw_c4, sw_c5, sw_c3x3, sw_c4x4, sw_c5x5, c_rf, two_k_rf, half_two_k_rf, sh_ewald;
 };
+
+template<int ELEC, int VDW, bool ENERGY>
+__device__ __forceinline__ void load_packed_consts(PackedConsts& k, const float* __restrict__ g)
+{
+    using Fl = Flavor<ELEC, VDW, ENERGY>;
+    k.rc2    = __ldg(g + pcRc2);
+    k.epsfac = __ldg(g + pcEpsfac);
+    if (Fl::vdwCutoffCheck) k.rvdw2 = __ldg(g + pcRvdw2);
+    if (Fl::ewaldAna)
+    {
+#pragma unroll
+        for (int n = 0; n < 7; n++) k.num[n] = __ldg(g + pcNum0 + n);
+#pragma unroll
+        for (int n = 1; n < 5; n++) k.den[n] = __ldg(g + pcDen0 + n);
+        if (ENERGY)
+        {
+            k.beta     = __ldg(g + pcBeta);
+            k.sh_ewald = __ldg(g + pcShEwald);
+        }
+    }
+    if (ENERGY || Fl::ljPSwitch)
+    {
+        k.disp_cpot = __ldg(g + pcDispCpot);
+        k.rep_cpot  = __ldg(g + pcRepCpot);
+    }
+    if (Fl::ljFSwitch || Fl::ljPSwitch) k.rvdw_switch = __ldg(g + pcRvdwSwitch);
+    if (Fl::ljFSwitch)
+    {
+        k.disp_c2 = __ldg(g + pcDispC2);
+        k.disp_c3 = __ldg(g + pcDispC3);
+        k.rep_c2  = __ldg(g + pcRepC2);
+        k.rep_c3  = __ldg(g + pcRepC3);
+        if (ENERGY)
+        {
+            k.disp_c2_3 = __ldg(g + pcDispC2Third);
+            k.disp_c3_4 = __ldg(g + pcDispC3Quarter);
+            k.rep_c2_3  = __ldg(g + pcRepC2Third);
+            k.rep_c3_4  = __ldg(g + pcRepC3Quarter);
+        }
+    }
+    if (Fl::ljPSwitch)
+    {
+        k.sw_c3   = __ldg(g + pcSwC3);
+        k.sw_c4   = __ldg(g + pcSwC4);
+        k.sw_c5   = __ldg(g + pcSwC5);
+        k.sw_c3x3 = __ldg(g + pcSwC3x3);
+        k.sw_c4x4 = __ldg(g + pcSwC4x4);
+        k.sw_c5x5 = __ldg(g + pcSwC5x5);
+    }
+    if (Fl::elecCut || Fl::elecRF) k.c_rf = __ldg(g + pcCrf);
+    if (Fl::elecRF)
+    {
+        k.two_k_rf      = __ldg(g + pcTwoKrf);
+        k.half_two_k_rf = __ldg(g + pcHalfTwoKrf);
+    }
+}
 
 /* W = (F/r) r^2 and r^-2 of one pair (V = float) or two (V = f32x2); F/r = W r^-2 is left to the caller, which
  * masks it.  c6n = -6*C6, c12 = 12*C12, qq = qi*qj (with epsfac unless ENERGY); intBit = 1/0, only read when EXCL.
@@ -205,8 +270,8 @@ __device__ __forceinline__ V pair_w(const ParamsDev&    p,
     if (ENERGY || Fl::ljPSwitch)
     {
         /* c12 (invR6^2 + rep.cpot) / 12 - c6 (invR6 + disp.cpot) / 6 */
-        eLJ = vfma(vmul(c12, vbc<V>(c_oneTwelfth)), vfma(invR6, invR6, vbc<V>(p.rep_cpot)),
-                   vmul(vmul(c6n, vbc<V>(c_oneSixth)), vadd(invR6, vbc<V>(p.disp_cpot))));
+        eLJ = vfma(vmul(c12, vbc<V>(c_oneTwelfth)), vfma(invR6, invR6, vbc<V>(k.rep_cpot)),
+                   vmul(vmul(c6n, vbc<V>(c_oneSixth)), vadd(invR6, vbc<V>(k.disp_cpot))));
         if (EXCL && Fl::exclusionForces)
         {
             eLJ = vmul(eLJ, intBit);
@@ -219,32 +284,33 @@ __device__ __forceinline__ V pair_w(const ParamsDev&    p,
     }
     if (Fl::ljFSwitch || Fl::ljPSwitch)
     {
-        const V rsw = vmax0(vsub(r, vbc<V>(p.rvdw_switch)));
+        const V rsw = vmax0(vsub(r, vbc<V>(k.rvdw_switch)));
         if (Fl::ljFSwitch)
         {
             /* F/r += (-c6 (d2 + d3 rsw) + c12 (r2 + r3 rsw)) rsw^2 / r, i.e. W += (...) rsw^2 r */
-            const V disp = vfma(rsw, vbc<V>(p.disp_c3), vbc<V>(p.disp_c2));
-            const V rep  = vfma(rsw, vbc<V>(p.rep_c3), vbc<V>(p.rep_c2));
+            const V disp = vfma(rsw, vbc<V>(k.disp_c3), vbc<V>(k.disp_c2));
+            const V rep  = vfma(rsw, vbc<V>(k.rep_c3), vbc<V>(k.rep_c2));
             const V t    = vfma(c12, rep, vmul(c6n, disp));
             const V rsw2 = vmul(rsw, rsw);
             W            = vfma(vmul(t, rsw2), r, W);
             if (ENERGY)
             {
                 /* (c6 (d2/3 + d3/4 rsw) - c12 (r2/3 + r3/4 rsw)) rsw^3, with c6n = -c6 */
-                const V dispE = vfma(rsw, vbc<V>(p.disp_c3 * 0.25f), vbc<V>(p.disp_c2 * (1.0f / 3.0f)));
-                const V repE  = vfma(rsw, vbc<V>(p.rep_c3 * 0.25f), vbc<V>(p.rep_c2 * (1.0f / 3.0f)));
-                const V u     = vfma(c12, repE, vmul(c6n, dispE));
-                eLJ           = vfma(vsub(vbc<V>(0.0f), u), vmul(rsw2, rsw), eLJ);
+                const V dispE = vfma(rsw, vbc<V>(-k.disp_c3_4), vbc<V>(-k.disp_c2_3));
+                const V repE  = vfma(rsw, vbc<V>(-k.rep_c3_4), vbc<V>(-k.rep_c2_3));
+                const V u     = vfma(c12, repE, vmul(c6n, dispE)); /* minus the switch energy per rsw^3 */
+                eLJ           = vfma(u, vmul(rsw2, rsw), eLJ);
             }
         }
         else
         {
             /* potential switch needs the pair energy even in the force-only kernel */
             const V rsw2 = vmul(rsw, rsw);
-            const V sw   = vfma(vmul(rsw2, rsw), vfma(vfma(rsw, vbc<V>(p.sw_c5), vbc<V>(p.sw_c4)), rsw, vbc<V>(p.sw_c3)), vbc<V>(1.0f));
-            const V dsw  = vmul(rsw2, vfma(vfma(rsw, vbc<V>(5.0f * p.sw_c5), vbc<V>(4.0f * p.sw_c4)), rsw, vbc<V>(3.0f * p.sw_c3)));
+            const V sw   = vfma(vmul(rsw2, rsw), vfma(vfma(rsw, vbc<V>(k.sw_c5), vbc<V>(k.sw_c4)), rsw, vbc<V>(k.sw_c3)), vbc<V>(1.0f));
+            /* minus the derivative of the switch function */
+            const V ndsw = vmul(rsw2, vfma(vfma(rsw, vbc<V>(-k.sw_c5x5), vbc<V>(-k.sw_c4x4)), rsw, vbc<V>(-k.sw_c3x3)));
             /* F/r = F/r sw - eLJ dsw / r, i.e. W = W sw - r eLJ dsw (rsw = 0 gives sw = 1, dsw = 0) */
-            W   = vfma(W, sw, vmul(vmul(r, eLJ), vsub(vbc<V>(0.0f), dsw)));
+            W   = vfma(W, sw, vmul(vmul(r, eLJ), ndsw));
             eLJ = vmul(eLJ, sw);
         }
     }
@@ -261,13 +327,13 @@ __device__ __forceinline__ V pair_w(const ParamsDev&    p,
     if (Fl::elecCut)
     {
         W = vfma(qqF, invRi, W);
-        if (ENERGY) eEl = vmul(qq, vsub(invRi, vbc<V>(p.c_rf)));
+        if (ENERGY) eEl = vmul(qq, vsub(invRi, vbc<V>(k.c_rf)));
     }
     if (Fl::elecRF)
     {
         /* F/r += qq (invR3 - 2k), i.e. W += qq (invR - 2k r2) */
-        W = vfma(qqF, vfma(r2, vbc<V>(-p.two_k_rf), invRi), W);
-        if (ENERGY) eEl = vmul(qq, vadd(invRi, vfma(r2, vbc<V>(0.5f * p.two_k_rf), vbc<V>(-p.c_rf))));
+        W = vfma(qqF, vfma(r2, vbc<V>(-k.two_k_rf), invRi), W);
+        if (ENERGY) eEl = vmul(qq, vadd(invRi, vfma(r2, vbc<V>(k.half_two_k_rf), vbc<V>(-k.c_rf))));
     }
     if (Fl::ewaldAna)
     {
@@ -291,11 +357,11 @@ __device__ __forceinline__ V pair_w(const ParamsDev&    p,
             const V ec = erfc_poly(vmul(r, vbc<V>(k.beta)));
             if (EXCL)
             {
-                eEl = vmul(qq, vfma(invR, vadd(ec, vsub(intBit, vbc<V>(1.0f))), vmul(intBit, vbc<V>(-p.sh_ewald))));
+                eEl = vmul(qq, vfma(invR, vadd(ec, vsub(intBit, vbc<V>(1.0f))), vmul(intBit, vbc<V>(-k.sh_ewald))));
             }
             else
             {
-                eEl = vmul(qq, vfma(invR, ec, vbc<V>(-p.sh_ewald)));
+                eEl = vmul(qq, vfma(invR, ec, vbc<V>(-k.sh_ewald)));
             }
         }
     }
@@ -328,6 +394,59 @@ struct PackedShared
     /* the cjPacked groups of the current chunk of the sci entry, as in the list: cj[4], (imask, excl_ind) x 2 */
     uint4 desc[2 * c_descChunk];
 };
+
+/* 32-bit shared-memory addresses and explicit ld/st.shared: with generic pointers into the shared struct ptxas
+ * re-derives the shared window base (S2UR SR_CgaCtaId, ULEA) and the lane offsets in front of the accesses of every
+ * loop iteration. */
+__device__ __forceinline__ unsigned smem_u32(const void* p)
+{
+    return static_cast<unsigned>(__cvta_generic_to_shared(p));
+}
+__device__ __forceinline__ float4 lds128(const unsigned a)
+{
+    float4 v;
+    asm volatile("ld.shared.v4.f32 {%0, %1, %2, %3}, [%4];" : "=f"(v.x), "=f"(v.y), "=f"(v.z), "=f"(v.w) : "r"(a) : "memory");
+    return v;
+}
+__device__ __forceinline__ uint4 lds128u(const unsigned a)
+{
+    uint4 v;
+    asm volatile("ld.shared.v4.u32 {%0, %1, %2, %3}, [%4];" : "=r"(v.x), "=r"(v.y), "=r"(v.z), "=r"(v.w) : "r"(a) : "memory");
+    return v;
+}
+__device__ __forceinline__ float2 lds64(const unsigned a)
+{
+    float2 v;
+    asm volatile("ld.shared.v2.f32 {%0, %1}, [%2];" : "=f"(v.x), "=f"(v.y) : "r"(a) : "memory");
+    return v;
+}
+__device__ __forceinline__ int lds32i(const unsigned a)
+{
+    int v;
+    asm volatile("ld.shared.u32 %0, [%1];" : "=r"(v) : "r"(a) : "memory");
+    return v;
+}
+__device__ __forceinline__ float lds32f(const unsigned a)
+{
+    float v;
+    asm volatile("ld.shared.f32 %0, [%1];" : "=f"(v) : "r"(a) : "memory");
+    return v;
+}
+__device__ __forceinline__ void sts128(const unsigned a, const float x, const float y, const float z, const float w)
+{
+    asm volatile("st.shared.v4.f32 [%0], {%1, %2, %3, %4};" ::"r"(a), "f"(x), "f"(y), "f"(z), "f"(w) : "memory");
+}
+__device__ __forceinline__ void sts128u(const unsigned a, const uint4 v)
+{
+    asm volatile("st.shared.v4.u32 [%0], {%1, %2, %3, %4};" ::"r"(a), "r"(v.x), "r"(v.y), "r"(v.z), "r"(v.w) : "memory");
+}
+__device__ __forceinline__ void sts32(const unsigned a, const float x)
+{
+    asm volatile("st.shared.f32 [%0], %1;" ::"r"(a), "f"(x) : "memory");
+}
+
+/* byte distance of the two type tables in PackedShared */
+constexpr unsigned c_nbC12FromC6n = sizeof(float) * c_packedMaxTypes * c_packedMaxTypes;
 
 /* j-atoms of one j-cluster as this lane sees them: atoms jl (lo) and jl+4 (hi) */
 struct PackedJ
@@ -363,10 +482,10 @@ __device__ __forceinline__ void lj_params_packed(const PackedShared& sm, const f
     }
     else
     {
-        const int tiN = __float_as_int(pi.x);
-        const int ia = tiN + __float_as_int(lo(j.lj0)), ib = tiN + __float_as_int(hi(j.lj0));
-        c6n          = pk(sm.nbC6n[ia], sm.nbC6n[ib]);
-        c12          = pk(sm.nbC12[ia], sm.nbC12[ib]);
+        /* pi.x: shared-memory address of the i-type's row of nbC6n, j.lj0: 4 * j-type */
+        const unsigned ia = __float_as_uint(pi.x) + __float_as_uint(lo(j.lj0)), ib = __float_as_uint(pi.x) + __float_as_uint(hi(j.lj0));
+        c6n               = pk(lds32f(ia), lds32f(ib));
+        c12               = pk(lds32f(ia + c_nbC12FromC6n), lds32f(ib + c_nbC12FromC6n));
     }
 }
 
@@ -444,9 +563,9 @@ __device__ __forceinline__ void body_single(const ParamsDev&    p,
     }
     else
     {
-        const int ia = __float_as_int(pi.x) + __float_as_int(l0);
-        c6n          = sm.nbC6n[ia];
-        c12          = sm.nbC12[ia];
+        const unsigned ia = __float_as_uint(pi.x) + __float_as_uint(l0);
+        c6n               = lds32f(ia);
+        c12               = lds32f(ia + c_nbC12FromC6n);
     }
     float       invR2, e0, e1;
     const float W = pair_w<float, ELEC, VDW, false, false>(p, k, r2, xi.w * qj, c6n, c12, 0.0f, invR2, e0, e1);
@@ -513,60 +632,20 @@ __device__ __forceinline__ f32x2 body_general(const ParamsDev&    p,
     }
     f32x2 c6n, c12;
     lj_params_packed<ELEC, VDW>(sm, pi, j, c6n, c12);
-    const f32x2 r2c = pk(fmaxf(lo(r2), c_minDistanceSquared), fmaxf(hi(r2), c_minDistanceSquared));
+    /* clamped from both sides: the masking below is a multiplication, so pairs with filler atoms (parked at -1e6 nm)
+     * must stay finite in the Ewald polynomials too; real pairs of a listed cluster pair are a few nm apart */
+    const f32x2 r2c = pk(fminf(fmaxf(lo(r2), c_minDistanceSquared), c_maxDistanceSquared),
+                         fminf(fmaxf(hi(r2), c_minDistanceSquared), c_maxDistanceSquared));
     f32x2       invR2, ePairLJ, ePairEl;
     const f32x2 W = pair_w<f32x2, ELEC, VDW, ENERGY, EXCL>(p, k, r2c, vmul(pk(xi.w, xi.w), j.q), c6n, c12, intBit, invR2, ePairLJ, ePairEl);
-    const f32x2 F = vmul(W, invR2);
+    /* masking by multiplication: every quantity is finite (r2 is clamped), and the energy sums become FMAs */
+    const f32x2 wm = pk(w0 ? 1.0f : 0.0f, w1 ? 1.0f : 0.0f);
     if (ENERGY)
     {
-        eLJacc = vadd(eLJacc, pk(w0 ? lo(ePairLJ) : 0.0f, w1 ? hi(ePairLJ) : 0.0f));
-        eElacc = vadd(eElacc, pk(w0 ? lo(ePairEl) : 0.0f, w1 ? hi(ePairEl) : 0.0f));
+        eLJacc = vfma(ePairLJ, wm, eLJacc);
+        eElacc = vfma(ePairEl, wm, eElacc);
     }
-    return pk(w0 ? lo(F) : 0.0f, w1 ? hi(F) : 0.0f);
-}
-
-/* 32-bit shared-memory addresses and explicit ld/st.shared: with generic pointers into the shared struct ptxas
- * re-derives the shared window base (S2UR SR_CgaCtaId, ULEA) and the lane offsets in front of the accesses of every
- * loop iteration. */
-__device__ __forceinline__ unsigned smem_u32(const void* p)
-{
-    return static_cast<unsigned>(__cvta_generic_to_shared(p));
-}
-__device__ __forceinline__ float4 lds128(const unsigned a)
-{
-    float4 v;
-    asm volatile("ld.shared.v4.f32 {%0, %1, %2, %3}, [%4];" : "=f"(v.x), "=f"(v.y), "=f"(v.z), "=f"(v.w) : "r"(a) : "memory");
-    return v;
-}
-__device__ __forceinline__ uint4 lds128u(const unsigned a)
-{
-    uint4 v;
-    asm volatile("ld.shared.v4.u32 {%0, %1, %2, %3}, [%4];" : "=r"(v.x), "=r"(v.y), "=r"(v.z), "=r"(v.w) : "r"(a) : "memory");
-    return v;
-}
-__device__ __forceinline__ float2 lds64(const unsigned a)
-{
-    float2 v;
-    asm volatile("ld.shared.v2.f32 {%0, %1}, [%2];" : "=f"(v.x), "=f"(v.y) : "r"(a) : "memory");
-    return v;
-}
-__device__ __forceinline__ int lds32i(const unsigned a)
-{
-    int v;
-    asm volatile("ld.shared.u32 %0, [%1];" : "=r"(v) : "r"(a) : "memory");
-    return v;
-}
-__device__ __forceinline__ void sts128(const unsigned a, const float x, const float y, const float z, const float w)
-{
-    asm volatile("st.shared.v4.f32 [%0], {%1, %2, %3, %4};" ::"r"(a), "f"(x), "f"(y), "f"(z), "f"(w) : "memory");
-}
-__device__ __forceinline__ void sts128u(const unsigned a, const uint4 v)
-{
-    asm volatile("st.shared.v4.u32 [%0], {%1, %2, %3, %4};" ::"r"(a), "r"(v.x), "r"(v.y), "r"(v.z), "r"(v.w) : "memory");
-}
-__device__ __forceinline__ void sts32(const unsigned a, const float x)
-{
-    asm volatile("st.shared.f32 [%0], %1;" ::"r"(a), "f"(x) : "memory");
+    return vmul(W, vmul(invR2, wm));
 }
 
 template<int ELEC, int VDW, bool ENERGY>
@@ -586,21 +665,8 @@ __global__ void __launch_bounds__(32, ENERGY ? NBNXM_PACKED_MIN_BLOCKS_ENERGY : 
 
     const float shx = ad.shiftVec[3 * s.shift], shy = ad.shiftVec[3 * s.shift + 1], shz = ad.shiftVec[3 * s.shift + 2];
 
-    /* The constants of the pair bodies come from global memory, not from the kernel parameters: values loaded
-     * from the constant bank are re-loaded by ptxas in every pair body (FFMA2 takes no constant-bank operand),
-     * a dozen instructions per body; loaded values stay in (uniform) registers. */
     PackedConsts k;
-    k.rc2    = __ldg(p.packedConsts + 0);
-    k.rvdw2  = p.rvdw_sq;
-    k.beta   = p.ewald_beta;
-    k.epsfac = p.epsfac;
-    if (Fl::ewaldAna)
-    {
-#pragma unroll
-        for (int n = 0; n < 7; n++) k.num[n] = __ldg(p.packedConsts + 1 + n);
-#pragma unroll
-        for (int n = 1; n < 5; n++) k.den[n] = __ldg(p.packedConsts + 8 + n);
-    }
+    load_packed_consts<ELEC, VDW, ENERGY>(k, p.packedConsts);
 
     /* Lane-dependent shared-memory addresses, passed through a shuffle: ptxas would otherwise re-derive each of
      * them from the thread index (S2R, shifts, masks) in front of every use instead of keeping a register. */
@@ -665,7 +731,7 @@ __global__ void __launch_bounds__(32, ENERGY ? NBNXM_PACKED_MIN_BLOCKS_ENERGY : 
         }
         else
         {
-            sm.lji[lane + 32 * h] = make_float4(__int_as_float(ad.atomType[ai] * ad.numTypes), 0.0f, 0.0f, 0.0f);
+            sm.lji[lane + 32 * h] = make_float4(__uint_as_float(smem_u32(sm.nbC6n + ad.atomType[ai] * ad.numTypes)), 0.0f, 0.0f, 0.0f);
         }
     }
 
@@ -712,7 +778,7 @@ __global__ void __launch_bounds__(32, ENERGY ? NBNXM_PACKED_MIN_BLOCKS_ENERGY : 
                 }
                 else
                 {
-                    pjNext.x = __int_as_float(ad.atomType[aj]);
+                    pjNext.x = __int_as_float(4 * ad.atomType[aj]);
                 }
             }
             /* entry 0 of the exclusion array is all ones (pairlist.h:274-287) */
@@ -808,6 +874,8 @@ __global__ void __launch_bounds__(32, ENERGY ? NBNXM_PACKED_MIN_BLOCKS_ENERGY : 
                 }
                 else
                 {
+                    /* one body type only: packed j-force accumulators */
+                    f32x2 pjx = 0ull, pjy = 0ull, pjz = 0ull;
 #pragma unroll
                     for (int ci = 0; ci < c_superClusterSize; ci++)
                     {
@@ -820,17 +888,20 @@ __global__ void __launch_bounds__(32, ENERGY ? NBNXM_PACKED_MIN_BLOCKS_ENERGY : 
                                                                                    (m1 & (1u << ci)) != 0u, true, true, false,
                                                                                    false, dx, dy, dz, eLJj, eElj);
                             fi[ci][0] = fmaf(lo(F), lo(dx), fmaf(hi(F), hi(dx), fi[ci][0]));
-                            fi[ci][1] = fmaf(lo(F), lo(dy), fmaf(hi(F), hi(dy), fi[ci][1]));
-                            fi[ci][2] = fmaf(lo(F), lo(dz), fmaf(hi(F), hi(dz), fi[ci][2]));
-                            fj.xA     = fmaf(lo(F), lo(dx), fj.xA);
-                            fj.yA     = fmaf(lo(F), lo(dy), fj.yA);
-                            fj.zA     = fmaf(lo(F), lo(dz), fj.zA);
-                            fj.xB     = fmaf(hi(F), hi(dx), fj.xB);
-                            fj.yB     = fmaf(hi(F), hi(dy), fj.yB);
-                            fj.zB     = fmaf(hi(F), hi(dz), fj.zB);
-                        }
+                        fi[ci][1] = fmaf(lo(F), lo(dy), fmaf(hi(F), hi(dy), fi[ci][1]));
+                        fi[ci][2] = fmaf(lo(F), lo(dz), fmaf(hi(F), hi(dz), fi[ci][2]));
+                        pjx       = vfma(F, dx, pjx);
+                        pjy       = vfma(F, dy, pjy);
+                        pjz       = vfma(F, dz, pjz);
                     }
                 }
+                fj.xA = lo(pjx);
+                fj.yA = lo(pjy);
+                fj.zA = lo(pjz);
+                fj.xB = hi(pjx);
+                fj.yB = hi(pjy);
+                fj.zB = hi(pjz);
+            }
                 /* the few cluster pairs with exclusion masks: one loop body for all i-clusters, own accumulators */
                 unsigned mEx = (m0 | m1) & curEx;
                 if (mEx != 0u)
