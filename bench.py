@@ -33,6 +33,28 @@ DEFAULT_WORKLOAD = "water96k_fswitch"
 REF_VDW = {"cut": "cut", "fswitch": "fswitch", "pswitch": "pswitch", "ljpme": "ljpme"}
 
 
+_JSON_FD = None
+
+
+def claim_stdout():
+    """Keep stdout for the ONE JSON line: everything else that libraries write to file descriptor 1 (NCCL prints its
+    version there) goes to stderr."""
+    global _JSON_FD
+    if _JSON_FD is None:
+        sys.stdout.flush()
+        _JSON_FD = os.dup(1)
+        os.dup2(2, 1)
+
+
+def emit(line):
+    data = (json.dumps(line) + "\n").encode()
+    if _JSON_FD is None:
+        sys.stdout.write(data.decode())
+        sys.stdout.flush()
+    else:
+        os.write(_JSON_FD, data)
+
+
 def host_cores():
     try:
         return len(os.sched_getaffinity(0))
@@ -153,7 +175,7 @@ def reference_arm(args):
     cfg = CONFIGS[args.workload]
     res = run_reference_cpu(cfg, cfg["k"], budget_s=max(5.0, min(60.0, 6.0 * args.steps)))
     if res is None:
-        print(json.dumps({"impl": "reference", "unavailable": "oracle/_ref/bench_ref is not built (needs the reference sources)"}))
+        emit(({"impl": "reference", "unavailable": "oracle/_ref/bench_ref is not built (needs the reference sources)"}))
         return
     value = res["useful_pairs"] / res["sec_per_iter"] * 1e-9
     line = {
@@ -167,7 +189,7 @@ def reference_arm(args):
                          "sample": "%d iterations of the full %d-atom system" % (res["iters"], int(res["natoms"]))},
         "e2e": {"value": value, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
     }
-    print(json.dumps(line))
+    emit(line)
 
 
 def main():
@@ -181,6 +203,7 @@ def main():
     ap.add_argument("--no-l2-flush", action="store_true")
     ap.add_argument("--min-sci", type=int, default=0, help="override gpu_min_ci_balanced (list splitting target)")
     args = ap.parse_args()
+    claim_stdout()
     if args.workload is None:
         args.workload = DEFAULT_WORKLOAD if args.gpus == 1 else "water1536k"
     if args.impl == "reference":
@@ -225,14 +248,11 @@ def main():
     flush = None if args.no_l2_flush else torch.empty(256 << 20, dtype=torch.uint8, device="cuda")
 
     def step(i, host_io):
-        if host_io:
-            nb.gpu_copy_xq_to_gpu(nbat, LOCAL)
-        nb.gpu_clear_outputs(computeVirial=energy)
-        nb.gpu_launch_kernel(sw, LOCAL)
-        if cfg["dynamic_pruning"] and i % 2 == 1:     # isDynamicPruningStepGpu, pairlistsets.h:108-115
-            nb.gpu_launch_kernel_pruneonly(LOCAL, num_parts)
+        # the do_force sequence: [H2D xq] -> clear outputs -> force(+energy) kernel -> rolling prune on odd steps
+        # (isDynamicPruningStepGpu, pairlistsets.h:108-115) -> f4 -> f3 [-> D2H f, energies], one foreign call
         sw.useGpuFBufferOps = not host_io
-        nb.gpu_launch_cpyback(nbat, sw, LOCAL)
+        nb.do_force_step(i, sw, have_halo=False, dynamic_pruning=cfg["dynamic_pruning"], num_parts=num_parts,
+                         xq_host=nbat.xq if host_io else None, f_host=nbat.f if host_io else None)
         if host_io:
             return nb.gpu_wait_finish_task(sw, LOCAL)
 
@@ -329,7 +349,7 @@ def main():
             line["cpu_baseline"] = {"value": wl.useful_pairs * frac / r["sec"] * 1e-9, "unit": UNIT, "cores": r["threads"],
                                     "kind": "port", "sample": "%d of %d sci entries" % (r["sample_sci"], r["nsci"])}
     nb.gpu_free()
-    print(json.dumps(line))
+    emit(line)
 
 
 if __name__ == "__main__":

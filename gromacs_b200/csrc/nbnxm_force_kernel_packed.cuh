@@ -587,6 +587,59 @@ __device__ __forceinline__ void body_single(const ParamsDev&    p,
     }
 }
 
+/* One (i-cluster, j-cluster) pair with one half in the list and no exclusion masks, with energies: a scalar pair body
+ * on the j-atom of the half chosen at run time.  Returns the masked F/r and the distance vector. */
+template<int ELEC, int VDW, bool ENERGY>
+__device__ __forceinline__ float body_single_general(const ParamsDev&    p,
+                                                     const PackedConsts& k,
+                                                     const float4        xi,
+                                                     const float2        pi,
+                                                     const PackedJ&      j,
+                                                     const bool          half1,
+                                                     float&              dx,
+                                                     float&              dy,
+                                                     float&              dz,
+                                                     float&              eLJacc,
+                                                     float&              eElacc)
+{
+    using Fl       = Flavor<ELEC, VDW, ENERGY>;
+    const float xj = half1 ? hi(j.x) : lo(j.x), yj = half1 ? hi(j.y) : lo(j.y), zj = half1 ? hi(j.z) : lo(j.z);
+    const float qj = half1 ? hi(j.q) : lo(j.q), l0 = half1 ? hi(j.lj0) : lo(j.lj0), l1 = half1 ? hi(j.lj1) : lo(j.lj1);
+    dx             = xi.x - xj;
+    dy             = xi.y - yj;
+    dz             = xi.z - zj;
+    const float r2 = fmaf(dz, dz, fmaf(dy, dy, dx * dx));
+    float       c6n, c12;
+    if (Fl::ljCombGeom)
+    {
+        c6n = -pi.x * l0;
+        c12 = pi.y * l1;
+    }
+    else if (Fl::ljCombLB)
+    {
+        const float sigma = pi.x + l0, eps = pi.y * l1, sigma2 = sigma * sigma, sigma6 = sigma2 * sigma2 * sigma2;
+        const float c6 = eps * sigma6;
+        c12 = c6 * sigma6;
+        c6n = -c6;
+    }
+    else
+    {
+        const unsigned ia = __float_as_uint(pi.x) + __float_as_uint(l0);
+        c6n               = lds32f(ia);
+        c12               = lds32f(ia + c_nbC12FromC6n);
+    }
+    float       invR2, ePairLJ, ePairEl;
+    const float W = pair_w<float, ELEC, VDW, ENERGY, false>(p, k, fmaxf(r2, c_minDistanceSquared), xi.w * qj, c6n, c12, 1.0f, invR2,
+                                                            ePairLJ, ePairEl);
+    const bool  w = r2 < k.rc2;
+    if (ENERGY)
+    {
+        eLJacc += w ? ePairLJ : 0.0f;
+        eElacc += w ? ePairEl : 0.0f;
+    }
+    return w ? W * invR2 : 0.0f;
+}
+
 /* One (i-cluster, j-cluster) pair, general: list mask bits per half, optional exclusion masks, optional energies.
  * Returns the masked F/r of the two pairs and the distance vectors. */
 template<int ELEC, int VDW, bool ENERGY, bool EXCL>
@@ -857,7 +910,7 @@ __global__ void __launch_bounds__(32, ENERGY ? NBNXM_PACKED_MIN_BLOCKS_ENERGY : 
                         {
                             const float4 xi = lds128(xqiAddr + ci * (16 * c_clusterSize));
                             const float2 pi = lds64(xqiAddr + c_ljiFromXqi + ci * (16 * c_clusterSize));
-                            if (mBoth & (1u << ci))
+                            if (__builtin_expect((mBoth & (1u << ci)) != 0u, 1))
                             {
                                 body_both<ELEC, VDW>(p, k, sm, xi, pi, j, fi[ci], fj);
                             }
@@ -874,34 +927,84 @@ __global__ void __launch_bounds__(32, ENERGY ? NBNXM_PACKED_MIN_BLOCKS_ENERGY : 
                 }
                 else
                 {
-                    /* one body type only: packed j-force accumulators */
-                    f32x2 pjx = 0ull, pjy = 0ull, pjz = 0ull;
+                    /* cluster pairs with both halves in the list: packed bodies, packed j-force accumulators */
+                    const unsigned mBoth = m0 & m1 & mFast;
+                    f32x2          pjx = 0ull, pjy = 0ull, pjz = 0ull;
 #pragma unroll
                     for (int ci = 0; ci < c_superClusterSize; ci++)
                     {
-                        if (mFast & (1u << ci))
+                        if (mBoth & (1u << ci))
                         {
                             const float4 xi = lds128(xqiAddr + ci * (16 * c_clusterSize));
                             const float2 pi = lds64(xqiAddr + c_ljiFromXqi + ci * (16 * c_clusterSize));
                             f32x2        dx, dy, dz;
-                            const f32x2  F = body_general<ELEC, VDW, ENERGY, false>(p, k, sm, xi, pi, j, (m0 & (1u << ci)) != 0u,
-                                                                                   (m1 & (1u << ci)) != 0u, true, true, false,
+                            const f32x2  F = body_general<ELEC, VDW, ENERGY, false>(p, k, sm, xi, pi, j, true, true, true, true, false,
                                                                                    false, dx, dy, dz, eLJj, eElj);
                             fi[ci][0] = fmaf(lo(F), lo(dx), fmaf(hi(F), hi(dx), fi[ci][0]));
-                        fi[ci][1] = fmaf(lo(F), lo(dy), fmaf(hi(F), hi(dy), fi[ci][1]));
-                        fi[ci][2] = fmaf(lo(F), lo(dz), fmaf(hi(F), hi(dz), fi[ci][2]));
-                        pjx       = vfma(F, dx, pjx);
-                        pjy       = vfma(F, dy, pjy);
-                        pjz       = vfma(F, dz, pjz);
+                            fi[ci][1] = fmaf(lo(F), lo(dy), fmaf(hi(F), hi(dy), fi[ci][1]));
+                            fi[ci][2] = fmaf(lo(F), lo(dz), fmaf(hi(F), hi(dz), fi[ci][2]));
+                            pjx       = vfma(F, dx, pjx);
+                            pjy       = vfma(F, dy, pjy);
+                            pjz       = vfma(F, dz, pjz);
+                        }
+                    }
+                    fj.xA = lo(pjx);
+                    fj.yA = lo(pjy);
+                    fj.zA = lo(pjz);
+                    fj.xB = hi(pjx);
+                    fj.yB = hi(pjy);
+                    fj.zB = hi(pjz);
+                    /* cluster pairs with one half only (about one in four after pruning): a scalar body on that half,
+                     * one loop body for all i-clusters (the unrolled form would not fit the instruction cache) */
+                    unsigned mSingle = mFast & ~mBoth;
+                    if (mSingle != 0u)
+                    {
+                        float eLJs = 0.0f, eEls = 0.0f;
+#pragma unroll 1
+                        for (; mSingle != 0u; mSingle &= mSingle - 1u)
+                        {
+                            const int    ci    = __ffs(mSingle) - 1;
+                            const bool   half1 = ((m0 >> ci) & 1u) == 0u;
+                            const float4 xi    = lds128(xqiAddr + ci * (16 * c_clusterSize));
+                            const float2 pi    = lds64(xqiAddr + c_ljiFromXqi + ci * (16 * c_clusterSize));
+                            float        dx, dy, dz;
+                            const float  F = body_single_general<ELEC, VDW, ENERGY>(p, k, xi, pi, j, half1, dx, dy, dz, eLJs, eEls);
+                            const float  fx = F * dx, fy = F * dy, fz = F * dz;
+                            switch (ci)
+                            {
+#define NBNXM_FI_CASE(c) \
+    case c:              \
+        fi[c][0] += fx;  \
+        fi[c][1] += fy;  \
+        fi[c][2] += fz;  \
+        break;
+                                NBNXM_FI_CASE(0)
+                                NBNXM_FI_CASE(1)
+                                NBNXM_FI_CASE(2)
+                                NBNXM_FI_CASE(3)
+                                NBNXM_FI_CASE(4)
+                                NBNXM_FI_CASE(5)
+                                NBNXM_FI_CASE(6)
+                                NBNXM_FI_CASE(7)
+#undef NBNXM_FI_CASE
+                            }
+                            if (half1)
+                            {
+                                fj.xB += fx;
+                                fj.yB += fy;
+                                fj.zB += fz;
+                            }
+                            else
+                            {
+                                fj.xA += fx;
+                                fj.yA += fy;
+                                fj.zA += fz;
+                            }
+                        }
+                        eLJ += eLJs;
+                        eEl += eEls;
                     }
                 }
-                fj.xA = lo(pjx);
-                fj.yA = lo(pjy);
-                fj.zA = lo(pjz);
-                fj.xB = hi(pjx);
-                fj.yB = hi(pjy);
-                fj.zB = hi(pjz);
-            }
                 /* the few cluster pairs with exclusion masks: one loop body for all i-clusters, own accumulators */
                 unsigned mEx = (m0 | m1) & curEx;
                 if (mEx != 0u)

@@ -278,3 +278,38 @@ int nbnxm_b200_halo_get_timings(nbnxm_b200_t* nb, double* x_ms, double* f_ms, in
 }
 
 } // extern "C"
+
+int nbnxm_b200_do_force_step(nbnxm_b200_t* nb, int step, const nbnxm_b200_step_flags_t* fl, const float* xq_host, float* f_host)
+{
+    if (!nb || !fl) return nbb::fail("nbnxm_b200_do_force_step: null argument");
+    const int e = fl->compute_energy, v = fl->compute_virial;
+    if (xq_host && nbnxm_b200_copy_xq_to_gpu(nb, 0, xq_host)) return 1;
+    if (nbnxm_b200_clear_outputs(nb, v)) return 1;
+    if (fl->have_halo)
+    {
+        /* clear + H2D done -> the non-local stream may start */
+        if (nbnxm_b200_insert_nonlocal_dependency(nb, 0)) return 1;
+        if (nbnxm_b200_halo_exchange_x(nb)) return 1;
+    }
+    if (nbnxm_b200_launch_kernel(nb, 0, e, v)) return 1;
+    if (fl->have_halo)
+    {
+        if (nbnxm_b200_launch_kernel(nb, 1, e, v)) return 1;
+        if (nbnxm_b200_halo_exchange_f(nb)) return 1;
+    }
+    if (fl->dynamic_pruning)
+    {
+        if (!fl->have_halo)
+        {
+            if (step % 2 == 1 && nbnxm_b200_launch_kernel_pruneonly(nb, 0, fl->rolling_prune_parts)) return 1;
+        }
+        else if (nbnxm_b200_launch_kernel_pruneonly(nb, step % 2 == 0 ? 0 : 1, fl->rolling_prune_parts))
+        {
+            return 1;
+        }
+    }
+    const int onDevice = (f_host == nullptr);
+    if (fl->have_halo && nbnxm_b200_launch_cpyback(nb, 1, f_host, 0, 0, 1)) return 1;
+    return nbnxm_b200_launch_cpyback(nb, 0, f_host, e, v, onDevice);
+}
+

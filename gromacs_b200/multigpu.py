@@ -147,6 +147,20 @@ class SlabStep:
         nb.gpu_copy_xq_to_gpu(plan.nbat, LOCAL)
 
     def __call__(self, step, host_io=False):
+        """The do_force sequence (sim_util.cpp:1639-2442) through nbnxm_b200_do_force_step, which issues the same
+        gpu_* calls as `sequence()` below in one foreign call."""
+        nb, sw = self.nb, self.sw
+        sw.useGpuFBufferOps = not host_io
+        nb.do_force_step(step, sw, have_halo=self.multi, dynamic_pruning=self.dynamic_pruning, num_parts=self.num_parts,
+                         xq_host=self.plan.nbat.xq if host_io else None, f_host=self.plan.nbat.f if host_io else None)
+        if host_io:
+            if self.multi:
+                nb.gpu_wait_finish_task(sw, NONLOCAL)
+            return nb.gpu_wait_finish_task(sw, LOCAL)
+        return None
+
+    def sequence(self, step, host_io=False):
+        """The same step spelled out call by call, as the reference's do_force issues it (used by the tests)."""
         nb, sw = self.nb, self.sw
         if host_io:
             nb.gpu_copy_xq_to_gpu(self.plan.nbat, LOCAL)
@@ -318,7 +332,8 @@ def bench_multi_gpu(args, rank, world, local_rank):
                          "kernel_us": k_ms * 1e3, "flops_per_pair": wl.flops_per_pair,
                          "note": "local + non-local force launches of the slowest rank; pairs summed over ranks; peak = measured FFMA peak x n_gpus"},
         }
-        print(json.dumps(line), flush=True)
+        from bench import emit
+        emit(line)
     halo_free = getattr(lib, "nbnxm_b200_halo_free")
     halo_free(nb._h)
     nb.gpu_free()

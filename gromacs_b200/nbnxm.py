@@ -24,7 +24,7 @@ VDW_TYPES = {"Cut": 0, "CutCombGeom": 1, "CutCombLB": 2, "FSwitch": 3, "PSwitch"
 
 # every symbol include/nbnxm_b200.h declares
 EXPORTED_SYMBOLS = [
-    "nbnxm_b200_last_error", "nbnxm_b200_init", "nbnxm_b200_free", "nbnxm_b200_update_params",
+    "nbnxm_b200_last_error", "nbnxm_b200_init", "nbnxm_b200_free", "nbnxm_b200_update_params", "nbnxm_b200_do_force_step",
     "nbnxm_b200_init_pairlist", "nbnxm_b200_init_atomdata", "nbnxm_b200_upload_shiftvec",
     "nbnxm_b200_copy_xq_to_gpu", "nbnxm_b200_init_x_to_nbat_x", "nbnxm_b200_x_to_nbat_x",
     "nbnxm_b200_launch_kernel", "nbnxm_b200_launch_kernel_pruneonly", "nbnxm_b200_launch_cpyback",
@@ -54,6 +54,12 @@ class Params(C.Structure):
             "rcoulomb_sq", "rvdw_sq", "rvdw_switch", "rlist_outer_sq", "rlist_inner_sq",
             "disp_c2", "disp_c3", "disp_cpot", "rep_c2", "rep_c3", "rep_cpot",
             "sw_c3", "sw_c4", "sw_c5", "coulomb_tab_scale")] + [("use_dynamic_pruning", C.c_int)]
+
+
+class StepFlags(C.Structure):
+    """nbnxm_b200_step_flags_t"""
+    _fields_ = [("compute_energy", C.c_int), ("compute_virial", C.c_int), ("have_halo", C.c_int),
+                ("dynamic_pruning", C.c_int), ("rolling_prune_parts", C.c_int)]
 
 
 class Timings(C.Structure):
@@ -259,6 +265,16 @@ class NbnxmGpu:
         if done.value and shiftForces is not None:
             shiftForces += fs
         return bool(done.value), e_lj.value, e_el.value
+
+    def do_force_step(self, step, stepWork: StepWorkload, have_halo=False, dynamic_pruning=False, num_parts=1,
+                      xq_host=None, f_host=None):
+        """The nonbonded part of one do_force step in one foreign call (nbnxm_b200_do_force_step): the same sequence
+        as the individual gpu_* calls, for callers that pay per call."""
+        fl = StepFlags(int(stepWork.computeEnergy), int(stepWork.computeVirial), int(have_halo), int(dynamic_pruning),
+                       int(num_parts))
+        xq = _ptr(xq_host, C.c_float) if xq_host is not None else None
+        f = _ptr(f_host, C.c_float) if f_host is not None else None
+        self._check(self._lib.nbnxm_b200_do_force_step(self._h, C.c_int(step), C.byref(fl), xq, f))
 
     def gpu_clear_outputs(self, computeVirial=True):
         self._check(self._lib.nbnxm_b200_clear_outputs(self._h, C.c_int(int(computeVirial))))

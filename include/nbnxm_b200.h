@@ -226,6 +226,22 @@ int nbnxm_b200_halo_exchange_f(nbnxm_b200_t* nb);
 int nbnxm_b200_halo_set_timing(nbnxm_b200_t* nb, int enable);
 int nbnxm_b200_halo_get_timings(nbnxm_b200_t* nb, double* x_ms, double* f_ms, int reset);
 
+/* ---- the nonbonded part of one do_force step in one call (src/gromacs/mdlib/sim_util.cpp:1639-2442): what the
+ * reference's do_force does around the two kernels, in its order: [copy xq H2D] -> clear outputs -> non-local
+ * dependency + halo coordinates -> local kernel -> non-local kernel + halo forces -> rolling prune on its schedule
+ * (local on even steps, non-local on odd ones with a halo; odd steps without, prunekerneldispatch.cpp:123-128) ->
+ * force copy-back of both localities.  Nothing here is new functionality: it saves a caller that is not compiled
+ * code (the Python bench and tests) a dozen foreign-function calls per step.
+ * xq_host / f_host may be NULL (coordinates resident, forces left on the device). ---- */
+typedef struct nbnxm_b200_step_flags
+{
+    int compute_energy, compute_virial;
+    int have_halo;              /* 1: the handle was created with local_and_nonlocal and halo ranges are set */
+    int dynamic_pruning;        /* 1: launch the rolling prune on its schedule */
+    int rolling_prune_parts;
+} nbnxm_b200_step_flags_t;
+int nbnxm_b200_do_force_step(nbnxm_b200_t* nb, int step, const nbnxm_b200_step_flags_t* flags, const float* xq_host, float* f_host);
+
 #ifdef __cplusplus
 }
 #endif
