@@ -202,6 +202,8 @@ def main():
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-l2-flush", action="store_true")
     ap.add_argument("--min-sci", type=int, default=0, help="override gpu_min_ci_balanced (list splitting target)")
+    ap.add_argument("--halo", default="peer", choices=["peer", "nccl"],
+                    help="N > 1: peer-memory halo over NVLink (no transport calls) or ncclSend/ncclRecv")
     args = ap.parse_args()
     claim_stdout()
     if args.workload is None:

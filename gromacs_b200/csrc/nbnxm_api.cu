@@ -539,7 +539,7 @@ int nbnxm_b200_launch_kernel_pruneonly(nbnxm_b200_t* nb, int iloc, int num_parts
         return 0;
     }
     beginRegion(nb, pl.haveFreshList ? 4 : 5, st);
-    launch_prune(pl.haveFreshList, nb->ad(), nb->pd, pl.dev(false), num_parts, st);
+    launch_prune(pl.haveFreshList, nb->ad(iloc), nb->pd, pl.dev(false), num_parts, st);
     nb->launches++;
     if (pl.haveFreshList)
     {
@@ -597,7 +597,7 @@ int nbnxm_b200_launch_kernel(nbnxm_b200_t* nb, int iloc, int compute_energy, int
                                 cudaSharedmemCarveoutMaxShared));
     }
     /* one 32-thread CTA per sci entry */
-    kernel<<<pl.numSci, 32, 0, st>>>(nb->ad(), nb->pd, pl.dev(false), compute_virial != 0);
+    kernel<<<pl.numSci, 32, 0, st>>>(nb->ad(iloc), nb->pd, pl.dev(false), compute_virial != 0);
     nb->launches++;
     if (doPrune)
     {

@@ -37,6 +37,12 @@ struct AtomDataDev
 {
     const float4* xq;
     float4*       f4;
+    /* j-atoms: the same arrays, except in the non-local launch of the peer-memory halo path, where the j-atoms of the
+     * list are the +x neighbour's home atoms, read from and reduced into its memory over NVLink (nbnxm_halo.cu);
+     * offset so that the list's j-atom indices apply */
+    const float4* xqJ;
+    float4*       f4J;
+
     const int*    atomType;
     const float2* ljComb;
     const float*  shiftVec;
@@ -100,6 +106,21 @@ __device__ __forceinline__ void red_add_v4_if(const bool doIt, float4* addr, flo
             "}" ::"l"(addr),
             "f"(x), "f"(y), "f"(z), "f"(0.0f), "r"(static_cast<int>(doIt))
             : "memory");
+}
+
+/* Spin until the 32-bit flag (written by another GPU with a system-scope release) reaches `value`; gives up after about
+ * two seconds and raises *errorFlag instead of hanging the device. */
+__device__ __forceinline__ void wait_flag_geq(const int* flag, const int value, int* errorFlag)
+{
+    const long long t0 = clock64();
+    int             v;
+    do
+    {
+        asm volatile("ld.acquire.sys.global.s32 %0, [%1];" : "=r"(v) : "l"(flag) : "memory");
+        if (v >= value) return;
+        __nanosleep(200);
+    } while (clock64() - t0 < 4000000000ll);
+    if (errorFlag) atomicExch(errorFlag, 1);
 }
 
 __device__ __forceinline__ float norm2_fma(float dx, float dy, float dz)

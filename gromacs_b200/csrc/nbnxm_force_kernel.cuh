@@ -373,7 +373,6 @@ __global__ void __launch_bounds__(32, (ENERGY || PRUNE) ? c_forceMinBlocksPerSM 
     __shared__ __align__(128) float4 sm_fj[32 * c_clusterSize];
 
     const float shx = ad.shiftVec[3 * s.shift], shy = ad.shiftVec[3 * s.shift + 1], shz = ad.shiftVec[3 * s.shift + 2];
-
     PairConsts k;
     k.rc2         = p.rcoulomb_sq;
     k.rcoulomb    = sqrtf(p.rcoulomb_sq);
@@ -462,7 +461,7 @@ __global__ void __launch_bounds__(32, (ENERGY || PRUNE) ? c_forceMinBlocksPerSM 
         if ((mev.x | mev.z) & (0xffu << (8 * jl)))
         {
             const int aj = static_cast<int>(select4(cjv.x, cjv.y, cjv.z, cjv.w, jl)) * c_clusterSize + il;
-            xj           = ad.xq[aj];
+            xj           = ad.xqJ[aj];
             if (Fl::ljComb)
             {
                 const float2 c = ad.ljComb[aj];
@@ -591,7 +590,7 @@ __global__ void __launch_bounds__(32, (ENERGY || PRUNE) ? c_forceMinBlocksPerSM 
                     sy += v.y;
                     sz += v.z;
                 }
-                red_add_v4(ad.f4 + ajOwn, sx, sy, sz);
+                red_add_v4(ad.f4J + ajOwn, sx, sy, sz);
             }
         }
         if (PRUNE)

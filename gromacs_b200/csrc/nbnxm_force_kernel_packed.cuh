@@ -824,7 +824,7 @@ __global__ void __launch_bounds__(32, ENERGY ? NBNXM_PACKED_MIN_BLOCKS_ENERGY : 
             if (fetchedNext)
             {
                 const int aj = lds32i(descAddr + 32 * g + 4u * NBNXM_JL_FROM_ADDR) * c_clusterSize + NBNXM_IL_FROM_ADDR;
-                xjNext       = ad.xq[aj];
+                xjNext       = ad.xqJ[aj];
                 if (Fl::ljComb)
                 {
                     pjNext = ad.ljComb[aj];
@@ -1089,7 +1089,7 @@ __global__ void __launch_bounds__(32, ENERGY ? NBNXM_PACKED_MIN_BLOCKS_ENERGY : 
                     }
                     /* the atom this lane fetched for the group */
                     const int ajOwn = lds32i(descAddr + 32 * g + 4u * NBNXM_JL_FROM_ADDR) * c_clusterSize + NBNXM_IL_FROM_ADDR;
-                    red_add_v4(ad.f4 + ajOwn, -sx, -sy, -sz);
+                    red_add_v4(ad.f4J + ajOwn, -sx, -sy, -sz);
                 }
             }
         }

@@ -101,7 +101,39 @@ struct HaloState
     cudaEvent_t    ev[4]  = { nullptr, nullptr, nullptr, nullptr };
     double         xMs = 0, fMs = 0;
     int            xCount = 0, fCount = 0;
+
+    /* Peer-memory path: no transport calls at all.  The non-local kernel reads the +x neighbour's home coordinates
+     * and reduces the forces on them straight into the neighbour's accumulator over NVLink (the arrays are mapped
+     * with CUDA IPC); ranks synchronise through step counters in device memory:
+     *   flags[0] of a rank = last step for which its coordinates are in place and its accumulator is cleared,
+     *   flags[1] of a rank = last step for which its -x neighbour has finished adding forces to it. */
+    bool        peerEnabled = false;
+    int         peerStep    = 0;
+    DevBuf<int> flags;               /* ours: [0] ready, [1] forces from -x neighbour done, [2] error */
+    float4*     upXq    = nullptr;   /* +x neighbour's xq / f4 / flags, mapped */
+    float4*     upF4    = nullptr;
+    int*        upFlags = nullptr;
 };
+
+/* what a rank publishes to its -x neighbour */
+struct PeerBlob
+{
+    cudaIpcMemHandle_t xq, f4, flags;
+    int                homeFirst; /* first atom of the range the neighbour imports as its halo */
+    int                natoms;
+};
+
+__global__ void flag_set_kernel(int* flag, int value)
+{
+    /* everything this stream did before (kernels writing our or the neighbour's memory) is ordered before the flag */
+    __threadfence_system();
+    asm volatile("st.release.sys.global.s32 [%0], %1;" ::"l"(flag), "r"(value) : "memory");
+}
+
+__global__ void flag_wait_kernel(const int* flag, int value, int* errorFlag)
+{
+    wait_flag_geq(flag, value, errorFlag);
+}
 
 __global__ void __launch_bounds__(256) halo_add_f_kernel(float4* __restrict__ f4, const float4* __restrict__ in, int n)
 {
@@ -157,9 +189,11 @@ int nbnxm_b200_halo_free(nbnxm_b200_t* nb)
     if (!nb || !nb->halo) return 0;
     cudaSetDevice(nb->device);
     cudaDeviceSynchronize();
+    nbnxm_b200_peer_close(nb);
     HaloState* h = nb->halo;
     if (h->comm) g_nccl.CommDestroy(h->comm);
     h->fRecv.release();
+    h->flags.release();
     for (cudaEvent_t e : h->ev)
         if (e) cudaEventDestroy(e);
     delete h;
@@ -279,23 +313,143 @@ int nbnxm_b200_halo_get_timings(nbnxm_b200_t* nb, double* x_ms, double* f_ms, in
 
 } // extern "C"
 
+/* ---- peer-memory halo path ---- */
+int nbnxm_b200_peer_blob_size(void) { return int(sizeof(PeerBlob)); }
+
+int nbnxm_b200_peer_export(nbnxm_b200_t* nb, unsigned char* blob, int nbytes)
+{
+    if (!nb || !nb->halo || !blob || nbytes < int(sizeof(PeerBlob))) return fail("nbnxm_b200_peer_export: bad argument");
+    if (!nb->xq.p || !nb->f4.p) return fail("nbnxm_b200_peer_export: call after gpu_init_atomdata");
+    HaloState* h = nb->halo;
+    CU(cudaSetDevice(nb->device));
+    if (!h->flags.p)
+    {
+        CU(h->flags.reserve(8));
+        CU(cudaMemset(h->flags.p, 0, sizeof(int) * 8));
+    }
+    PeerBlob b;
+    memset(&b, 0, sizeof(b));
+    CU(cudaIpcGetMemHandle(&b.xq, nb->xq.p));
+    CU(cudaIpcGetMemHandle(&b.f4, nb->f4.p));
+    CU(cudaIpcGetMemHandle(&b.flags, h->flags.p));
+    b.homeFirst = h->sendFirst;
+    b.natoms    = nb->natoms;
+    memcpy(blob, &b, sizeof(b));
+    return 0;
+}
+
+/* maps the +x neighbour's arrays; collective in the sense that every rank must have exported first */
+int nbnxm_b200_peer_import(nbnxm_b200_t* nb, const unsigned char* up_blob, int nbytes)
+{
+    if (!nb || !nb->halo || !up_blob || nbytes < int(sizeof(PeerBlob))) return fail("nbnxm_b200_peer_import: bad argument");
+    HaloState* h = nb->halo;
+    if (h->nranks < 2) return fail("nbnxm_b200_peer_import: needs at least two ranks");
+    if (!h->flags.p) return fail("nbnxm_b200_peer_import: export first");
+    CU(cudaSetDevice(nb->device));
+    PeerBlob b;
+    memcpy(&b, up_blob, sizeof(b));
+    void *xq = nullptr, *f4 = nullptr, *fl = nullptr;
+    CU(cudaIpcOpenMemHandle(&xq, b.xq, cudaIpcMemLazyEnablePeerAccess));
+    CU(cudaIpcOpenMemHandle(&f4, b.f4, cudaIpcMemLazyEnablePeerAccess));
+    CU(cudaIpcOpenMemHandle(&fl, b.flags, cudaIpcMemLazyEnablePeerAccess));
+    h->upXq    = static_cast<float4*>(xq);
+    h->upF4    = static_cast<float4*>(f4);
+    h->upFlags = static_cast<int*>(fl);
+    /* our halo atoms [recvFirst, recvFirst + recvCount) are the neighbour's [homeFirst, ...) */
+    nb->peerXqJ    = h->upXq + b.homeFirst - h->recvFirst;
+    nb->peerF4J    = h->upF4 + b.homeFirst - h->recvFirst;
+    h->peerEnabled = true;
+    h->peerStep    = 0;
+    return 0;
+}
+
+int nbnxm_b200_peer_close(nbnxm_b200_t* nb)
+{
+    if (!nb || !nb->halo) return 0;
+    HaloState* h = nb->halo;
+    cudaSetDevice(nb->device);
+    cudaDeviceSynchronize();
+    if (h->upXq) cudaIpcCloseMemHandle(h->upXq);
+    if (h->upF4) cudaIpcCloseMemHandle(h->upF4);
+    if (h->upFlags) cudaIpcCloseMemHandle(h->upFlags);
+    h->upXq = h->upF4 = nullptr;
+    h->upFlags     = nullptr;
+    nb->peerXqJ    = nullptr;
+    nb->peerF4J    = nullptr;
+    h->peerEnabled = false;
+    return 0;
+}
+
+/* 0 = fine, 1 = a wait on a neighbour's step counter timed out */
+int nbnxm_b200_peer_error(nbnxm_b200_t* nb, int* error)
+{
+    if (!nb || !nb->halo || !error) return fail("nbnxm_b200_peer_error: bad argument");
+    *error = 0;
+    if (nb->halo->flags.p)
+    {
+        CU(cudaSetDevice(nb->device));
+        CU(cudaMemcpy(error, nb->halo->flags.p + 2, sizeof(int), cudaMemcpyDeviceToHost));
+    }
+    return 0;
+}
+
+/* The do_force sequence with the peer-memory halo: no coordinate or force transport.
+ *   local stream   : [H2D xq] clear -> flags[0] = step -> local kernel -> [local rolling prune] -> wait own non-local
+ *                    stream, wait flags[1] >= step -> copy-back
+ *   non-local strm : wait (clear done), wait +x neighbour's flags[0] >= step -> non-local kernel (j-atoms in the
+ *                    neighbour's memory) -> [non-local rolling prune] -> neighbour's flags[1] = step */
+static int peerForceStep(nbnxm_b200_t* nb, int step, const nbnxm_b200_step_flags_t* fl, const float* xq_host, float* f_host)
+{
+    HaloState*   h  = nb->halo;
+    const int    e = fl->compute_energy, v = fl->compute_virial;
+    cudaStream_t sl = nb->stream[0], sn = nb->stream[1];
+    const int    n  = ++h->peerStep;
+    CU(cudaSetDevice(nb->device));
+    if (xq_host && nbnxm_b200_copy_xq_to_gpu(nb, 0, xq_host)) return 1;
+    if (nbnxm_b200_clear_outputs(nb, v)) return 1;
+    flag_set_kernel<<<1, 1, 0, sl>>>(h->flags.p + 0, n);
+    if (nbnxm_b200_insert_nonlocal_dependency(nb, 0)) return 1;
+    if (nbnxm_b200_insert_nonlocal_dependency(nb, 1)) return 1;
+    flag_wait_kernel<<<1, 1, 0, sn>>>(h->upFlags + 0, n, h->flags.p + 2);
+    nb->launches += 2;
+    if (nbnxm_b200_launch_kernel(nb, 0, e, v)) return 1;
+    if (nbnxm_b200_launch_kernel(nb, 1, e, v)) return 1;
+    if (fl->dynamic_pruning)
+    {
+        if (nbnxm_b200_launch_kernel_pruneonly(nb, step % 2 == 0 ? 0 : 1, fl->rolling_prune_parts)) return 1;
+    }
+    /* the neighbour may use its forces (and overwrite its coordinates) once our non-local work on them is done */
+    flag_set_kernel<<<1, 1, 0, sn>>>(h->upFlags + 1, n);
+    nb->launches++;
+    if (nbnxm_b200_launch_cpyback(nb, 1, f_host, 0, 0, 1)) return 1;
+    /* the -x neighbour's non-local kernel adds to our accumulator: wait for it before reading the forces */
+    flag_wait_kernel<<<1, 1, 0, sl>>>(h->flags.p + 1, n, h->flags.p + 2);
+    nb->launches++;
+    return nbnxm_b200_launch_cpyback(nb, 0, f_host, e, v, f_host == nullptr);
+}
+
 int nbnxm_b200_do_force_step(nbnxm_b200_t* nb, int step, const nbnxm_b200_step_flags_t* fl, const float* xq_host, float* f_host)
 {
     if (!nb || !fl) return nbb::fail("nbnxm_b200_do_force_step: null argument");
     const int e = fl->compute_energy, v = fl->compute_virial;
+    if (fl->have_halo == 3)
+    {
+        if (!nb->halo || !nb->halo->peerEnabled) return nbb::fail("nbnxm_b200_do_force_step: peer-memory halo not set up");
+        return peerForceStep(nb, step, fl, xq_host, f_host);
+    }
     if (xq_host && nbnxm_b200_copy_xq_to_gpu(nb, 0, xq_host)) return 1;
     if (nbnxm_b200_clear_outputs(nb, v)) return 1;
     if (fl->have_halo)
     {
         /* clear + H2D done -> the non-local stream may start */
         if (nbnxm_b200_insert_nonlocal_dependency(nb, 0)) return 1;
-        if (nbnxm_b200_halo_exchange_x(nb)) return 1;
+        if (fl->have_halo == 1 && nbnxm_b200_halo_exchange_x(nb)) return 1;
     }
     if (nbnxm_b200_launch_kernel(nb, 0, e, v)) return 1;
     if (fl->have_halo)
     {
         if (nbnxm_b200_launch_kernel(nb, 1, e, v)) return 1;
-        if (nbnxm_b200_halo_exchange_f(nb)) return 1;
+        if (fl->have_halo == 1 && nbnxm_b200_halo_exchange_f(nb)) return 1;
     }
     if (fl->dynamic_pruning)
     {

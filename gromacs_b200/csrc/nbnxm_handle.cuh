@@ -157,12 +157,20 @@ struct nbnxm_b200
     nbb::HaloState* halo = nullptr;
     std::set<const void*> carveoutSet; /* kernels whose shared-memory carve-out preference was set */
 
+    /* peer-memory halo path: j-atom arrays of the non-local launch (null: our own arrays) */
+    const float4* peerXqJ   = nullptr;
+    float4*       peerF4J   = nullptr;
+
     nbb::ParamsDev   pd{};
-    nbb::AtomDataDev ad() const
+    nbb::AtomDataDev ad(int iloc = 0) const
     {
         nbb::AtomDataDev a;
         a.xq       = xq.p;
         a.f4       = f4.p;
+        const bool peer = (iloc == 1 && peerXqJ != nullptr);
+        a.xqJ       = peer ? peerXqJ : xq.p;
+        a.f4J       = peer ? peerF4J : f4.p;
+
         a.atomType = atomType.p;
         a.ljComb   = ljComb.p;
         a.shiftVec = shiftVec.p;

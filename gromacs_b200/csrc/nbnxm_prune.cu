@@ -90,7 +90,7 @@ __global__ void __launch_bounds__(32) nbnxm_prune_kernel(const AtomDataDev ad, c
         if (checkAny & (0xffu << (8 * jl)))
         {
             const int cj = static_cast<int>(jl == 0 ? cjv.x : (jl == 1 ? cjv.y : (jl == 2 ? cjv.z : cjv.w)));
-            xj           = ad.xq[cj * c_clusterSize + il];
+            xj           = ad.xqJ[cj * c_clusterSize + il];
         }
     };
 

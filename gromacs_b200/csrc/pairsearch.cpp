@@ -95,7 +95,12 @@ extern "C" {
 
 int nbnxm_b200_grid_create(nbnxm_b200_grid_t** out, const float* box, int natoms, const float* x, int nthreads)
 {
-    if (!out || !box || !x || natoms <= 0) return fail("grid_create: bad argument");
+    return nbnxm_b200_grid_create_slabs(out, box, natoms, x, nthreads, 1);
+}
+
+int nbnxm_b200_grid_create_slabs(nbnxm_b200_grid_t** out, const float* box, int natoms, const float* x, int nthreads, int nslabs)
+{
+    if (!out || !box || !x || natoms <= 0 || nslabs < 1) return fail("grid_create: bad argument");
     if (nthreads < 1) nthreads = 1;
     nbnxm_b200_grid* g = new nbnxm_b200_grid();
     for (int d = 0; d < 3; d++) g->box[d] = box[d];
@@ -105,6 +110,12 @@ int nbnxm_b200_grid_create(nbnxm_b200_grid_t** out, const float* box, int natoms
     const double density = natoms / (double(box[0]) * box[1] * box[2]);
     const double tlen    = std::cbrt(c_cl / density);
     g->ncx               = std::max(1, int(box[0] / (2 * tlen)));
+    if (nslabs > 1)
+    {
+        /* x-slab decomposition over nslabs GPUs: a whole number of columns per slab, so that the slabs hold equal
+         * numbers of atoms (the reference grids every domain separately) */
+        g->ncx = std::max(nslabs, (g->ncx / nslabs) * nslabs);
+    }
     g->ncy               = std::max(1, int(box[1] / (2 * tlen)));
     g->cellSize[0]       = box[0] / g->ncx;
     g->cellSize[1]       = box[1] / g->ncy;

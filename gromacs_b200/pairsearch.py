@@ -9,7 +9,7 @@ import numpy as np
 from .nbnxm import AtomData, NbnxmError, PairlistGpu, load_library
 
 SEARCH_SYMBOLS = [
-    "nbnxm_b200_grid_create", "nbnxm_b200_grid_free", "nbnxm_b200_grid_info", "nbnxm_b200_grid_get_order",
+    "nbnxm_b200_grid_create", "nbnxm_b200_grid_create_slabs", "nbnxm_b200_grid_free", "nbnxm_b200_grid_info", "nbnxm_b200_grid_get_order",
     "nbnxm_b200_grid_fill_atomdata", "nbnxm_b200_pairlist_build", "nbnxm_b200_pairlist_sizes",
     "nbnxm_b200_pairlist_copy",
 ]
@@ -22,16 +22,16 @@ def _p(a, ct):
 class Grid:
     """One pair-search grid over a rectangular periodic box (Grid / GridSet of the reference)."""
 
-    def __init__(self, box, x, nthreads=None):
+    def __init__(self, box, x, nthreads=None, nslabs=1):
         self._lib = load_library()
         self._g = C.c_void_p()
         self.nthreads = nthreads or min(os.cpu_count() or 1, 64)
         self.box = np.ascontiguousarray(box, np.float32)
         x = np.ascontiguousarray(x, np.float32)
         self.natoms = x.shape[0]
-        if self._lib.nbnxm_b200_grid_create(C.byref(self._g), _p(self.box, C.c_float), C.c_int(self.natoms),
-                                            _p(x, C.c_float), C.c_int(self.nthreads)):
-            raise NbnxmError("nbnxm_b200_grid_create failed")
+        if self._lib.nbnxm_b200_grid_create_slabs(C.byref(self._g), _p(self.box, C.c_float), C.c_int(self.natoms),
+                                                  _p(x, C.c_float), C.c_int(self.nthreads), C.c_int(nslabs)):
+            raise NbnxmError("nbnxm_b200_grid_create_slabs failed")
         n, nb, ncx, ncy = C.c_int(), C.c_int(), C.c_int(), C.c_int()
         self._lib.nbnxm_b200_grid_info(self._g, C.byref(n), C.byref(nb), C.byref(ncx), C.byref(ncy))
         self.natoms_nbat, self.nbins, self.ncx, self.ncy = n.value, nb.value, ncx.value, ncy.value

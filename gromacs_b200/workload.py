@@ -71,12 +71,12 @@ def make_interaction_params(vdw, rc, rlist_outer, rlist_inner, dynamic_pruning, 
     raise ValueError(vdw)
 
 
-def make_workload(name, nthreads=None, energy=None) -> Workload:
+def make_workload(name, nthreads=None, energy=None, nslabs=1) -> Workload:
     cfg = dict(CONFIGS[name])
     if energy is not None:
         cfg["energy"] = energy
     box = S.benchmark_system(cfg["k"])
-    grid = Grid(box.box, box.x, nthreads=nthreads)
+    grid = Grid(box.box, box.x, nthreads=nthreads, nslabs=nslabs)
     nbfp, nt = S.spce_nbfp()
     comb = S.geometric_comb_params(nbfp, nt)
     nbat = grid.atomdata(box.x, box.q, box.type, nbfp, nt, nbfp_comb=comb, lj_comb_per_type=comb)

@@ -233,10 +233,28 @@ int nbnxm_b200_halo_get_timings(nbnxm_b200_t* nb, double* x_ms, double* f_ms, in
  * force copy-back of both localities.  Nothing here is new functionality: it saves a caller that is not compiled
  * code (the Python bench and tests) a dozen foreign-function calls per step.
  * xq_host / f_host may be NULL (coordinates resident, forces left on the device). ---- */
+/* ---- peer-memory halo: the B200 / NVSwitch way of the same exchange.  Instead of sending halo coordinates and
+ * returning halo forces, every rank maps its +x neighbour's xq and force accumulator (CUDA IPC over NVLink); the
+ * non-local kernel reads the neighbour's coordinates and reduces j-forces into the neighbour's accumulator directly
+ * (red.global.add over NVLink), and ranks synchronise through step counters in device memory.  No transport call,
+ * no pack / add kernels, no halo copy.  Replaces communicateHaloCoordinates + communicateHaloForces
+ * (gpuhaloexchange_impl_gpu.cpp:286-470) when all ranks sit on one NVLink domain.
+ * Set-up (after gpu_init_atomdata and halo_set_ranges at every search step): every rank exports a blob, the caller
+ * hands each rank the blob of its +x neighbour (e.g. all_gather), then peer_import.  Use have_halo = 3 in
+ * nbnxm_b200_do_force_step. ---- */
+int nbnxm_b200_peer_blob_size(void);
+int nbnxm_b200_peer_export(nbnxm_b200_t* nb, unsigned char* blob, int nbytes);
+int nbnxm_b200_peer_import(nbnxm_b200_t* nb, const unsigned char* up_blob, int nbytes);
+int nbnxm_b200_peer_close(nbnxm_b200_t* nb);
+int nbnxm_b200_peer_error(nbnxm_b200_t* nb, int* error);
+
 typedef struct nbnxm_b200_step_flags
 {
     int compute_energy, compute_virial;
-    int have_halo;              /* 1: the handle was created with local_and_nonlocal and halo ranges are set */
+    int have_halo;              /* 1: the handle was created with local_and_nonlocal and halo ranges are set;
+                                   3: peer-memory halo (nbnxm_b200_peer_import done);
+                                   2: local and non-local lists but no transport (one slab of a decomposition run alone,
+                                   halo coordinates resident: a profiling aid) */
     int dynamic_pruning;        /* 1: launch the rolling prune on its schedule */
     int rolling_prune_parts;
 } nbnxm_b200_step_flags_t;

@@ -26,6 +26,8 @@ typedef struct nbnxm_b200_grid nbnxm_b200_grid_t;
 /* nonbonded_verlet_t::putAtomsOnGrid (src/gromacs/nbnxm/nbnxm.cpp:78): bins natoms atoms (x: natoms x 3,
  * inside the rectangular box [0, box)) and sorts them into nbat order. */
 int nbnxm_b200_grid_create(nbnxm_b200_grid_t** grid, const float* box, int natoms, const float* x, int nthreads);
+/* the same with the number of x columns rounded down to a multiple of nslabs (x-slab decomposition over nslabs GPUs) */
+int nbnxm_b200_grid_create_slabs(nbnxm_b200_grid_t** grid, const float* box, int natoms, const float* x, int nthreads, int nslabs);
 int nbnxm_b200_grid_free(nbnxm_b200_grid_t* grid);
 /* number of nbat slots (atoms padded to whole 64-atom bins) and bins, grid columns along x and y */
 int nbnxm_b200_grid_info(const nbnxm_b200_grid_t* grid, int* natoms_nbat, int* nbins, int* ncx, int* ncy);

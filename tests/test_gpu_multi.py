@@ -1,5 +1,5 @@
-"""Multi-GPU parity (needs >= 2 GPUs on the box; skipped otherwise): the x-slab step with the NCCL halo exchange
-of the library, one process per GPU, against the oracle on the whole system."""
+"""Multi-GPU parity (needs >= 2 GPUs on the box; skipped otherwise): the x-slab step with the library's NCCL halo
+exchange and with its peer-memory halo (no transport), one process per GPU, against the oracle on the whole system."""
 import os
 import socket
 
@@ -17,7 +17,7 @@ def _free_port():
     return port
 
 
-def _worker(rank, world, port, out):
+def _worker(rank, world, port, out, peer):
     import torch
     import torch.distributed as dist
     os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port))
@@ -41,12 +41,22 @@ def _worker(rank, world, port, out):
         plan.nbat.xq[plan.recv_first:] = 0
         step = SlabStep(nb, halo, plan, energy=True, dynamic_pruning=False)
         step.search_step()
+        if peer:
+            # no transport: the non-local kernel reads the neighbour's coordinates / adds to its forces over NVLink
+            def gather(b):
+                parts = [None] * world
+                dist.all_gather_object(parts, b)
+                return parts
+            halo.enable_peer_memory(gather, rank, world)
+            dist.barrier()
         results = []
         for i in range(3):
             e_lj, e_el = step(i, host_io=True)
             results.append((plan.nbat.f[:plan.nbat.numLocalAtoms].astype(np.float64).copy(), e_lj, e_el))
+        assert halo.peer_error() == 0
         parts = [None] * world
         dist.all_gather_object(parts, (plan.home_slice.start, results))
+        dist.barrier()
         lib.nbnxm_b200_halo_free(nb._h)
         nb.gpu_free()
         if rank == 0:
@@ -55,8 +65,9 @@ def _worker(rank, world, port, out):
         dist.destroy_process_group()
 
 
+@pytest.mark.parametrize("peer", [False, True], ids=["nccl", "peer"])
 @pytest.mark.parametrize("world", [2, 4])
-def test_x_slab_step_matches_oracle(oracle, world):
+def test_x_slab_step_matches_oracle(oracle, world, peer):
     import torch
     if torch.cuda.device_count() < world:
         pytest.skip("needs %d GPUs" % world)
@@ -65,7 +76,7 @@ def test_x_slab_step_matches_oracle(oracle, world):
     ctx = mp.get_context("spawn")
     out = ctx.Queue()
     port = _free_port()
-    procs = [ctx.Process(target=_worker, args=(r, world, port, out)) for r in range(world)]
+    procs = [ctx.Process(target=_worker, args=(r, world, port, out, peer)) for r in range(world)]
     for pr in procs:
         pr.start()
     parts = out.get(timeout=600)
