@@ -3,15 +3,22 @@
 
   python bench.py [--gpus N] [--steps K] [--warmup W] [--workload NAME] [--impl reference]
 
-A "step" is one pass of the hot path over the synthetic water box named in config.workload:
-clear outputs -> force(+energy) kernel on the dynamically pruned list -> rolling prune on the reference's
-schedule (every 2nd step, numParts = nstlistPrune/2) -> pack forces (float4 -> float3), with coordinates
-already resident in HBM.  `value` = useful pair interactions per second, the quantity
-`gmx nonbonded-benchmark` prints (N/2 (rho 4/3 pi rc^3 + 1) pairs per step,
-src/gromacs/nbnxm/benchmark/bench_setup.cpp:332-337).  `e2e` is the same metric through the public API
-with host buffers (H2D of xq and D2H of forces + energies inside the timed region).  `roofline` reports
-the force kernel alone against the measured FP32-FMA peak using the reference's flop model
-(src/gromacs/gmxlib/nrnb.cpp:92-112) on the pairs the kernel actually evaluates.
+A "step" is one pass of the hot path over the synthetic water box named in config.workload, the nonbonded part of
+do_force in the reference's order (nbnxm_b200_do_force_step): clear outputs -> force(+energy) kernel on the
+dynamically pruned list -> rolling prune on the reference's schedule (every 2nd step, numParts = nstlistPrune/2)
+-> pack forces (float4 -> float3), with coordinates already resident in HBM.  `value` = useful pair interactions
+per second, the quantity `gmx nonbonded-benchmark` prints (N/2 (rho 4/3 pi rc^3 + 1) pairs per step,
+src/gromacs/nbnxm/benchmark/bench_setup.cpp:332-337).  `e2e` is the same metric through the public API with host
+buffers (H2D of xq and D2H of forces + energies inside the timed region).  `roofline` reports the force kernel
+alone against the measured FP32-FMA peak using the reference's flop model (src/gromacs/gmxlib/nrnb.cpp:92-112)
+on the pairs the kernel actually evaluates.
+
+The default workload is the same for every N, so that the driver's 1/2/4/8-GPU lines are one strong-scaling
+series: water12m, BASELINE.json's configs[4] (12.3 M atoms, rc 1.2 nm, dynamic + rolling pruning), the box the
+north-star targets (kernel fraction of FP32 peak at 1 GPU, parallel efficiency at 8) are stated on; it fits one
+GPU.  The other configurations (--workload water96k_fswitch = configs[1], water384k_*, water1536k, bench3k) are
+recorded in profiles/ and DESIGN.md.  N > 1: x-slabs, one process per GPU, peer-memory halo over NVLink by
+default (--halo nccl for the ncclSend/ncclRecv exchange).
 
 --impl reference times the UNMODIFIED reference's CPU SIMD kernel (oracle/_ref/bench_ref, linked against
 the reference's own libgromacs) on the host cores for the same workload.
@@ -29,7 +36,7 @@ sys.path.insert(0, ROOT)
 
 METRIC = "useful_pair_interactions_per_s"
 UNIT = "Gpairs/s"
-DEFAULT_WORKLOAD = "water96k_fswitch"
+DEFAULT_WORKLOAD = "water12m"
 REF_VDW = {"cut": "cut", "fswitch": "fswitch", "pswitch": "pswitch", "ljpme": "ljpme"}
 
 
@@ -207,7 +214,7 @@ def main():
     args = ap.parse_args()
     claim_stdout()
     if args.workload is None:
-        args.workload = DEFAULT_WORKLOAD if args.gpus == 1 else "water1536k"
+        args.workload = DEFAULT_WORKLOAD
     if args.impl == "reference":
         return reference_arm(args)
 
@@ -307,6 +314,13 @@ def main():
     prune_ms = t.rolling_prune_ms / max(1, t.rolling_prune_count)
     fp32_peak = measure_fp32_peak(local_rank)
     achieved = computed_pairs * wl.flops_per_pair / (k_ms * 1e-3) * 1e-12
+    # dram__bytes_read.sum + dram__bytes_write.sum of one force-kernel launch from the committed ncu --set full captures
+    traffic = None
+    try:
+        with open(os.path.join(ROOT, "profiles", "force_kernel_dram_traffic.json")) as fh:
+            traffic = json.load(fh).get(args.workload, {}).get("bytes_per_launch")
+    except Exception:
+        pass
 
     # end to end through the public API with host buffers
     for i in range(args.warmup):
@@ -334,7 +348,7 @@ def main():
                 "h2d_bytes_per_step": int(nbat.numAtoms() * 16),
                 "d2h_bytes_per_step": int(nbat.numAtoms() * 12 + (16 + 45 * 24 if energy else 0))},
         "roofline": {"bound": "fp32_fma", "achieved": achieved, "peak": fp32_peak, "unit": "TFLOP/s",
-                     "frac": achieved / fp32_peak, "traffic": None,
+                     "frac": achieved / fp32_peak, "traffic": traffic,
                      "kernel": "nbnxm_force_kernel", "kernel_us": k_ms * 1e3, "rolling_prune_us": prune_ms * 1e3,
                      "flops_per_pair": wl.flops_per_pair,
                      "peak_source": "measured live: pure-FFMA kernel (nbnxm_b200_measure_fp32_peak); nominal 148 SM x 128 x 2 x 1.965 GHz = 74.45"},

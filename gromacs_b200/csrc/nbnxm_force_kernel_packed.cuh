@@ -701,9 +701,21 @@ __device__ __forceinline__ f32x2 body_general(const ParamsDev&    p,
     return vmul(W, vmul(invR2, wm));
 }
 
+#if defined(NBNXM_PACKED_MAXNREG_ENERGY) || defined(NBNXM_PACKED_MAXNREG_FORCE)
+#    ifndef NBNXM_PACKED_MAXNREG_ENERGY
+#        define NBNXM_PACKED_MAXNREG_ENERGY 128
+#    endif
+#    ifndef NBNXM_PACKED_MAXNREG_FORCE
+#        define NBNXM_PACKED_MAXNREG_FORCE 96
+#    endif
+template<int ELEC, int VDW, bool ENERGY>
+__global__ void __maxnreg__(ENERGY ? NBNXM_PACKED_MAXNREG_ENERGY : NBNXM_PACKED_MAXNREG_FORCE)
+        nbnxm_force_kernel_packed(const AtomDataDev ad, const ParamsDev p, const PairlistDev pl, const int calcFshift)
+#else
 template<int ELEC, int VDW, bool ENERGY>
 __global__ void __launch_bounds__(32, ENERGY ? NBNXM_PACKED_MIN_BLOCKS_ENERGY : NBNXM_PACKED_MIN_BLOCKS)
         nbnxm_force_kernel_packed(const AtomDataDev ad, const ParamsDev p, const PairlistDev pl, const int calcFshift)
+#endif
 {
     using Fl                   = Flavor<ELEC, VDW, ENERGY>;
     constexpr unsigned c_full  = 0xffffffffu;

@@ -151,7 +151,11 @@ __global__ void __launch_bounds__(32) bodychain(float* out, int iters, float see
 #pragma unroll 1
         for (int ci = 0; ci < 8; ci++)
         {
-            float4 xi = *(volatile float4*)(sm + ((ci * 8 + (threadIdx.x & 7) + it) & 63));
+            float4 xi;
+            {
+                const unsigned a = static_cast<unsigned>(__cvta_generic_to_shared(sm + ((ci * 8 + (threadIdx.x & 7) + it) & 63)));
+                asm volatile("ld.shared.v4.f32 {%0, %1, %2, %3}, [%4];" : "=f"(xi.x), "=f"(xi.y), "=f"(xi.z), "=f"(xi.w) : "r"(a) : "memory");
+            }
             u64    dx, dy, dz, r2;
             asm volatile("sub.rn.f32x2 %0, %1, %2;" : "=l"(dx) : "l"(pk(xi.x, xi.x)), "l"(xj));
             asm volatile("sub.rn.f32x2 %0, %1, %2;" : "=l"(dy) : "l"(pk(xi.y, xi.y)), "l"(yj));

@@ -6,12 +6,12 @@ for v in "$@"; do
   name=${v%%:*}; extra=${v#*:}
   touch gromacs_b200/csrc/*.cuh
   make -s -j32 -C gromacs_b200/csrc EXTRA="$extra" > gpurun_out/build_$name.log 2>&1 || { echo "build failed $name"; tail -5 gpurun_out/build_$name.log; continue; }
-  if [ $first = 1 ]; then
+  if [ $first = 1 ] && [ -z "$SKIP_TESTS" ]; then
     timeout 900 python -m pytest tests -m gpu -x -q > gpurun_out/pytest_gpu.log 2>&1; echo "pytest exit $?" >> gpurun_out/pytest_gpu.log; tail -5 gpurun_out/pytest_gpu.log
-    first=0
   fi
+  first=0
   timeout 600 python bench.py --workload water1536k --steps 20 --no-cpu-baseline > gpurun_out/bench_1536k_$name.json 2> gpurun_out/bench_1536k_$name.err
-  timeout 600 python bench.py --no-cpu-baseline > gpurun_out/bench_96k_$name.json 2> gpurun_out/bench_96k_$name.err
+  timeout 600 python bench.py --workload water96k_fswitch --no-cpu-baseline > gpurun_out/bench_96k_$name.json 2> gpurun_out/bench_96k_$name.err
   python - <<PY
 import json
 for w in ("1536k","96k"):

@@ -86,3 +86,65 @@ def test_1536k_box_properties(oracle, monkeypatch):
                                       g.nbfp_comb, g.shift_vec, nthreads=8)
     f_sub, _ = gpu_forces(wl, sub, energy=False, dynamic_pruning=False)
     assert relrms(f_sub, f32.astype(np.float64)) <= 5e-6
+
+
+@pytest.mark.parametrize("energy", [False, True])
+def test_long_sci_entries_span_descriptor_chunks(oracle, energy):
+    """Unsplit sci entries with more than 64 cjPacked groups: the packed kernel stages the groups of an entry in
+    shared memory 64 at a time (c_descChunk), so this walks more than one chunk per entry."""
+    import copy
+    from gromacs_b200.workload import make_workload
+    wl = make_workload("water48k_test", energy=energy)
+    wl.params = copy.copy(wl.params)
+    plist = wl.grid.pairlist(1.7, wl.box.excl_index, wl.box.excl_atoms, min_sci=0)
+    assert (plist.sci[:, 3] - plist.sci[:, 2]).max() > 64
+    g = wl.nbat
+    f_ref, _, e_ref, _ = oracle.forces(orc_params(oracle, wl), plist.sci, plist.cjPacked, plist.excl, g.xq, g.type,
+                                       g.lj_comb, g.nbfp, g.nbfp_comb, g.shift_vec)
+    f, (e_lj, e_el) = gpu_forces(wl, plist, energy=energy, dynamic_pruning=False)
+    assert relrms(f, f_ref) <= 5e-6
+    if energy:
+        assert abs(e_el - e_ref[1]) <= 1e-6 * abs(e_ref[1]), (e_el, e_ref[1])
+        assert abs(e_lj - e_ref[0]) <= 1e-6 * abs(e_ref[0]), (e_lj, e_ref[0])
+
+
+def test_do_force_step_matches_call_sequence():
+    """nbnxm_b200_do_force_step issues the same launches as the individual gpu_* calls: bit-identical masks, forces within
+    the atomics' summation-order noise."""
+    from gromacs_b200 import LOCAL, NbnxmGpu, StepWorkload
+    from gromacs_b200.workload import make_workload
+    wl = make_workload("water48k_test", energy=True)
+    import copy
+    params = copy.copy(wl.params)
+    params.use_dynamic_pruning = 1
+    params.rlist_inner_sq = np.float32(0.905 ** 2)
+    plist = wl.pairlist(min_sci=2000)
+    out = []
+    for composite in (False, True):
+        nbat = wl.nbat
+        nb = NbnxmGpu(params, nbat)
+        try:
+            sw = StepWorkload(computeEnergy=True, computeVirial=True)
+            nb.gpu_init_atomdata(nbat)
+            nb.gpu_init_pairlist(plist, LOCAL)
+            nb.setupGpuShortRangeWork(LOCAL)
+            nb.gpu_upload_shiftvec(nbat)
+            nb.gpu_copy_xq_to_gpu(nbat, LOCAL)
+            for step in range(4):
+                if composite:
+                    sw.useGpuFBufferOps = False
+                    nb.do_force_step(step, sw, have_halo=False, dynamic_pruning=True, num_parts=3, xq_host=nbat.xq, f_host=nbat.f)
+                else:
+                    nb.gpu_copy_xq_to_gpu(nbat, LOCAL)
+                    nb.gpu_clear_outputs(True)
+                    nb.gpu_launch_kernel(sw, LOCAL)
+                    if step % 2 == 1:
+                        nb.gpu_launch_kernel_pruneonly(LOCAL, 3)
+                    nb.gpu_launch_cpyback(nbat, sw, LOCAL)
+                e = nb.gpu_wait_finish_task(sw, LOCAL)
+            out.append((nbat.f.astype(np.float64).copy(), e))
+        finally:
+            nb.gpu_free()
+    (f0, e0), (f1, e1) = out
+    assert relrms(f1, f0) <= 1e-6
+    assert abs(e1[0] - e0[0]) <= 1e-6 * abs(e0[0]) and abs(e1[1] - e0[1]) <= 1e-6 * abs(e0[1])
