@@ -106,6 +106,10 @@ int fillParamsDev(nbnxm_b200* nb)
         h[pcSwC3] = d.sw_c3; h[pcSwC4] = d.sw_c4; h[pcSwC5] = d.sw_c5;
         h[pcSwC3x3] = 3.0f * d.sw_c3; h[pcSwC4x4] = 4.0f * d.sw_c4; h[pcSwC5x5] = 5.0f * d.sw_c5;
         h[pcCrf] = d.c_rf; h[pcTwoKrf] = d.two_k_rf; h[pcHalfTwoKrf] = 0.5f * d.two_k_rf; h[pcShEwald] = d.sh_ewald;
+        {
+            const float c2 = d.ewaldcoeff_lj * d.ewaldcoeff_lj;
+            h[pcLjeCoeff2] = c2; h[pcLjeCoeff6Sixth] = c2 * c2 * c2 * c_oneSixth; h[pcShLjEwald] = d.sh_lj_ewald;
+        }
         CU(nb->packedConsts.reserve(pcCount));
         if (nb->stream[0]) CU(cudaStreamSynchronize(nb->stream[0]));
         if (nb->stream[1]) CU(cudaStreamSynchronize(nb->stream[1]));

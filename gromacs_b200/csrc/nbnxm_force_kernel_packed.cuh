@@ -137,7 +137,7 @@ template<int ELEC, int VDW>
 struct PackedFlavor
 {
     using Fl                        = Flavor<ELEC, VDW, false>;
-    static constexpr bool available = !Fl::ewaldTab && !Fl::ljEwald;
+    static constexpr bool available = !Fl::ewaldTab && !Fl::ljEwaldLB;
     /* LJ parameters from the type table (staged in shared memory) instead of per-atom combination parameters */
     static constexpr bool typeTable = !Fl::ljComb;
 };
@@ -177,6 +177,7 @@ struct PackedConsts
     float num[7], den[5]; /* pmeCorrF with beta folded in: beta^3 pmeCorrF(beta^2 r^2) = num(r^2) / den(r^2) */
     float rvdw_switch, disp_c2, disp_c3, rep_c2, rep_c3, disp_c2_3, disp_c3_4, rep_c2_3, rep_c3_4, disp_cpot, rep_cpot;
     float sw_c3, sw_c4, sw_c5, sw_c3x3, sw_c4x4, sw_c5x5, c_rf, two_k_rf, half_two_k_rf, sh_ewald;
+    float lje_coeff2, lje_coeff6_6, sh_lj_ewald; /* LJ-PME: ewaldcoeff_lj^2, ewaldcoeff_lj^6 / 6, potential shift */
 };
 
 template<int ELEC, int VDW, bool ENERGY>
@@ -227,6 +228,12 @@ __device__ __forceinline__ void load_packed_consts(PackedConsts& k, const float*
         k.sw_c4x4 = __ldg(g + pcSwC4x4);
         k.sw_c5x5 = __ldg(g + pcSwC5x5);
     }
+    if (Fl::ljEwald)
+    {
+        k.lje_coeff2   = __ldg(g + pcLjeCoeff2);
+        k.lje_coeff6_6 = __ldg(g + pcLjeCoeff6Sixth);
+        if (ENERGY) k.sh_lj_ewald = __ldg(g + pcShLjEwald);
+    }
     if (Fl::elecCut || Fl::elecRF) k.c_rf = __ldg(g + pcCrf);
     if (Fl::elecRF)
     {
@@ -245,6 +252,7 @@ __device__ __forceinline__ V pair_w(const ParamsDev&    p,
                                     const V             qq,
                                     const V             c6n,
                                     const V             c12,
+                                    const V             c6grid, /* LJ-PME only */
                                     const V             intBit,
                                     V&                  invR2out,
                                     V&                  eLJout,
@@ -281,6 +289,22 @@ __device__ __forceinline__ V pair_w(const ParamsDev&    p,
     if (Fl::ljFSwitch || Fl::ljPSwitch || (Fl::ewaldAna && ENERGY))
     {
         r = vmul(r2, invR);
+    }
+    if (Fl::ljEwald)
+    {
+        /* LJ-PME grid correction with the geometric grid coefficient (nbnxm_cuda_kernel_utils.cuh:194-245):
+         * F/r += c6grid (r^-6 - exp(-c^2 r^2) (r^-6 (1 + c^2 r^2 + c^4 r^4 / 2) + c^6 / 6)) r^-2; excluded pairs get it too */
+        const V invR6nm = vmul(vmul(invR2, invR2), invR2);
+        const V cr2     = vmul(r2, vbc<V>(k.lje_coeff2));
+        const V expmcr2 = vex2(vmul(cr2, vbc<V>(-1.4426950408889634f)));
+        const V npoly   = vfma(vfma(cr2, vbc<V>(-0.5f), vbc<V>(-1.0f)), cr2, vbc<V>(-1.0f)); /* -(1 + cr2 + cr2^2 / 2) */
+        W               = vfma(c6grid, vfma(expmcr2, vfma(invR6nm, npoly, vbc<V>(-k.lje_coeff6_6)), invR6nm), W);
+        if (ENERGY)
+        {
+            /* c6grid / 6 (r^-6 (1 - exp(-c^2 r^2) poly) + sh_lj_ewald intBit) */
+            const V sh = EXCL ? vmul(intBit, vbc<V>(k.sh_lj_ewald)) : vbc<V>(k.sh_lj_ewald);
+            eLJ        = vfma(vmul(c6grid, vbc<V>(c_oneSixth)), vfma(invR6nm, vfma(expmcr2, npoly, vbc<V>(1.0f)), sh), eLJ);
+        }
     }
     if (Fl::ljFSwitch || Fl::ljPSwitch)
     {
@@ -445,6 +469,18 @@ __device__ __forceinline__ void sts32(const unsigned a, const float x)
     asm volatile("st.shared.f32 [%0], %1;" ::"r"(a), "f"(x) : "memory");
 }
 
+/* LJ parameters of an i-atom: two floats, four with LJ-PME (the grid factor) */
+template<int ELEC, int VDW>
+__device__ __forceinline__ float4 load_lji(const unsigned a)
+{
+    if (Flavor<ELEC, VDW, false>::ljEwald)
+    {
+        return lds128(a);
+    }
+    const float2 v = lds64(a);
+    return make_float4(v.x, v.y, 0.0f, 0.0f);
+}
+
 /* byte distance of the two type tables in PackedShared */
 constexpr unsigned c_nbC12FromC6n = sizeof(float) * c_packedMaxTypes * c_packedMaxTypes;
 
@@ -462,7 +498,7 @@ struct FjAcc
 
 /* LJ parameters of two pairs: c6n = -6*C6, c12 = 12*C12 */
 template<int ELEC, int VDW>
-__device__ __forceinline__ void lj_params_packed(const PackedShared& sm, const float2 pi, const PackedJ& j, f32x2& c6n, f32x2& c12)
+__device__ __forceinline__ void lj_params_packed(const PackedShared& sm, const float4 pi, const PackedJ& j, f32x2& c6n, f32x2& c12, f32x2& c6grid)
 {
     using Fl = Flavor<ELEC, VDW, false>;
     if (Fl::ljCombGeom)
@@ -487,6 +523,8 @@ __device__ __forceinline__ void lj_params_packed(const PackedShared& sm, const f
         c6n               = pk(lds32f(ia), lds32f(ib));
         c12               = pk(lds32f(ia + c_nbC12FromC6n), lds32f(ib + c_nbC12FromC6n));
     }
+    /* LJ-PME, geometric grid coefficient: product of the per-atom factors (pi.z, j.lj1) */
+    c6grid = Fl::ljEwaldGeom ? vmul(pk(pi.z, pi.z), j.lj1) : 0ull;
 }
 
 /* One (i-cluster, j-cluster) pair with BOTH halves in the list and no exclusion masks, force only: the hot body. */
@@ -495,7 +533,7 @@ __device__ __forceinline__ void body_both(const ParamsDev&    p,
                                           const PackedConsts& k,
                                           const PackedShared& sm,
                                           const float4        xi,
-                                          const float2        pi,
+                                          const float4        pi,
                                           const PackedJ&      j,
                                           float (&fi)[3],
                                           FjAcc& fj)
@@ -512,10 +550,10 @@ __device__ __forceinline__ void body_both(const ParamsDev&    p,
     {
         r2 = vfma(dz, dz, vfma(dy, dy, vfma(dx, dx, pk(c_r2Guard, c_r2Guard))));
     }
-    f32x2 c6n, c12;
-    lj_params_packed<ELEC, VDW>(sm, pi, j, c6n, c12);
+    f32x2 c6n, c12, c6grid;
+    lj_params_packed<ELEC, VDW>(sm, pi, j, c6n, c12, c6grid);
     f32x2       invR2, e0, e1;
-    const f32x2 W  = pair_w<f32x2, ELEC, VDW, false, false>(p, k, r2, vmul(pk(xi.w, xi.w), j.q), c6n, c12, 0ull, invR2, e0, e1);
+    const f32x2 W  = pair_w<f32x2, ELEC, VDW, false, false>(p, k, r2, vmul(pk(xi.w, xi.w), j.q), c6n, c12, c6grid, 0ull, invR2, e0, e1);
     const f32x2 F  = vmul(W, invR2);
     const float F0 = (lo(r2) < k.rc2) ? lo(F) : 0.0f;
     const float F1 = (hi(r2) < k.rc2) ? hi(F) : 0.0f;
@@ -537,7 +575,7 @@ __device__ __forceinline__ void body_single(const ParamsDev&    p,
                                             const PackedConsts& k,
                                             const PackedShared& sm,
                                             const float4        xi,
-                                            const float2        pi,
+                                            const float4        pi,
                                             const PackedJ&      j,
                                             float (&fi)[3],
                                             FjAcc& fj)
@@ -568,7 +606,8 @@ __device__ __forceinline__ void body_single(const ParamsDev&    p,
         c12               = lds32f(ia + c_nbC12FromC6n);
     }
     float       invR2, e0, e1;
-    const float W = pair_w<float, ELEC, VDW, false, false>(p, k, r2, xi.w * qj, c6n, c12, 0.0f, invR2, e0, e1);
+    const float c6grid = Fl::ljEwaldGeom ? pi.z * l1 : 0.0f;
+    const float W = pair_w<float, ELEC, VDW, false, false>(p, k, r2, xi.w * qj, c6n, c12, c6grid, 0.0f, invR2, e0, e1);
     const float F = (r2 < k.rc2) ? W * invR2 : 0.0f;
     fi[0]         = fmaf(F, dx, fi[0]);
     fi[1]         = fmaf(F, dy, fi[1]);
@@ -593,7 +632,7 @@ template<int ELEC, int VDW, bool ENERGY>
 __device__ __forceinline__ float body_single_general(const ParamsDev&    p,
                                                      const PackedConsts& k,
                                                      const float4        xi,
-                                                     const float2        pi,
+                                                     const float4        pi,
                                                      const PackedJ&      j,
                                                      const bool          half1,
                                                      float&              dx,
@@ -629,7 +668,8 @@ __device__ __forceinline__ float body_single_general(const ParamsDev&    p,
         c12               = lds32f(ia + c_nbC12FromC6n);
     }
     float       invR2, ePairLJ, ePairEl;
-    const float W = pair_w<float, ELEC, VDW, ENERGY, false>(p, k, fmaxf(r2, c_minDistanceSquared), xi.w * qj, c6n, c12, 1.0f, invR2,
+    const float c6grid = Fl::ljEwaldGeom ? pi.z * l1 : 0.0f;
+    const float W = pair_w<float, ELEC, VDW, ENERGY, false>(p, k, fmaxf(r2, c_minDistanceSquared), xi.w * qj, c6n, c12, c6grid, 1.0f, invR2,
                                                             ePairLJ, ePairEl);
     const bool  w = r2 < k.rc2;
     if (ENERGY)
@@ -647,7 +687,7 @@ __device__ __forceinline__ f32x2 body_general(const ParamsDev&    p,
                                               const PackedConsts& k,
                                               const PackedShared& sm,
                                               const float4        xi,
-                                              const float2        pi,
+                                              const float4        pi,
                                               const PackedJ&      j,
                                               const bool          m0, /* list mask bits of the two halves */
                                               const bool          m1,
@@ -683,14 +723,14 @@ __device__ __forceinline__ f32x2 body_general(const ParamsDev&    p,
             w1 = w1 && i1;
         }
     }
-    f32x2 c6n, c12;
-    lj_params_packed<ELEC, VDW>(sm, pi, j, c6n, c12);
+    f32x2 c6n, c12, c6grid;
+    lj_params_packed<ELEC, VDW>(sm, pi, j, c6n, c12, c6grid);
     /* clamped from both sides: the masking below is a multiplication, so pairs with filler atoms (parked at -1e6 nm)
      * must stay finite in the Ewald polynomials too; real pairs of a listed cluster pair are a few nm apart */
     const f32x2 r2c = pk(fminf(fmaxf(lo(r2), c_minDistanceSquared), c_maxDistanceSquared),
                          fminf(fmaxf(hi(r2), c_minDistanceSquared), c_maxDistanceSquared));
     f32x2       invR2, ePairLJ, ePairEl;
-    const f32x2 W = pair_w<f32x2, ELEC, VDW, ENERGY, EXCL>(p, k, r2c, vmul(pk(xi.w, xi.w), j.q), c6n, c12, intBit, invR2, ePairLJ, ePairEl);
+    const f32x2 W = pair_w<f32x2, ELEC, VDW, ENERGY, EXCL>(p, k, r2c, vmul(pk(xi.w, xi.w), j.q), c6n, c12, c6grid, intBit, invR2, ePairLJ, ePairEl);
     /* masking by multiplication: every quantity is finite (r2 is clamped), and the energy sums become FMAs */
     const f32x2 wm = pk(w0 ? 1.0f : 0.0f, w1 ? 1.0f : 0.0f);
     if (ENERGY)
@@ -796,7 +836,14 @@ __global__ void __launch_bounds__(32, ENERGY ? NBNXM_PACKED_MIN_BLOCKS_ENERGY : 
         }
         else
         {
-            sm.lji[lane + 32 * h] = make_float4(__uint_as_float(smem_u32(sm.nbC6n + ad.atomType[ai] * ad.numTypes)), 0.0f, 0.0f, 0.0f);
+            const int   t      = ad.atomType[ai];
+            const float c6grid = Fl::ljEwald ? __ldg(p.nbfpComb + t).x : 0.0f;
+            sm.lji[lane + 32 * h] = make_float4(__uint_as_float(smem_u32(sm.nbC6n + t * ad.numTypes)), 0.0f, c6grid, 0.0f);
+            if (ENERGY && Fl::ljEwald && diagonalEntry)
+            {
+                /* LJ-PME self term, once per diagonal sci entry (nbnxm_cuda_kernel.cuh:395-408) */
+                eLJ += __ldg(p.nbfp + t * (ad.numTypes + 1)).x * 0.5f * c_oneSixth * k.lje_coeff6_6;
+            }
         }
     }
 
@@ -843,7 +890,9 @@ __global__ void __launch_bounds__(32, ENERGY ? NBNXM_PACKED_MIN_BLOCKS_ENERGY : 
                 }
                 else
                 {
-                    pjNext.x = __int_as_float(4 * ad.atomType[aj]);
+                    const int t = ad.atomType[aj];
+                    pjNext.x    = __int_as_float(4 * t);
+                    if (Fl::ljEwald) pjNext.y = __ldg(p.nbfpComb + t).x;
                 }
             }
             /* entry 0 of the exclusion array is all ones (pairlist.h:274-287) */
@@ -869,7 +918,7 @@ __global__ void __launch_bounds__(32, ENERGY ? NBNXM_PACKED_MIN_BLOCKS_ENERGY : 
             sts32(stageAddr + 256, xjNext.z);
             sts32(stageAddr + 256 + 8, xjNext.w);
             sts32(stageAddr + 512, pjNext.x);
-            if (Fl::ljComb)
+            if (Fl::ljComb || Fl::ljEwald)
             {
                 sts32(stageAddr + 512 + 8, pjNext.y);
             }
@@ -921,7 +970,7 @@ __global__ void __launch_bounds__(32, ENERGY ? NBNXM_PACKED_MIN_BLOCKS_ENERGY : 
                         if (mFast & (1u << ci))
                         {
                             const float4 xi = lds128(xqiAddr + ci * (16 * c_clusterSize));
-                            const float2 pi = lds64(xqiAddr + c_ljiFromXqi + ci * (16 * c_clusterSize));
+                            const float4 pi = load_lji<ELEC, VDW>(xqiAddr + c_ljiFromXqi + ci * (16 * c_clusterSize));
                             if (__builtin_expect((mBoth & (1u << ci)) != 0u, 1))
                             {
                                 body_both<ELEC, VDW>(p, k, sm, xi, pi, j, fi[ci], fj);
@@ -948,7 +997,7 @@ __global__ void __launch_bounds__(32, ENERGY ? NBNXM_PACKED_MIN_BLOCKS_ENERGY : 
                         if (mBoth & (1u << ci))
                         {
                             const float4 xi = lds128(xqiAddr + ci * (16 * c_clusterSize));
-                            const float2 pi = lds64(xqiAddr + c_ljiFromXqi + ci * (16 * c_clusterSize));
+                            const float4 pi = load_lji<ELEC, VDW>(xqiAddr + c_ljiFromXqi + ci * (16 * c_clusterSize));
                             f32x2        dx, dy, dz;
                             const f32x2  F = body_general<ELEC, VDW, ENERGY, false>(p, k, sm, xi, pi, j, true, true, true, true, false,
                                                                                    false, dx, dy, dz, eLJj, eElj);
@@ -978,7 +1027,7 @@ __global__ void __launch_bounds__(32, ENERGY ? NBNXM_PACKED_MIN_BLOCKS_ENERGY : 
                             const int    ci    = __ffs(mSingle) - 1;
                             const bool   half1 = ((m0 >> ci) & 1u) == 0u;
                             const float4 xi    = lds128(xqiAddr + ci * (16 * c_clusterSize));
-                            const float2 pi    = lds64(xqiAddr + c_ljiFromXqi + ci * (16 * c_clusterSize));
+                            const float4 pi    = load_lji<ELEC, VDW>(xqiAddr + c_ljiFromXqi + ci * (16 * c_clusterSize));
                             float        dx, dy, dz;
                             const float  F = body_single_general<ELEC, VDW, ENERGY>(p, k, xi, pi, j, half1, dx, dy, dz, eLJs, eEls);
                             const float  fx = F * dx, fy = F * dy, fz = F * dz;
@@ -1033,7 +1082,7 @@ __global__ void __launch_bounds__(32, ENERGY ? NBNXM_PACKED_MIN_BLOCKS_ENERGY : 
                     {
                         const int    ci = __ffs(mEx) - 1;
                         const float4 xi = lds128(xqiAddr + ci * (16 * c_clusterSize));
-                        const float2 pi = lds64(xqiAddr + c_ljiFromXqi + ci * (16 * c_clusterSize));
+                        const float4 pi = load_lji<ELEC, VDW>(xqiAddr + c_ljiFromXqi + ci * (16 * c_clusterSize));
                         const bool   onDiagonal = (ciDiag == ci);
                         const int    bit        = 8 * jm + ci;
                         f32x2        dx, dy, dz;
