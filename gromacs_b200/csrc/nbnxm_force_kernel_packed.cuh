@@ -760,6 +760,10 @@ __global__ void __launch_bounds__(32, ENERGY ? NBNXM_PACKED_MIN_BLOCKS_ENERGY : 
     using Fl                   = Flavor<ELEC, VDW, ENERGY>;
     constexpr unsigned c_full  = 0xffffffffu;
     constexpr bool     c_types = PackedFlavor<ELEC, VDW>::typeTable;
+    /* Single-half cluster pairs: two unrolled scalar bodies per i-cluster in the force-only kernels, one loop body for all
+     * i-clusters where the pair body is long (energies, potential switch): the unrolled form exceeds the 32 KB
+     * instruction cache by too much (measured: potential switch 515 -> 433 us with the loop, LJ-PME 365 -> 386 us) */
+    constexpr bool c_unrollSingle = !ENERGY && !Fl::ljPSwitch;
 
     const int lane = threadIdx.x;
     const int il   = lane & 7;
@@ -961,7 +965,7 @@ __global__ void __launch_bounds__(32, ENERGY ? NBNXM_PACKED_MIN_BLOCKS_ENERGY : 
                 FjAcc fj = { 0.0f, 0.0f, 0.0f, 0.0f, 0.0f, 0.0f };
                 f32x2 eLJj = 0ull, eElj = 0ull;
                 const unsigned mFast = (m0 | m1) & ~curEx;
-                if (!ENERGY)
+                if (c_unrollSingle)
                 {
                     const unsigned mBoth = m0 & m1;
 #pragma unroll
@@ -988,7 +992,7 @@ __global__ void __launch_bounds__(32, ENERGY ? NBNXM_PACKED_MIN_BLOCKS_ENERGY : 
                 }
                 else
                 {
-                    /* cluster pairs with both halves in the list: packed bodies, packed j-force accumulators */
+                    /* cluster pairs with both halves in the list: packed bodies (with energies: packed j-force accumulators) */
                     const unsigned mBoth = m0 & m1 & mFast;
                     f32x2          pjx = 0ull, pjy = 0ull, pjz = 0ull;
 #pragma unroll
@@ -998,23 +1002,33 @@ __global__ void __launch_bounds__(32, ENERGY ? NBNXM_PACKED_MIN_BLOCKS_ENERGY : 
                         {
                             const float4 xi = lds128(xqiAddr + ci * (16 * c_clusterSize));
                             const float4 pi = load_lji<ELEC, VDW>(xqiAddr + c_ljiFromXqi + ci * (16 * c_clusterSize));
-                            f32x2        dx, dy, dz;
-                            const f32x2  F = body_general<ELEC, VDW, ENERGY, false>(p, k, sm, xi, pi, j, true, true, true, true, false,
-                                                                                   false, dx, dy, dz, eLJj, eElj);
-                            fi[ci][0] = fmaf(lo(F), lo(dx), fmaf(hi(F), hi(dx), fi[ci][0]));
-                            fi[ci][1] = fmaf(lo(F), lo(dy), fmaf(hi(F), hi(dy), fi[ci][1]));
-                            fi[ci][2] = fmaf(lo(F), lo(dz), fmaf(hi(F), hi(dz), fi[ci][2]));
-                            pjx       = vfma(F, dx, pjx);
-                            pjy       = vfma(F, dy, pjy);
-                            pjz       = vfma(F, dz, pjz);
+                            if (ENERGY)
+                            {
+                                f32x2       dx, dy, dz;
+                                const f32x2 F = body_general<ELEC, VDW, ENERGY, false>(p, k, sm, xi, pi, j, true, true, true, true,
+                                                                                      false, false, dx, dy, dz, eLJj, eElj);
+                                fi[ci][0] = fmaf(lo(F), lo(dx), fmaf(hi(F), hi(dx), fi[ci][0]));
+                                fi[ci][1] = fmaf(lo(F), lo(dy), fmaf(hi(F), hi(dy), fi[ci][1]));
+                                fi[ci][2] = fmaf(lo(F), lo(dz), fmaf(hi(F), hi(dz), fi[ci][2]));
+                                pjx       = vfma(F, dx, pjx);
+                                pjy       = vfma(F, dy, pjy);
+                                pjz       = vfma(F, dz, pjz);
+                            }
+                            else
+                            {
+                                body_both<ELEC, VDW>(p, k, sm, xi, pi, j, fi[ci], fj);
+                            }
                         }
                     }
-                    fj.xA = lo(pjx);
-                    fj.yA = lo(pjy);
-                    fj.zA = lo(pjz);
-                    fj.xB = hi(pjx);
-                    fj.yB = hi(pjy);
-                    fj.zB = hi(pjz);
+                    if (ENERGY)
+                    {
+                        fj.xA = lo(pjx);
+                        fj.yA = lo(pjy);
+                        fj.zA = lo(pjz);
+                        fj.xB = hi(pjx);
+                        fj.yB = hi(pjy);
+                        fj.zB = hi(pjz);
+                    }
                     /* cluster pairs with one half only (about one in four after pruning): a scalar body on that half,
                      * one loop body for all i-clusters (the unrolled form would not fit the instruction cache) */
                     unsigned mSingle = mFast & ~mBoth;
