@@ -763,7 +763,11 @@ __global__ void __launch_bounds__(32, ENERGY ? NBNXM_PACKED_MIN_BLOCKS_ENERGY : 
     /* Single-half cluster pairs: two unrolled scalar bodies per i-cluster in the force-only kernels, one loop body for all
      * i-clusters where the pair body is long (energies, potential switch): the unrolled form exceeds the 32 KB
      * instruction cache by too much (measured: potential switch 515 -> 433 us with the loop, LJ-PME 365 -> 386 us) */
+#ifdef NBNXM_PACKED_NO_UNROLLED_SINGLE
+    constexpr bool c_unrollSingle = false;
+#else
     constexpr bool c_unrollSingle = !ENERGY && !Fl::ljPSwitch;
+#endif
 
     const int lane = threadIdx.x;
     const int il   = lane & 7;

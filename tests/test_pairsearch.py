@@ -92,3 +92,21 @@ def test_x_slab_lists_partition_the_pairs(oracle, nslabs):
     # (x + shift) is rounded to float per image, so a pair seen from the other side differs by ~1e-7
     assert relrms(f, f_ref) < 1e-6
     assert abs(e[1] - e_ref[1]) < 1e-7 * abs(e_ref[1])
+
+
+@pytest.mark.parametrize("nslabs", [2, 4, 8])
+def test_slab_grid_gives_equal_slabs(nslabs):
+    """nbnxm_b200_grid_create_slabs: a whole number of x columns per slab, so that every slab of the (uniform) water box
+    holds the same number of bins, and the halo stays inside the next slab."""
+    from gromacs_b200.slabs import slab_bin_ranges
+    from gromacs_b200.workload import make_workload
+    wl = make_workload("water48k_test", nthreads=4, nslabs=nslabs)
+    assert wl.grid.ncx % nslabs == 0
+    sizes = []
+    for r in range(nslabs):
+        home, halo, tx = slab_bin_ranges(wl.grid, nslabs, r, 0.95)
+        sizes.append(home[1] - home[0])
+        assert 0 < halo[1] - halo[0] <= 1.1 * (home[1] - home[0])
+        assert tx == (-1 if r == nslabs - 1 else 0)
+    assert max(sizes) - min(sizes) <= 0.05 * max(sizes), sizes
+    assert sum(sizes) == wl.grid.nbins
