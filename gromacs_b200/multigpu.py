@@ -13,6 +13,7 @@ Host-side pieces (slab ranges, list re-indexing) are pure numpy and are tested o
 import ctypes as C
 import json
 import os
+import sys
 import time
 from dataclasses import dataclass
 
@@ -254,7 +255,17 @@ def bench_multi_gpu(args, rank, world, local_rank):
             parts = [torch.empty_like(t) for _ in range(world)]
             dist.all_gather(parts, t)
             return [bytes(p.cpu().numpy().tobytes()) for p in parts]
-        halo.enable_peer_memory(gather, rank, world)
+        # all ranks use the same transport: fall back to NCCL if mapping the neighbour's memory fails anywhere
+        ok = torch.ones(1, dtype=torch.int32, device="cuda")
+        try:
+            halo.enable_peer_memory(gather, rank, world)
+        except Exception as exc:    # e.g. CUDA IPC not permitted in this container
+            print("rank %d: peer-memory halo unavailable (%s), using NCCL" % (rank, exc), file=sys.stderr)
+            ok.zero_()
+        dist.all_reduce(ok, op=dist.ReduceOp.MIN)
+        if int(ok.item()) == 0 and halo.peer:
+            nb._check(lib.nbnxm_b200_peer_close(nb._h))
+            halo.peer = False
         dist.barrier()
     local_stream = torch.cuda.ExternalStream(nb.streams()[0])
     flush = None if args.no_l2_flush else torch.empty(256 << 20, dtype=torch.uint8, device="cuda")
@@ -368,8 +379,11 @@ def bench_multi_gpu(args, rank, world, local_rank):
         if emit_line is None:
             from bench import emit as emit_line
         emit_line(line)
+    torch.cuda.synchronize()
+    dist.barrier()          # nobody unmaps or frees memory a neighbour's kernels may still touch
     halo_free = getattr(lib, "nbnxm_b200_halo_free")
     halo_free(nb._h)
+    dist.barrier()
     nb.gpu_free()
     dist.barrier()
     dist.destroy_process_group()
