@@ -5,21 +5,23 @@
  * profiles/microbench).  This kernel is therefore built around the instruction count per atom pair:
  *   - the two halves of a cluster pair (j-atoms jl and jl+4 against the same i-atom) are one packed pair stream
  *     (fma.rn.f32x2): ALU, MUFU-feeding, shared-memory and control instructions are shared by two pairs.  A
- *     cluster pair of which only one half survived pruning (about one in four) runs a scalar body on that half
- *     in the force-only kernel, so a pruned half costs nothing;
+ *     cluster pair of which only one half survived pruning (about one in four) runs a scalar body on that half, so a
+ *     pruned half costs nothing (unrolled per i-cluster in the force-only kernels, one loop body where the pair body
+ *     is long: energies, potential switch);
  *   - the pair force is evaluated as W = (F/r) r^2 (one multiplication by r^-2 at the end, no r^-3), the Ewald
  *     correction polynomial runs on r^2 with the powers of beta folded into its coefficients, and the r^2 = 0
  *     guard of filler atoms is an additive 1e-12 inside the first FMA instead of a max;
  *   - the path with exclusion masks is chosen per (j-cluster, i-cluster) from a warp-wide OR of the mask words,
  *     not per cjPacked group, and is one non-unrolled loop: about 3 % of the cluster pairs of a water box carry
  *     exclusions, but 28 % of the groups do;
- *   - per-group bookkeeping is kept small: every lane loads the j-cluster index it needs itself, the lane-dependent
- *     shared-memory offsets are computed once (and kept from being re-derived from the thread index in every
+ *   - per-group bookkeeping is kept small: the cjPacked groups of an entry are staged in shared memory 64 at a time, the
+ *     pair-body constants live in uniform registers (loaded from global memory once), the lane-dependent
+ *     shared-memory addresses are computed once (and kept from being re-derived from the thread index in every
  *     body), partial j forces are parked without sign change in rows padded to 9 float4 (conflict-free without a
  *     swizzle) and reduced once per group.
  *
  * Same list walk and reductions as nbnxm_force_kernel (nbnxm_force_kernel.cuh), which remains the kernel for the
- * fused-prune variant, for the flavors that need per-pair table look-ups or expf (tabulated Ewald, LJ-PME) and for
+ * fused-prune variant, for tabulated Ewald (per-pair table look-ups), LJ-PME with the Lorentz-Berthelot grid and for
  * type-table flavors with more than c_packedMaxTypes atom types.  Physics from
  * src/gromacs/nbnxm/nbnxm_kernel_utils.h:56-289 and src/gromacs/nbnxm/cuda/nbnxm_cuda_kernel.cuh:505-660.
  */
