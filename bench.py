@@ -209,6 +209,10 @@ def main():
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-l2-flush", action="store_true")
     ap.add_argument("--min-sci", type=int, default=0, help="override gpu_min_ci_balanced (list splitting target)")
+    ap.add_argument("--e2e-chunks", type=int, default=0,
+                    help="N = 1: chunks of the pipelined end-to-end step (1 = plain copy-compute-copy sequence; "
+                         "0 = one chunk per 250k atoms, at most 24: measured 22.0 / 17.9 / 15.9 / 14.9 / 14.9 ms per step "
+                         "with 1 / 8 / 16 / 24 / 32 chunks on the 12.3 M-atom box)")
     ap.add_argument("--halo", default="peer", choices=["peer", "nccl"],
                     help="N > 1: peer-memory halo over NVLink (no transport calls) or ncclSend/ncclRecv")
     args = ap.parse_args()
@@ -247,6 +251,13 @@ def main():
 
     nb = NbnxmGpu(wl.params, nbat, device=local_rank)
     plist = wl.pairlist(min_sci=args.min_sci or nb.gpu_min_ci_balanced())
+    # end-to-end path: coordinates go up and forces come down in chunks of grid columns, pipelined against the kernel
+    # (nbnxm_b200_do_force_step_pipelined); the list is the same, with its sci entries grouped by chunk
+    from gromacs_b200.pipeline import make_chunk_plan
+    nchunks = args.e2e_chunks if args.e2e_chunks > 0 else max(1, min(24, wl.box.natoms // 250000))
+    chunks = make_chunk_plan(wl.grid, plist, nchunks) if nchunks > 1 else None
+    if chunks is not None:
+        plist = chunks.plist
     nb.gpu_init_atomdata(nbat)
     nb.gpu_init_pairlist(plist, LOCAL)
     nb.setupGpuShortRangeWork(LOCAL)
@@ -260,8 +271,11 @@ def main():
         # the do_force sequence: [H2D xq] -> clear outputs -> force(+energy) kernel -> rolling prune on odd steps
         # (isDynamicPruningStepGpu, pairlistsets.h:108-115) -> f4 -> f3 [-> D2H f, energies], one foreign call
         sw.useGpuFBufferOps = not host_io
-        nb.do_force_step(i, sw, have_halo=False, dynamic_pruning=cfg["dynamic_pruning"], num_parts=num_parts,
-                         xq_host=nbat.xq if host_io else None, f_host=nbat.f if host_io else None)
+        if host_io and chunks is not None:
+            nb.do_force_step_pipelined(i, sw, chunks, nbat.xq, nbat.f, dynamic_pruning=cfg["dynamic_pruning"], num_parts=num_parts)
+        else:
+            nb.do_force_step(i, sw, have_halo=False, dynamic_pruning=cfg["dynamic_pruning"], num_parts=num_parts,
+                             xq_host=nbat.xq if host_io else None, f_host=nbat.f if host_io else None)
         if host_io:
             return nb.gpu_wait_finish_task(sw, LOCAL)
 
@@ -346,7 +360,9 @@ def main():
         "clocks": clock_rec,
         "e2e": {"value": wl.useful_pairs / (ms_e2e * 1e-3) * 1e-9, "unit": UNIT, "ms_per_step": ms_e2e,
                 "h2d_bytes_per_step": int(nbat.numAtoms() * 16),
-                "d2h_bytes_per_step": int(nbat.numAtoms() * 12 + (16 + 45 * 24 if energy else 0))},
+                "d2h_bytes_per_step": int(nbat.numAtoms() * 12 + (16 + 45 * 24 if energy else 0)),
+                "pipeline": ("%d chunks of grid columns: H2D, force kernel and D2H of different chunks overlap "
+                             "(nbnxm_b200_do_force_step_pipelined)" % chunks.nchunks) if chunks is not None else "none"},
         "roofline": {"bound": "fp32_fma", "achieved": achieved, "peak": fp32_peak, "unit": "TFLOP/s",
                      "frac": achieved / fp32_peak, "traffic": traffic,
                      "kernel": "nbnxm_force_kernel", "kernel_us": k_ms * 1e3, "rolling_prune_us": prune_ms * 1e3,

@@ -5,6 +5,7 @@
  * src/gromacs/nbnxm/gpu_common.h (task completion :141-431), behind plain C entry points.
  * There is no CPU path: every entry point needs a CUDA device.
  */
+#include <algorithm>
 #include <cstdarg>
 #include <cstdio>
 #include <cstring>
@@ -291,6 +292,13 @@ int nbnxm_b200_free(nbnxm_b200_t* nb)
         pl.sciOffset.release(); pl.rollingPart.release(); pl.cjPacked.release(); pl.imaskOuter.release();
         pl.excl.release(); pl.pairCount.release();
     }
+    for (cudaEvent_t ev : nb->chunkH2D) cudaEventDestroy(ev);
+    for (cudaEvent_t ev : nb->chunkKernel) cudaEventDestroy(ev);
+    if (nb->pipeStart) cudaEventDestroy(nb->pipeStart);
+    if (nb->pipeD2HDone) cudaEventDestroy(nb->pipeD2HDone);
+    if (nb->h2dStream) cudaStreamDestroy(nb->h2dStream);
+    if (nb->d2hStream) cudaStreamDestroy(nb->d2hStream);
+    if (nb->pipeKernelStream) cudaStreamDestroy(nb->pipeKernelStream);
     if (nb->h_fshift) cudaFreeHost(nb->h_fshift);
     if (nb->h_energy) cudaFreeHost(nb->h_energy);
     if (nb->nonlocalDone) cudaEventDestroy(nb->nonlocalDone);
@@ -611,6 +619,147 @@ int nbnxm_b200_launch_kernel(nbnxm_b200_t* nb, int iloc, int compute_energy, int
         pl.haveFreshList = false;
     }
     endRegion(nb, st);
+    CU(cudaGetLastError());
+    return 0;
+}
+
+/* Force kernel over a contiguous range of the sci array in the caller's order (not the count-sorted copy): the chunk
+ * launches of the pipelined step. */
+static int launchKernelRange(nbnxm_b200_t* nb, int firstSci, int numSci, int compute_energy, int compute_virial, cudaStream_t st)
+{
+    PairList& pl = nb->plist[0];
+    if (numSci <= 0) return 0;
+    ForceKernelPtr kernel = select_force_kernel(nb->params.elec_type, nb->params.vdw_type, compute_energy != 0, false, nb->numTypes);
+    if (!kernel) return fail("no kernel for elec_type %d vdw_type %d", nb->params.elec_type, nb->params.vdw_type);
+    if (nb->carveoutSet.insert(reinterpret_cast<const void*>(kernel)).second)
+    {
+        CU(cudaFuncSetAttribute(reinterpret_cast<const void*>(kernel), cudaFuncAttributePreferredSharedMemoryCarveout,
+                                cudaSharedmemCarveoutMaxShared));
+    }
+    PairlistDev d = pl.dev(false);
+    d.sciSorted   = const_cast<nbnxm_b200_sci_t*>(pl.sci.p) + firstSci;
+    d.numSci      = numSci;
+    kernel<<<numSci, 32, 0, st>>>(nb->ad(0), nb->pd, d, compute_virial != 0);
+    nb->launches++;
+    CU(cudaGetLastError());
+    return 0;
+}
+
+int nbnxm_b200_do_force_step_pipelined(nbnxm_b200_t* nb, int step, const nbnxm_b200_step_flags_t* fl, const float* xq_host,
+                                       float* f_host, int nchunks, const int* chunk_first_atom, const int* chunk_first_sci,
+                                       const unsigned int* chunk_needs)
+{
+    if (!nb || !fl || !xq_host || !f_host || !chunk_first_atom || !chunk_first_sci || !chunk_needs)
+    {
+        return fail("nbnxm_b200_do_force_step_pipelined: null argument");
+    }
+    if (nchunks < 1 || nchunks > 32) return fail("nbnxm_b200_do_force_step_pipelined: 1..32 chunks");
+    if (fl->have_halo) return fail("nbnxm_b200_do_force_step_pipelined: single-rank path only");
+    PairList& pl = nb->plist[0];
+    if (chunk_first_atom[0] != 0 || chunk_first_atom[nchunks] != nb->natoms || chunk_first_sci[0] != 0
+        || chunk_first_sci[nchunks] != pl.numSci)
+    {
+        return fail("nbnxm_b200_do_force_step_pipelined: the chunks must cover all atoms and all sci entries");
+    }
+    if (pl.haveFreshList || pl.numSci == 0)
+    {
+        /* the first-pass prune of a fresh list needs every coordinate: plain sequence on search steps */
+        return nbnxm_b200_do_force_step(nb, step, fl, xq_host, f_host);
+    }
+    CU(cudaSetDevice(nb->device));
+    const int    e = fl->compute_energy, v = fl->compute_virial;
+    cudaStream_t st = nb->stream[0];
+    if (!nb->h2dStream)
+    {
+        CU(cudaStreamCreateWithFlags(&nb->h2dStream, cudaStreamNonBlocking));
+        CU(cudaStreamCreateWithFlags(&nb->d2hStream, cudaStreamNonBlocking));
+        CU(cudaStreamCreateWithFlags(&nb->pipeKernelStream, cudaStreamNonBlocking));
+        CU(cudaEventCreateWithFlags(&nb->pipeStart, cudaEventDisableTiming));
+        CU(cudaEventCreateWithFlags(&nb->pipeD2HDone, cudaEventDisableTiming));
+    }
+    while (int(nb->chunkH2D.size()) < nchunks)
+    {
+        cudaEvent_t a, b;
+        CU(cudaEventCreateWithFlags(&a, cudaEventDisableTiming));
+        CU(cudaEventCreateWithFlags(&b, cudaEventDisableTiming));
+        nb->chunkH2D.push_back(a);
+        nb->chunkKernel.push_back(b);
+    }
+    /* everything of the previous step on the local stream (kernels reading xq, copies of f) comes first */
+    if (nbnxm_b200_clear_outputs(nb, v)) return 1;
+    CU(cudaEventRecord(nb->pipeStart, st));
+    CU(cudaStreamWaitEvent(nb->h2dStream, nb->pipeStart, 0));
+    CU(cudaStreamWaitEvent(nb->d2hStream, nb->pipeStart, 0));
+    for (int c = 0; c < nchunks; c++)
+    {
+        const int first = chunk_first_atom[c], count = chunk_first_atom[c + 1] - first;
+        if (count > 0)
+        {
+            CU(cudaMemcpyAsync(nb->xq.p + first, xq_host + 4 * size_t(first), sizeof(float4) * count, cudaMemcpyHostToDevice,
+                               nb->h2dStream));
+        }
+        CU(cudaEventRecord(nb->chunkH2D[c], nb->h2dStream));
+    }
+    /* sci chunks in the order in which their coordinates are complete: by the last atom chunk they need */
+    int order[32], lastNeeded[32];
+    for (int k = 0; k < nchunks; k++)
+    {
+        order[k]      = k;
+        lastNeeded[k] = 0;
+        for (int c = 0; c < nchunks; c++)
+            if (chunk_needs[k] & (1u << c)) lastNeeded[k] = c;
+    }
+    for (int a = 1; a < nchunks; a++)
+        for (int b = a; b > 0 && lastNeeded[order[b]] < lastNeeded[order[b - 1]]; b--) std::swap(order[b], order[b - 1]);
+    /* the chunk kernels alternate between two streams so that the tail of one overlaps the head of the next (their
+     * force reductions are atomic) */
+    CU(cudaStreamWaitEvent(nb->pipeKernelStream, nb->pipeStart, 0));
+    for (int n = 0; n < nchunks; n++)
+    {
+        const int    k  = order[n];
+        cudaStream_t ks = (n & 1) ? nb->pipeKernelStream : st;
+        for (int c = 0; c < nchunks; c++)
+            if (chunk_needs[k] & (1u << c)) CU(cudaStreamWaitEvent(ks, nb->chunkH2D[c], 0));
+        if (launchKernelRange(nb, chunk_first_sci[k], chunk_first_sci[k + 1] - chunk_first_sci[k], e, v, ks)) return 1;
+        CU(cudaEventRecord(nb->chunkKernel[k], ks));
+    }
+    /* what follows on the local stream (rolling prune, energy copies) comes after every chunk kernel */
+    for (int n = 1; n < nchunks; n += 2) CU(cudaStreamWaitEvent(st, nb->chunkKernel[order[n]], 0));
+    /* forces of an atom chunk are final once every sci chunk that touches it has run: atom chunks in that order */
+    int position[32], readyAt[32], chunkOrder[32];
+    for (int n = 0; n < nchunks; n++) position[order[n]] = n;
+    for (int c = 0; c < nchunks; c++)
+    {
+        chunkOrder[c] = c;
+        readyAt[c]    = 0;
+        for (int k = 0; k < nchunks; k++)
+            if (chunk_needs[k] & (1u << c)) readyAt[c] = std::max(readyAt[c], position[k]);
+    }
+    for (int a = 1; a < nchunks; a++)
+        for (int b = a; b > 0 && readyAt[chunkOrder[b]] < readyAt[chunkOrder[b - 1]]; b--) std::swap(chunkOrder[b], chunkOrder[b - 1]);
+    for (int n = 0; n < nchunks; n++)
+    {
+        const int c = chunkOrder[n];
+        for (int k = 0; k < nchunks; k++)
+            if (chunk_needs[k] & (1u << c)) CU(cudaStreamWaitEvent(nb->d2hStream, nb->chunkKernel[k], 0));
+        const int first = chunk_first_atom[c], count = chunk_first_atom[c + 1] - first;
+        if (count > 0)
+        {
+            launch_f4_to_f3(nb->f4.p, nb->f3.p, first, count, nb->d2hStream);
+            nb->launches++;
+            CU(cudaMemcpyAsync(f_host + 3 * size_t(first), nb->f3.p + 3 * size_t(first), sizeof(float) * 3 * count,
+                               cudaMemcpyDeviceToHost, nb->d2hStream));
+        }
+    }
+    CU(cudaEventRecord(nb->pipeD2HDone, nb->d2hStream));
+    if (fl->dynamic_pruning && step % 2 == 1)
+    {
+        if (nbnxm_b200_launch_kernel_pruneonly(nb, 0, fl->rolling_prune_parts)) return 1;
+    }
+    if (v) CU(cudaMemcpyAsync(nb->h_fshift, nb->fshift.p, sizeof(double) * 3 * c_numShiftVectors, cudaMemcpyDeviceToHost, st));
+    if (e) CU(cudaMemcpyAsync(nb->h_energy, nb->energy.p, sizeof(double) * 2, cudaMemcpyDeviceToHost, st));
+    /* gpu_wait_finish_task synchronises the local stream: make it cover the force copies */
+    CU(cudaStreamWaitEvent(st, nb->pipeD2HDone, 0));
     CU(cudaGetLastError());
     return 0;
 }

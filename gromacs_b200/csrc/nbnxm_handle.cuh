@@ -154,6 +154,11 @@ struct nbnxm_b200
     bool                     pairCounting = false;
     long long                launches     = 0;
 
+    /* copy streams and events of the chunk-pipelined step (nbnxm_b200_do_force_step_pipelined), created on first use */
+    cudaStream_t             h2dStream = nullptr, d2hStream = nullptr, pipeKernelStream = nullptr;
+    std::vector<cudaEvent_t> chunkH2D, chunkKernel;
+    cudaEvent_t              pipeStart = nullptr, pipeD2HDone = nullptr;
+
     nbb::HaloState* halo = nullptr;
     std::set<const void*> carveoutSet; /* kernels whose shared-memory carve-out preference was set */
 

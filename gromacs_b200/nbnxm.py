@@ -24,7 +24,7 @@ VDW_TYPES = {"Cut": 0, "CutCombGeom": 1, "CutCombLB": 2, "FSwitch": 3, "PSwitch"
 
 # every symbol include/nbnxm_b200.h declares
 EXPORTED_SYMBOLS = [
-    "nbnxm_b200_last_error", "nbnxm_b200_init", "nbnxm_b200_free", "nbnxm_b200_update_params", "nbnxm_b200_do_force_step", "nbnxm_b200_peer_blob_size", "nbnxm_b200_peer_export", "nbnxm_b200_peer_import",
+    "nbnxm_b200_last_error", "nbnxm_b200_init", "nbnxm_b200_free", "nbnxm_b200_update_params", "nbnxm_b200_do_force_step", "nbnxm_b200_do_force_step_pipelined", "nbnxm_b200_peer_blob_size", "nbnxm_b200_peer_export", "nbnxm_b200_peer_import",
     "nbnxm_b200_peer_close", "nbnxm_b200_peer_error",
     "nbnxm_b200_init_pairlist", "nbnxm_b200_init_atomdata", "nbnxm_b200_upload_shiftvec",
     "nbnxm_b200_copy_xq_to_gpu", "nbnxm_b200_init_x_to_nbat_x", "nbnxm_b200_x_to_nbat_x",
@@ -276,6 +276,14 @@ class NbnxmGpu:
         xq = _ptr(xq_host, C.c_float) if xq_host is not None else None
         f = _ptr(f_host, C.c_float) if f_host is not None else None
         self._check(self._lib.nbnxm_b200_do_force_step(self._h, C.c_int(step), C.byref(fl), xq, f))
+
+    def do_force_step_pipelined(self, step, stepWork: StepWorkload, plan, xq_host, f_host, dynamic_pruning=False, num_parts=1):
+        """nbnxm_b200_do_force_step_pipelined with a ChunkPlan (gromacs_b200/pipeline.py); the pair list uploaded with
+        gpu_init_pairlist must be plan.plist."""
+        fl = StepFlags(int(stepWork.computeEnergy), int(stepWork.computeVirial), 0, int(dynamic_pruning), int(num_parts))
+        self._check(self._lib.nbnxm_b200_do_force_step_pipelined(
+            self._h, C.c_int(step), C.byref(fl), _ptr(xq_host, C.c_float), _ptr(f_host, C.c_float), C.c_int(plan.nchunks),
+            _ptr(plan.first_atom, C.c_int), _ptr(plan.first_sci, C.c_int), _ptr(plan.needs, C.c_uint32)))
 
     def gpu_clear_outputs(self, computeVirial=True):
         self._check(self._lib.nbnxm_b200_clear_outputs(self._h, C.c_int(int(computeVirial))))

@@ -259,6 +259,17 @@ typedef struct nbnxm_b200_step_flags
     int rolling_prune_parts;
 } nbnxm_b200_step_flags_t;
 int nbnxm_b200_do_force_step(nbnxm_b200_t* nb, int step, const nbnxm_b200_step_flags_t* flags, const float* xq_host, float* f_host);
+/* The same step for host-resident coordinates and forces (single rank), with the transfers pipelined against the
+ * force kernel: atoms are cut into nchunks contiguous ranges (chunk_first_atom[nchunks + 1], whole grid columns), the
+ * sci array - in the caller's order, grouped by the chunk of the i-atoms - into the matching ranges
+ * (chunk_first_sci[nchunks + 1]); chunk_needs[k] is the bit mask of the atom chunks the entries of sci chunk k read
+ * coordinates from / add forces to (from the outer list).  Coordinates go up chunk by chunk, the kernel of an sci chunk
+ * starts when the chunks it needs have arrived, the forces of an atom chunk come down when every sci chunk touching it
+ * has run.  The reference overlaps its non-local transfer with local work in the same spirit (sim_util.cpp:1772-1922).
+ * Falls back to the plain sequence on steps with a fresh list. */
+int nbnxm_b200_do_force_step_pipelined(nbnxm_b200_t* nb, int step, const nbnxm_b200_step_flags_t* flags, const float* xq_host,
+                                       float* f_host, int nchunks, const int* chunk_first_atom, const int* chunk_first_sci,
+                                       const unsigned int* chunk_needs);
 
 #ifdef __cplusplus
 }

@@ -148,3 +148,42 @@ def test_do_force_step_matches_call_sequence():
     (f0, e0), (f1, e1) = out
     assert relrms(f1, f0) <= 1e-6
     assert abs(e1[0] - e0[0]) <= 1e-6 * abs(e0[0]) and abs(e1[1] - e0[1]) <= 1e-6 * abs(e0[1])
+
+
+@pytest.mark.parametrize("energy", [False, True])
+def test_pipelined_step_matches_plain_step(energy):
+    """nbnxm_b200_do_force_step_pipelined (chunked H2D / kernel / D2H) against the plain sequence on the same list."""
+    import copy
+    from gromacs_b200 import LOCAL, NbnxmGpu, StepWorkload
+    from gromacs_b200.pipeline import make_chunk_plan
+    from gromacs_b200.workload import make_workload
+    wl = make_workload("water48k_test", energy=energy)
+    params = copy.copy(wl.params)
+    params.use_dynamic_pruning = 1
+    params.rlist_inner_sq = np.float32(0.905 ** 2)
+    plan = make_chunk_plan(wl.grid, wl.pairlist(min_sci=3000), 4)
+    assert plan.first_sci[-1] == plan.plist.sci.shape[0] and plan.first_atom[-1] == wl.nbat.numAtoms()
+    out = []
+    for pipelined in (False, True):
+        nbat = wl.nbat
+        nbat.f[:] = 0
+        nb = NbnxmGpu(params, nbat)
+        try:
+            sw = StepWorkload(computeEnergy=energy, computeVirial=energy, useGpuFBufferOps=False)
+            nb.gpu_init_atomdata(nbat)
+            nb.gpu_init_pairlist(plan.plist, LOCAL)
+            nb.setupGpuShortRangeWork(LOCAL)
+            nb.gpu_upload_shiftvec(nbat)
+            for step in range(4):
+                if pipelined:
+                    nb.do_force_step_pipelined(step, sw, plan, nbat.xq, nbat.f, dynamic_pruning=True, num_parts=3)
+                else:
+                    nb.do_force_step(step, sw, dynamic_pruning=True, num_parts=3, xq_host=nbat.xq, f_host=nbat.f)
+                e = nb.gpu_wait_finish_task(sw, LOCAL)
+            out.append((nbat.f.astype(np.float64).copy(), e))
+        finally:
+            nb.gpu_free()
+    (f0, e0), (f1, e1) = out
+    assert relrms(f1, f0) <= 1e-6
+    if energy:
+        assert abs(e1[0] - e0[0]) <= 1e-6 * abs(e0[0]) and abs(e1[1] - e0[1]) <= 1e-6 * abs(e0[1])
