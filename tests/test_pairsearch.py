@@ -110,3 +110,31 @@ def test_slab_grid_gives_equal_slabs(nslabs):
         assert tx == (-1 if r == nslabs - 1 else 0)
     assert max(sizes) - min(sizes) <= 0.05 * max(sizes), sizes
     assert sum(sizes) == wl.grid.nbins
+
+
+@pytest.mark.parametrize("nchunks", [2, 5])
+def test_chunk_plan_covers_every_atom_an_entry_touches(nchunks):
+    """gromacs_b200/pipeline.py: the sci array grouped by chunk is a permutation of the list's entries, chunk ranges
+    tile atoms and entries, and chunk_needs[k] contains the chunk of every i- and j-atom the entries of sci chunk k
+    touch (checked entry by entry)."""
+    from gromacs_b200.pipeline import make_chunk_plan
+    from gromacs_b200.workload import make_workload
+    wl = make_workload("water48k_test", nthreads=4)
+    plist = wl.pairlist(min_sci=1500)
+    plan = make_chunk_plan(wl.grid, plist, nchunks)
+    k = plan.nchunks
+    assert plan.first_atom[0] == 0 and plan.first_atom[-1] == wl.nbat.numAtoms()
+    assert plan.first_sci[0] == 0 and plan.first_sci[-1] == plist.sci.shape[0]
+    assert np.all(np.diff(plan.first_atom) > 0) and np.all(np.diff(plan.first_sci) >= 0)
+    a = np.ascontiguousarray(plist.sci).reshape(-1, 4)
+    b = np.ascontiguousarray(plan.plist.sci).reshape(-1, 4)
+    assert sorted(map(tuple, a.tolist())) == sorted(map(tuple, b.tolist()))
+    cjp = np.ascontiguousarray(plist.cjPacked).view(np.uint32).reshape(-1, 8)
+    chunk_of_atom = lambda atom: int(np.searchsorted(plan.first_atom, atom, side="right") - 1)
+    for c in range(k):
+        for e in b[plan.first_sci[c]:plan.first_sci[c + 1]:7]:       # every 7th entry keeps the test short
+            assert chunk_of_atom(e[0] * 64) == c
+            for g in cjp[e[2]:e[3]]:
+                for jm in range(4):
+                    if ((int(g[4]) | int(g[6])) >> (8 * jm)) & 0xff:
+                        assert plan.needs[c] & (1 << chunk_of_atom(int(g[jm]) * 8)), (c, jm, g)
