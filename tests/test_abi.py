@@ -48,3 +48,35 @@ def test_no_cpu_fallback():
     nbat, _ = product_inputs(d)
     with pytest.raises(NbnxmError, match="no CUDA device"):
         NbnxmGpu(product_params(d), nbat)
+
+
+def test_sm100a_kernels_keep_their_register_budget():
+    """The force kernels' occupancy is part of the design: the packed force-only Ewald kernels must fit 96
+    registers (20 warps per SM) without spilling, the energy kernels 128; and the library must carry sm_100a code only."""
+    import shutil
+    import subprocess
+    lib = os.path.join(ROOT, "gromacs_b200", "libnbnxm_b200.so")
+    if shutil.which("cuobjdump") is None or not os.path.exists(lib):
+        pytest.skip("cuobjdump or the built library is missing")
+    out = subprocess.run(["cuobjdump", "-res-usage", lib], capture_output=True, text=True, check=True).stdout
+    assert "sm_100a" in out and "sm_90" not in out and "sm_80" not in out
+    usage = {}
+    name = None
+    for line in out.splitlines():
+        m = re.match(r"\s*Function (\S+):", line)
+        if m:
+            name = m.group(1)
+            continue
+        m = re.search(r"REG:(\d+) STACK:(\d+)", line)
+        if m and name:
+            usage[name] = (int(m.group(1)), int(m.group(2)))
+    packed = {k: v for k, v in usage.items() if "nbnxm_force_kernel_packed" in k}
+    assert len(packed) >= 4 * 6 * 2
+    for k, (reg, stack) in packed.items():
+        energy = "Lb1EEE" in k
+        assert reg <= (128 if energy else 96), (k, reg)
+        assert stack <= 32, (k, stack)
+    # the headline flavors do not spill at all: Ewald analytical + LJ cut (type table) F and F+E, + force switch F+E
+    for vdw, e in ((1, 0), (1, 1), (3, 1)):
+        k = [n for n in packed if "packedILi4ELi%dELb%dEEE" % (vdw, e) in n]
+        assert k and packed[k[0]][1] == 0, (vdw, e, k and packed[k[0]])
