@@ -1,0 +1,637 @@
+/* Per-thread bodies of the GPU pair-list builder (nbnxm_gpusearch.cu), written as host+device functions.
+ *
+ * The builder is a sequence of data-parallel passes with a prefix sum between them; every pass is "one thread per
+ * work item, no intra-block cooperation", so each body below is a plain function of the item index.  The CUDA
+ * kernels are thin wrappers (`index = blockIdx.x * blockDim.x + threadIdx.x`); tests/kernel_emu runs the same
+ * bodies in a host loop so that the search logic is checked on a machine without a GPU (test infrastructure, not a
+ * product path: the library itself only ever launches the kernels).
+ *
+ * What is built is what the reference's CPU search hands to gpu_init_pairlist, in its formats
+ * (src/gromacs/nbnxm/pairlist.h:189-287): super-cluster entries from a bounding-box sweep over the column grid
+ * (pairlist.cpp:2827-3310), cluster-pair masks with the bounding-box / atom-pair distance test
+ * (make_cluster_list_supersub, pairlist.cpp:813-966), self + Newton exclusions on the diagonal (:651-688), topology
+ * exclusions (:1561-1660) and splitting of long i-entries (:1769-1879).
+ *
+ * Arithmetic is spelled with explicit fmaf so that the host builder (pairsearch.cpp), the emulation and the device
+ * produce the same bits; the lists are then equal entry for entry.
+ *
+ * Work items:
+ *   entry slot e = (bin - binBegin) * 27 + s, s = (tz+1)*9 + (ty+1)*3 + (tx+1): one candidate i-entry (bin, shift);
+ *   bin pair p: (entry, j-bin) whose bounding boxes are within rlist, listed per entry in ascending j-bin order
+ *   (own bin first on the central shift), so that the j-clusters of an entry are sorted by cluster index.
+ */
+#ifndef NBNXM_B200_GPUSEARCH_BODIES_H
+#define NBNXM_B200_GPUSEARCH_BODIES_H
+
+#include <math.h>
+
+#include "../../include/nbnxm_b200.h"
+
+#if defined(__CUDACC__)
+#    define NBS_HD __host__ __device__ __forceinline__
+#else
+#    define NBS_HD inline
+#endif
+
+namespace nbs
+{
+
+constexpr int   c_cl        = 8;  /* atoms per cluster */
+constexpr int   c_binCl     = 8;  /* clusters per bin (super-cluster) */
+constexpr int   c_binAtoms  = 64; /* atoms per bin */
+constexpr int   c_central   = 22; /* central shift index, pbcutil/ishift.h */
+constexpr int   c_numSlots  = 27; /* shift candidates per bin */
+constexpr float c_farAway   = -1000000.0f; /* filler coordinate, atomdata.cpp:171 */
+
+struct BB
+{
+    float lo[3], hi[3];
+};
+
+struct alignas(16) XQ
+{
+    float x, y, z, q;
+};
+
+/* squared distance between bounding box a (shifted by sh) and b; 0 when they overlap */
+NBS_HD float bbDist2(const BB& a, const float* sh, const BB& b)
+{
+    float d2 = 0.0f;
+    for (int d = 0; d < 3; d++)
+    {
+        const float dl = (a.lo[d] + sh[d]) - b.hi[d];
+        const float dh = b.lo[d] - (a.hi[d] + sh[d]);
+        const float dm = fmaxf(fmaxf(dl, dh), 0.0f);
+        d2             = fmaf(dm, dm, d2);
+    }
+    return d2;
+}
+
+/* square of the bounding-box distance below which a cluster pair is accepted without looking at the atoms: rlist minus
+ * half the average x/y diagonal of a cluster (boundingbox_only_distance2, pairlist.cpp); host side */
+inline float bbOnlyDistance2(const float* cellSize, float rlist)
+{
+    const float bbx = 0.5f * cellSize[0];
+    const float bby = 0.5f * cellSize[1];
+    const float rbb = fmaxf(0.0f, rlist - 0.5f * sqrtf(fmaf(bby, bby, bbx * bbx)));
+    return rbb * rbb;
+}
+
+NBS_HD float dist2(float dx, float dy, float dz)
+{
+    return fmaf(dz, dz, fmaf(dy, dy, dx * dx));
+}
+
+/* is any atom pair of i-cluster gci (shifted) and j-cluster gcj within rl2? (clusterpair_in_range, pairlist.cpp) */
+NBS_HD bool clusterPairInRange(const XQ* xq, int gci, int gcj, const float* sh, float rl2)
+{
+    for (int i = 0; i < c_cl; i++)
+    {
+        const XQ xi = xq[gci * c_cl + i];
+        if (xi.x == c_farAway)
+        {
+            continue;
+        }
+        const float px = xi.x + sh[0], py = xi.y + sh[1], pz = xi.z + sh[2];
+        for (int j = 0; j < c_cl; j++)
+        {
+            const XQ xj = xq[gcj * c_cl + j];
+            if (dist2(px - xj.x, py - xj.y, pz - xj.z) < rl2)
+            {
+                return true;
+            }
+        }
+    }
+    return false;
+}
+
+struct Grid
+{
+    float      box[3];
+    float      cellSize[2];
+    int        ncx, ncy, nbins, natoms;
+    const int* colFirstBin; /* ncx*ncy + 1 */
+    const int* atomIndex;   /* nbat slot -> atom, -1 = filler */
+    const int* slotOfAtom;  /* atom -> nbat slot */
+    const XQ*  xq;          /* nbat order */
+    BB*        clBB;        /* per cluster */
+    int*       clCount;     /* real atoms per cluster */
+    BB*        binBB;       /* per bin, lo > hi when the bin holds no atom */
+    const int* exclIndex;   /* topology exclusions, CSR in atom order; may be null */
+    const int* exclAtoms;
+};
+
+struct Params
+{
+    float rlist, rl2, rbb2;
+    int   binBegin, binEnd; /* i-bins */
+    int   jBinLo, jBinHi;   /* j-bins */
+    int   interZone, requiredTx;
+    int   maxGroups;        /* cjPacked groups per sci entry after splitting */
+};
+
+struct Work
+{
+    int*           entryNumBinPairs; /* per entry slot (+1) */
+    int*           entryBinPairOff;  /* exclusive scan of the above (+1: total) */
+    int*           binPairJ;         /* per bin pair: j-bin */
+    int*           binPairEntry;     /* per bin pair: entry slot */
+    unsigned char* binPairMask;      /* per (bin pair, j-cluster): i-cluster mask */
+    int*           entryNumJ;        /* j-clusters per entry */
+    int*           entryGroups;      /* cjPacked groups per entry (+1) */
+    int*           entryCjOff;       /* scan */
+    int*           entryNumSci;      /* sci entries per entry after splitting (+1) */
+    int*           entrySciOff;      /* scan */
+    int*           entryNonEmpty;    /* 1 when the entry has j-clusters (+1) */
+    int*           entryCompactOff;  /* scan */
+    int*           compactEntry;     /* compact index -> entry slot */
+    unsigned long long*     numClusterPairs;
+    nbnxm_b200_sci_t*       sci;
+    nbnxm_b200_cj_packed_t* cjp;
+    nbnxm_b200_excl_t*      excl;
+    int*                    exclFlag; /* per (cjPacked, half) (+1) */
+    int*                    exclOff;  /* scan */
+};
+
+NBS_HD void atomicAddULL(unsigned long long* p, unsigned long long v)
+{
+#if defined(__CUDA_ARCH__)
+    atomicAdd(p, v);
+#else
+#    if defined(_OPENMP)
+#        pragma omp atomic
+#    endif
+    *p += v;
+#endif
+}
+
+NBS_HD void atomicAndU32(unsigned int* p, unsigned int v)
+{
+#if defined(__CUDA_ARCH__)
+    atomicAnd(p, v);
+#else
+#    if defined(_OPENMP)
+#        pragma omp atomic
+#    endif
+    *p &= v;
+#endif
+}
+
+/* ---- pass 0: bounding boxes from the coordinates (Grid::calcBoundingBoxes, grid.cpp) ---- */
+
+NBS_HD void clusterBoundingBox(const Grid& g, int cluster)
+{
+    BB bb;
+    for (int d = 0; d < 3; d++)
+    {
+        bb.lo[d] = 1e30f;
+        bb.hi[d] = -1e30f;
+    }
+    int count = 0;
+    for (int i = 0; i < c_cl; i++)
+    {
+        const int slot = cluster * c_cl + i;
+        if (g.atomIndex[slot] >= 0)
+        {
+            const XQ v = g.xq[slot];
+            count++;
+            bb.lo[0] = fminf(bb.lo[0], v.x);
+            bb.hi[0] = fmaxf(bb.hi[0], v.x);
+            bb.lo[1] = fminf(bb.lo[1], v.y);
+            bb.hi[1] = fmaxf(bb.hi[1], v.y);
+            bb.lo[2] = fminf(bb.lo[2], v.z);
+            bb.hi[2] = fmaxf(bb.hi[2], v.z);
+        }
+    }
+    g.clBB[cluster]    = bb;
+    g.clCount[cluster] = count;
+}
+
+NBS_HD void binBoundingBox(const Grid& g, int bin)
+{
+    BB bb;
+    for (int d = 0; d < 3; d++)
+    {
+        bb.lo[d] = 1e30f;
+        bb.hi[d] = -1e30f;
+    }
+    for (int cl = 0; cl < c_binCl; cl++)
+    {
+        if (g.clCount[bin * c_binCl + cl] > 0)
+        {
+            const BB cb = g.clBB[bin * c_binCl + cl];
+            for (int d = 0; d < 3; d++)
+            {
+                bb.lo[d] = fminf(bb.lo[d], cb.lo[d]);
+                bb.hi[d] = fmaxf(bb.hi[d], cb.hi[d]);
+            }
+        }
+    }
+    g.binBB[bin] = bb;
+}
+
+/* ---- entries ---- */
+
+struct Entry
+{
+    int   bi = 0, shift = 0;
+    float sh[3] = { 0.0f, 0.0f, 0.0f };
+    bool  subDiag = false; /* central shift within one zone: half of the own bin, and only bins above it */
+};
+
+/* decodes entry slot e; false when the slot cannot hold an entry (shift not in the half shell / not the zone's x
+ * shift, empty i-bin, shifted bin further than rlist from the unit cell) */
+NBS_HD bool entryDecode(const Grid& g, const Params& p, int e, Entry& en)
+{
+    en.bi       = p.binBegin + e / c_numSlots;
+    const int s = e % c_numSlots;
+    const int tz = s / 9 - 1, ty = (s / 3) % 3 - 1, tx = s % 3 - 1;
+    en.shift    = ((tz + 1) * 3 + (ty + 1)) * 5 + (tx + 2);
+    if (p.interZone)
+    {
+        if (tx != p.requiredTx)
+        {
+            return false;
+        }
+    }
+    else if (en.shift > c_central)
+    {
+        return false; /* half shell: backward shifts only */
+    }
+    en.sh[0]   = tx * g.box[0];
+    en.sh[1]   = ty * g.box[1];
+    en.sh[2]   = tz * g.box[2];
+    en.subDiag = (!p.interZone && en.shift == c_central);
+    const BB ibb = g.binBB[en.bi];
+    if (ibb.lo[0] > ibb.hi[0])
+    {
+        return false;
+    }
+    for (int d = 0; d < 3; d++)
+    {
+        if (ibb.lo[d] + en.sh[d] - p.rlist > g.box[d] || ibb.hi[d] + en.sh[d] + p.rlist < 0)
+        {
+            return false;
+        }
+    }
+    return true;
+}
+
+/* calls f(bj) for the j-bins of a (valid) entry whose bounding box is within rlist of the shifted i-bin, in list
+ * order: own bin first on the central shift, then by column (x-major) and along z */
+template<typename F>
+NBS_HD void forEachJBin(const Grid& g, const Params& p, const Entry& en, F&& f)
+{
+    const BB ibb    = g.binBB[en.bi];
+    auto     tryBin = [&](int bj) {
+        if (bj < p.jBinLo || bj >= p.jBinHi)
+        {
+            return;
+        }
+        const BB jbb = g.binBB[bj];
+        if (jbb.lo[0] > jbb.hi[0])
+        {
+            return;
+        }
+        if (bbDist2(ibb, en.sh, jbb) >= p.rl2)
+        {
+            return;
+        }
+        f(bj);
+    };
+    if (en.subDiag)
+    {
+        tryBin(en.bi);
+    }
+    const float xlo = ibb.lo[0] + en.sh[0] - p.rlist, xhi = ibb.hi[0] + en.sh[0] + p.rlist;
+    const float ylo = ibb.lo[1] + en.sh[1] - p.rlist, yhi = ibb.hi[1] + en.sh[1] + p.rlist;
+    int         cx0 = int(floorf(xlo / g.cellSize[0]));
+    int         cx1 = int(floorf(xhi / g.cellSize[0]));
+    int         cy0 = int(floorf(ylo / g.cellSize[1]));
+    int         cy1 = int(floorf(yhi / g.cellSize[1]));
+    cx0             = cx0 > 0 ? cx0 : 0;
+    cy0             = cy0 > 0 ? cy0 : 0;
+    cx1             = cx1 < g.ncx - 1 ? cx1 : g.ncx - 1;
+    cy1             = cy1 < g.ncy - 1 ? cy1 : g.ncy - 1;
+    for (int cx = cx0; cx <= cx1; cx++)
+    {
+        for (int cy = cy0; cy <= cy1; cy++)
+        {
+            const int c = cx * g.ncy + cy;
+            for (int bj = g.colFirstBin[c]; bj < g.colFirstBin[c + 1]; bj++)
+            {
+                if (en.subDiag && bj <= en.bi)
+                {
+                    continue; /* own bin done, lower bins own the pair */
+                }
+                const float zhi = g.binBB[bj].hi[2], zlo = g.binBB[bj].lo[2];
+                if ((ibb.lo[2] + en.sh[2]) - zhi >= p.rlist)
+                {
+                    continue;
+                }
+                if (zlo - (ibb.hi[2] + en.sh[2]) >= p.rlist)
+                {
+                    break; /* bins of a column are sorted along z */
+                }
+                tryBin(bj);
+            }
+        }
+    }
+}
+
+/* ---- pass 1 / 2: count, then list, the bin pairs of entry slot e ---- */
+
+template<bool WRITE>
+NBS_HD void entryBinPairs(const Grid& g, const Params& p, const Work& w, int e)
+{
+    Entry en;
+    int   n = 0;
+    if (entryDecode(g, p, e, en))
+    {
+        const int off = WRITE ? w.entryBinPairOff[e] : 0;
+        forEachJBin(g, p, en, [&](int bj) {
+            if (WRITE)
+            {
+                w.binPairJ[off + n]     = bj;
+                w.binPairEntry[off + n] = e;
+            }
+            n++;
+        });
+    }
+    if (!WRITE)
+    {
+        w.entryNumBinPairs[e] = n;
+    }
+}
+
+/* ---- pass 3: i-cluster mask of j-cluster (bin pair p, cj): item = p * 8 + cj ---- */
+
+NBS_HD void binPairMask(const Grid& g, const Params& p, const Work& w, int item)
+{
+    const int pr = item >> 3, cj = item & 7;
+    const int e  = w.binPairEntry[pr];
+    const int bj = w.binPairJ[pr];
+    Entry     en;
+    entryDecode(g, p, e, en);
+    const int    gcj  = bj * c_binCl + cj;
+    unsigned int mask = 0;
+    if (g.clCount[gcj] > 0)
+    {
+        const BB jbb = g.clBB[gcj];
+        if (bbDist2(g.binBB[en.bi], en.sh, jbb) < p.rl2)
+        {
+            for (int ci = 0; ci < c_binCl; ci++)
+            {
+                const int gci = en.bi * c_binCl + ci;
+                if (g.clCount[gci] == 0)
+                {
+                    continue;
+                }
+                if (en.subDiag && bj == en.bi && ci > cj)
+                {
+                    continue;
+                }
+                const float d2 = bbDist2(g.clBB[gci], en.sh, jbb);
+                if (d2 >= p.rl2)
+                {
+                    continue;
+                }
+                /* bounding boxes closer than rbb are accepted without looking at the atoms */
+                if (d2 < p.rbb2 || clusterPairInRange(g.xq, gci, gcj, en.sh, p.rl2))
+                {
+                    mask |= 1u << ci;
+                }
+            }
+        }
+    }
+    w.binPairMask[item] = (unsigned char)mask;
+}
+
+/* ---- pass 4: j-clusters and cjPacked groups per entry ---- */
+
+NBS_HD void entryCountJ(const Work& w, int e)
+{
+    int                nj = 0;
+    unsigned long long ncp = 0;
+    for (int pr = w.entryBinPairOff[e]; pr < w.entryBinPairOff[e + 1]; pr++)
+    {
+        for (int cj = 0; cj < c_binCl; cj++)
+        {
+            const unsigned int m = w.binPairMask[pr * c_binCl + cj];
+            if (m)
+            {
+                nj++;
+#if defined(__CUDA_ARCH__)
+                ncp += __popc(m);
+#else
+                ncp += __builtin_popcount(m);
+#endif
+            }
+        }
+    }
+    w.entryNumJ[e]     = nj;
+    w.entryGroups[e]   = (nj + 3) / 4;
+    w.entryNonEmpty[e] = nj > 0 ? 1 : 0;
+    if (ncp)
+    {
+        atomicAddULL(w.numClusterPairs, ncp);
+    }
+}
+
+/* sci entries per entry slot once the total number of groups (hence maxGroups) is known */
+NBS_HD void entryCountSci(const Params& p, const Work& w, int e)
+{
+    const int ng     = w.entryGroups[e];
+    w.entryNumSci[e] = ng > 0 ? (ng + p.maxGroups - 1) / p.maxGroups : 0;
+}
+
+/* ---- pass 5: write the cjPacked groups and sci entries of entry slot e ---- */
+
+NBS_HD void entryFill(const Grid& g, const Params& p, const Work& w, int e)
+{
+    const int nj = w.entryNumJ[e];
+    if (nj == 0)
+    {
+        return;
+    }
+    Entry en;
+    entryDecode(g, p, e, en);
+    const int              cjp0 = w.entryCjOff[e];
+    int                    k    = 0;
+    nbnxm_b200_cj_packed_t grp;
+    for (int pr = w.entryBinPairOff[e]; pr < w.entryBinPairOff[e + 1]; pr++)
+    {
+        const int bj = w.binPairJ[pr];
+        for (int cj = 0; cj < c_binCl; cj++)
+        {
+            const unsigned int m = w.binPairMask[pr * c_binCl + cj];
+            if (!m)
+            {
+                continue;
+            }
+            const int jm = k & 3;
+            if (jm == 0)
+            {
+                for (int q = 0; q < 4; q++)
+                {
+                    grp.cj[q] = 0;
+                }
+                grp.imei[0].imask    = 0;
+                grp.imei[0].excl_ind = 0;
+                grp.imei[1].excl_ind = 0;
+            }
+            grp.cj[jm] = bj * c_binCl + cj;
+            grp.imei[0].imask |= m << (jm * 8);
+            k++;
+            if (jm == 3 || k == nj)
+            {
+                grp.imei[1].imask     = grp.imei[0].imask; /* both halves start identical, pairlist.cpp:951-954 */
+                w.cjp[cjp0 + (k - 1) / 4] = grp;
+            }
+        }
+    }
+    const int ng   = w.entryGroups[e];
+    int       isci = w.entrySciOff[e];
+    for (int b = 0; b < ng; b += p.maxGroups)
+    {
+        nbnxm_b200_sci_t s;
+        s.sci             = en.bi;
+        s.shift           = en.shift;
+        s.cj_packed_begin = cjp0 + b;
+        s.cj_packed_end   = cjp0 + (b + p.maxGroups < ng ? b + p.maxGroups : ng);
+        w.sci[isci++]     = s;
+    }
+    w.compactEntry[w.entryCompactOff[e]] = e;
+}
+
+/* ---- pass 6: exclusions; item = compact entry * 64 + i-atom.  FILL = false marks the (cjPacked, half) mask
+ * words that need their own exclusion entry, FILL = true clears the bits (after excl_ind has been assigned) ---- */
+
+/* position of j-cluster gcj in the (sorted) j-list of an entry, -1 when absent */
+NBS_HD int findJ(const Work& w, int cjp0, int nj, int gcj)
+{
+    int lo = 0, hi = nj - 1;
+    while (lo <= hi)
+    {
+        const int mid = (lo + hi) >> 1;
+        const int v   = w.cjp[cjp0 + (mid >> 2)].cj[mid & 3];
+        if (v == gcj)
+        {
+            return mid;
+        }
+        if (v < gcj)
+        {
+            lo = mid + 1;
+        }
+        else
+        {
+            hi = mid - 1;
+        }
+    }
+    return -1;
+}
+
+template<bool FILL>
+NBS_HD void entryExclusions(const Grid& g, const Params& p, const Work& w, int item)
+{
+    const int e = w.compactEntry[item >> 6];
+    const int i = item & 63;
+    Entry     en;
+    entryDecode(g, p, e, en);
+    const int cjp0 = w.entryCjOff[e];
+    const int nj   = w.entryNumJ[e];
+    /* self + Newton exclusions on the diagonal cluster pair of i-cluster ci = i: only j > i interacts
+     * (setSelfAndNewtonExclusionsGpu, pairlist.cpp:651-688) */
+    if (en.subDiag && i < c_binCl)
+    {
+        const int ci = i;
+        const int k  = findJ(w, cjp0, nj, en.bi * c_binCl + ci);
+        if (k >= 0)
+        {
+            nbnxm_b200_cj_packed_t& grp = w.cjp[cjp0 + (k >> 2)];
+            const unsigned int      bit = 1u << ((k & 3) * 8 + ci);
+            if (grp.imei[0].imask & bit)
+            {
+                for (int half = 0; half < 2; half++)
+                {
+                    if (!FILL)
+                    {
+                        w.exclFlag[(cjp0 + (k >> 2)) * 2 + half] = 1;
+                    }
+                    else
+                    {
+                        nbnxm_b200_excl_t& ex = w.excl[grp.imei[half].excl_ind];
+                        for (int jj = 0; jj < 4; jj++)
+                        {
+                            const int ja = half * 4 + jj;
+                            for (int ia = 0; ia < c_cl; ia++)
+                            {
+                                if (ja <= ia)
+                                {
+                                    atomicAndU32(&ex.pair[jj * c_cl + ia], ~bit);
+                                }
+                            }
+                        }
+                    }
+                }
+            }
+        }
+    }
+    /* topology exclusions of i-atom i (setExclusionsForIEntry, pairlist.cpp:1561-1660) */
+    if (g.exclIndex != nullptr && g.exclAtoms != nullptr)
+    {
+        const int islot = en.bi * c_binAtoms + i;
+        const int ia    = g.atomIndex[islot];
+        if (ia >= 0)
+        {
+            for (int x = g.exclIndex[ia]; x < g.exclIndex[ia + 1]; x++)
+            {
+                const int ja = g.exclAtoms[x];
+                if (ja == ia)
+                {
+                    continue;
+                }
+                const int jslot = g.slotOfAtom[ja];
+                if (en.subDiag && jslot <= islot)
+                {
+                    continue;
+                }
+                const int k = findJ(w, cjp0, nj, jslot / c_cl);
+                if (k < 0)
+                {
+                    continue;
+                }
+                nbnxm_b200_cj_packed_t& grp = w.cjp[cjp0 + (k >> 2)];
+                const unsigned int      bit = 1u << ((k & 3) * 8 + i / c_cl);
+                if (!(grp.imei[0].imask & bit))
+                {
+                    continue;
+                }
+                const int jin  = jslot & (c_cl - 1);
+                const int half = jin / 4;
+                if (!FILL)
+                {
+                    w.exclFlag[(cjp0 + (k >> 2)) * 2 + half] = 1;
+                }
+                else
+                {
+                    atomicAndU32(&w.excl[grp.imei[half].excl_ind].pair[(jin & 3) * c_cl + (i & (c_cl - 1))], ~bit);
+                }
+            }
+        }
+    }
+}
+
+/* ---- pass 7: exclusion index of (cjPacked, half) item; entry 0 stays the shared all-ones mask ---- */
+
+NBS_HD void assignExclIndex(const Work& w, int item)
+{
+    if (w.exclFlag[item])
+    {
+        w.cjp[item >> 1].imei[item & 1].excl_ind = 1 + w.exclOff[item];
+    }
+}
+
+} // namespace nbs
+
+#endif

@@ -1,0 +1,341 @@
+/* Pass sequence of the GPU pair-list builder, written once over a backend:
+ *   nbnxm_gpusearch.cu instantiates it with the CUDA backend (kernels on the handle's stream, device buffers),
+ *   tests/kernel_emu/search_emu.cpp with a host-loop backend that runs the same bodies on the CPU (test only).
+ *
+ * Backend concept:
+ *   template<typename T> struct Buf { T* p; ... };          grow-only buffer
+ *   int  reserve(Buf<T>&, size_t count)                      0 = ok; contents are not preserved
+ *   int  zero(void* p, size_t bytes), int ones(void* p, size_t bytes)
+ *   int  upload(T* dst, const T* hostSrc, size_t count)
+ *   int  scan(const int* in, int* out, int n)                exclusive prefix sum
+ *   int  readInt(const int* p, int* hostValue), readULL(...) synchronising read-back of one value
+ *   int  forEach(int n, F f)                                 f(i) for i in [0, n), f copied by value
+ */
+#ifndef NBNXM_B200_GPUSEARCH_DRIVER_H
+#define NBNXM_B200_GPUSEARCH_DRIVER_H
+
+#include <cmath>
+#include <cstddef>
+
+#include "gpusearch_bodies.h"
+
+namespace nbs
+{
+
+/* pass functors (arguments by value: they become kernel parameters) */
+struct FSlotOfAtom
+{
+    const int* atomIndex;
+    int*       slotOfAtom;
+    NBS_HD void operator()(int slot) const
+    {
+        const int a = atomIndex[slot];
+        if (a >= 0)
+        {
+            slotOfAtom[a] = slot;
+        }
+    }
+};
+struct FClusterBB
+{
+    Grid g;
+    NBS_HD void operator()(int i) const { clusterBoundingBox(g, i); }
+};
+struct FBinBB
+{
+    Grid g;
+    NBS_HD void operator()(int i) const { binBoundingBox(g, i); }
+};
+/* entry passes run slot-major (neighbouring threads: neighbouring bins, same shift) so that warps stay coherent;
+ * the arrays are indexed bin-major, the order of the list */
+template<bool WRITE>
+struct FEntryBinPairs
+{
+    Grid   g;
+    Params p;
+    Work   w;
+    int    numIBins;
+    NBS_HD void operator()(int i) const { entryBinPairs<WRITE>(g, p, w, (i % numIBins) * c_numSlots + i / numIBins); }
+};
+struct FBinPairMask
+{
+    Grid   g;
+    Params p;
+    Work   w;
+    NBS_HD void operator()(int i) const { binPairMask(g, p, w, i); }
+};
+struct FEntryCountJ
+{
+    Work w;
+    NBS_HD void operator()(int i) const { entryCountJ(w, i); }
+};
+struct FEntryCountSci
+{
+    Params p;
+    Work   w;
+    NBS_HD void operator()(int i) const { entryCountSci(p, w, i); }
+};
+struct FEntryFill
+{
+    Grid   g;
+    Params p;
+    Work   w;
+    NBS_HD void operator()(int i) const { entryFill(g, p, w, i); }
+};
+template<bool FILL>
+struct FEntryExclusions
+{
+    Grid   g;
+    Params p;
+    Work   w;
+    NBS_HD void operator()(int i) const { entryExclusions<FILL>(g, p, w, i); }
+};
+struct FAssignExclIndex
+{
+    Work w;
+    NBS_HD void operator()(int i) const { assignExclIndex(w, i); }
+};
+
+template<typename BE>
+struct SearchState
+{
+    template<typename T>
+    using Buf = typename BE::template Buf<T>;
+
+    Grid g{};
+    bool haveGrid = false;
+    int  numExclAtoms = 0;
+
+    Buf<int> colFirstBin, atomIndex, slotOfAtom, clCount, exclIndex, exclAtoms;
+    Buf<BB>  clBB, binBB;
+
+    Buf<int>           entryNumBinPairs, entryBinPairOff, binPairJ, binPairEntry;
+    Buf<unsigned char> binPairMask;
+    Buf<int>           entryNumJ, entryGroups, entryCjOff, entryNumSci, entrySciOff, entryNonEmpty, entryCompactOff;
+    Buf<int>           compactEntry, exclFlag, exclOff;
+    Buf<unsigned long long> numClusterPairs;
+
+    /* the list built last */
+    Buf<nbnxm_b200_sci_t>       sci;
+    Buf<nbnxm_b200_cj_packed_t> cjp;
+    Buf<nbnxm_b200_excl_t>      excl;
+    int       nsci = 0, ncjp = 0, nexcl = 0, numBinPairs = 0, numEntries = 0;
+    long long numClusterPairsHost = 0;
+};
+
+#define NBS_TRY(call)        \
+    do                       \
+    {                        \
+        if ((call) != 0)     \
+        {                    \
+            return 1;        \
+        }                    \
+    } while (0)
+
+/* grid description from the host gridder (putAtomsOnGrid): columns, atom order, topology exclusions */
+template<typename BE>
+int setGrid(BE& be, SearchState<BE>& st, const float* box, int ncx, int ncy, const int* firstBinOfColumn,
+            const int* atomIndex, int nbins, int natoms, const int* exclIndex, const int* exclAtoms)
+{
+    const int ncol   = ncx * ncy;
+    const int nslots = nbins * c_binAtoms;
+    for (int d = 0; d < 3; d++)
+    {
+        st.g.box[d] = box[d];
+    }
+    st.g.cellSize[0] = box[0] / ncx;
+    st.g.cellSize[1] = box[1] / ncy;
+    st.g.ncx         = ncx;
+    st.g.ncy         = ncy;
+    st.g.nbins       = nbins;
+    st.g.natoms      = natoms;
+    NBS_TRY(be.reserve(st.colFirstBin, ncol + 1));
+    NBS_TRY(be.reserve(st.atomIndex, nslots));
+    NBS_TRY(be.reserve(st.slotOfAtom, natoms));
+    NBS_TRY(be.reserve(st.clCount, size_t(nbins) * c_binCl));
+    NBS_TRY(be.reserve(st.clBB, size_t(nbins) * c_binCl));
+    NBS_TRY(be.reserve(st.binBB, nbins));
+    NBS_TRY(be.upload(st.colFirstBin.p, firstBinOfColumn, ncol + 1));
+    NBS_TRY(be.upload(st.atomIndex.p, atomIndex, nslots));
+    NBS_TRY(be.ones(st.slotOfAtom.p, sizeof(int) * natoms)); /* -1 */
+    st.g.colFirstBin = st.colFirstBin.p;
+    st.g.atomIndex   = st.atomIndex.p;
+    st.g.slotOfAtom  = st.slotOfAtom.p;
+    st.g.clCount     = st.clCount.p;
+    st.g.clBB        = st.clBB.p;
+    st.g.binBB       = st.binBB.p;
+    st.g.exclIndex   = nullptr;
+    st.g.exclAtoms   = nullptr;
+    if (exclIndex != nullptr && exclAtoms != nullptr)
+    {
+        const int nex = exclIndex[natoms];
+        NBS_TRY(be.reserve(st.exclIndex, natoms + 1));
+        NBS_TRY(be.reserve(st.exclAtoms, nex > 0 ? nex : 1));
+        NBS_TRY(be.upload(st.exclIndex.p, exclIndex, natoms + 1));
+        if (nex > 0)
+        {
+            NBS_TRY(be.upload(st.exclAtoms.p, exclAtoms, nex));
+        }
+        st.g.exclIndex = st.exclIndex.p;
+        st.g.exclAtoms = st.exclAtoms.p;
+    }
+    NBS_TRY(be.forEach(nslots, FSlotOfAtom{ st.atomIndex.p, st.slotOfAtom.p }));
+    st.haveGrid = true;
+    return 0;
+}
+
+/* constructPairlist (pairlist.cpp:4056) for the GPU layout from coordinates xq in nbat order; arguments as
+ * nbnxm_b200_pairlist_build (include/nbnxm_b200_search.h) */
+template<typename BE>
+int buildPairlist(BE& be, SearchState<BE>& st, const XQ* xq, float rlist, int minSci, int binBegin, int binEnd, int jBinLo,
+                  int jBinHi, int interZone, int requiredTx)
+{
+    Grid& g = st.g;
+    g.xq    = xq;
+    Params p;
+    p.rlist = rlist;
+    p.rl2   = rlist * rlist;
+    p.rbb2  = bbOnlyDistance2(g.cellSize, rlist);
+    p.binBegin      = binBegin;
+    p.binEnd        = binEnd;
+    p.jBinLo        = jBinLo;
+    p.jBinHi        = jBinHi;
+    p.interZone     = interZone;
+    p.requiredTx    = requiredTx;
+    p.maxGroups     = 1 << 30;
+
+    const int numIBins = binEnd - binBegin;
+    const int nE       = numIBins * c_numSlots;
+    st.nsci = st.ncjp = st.numBinPairs = st.numEntries = 0;
+    st.nexcl               = 1;
+    st.numClusterPairsHost = 0;
+
+    /* pass 0: bounding boxes of the current coordinates */
+    NBS_TRY(be.forEach(g.nbins * c_binCl, FClusterBB{ g }));
+    NBS_TRY(be.forEach(g.nbins, FBinBB{ g }));
+
+    NBS_TRY(be.reserve(st.entryNumBinPairs, nE + 1));
+    NBS_TRY(be.reserve(st.entryBinPairOff, nE + 1));
+    NBS_TRY(be.reserve(st.entryNumJ, nE + 1));
+    NBS_TRY(be.reserve(st.entryGroups, nE + 1));
+    NBS_TRY(be.reserve(st.entryCjOff, nE + 1));
+    NBS_TRY(be.reserve(st.entryNumSci, nE + 1));
+    NBS_TRY(be.reserve(st.entrySciOff, nE + 1));
+    NBS_TRY(be.reserve(st.entryNonEmpty, nE + 1));
+    NBS_TRY(be.reserve(st.entryCompactOff, nE + 1));
+    NBS_TRY(be.reserve(st.numClusterPairs, 1));
+    NBS_TRY(be.zero(st.entryNumBinPairs.p, sizeof(int) * (nE + 1)));
+    NBS_TRY(be.zero(st.entryGroups.p, sizeof(int) * (nE + 1)));
+    NBS_TRY(be.zero(st.entryNumSci.p, sizeof(int) * (nE + 1)));
+    NBS_TRY(be.zero(st.entryNonEmpty.p, sizeof(int) * (nE + 1)));
+    NBS_TRY(be.zero(st.numClusterPairs.p, sizeof(unsigned long long)));
+
+    Work w{};
+    w.entryNumBinPairs = st.entryNumBinPairs.p;
+    w.entryBinPairOff  = st.entryBinPairOff.p;
+    w.entryNumJ        = st.entryNumJ.p;
+    w.entryGroups      = st.entryGroups.p;
+    w.entryCjOff       = st.entryCjOff.p;
+    w.entryNumSci      = st.entryNumSci.p;
+    w.entrySciOff      = st.entrySciOff.p;
+    w.entryNonEmpty    = st.entryNonEmpty.p;
+    w.entryCompactOff  = st.entryCompactOff.p;
+    w.numClusterPairs  = st.numClusterPairs.p;
+
+    /* excl entry 0: the shared all-ones mask */
+    auto finishEmpty = [&]() -> int {
+        NBS_TRY(be.reserve(st.excl, 1));
+        NBS_TRY(be.ones(st.excl.p, sizeof(nbnxm_b200_excl_t)));
+        return 0;
+    };
+    if (nE == 0)
+    {
+        return finishEmpty();
+    }
+
+    /* pass 1: bin pairs per entry slot, scan, pass 2: list them */
+    NBS_TRY(be.forEach(nE, FEntryBinPairs<false>{ g, p, w, numIBins }));
+    NBS_TRY(be.scan(w.entryNumBinPairs, w.entryBinPairOff, nE + 1));
+    NBS_TRY(be.readInt(w.entryBinPairOff + nE, &st.numBinPairs));
+    if (st.numBinPairs == 0)
+    {
+        return finishEmpty();
+    }
+    if (st.numBinPairs >= (1 << 28))
+    {
+        return be.fail("pair search: too many bin pairs for 32-bit item indices");
+    }
+    NBS_TRY(be.reserve(st.binPairJ, st.numBinPairs));
+    NBS_TRY(be.reserve(st.binPairEntry, st.numBinPairs));
+    NBS_TRY(be.reserve(st.binPairMask, size_t(st.numBinPairs) * c_binCl));
+    w.binPairJ     = st.binPairJ.p;
+    w.binPairEntry = st.binPairEntry.p;
+    w.binPairMask  = st.binPairMask.p;
+    NBS_TRY(be.forEach(nE, FEntryBinPairs<true>{ g, p, w, numIBins }));
+
+    /* pass 3: cluster-pair masks */
+    NBS_TRY(be.forEach(st.numBinPairs * c_binCl, FBinPairMask{ g, p, w }));
+
+    /* pass 4: sizes */
+    NBS_TRY(be.forEach(nE, FEntryCountJ{ w }));
+    NBS_TRY(be.scan(w.entryGroups, w.entryCjOff, nE + 1));
+    NBS_TRY(be.readInt(w.entryCjOff + nE, &st.ncjp));
+    NBS_TRY(be.scan(w.entryNonEmpty, w.entryCompactOff, nE + 1));
+    NBS_TRY(be.readInt(w.entryCompactOff + nE, &st.numEntries));
+    {
+        unsigned long long ncp = 0;
+        NBS_TRY(be.readULL(w.numClusterPairs, &ncp));
+        st.numClusterPairsHost = (long long)ncp;
+    }
+    if (st.ncjp == 0)
+    {
+        return finishEmpty();
+    }
+    if (st.ncjp >= (1 << 29))
+    {
+        return be.fail("pair search: too many cjPacked groups for 32-bit item indices");
+    }
+    /* split long i-entries so that about minSci entries exist (split_sci_entry, pairlist.cpp:1769-1879) */
+    if (minSci > 0)
+    {
+        const int mg = (st.ncjp + minSci - 1) / minSci;
+        p.maxGroups  = mg > 1 ? mg : 1;
+    }
+    NBS_TRY(be.forEach(nE, FEntryCountSci{ p, w }));
+    NBS_TRY(be.scan(w.entryNumSci, w.entrySciOff, nE + 1));
+    NBS_TRY(be.readInt(w.entrySciOff + nE, &st.nsci));
+
+    /* pass 5: the list */
+    NBS_TRY(be.reserve(st.sci, st.nsci));
+    NBS_TRY(be.reserve(st.cjp, st.ncjp));
+    NBS_TRY(be.reserve(st.compactEntry, st.numEntries));
+    NBS_TRY(be.reserve(st.exclFlag, size_t(st.ncjp) * 2 + 1));
+    NBS_TRY(be.reserve(st.exclOff, size_t(st.ncjp) * 2 + 1));
+    NBS_TRY(be.zero(st.exclFlag.p, sizeof(int) * (size_t(st.ncjp) * 2 + 1)));
+    w.sci          = st.sci.p;
+    w.cjp          = st.cjp.p;
+    w.compactEntry = st.compactEntry.p;
+    w.exclFlag     = st.exclFlag.p;
+    w.exclOff      = st.exclOff.p;
+    NBS_TRY(be.forEach(nE, FEntryFill{ g, p, w }));
+
+    /* passes 6 / 7: exclusion masks */
+    int numExclExtra = 0;
+    NBS_TRY(be.forEach(st.numEntries * c_binAtoms, FEntryExclusions<false>{ g, p, w }));
+    NBS_TRY(be.scan(w.exclFlag, w.exclOff, st.ncjp * 2 + 1));
+    NBS_TRY(be.readInt(w.exclOff + st.ncjp * 2, &numExclExtra));
+    st.nexcl = 1 + numExclExtra;
+    NBS_TRY(be.reserve(st.excl, st.nexcl));
+    NBS_TRY(be.ones(st.excl.p, sizeof(nbnxm_b200_excl_t) * st.nexcl));
+    w.excl = st.excl.p;
+    if (numExclExtra > 0)
+    {
+        NBS_TRY(be.forEach(st.ncjp * 2, FAssignExclIndex{ w }));
+        NBS_TRY(be.forEach(st.numEntries * c_binAtoms, FEntryExclusions<true>{ g, p, w }));
+    }
+    return 0;
+}
+
+} // namespace nbs
+
+#endif

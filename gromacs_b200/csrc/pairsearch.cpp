@@ -20,33 +20,20 @@
 #endif
 
 #include "../../include/nbnxm_b200_search.h"
+#include "gpusearch_bodies.h"
 
 namespace
 {
+
+/* distance arithmetic shared with the GPU builder (explicit fmaf), so that both produce the same list */
+using nbs::BB;
+using nbs::bbDist2;
 
 constexpr int   c_cl       = 8;  // atoms per cluster
 constexpr int   c_binCl    = 8;  // clusters per bin
 constexpr int   c_binAtoms = 64; // atoms per bin
 constexpr int   c_central  = 22;
 constexpr float c_farAway  = -1000000.0f; // filler coordinate, atomdata.cpp:171
-
-struct BB
-{
-    float lo[3], hi[3];
-};
-
-inline float bbDist2(const BB& a, const float* sh, const BB& b)
-{
-    float d2 = 0;
-    for (int d = 0; d < 3; d++)
-    {
-        const float dl = (a.lo[d] + sh[d]) - b.hi[d];
-        const float dh = b.lo[d] - (a.hi[d] + sh[d]);
-        const float dm = std::max(std::max(dl, dh), 0.0f);
-        d2 += dm * dm;
-    }
-    return d2;
-}
 
 struct ThreadList
 {
@@ -304,10 +291,7 @@ int nbnxm_b200_pairlist_build(nbnxm_b200_grid_t* g, float rlist, const int* excl
     const float rl2 = rlist * rlist;
     /* bounding-box-only acceptance distance: rlist minus half the average x/y diagonal of a cluster
      * (pairlist.cpp: boundingbox_only_distance2) */
-    const float bbx  = 0.5f * g->cellSize[0];
-    const float bby  = 0.5f * g->cellSize[1];
-    const float rbb  = std::max(0.0f, rlist - 0.5f * std::sqrt(bbx * bbx + bby * bby));
-    const float rbb2 = rbb * rbb;
+    const float rbb2 = nbs::bbOnlyDistance2(g->cellSize, rlist);
     const int   ncol = g->ncx * g->ncy;
 
     std::vector<int> colOfBin(g->nbins);
@@ -397,7 +381,7 @@ int nbnxm_b200_pairlist_build(nbnxm_b200_grid_t* g, float rlist, const int* excl
                                             {
                                                 const float* xj = &g->xs[3 * (gcj * c_cl + j)];
                                                 const float  dx = px - xj[0], dy = py - xj[1], dz = pz - xj[2];
-                                                if (dx * dx + dy * dy + dz * dz < rl2)
+                                                if (nbs::dist2(dx, dy, dz) < rl2)
                                                 {
                                                     in = true;
                                                     break;

@@ -1,0 +1,131 @@
+/* TEST INFRASTRUCTURE — host-loop backend for the pass sequence of the GPU pair-list builder.
+ *
+ * Runs gromacs_b200/csrc/gpusearch_driver.h + gpusearch_bodies.h (the exact bodies the CUDA kernels wrap) on the CPU,
+ * one loop iteration per CUDA thread, so that tests/test_gpusearch_emu.py can check the search logic against the
+ * independent host builder (pairsearch.cpp) without a GPU.  Nothing in the product links or loads this file.
+ */
+#include <cstdarg>
+#include <cstdio>
+#include <cstdlib>
+#include <cstring>
+
+#include "../../gromacs_b200/csrc/gpusearch_driver.h"
+
+namespace
+{
+
+struct HostBackend
+{
+    template<typename T>
+    struct Buf
+    {
+        T*     p     = nullptr;
+        size_t n     = 0;
+        size_t alloc = 0;
+    };
+    template<typename T>
+    int reserve(Buf<T>& b, size_t count)
+    {
+        b.n = count;
+        if (count > b.alloc)
+        {
+            std::free(b.p);
+            b.alloc = count + count / 5 + 64;
+            b.p     = static_cast<T*>(std::malloc(b.alloc * sizeof(T)));
+            /* poison, so that a pass reading what no pass wrote shows up */
+            std::memset(static_cast<void*>(b.p), 0x5a, b.alloc * sizeof(T));
+        }
+        return b.p == nullptr;
+    }
+    int zero(void* p, size_t bytes)
+    {
+        std::memset(p, 0, bytes);
+        return 0;
+    }
+    int ones(void* p, size_t bytes)
+    {
+        std::memset(p, 0xff, bytes);
+        return 0;
+    }
+    template<typename T>
+    int upload(T* dst, const T* src, size_t count)
+    {
+        std::memcpy(dst, src, count * sizeof(T));
+        return 0;
+    }
+    int scan(const int* in, int* out, int n)
+    {
+        int sum = 0;
+        for (int i = 0; i < n; i++)
+        {
+            const int v = in[i];
+            out[i]      = sum;
+            sum += v;
+        }
+        return 0;
+    }
+    int readInt(const int* p, int* v)
+    {
+        *v = *p;
+        return 0;
+    }
+    int readULL(const unsigned long long* p, unsigned long long* v)
+    {
+        *v = *p;
+        return 0;
+    }
+    template<typename F>
+    int forEach(int n, F f)
+    {
+        /* reversed order: no pass may depend on the order its items run in */
+        for (int i = n - 1; i >= 0; i--)
+        {
+            f(i);
+        }
+        return 0;
+    }
+    int fail(const char* msg)
+    {
+        std::fprintf(stderr, "search_emu: %s\n", msg);
+        return 1;
+    }
+};
+
+HostBackend                   g_be;
+nbs::SearchState<HostBackend> g_st;
+
+} // namespace
+
+extern "C" {
+
+int search_emu_set_grid(const float* box, int ncx, int ncy, const int* first_bin_of_column, const int* atom_index, int nbins,
+                        int natoms, const int* excl_index, const int* excl_atoms)
+{
+    return nbs::setGrid(g_be, g_st, box, ncx, ncy, first_bin_of_column, atom_index, nbins, natoms, excl_index, excl_atoms);
+}
+
+int search_emu_build(const float* xq, float rlist, int min_sci, int bin_begin, int bin_end, int j_bin_lo, int j_bin_hi,
+                     int inter_zone, int required_tx, int* sizes, long long* ncluster_pairs)
+{
+    if (nbs::buildPairlist(g_be, g_st, reinterpret_cast<const nbs::XQ*>(xq), rlist, min_sci, bin_begin, bin_end, j_bin_lo,
+                           j_bin_hi, inter_zone, required_tx))
+    {
+        return 1;
+    }
+    sizes[0]        = g_st.nsci;
+    sizes[1]        = g_st.ncjp;
+    sizes[2]        = g_st.nexcl;
+    sizes[3]        = g_st.numBinPairs;
+    *ncluster_pairs = g_st.numClusterPairsHost;
+    return 0;
+}
+
+int search_emu_copy(nbnxm_b200_sci_t* sci, nbnxm_b200_cj_packed_t* cjp, nbnxm_b200_excl_t* excl)
+{
+    if (g_st.nsci) std::memcpy(sci, g_st.sci.p, sizeof(*sci) * g_st.nsci);
+    if (g_st.ncjp) std::memcpy(cjp, g_st.cjp.p, sizeof(*cjp) * g_st.ncjp);
+    std::memcpy(excl, g_st.excl.p, sizeof(*excl) * g_st.nexcl);
+    return 0;
+}
+
+} // extern "C"

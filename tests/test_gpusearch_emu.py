@@ -1,0 +1,136 @@
+"""CPU tests of the GPU pair-list builder's passes (gromacs_b200/csrc/gpusearch_bodies.h + gpusearch_driver.h), run
+through the host-loop backend of tests/kernel_emu (one loop iteration per CUDA thread, items in reversed order, work
+buffers poisoned): the list must equal, entry for entry, the one the independent host builder
+(gromacs_b200/csrc/pairsearch.cpp, one thread) makes from the same grid — sci and cjPacked arrays bit for bit, the
+exclusion masks after expansion per (cjPacked, half), since the two allocate nbnxm_excl_t entries in a different
+order.  The host builder itself is checked against brute force and the reference's lists in test_pairsearch.py."""
+import ctypes as C
+import os
+import subprocess
+
+import numpy as np
+import pytest
+
+from util import load_golden
+
+HERE = os.path.dirname(os.path.abspath(__file__))
+
+
+@pytest.fixture(scope="module")
+def emu():
+    subprocess.run(["make", "-s", "-C", os.path.join(HERE, "kernel_emu")], check=True)
+    return C.CDLL(os.path.join(HERE, "kernel_emu", "libsearch_emu.so"))
+
+
+def _p(a, ct):
+    return None if a is None else a.ctypes.data_as(C.POINTER(ct))
+
+
+def emu_pairlist(emu, grid, xq, rlist, ei, ea, min_sci=0, bins=None, j_bins=None, inter_zone=False, required_tx=0):
+    box = np.ascontiguousarray(grid.box, np.float32)
+    ei = None if ei is None else np.ascontiguousarray(ei, np.int32)
+    ea = None if ea is None else np.ascontiguousarray(ea, np.int32)
+    assert emu.search_emu_set_grid(_p(box, C.c_float), grid.ncx, grid.ncy, _p(grid.first_bin_of_column, C.c_int),
+                                   _p(grid.atom_index, C.c_int), grid.nbins, grid.natoms, _p(ei, C.c_int), _p(ea, C.c_int)) == 0
+    b0, b1 = bins if bins is not None else (0, grid.nbins)
+    j0, j1 = j_bins if j_bins is not None else (0, grid.nbins)
+    sizes = (C.c_int * 4)()
+    ncp = C.c_longlong()
+    xq = np.ascontiguousarray(xq, np.float32)
+    assert emu.search_emu_build(_p(xq, C.c_float), C.c_float(rlist), min_sci, b0, b1, j0, j1, int(inter_zone), required_tx,
+                                sizes, C.byref(ncp)) == 0
+    sci = np.zeros((sizes[0], 4), np.int32)
+    cjp = np.zeros((sizes[1], 8), np.uint32)
+    excl = np.zeros((sizes[2], 32), np.uint32)
+    emu.search_emu_copy(_p(sci, C.c_int), _p(cjp, C.c_uint32), _p(excl, C.c_uint32))
+    return sci, cjp, excl, ncp.value
+
+
+def expanded_excl(cjp, excl):
+    """exclusion words per (cjPacked, half): independent of how excl entries were numbered"""
+    cjp = np.ascontiguousarray(cjp).view(np.uint32).reshape(-1, 8)
+    return excl[cjp[:, 5].astype(np.int64)], excl[cjp[:, 7].astype(np.int64)]
+
+
+def assert_same_list(a, b):
+    sci_a, cjp_a, excl_a = a
+    sci_b, cjp_b, excl_b = b
+    sci_a = np.ascontiguousarray(sci_a).view(np.int32).reshape(-1, 4)
+    sci_b = np.ascontiguousarray(sci_b).view(np.int32).reshape(-1, 4)
+    cjp_a = np.ascontiguousarray(cjp_a).view(np.uint32).reshape(-1, 8)
+    cjp_b = np.ascontiguousarray(cjp_b).view(np.uint32).reshape(-1, 8)
+    assert sci_a.shape == sci_b.shape and np.array_equal(sci_a, sci_b)
+    assert cjp_a.shape == cjp_b.shape
+    assert np.array_equal(cjp_a[:, [0, 1, 2, 3, 4, 6]], cjp_b[:, [0, 1, 2, 3, 4, 6]])       # cj[4], imask of both halves
+    assert np.array_equal(cjp_a[:, [5, 7]] != 0, cjp_b[:, [5, 7]] != 0)                      # who has exclusions
+    assert excl_a.shape == excl_b.shape and np.all(excl_a[0] == 0xffffffff)
+    for xa, xb in zip(expanded_excl(cjp_a, excl_a), expanded_excl(cjp_b, excl_b)):
+        assert np.array_equal(xa, xb)
+    # every exclusion entry but the shared entry 0 is used exactly once
+    used = np.sort(cjp_a[:, [5, 7]][cjp_a[:, [5, 7]] != 0])
+    assert np.array_equal(used, np.arange(1, excl_a.shape[0]))
+
+
+def host_grid(d, nthreads=1):
+    from gromacs_b200.pairsearch import Grid
+    grid = Grid(d["sys_box"], d["sys_x"], nthreads=nthreads)
+    nt = int(d["nbat_ntypes"][0])
+    nbat = grid.atomdata(d["sys_x"], d["sys_q"], d["sys_type"], d["nbat_nbfp"], nt, nbfp_comb=d["nbat_nbfp_comb"])
+    return grid, nbat
+
+
+@pytest.mark.parametrize("case,rlist,min_sci", [("test243_ewald_cutnone", 0.9, 0), ("test243_ewald_cutnone", 0.93, 60),
+                                                ("bench1_ewald_cutnone", 1.0, 0), ("bench1_ewald_cutnone", 1.05, 500),
+                                                ("bench1_ewald_cutnone", 0.7, 3000)])
+def test_passes_give_the_host_builders_list(emu, case, rlist, min_sci):
+    d = load_golden(case)
+    grid, nbat = host_grid(d)
+    ref = grid.pairlist(rlist, d["sys_excl_index"], d["sys_excl_atoms"], min_sci=min_sci)
+    sci, cjp, excl, ncp = emu_pairlist(emu, grid, nbat.xq, rlist, d["sys_excl_index"], d["sys_excl_atoms"], min_sci=min_sci)
+    assert_same_list((sci, cjp, excl), (ref.sci, ref.cjPacked, ref.excl))
+    assert ncp == ref.nci_tot
+    assert cjp.shape[0] > 0 and excl.shape[0] > 1
+
+
+def test_passes_without_topology_exclusions(emu):
+    d = load_golden("bench1_ewald_cutnone")
+    grid, nbat = host_grid(d)
+    ref = grid.pairlist(0.9)
+    got = emu_pairlist(emu, grid, nbat.xq, 0.9, None, None)
+    assert_same_list(got[:3], (ref.sci, ref.cjPacked, ref.excl))
+
+
+@pytest.mark.parametrize("nslabs", [2, 3])
+def test_passes_build_slab_and_halo_lists(emu, nslabs):
+    """bin ranges and the inter-zone mode (home x-slab against its +x neighbour's halo, one x shift)"""
+    from gromacs_b200.pairsearch import Grid
+    from gromacs_b200.slabs import slab_bin_ranges
+    d = load_golden("bench1_ewald_cutnone")
+    x = np.concatenate([d["sys_x"] + np.array([i * d["sys_box"][0], 0, 0], np.float32) for i in range(4)])
+    n0 = d["sys_x"].shape[0]
+    box = d["sys_box"] * np.array([4, 1, 1], np.float32)
+    ei = np.concatenate([d["sys_excl_index"][:-1] + i * d["sys_excl_atoms"].shape[0] for i in range(4)]
+                        + [[4 * d["sys_excl_atoms"].shape[0]]]).astype(np.int32)
+    ea = np.concatenate([d["sys_excl_atoms"] + i * n0 for i in range(4)]).astype(np.int32)
+    grid = Grid(box, x, nthreads=1)
+    nt = int(d["nbat_ntypes"][0])
+    nbat = grid.atomdata(x, np.tile(d["sys_q"], 4), np.tile(d["sys_type"], 4), d["nbat_nbfp"], nt, nbfp_comb=d["nbat_nbfp_comb"])
+    rlist = 1.0
+    for r in range(nslabs):
+        home, halo, tx = slab_bin_ranges(grid, nslabs, r, rlist)
+        ref = grid.pairlist(rlist, ei, ea, bins=home, j_bins=home, min_sci=200)
+        got = emu_pairlist(emu, grid, nbat.xq, rlist, ei, ea, bins=home, j_bins=home, min_sci=200)
+        assert_same_list(got[:3], (ref.sci, ref.cjPacked, ref.excl))
+        ref = grid.pairlist(rlist, ei, ea, bins=home, j_bins=halo, inter_zone=True, required_tx=tx)
+        got = emu_pairlist(emu, grid, nbat.xq, rlist, ei, ea, bins=home, j_bins=halo, inter_zone=True, required_tx=tx)
+        assert_same_list(got[:3], (ref.sci, ref.cjPacked, ref.excl))
+        assert got[0].shape[0] > 0
+
+
+def test_passes_on_an_empty_range(emu):
+    d = load_golden("test243_ewald_cutnone")
+    grid, nbat = host_grid(d)
+    sci, cjp, excl, ncp = emu_pairlist(emu, grid, nbat.xq, 0.9, None, None, bins=(0, 0))
+    assert sci.shape[0] == 0 and cjp.shape[0] == 0 and excl.shape[0] == 1 and np.all(excl == 0xffffffff) and ncp == 0
+    sci, cjp, excl, ncp = emu_pairlist(emu, grid, nbat.xq, 0.9, None, None, j_bins=(0, 0))
+    assert sci.shape[0] == 0 and cjp.shape[0] == 0 and excl.shape[0] == 1
