@@ -23,6 +23,8 @@ void launch_sci_sort(const PairlistDev& pl, cudaStream_t stream);
 void launch_count_pairs(const PairlistDev& pl, cudaStream_t stream);
 void launch_x_to_nbat_x(float4* xq, const float* x, const int* atomIndex, int first, int n, cudaStream_t s);
 void launch_f4_to_f3(const float4* f4, float* f3, int first, int n, cudaStream_t s);
+void launch_reduce_f(const float4* f4, const float* rvecToAdd, float* fTotal, const int* cell, int atomStart, int n, bool accumulate,
+                     cudaStream_t s);
 void launch_pack_xq(const float4* xq, const int* index, int n, const float* shift, float4* out, cudaStream_t s);
 void launch_copy4(const float4* in, float4* out, int n, cudaStream_t s);
 void launch_unpack_add_f(float4* f4, const int* index, int n, const float4* in, cudaStream_t s);
@@ -285,7 +287,7 @@ int nbnxm_b200_free(nbnxm_b200_t* nb)
     collectTimings(nb);
     nb->xq.release(); nb->f4.release(); nb->f3.release(); nb->atomType.release(); nb->ljComb.release();
     nb->shiftVec.release(); nb->fshift.release(); nb->energy.release(); nb->nbfp.release();
-    nb->nbfpComb.release(); nb->coulombTab.release(); nb->atomIndex.release(); nb->packedConsts.release();
+    nb->nbfpComb.release(); nb->coulombTab.release(); nb->atomIndex.release(); nb->packedConsts.release(); nb->cell.release();
     for (PairList& pl : nb->plist)
     {
         pl.sci.release(); pl.sciSorted.release(); pl.sciCount.release(); pl.sciHistogram.release();
@@ -328,9 +330,8 @@ int nbnxm_b200_update_params(nbnxm_b200_t* nb, const nbnxm_b200_params_t* params
     return fillParamsDev(nb);
 }
 
-int nbnxm_b200_init_pairlist(nbnxm_b200_t* nb, int iloc, const nbnxm_b200_sci_t* sci, int nsci,
-                             const nbnxm_b200_cj_packed_t* cj_packed, int ncj_packed, const nbnxm_b200_excl_t* excl,
-                             int nexcl, int na_ci)
+static int initPairlist(nbnxm_b200_t* nb, int iloc, const nbnxm_b200_sci_t* sci, int nsci, const nbnxm_b200_cj_packed_t* cj_packed,
+                        int ncj_packed, const nbnxm_b200_excl_t* excl, int nexcl, int na_ci, cudaMemcpyKind kind)
 {
     if (!nb || iloc < 0 || iloc > 1) return fail("nbnxm_b200_init_pairlist: bad argument");
     if (nsci < 0 || ncj_packed < 0 || nexcl < 0) return fail("nbnxm_b200_init_pairlist: negative size");
@@ -345,7 +346,7 @@ int nbnxm_b200_init_pairlist(nbnxm_b200_t* nb, int iloc, const nbnxm_b200_sci_t*
     pl.naCi = na_ci;
     /* buffers may still be in use by the previous list's kernels */
     CU(cudaStreamSynchronize(st));
-    beginRegion(nb, 8, st);
+    if (kind == cudaMemcpyHostToDevice) beginRegion(nb, 8, st);
     pl.numSci = nsci;
     CU(pl.sci.reserve(nsci));
     CU(pl.sciSorted.reserve(nsci));
@@ -358,27 +359,41 @@ int nbnxm_b200_init_pairlist(nbnxm_b200_t* nb, int iloc, const nbnxm_b200_sci_t*
     CU(pl.excl.reserve(nexcl > 0 ? nexcl : 1));
     if (nsci > 0)
     {
-        CU(cudaMemcpyAsync(pl.sci.p, sci, sizeof(*sci) * nsci, cudaMemcpyHostToDevice, st));
-        CU(cudaMemcpyAsync(pl.sciSorted.p, sci, sizeof(*sci) * nsci, cudaMemcpyHostToDevice, st));
+        CU(cudaMemcpyAsync(pl.sci.p, sci, sizeof(*sci) * nsci, kind, st));
+        CU(cudaMemcpyAsync(pl.sciSorted.p, sci, sizeof(*sci) * nsci, kind, st));
         CU(cudaMemsetAsync(pl.rollingPart.p, 0, sizeof(int) * nsci, st));
         CU(cudaMemsetAsync(pl.sciCount.p, 0, sizeof(int) * nsci, st));
     }
     CU(cudaMemsetAsync(pl.sciHistogram.p, 0, sizeof(int) * (c_sciHistogramSize + 1), st));
     if (ncj_packed > 0)
     {
-        CU(cudaMemcpyAsync(pl.cjPacked.p, cj_packed, sizeof(*cj_packed) * ncj_packed, cudaMemcpyHostToDevice, st));
+        CU(cudaMemcpyAsync(pl.cjPacked.p, cj_packed, sizeof(*cj_packed) * ncj_packed, kind, st));
         CU(cudaMemsetAsync(pl.imaskOuter.p, 0, sizeof(unsigned int) * 2 * ncj_packed, st));
     }
     if (nexcl > 0)
     {
-        CU(cudaMemcpyAsync(pl.excl.p, excl, sizeof(*excl) * nexcl, cudaMemcpyHostToDevice, st));
+        CU(cudaMemcpyAsync(pl.excl.p, excl, sizeof(*excl) * nexcl, kind, st));
     }
-    endRegion(nb, st);
+    if (kind == cudaMemcpyHostToDevice) endRegion(nb, st);
     pl.haveFreshList   = true;
     pl.didPrune        = false;
     pl.didRollingPrune = false;
     pl.rollingNumParts = 0;
     return 0;
+}
+
+int nbnxm_b200_init_pairlist(nbnxm_b200_t* nb, int iloc, const nbnxm_b200_sci_t* sci, int nsci,
+                             const nbnxm_b200_cj_packed_t* cj_packed, int ncj_packed, const nbnxm_b200_excl_t* excl,
+                             int nexcl, int na_ci)
+{
+    return initPairlist(nb, iloc, sci, nsci, cj_packed, ncj_packed, excl, nexcl, na_ci, cudaMemcpyHostToDevice);
+}
+
+int nbnxm_b200_init_pairlist_device(nbnxm_b200_t* nb, int iloc, const nbnxm_b200_sci_t* d_sci, int nsci,
+                                    const nbnxm_b200_cj_packed_t* d_cj_packed, int ncj_packed, const nbnxm_b200_excl_t* d_excl,
+                                    int nexcl, int na_ci)
+{
+    return initPairlist(nb, iloc, d_sci, nsci, d_cj_packed, ncj_packed, d_excl, nexcl, na_ci, cudaMemcpyDeviceToDevice);
 }
 
 int nbnxm_b200_init_atomdata(nbnxm_b200_t* nb, int natoms, int natoms_local, const int* atom_type, const float* lj_comb)
@@ -519,6 +534,40 @@ int nbnxm_b200_x_to_nbat_x(nbnxm_b200_t* nb, const float* d_x, void* x_ready_eve
     }
     CU(cudaGetLastError());
     if (aloc == 0) nbnxm_b200_insert_nonlocal_dependency(nb, 0);
+    return 0;
+}
+
+int nbnxm_b200_init_reduce_f(nbnxm_b200_t* nb, const int* cell, int natoms)
+{
+    if (!nb || !cell || natoms < 0) return fail("nbnxm_b200_init_reduce_f: bad argument");
+    CU(cudaSetDevice(nb->device));
+    if (size_t(natoms) > nb->cell.alloc)
+    {
+        CU(cudaStreamSynchronize(nb->stream[0]));
+        CU(cudaStreamSynchronize(nb->stream[1]));
+    }
+    CU(nb->cell.reserve(natoms > 0 ? natoms : 1));
+    nb->numCells = natoms;
+    if (natoms > 0) CU(cudaMemcpyAsync(nb->cell.p, cell, sizeof(int) * natoms, cudaMemcpyHostToDevice, nb->stream[0]));
+    /* the caller's array may be pageable and short-lived */
+    CU(cudaStreamSynchronize(nb->stream[0]));
+    return 0;
+}
+
+int nbnxm_b200_reduce_f(nbnxm_b200_t* nb, float* d_f_total, const float* d_rvec_force_to_add, int atom_start, int num_atoms,
+                        int accumulate, void* stream)
+{
+    if (!nb || !d_f_total) return fail("nbnxm_b200_reduce_f: null argument");
+    if (atom_start < 0 || num_atoms < 0 || atom_start + num_atoms > nb->numCells)
+    {
+        return fail("nbnxm_b200_reduce_f: atom range [%d, %d) outside the %d atoms of nbnxm_b200_init_reduce_f", atom_start,
+                    atom_start + num_atoms, nb->numCells);
+    }
+    CU(cudaSetDevice(nb->device));
+    cudaStream_t st = stream ? static_cast<cudaStream_t>(stream) : nb->stream[0];
+    launch_reduce_f(nb->f4.p, d_rvec_force_to_add, d_f_total, nb->cell.p, atom_start, num_atoms, accumulate != 0, st);
+    if (num_atoms > 0) nb->launches++;
+    CU(cudaGetLastError());
     return 0;
 }
 

@@ -4,6 +4,9 @@
  *               (src/gromacs/nbnxm/cuda/nbnxm_gpu_buffer_ops_internal.cu:73-120)
  * f4_to_f3    : packs the 16-byte-aligned internal force accumulator into the float3 layout of
  *               NBAtomDataGpu::f (src/gromacs/nbnxm/gpu_types_common.h:178)
+ * reduce_f     : replaces reduceKernel (src/gromacs/mdlib/gpuforcereduction_impl_internal.cu:61-118): the nbat-order
+ *               forces gathered into the caller's atom-order rvec array, read straight from the float4 accumulator
+ *               (no f4 -> f3 pass in between)
  * halo pack / unpack : the x-slab analogue of packSendBufKernel / unpackRecvBufKernel
  *               (src/gromacs/domdec/gpuhaloexchange_impl_gpu.cu:82-137)
  * All are HBM-bound streaming kernels: one thread per atom, 16-byte accesses on the nbat side.
@@ -81,7 +84,51 @@ __global__ void __launch_bounds__(256)
     }
 }
 
+template<bool ADD_RVEC, bool ACCUMULATE>
+__global__ void __launch_bounds__(256) reduce_f_kernel(const float4* __restrict__ f4, const float* __restrict__ rvecToAdd,
+                                                       float* __restrict__ fTotal, const int* __restrict__ cell, int atomStart, int n)
+{
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i < n)
+    {
+        const int    a = atomStart + i;
+        const float4 v = f4[cell[a]];
+        float        x = v.x, y = v.y, z = v.z;
+        if (ACCUMULATE)
+        {
+            x += fTotal[3 * a];
+            y += fTotal[3 * a + 1];
+            z += fTotal[3 * a + 2];
+        }
+        if (ADD_RVEC)
+        {
+            x += rvecToAdd[3 * a];
+            y += rvecToAdd[3 * a + 1];
+            z += rvecToAdd[3 * a + 2];
+        }
+        fTotal[3 * a]     = x;
+        fTotal[3 * a + 1] = y;
+        fTotal[3 * a + 2] = z;
+    }
+}
+
 static inline int nblk(int n) { return (n + 255) / 256; }
+
+void launch_reduce_f(const float4* f4, const float* rvecToAdd, float* fTotal, const int* cell, int atomStart, int n, bool accumulate,
+                     cudaStream_t s)
+{
+    if (n <= 0) return;
+    if (rvecToAdd != nullptr)
+    {
+        if (accumulate) reduce_f_kernel<true, true><<<nblk(n), 256, 0, s>>>(f4, rvecToAdd, fTotal, cell, atomStart, n);
+        else reduce_f_kernel<true, false><<<nblk(n), 256, 0, s>>>(f4, rvecToAdd, fTotal, cell, atomStart, n);
+    }
+    else
+    {
+        if (accumulate) reduce_f_kernel<false, true><<<nblk(n), 256, 0, s>>>(f4, rvecToAdd, fTotal, cell, atomStart, n);
+        else reduce_f_kernel<false, false><<<nblk(n), 256, 0, s>>>(f4, rvecToAdd, fTotal, cell, atomStart, n);
+    }
+}
 
 void launch_x_to_nbat_x(float4* xq, const float* x, const int* atomIndex, int first, int n, cudaStream_t s)
 {

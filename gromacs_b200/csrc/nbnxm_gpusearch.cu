@@ -1,0 +1,320 @@
+/* GPU pair-list construction for the GPU layout (include/nbnxm_b200_search.h, nbnxm_b200_gpu_search_*).
+ *
+ * Builds, on the device and from the coordinates already resident in the handle (`xq`, nbat order), what the
+ * reference builds on the CPU and uploads every nstlist steps: nonbonded_verlet_t::constructPairlist
+ * (src/gromacs/nbnxm/pairlist.cpp:4056) -> gpu_init_pairlist (nbnxm_gpu_data_mgmt.cpp:739).  The list never
+ * visits the host (at 12.3 M atoms it is 0.65 GB of cjPacked plus 0.14 GB of exclusion masks).
+ *
+ * The search is a sequence of one-thread-per-item passes separated by prefix sums; the per-item bodies live in
+ * gpusearch_bodies.h, the sequence in gpusearch_driver.h (both shared with the CPU emulation of the tests).  This
+ * file provides the CUDA backend: the generic item kernel, a two-level exclusive scan, buffers and the C ABI.
+ * All passes are integer / bounding-box work bound by memory latency and divergence, not by FP32 throughput.
+ */
+#include "../../include/nbnxm_b200_search.h"
+#include "gpusearch_driver.h"
+#include "nbnxm_handle.cuh"
+
+namespace nbb
+{
+
+template<typename F>
+__global__ void __launch_bounds__(256) search_items_kernel(const F f, int n)
+{
+    const int i = blockIdx.x * 256 + threadIdx.x;
+    if (i < n)
+    {
+        f(i);
+    }
+}
+
+/* ---- exclusive prefix sum: tiles of 8192 ints per CTA (the block scan of nbnxm_sci_histogram_scan_kernel), tile
+ * totals scanned by the same kernel, then added back ---- */
+constexpr int c_scanTile = 8192;
+
+__global__ void __launch_bounds__(1024) search_scan_tile_kernel(const int* __restrict__ in, int* __restrict__ out, int n, int* __restrict__ tileSums)
+{
+    constexpr int  perThread = c_scanTile / 1024;
+    __shared__ int warpSums[32];
+    const int      t    = threadIdx.x;
+    const int      base = blockIdx.x * c_scanTile + t * perThread;
+    int            v[perThread];
+    int            sum = 0;
+#pragma unroll
+    for (int i = 0; i < perThread; i++)
+    {
+        v[i] = (base + i < n) ? in[base + i] : 0;
+        sum += v[i];
+    }
+    int incl = sum;
+#pragma unroll
+    for (int m = 1; m < 32; m <<= 1)
+    {
+        const int up = __shfl_up_sync(0xffffffffu, incl, m);
+        if ((t & 31) >= m) incl += up;
+    }
+    if ((t & 31) == 31) warpSums[t >> 5] = incl;
+    __syncthreads();
+    if (t < 32)
+    {
+        int w = warpSums[t];
+#pragma unroll
+        for (int m = 1; m < 32; m <<= 1)
+        {
+            const int up = __shfl_up_sync(0xffffffffu, w, m);
+            if (t >= m) w += up;
+        }
+        warpSums[t] = w;
+    }
+    __syncthreads();
+    int run = incl - sum + ((t >> 5) > 0 ? warpSums[(t >> 5) - 1] : 0);
+#pragma unroll
+    for (int i = 0; i < perThread; i++)
+    {
+        if (base + i < n) out[base + i] = run;
+        run += v[i];
+    }
+    if (t == 0 && tileSums != nullptr)
+    {
+        tileSums[blockIdx.x] = warpSums[31];
+    }
+}
+
+__global__ void __launch_bounds__(256) search_scan_add_kernel(int* __restrict__ out, int n, const int* __restrict__ tileOffsets)
+{
+    const int i = blockIdx.x * 256 + threadIdx.x;
+    if (i < n)
+    {
+        out[i] += tileOffsets[i / c_scanTile];
+    }
+}
+
+struct CudaSearchBackend
+{
+    template<typename T>
+    using Buf = DevBuf<T>;
+
+    cudaStream_t st       = nullptr;
+    long long    launches = 0;
+    DevBuf<int>  tileSums, tileOffsets;
+    int*         h_value = nullptr; /* pinned, 8 bytes */
+
+    int fail(const char* msg) { return nbb::fail("%s", msg); }
+
+    template<typename T>
+    int reserve(Buf<T>& b, size_t count)
+    {
+        if (count > b.alloc)
+        {
+            /* the buffer may still be read by kernels of the previous build */
+            CU(cudaStreamSynchronize(st));
+        }
+        CU(b.reserve(count));
+        return 0;
+    }
+    int zero(void* p, size_t bytes)
+    {
+        if (bytes > 0) CU(cudaMemsetAsync(p, 0, bytes, st));
+        return 0;
+    }
+    int ones(void* p, size_t bytes)
+    {
+        if (bytes > 0) CU(cudaMemsetAsync(p, 0xff, bytes, st));
+        return 0;
+    }
+    template<typename T>
+    int upload(T* dst, const T* src, size_t count)
+    {
+        if (count > 0) CU(cudaMemcpyAsync(dst, src, sizeof(T) * count, cudaMemcpyHostToDevice, st));
+        return 0;
+    }
+    int scan(const int* in, int* out, int n)
+    {
+        if (n <= 0) return 0;
+        const int numTiles = (n + c_scanTile - 1) / c_scanTile;
+        if (numTiles > c_scanTile) return nbb::fail("pair search: scan of %d items exceeds two levels", n);
+        if (numTiles == 1)
+        {
+            search_scan_tile_kernel<<<1, 1024, 0, st>>>(in, out, n, nullptr);
+            launches++;
+        }
+        else
+        {
+            if (reserve(tileSums, numTiles) || reserve(tileOffsets, numTiles)) return 1;
+            search_scan_tile_kernel<<<numTiles, 1024, 0, st>>>(in, out, n, tileSums.p);
+            search_scan_tile_kernel<<<1, 1024, 0, st>>>(tileSums.p, tileOffsets.p, numTiles, nullptr);
+            search_scan_add_kernel<<<(n + 255) / 256, 256, 0, st>>>(out, n, tileOffsets.p);
+            launches += 3;
+        }
+        CU(cudaGetLastError());
+        return 0;
+    }
+    int readInt(const int* p, int* v)
+    {
+        CU(cudaMemcpyAsync(h_value, p, sizeof(int), cudaMemcpyDeviceToHost, st));
+        CU(cudaStreamSynchronize(st));
+        *v = *reinterpret_cast<int*>(h_value);
+        return 0;
+    }
+    int readULL(const unsigned long long* p, unsigned long long* v)
+    {
+        CU(cudaMemcpyAsync(h_value, p, sizeof(unsigned long long), cudaMemcpyDeviceToHost, st));
+        CU(cudaStreamSynchronize(st));
+        *v = *reinterpret_cast<unsigned long long*>(h_value);
+        return 0;
+    }
+    template<typename F>
+    int forEach(int n, F f)
+    {
+        if (n <= 0) return 0;
+        search_items_kernel<F><<<(n + 255) / 256, 256, 0, st>>>(f, n);
+        launches++;
+        CU(cudaGetLastError());
+        return 0;
+    }
+};
+
+template<typename... B>
+static void releaseAll(B&... b)
+{
+    (b.release(), ...);
+}
+
+} // namespace nbb
+
+struct nbnxm_b200_gpu_search
+{
+    nbnxm_b200*                              nb = nullptr;
+    int                                      device = 0;
+    nbb::CudaSearchBackend                   be;
+    nbs::SearchState<nbb::CudaSearchBackend> st;
+    cudaEvent_t                              evStart = nullptr, evStop = nullptr;
+    float                                    lastBuildMs = 0.0f;
+};
+
+using nbb::fail;
+
+extern "C" {
+
+int nbnxm_b200_gpu_search_create(nbnxm_b200_gpu_search_t** out, nbnxm_b200_t* nb)
+{
+    if (!out || !nb) return fail("nbnxm_b200_gpu_search_create: null argument");
+    CU(cudaSetDevice(nb->device));
+    nbnxm_b200_gpu_search* s = new nbnxm_b200_gpu_search();
+    s->nb                    = nb;
+    s->device                = nb->device;
+    s->be.st                 = nb->stream[0];
+    void* pinned             = nullptr;
+    CU(cudaMallocHost(&pinned, 16));
+    s->be.h_value = static_cast<int*>(pinned);
+    CU(cudaEventCreate(&s->evStart));
+    CU(cudaEventCreate(&s->evStop));
+    *out = s;
+    return 0;
+}
+
+int nbnxm_b200_gpu_search_free(nbnxm_b200_gpu_search_t* s)
+{
+    if (!s) return 0;
+    /* the handle may already be gone (nbnxm_b200_free synchronises the device): nothing of it is touched here */
+    cudaSetDevice(s->device);
+    cudaDeviceSynchronize();
+    auto& t = s->st;
+    nbb::releaseAll(t.colFirstBin, t.atomIndex, t.slotOfAtom, t.clCount, t.exclIndex, t.exclAtoms, t.clBB, t.binBB,
+                    t.entryNumBinPairs, t.entryBinPairOff, t.binPairJ, t.binPairEntry, t.binPairMask, t.entryNumJ,
+                    t.entryGroups, t.entryCjOff, t.entryNumSci, t.entrySciOff, t.entryNonEmpty, t.entryCompactOff,
+                    t.compactEntry, t.exclFlag, t.exclOff, t.numClusterPairs, t.sci, t.cjp, t.excl, s->be.tileSums, s->be.tileOffsets);
+    if (s->be.h_value) cudaFreeHost(s->be.h_value);
+    if (s->evStart) cudaEventDestroy(s->evStart);
+    if (s->evStop) cudaEventDestroy(s->evStop);
+    delete s;
+    return 0;
+}
+
+int nbnxm_b200_gpu_search_set_grid(nbnxm_b200_gpu_search_t* s, const float* box, int ncx, int ncy, const int* first_bin_of_column,
+                                   const int* atom_index, int nbins, int natoms, const int* excl_index, const int* excl_atoms)
+{
+    if (!s || !box || !first_bin_of_column || !atom_index || ncx < 1 || ncy < 1 || nbins < 1 || natoms < 1)
+    {
+        return fail("nbnxm_b200_gpu_search_set_grid: bad argument");
+    }
+    if (nbins * nbs::c_binAtoms != s->nb->natoms)
+    {
+        return fail("nbnxm_b200_gpu_search_set_grid: the grid has %d nbat slots, the handle %d atoms (call nbnxm_b200_init_atomdata first)",
+                    nbins * nbs::c_binAtoms, s->nb->natoms);
+    }
+    CU(cudaSetDevice(s->nb->device));
+    /* the previous build may still read the grid arrays */
+    CU(cudaStreamSynchronize(s->be.st));
+    if (nbs::setGrid(s->be, s->st, box, ncx, ncy, first_bin_of_column, atom_index, nbins, natoms, excl_index, excl_atoms)) return 1;
+    /* the host arrays are the caller's: finish the uploads before returning */
+    CU(cudaStreamSynchronize(s->be.st));
+    s->nb->launches += s->be.launches;
+    s->be.launches = 0;
+    return 0;
+}
+
+int nbnxm_b200_gpu_search_build(nbnxm_b200_gpu_search_t* s, int iloc, float rlist, int min_sci, int bin_begin, int bin_end,
+                                int j_bin_lo, int j_bin_hi, int inter_zone, int required_tx)
+{
+    if (!s || iloc < 0 || iloc > 1) return fail("nbnxm_b200_gpu_search_build: bad argument");
+    if (!s->st.haveGrid) return fail("nbnxm_b200_gpu_search_build: call nbnxm_b200_gpu_search_set_grid first");
+    const nbs::Grid& g = s->st.g;
+    if (bin_begin < 0 || bin_end > g.nbins || bin_begin > bin_end || j_bin_lo < 0 || j_bin_hi > g.nbins)
+    {
+        return fail("nbnxm_b200_gpu_search_build: bin range");
+    }
+    for (int d = 0; d < 3; d++)
+    {
+        if (2 * rlist >= g.box[d]) return fail("nbnxm_b200_gpu_search_build: rlist %g must be shorter than half the box (%g)", rlist, g.box[d]);
+    }
+    nbnxm_b200* nb = s->nb;
+    CU(cudaSetDevice(nb->device));
+    /* coordinates are copied on the local / non-local streams; the search runs on the local stream */
+    if (nb->stream[1] != nb->stream[0]) CU(cudaStreamSynchronize(nb->stream[1]));
+    CU(cudaEventRecord(s->evStart, s->be.st));
+    if (nbs::buildPairlist(s->be, s->st, reinterpret_cast<const nbs::XQ*>(nb->xq.p), rlist, min_sci, bin_begin, bin_end, j_bin_lo,
+                           j_bin_hi, inter_zone, required_tx))
+    {
+        return 1;
+    }
+    CU(cudaEventRecord(s->evStop, s->be.st));
+    CU(cudaStreamSynchronize(s->be.st));
+    CU(cudaGetLastError());
+    CU(cudaEventElapsedTime(&s->lastBuildMs, s->evStart, s->evStop));
+    nb->launches += s->be.launches;
+    s->be.launches = 0;
+    /* gpu_init_pairlist without the host: device-to-device into the handle's list */
+    if (nbnxm_b200_init_pairlist_device(nb, iloc, s->st.sci.p, s->st.nsci, s->st.cjp.p, s->st.ncjp, s->st.excl.p, s->st.nexcl, nbs::c_cl))
+    {
+        return 1;
+    }
+    /* the copies run on the list's stream; the next build (local stream) overwrites their source */
+    if (nb->stream[iloc] != s->be.st) CU(cudaStreamSynchronize(nb->stream[iloc]));
+    return 0;
+}
+
+int nbnxm_b200_gpu_search_sizes(const nbnxm_b200_gpu_search_t* s, int* nsci, int* ncj_packed, int* nexcl, long long* ncluster_pairs,
+                                float* build_ms)
+{
+    if (!s) return fail("null search handle");
+    if (nsci) *nsci = s->st.nsci;
+    if (ncj_packed) *ncj_packed = s->st.ncjp;
+    if (nexcl) *nexcl = s->st.nexcl;
+    if (ncluster_pairs) *ncluster_pairs = s->st.numClusterPairsHost;
+    if (build_ms) *build_ms = s->lastBuildMs;
+    return 0;
+}
+
+int nbnxm_b200_gpu_search_download(nbnxm_b200_gpu_search_t* s, nbnxm_b200_sci_t* sci, nbnxm_b200_cj_packed_t* cj_packed,
+                                   nbnxm_b200_excl_t* excl)
+{
+    if (!s) return fail("null search handle");
+    CU(cudaSetDevice(s->nb->device));
+    CU(cudaStreamSynchronize(s->be.st));
+    if (sci && s->st.nsci > 0) CU(cudaMemcpy(sci, s->st.sci.p, sizeof(*sci) * s->st.nsci, cudaMemcpyDeviceToHost));
+    if (cj_packed && s->st.ncjp > 0) CU(cudaMemcpy(cj_packed, s->st.cjp.p, sizeof(*cj_packed) * s->st.ncjp, cudaMemcpyDeviceToHost));
+    if (excl && s->st.nexcl > 0) CU(cudaMemcpy(excl, s->st.excl.p, sizeof(*excl) * s->st.nexcl, cudaMemcpyDeviceToHost));
+    return 0;
+}
+
+} // extern "C"

@@ -139,6 +139,8 @@ struct nbnxm_b200
     };
     std::vector<XGrid> xgrids;
     nbb::DevBuf<int>        atomIndex;
+    nbb::DevBuf<int>        cell; /* atom -> nbat slot, for the force reduction (GpuForceReduction::Impl::cellInfo_) */
+    int                     numCells = 0;
 
     nbb::PairList plist[2];
     bool     haveWork[2] = { false, false };

@@ -26,14 +26,14 @@ VDW_TYPES = {"Cut": 0, "CutCombGeom": 1, "CutCombLB": 2, "FSwitch": 3, "PSwitch"
 EXPORTED_SYMBOLS = [
     "nbnxm_b200_last_error", "nbnxm_b200_init", "nbnxm_b200_free", "nbnxm_b200_update_params", "nbnxm_b200_do_force_step", "nbnxm_b200_do_force_step_pipelined", "nbnxm_b200_peer_blob_size", "nbnxm_b200_peer_export", "nbnxm_b200_peer_import",
     "nbnxm_b200_peer_close", "nbnxm_b200_peer_error",
-    "nbnxm_b200_init_pairlist", "nbnxm_b200_init_atomdata", "nbnxm_b200_upload_shiftvec",
+    "nbnxm_b200_init_pairlist", "nbnxm_b200_init_pairlist_device", "nbnxm_b200_init_atomdata", "nbnxm_b200_upload_shiftvec",
     "nbnxm_b200_copy_xq_to_gpu", "nbnxm_b200_init_x_to_nbat_x", "nbnxm_b200_x_to_nbat_x",
     "nbnxm_b200_launch_kernel", "nbnxm_b200_launch_kernel_pruneonly", "nbnxm_b200_launch_cpyback",
     "nbnxm_b200_try_finish_task", "nbnxm_b200_wait_finish_task", "nbnxm_b200_clear_outputs",
     "nbnxm_b200_insert_nonlocal_dependency", "nbnxm_b200_setup_short_range_work",
     "nbnxm_b200_have_short_range_work", "nbnxm_b200_min_ci_balanced",
     "nbnxm_b200_is_kernel_ewald_analytical", "nbnxm_b200_get_timings", "nbnxm_b200_reset_timings",
-    "nbnxm_b200_set_timing", "nbnxm_b200_get_device_buffers", "nbnxm_b200_get_streams",
+    "nbnxm_b200_set_timing", "nbnxm_b200_init_reduce_f", "nbnxm_b200_reduce_f", "nbnxm_b200_get_device_buffers", "nbnxm_b200_get_streams",
     "nbnxm_b200_download_pairlist", "nbnxm_b200_set_pair_counting", "nbnxm_b200_get_pair_count",
     "nbnxm_b200_launch_count", "nbnxm_b200_pack_xq", "nbnxm_b200_unpack_xq", "nbnxm_b200_pack_f",
     "nbnxm_b200_unpack_add_f", "nbnxm_b200_measure_fp32_peak",
@@ -196,10 +196,13 @@ class NbnxmGpu:
             self._h, C.c_int(iloc), _ptr(h_plist.sci, C.c_int), C.c_int(h_plist.sci.shape[0]),
             _ptr(h_plist.cjPacked, C.c_uint32), C.c_int(h_plist.cjPacked.shape[0]),
             _ptr(h_plist.excl, C.c_uint32), C.c_int(h_plist.excl.shape[0]), C.c_int(h_plist.na_ci)))
+        self._set_list_sizes(iloc, h_plist.sci.shape[0], h_plist.cjPacked.shape[0])
+
+    def _set_list_sizes(self, iloc, nsci, ncj):
         self._numSci = getattr(self, "_numSci", {})
-        self._numSci[iloc] = h_plist.sci.shape[0]
+        self._numSci[iloc] = nsci
         self._ncj = getattr(self, "_ncj", {})
-        self._ncj[iloc] = h_plist.cjPacked.shape[0]
+        self._ncj[iloc] = ncj
 
     def gpu_init_atomdata(self, nbat: AtomData):
         t = _i32(nbat.type)
@@ -231,6 +234,18 @@ class NbnxmGpu:
 
     def nbnxm_gpu_x_to_nbat_x(self, d_x_ptr, xReadyOnDevice=None, aloc=LOCAL):
         self._check(self._lib.nbnxm_b200_x_to_nbat_x(self._h, C.c_void_p(d_x_ptr), C.c_void_p(xReadyOnDevice), C.c_int(aloc)))
+
+    def gpu_force_reduction_reinit(self, cell):
+        """GpuForceReduction::reinit: cell[natoms] maps atoms to nbat slots (GridSet::cells())."""
+        c = _i32(cell)
+        self._check(self._lib.nbnxm_b200_init_reduce_f(self._h, _ptr(c, C.c_int), C.c_int(c.shape[0])))
+
+    def gpu_force_reduction_execute(self, d_f_total_ptr, d_rvec_to_add_ptr=None, atom_start=0, num_atoms=None, accumulate=False,
+                                    stream=None):
+        """GpuForceReduction::execute: f_total[a] (+)= f_nbat[cell[a]] (+ rvec[a]) on the device."""
+        self._check(self._lib.nbnxm_b200_reduce_f(
+            self._h, C.c_void_p(d_f_total_ptr), C.c_void_p(d_rvec_to_add_ptr), C.c_int(atom_start), C.c_int(num_atoms),
+            C.c_int(int(accumulate)), C.c_void_p(stream)))
 
     def gpu_launch_kernel(self, stepWork: StepWorkload, iloc=LOCAL):
         self._check(self._lib.nbnxm_b200_launch_kernel(

@@ -12,6 +12,8 @@ SEARCH_SYMBOLS = [
     "nbnxm_b200_grid_create", "nbnxm_b200_grid_create_slabs", "nbnxm_b200_grid_free", "nbnxm_b200_grid_info", "nbnxm_b200_grid_get_order",
     "nbnxm_b200_grid_fill_atomdata", "nbnxm_b200_pairlist_build", "nbnxm_b200_pairlist_sizes",
     "nbnxm_b200_pairlist_copy",
+    "nbnxm_b200_gpu_search_create", "nbnxm_b200_gpu_search_free", "nbnxm_b200_gpu_search_set_grid",
+    "nbnxm_b200_gpu_search_build", "nbnxm_b200_gpu_search_sizes", "nbnxm_b200_gpu_search_download",
 ]
 
 
@@ -82,6 +84,63 @@ class Grid:
         self._lib.nbnxm_b200_pairlist_copy(self._g, _p(sci, C.c_int), _p(cjp, C.c_uint32), _p(excl, C.c_uint32))
         pl = PairlistGpu(sci=sci, cjPacked=cjp, excl=excl, na_ci=8, rlist=rlist)
         pl.nci_tot = ncp.value
+        return pl
+
+
+class GpuPairSearch:
+    """constructPairlist + gpu_init_pairlist on the device (nbnxm_b200_gpu_search_*): the list is built from the
+    coordinates resident in the NbnxmGpu handle and becomes its list for `iloc`; nothing is staged on the host."""
+
+    def __init__(self, nb, grid: Grid, excl_index=None, excl_atoms=None):
+        self._lib = load_library()
+        self._nb = nb
+        self._s = C.c_void_p()
+        self.grid = grid
+        nb._check(self._lib.nbnxm_b200_gpu_search_create(C.byref(self._s), nb._h))
+        ei = None if excl_index is None else np.ascontiguousarray(excl_index, np.int32)
+        ea = None if excl_atoms is None else np.ascontiguousarray(excl_atoms, np.int32)
+        nb._check(self._lib.nbnxm_b200_gpu_search_set_grid(
+            self._s, _p(grid.box, C.c_float), C.c_int(grid.ncx), C.c_int(grid.ncy), _p(grid.first_bin_of_column, C.c_int),
+            _p(grid.atom_index, C.c_int), C.c_int(grid.nbins), C.c_int(grid.natoms), _p(ei, C.c_int), _p(ea, C.c_int)))
+        self.build_ms = 0.0
+        self.nci_tot = 0
+
+    def free(self):
+        if self._s:
+            self._lib.nbnxm_b200_gpu_search_free(self._s)
+            self._s = C.c_void_p()
+
+    def __del__(self):
+        try:
+            self.free()
+        except Exception:
+            pass
+
+    def build(self, rlist, iloc=0, min_sci=0, bins=None, j_bins=None, inter_zone=False, required_tx=0):
+        """Builds and installs the list; returns (nsci, ncj_packed, nexcl)."""
+        b0, b1 = bins if bins is not None else (0, self.grid.nbins)
+        j0, j1 = j_bins if j_bins is not None else (0, self.grid.nbins)
+        self._nb._check(self._lib.nbnxm_b200_gpu_search_build(
+            self._s, C.c_int(iloc), C.c_float(rlist), C.c_int(min_sci), C.c_int(b0), C.c_int(b1), C.c_int(j0), C.c_int(j1),
+            C.c_int(int(inter_zone)), C.c_int(required_tx)))
+        nsci, ncj, nex, ncp, ms = C.c_int(), C.c_int(), C.c_int(), C.c_longlong(), C.c_float()
+        self._nb._check(self._lib.nbnxm_b200_gpu_search_sizes(self._s, C.byref(nsci), C.byref(ncj), C.byref(nex),
+                                                             C.byref(ncp), C.byref(ms)))
+        self.build_ms, self.nci_tot, self.rlist = ms.value, ncp.value, rlist
+        self._sizes = (nsci.value, ncj.value, nex.value)
+        self._nb._set_list_sizes(iloc, nsci.value, ncj.value)
+        return self._sizes
+
+    def download(self) -> PairlistGpu:
+        """Host copy of the list built last."""
+        nsci, ncj, nex = self._sizes
+        sci = np.zeros((nsci, 4), np.int32)
+        cjp = np.zeros((ncj, 8), np.uint32)
+        excl = np.zeros((nex, 32), np.uint32)
+        self._nb._check(self._lib.nbnxm_b200_gpu_search_download(self._s, _p(sci, C.c_int), _p(cjp, C.c_uint32),
+                                                                _p(excl, C.c_uint32)))
+        pl = PairlistGpu(sci=sci, cjPacked=cjp, excl=excl, na_ci=8, rlist=self.rlist)
+        pl.nci_tot = self.nci_tot
         return pl
 
 

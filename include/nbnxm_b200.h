@@ -123,6 +123,11 @@ int nbnxm_b200_update_params(nbnxm_b200_t* nb, const nbnxm_b200_params_t* params
 int nbnxm_b200_init_pairlist(nbnxm_b200_t* nb, int iloc, const nbnxm_b200_sci_t* sci, int nsci,
                              const nbnxm_b200_cj_packed_t* cj_packed, int ncj_packed,
                              const nbnxm_b200_excl_t* excl, int nexcl, int na_ci);
+/* the same for a list that is already in device memory (built by nbnxm_b200_gpu_search_build, include/nbnxm_b200_search.h):
+ * device-to-device copies on the list's stream, no host staging */
+int nbnxm_b200_init_pairlist_device(nbnxm_b200_t* nb, int iloc, const nbnxm_b200_sci_t* d_sci, int nsci,
+                                    const nbnxm_b200_cj_packed_t* d_cj_packed, int ncj_packed,
+                                    const nbnxm_b200_excl_t* d_excl, int nexcl, int na_ci);
 /* gpu_init_atomdata, nbnxm_gpu_data_mgmt.cpp:1006.  atom_type and/or lj_comb (natoms float pairs)
  * as the flavor needs (types for Cut/FSwitch/PSwitch/Ewald*, lj_comb for CutComb*). */
 int nbnxm_b200_init_atomdata(nbnxm_b200_t* nb, int natoms, int natoms_local, const int* atom_type,
@@ -175,6 +180,15 @@ int nbnxm_b200_set_timing(nbnxm_b200_t* nb, int enable);
  * d_f is float3-packed (natoms x 3), valid after nbnxm_b200_launch_cpyback's reduction stage
  * (use_gpu_f_buffer_ops = 1 keeps it on the device); d_xq is float4. */
 int nbnxm_b200_get_device_buffers(nbnxm_b200_t* nb, float** d_xq, float** d_f, int* natoms);
+/* GpuForceReduction::reinit / execute (src/gromacs/mdlib/gpuforcereduction_impl.cpp, reduceKernel in
+ * gpuforcereduction_impl_internal.cu:61-118): f_total[a] (+)= f_nbat[cell[a]] (+ rvec_force_to_add[a]) for the atoms
+ * [atom_start, atom_start + num_atoms), all arrays but `cell` in device memory, rvecs as packed float3.  cell[natoms]:
+ * atom -> nbat slot (GridSet::cells()).  The nbat forces are read from the kernels' accumulator, so neither
+ * nbnxm_b200_launch_cpyback nor a packing pass is needed first; the caller orders `stream` (NULL: the local stream)
+ * after the force kernels, as the reference does with its dependency list. */
+int nbnxm_b200_init_reduce_f(nbnxm_b200_t* nb, const int* cell, int natoms);
+int nbnxm_b200_reduce_f(nbnxm_b200_t* nb, float* d_f_total, const float* d_rvec_force_to_add, int atom_start,
+                        int num_atoms, int accumulate, void* stream);
 /* streams the handle runs on (cudaStream_t), for callers that order their own work against it */
 int nbnxm_b200_get_streams(nbnxm_b200_t* nb, void** local_stream, void** nonlocal_stream);
 

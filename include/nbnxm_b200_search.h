@@ -1,4 +1,4 @@
-/* nbnxm_b200_search — host-side grid binning and GPU-layout pair-list construction (C ABI).
+/* nbnxm_b200_search — grid binning (host) and GPU-layout pair-list construction (host and GPU builders) (C ABI).
  *
  * This is the caller side of the force path ("next" row of the scope table): it produces exactly the
  * inputs the reference hands to gpu_init_atomdata / gpu_init_pairlist, in the reference's formats:
@@ -58,6 +58,33 @@ int nbnxm_b200_pairlist_sizes(const nbnxm_b200_grid_t* grid, int* nsci, int* ncj
                               long long* ncluster_pairs);
 int nbnxm_b200_pairlist_copy(const nbnxm_b200_grid_t* grid, nbnxm_b200_sci_t* sci, nbnxm_b200_cj_packed_t* cj_packed,
                              nbnxm_b200_excl_t* excl);
+
+/* ---- the same list built on the GPU (gromacs_b200/csrc/nbnxm_gpusearch.cu) ----
+ *
+ * constructPairlist + gpu_init_pairlist (pairlist.cpp:4056, nbnxm_gpu_data_mgmt.cpp:739) without the host in
+ * between: the list is built from the coordinates resident in the handle (`xq` after nbnxm_b200_copy_xq_to_gpu /
+ * nbnxm_b200_x_to_nbat_x) and installed as the handle's list for `iloc`; it equals the list of
+ * nbnxm_b200_pairlist_build (one thread) entry for entry, except for the numbering of the nbnxm_excl_t entries.
+ * Order of calls at a search step: grid (nbnxm_b200_grid_create, host) -> nbnxm_b200_init_atomdata ->
+ * nbnxm_b200_copy_xq_to_gpu -> nbnxm_b200_gpu_search_set_grid -> nbnxm_b200_gpu_search_build. */
+typedef struct nbnxm_b200_gpu_search nbnxm_b200_gpu_search_t;
+
+int nbnxm_b200_gpu_search_create(nbnxm_b200_gpu_search_t** search, nbnxm_b200_t* nb);
+int nbnxm_b200_gpu_search_free(nbnxm_b200_gpu_search_t* search);
+/* the grid of nbnxm_b200_grid_get_order / nbnxm_b200_grid_info (nbins * 64 must equal the handle's natoms) and the
+ * topology exclusions (CSR in atom order, may be NULL); the arrays are copied before the call returns */
+int nbnxm_b200_gpu_search_set_grid(nbnxm_b200_gpu_search_t* search, const float* box, int ncx, int ncy,
+                                   const int* first_bin_of_column, const int* atom_index, int nbins, int natoms,
+                                   const int* excl_index, const int* excl_atoms);
+/* arguments as nbnxm_b200_pairlist_build; the result becomes the handle's list for iloc (haveFreshList set) */
+int nbnxm_b200_gpu_search_build(nbnxm_b200_gpu_search_t* search, int iloc, float rlist, int min_sci, int bin_begin,
+                                int bin_end, int j_bin_lo, int j_bin_hi, int inter_zone, int required_tx);
+/* sizes of the list built last, cluster pairs in it, device time of the build (ms, CUDA events) */
+int nbnxm_b200_gpu_search_sizes(const nbnxm_b200_gpu_search_t* search, int* nsci, int* ncj_packed, int* nexcl,
+                                long long* ncluster_pairs, float* build_ms);
+/* copy of the list built last (tests, callers that keep a host copy) */
+int nbnxm_b200_gpu_search_download(nbnxm_b200_gpu_search_t* search, nbnxm_b200_sci_t* sci,
+                                   nbnxm_b200_cj_packed_t* cj_packed, nbnxm_b200_excl_t* excl);
 
 #ifdef __cplusplus
 }

@@ -12,8 +12,8 @@ from util import load_golden, product_inputs, product_params
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 
 
-def declared_symbols():
-    txt = open(os.path.join(ROOT, "include", "nbnxm_b200.h")).read()
+def declared_symbols(header="nbnxm_b200.h"):
+    txt = open(os.path.join(ROOT, "include", header)).read()
     txt = re.sub(r"/\*.*?\*/", "", txt, flags=re.S)
     return sorted(set(re.findall(r"\b(nbnxm_b200_[a-z0-9_]+)\s*\(", txt)))
 
@@ -26,8 +26,13 @@ def test_header_and_binding_agree():
 def test_library_exports_every_declared_symbol():
     from gromacs_b200 import load_library
     lib = load_library()
-    for name in declared_symbols():
+    for name in declared_symbols() + declared_symbols("nbnxm_b200_search.h"):
         assert hasattr(lib, name), name
+
+
+def test_search_header_and_binding_agree():
+    from gromacs_b200.pairsearch import SEARCH_SYMBOLS
+    assert declared_symbols("nbnxm_b200_search.h") == sorted(SEARCH_SYMBOLS)
 
 
 def test_struct_layouts_match_reference_pairlist_structs():

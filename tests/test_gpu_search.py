@@ -1,0 +1,181 @@
+"""GPU tests of the pair-list builder on the device (nbnxm_b200_gpu_search_*, gromacs_b200/csrc/nbnxm_gpusearch.cu):
+the list built from the coordinates resident in the handle must equal the host builder's (one thread) entry for
+entry — integer / mask work, so bit-exact — and the force kernel run on the list installed from device memory must
+give the forces it gives with the host builder's list."""
+import json
+import os
+import time
+
+import numpy as np
+import pytest
+
+from test_gpusearch_emu import assert_same_list
+from util import load_golden, product_params, relrms
+
+pytestmark = pytest.mark.gpu
+
+
+def golden_system(case):
+    from gromacs_b200.pairsearch import Grid
+    d = load_golden(case)
+    grid = Grid(d["sys_box"], d["sys_x"], nthreads=1)
+    nt = int(d["nbat_ntypes"][0])
+    nbat = grid.atomdata(d["sys_x"], d["sys_q"], d["sys_type"], d["nbat_nbfp"], nt, nbfp_comb=d["nbat_nbfp_comb"])
+    return d, grid, nbat
+
+
+def run_step(nb, nbat, energy=True):
+    from gromacs_b200 import LOCAL, StepWorkload
+    sw = StepWorkload(computeEnergy=energy, computeVirial=energy)
+    nb.gpu_clear_outputs(True)
+    nb.gpu_launch_kernel(sw, LOCAL)
+    nb.gpu_launch_cpyback(nbat, sw, LOCAL)
+    e = nb.gpu_wait_finish_task(sw, LOCAL)
+    return nbat.f.astype(np.float64).copy(), e
+
+
+@pytest.mark.parametrize("case,rlist,min_sci", [("test243_ewald_cutnone", 0.9, 0), ("bench1_ewald_cutnone", 1.0, 0),
+                                                ("bench1_ewald_cutnone", 1.05, 500)])
+def test_device_list_equals_host_list_and_gives_the_same_forces(case, rlist, min_sci):
+    from gromacs_b200 import LOCAL, NbnxmGpu
+    from gromacs_b200.pairsearch import GpuPairSearch
+    d, grid, nbat = golden_system(case)
+    ref = grid.pairlist(rlist, d["sys_excl_index"], d["sys_excl_atoms"], min_sci=min_sci)
+    nb = NbnxmGpu(product_params(d, vdw="Cut"), nbat)
+    try:
+        nb.gpu_init_atomdata(nbat)
+        nb.gpu_upload_shiftvec(nbat)
+        nb.gpu_copy_xq_to_gpu(nbat, LOCAL)
+        search = GpuPairSearch(nb, grid, d["sys_excl_index"], d["sys_excl_atoms"])
+        sizes = search.build(rlist, LOCAL, min_sci=min_sci)
+        got = search.download()
+        assert sizes == (ref.sci.shape[0], ref.cjPacked.shape[0], ref.excl.shape[0])
+        assert_same_list((got.sci, got.cjPacked, got.excl), (ref.sci, ref.cjPacked, ref.excl))
+        assert search.nci_tot == ref.nci_tot
+        nb.setupGpuShortRangeWork(LOCAL)
+        f_dev, e_dev = run_step(nb, nbat)
+        # a second build reuses every buffer
+        assert search.build(rlist, LOCAL, min_sci=min_sci) == sizes
+        f_dev2, _ = run_step(nb, nbat)
+        nb.gpu_init_pairlist(ref, LOCAL)
+        f_host, e_host = run_step(nb, nbat)
+        search.free()
+    finally:
+        nb.gpu_free()
+    # same entries in the same order: only the order of the floating-point atomics differs
+    assert relrms(f_dev, f_host) < 1e-6 and relrms(f_dev2, f_host) < 1e-6
+    assert abs(e_dev[0] - e_host[0]) <= 1e-6 * abs(e_host[0]) and abs(e_dev[1] - e_host[1]) <= 1e-6 * abs(e_host[1])
+
+
+def test_device_list_of_the_96k_box(oracle):
+    """BASELINE configs[1] (96 000 atoms, rlist 1.18): two-level scans, 67 k cjPacked groups, 14 k exclusion entries;
+    records the device time of the build next to the host builder's wall time."""
+    from gromacs_b200 import LOCAL, NbnxmGpu
+    from gromacs_b200.pairsearch import GpuPairSearch
+    from gromacs_b200.workload import make_workload
+    wl = make_workload("water96k_fswitch", nthreads=1)
+    t0 = time.time()
+    ref = wl.pairlist(min_sci=9000)
+    host_s = time.time() - t0
+    nb = NbnxmGpu(wl.params, wl.nbat)
+    try:
+        nb.gpu_init_atomdata(wl.nbat)
+        nb.gpu_upload_shiftvec(wl.nbat)
+        nb.gpu_copy_xq_to_gpu(wl.nbat, LOCAL)
+        search = GpuPairSearch(nb, wl.grid, wl.box.excl_index, wl.box.excl_atoms)
+        search.build(wl.cfg["rlist_outer"], LOCAL, min_sci=9000)          # warm-up: allocations
+        search.build(wl.cfg["rlist_outer"], LOCAL, min_sci=9000)
+        got = search.download()
+        assert_same_list((got.sci, got.cjPacked, got.excl), (ref.sci, ref.cjPacked, ref.excl))
+        nb.setupGpuShortRangeWork(LOCAL)
+        f_dev, _ = run_step(nb, wl.nbat)
+        nb.gpu_init_pairlist(ref, LOCAL)
+        f_host, _ = run_step(nb, wl.nbat)
+        ms = search.build_ms
+        search.free()
+    finally:
+        nb.gpu_free()
+    assert relrms(f_dev, f_host) < 1e-6
+    out = os.path.join(os.path.dirname(os.path.dirname(os.path.abspath(__file__))), "gpurun_out")
+    if os.path.isdir(out):
+        with open(os.path.join(out, "gpu_search_96k.json"), "w") as fh:
+            json.dump({"workload": "water96k_fswitch", "natoms": wl.box.natoms, "rlist": wl.cfg["rlist_outer"],
+                       "ncj_packed": int(ref.cjPacked.shape[0]), "nsci": int(ref.sci.shape[0]),
+                       "gpu_build_ms": ms, "host_build_1thread_s": host_s}, fh)
+
+
+def test_device_list_of_the_1536k_box():
+    """BASELINE configs[3] (1 536 000 atoms): 1.0 M cjPacked groups, 0.22 M exclusion entries, two-level scans of 2 M
+    items; equality with the host builder's list (all threads: same entries, other exclusion numbering) and timing."""
+    from gromacs_b200 import LOCAL, NbnxmGpu
+    from gromacs_b200.pairsearch import GpuPairSearch
+    from gromacs_b200.workload import make_workload
+    wl = make_workload("water1536k")
+    t0 = time.time()
+    ref = wl.pairlist(min_sci=18944)
+    host_s = time.time() - t0
+    nb = NbnxmGpu(wl.params, wl.nbat)
+    try:
+        nb.gpu_init_atomdata(wl.nbat)
+        nb.gpu_upload_shiftvec(wl.nbat)
+        nb.gpu_copy_xq_to_gpu(wl.nbat, LOCAL)
+        search = GpuPairSearch(nb, wl.grid, wl.box.excl_index, wl.box.excl_atoms)
+        search.build(wl.cfg["rlist_outer"], LOCAL, min_sci=18944)
+        search.build(wl.cfg["rlist_outer"], LOCAL, min_sci=18944)
+        ms = search.build_ms
+        got = search.download()
+        search.free()
+    finally:
+        nb.gpu_free()
+    assert_same_list((got.sci, got.cjPacked, got.excl), (ref.sci, ref.cjPacked, ref.excl))
+    out = os.path.join(os.path.dirname(os.path.dirname(os.path.abspath(__file__))), "gpurun_out")
+    if os.path.isdir(out):
+        with open(os.path.join(out, "gpu_search_1536k.json"), "w") as fh:
+            json.dump({"workload": "water1536k", "natoms": wl.box.natoms, "rlist": wl.cfg["rlist_outer"],
+                       "ncj_packed": int(ref.cjPacked.shape[0]), "nsci": int(ref.sci.shape[0]), "gpu_build_ms": ms,
+                       "host_build_s": host_s, "host_threads": wl.grid.nthreads}, fh)
+
+
+def test_force_reduction_gathers_nbat_forces_into_atom_order():
+    """nbnxm_b200_reduce_f (reduceKernel, mdlib/gpuforcereduction_impl_internal.cu:61-118): set / accumulate, with and
+    without an extra rvec force, on an atom sub-range, against the copied-back nbat forces."""
+    import torch
+    from gromacs_b200 import LOCAL, NbnxmGpu
+    d, grid, nbat = golden_system("bench1_ewald_cutnone")
+    plist = grid.pairlist(0.9, d["sys_excl_index"], d["sys_excl_atoms"])
+    n = d["sys_x"].shape[0]
+    cell = np.zeros(n, np.int32)
+    slots = np.nonzero(grid.atom_index >= 0)[0]
+    cell[grid.atom_index[slots]] = slots
+    nb = NbnxmGpu(product_params(d, vdw="Cut"), nbat)
+    try:
+        nb.gpu_init_atomdata(nbat)
+        nb.gpu_upload_shiftvec(nbat)
+        nb.gpu_copy_xq_to_gpu(nbat, LOCAL)
+        nb.gpu_init_pairlist(plist, LOCAL)
+        nb.setupGpuShortRangeWork(LOCAL)
+        f_nbat, _ = run_step(nb, nbat, energy=False)
+        f_atoms = f_nbat[cell].astype(np.float32)
+        nb.gpu_force_reduction_reinit(cell)
+        rng = np.random.default_rng(7)
+        extra = rng.standard_normal((n, 3)).astype(np.float32)
+        base = rng.standard_normal((n, 3)).astype(np.float32)
+        d_extra = torch.from_numpy(extra).cuda()
+        stream = nb.streams()[0]
+        for accumulate in (False, True):
+            for with_extra in (False, True):
+                d_total = torch.from_numpy(base).cuda()
+                torch.cuda.synchronize()
+                a0, na = 64, n - 100
+                nb.gpu_force_reduction_execute(d_total.data_ptr(), d_extra.data_ptr() if with_extra else None, a0, na,
+                                               accumulate, stream)
+                nb.gpu_wait_finish_task(__import__("gromacs_b200").StepWorkload(), LOCAL)
+                torch.cuda.synchronize()
+                want = base.copy()
+                sl = slice(a0, a0 + na)
+                want[sl] = (base[sl] if accumulate else 0) + f_atoms[sl] + (extra[sl] if with_extra else 0)
+                got = d_total.cpu().numpy()
+                assert np.array_equal(got[:a0], base[:a0]) and np.array_equal(got[a0 + na:], base[a0 + na:])
+                assert np.allclose(got[sl], want[sl], rtol=1e-6, atol=1e-4 * np.abs(f_atoms).max() * 1e-3)
+    finally:
+        nb.gpu_free()
