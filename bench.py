@@ -269,7 +269,11 @@ def main():
     nbat.f = f_pin.numpy()
 
     nb = NbnxmGpu(wl.params, nbat, device=local_rank)
-    plist = wl.pairlist(min_sci=args.min_sci or nb.gpu_min_ci_balanced())
+    min_sci = args.min_sci or nb.gpu_min_ci_balanced()
+    t_search = time.perf_counter()
+    plist = wl.pairlist(min_sci=min_sci)
+    host_search_s = time.perf_counter() - t_search
+    list_bytes = int(plist.sci.nbytes + plist.cjPacked.nbytes + plist.excl.nbytes)
     # end-to-end path: coordinates go up and forces come down in chunks of grid columns, pipelined against the kernel
     # (nbnxm_b200_do_force_step_pipelined); the list is the same, with its sci entries grouped by chunk
     from gromacs_b200.pipeline import make_chunk_plan
@@ -360,6 +364,22 @@ def main():
         step(i, True)
     ms_e2e, _, _ = timed_run(True)
 
+    # the search step on either side of the path, untimed above: the same list built on the device from
+    # the resident coordinates (nbnxm_b200_gpu_search_build) next to the host builder + upload it replaces
+    try:
+        from gromacs_b200.pairsearch import GpuPairSearch
+        gs = GpuPairSearch(nb, wl.grid, wl.box.excl_index, wl.box.excl_atoms)
+        build_ms = []
+        for _ in range(3):
+            sizes = gs.build(cfg["rlist_outer"], LOCAL, min_sci=min_sci)
+            build_ms.append(gs.build_ms)
+        gs.free()
+        search_rec = {"gpu_build_ms": min(build_ms[1:]), "host_build_s": host_search_s, "host_threads": wl.grid.nthreads,
+                      "list_bytes_not_uploaded": list_bytes,
+                      "same_sizes_as_host_list": list(sizes[:2]) == [int(plist.sci.shape[0]), int(plist.cjPacked.shape[0])]}
+    except Exception as e:      # reported, never fatal for the force-step measurement
+        search_rec = {"error": str(e)}
+
     value = wl.useful_pairs / (ms_step * 1e-3) * 1e-9
     line = {
         "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": 1, "steps": args.steps, "warmup": args.warmup,
@@ -376,6 +396,7 @@ def main():
         "computed_gpairs_per_s": computed_pairs / (ms_step * 1e-3) * 1e-9,
         "unpruned_pairs_first_step": pairs_first,
         "gpu_launches": launches,
+        "search_step": search_rec,
         "clocks": clock_rec,
         "e2e": {"value": wl.useful_pairs / (ms_e2e * 1e-3) * 1e-9, "unit": UNIT, "ms_per_step": ms_e2e,
                 "h2d_bytes_per_step": int(nbat.numAtoms() * 16),

@@ -1,0 +1,42 @@
+"""Builds the pair list of a workload on the GPU (nbnxm_b200_gpu_search_build) a few times and prints the device time
+of each build; run under `ncu --metrics gpu__time_duration.sum` for the per-pass launch list.
+usage: python profiles/tools/search_profile.py [workload] [builds] [min_sci]"""
+import json
+import os
+import sys
+import time
+
+sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.dirname(os.path.abspath(__file__)))))
+from gromacs_b200 import LOCAL, NbnxmGpu  # noqa: E402
+from gromacs_b200.pairsearch import GpuPairSearch  # noqa: E402
+from gromacs_b200.workload import make_workload  # noqa: E402
+
+name = sys.argv[1] if len(sys.argv) > 1 else "water1536k"
+builds = int(sys.argv[2]) if len(sys.argv) > 2 else 3
+min_sci = int(sys.argv[3]) if len(sys.argv) > 3 else 18944
+wl = make_workload(name)
+t0 = time.time()
+ref = wl.pairlist(min_sci=min_sci)
+host_s = time.time() - t0
+nb = NbnxmGpu(wl.params, wl.nbat)
+nb.gpu_init_atomdata(wl.nbat)
+nb.gpu_upload_shiftvec(wl.nbat)
+nb.gpu_copy_xq_to_gpu(wl.nbat, LOCAL)
+search = GpuPairSearch(nb, wl.grid, wl.box.excl_index, wl.box.excl_atoms)
+ms = []
+for _ in range(builds):
+    sizes = search.build(wl.cfg["rlist_outer"], LOCAL, min_sci=min_sci)
+    ms.append(search.build_ms)
+# the host path for comparison: upload of the host builder's list (gpu_init_pairlist from pageable numpy arrays)
+from gromacs_b200 import StepWorkload  # noqa: E402
+nb.gpu_wait_finish_task(StepWorkload(), LOCAL)
+t0 = time.time()
+nb.gpu_init_pairlist(ref, LOCAL)
+nb.gpu_wait_finish_task(StepWorkload(), LOCAL)
+h2d_s = time.time() - t0
+print(json.dumps({"host_list_upload_s": h2d_s, "workload": name, "natoms": wl.box.natoms, "rlist": wl.cfg["rlist_outer"], "nsci": sizes[0],
+                  "ncj_packed": sizes[1], "nexcl": sizes[2], "same_sizes_as_host": sizes == (ref.sci.shape[0], ref.cjPacked.shape[0], ref.excl.shape[0]),
+                  "gpu_build_ms": ms, "host_build_s": host_s, "host_threads": wl.grid.nthreads,
+                  "list_bytes": int(ref.sci.nbytes + ref.cjPacked.nbytes + ref.excl.nbytes)}))
+search.free()
+nb.gpu_free()
