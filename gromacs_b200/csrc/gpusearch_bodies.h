@@ -632,6 +632,281 @@ NBS_HD void assignExclIndex(const Work& w, int item)
     }
 }
 
+/* ======================================================================================================================
+ * Gridding on the device: atoms (atom order, rvec) -> columns -> nbat order (Grid::putOnGrid, grid.cpp:1612;
+ * sortCellsGpuGeometry :1169), the same order as the host gridder nbnxm_b200_grid_create (pairsearch.cpp): columns
+ * x-major; within a column atoms sorted along z, then every 32 along +-y, then every 16 along +-x (the direction
+ * alternates so that consecutive clusters stay adjacent); ties broken by atom index, so the order is unique.
+ * ====================================================================================================================== */
+
+struct GridBuild
+{
+    float        cellSize[2];
+    int          ncx, ncy, natoms;
+    const float* x;            /* atom order, 3 floats per atom */
+    int*         colOfAtom;    /* natoms */
+    int*         colCount;     /* atoms per column (+1) */
+    int*         colAtomStart; /* scan (+1) */
+    int*         colBins;      /* 64-atom bins per column (+1) */
+    int*         colFirstBin;  /* scan (+1) */
+    int*         colFill;      /* scatter counters */
+    int*         colAtoms;     /* atoms grouped by column */
+    int*         maxColCount;  /* scalar */
+    int*         atomIndex;    /* nbat slot -> atom, prefilled with -1 */
+    int*         slotOfAtom;   /* atom -> nbat slot */
+};
+
+NBS_HD int atomicAddInt(int* p, int v)
+{
+#if defined(__CUDA_ARCH__)
+    return atomicAdd(p, v);
+#else
+    const int old = *p;
+    *p += v;
+    return old;
+#endif
+}
+
+NBS_HD void atomicMaxInt(int* p, int v)
+{
+#if defined(__CUDA_ARCH__)
+    atomicMax(p, v);
+#else
+    if (v > *p)
+    {
+        *p = v;
+    }
+#endif
+}
+
+/* pass G1: column of atom a */
+NBS_HD void gridColumnOfAtom(const GridBuild& g, int a)
+{
+    int cx = int(g.x[3 * a] / g.cellSize[0]);
+    int cy = int(g.x[3 * a + 1] / g.cellSize[1]);
+    cx     = cx < 0 ? 0 : (cx > g.ncx - 1 ? g.ncx - 1 : cx);
+    cy     = cy < 0 ? 0 : (cy > g.ncy - 1 ? g.ncy - 1 : cy);
+    const int col  = cx * g.ncy + cy; /* x-major, grid.h:100 */
+    g.colOfAtom[a] = col;
+    atomicAddInt(&g.colCount[col], 1);
+}
+
+/* pass G2: bins of column c */
+NBS_HD void gridColumnBins(const GridBuild& g, int c)
+{
+    const int n  = g.colCount[c];
+    g.colBins[c] = (n + c_binAtoms - 1) / c_binAtoms;
+    atomicMaxInt(g.maxColCount, n);
+}
+
+/* pass G3: scatter into columns (any order: the sort below is a total order) */
+NBS_HD void gridScatterAtom(const GridBuild& g, int a)
+{
+    const int col = g.colOfAtom[a];
+    const int pos = atomicAddInt(&g.colFill[col], 1);
+    g.colAtoms[g.colAtomStart[col] + pos] = a;
+}
+
+/* pass G4: one block per column, bitonic networks in the block's scratch memory (key[nPad], idx[nPad]); the stages
+ * are separated by block barriers, every item of a stage touches its own elements only */
+NBS_HD int nextPow2AtLeast32(int n)
+{
+    int p = 32;
+    while (p < n)
+    {
+        p <<= 1;
+    }
+    return p;
+}
+
+NBS_HD int log2Int(int p)
+{
+    int l = 0;
+    while ((1 << l) < p)
+    {
+        l++;
+    }
+    return l;
+}
+
+struct ColumnSort
+{
+    GridBuild g;
+    int       scratchPad; /* elements of scratch per block (max nPad) */
+
+    NBS_HD int numStages(int c) const
+    {
+        const int n = g.colCount[c];
+        if (n == 0)
+        {
+            return 0;
+        }
+        const int l = log2Int(nextPow2AtLeast32(n));
+        return 1 + l * (l + 1) / 2 + 1 + 15 + 1 + 10 + 1;
+    }
+
+    /* decodes stage s: kind 0 = load key of dimension dim (segment length seg for the direction), 1 = bitonic (k, j,
+     * kmax), 2 = store */
+    NBS_HD void decode(int c, int s, int& kind, int& dim, int& k, int& j, int& kmax) const
+    {
+        const int nPad = nextPow2AtLeast32(g.colCount[c]);
+        const int l    = log2Int(nPad);
+        const int s1   = l * (l + 1) / 2;
+        int       q;
+        if (s == 0)
+        {
+            kind = 0;
+            dim  = 2;
+            kmax = nPad;
+            return;
+        }
+        else if (s <= s1)
+        {
+            q    = s - 1;
+            kmax = nPad;
+            dim  = 2;
+        }
+        else if (s == s1 + 1)
+        {
+            kind = 0;
+            dim  = 1;
+            kmax = 32;
+            return;
+        }
+        else if (s <= s1 + 1 + 15)
+        {
+            q    = s - (s1 + 2);
+            kmax = 32;
+            dim  = 1;
+        }
+        else if (s == s1 + 17)
+        {
+            kind = 0;
+            dim  = 0;
+            kmax = 16;
+            return;
+        }
+        else if (s <= s1 + 17 + 10)
+        {
+            q    = s - (s1 + 18);
+            kmax = 16;
+            dim  = 0;
+        }
+        else
+        {
+            kind = 2;
+            dim  = 0;
+            kmax = 0;
+            return;
+        }
+        kind = 1;
+        for (k = 2;; k <<= 1)
+        {
+            const int nj = log2Int(k);
+            if (q < nj)
+            {
+                j = k >> (q + 1);
+                break;
+            }
+            q -= nj;
+        }
+    }
+
+    NBS_HD int numItems(int c, int s) const
+    {
+        const int nPad = nextPow2AtLeast32(g.colCount[c]);
+        int       kind = 0, dim = 0, k = 0, j = 0, kmax = 0;
+        decode(c, s, kind, dim, k, j, kmax);
+        return kind == 1 ? nPad / 2 : nPad;
+    }
+
+    NBS_HD void operator()(int c, int s, int t, void* scratch) const
+    {
+        const int n    = g.colCount[c];
+        float*    key  = static_cast<float*>(scratch);
+        int*      idx  = reinterpret_cast<int*>(key + scratchPad);
+        int       kind = 0, dim = 0, k = 0, j = 0, kmax = 0;
+        decode(c, s, kind, dim, k, j, kmax);
+        if (kind == 0)
+        {
+            /* (re)load the sort key; z: ascending over the column; y / x: direction by segment parity */
+            if (dim == 2)
+            {
+                idx[t] = t < n ? g.colAtoms[g.colAtomStart[c] + t] : 0x7fffffff;
+            }
+            float v = 3.0e38f;
+            if (t < n)
+            {
+                v = g.x[3 * idx[t] + dim];
+                if (dim != 2 && ((t / kmax) & 1))
+                {
+                    v = -v;
+                }
+            }
+            key[t] = v;
+        }
+        else if (kind == 1)
+        {
+            const int  i   = 2 * j * (t / j) + (t % j);
+            const int  p   = i + j;
+            const bool asc = (k == kmax) || ((i & k) == 0);
+            const float ka = key[i], kb = key[p];
+            const int   ia = idx[i], ib = idx[p];
+            const bool  bLessA = (kb < ka) || (kb == ka && ib < ia);
+            const bool  aLessB = (ka < kb) || (ka == kb && ia < ib);
+            if (asc ? bLessA : aLessB)
+            {
+                key[i] = kb;
+                key[p] = ka;
+                idx[i] = ib;
+                idx[p] = ia;
+            }
+        }
+        else if (t < n)
+        {
+            const int slot       = g.colFirstBin[c] * c_binAtoms + t;
+            g.atomIndex[slot]    = idx[t];
+            g.slotOfAtom[idx[t]] = slot;
+        }
+    }
+};
+
+/* pass G5: atom data in nbat order (nbnxm_atomdata_t::copy x / setAtomProperties, atomdata.cpp:159-280, :1107);
+ * fillers: x = -1e6, q = 0, type = ntypes - 1 */
+struct AtomFill
+{
+    const int*   atomIndex;
+    const float* x;
+    const float* q;             /* atom order, may be null */
+    const int*   type;          /* atom order, may be null */
+    const float* ljCombPerType; /* ntypes x 2, may be null */
+    int          ntypes;
+    XQ*          xq;
+    int*         typeNbat;   /* may be null */
+    float*       ljCombNbat; /* 2 per slot, may be null */
+};
+
+NBS_HD void fillAtomSlot(const AtomFill& f, int slot)
+{
+    const int a = f.atomIndex[slot];
+    XQ        v;
+    v.x = a >= 0 ? f.x[3 * a] : c_farAway;
+    v.y = a >= 0 ? f.x[3 * a + 1] : c_farAway;
+    v.z = a >= 0 ? f.x[3 * a + 2] : c_farAway;
+    v.q = (a >= 0 && f.q != nullptr) ? f.q[a] : 0.0f;
+    f.xq[slot]  = v;
+    const int t = (a >= 0 && f.type != nullptr) ? f.type[a] : f.ntypes - 1;
+    if (f.typeNbat != nullptr)
+    {
+        f.typeNbat[slot] = t;
+    }
+    if (f.ljCombNbat != nullptr && f.ljCombPerType != nullptr)
+    {
+        f.ljCombNbat[2 * slot]     = f.ljCombPerType[2 * t];
+        f.ljCombNbat[2 * slot + 1] = f.ljCombPerType[2 * t + 1];
+    }
+}
+
 } // namespace nbs
 
 #endif

@@ -10,6 +10,9 @@
  *   int  scan(const int* in, int* out, int n)                exclusive prefix sum
  *   int  readInt(const int* p, int* hostValue), readULL(...) synchronising read-back of one value
  *   int  forEach(int n, F f)                                 f(i) for i in [0, n), f copied by value
+ *   int  forEachBlock(int blocks, int threads, size_t scratchBytes, F f)
+ *                                                            per block b: for s < f.numStages(b): f(b, s, t, scratch) for
+ *                                                            t < f.numItems(b, s), a block barrier between stages
  */
 #ifndef NBNXM_B200_GPUSEARCH_DRIVER_H
 #define NBNXM_B200_GPUSEARCH_DRIVER_H
@@ -96,6 +99,29 @@ struct FAssignExclIndex
     NBS_HD void operator()(int i) const { assignExclIndex(w, i); }
 };
 
+struct FGridColumnOfAtom
+{
+    GridBuild g;
+    NBS_HD void operator()(int i) const { gridColumnOfAtom(g, i); }
+};
+struct FGridColumnBins
+{
+    GridBuild g;
+    NBS_HD void operator()(int i) const { gridColumnBins(g, i); }
+};
+struct FGridScatterAtom
+{
+    GridBuild g;
+    NBS_HD void operator()(int i) const { gridScatterAtom(g, i); }
+};
+struct FAtomFill
+{
+    AtomFill f;
+    NBS_HD void operator()(int i) const { fillAtomSlot(f, i); }
+};
+
+constexpr int c_maxColumnAtoms = 8192; /* one block sorts a column in 64 KB of shared memory */
+
 template<typename BE>
 struct SearchState
 {
@@ -108,6 +134,13 @@ struct SearchState
 
     Buf<int> colFirstBin, atomIndex, slotOfAtom, clCount, exclIndex, exclAtoms;
     Buf<BB>  clBB, binBB;
+
+    /* gridding on the device */
+    Buf<int>   colOfAtom, colCount, colAtomStart, colBins, colFill, colAtoms, maxColCount;
+    Buf<float> qAtom, ljCombPerType; /* static per-atom / per-type properties, atom order */
+    Buf<int>   typeAtom;
+    int        ntypes = 0, maxColumnAtoms = 0;
+    bool       haveQ = false, haveType = false, haveLjComb = false;
 
     Buf<int>           entryNumBinPairs, entryBinPairOff, binPairJ, binPairEntry;
     Buf<unsigned char> binPairMask;
@@ -132,13 +165,9 @@ struct SearchState
         }                    \
     } while (0)
 
-/* grid description from the host gridder (putAtomsOnGrid): columns, atom order, topology exclusions */
 template<typename BE>
-int setGrid(BE& be, SearchState<BE>& st, const float* box, int ncx, int ncy, const int* firstBinOfColumn,
-            const int* atomIndex, int nbins, int natoms, const int* exclIndex, const int* exclAtoms)
+int setGridPointers(BE& be, SearchState<BE>& st, const float* box, int ncx, int ncy, int nbins, int natoms)
 {
-    const int ncol   = ncx * ncy;
-    const int nslots = nbins * c_binAtoms;
     for (int d = 0; d < 3; d++)
     {
         st.g.box[d] = box[d];
@@ -149,23 +178,25 @@ int setGrid(BE& be, SearchState<BE>& st, const float* box, int ncx, int ncy, con
     st.g.ncy         = ncy;
     st.g.nbins       = nbins;
     st.g.natoms      = natoms;
-    NBS_TRY(be.reserve(st.colFirstBin, ncol + 1));
-    NBS_TRY(be.reserve(st.atomIndex, nslots));
-    NBS_TRY(be.reserve(st.slotOfAtom, natoms));
     NBS_TRY(be.reserve(st.clCount, size_t(nbins) * c_binCl));
     NBS_TRY(be.reserve(st.clBB, size_t(nbins) * c_binCl));
     NBS_TRY(be.reserve(st.binBB, nbins));
-    NBS_TRY(be.upload(st.colFirstBin.p, firstBinOfColumn, ncol + 1));
-    NBS_TRY(be.upload(st.atomIndex.p, atomIndex, nslots));
-    NBS_TRY(be.ones(st.slotOfAtom.p, sizeof(int) * natoms)); /* -1 */
     st.g.colFirstBin = st.colFirstBin.p;
     st.g.atomIndex   = st.atomIndex.p;
     st.g.slotOfAtom  = st.slotOfAtom.p;
     st.g.clCount     = st.clCount.p;
     st.g.clBB        = st.clBB.p;
     st.g.binBB       = st.binBB.p;
-    st.g.exclIndex   = nullptr;
-    st.g.exclAtoms   = nullptr;
+    st.haveGrid      = true;
+    return 0;
+}
+
+/* topology exclusions, CSR in atom order (host arrays; null: none) */
+template<typename BE>
+int setExclusions(BE& be, SearchState<BE>& st, int natoms, const int* exclIndex, const int* exclAtoms)
+{
+    st.g.exclIndex = nullptr;
+    st.g.exclAtoms = nullptr;
     if (exclIndex != nullptr && exclAtoms != nullptr)
     {
         const int nex = exclIndex[natoms];
@@ -179,9 +210,130 @@ int setGrid(BE& be, SearchState<BE>& st, const float* box, int ncx, int ncy, con
         st.g.exclIndex = st.exclIndex.p;
         st.g.exclAtoms = st.exclAtoms.p;
     }
-    NBS_TRY(be.forEach(nslots, FSlotOfAtom{ st.atomIndex.p, st.slotOfAtom.p }));
-    st.haveGrid = true;
     return 0;
+}
+
+/* grid description from the host gridder (putAtomsOnGrid): columns, atom order, topology exclusions */
+template<typename BE>
+int setGrid(BE& be, SearchState<BE>& st, const float* box, int ncx, int ncy, const int* firstBinOfColumn,
+            const int* atomIndex, int nbins, int natoms, const int* exclIndex, const int* exclAtoms)
+{
+    const int ncol   = ncx * ncy;
+    const int nslots = nbins * c_binAtoms;
+    NBS_TRY(be.reserve(st.colFirstBin, ncol + 1));
+    NBS_TRY(be.reserve(st.atomIndex, nslots));
+    NBS_TRY(be.reserve(st.slotOfAtom, natoms));
+    NBS_TRY(be.upload(st.colFirstBin.p, firstBinOfColumn, ncol + 1));
+    NBS_TRY(be.upload(st.atomIndex.p, atomIndex, nslots));
+    NBS_TRY(be.ones(st.slotOfAtom.p, sizeof(int) * natoms)); /* -1 */
+    NBS_TRY(setGridPointers(be, st, box, ncx, ncy, nbins, natoms));
+    NBS_TRY(setExclusions(be, st, natoms, exclIndex, exclAtoms));
+    NBS_TRY(be.forEach(nslots, FSlotOfAtom{ st.atomIndex.p, st.slotOfAtom.p }));
+    return 0;
+}
+
+/* static atom properties in atom order (host arrays, any may be null), uploaded once per topology */
+template<typename BE>
+int setAtomProperties(BE& be, SearchState<BE>& st, int natoms, const float* q, const int* type, int ntypes,
+                      const float* ljCombPerType)
+{
+    st.ntypes     = ntypes;
+    st.haveQ      = q != nullptr;
+    st.haveType   = type != nullptr;
+    st.haveLjComb = ljCombPerType != nullptr;
+    if (q != nullptr)
+    {
+        NBS_TRY(be.reserve(st.qAtom, natoms));
+        NBS_TRY(be.upload(st.qAtom.p, q, natoms));
+    }
+    if (type != nullptr)
+    {
+        NBS_TRY(be.reserve(st.typeAtom, natoms));
+        NBS_TRY(be.upload(st.typeAtom.p, type, natoms));
+    }
+    if (ljCombPerType != nullptr)
+    {
+        NBS_TRY(be.reserve(st.ljCombPerType, size_t(ntypes) * 2));
+        NBS_TRY(be.upload(st.ljCombPerType.p, ljCombPerType, size_t(ntypes) * 2));
+    }
+    return 0;
+}
+
+/* nonbonded_verlet_t::putAtomsOnGrid (nbnxm.cpp:78) on the backend: x is natoms rvecs in backend memory, atom order,
+ * inside the rectangular box; ncx / ncy from nbnxm_b200_grid_dims.  Leaves the grid (columns, atom order) in the
+ * search state, ready for buildPairlist; *nbinsOut bins of 64 atoms. */
+template<typename BE>
+int putAtomsOnGrid(BE& be, SearchState<BE>& st, const float* box, int ncx, int ncy, int natoms, const float* x, int* nbinsOut)
+{
+    const int ncol = ncx * ncy;
+    NBS_TRY(be.reserve(st.colOfAtom, natoms));
+    NBS_TRY(be.reserve(st.colAtoms, natoms));
+    NBS_TRY(be.reserve(st.colCount, ncol + 1));
+    NBS_TRY(be.reserve(st.colAtomStart, ncol + 1));
+    NBS_TRY(be.reserve(st.colBins, ncol + 1));
+    NBS_TRY(be.reserve(st.colFirstBin, ncol + 1));
+    NBS_TRY(be.reserve(st.colFill, ncol + 1));
+    NBS_TRY(be.reserve(st.maxColCount, 1));
+    NBS_TRY(be.zero(st.colCount.p, sizeof(int) * (ncol + 1)));
+    NBS_TRY(be.zero(st.colBins.p, sizeof(int) * (ncol + 1)));
+    NBS_TRY(be.zero(st.colFill.p, sizeof(int) * (ncol + 1)));
+    NBS_TRY(be.zero(st.maxColCount.p, sizeof(int)));
+    GridBuild gb{};
+    gb.cellSize[0]  = box[0] / ncx;
+    gb.cellSize[1]  = box[1] / ncy;
+    gb.ncx          = ncx;
+    gb.ncy          = ncy;
+    gb.natoms       = natoms;
+    gb.x            = x;
+    gb.colOfAtom    = st.colOfAtom.p;
+    gb.colCount     = st.colCount.p;
+    gb.colAtomStart = st.colAtomStart.p;
+    gb.colBins      = st.colBins.p;
+    gb.colFirstBin  = st.colFirstBin.p;
+    gb.colFill      = st.colFill.p;
+    gb.colAtoms     = st.colAtoms.p;
+    gb.maxColCount  = st.maxColCount.p;
+    NBS_TRY(be.forEach(natoms, FGridColumnOfAtom{ gb }));
+    NBS_TRY(be.forEach(ncol, FGridColumnBins{ gb }));
+    NBS_TRY(be.scan(gb.colCount, gb.colAtomStart, ncol + 1));
+    NBS_TRY(be.scan(gb.colBins, gb.colFirstBin, ncol + 1));
+    int nbins = 0;
+    NBS_TRY(be.readInt(gb.colFirstBin + ncol, &nbins));
+    NBS_TRY(be.readInt(gb.maxColCount, &st.maxColumnAtoms));
+    if (st.maxColumnAtoms > c_maxColumnAtoms)
+    {
+        return be.fail("gridding on the device: a grid column holds more atoms than one block sorts (8192); use the host gridder");
+    }
+    const int nslots = nbins * c_binAtoms;
+    NBS_TRY(be.reserve(st.atomIndex, nslots));
+    NBS_TRY(be.reserve(st.slotOfAtom, natoms));
+    NBS_TRY(be.ones(st.atomIndex.p, sizeof(int) * nslots)); /* -1: filler */
+    gb.atomIndex  = st.atomIndex.p;
+    gb.slotOfAtom = st.slotOfAtom.p;
+    NBS_TRY(be.forEach(natoms, FGridScatterAtom{ gb }));
+    const int nPad    = nextPow2AtLeast32(st.maxColumnAtoms);
+    const int threads = nPad / 2 < 1024 ? nPad / 2 : 1024;
+    NBS_TRY(be.forEachBlock(ncol, threads, size_t(nPad) * (sizeof(float) + sizeof(int)), ColumnSort{ gb, nPad }));
+    NBS_TRY(setGridPointers(be, st, box, ncx, ncy, nbins, natoms));
+    *nbinsOut = nbins;
+    return 0;
+}
+
+/* atom data in nbat order from the grid in the state and the properties of setAtomProperties */
+template<typename BE>
+int fillAtomData(BE& be, SearchState<BE>& st, const float* x, XQ* xq, int* typeNbat, float* ljCombNbat)
+{
+    AtomFill f{};
+    f.atomIndex     = st.atomIndex.p;
+    f.x             = x;
+    f.q             = st.haveQ ? st.qAtom.p : nullptr;
+    f.type          = st.haveType ? st.typeAtom.p : nullptr;
+    f.ljCombPerType = st.haveLjComb ? st.ljCombPerType.p : nullptr;
+    f.ntypes        = st.ntypes;
+    f.xq            = xq;
+    f.typeNbat      = typeNbat;
+    f.ljCombNbat    = ljCombNbat;
+    return be.forEach(st.g.nbins * c_binAtoms, FAtomFill{ f });
 }
 
 /* constructPairlist (pairlist.cpp:4056) for the GPU layout from coordinates xq in nbat order; arguments as

@@ -396,16 +396,13 @@ int nbnxm_b200_init_pairlist_device(nbnxm_b200_t* nb, int iloc, const nbnxm_b200
     return initPairlist(nb, iloc, d_sci, nsci, d_cj_packed, ncj_packed, d_excl, nexcl, na_ci, cudaMemcpyDeviceToDevice);
 }
 
-int nbnxm_b200_init_atomdata(nbnxm_b200_t* nb, int natoms, int natoms_local, const int* atom_type, const float* lj_comb)
+/* buffers of gpu_init_atomdata (nbnxm_gpu_data_mgmt.cpp:1006) for natoms nbat slots, contents left to the caller */
+static int reserveAtomdata(nbnxm_b200_t* nb, int natoms, int natoms_local)
 {
-    if (!nb || natoms < 0 || natoms_local < 0 || natoms_local > natoms) return fail("nbnxm_b200_init_atomdata: bad argument");
     if (natoms % (c_clusterSize * c_superClusterSize) != 0 && natoms % c_clusterSize != 0)
     {
         return fail("nbnxm_b200_init_atomdata: natoms (%d) must be a multiple of the cluster size", natoms);
     }
-    const bool comb = usesLjComb(nb->params.vdw_type);
-    if (comb && !lj_comb) return fail("nbnxm_b200_init_atomdata: this VdW flavor needs lj_comb");
-    if (!comb && !atom_type) return fail("nbnxm_b200_init_atomdata: this VdW flavor needs atom types");
     CU(cudaSetDevice(nb->device));
     cudaStream_t st = nb->stream[0];
     const bool   realloc = size_t(natoms) > nb->xq.alloc;
@@ -426,12 +423,29 @@ int nbnxm_b200_init_atomdata(nbnxm_b200_t* nb, int natoms, int natoms_local, con
     }
     nb->natoms      = natoms;
     nb->natomsLocal = natoms_local;
+    return 0;
+}
+
+int nbnxm_b200_init_atomdata(nbnxm_b200_t* nb, int natoms, int natoms_local, const int* atom_type, const float* lj_comb)
+{
+    if (!nb || natoms < 0 || natoms_local < 0 || natoms_local > natoms) return fail("nbnxm_b200_init_atomdata: bad argument");
+    const bool comb = usesLjComb(nb->params.vdw_type);
+    if (comb && !lj_comb) return fail("nbnxm_b200_init_atomdata: this VdW flavor needs lj_comb");
+    if (!comb && !atom_type) return fail("nbnxm_b200_init_atomdata: this VdW flavor needs atom types");
+    if (reserveAtomdata(nb, natoms, natoms_local)) return 1;
+    cudaStream_t st = nb->stream[0];
     if (natoms > 0)
     {
         if (atom_type) CU(cudaMemcpyAsync(nb->atomType.p, atom_type, sizeof(int) * natoms, cudaMemcpyHostToDevice, st));
         if (lj_comb) CU(cudaMemcpyAsync(nb->ljComb.p, lj_comb, sizeof(float2) * natoms, cudaMemcpyHostToDevice, st));
     }
     return 0;
+}
+
+int nbnxm_b200_init_atomdata_device(nbnxm_b200_t* nb, int natoms, int natoms_local)
+{
+    if (!nb || natoms < 0 || natoms_local < 0 || natoms_local > natoms) return fail("nbnxm_b200_init_atomdata_device: bad argument");
+    return reserveAtomdata(nb, natoms, natoms_local);
 }
 
 int nbnxm_b200_upload_shiftvec(nbnxm_b200_t* nb, const float* shift_vec, int dynamic_box)

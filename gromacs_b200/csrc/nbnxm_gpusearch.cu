@@ -27,6 +27,24 @@ __global__ void __launch_bounds__(256) search_items_kernel(const F f, int n)
     }
 }
 
+/* block kernel: stages of independent items separated by block barriers, scratch in dynamic shared memory */
+template<typename F>
+__global__ void __launch_bounds__(1024) search_block_kernel(const F f)
+{
+    extern __shared__ __align__(16) unsigned char scratch[];
+    const int b  = blockIdx.x;
+    const int ns = f.numStages(b);
+    for (int s = 0; s < ns; s++)
+    {
+        const int ni = f.numItems(b, s);
+        for (int t = threadIdx.x; t < ni; t += blockDim.x)
+        {
+            f(b, s, t, scratch);
+        }
+        __syncthreads();
+    }
+}
+
 /* ---- exclusive prefix sum: tiles of 8192 ints per CTA (the block scan of nbnxm_sci_histogram_scan_kernel), tile
  * totals scanned by the same kernel, then added back ---- */
 constexpr int c_scanTile = 8192;
@@ -171,6 +189,19 @@ struct CudaSearchBackend
         CU(cudaGetLastError());
         return 0;
     }
+    template<typename F>
+    int forEachBlock(int blocks, int threads, size_t scratchBytes, F f)
+    {
+        if (blocks <= 0) return 0;
+        if (scratchBytes > 48 * 1024)
+        {
+            CU(cudaFuncSetAttribute(search_block_kernel<F>, cudaFuncAttributeMaxDynamicSharedMemorySize, int(scratchBytes)));
+        }
+        search_block_kernel<F><<<blocks, threads, scratchBytes, st>>>(f);
+        launches++;
+        CU(cudaGetLastError());
+        return 0;
+    }
 };
 
 template<typename... B>
@@ -188,7 +219,9 @@ struct nbnxm_b200_gpu_search
     nbb::CudaSearchBackend                   be;
     nbs::SearchState<nbb::CudaSearchBackend> st;
     cudaEvent_t                              evStart = nullptr, evStop = nullptr;
-    float                                    lastBuildMs = 0.0f;
+    float                                    lastBuildMs = 0.0f, lastGridMs = 0.0f;
+    int                                      numAtomsSet = 0;
+    bool                                     haveExclSet = false;
 };
 
 using nbb::fail;
@@ -222,7 +255,9 @@ int nbnxm_b200_gpu_search_free(nbnxm_b200_gpu_search_t* s)
     nbb::releaseAll(t.colFirstBin, t.atomIndex, t.slotOfAtom, t.clCount, t.exclIndex, t.exclAtoms, t.clBB, t.binBB,
                     t.entryNumBinPairs, t.entryBinPairOff, t.binPairJ, t.binPairEntry, t.binPairMask, t.entryNumJ,
                     t.entryGroups, t.entryCjOff, t.entryNumSci, t.entrySciOff, t.entryNonEmpty, t.entryCompactOff,
-                    t.compactEntry, t.exclFlag, t.exclOff, t.numClusterPairs, t.sci, t.cjp, t.excl, s->be.tileSums, s->be.tileOffsets);
+                    t.compactEntry, t.exclFlag, t.exclOff, t.numClusterPairs, t.sci, t.cjp, t.excl, s->be.tileSums, s->be.tileOffsets,
+                    t.colOfAtom, t.colCount, t.colAtomStart, t.colBins, t.colFill, t.colAtoms, t.maxColCount, t.qAtom, t.ljCombPerType,
+                    t.typeAtom);
     if (s->be.h_value) cudaFreeHost(s->be.h_value);
     if (s->evStart) cudaEventDestroy(s->evStart);
     if (s->evStop) cudaEventDestroy(s->evStop);
@@ -250,6 +285,91 @@ int nbnxm_b200_gpu_search_set_grid(nbnxm_b200_gpu_search_t* s, const float* box,
     CU(cudaStreamSynchronize(s->be.st));
     s->nb->launches += s->be.launches;
     s->be.launches = 0;
+    return 0;
+}
+
+int nbnxm_b200_gpu_search_set_atoms(nbnxm_b200_gpu_search_t* s, int natoms, const float* q, const int* type, int ntypes,
+                                    const float* lj_comb_per_type, const int* excl_index, const int* excl_atoms)
+{
+    if (!s || natoms < 1 || ntypes < 1) return fail("nbnxm_b200_gpu_search_set_atoms: bad argument");
+    CU(cudaSetDevice(s->device));
+    CU(cudaStreamSynchronize(s->be.st));
+    if (nbs::setAtomProperties(s->be, s->st, natoms, q, type, ntypes, lj_comb_per_type)) return 1;
+    if (nbs::setExclusions(s->be, s->st, natoms, excl_index, excl_atoms)) return 1;
+    s->numAtomsSet  = natoms;
+    s->haveExclSet  = excl_index != nullptr && excl_atoms != nullptr;
+    CU(cudaStreamSynchronize(s->be.st));
+    return 0;
+}
+
+int nbnxm_b200_gpu_search_put_atoms_on_grid(nbnxm_b200_gpu_search_t* s, const float* box, int nslabs, const float* d_x,
+                                            void* x_ready_event, int* natoms_nbat, int* nbins_out, int* ncx_out, int* ncy_out)
+{
+    if (!s || !box || !d_x) return fail("nbnxm_b200_gpu_search_put_atoms_on_grid: null argument");
+    if (s->numAtomsSet < 1) return fail("nbnxm_b200_gpu_search_put_atoms_on_grid: call nbnxm_b200_gpu_search_set_atoms first");
+    nbnxm_b200* nb = s->nb;
+    const bool  comb = (nb->params.vdw_type == NBNXM_B200_VDW_CUT_COMB_GEOM || nb->params.vdw_type == NBNXM_B200_VDW_CUT_COMB_LB);
+    if (comb && !s->st.haveLjComb) return fail("nbnxm_b200_gpu_search_put_atoms_on_grid: this VdW flavor needs lj_comb_per_type");
+    if (!comb && !s->st.haveType) return fail("nbnxm_b200_gpu_search_put_atoms_on_grid: this VdW flavor needs atom types");
+    CU(cudaSetDevice(s->device));
+    const int natoms = s->numAtomsSet;
+    int       ncx = 1, ncy = 1, nbins = 0;
+    if (nbnxm_b200_grid_dims(box, natoms, nslabs, &ncx, &ncy)) return fail("nbnxm_b200_gpu_search_put_atoms_on_grid: grid dimensions");
+    if (x_ready_event) CU(cudaStreamWaitEvent(s->be.st, static_cast<cudaEvent_t>(x_ready_event), 0));
+    CU(cudaEventRecord(s->evStart, s->be.st));
+    if (nbs::putAtomsOnGrid(s->be, s->st, box, ncx, ncy, natoms, d_x, &nbins)) return 1;
+    const int nslots = nbins * nbs::c_binAtoms;
+    /* gpu_init_atomdata for the new grid, then atom data in nbat order, written on the device */
+    if (nbnxm_b200_init_atomdata_device(nb, nslots, nslots)) return 1;
+    if (nbs::fillAtomData(s->be, s->st, d_x, reinterpret_cast<nbs::XQ*>(nb->xq.p), comb ? nullptr : nb->atomType.p,
+                          comb ? reinterpret_cast<float*>(nb->ljComb.p) : nullptr))
+    {
+        return 1;
+    }
+    /* the buffer ops of the following steps use the same order: x_to_nbat_x (slot -> atom), reduce_f (atom -> slot) */
+    if (size_t(nslots) > nb->atomIndex.alloc || size_t(natoms) > nb->cell.alloc)
+    {
+        CU(cudaStreamSynchronize(nb->stream[0]));
+        CU(cudaStreamSynchronize(nb->stream[1]));
+    }
+    CU(nb->atomIndex.reserve(nslots));
+    CU(nb->cell.reserve(natoms));
+    CU(cudaMemcpyAsync(nb->atomIndex.p, s->st.atomIndex.p, sizeof(int) * nslots, cudaMemcpyDeviceToDevice, s->be.st));
+    CU(cudaMemcpyAsync(nb->cell.p, s->st.slotOfAtom.p, sizeof(int) * natoms, cudaMemcpyDeviceToDevice, s->be.st));
+    nb->numCells = natoms;
+    nb->xgrids.assign(1, nbnxm_b200::XGrid());
+    nb->xgrids[0].first = 0;
+    nb->xgrids[0].n     = nslots;
+    CU(cudaEventRecord(s->evStop, s->be.st));
+    CU(cudaStreamSynchronize(s->be.st));
+    CU(cudaGetLastError());
+    CU(cudaEventElapsedTime(&s->lastGridMs, s->evStart, s->evStop));
+    nb->launches += s->be.launches;
+    s->be.launches = 0;
+    if (!s->haveExclSet)
+    {
+        s->st.g.exclIndex = nullptr;
+        s->st.g.exclAtoms = nullptr;
+    }
+    if (natoms_nbat) *natoms_nbat = nslots;
+    if (nbins_out) *nbins_out = nbins;
+    if (ncx_out) *ncx_out = ncx;
+    if (ncy_out) *ncy_out = ncy;
+    return 0;
+}
+
+int nbnxm_b200_gpu_search_get_order(nbnxm_b200_gpu_search_t* s, int* atom_index, int* first_bin_of_column, float* grid_ms)
+{
+    if (!s || !s->st.haveGrid) return fail("nbnxm_b200_gpu_search_get_order: no grid");
+    CU(cudaSetDevice(s->device));
+    CU(cudaStreamSynchronize(s->be.st));
+    const nbs::Grid& g = s->st.g;
+    if (atom_index) CU(cudaMemcpy(atom_index, s->st.atomIndex.p, sizeof(int) * g.nbins * nbs::c_binAtoms, cudaMemcpyDeviceToHost));
+    if (first_bin_of_column)
+    {
+        CU(cudaMemcpy(first_bin_of_column, s->st.colFirstBin.p, sizeof(int) * (g.ncx * g.ncy + 1), cudaMemcpyDeviceToHost));
+    }
+    if (grid_ms) *grid_ms = s->lastGridMs;
     return 0;
 }
 

@@ -80,6 +80,24 @@ struct nbnxm_b200_grid
 
 extern "C" {
 
+int nbnxm_b200_grid_dims(const float* box, int natoms, int nslabs, int* ncx, int* ncy)
+{
+    if (!box || !ncx || !ncy || natoms <= 0 || nslabs < 1) return fail("grid_dims: bad argument");
+    /* approximately cubic clusters of 8 atoms, 2x2 of them per column cross-section; round the column
+     * count down (grid.cpp:161-182, 296-311) */
+    const double density = natoms / (double(box[0]) * box[1] * box[2]);
+    const double tlen    = std::cbrt(c_cl / density);
+    *ncx                 = std::max(1, int(box[0] / (2 * tlen)));
+    if (nslabs > 1)
+    {
+        /* x-slab decomposition over nslabs GPUs: a whole number of columns per slab, so that the slabs hold equal
+         * numbers of atoms (the reference grids every domain separately) */
+        *ncx = std::max(nslabs, (*ncx / nslabs) * nslabs);
+    }
+    *ncy = std::max(1, int(box[1] / (2 * tlen)));
+    return 0;
+}
+
 int nbnxm_b200_grid_create(nbnxm_b200_grid_t** out, const float* box, int natoms, const float* x, int nthreads)
 {
     return nbnxm_b200_grid_create_slabs(out, box, natoms, x, nthreads, 1);
@@ -92,18 +110,7 @@ int nbnxm_b200_grid_create_slabs(nbnxm_b200_grid_t** out, const float* box, int 
     nbnxm_b200_grid* g = new nbnxm_b200_grid();
     for (int d = 0; d < 3; d++) g->box[d] = box[d];
     g->natoms = natoms;
-    /* approximately cubic clusters of 8 atoms, 2x2 of them per column cross-section; round the column
-     * count down (grid.cpp:161-182, 296-311) */
-    const double density = natoms / (double(box[0]) * box[1] * box[2]);
-    const double tlen    = std::cbrt(c_cl / density);
-    g->ncx               = std::max(1, int(box[0] / (2 * tlen)));
-    if (nslabs > 1)
-    {
-        /* x-slab decomposition over nslabs GPUs: a whole number of columns per slab, so that the slabs hold equal
-         * numbers of atoms (the reference grids every domain separately) */
-        g->ncx = std::max(nslabs, (g->ncx / nslabs) * nslabs);
-    }
-    g->ncy               = std::max(1, int(box[1] / (2 * tlen)));
+    nbnxm_b200_grid_dims(box, natoms, nslabs, &g->ncx, &g->ncy);
     g->cellSize[0]       = box[0] / g->ncx;
     g->cellSize[1]       = box[1] / g->ncy;
     const int ncol       = g->ncx * g->ncy;

@@ -26,7 +26,7 @@ VDW_TYPES = {"Cut": 0, "CutCombGeom": 1, "CutCombLB": 2, "FSwitch": 3, "PSwitch"
 EXPORTED_SYMBOLS = [
     "nbnxm_b200_last_error", "nbnxm_b200_init", "nbnxm_b200_free", "nbnxm_b200_update_params", "nbnxm_b200_do_force_step", "nbnxm_b200_do_force_step_pipelined", "nbnxm_b200_peer_blob_size", "nbnxm_b200_peer_export", "nbnxm_b200_peer_import",
     "nbnxm_b200_peer_close", "nbnxm_b200_peer_error",
-    "nbnxm_b200_init_pairlist", "nbnxm_b200_init_pairlist_device", "nbnxm_b200_init_atomdata", "nbnxm_b200_upload_shiftvec",
+    "nbnxm_b200_init_pairlist", "nbnxm_b200_init_pairlist_device", "nbnxm_b200_init_atomdata", "nbnxm_b200_init_atomdata_device", "nbnxm_b200_upload_shiftvec",
     "nbnxm_b200_copy_xq_to_gpu", "nbnxm_b200_init_x_to_nbat_x", "nbnxm_b200_x_to_nbat_x",
     "nbnxm_b200_launch_kernel", "nbnxm_b200_launch_kernel_pruneonly", "nbnxm_b200_launch_cpyback",
     "nbnxm_b200_try_finish_task", "nbnxm_b200_wait_finish_task", "nbnxm_b200_clear_outputs",

@@ -9,11 +9,12 @@ import numpy as np
 from .nbnxm import AtomData, NbnxmError, PairlistGpu, load_library
 
 SEARCH_SYMBOLS = [
-    "nbnxm_b200_grid_create", "nbnxm_b200_grid_create_slabs", "nbnxm_b200_grid_free", "nbnxm_b200_grid_info", "nbnxm_b200_grid_get_order",
+    "nbnxm_b200_grid_dims", "nbnxm_b200_grid_create", "nbnxm_b200_grid_create_slabs", "nbnxm_b200_grid_free", "nbnxm_b200_grid_info", "nbnxm_b200_grid_get_order",
     "nbnxm_b200_grid_fill_atomdata", "nbnxm_b200_pairlist_build", "nbnxm_b200_pairlist_sizes",
     "nbnxm_b200_pairlist_copy",
     "nbnxm_b200_gpu_search_create", "nbnxm_b200_gpu_search_free", "nbnxm_b200_gpu_search_set_grid",
     "nbnxm_b200_gpu_search_build", "nbnxm_b200_gpu_search_sizes", "nbnxm_b200_gpu_search_download",
+    "nbnxm_b200_gpu_search_set_atoms", "nbnxm_b200_gpu_search_put_atoms_on_grid", "nbnxm_b200_gpu_search_get_order",
 ]
 
 
@@ -91,19 +92,57 @@ class GpuPairSearch:
     """constructPairlist + gpu_init_pairlist on the device (nbnxm_b200_gpu_search_*): the list is built from the
     coordinates resident in the NbnxmGpu handle and becomes its list for `iloc`; nothing is staged on the host."""
 
-    def __init__(self, nb, grid: Grid, excl_index=None, excl_atoms=None):
+    def __init__(self, nb, grid: Grid = None, excl_index=None, excl_atoms=None):
+        """With a host Grid: its columns / atom order / exclusions are uploaded (nbnxm_b200_gpu_search_set_grid).
+        Without: call set_atoms() once and put_atoms_on_grid() at every search step (gridding on the device)."""
         self._lib = load_library()
         self._nb = nb
         self._s = C.c_void_p()
         self.grid = grid
-        nb._check(self._lib.nbnxm_b200_gpu_search_create(C.byref(self._s), nb._h))
-        ei = None if excl_index is None else np.ascontiguousarray(excl_index, np.int32)
-        ea = None if excl_atoms is None else np.ascontiguousarray(excl_atoms, np.int32)
-        nb._check(self._lib.nbnxm_b200_gpu_search_set_grid(
-            self._s, _p(grid.box, C.c_float), C.c_int(grid.ncx), C.c_int(grid.ncy), _p(grid.first_bin_of_column, C.c_int),
-            _p(grid.atom_index, C.c_int), C.c_int(grid.nbins), C.c_int(grid.natoms), _p(ei, C.c_int), _p(ea, C.c_int)))
+        self.nbins = 0
         self.build_ms = 0.0
         self.nci_tot = 0
+        nb._check(self._lib.nbnxm_b200_gpu_search_create(C.byref(self._s), nb._h))
+        if grid is not None:
+            ei = None if excl_index is None else np.ascontiguousarray(excl_index, np.int32)
+            ea = None if excl_atoms is None else np.ascontiguousarray(excl_atoms, np.int32)
+            nb._check(self._lib.nbnxm_b200_gpu_search_set_grid(
+                self._s, _p(grid.box, C.c_float), C.c_int(grid.ncx), C.c_int(grid.ncy), _p(grid.first_bin_of_column, C.c_int),
+                _p(grid.atom_index, C.c_int), C.c_int(grid.nbins), C.c_int(grid.natoms), _p(ei, C.c_int), _p(ea, C.c_int)))
+            self.nbins = grid.nbins
+
+    def set_atoms(self, q, atom_type, ntypes, lj_comb_per_type=None, excl_index=None, excl_atoms=None):
+        """Static per-atom properties and topology exclusions, atom order (nbnxm_b200_gpu_search_set_atoms)."""
+        q = None if q is None else np.ascontiguousarray(q, np.float32)
+        t = None if atom_type is None else np.ascontiguousarray(atom_type, np.int32)
+        lj = None if lj_comb_per_type is None else np.ascontiguousarray(lj_comb_per_type, np.float32)
+        ei = None if excl_index is None else np.ascontiguousarray(excl_index, np.int32)
+        ea = None if excl_atoms is None else np.ascontiguousarray(excl_atoms, np.int32)
+        self.natoms = (q if q is not None else t).shape[0]
+        self._nb._check(self._lib.nbnxm_b200_gpu_search_set_atoms(
+            self._s, C.c_int(self.natoms), _p(q, C.c_float), _p(t, C.c_int), C.c_int(ntypes), _p(lj, C.c_float),
+            _p(ei, C.c_int), _p(ea, C.c_int)))
+
+    def put_atoms_on_grid(self, box, d_x_ptr, nslabs=1, x_ready_event=None):
+        """putAtomsOnGrid + setAtomProperties + gpu_init_atomdata on the device from natoms rvecs in device memory;
+        returns (natoms_nbat, nbins, ncx, ncy)."""
+        box = np.ascontiguousarray(box, np.float32)
+        n, nb_, ncx, ncy = C.c_int(), C.c_int(), C.c_int(), C.c_int()
+        self._nb._check(self._lib.nbnxm_b200_gpu_search_put_atoms_on_grid(
+            self._s, _p(box, C.c_float), C.c_int(nslabs), C.c_void_p(d_x_ptr), C.c_void_p(x_ready_event), C.byref(n),
+            C.byref(nb_), C.byref(ncx), C.byref(ncy)))
+        self.nbins, self.ncx, self.ncy = nb_.value, ncx.value, ncy.value
+        self._nb._natoms = n.value
+        return n.value, nb_.value, ncx.value, ncy.value
+
+    def get_order(self):
+        """(atom_index[natoms_nbat], first_bin_of_column[ncx*ncy+1], grid_ms) of the grid in use."""
+        ncol = (self.grid.ncx * self.grid.ncy) if self.grid is not None else self.ncx * self.ncy
+        ai = np.zeros(self.nbins * 64, np.int32)
+        fb = np.zeros(ncol + 1, np.int32)
+        ms = C.c_float()
+        self._nb._check(self._lib.nbnxm_b200_gpu_search_get_order(self._s, _p(ai, C.c_int), _p(fb, C.c_int), C.byref(ms)))
+        return ai, fb, ms.value
 
     def free(self):
         if self._s:
@@ -118,8 +157,8 @@ class GpuPairSearch:
 
     def build(self, rlist, iloc=0, min_sci=0, bins=None, j_bins=None, inter_zone=False, required_tx=0):
         """Builds and installs the list; returns (nsci, ncj_packed, nexcl)."""
-        b0, b1 = bins if bins is not None else (0, self.grid.nbins)
-        j0, j1 = j_bins if j_bins is not None else (0, self.grid.nbins)
+        b0, b1 = bins if bins is not None else (0, self.nbins)
+        j0, j1 = j_bins if j_bins is not None else (0, self.nbins)
         self._nb._check(self._lib.nbnxm_b200_gpu_search_build(
             self._s, C.c_int(iloc), C.c_float(rlist), C.c_int(min_sci), C.c_int(b0), C.c_int(b1), C.c_int(j0), C.c_int(j1),
             C.c_int(int(inter_zone)), C.c_int(required_tx)))

@@ -132,6 +132,9 @@ int nbnxm_b200_init_pairlist_device(nbnxm_b200_t* nb, int iloc, const nbnxm_b200
  * as the flavor needs (types for Cut/FSwitch/PSwitch/Ewald*, lj_comb for CutComb*). */
 int nbnxm_b200_init_atomdata(nbnxm_b200_t* nb, int natoms, int natoms_local, const int* atom_type,
                              const float* lj_comb);
+/* the same buffers without the uploads: types / lj_comb / xq are written on the device
+ * (nbnxm_b200_gpu_search_put_atoms_on_grid, include/nbnxm_b200_search.h) */
+int nbnxm_b200_init_atomdata_device(nbnxm_b200_t* nb, int natoms, int natoms_local);
 /* gpu_upload_shiftvec, nbnxm_gpu_data_mgmt.cpp:719.  shift_vec: 45 x 3 floats */
 int nbnxm_b200_upload_shiftvec(nbnxm_b200_t* nb, const float* shift_vec, int dynamic_box);
 /* gpu_copy_xq_to_gpu, nbnxm_gpu_data_mgmt.cpp:1489.  xq: natoms x 4 floats (nbat->x(), XYZQ) */

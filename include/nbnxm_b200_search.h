@@ -23,6 +23,9 @@ extern "C" {
 
 typedef struct nbnxm_b200_grid nbnxm_b200_grid_t;
 
+/* grid dimensions for natoms atoms in the box: columns of about 2 x 2 clusters of 8 atoms in cross-section
+ * (Grid::setDimensions, src/gromacs/nbnxm/grid.cpp:161-311); ncx a multiple of nslabs when nslabs > 1 */
+int nbnxm_b200_grid_dims(const float* box, int natoms, int nslabs, int* ncx, int* ncy);
 /* nonbonded_verlet_t::putAtomsOnGrid (src/gromacs/nbnxm/nbnxm.cpp:78): bins natoms atoms (x: natoms x 3,
  * inside the rectangular box [0, box)) and sorts them into nbat order. */
 int nbnxm_b200_grid_create(nbnxm_b200_grid_t** grid, const float* box, int natoms, const float* x, int nthreads);
@@ -76,6 +79,21 @@ int nbnxm_b200_gpu_search_free(nbnxm_b200_gpu_search_t* search);
 int nbnxm_b200_gpu_search_set_grid(nbnxm_b200_gpu_search_t* search, const float* box, int ncx, int ncy,
                                    const int* first_bin_of_column, const int* atom_index, int nbins, int natoms,
                                    const int* excl_index, const int* excl_atoms);
+/* ---- the grid itself on the GPU: nonbonded_verlet_t::putAtomsOnGrid + setAtomProperties + gpu_init_atomdata
+ * (nbnxm.cpp:78, atomdata.cpp:1107, nbnxm_gpu_data_mgmt.cpp:1006) from coordinates in device memory ----
+ * set_atoms (once per topology): charges, types (atom order), per-type LJ combination parameters (ntypes x 2, for the
+ * CutComb* flavors) and the topology exclusions (CSR in atom order); any array may be NULL.
+ * put_atoms_on_grid (every search step): d_x = natoms rvecs in device memory, atom order, inside the box; bins the
+ * atoms into the columns of nbnxm_b200_grid_dims, sorts every column (one block per column, bitonic networks in
+ * shared memory; a column may hold at most 8192 atoms), sizes the handle's atom buffers for the new grid and writes
+ * xq / types / lj_comb in nbat order, the slot -> atom map used by nbnxm_b200_x_to_nbat_x and the atom -> slot map
+ * used by nbnxm_b200_reduce_f.  The order equals nbnxm_b200_grid_create's.  Follow with nbnxm_b200_gpu_search_build. */
+int nbnxm_b200_gpu_search_set_atoms(nbnxm_b200_gpu_search_t* search, int natoms, const float* q, const int* type, int ntypes,
+                                    const float* lj_comb_per_type, const int* excl_index, const int* excl_atoms);
+int nbnxm_b200_gpu_search_put_atoms_on_grid(nbnxm_b200_gpu_search_t* search, const float* box, int nslabs, const float* d_x,
+                                            void* x_ready_event, int* natoms_nbat, int* nbins, int* ncx, int* ncy);
+/* host copies of the grid order (GridSet::atomIndices, Grid::cxy_ind) and the device time of the last gridding (ms) */
+int nbnxm_b200_gpu_search_get_order(nbnxm_b200_gpu_search_t* search, int* atom_index, int* first_bin_of_column, float* grid_ms);
 /* arguments as nbnxm_b200_pairlist_build; the result becomes the handle's list for iloc (haveFreshList set) */
 int nbnxm_b200_gpu_search_build(nbnxm_b200_gpu_search_t* search, int iloc, float rlist, int min_sci, int bin_begin,
                                 int bin_end, int j_bin_lo, int j_bin_hi, int inter_zone, int required_tx);

@@ -39,4 +39,26 @@ print(json.dumps({"host_list_upload_s": h2d_s, "workload": name, "natoms": wl.bo
                   "gpu_build_ms": ms, "host_build_s": host_s, "host_threads": wl.grid.nthreads,
                   "list_bytes": int(ref.sci.nbytes + ref.cjPacked.nbytes + ref.excl.nbytes)}))
 search.free()
+# the whole search step on the device: gridding from atom-order coordinates in device memory, then the list
+import torch  # noqa: E402
+from gromacs_b200.pairsearch import Grid  # noqa: E402
+import numpy as np  # noqa: E402
+t0 = time.time()
+Grid(wl.box.box, wl.box.x)
+host_grid_s = time.time() - t0
+x_dev = torch.from_numpy(np.ascontiguousarray(wl.box.x, np.float32)).cuda()
+torch.cuda.synchronize()
+s2 = GpuPairSearch(nb)
+s2.set_atoms(wl.box.q, wl.box.type, wl.nbat.numTypes, None, wl.box.excl_index, wl.box.excl_atoms)
+grid_ms, list_ms = [], []
+for _ in range(builds):
+    dims = s2.put_atoms_on_grid(wl.box.box, x_dev.data_ptr())
+    ai, fb, gms = s2.get_order()
+    sizes2 = s2.build(wl.cfg["rlist_outer"], LOCAL, min_sci=min_sci)
+    grid_ms.append(gms)
+    list_ms.append(s2.build_ms)
+print(json.dumps({"device_search_step": True, "workload": name, "gpu_grid_ms": grid_ms, "gpu_list_ms": list_ms,
+                  "host_grid_s": host_grid_s, "same_order_as_host": bool(np.array_equal(ai, wl.grid.atom_index)),
+                  "same_sizes_as_host": sizes2 == sizes, "max_column_atoms": int(np.diff(fb).max() * 64)}))
+s2.free()
 nb.gpu_free()

@@ -84,6 +84,25 @@ struct HostBackend
         }
         return 0;
     }
+    template<typename F>
+    int forEachBlock(int blocks, int /*threads*/, size_t scratchBytes, F f)
+    {
+        void* scratch = std::malloc(scratchBytes);
+        for (int b = blocks - 1; b >= 0; b--)
+        {
+            std::memset(scratch, 0x5a, scratchBytes);
+            const int ns = f.numStages(b);
+            for (int s = 0; s < ns; s++)
+            {
+                for (int t = f.numItems(b, s) - 1; t >= 0; t--)
+                {
+                    f(b, s, t, scratch);
+                }
+            }
+        }
+        std::free(scratch);
+        return 0;
+    }
     int fail(const char* msg)
     {
         std::fprintf(stderr, "search_emu: %s\n", msg);
@@ -102,6 +121,27 @@ int search_emu_set_grid(const float* box, int ncx, int ncy, const int* first_bin
                         int natoms, const int* excl_index, const int* excl_atoms)
 {
     return nbs::setGrid(g_be, g_st, box, ncx, ncy, first_bin_of_column, atom_index, nbins, natoms, excl_index, excl_atoms);
+}
+
+int search_emu_put_atoms_on_grid(const float* box, int ncx, int ncy, int natoms, const float* x, const int* excl_index,
+                                 const int* excl_atoms, int* nbins)
+{
+    if (nbs::putAtomsOnGrid(g_be, g_st, box, ncx, ncy, natoms, x, nbins)) return 1;
+    return nbs::setExclusions(g_be, g_st, natoms, excl_index, excl_atoms);
+}
+
+int search_emu_get_order(int* atom_index, int* first_bin_of_column)
+{
+    std::memcpy(atom_index, g_st.atomIndex.p, sizeof(int) * g_st.g.nbins * nbs::c_binAtoms);
+    std::memcpy(first_bin_of_column, g_st.colFirstBin.p, sizeof(int) * (g_st.g.ncx * g_st.g.ncy + 1));
+    return 0;
+}
+
+int search_emu_fill_atomdata(int natoms, const float* x, const float* q, const int* type, int ntypes, const float* lj_comb_per_type,
+                             float* xq, int* type_nbat, float* lj_comb)
+{
+    if (nbs::setAtomProperties(g_be, g_st, natoms, q, type, ntypes, lj_comb_per_type)) return 1;
+    return nbs::fillAtomData(g_be, g_st, x, reinterpret_cast<nbs::XQ*>(xq), type_nbat, lj_comb);
 }
 
 int search_emu_build(const float* xq, float rlist, int min_sci, int bin_begin, int bin_end, int j_bin_lo, int j_bin_hi,

@@ -179,3 +179,95 @@ def test_force_reduction_gathers_nbat_forces_into_atom_order():
                 assert np.allclose(got[sl], want[sl], rtol=1e-6, atol=1e-4 * np.abs(f_atoms).max() * 1e-3)
     finally:
         nb.gpu_free()
+
+
+def device_search_step(nb, box, x, q, atom_type, ntypes, ei, ea, rlist, min_sci):
+    """putAtomsOnGrid + constructPairlist on the device from coordinates in device memory (atom order)"""
+    import torch
+    from gromacs_b200 import LOCAL
+    from gromacs_b200.pairsearch import GpuPairSearch
+    x_dev = torch.from_numpy(np.ascontiguousarray(x, np.float32)).cuda()
+    torch.cuda.synchronize()
+    search = GpuPairSearch(nb)
+    search.set_atoms(q, atom_type, ntypes, None, ei, ea)
+    dims = search.put_atoms_on_grid(box, x_dev.data_ptr())
+    search.put_atoms_on_grid(box, x_dev.data_ptr())        # again: every buffer is reused
+    atom_index, first_bin, grid_ms = search.get_order()
+    sizes = search.build(rlist, LOCAL, min_sci=min_sci)
+    sizes = search.build(rlist, LOCAL, min_sci=min_sci)
+    return search, x_dev, dims, atom_index, first_bin, grid_ms, sizes
+
+
+@pytest.mark.parametrize("case,rlist,min_sci", [("bench1_ewald_cutnone", 1.0, 0), ("test243_ewald_cutnone", 0.9, 50)])
+def test_search_step_entirely_on_the_device(case, rlist, min_sci):
+    """grid order, atom data, list and forces from device-resident atom-order coordinates equal the host path's; the
+    force reduction maps the forces back to atom order with the device-built atom -> slot map"""
+    import torch
+    from gromacs_b200 import LOCAL, NbnxmGpu
+    d, grid, nbat = golden_system(case)
+    n = d["sys_x"].shape[0]
+    ref = grid.pairlist(rlist, d["sys_excl_index"], d["sys_excl_atoms"], min_sci=min_sci)
+    nb = NbnxmGpu(product_params(d, vdw="Cut"), nbat)
+    try:
+        nb.gpu_upload_shiftvec(nbat)
+        search, x_dev, dims, atom_index, first_bin, _, sizes = device_search_step(
+            nb, d["sys_box"], d["sys_x"], d["sys_q"], d["sys_type"], int(d["nbat_ntypes"][0]), d["sys_excl_index"],
+            d["sys_excl_atoms"], rlist, min_sci)
+        assert dims == (grid.natoms_nbat, grid.nbins, grid.ncx, grid.ncy)
+        assert np.array_equal(atom_index, grid.atom_index) and np.array_equal(first_bin, grid.first_bin_of_column)
+        got = search.download()
+        assert_same_list((got.sci, got.cjPacked, got.excl), (ref.sci, ref.cjPacked, ref.excl))
+        nb.setupGpuShortRangeWork(LOCAL)
+        f_dev, e_dev = run_step(nb, nbat)
+        # forces back in atom order through the device-built cell map
+        d_total = torch.zeros((n, 3), dtype=torch.float32, device="cuda")
+        torch.cuda.synchronize()
+        nb.gpu_force_reduction_execute(d_total.data_ptr(), None, 0, n, False, nb.streams()[0])
+        nb.gpu_wait_finish_task(__import__("gromacs_b200").StepWorkload(), LOCAL)
+        torch.cuda.synchronize()
+        slots = np.nonzero(grid.atom_index >= 0)[0]
+        f_atoms = np.zeros((n, 3))
+        f_atoms[grid.atom_index[slots]] = f_dev[slots]
+        assert np.array_equal(d_total.cpu().numpy(), f_atoms.astype(np.float32))
+        search.free()
+        # the host path on the same handle
+        nb.gpu_init_atomdata(nbat)
+        nb.gpu_copy_xq_to_gpu(nbat, LOCAL)
+        nb.gpu_init_pairlist(ref, LOCAL)
+        f_host, e_host = run_step(nb, nbat)
+    finally:
+        nb.gpu_free()
+    assert relrms(f_dev, f_host) < 1e-6
+    assert abs(e_dev[0] - e_host[0]) <= 1e-6 * abs(e_host[0]) and abs(e_dev[1] - e_host[1]) <= 1e-6 * abs(e_host[1])
+
+
+def test_search_step_entirely_on_the_device_1536k():
+    """BASELINE configs[3]: 784 columns of up to 2176 atoms (4096-element sorting networks), grid and list equal to the
+    host's; records the device times of gridding and list construction next to the host's wall times."""
+    from gromacs_b200 import NbnxmGpu
+    from gromacs_b200.pairsearch import Grid
+    from gromacs_b200.workload import make_workload
+    wl = make_workload("water1536k")
+    t0 = time.time()
+    Grid(wl.box.box, wl.box.x)
+    host_grid_s = time.time() - t0
+    t0 = time.time()
+    ref = wl.pairlist(min_sci=18944)
+    host_list_s = time.time() - t0
+    nb = NbnxmGpu(wl.params, wl.nbat)
+    try:
+        search, x_dev, dims, atom_index, first_bin, grid_ms, sizes = device_search_step(
+            nb, wl.box.box, wl.box.x, wl.box.q, wl.box.type, wl.nbat.numTypes, wl.box.excl_index, wl.box.excl_atoms,
+            wl.cfg["rlist_outer"], 18944)
+        build_ms = search.build_ms
+        got = search.download()
+        search.free()
+    finally:
+        nb.gpu_free()
+    assert np.array_equal(atom_index, wl.grid.atom_index) and np.array_equal(first_bin, wl.grid.first_bin_of_column)
+    assert_same_list((got.sci, got.cjPacked, got.excl), (ref.sci, ref.cjPacked, ref.excl))
+    out = os.path.join(os.path.dirname(os.path.dirname(os.path.abspath(__file__))), "gpurun_out")
+    if os.path.isdir(out):
+        with open(os.path.join(out, "gpu_search_step_1536k.json"), "w") as fh:
+            json.dump({"workload": "water1536k", "natoms": wl.box.natoms, "gpu_grid_ms": grid_ms, "gpu_list_ms": build_ms,
+                       "host_grid_s": host_grid_s, "host_list_s": host_list_s, "host_threads": wl.grid.nthreads}, fh)

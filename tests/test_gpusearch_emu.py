@@ -134,3 +134,70 @@ def test_passes_on_an_empty_range(emu):
     assert sci.shape[0] == 0 and cjp.shape[0] == 0 and excl.shape[0] == 1 and np.all(excl == 0xffffffff) and ncp == 0
     sci, cjp, excl, ncp = emu_pairlist(emu, grid, nbat.xq, 0.9, None, None, j_bins=(0, 0))
     assert sci.shape[0] == 0 and cjp.shape[0] == 0 and excl.shape[0] == 1
+
+
+def emu_grid(emu, box, x, ncx, ncy, ei=None, ea=None):
+    box = np.ascontiguousarray(box, np.float32)
+    x = np.ascontiguousarray(x, np.float32)
+    ei = None if ei is None else np.ascontiguousarray(ei, np.int32)
+    ea = None if ea is None else np.ascontiguousarray(ea, np.int32)
+    nbins = C.c_int()
+    assert emu.search_emu_put_atoms_on_grid(_p(box, C.c_float), ncx, ncy, x.shape[0], _p(x, C.c_float), _p(ei, C.c_int),
+                                            _p(ea, C.c_int), C.byref(nbins)) == 0
+    atom_index = np.zeros(nbins.value * 64, np.int32)
+    first_bin = np.zeros(ncx * ncy + 1, np.int32)
+    emu.search_emu_get_order(_p(atom_index, C.c_int), _p(first_bin, C.c_int))
+    return nbins.value, atom_index, first_bin
+
+
+@pytest.mark.parametrize("case", ["test243_ewald_cutnone", "bench1_ewald_cutnone"])
+def test_gridding_passes_give_the_host_gridders_order(emu, case):
+    """putAtomsOnGrid as passes (column histogram, scans, scatter, one bitonic-network block per column): the same
+    columns, the same atom order and the same atom data as nbnxm_b200_grid_create / _grid_fill_atomdata."""
+    d = load_golden(case)
+    grid, nbat = host_grid(d)
+    nbins, atom_index, first_bin = emu_grid(emu, d["sys_box"], d["sys_x"], grid.ncx, grid.ncy)
+    assert nbins == grid.nbins
+    assert np.array_equal(first_bin, grid.first_bin_of_column)
+    assert np.array_equal(atom_index, grid.atom_index)
+    n = d["sys_x"].shape[0]
+    nt = int(d["nbat_ntypes"][0])
+    xq = np.zeros((nbins * 64, 4), np.float32)
+    tn = np.zeros(nbins * 64, np.int32)
+    x = np.ascontiguousarray(d["sys_x"], np.float32)
+    q = np.ascontiguousarray(d["sys_q"], np.float32)
+    t = np.ascontiguousarray(d["sys_type"], np.int32)
+    assert emu.search_emu_fill_atomdata(n, _p(x, C.c_float), _p(q, C.c_float), _p(t, C.c_int), nt, None, _p(xq, C.c_float),
+                                        _p(tn, C.c_int), None) == 0
+    assert np.array_equal(xq, nbat.xq) and np.array_equal(tn, nbat.type)
+
+
+def test_gridding_and_list_from_raw_coordinates(emu):
+    """the whole search step as passes, on a box with ragged columns (a water box with a slab of atoms removed, so
+    that column heights differ and some columns are empty): grid, then the list, equal to the host's"""
+    from gromacs_b200.pairsearch import Grid
+    d = load_golden("bench1_ewald_cutnone")
+    x, box = d["sys_x"], d["sys_box"]
+    mol = np.arange(x.shape[0]) // 3
+    ox = x[mol * 3]                                     # oxygen of each molecule decides
+    keep = ~((ox[:, 0] < 0.9) & (ox[:, 1] < 0.9)) & ~((ox[:, 2] > 1.0) & (ox[:, 2] < 1.7) & (ox[:, 0] > 2.0))
+    x = np.ascontiguousarray(x[keep])
+    n = x.shape[0]
+    assert n % 3 == 0 and n < d["sys_x"].shape[0]
+    ei = (np.arange(n + 1) * 3).astype(np.int32)       # each atom excludes the three atoms of its molecule
+    ea = (np.repeat(np.arange(n) // 3 * 3, 3) + np.tile(np.arange(3), n)).astype(np.int32)
+    grid = Grid(box, x, nthreads=1)
+    nbins, atom_index, first_bin = emu_grid(emu, box, x, grid.ncx, grid.ncy, ei, ea)
+    assert np.array_equal(first_bin, grid.first_bin_of_column) and np.array_equal(atom_index, grid.atom_index)
+    assert (np.diff(first_bin) == 0).any() or len(set(np.diff(first_bin).tolist())) > 1
+    nbat = grid.atomdata(x, np.zeros(n, np.float32), np.zeros(n, np.int32), d["nbat_nbfp"], int(d["nbat_ntypes"][0]))
+    ref = grid.pairlist(1.0, ei, ea, min_sci=300)
+    xq = np.ascontiguousarray(nbat.xq, np.float32)
+    sizes = (C.c_int * 4)()
+    ncp = C.c_longlong()
+    assert emu.search_emu_build(_p(xq, C.c_float), C.c_float(1.0), 300, 0, nbins, 0, nbins, 0, 0, sizes, C.byref(ncp)) == 0
+    sci = np.zeros((sizes[0], 4), np.int32)
+    cjp = np.zeros((sizes[1], 8), np.uint32)
+    excl = np.zeros((sizes[2], 32), np.uint32)
+    emu.search_emu_copy(_p(sci, C.c_int), _p(cjp, C.c_uint32), _p(excl, C.c_uint32))
+    assert_same_list((sci, cjp, excl), (ref.sci, ref.cjPacked, ref.excl))
