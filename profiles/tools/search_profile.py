@@ -49,7 +49,7 @@ host_grid_s = time.time() - t0
 x_dev = torch.from_numpy(np.ascontiguousarray(wl.box.x, np.float32)).cuda()
 torch.cuda.synchronize()
 s2 = GpuPairSearch(nb)
-s2.set_atoms(wl.box.q, wl.box.type, wl.nbat.numTypes, None, wl.box.excl_index, wl.box.excl_atoms)
+s2.set_atoms(wl.box.q, wl.box.type, wl.nbat.numTypes, wl.nbat.nbfp_comb, wl.box.excl_index, wl.box.excl_atoms)
 grid_ms, list_ms = [], []
 for _ in range(builds):
     dims = s2.put_atoms_on_grid(wl.box.box, x_dev.data_ptr())

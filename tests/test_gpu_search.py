@@ -181,7 +181,7 @@ def test_force_reduction_gathers_nbat_forces_into_atom_order():
         nb.gpu_free()
 
 
-def device_search_step(nb, box, x, q, atom_type, ntypes, ei, ea, rlist, min_sci):
+def device_search_step(nb, box, x, q, atom_type, ntypes, ei, ea, rlist, min_sci, lj_comb_per_type=None):
     """putAtomsOnGrid + constructPairlist on the device from coordinates in device memory (atom order)"""
     import torch
     from gromacs_b200 import LOCAL
@@ -189,7 +189,7 @@ def device_search_step(nb, box, x, q, atom_type, ntypes, ei, ea, rlist, min_sci)
     x_dev = torch.from_numpy(np.ascontiguousarray(x, np.float32)).cuda()
     torch.cuda.synchronize()
     search = GpuPairSearch(nb)
-    search.set_atoms(q, atom_type, ntypes, None, ei, ea)
+    search.set_atoms(q, atom_type, ntypes, lj_comb_per_type, ei, ea)
     dims = search.put_atoms_on_grid(box, x_dev.data_ptr())
     search.put_atoms_on_grid(box, x_dev.data_ptr())        # again: every buffer is reused
     atom_index, first_bin, grid_ms = search.get_order()
@@ -244,7 +244,7 @@ def test_search_step_entirely_on_the_device(case, rlist, min_sci):
 def test_search_step_entirely_on_the_device_1536k():
     """BASELINE configs[3]: 784 columns of up to 2176 atoms (4096-element sorting networks), grid and list equal to the
     host's; records the device times of gridding and list construction next to the host's wall times."""
-    from gromacs_b200 import NbnxmGpu
+    from gromacs_b200 import LOCAL, NbnxmGpu
     from gromacs_b200.pairsearch import Grid
     from gromacs_b200.workload import make_workload
     wl = make_workload("water1536k")
@@ -258,14 +258,24 @@ def test_search_step_entirely_on_the_device_1536k():
     try:
         search, x_dev, dims, atom_index, first_bin, grid_ms, sizes = device_search_step(
             nb, wl.box.box, wl.box.x, wl.box.q, wl.box.type, wl.nbat.numTypes, wl.box.excl_index, wl.box.excl_atoms,
-            wl.cfg["rlist_outer"], 18944)
+            wl.cfg["rlist_outer"], 18944, lj_comb_per_type=wl.nbat.nbfp_comb)      # LJ cut with the geometric rule
         build_ms = search.build_ms
         got = search.download()
+        # forces with everything built on the device against the host path on the same handle
+        nb.gpu_upload_shiftvec(wl.nbat)
+        nb.setupGpuShortRangeWork(LOCAL)
+        f_dev, _ = run_step(nb, wl.nbat, energy=False)
         search.free()
+        nb.gpu_init_atomdata(wl.nbat)
+        nb.gpu_copy_xq_to_gpu(wl.nbat, LOCAL)
+        nb.gpu_init_pairlist(ref, LOCAL)
+        f_host, _ = run_step(nb, wl.nbat, energy=False)
     finally:
         nb.gpu_free()
+    assert dims == (wl.grid.natoms_nbat, wl.grid.nbins, wl.grid.ncx, wl.grid.ncy)
     assert np.array_equal(atom_index, wl.grid.atom_index) and np.array_equal(first_bin, wl.grid.first_bin_of_column)
     assert_same_list((got.sci, got.cjPacked, got.excl), (ref.sci, ref.cjPacked, ref.excl))
+    assert relrms(f_dev, f_host) < 1e-6
     out = os.path.join(os.path.dirname(os.path.dirname(os.path.abspath(__file__))), "gpurun_out")
     if os.path.isdir(out):
         with open(os.path.join(out, "gpu_search_step_1536k.json"), "w") as fh:
