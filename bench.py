@@ -374,9 +374,22 @@ def main():
             sizes = gs.build(cfg["rlist_outer"], LOCAL, min_sci=min_sci)
             build_ms.append(gs.build_ms)
         gs.free()
-        search_rec = {"gpu_build_ms": min(build_ms[1:]), "host_build_s": host_search_s, "host_threads": wl.grid.nthreads,
+        search_rec = {"gpu_list_ms": min(build_ms[1:]), "host_list_s": host_search_s, "host_threads": wl.grid.nthreads,
                       "list_bytes_not_uploaded": list_bytes,
                       "same_sizes_as_host_list": list(sizes[:2]) == [int(plist.sci.shape[0]), int(plist.cjPacked.shape[0])]}
+        # ... and the gridding in front of it from atom-order coordinates in device memory
+        # (nbnxm_b200_gpu_search_put_atoms_on_grid); last, because it re-creates the handle's atom data
+        x_dev = torch.from_numpy(np.ascontiguousarray(wl.box.x, np.float32)).cuda()
+        torch.cuda.synchronize()
+        gs = GpuPairSearch(nb)
+        gs.set_atoms(wl.box.q, wl.box.type, nbat.numTypes, nbat.nbfp_comb, wl.box.excl_index, wl.box.excl_atoms)
+        grid_ms = []
+        for _ in range(3):
+            dims = gs.put_atoms_on_grid(wl.box.box, x_dev.data_ptr())
+            grid_ms.append(gs.get_order()[2])
+        gs.free()
+        search_rec.update({"gpu_grid_ms": min(grid_ms[1:]), "host_grid_s": wl.grid_seconds,
+                           "same_grid_as_host": list(dims) == [wl.grid.natoms_nbat, wl.grid.nbins, wl.grid.ncx, wl.grid.ncy]})
     except Exception as e:      # reported, never fatal for the force-step measurement
         search_rec = {"error": str(e)}
 

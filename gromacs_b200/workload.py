@@ -3,6 +3,7 @@ host pair search and the interaction-constant formulas — everything the refere
 `gmx nonbonded-benchmark` set-up (src/gromacs/nbnxm/benchmark/bench_setup.cpp:178-294) and mdrun's
 pair-list tuning would hand to the GPU path."""
 import math
+import time
 from dataclasses import dataclass
 
 import numpy as np
@@ -40,6 +41,7 @@ class Workload:
     params: object
     useful_pairs: float       # N/2 (rho 4/3 pi rc^3 + 1), bench_setup.cpp:332-337
     flops_per_pair: int
+    grid_seconds: float = 0.0  # wall time of the host gridder (nbnxm_b200_grid_create)
 
     def pairlist(self, min_sci=0, **kw) -> PairlistGpu:
         return self.grid.pairlist(self.cfg["rlist_outer"], self.box.excl_index, self.box.excl_atoms, min_sci=min_sci, **kw)
@@ -76,7 +78,9 @@ def make_workload(name, nthreads=None, energy=None, nslabs=1) -> Workload:
     if energy is not None:
         cfg["energy"] = energy
     box = S.benchmark_system(cfg["k"])
+    t_grid = time.perf_counter()
     grid = Grid(box.box, box.x, nthreads=nthreads, nslabs=nslabs)
+    t_grid = time.perf_counter() - t_grid
     nbfp, nt = S.spce_nbfp()
     comb = S.geometric_comb_params(nbfp, nt)
     nbat = grid.atomdata(box.x, box.q, box.type, nbfp, nt, nbfp_comb=comb, lj_comb_per_type=comb)
@@ -85,4 +89,5 @@ def make_workload(name, nthreads=None, energy=None, nslabs=1) -> Workload:
     density = n / float(np.prod(box.box.astype(np.float64)))
     useful = n * 0.5 * (density * 4.0 / 3.0 * math.pi * cfg["rc"] ** 3 + 1.0)
     fl = FLOPS_PER_PAIR[cfg["vdw"]][1 if cfg["energy"] else 0]
-    return Workload(name=name, cfg=cfg, box=box, grid=grid, nbat=nbat, params=params, useful_pairs=useful, flops_per_pair=fl)
+    return Workload(name=name, cfg=cfg, box=box, grid=grid, nbat=nbat, params=params, useful_pairs=useful, flops_per_pair=fl,
+                    grid_seconds=t_grid)
