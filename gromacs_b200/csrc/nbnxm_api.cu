@@ -67,7 +67,9 @@ int fillParamsDev(nbnxm_b200* nb)
 {
     const nbnxm_b200_params_t& s = nb->params;
     ParamsDev&                 d = nb->pd;
-    d.epsfac = s.epsfac; d.c_rf = s.c_rf; d.two_k_rf = s.two_k_rf; d.ewald_beta = s.ewald_beta;
+    /* ElecType::None: the plain cut-off kernels with the charges switched off (include/nbnxm_b200.h) */
+    d.epsfac = (s.elec_type == NBNXM_B200_ELEC_NONE) ? 0.0f : s.epsfac;
+    d.c_rf = s.c_rf; d.two_k_rf = s.two_k_rf; d.ewald_beta = s.ewald_beta;
     d.sh_ewald = s.sh_ewald; d.sh_lj_ewald = s.sh_lj_ewald; d.ewaldcoeff_lj = s.ewaldcoeff_lj;
     d.rcoulomb_sq = s.rcoulomb_sq; d.rvdw_sq = s.rvdw_sq; d.rvdw_switch = s.rvdw_switch;
     d.rlist_outer_sq = s.rlist_outer_sq; d.rlist_inner_sq = s.rlist_inner_sq;
@@ -120,6 +122,12 @@ int fillParamsDev(nbnxm_b200* nb)
         d.packedConsts = nb->packedConsts.p;
     }
     return 0;
+}
+
+/* kernel flavor that evaluates the handle's electrostatics type */
+int kernelElecType(const nbnxm_b200* nb)
+{
+    return nb->params.elec_type == NBNXM_B200_ELEC_NONE ? int(NBNXM_B200_ELEC_CUT) : nb->params.elec_type;
 }
 
 bool usesLjComb(int vdw) { return vdw == NBNXM_B200_VDW_CUT_COMB_GEOM || vdw == NBNXM_B200_VDW_CUT_COMB_LB; }
@@ -193,6 +201,11 @@ int nbnxm_b200_init(nbnxm_b200_t** out, int device, const nbnxm_b200_params_t* p
                     void* local_stream, void* nonlocal_stream)
 {
     if (!out || !params || !nbfp || ntypes <= 0) return fail("nbnxm_b200_init: null argument");
+    if (params->elec_type < 0 || params->elec_type > NBNXM_B200_ELEC_NONE || params->vdw_type < 0 || params->vdw_type > NBNXM_B200_VDW_EWALD_LB)
+    {
+        return fail("The requested electrostatics / VdW type (%d / %d) is not implemented in the GPU accelerated kernels",
+                    params->elec_type, params->vdw_type);
+    }
     int ndev = 0;
     if (cudaGetDeviceCount(&ndev) != cudaSuccess || ndev == 0)
     {
@@ -653,7 +666,7 @@ int nbnxm_b200_launch_kernel(nbnxm_b200_t* nb, int iloc, int compute_energy, int
     }
     if (!nb->shiftVecUploaded) return fail("nbnxm_b200_launch_kernel: shift vectors were never uploaded");
     const bool     doPrune = pl.haveFreshList && !pl.didPrune;
-    ForceKernelPtr kernel  = select_force_kernel(nb->params.elec_type, nb->params.vdw_type, compute_energy != 0, doPrune, nb->numTypes);
+    ForceKernelPtr kernel  = select_force_kernel(kernelElecType(nb), nb->params.vdw_type, compute_energy != 0, doPrune, nb->numTypes);
     if (!kernel)
     {
         return fail("nbnxm_b200_launch_kernel: no kernel for elec_type %d vdw_type %d", nb->params.elec_type, nb->params.vdw_type);
@@ -692,7 +705,7 @@ static int launchKernelRange(nbnxm_b200_t* nb, int firstSci, int numSci, int com
 {
     PairList& pl = nb->plist[0];
     if (numSci <= 0) return 0;
-    ForceKernelPtr kernel = select_force_kernel(nb->params.elec_type, nb->params.vdw_type, compute_energy != 0, false, nb->numTypes);
+    ForceKernelPtr kernel = select_force_kernel(kernelElecType(nb), nb->params.vdw_type, compute_energy != 0, false, nb->numTypes);
     if (!kernel) return fail("no kernel for elec_type %d vdw_type %d", nb->params.elec_type, nb->params.vdw_type);
     if (nb->carveoutSet.insert(reinterpret_cast<const void*>(kernel)).second)
     {

@@ -89,6 +89,10 @@ nbnxm_b200_params_t makeParams(const interaction_const_t& ic, const PairlistPara
     {
         p.elec_type = NBNXM_B200_ELEC_CUT;
     }
+    else if (ic.coulomb.type == CoulombInteractionType::Fmm && !ic.nbnxmIsDirectCoulombProvider)
+    {
+        p.elec_type = NBNXM_B200_ELEC_NONE;
+    }
     else if (usingRF(ic.coulomb.type))
     {
         p.elec_type = NBNXM_B200_ELEC_RF;

@@ -25,6 +25,8 @@ def pick_elec_type(coulomb_type, rcoulomb, rvdw, analytical=True):
     Analytical Ewald is the reference's default on every NVIDIA device except CC 7.0 / 8.0."""
     if coulomb_type == "Cut":
         return "Cut"
+    if coulomb_type == "Fmm":
+        return "None"           # FMM computes its own direct part (nbnxmIsDirectCoulombProvider false)
     if coulomb_type == "RF":
         return "RF"
     if coulomb_type in ("Pme", "Ewald"):

@@ -19,7 +19,7 @@ _LIB_PATH = os.path.join(_HERE, "libnbnxm_b200.so")
 
 LOCAL, NONLOCAL, ALL = 0, 1, 2
 
-ELEC_TYPES = {"Cut": 0, "RF": 1, "EwaldTab": 2, "EwaldTabTwin": 3, "EwaldAna": 4, "EwaldAnaTwin": 5}
+ELEC_TYPES = {"Cut": 0, "RF": 1, "EwaldTab": 2, "EwaldTabTwin": 3, "EwaldAna": 4, "EwaldAnaTwin": 5, "None": 6}
 VDW_TYPES = {"Cut": 0, "CutCombGeom": 1, "CutCombLB": 2, "FSwitch": 3, "PSwitch": 4, "EwaldGeom": 5, "EwaldLB": 6}
 
 # every symbol include/nbnxm_b200.h declares

@@ -37,7 +37,12 @@ enum nbnxm_b200_elec_type
     NBNXM_B200_ELEC_EWALD_TAB      = 2,
     NBNXM_B200_ELEC_EWALD_TAB_TWIN = 3,
     NBNXM_B200_ELEC_EWALD_ANA      = 4,
-    NBNXM_B200_ELEC_EWALD_ANA_TWIN = 5
+    NBNXM_B200_ELEC_EWALD_ANA_TWIN = 5,
+    /* ElecType::None (no NBNxM electrostatics, e.g. FMM computes its own direct part): the LJ-only kernels.  Runs the
+     * plain cut-off flavor with epsfac = 0: charges contribute neither forces nor energies, the pair cut-off stays
+     * rcoulomb like in the reference's ElecNone kernels.  ElecType::Fmm (7) is not implemented, as in the reference
+     * (nbnxm_gpu_data_mgmt.cpp:424-433). */
+    NBNXM_B200_ELEC_NONE           = 6
 };
 enum nbnxm_b200_vdw_type
 {
