@@ -201,3 +201,65 @@ def test_gridding_and_list_from_raw_coordinates(emu):
     excl = np.zeros((sizes[2], 32), np.uint32)
     emu.search_emu_copy(_p(sci, C.c_int), _p(cjp, C.c_uint32), _p(excl, C.c_uint32))
     assert_same_list((sci, cjp, excl), (ref.sci, ref.cjPacked, ref.excl))
+
+
+def chain_system(n, box, seed, reach=2):
+    """random coordinates, charges and types; every atom excludes its neighbours within `reach` along the chain, so
+    that exclusions cross clusters, bins and columns (a water box only has exclusions inside a cluster or two)"""
+    rng = np.random.default_rng(seed)
+    x = (rng.random((n, 3)) * box).astype(np.float32)
+    x[:5] = 0.0                                      # atoms on the box corner / coinciding columns edge
+    x[5, :] = box * (1 - 1e-7)
+    q = rng.uniform(-0.5, 0.5, n).astype(np.float32)
+    t = rng.integers(0, 2, n).astype(np.int32)
+    ei, ea = [0], []
+    for a in range(n):
+        ea += [b for b in range(max(0, a - reach), min(n, a + reach + 1))]
+        ei.append(len(ea))
+    return x, q, t, np.array(ei, np.int32), np.array(ea, np.int32)
+
+
+@pytest.mark.parametrize("n,seed,rlist,min_sci", [(1500, 1, 0.8, 0), (2500, 2, 1.1, 400), (700, 3, 1.2, 0)])
+def test_passes_on_a_random_chain_system_against_host_builder_and_brute_force(emu, oracle, n, seed, rlist, min_sci):
+    from gromacs_b200.pairsearch import Grid
+    from util import oracle_params, relrms
+    d = load_golden("bench1_rf_cutnone_split")
+    box = np.array([2.6, 3.1, 3.7], np.float32)
+    x, q, t, ei, ea = chain_system(n, box, seed)
+    # separate the coinciding atoms a little: brute force and kernels clamp r^2 differently at r = 0
+    x[:5] += np.arange(5, dtype=np.float32)[:, None] * 0.11
+    grid = Grid(box, x, nthreads=2)
+    nt = int(d["nbat_ntypes"][0])
+    nbat = grid.atomdata(x, q, t, d["nbat_nbfp"], nt, nbfp_comb=d["nbat_nbfp_comb"])
+    ref = grid.pairlist(rlist, ei, ea, min_sci=min_sci)
+    # the device builder's passes: grid, then list, from the raw coordinates
+    nbins, atom_index, first_bin = emu_grid(emu, box, x, grid.ncx, grid.ncy, ei, ea)
+    assert np.array_equal(atom_index, grid.atom_index) and np.array_equal(first_bin, grid.first_bin_of_column)
+    sizes = (C.c_int * 4)()
+    ncp = C.c_longlong()
+    xq = np.ascontiguousarray(nbat.xq, np.float32)
+    assert emu.search_emu_build(_p(xq, C.c_float), C.c_float(rlist), min_sci, 0, nbins, 0, nbins, 0, 0, sizes, C.byref(ncp)) == 0
+    sci = np.zeros((sizes[0], 4), np.int32)
+    cjp = np.zeros((sizes[1], 8), np.uint32)
+    excl = np.zeros((sizes[2], 32), np.uint32)
+    emu.search_emu_copy(_p(sci, C.c_int), _p(cjp, C.c_uint32), _p(excl, C.c_uint32))
+    assert_same_list((sci, cjp, excl), (ref.sci, ref.cjPacked, ref.excl))
+    # and the list is right: forces through the oracle's list walk = brute force over all pairs
+    p = oracle_params(oracle, d)
+    rc = min(rlist, 0.5 * float(box.min()) - 0.01) - 0.05
+    p.rcoulomb_sq = p.rvdw_sq = rc * rc
+    f, _, e, _ = oracle.forces(p, sci, cjp, excl, nbat.xq, nbat.type, np.zeros((nbat.numAtoms(), 2), np.float32), nbat.nbfp,
+                               nbat.nbfp_comb, nbat.shift_vec)
+    f = oracle.nbat_to_atom_order(f, grid.atom_index, n)
+    fb, eb = oracle.brute_force(p, x, q, t, d["nbat_nbfp"], d["nbat_nbfp_comb"], box, ei, ea)
+    assert relrms(f, fb) < 1e-6
+    assert abs(e[0] - eb[0]) <= 1e-6 * abs(eb[0]) + 1e-6 and abs(e[1] - eb[1]) <= 1e-6 * abs(eb[1]) + 1e-6
+
+
+def test_gridding_passes_refuse_a_column_taller_than_one_block(emu):
+    """8192 atoms per column is what one block sorts; the passes report it instead of mis-sorting"""
+    rng = np.random.default_rng(5)
+    box = np.array([1.0, 1.0, 400.0], np.float32)
+    x = (rng.random((9000, 3)) * box).astype(np.float32)
+    nbins = C.c_int()
+    assert emu.search_emu_put_atoms_on_grid(_p(box, C.c_float), 1, 1, x.shape[0], _p(x, C.c_float), None, None, C.byref(nbins)) == 1
