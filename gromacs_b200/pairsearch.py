@@ -1,6 +1,7 @@
-"""Host-side grid + GPU-layout pair-list construction (include/nbnxm_b200_search.h), the caller side of the
-force path: mirrors nonbonded_verlet_t::putAtomsOnGrid / setAtomProperties / constructPairlist
-(src/gromacs/nbnxm/nbnxm.cpp:78, atomdata.cpp:1107, pairlist.cpp:4056)."""
+"""Grid + GPU-layout pair-list construction (include/nbnxm_b200_search.h), the caller side of the force path:
+mirrors nonbonded_verlet_t::putAtomsOnGrid / setAtomProperties / constructPairlist
+(src/gromacs/nbnxm/nbnxm.cpp:78, atomdata.cpp:1107, pairlist.cpp:4056).  `Grid` is the host gridder / builder
+(C++/OpenMP in the library), `GpuPairSearch` the same search step on the device."""
 import ctypes as C
 import os
 

@@ -7,9 +7,11 @@
  *   - nbnxm_sci_t / nbnxm_cj_packed_t / nbnxm_excl_t arrays (src/gromacs/nbnxm/pairlist.h:189-287) with the
  *     mask conventions of src/gromacs/nbnxm/pairlist.cpp:651-688 (self/Newton exclusions), :1561-1660
  *     (topology exclusions), :1769-1879 (splitting of long i-entries for load balance).
- * It is an independent implementation (bounding-box search over a column grid, OpenMP over i-bins); the
- * list it builds is not entry-for-entry the reference's list (any list that covers all pairs within
- * rlist exactly once is valid), which tests/test_pairsearch.py verifies against brute force.
+ * It is an independent implementation (bounding-box search over a column grid); the list it builds is not
+ * entry-for-entry the reference's list (any list that covers all pairs within rlist exactly once is valid), which
+ * tests/test_pairsearch.py verifies against brute force.  Two builders produce the same grid and the same list:
+ * the host one (nbnxm_b200_grid_* / nbnxm_b200_pairlist_*, OpenMP over i-bins) and the device one
+ * (nbnxm_b200_gpu_search_*, data-parallel passes on the GPU that holds the coordinates).
  * Rectangular boxes only.
  */
 #ifndef NBNXM_B200_SEARCH_H
