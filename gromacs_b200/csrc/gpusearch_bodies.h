@@ -407,6 +407,166 @@ NBS_HD void binPairMask(const Grid& g, const Params& p, const Work& w, int item)
     w.binPairMask[item] = (unsigned char)mask;
 }
 
+/* ---- pass 3, warp-cooperative form: one warp per bin pair (64 cluster pairs), same result as binPairMask ----
+ * phase A, lane l: the two cluster pairs (cj = l >> 2, ci = 2 (l & 3) and ci + 1) are classified from their bounding
+ *   boxes: accepted (closer than rbb), to be checked atom by atom (between rbb and rlist), or out;
+ * phase B, once per cluster pair to be checked: lane l tests i-atom l >> 2 against j-atoms 2 (l & 3) and + 1, a warp
+ *   vote accepts the pair;
+ * phase C, lanes 0..7: lane cj assembles the 8-bit i-cluster mask of j-cluster cj from the accept votes.
+ * The per-lane functions below are shared by the CUDA kernel (ballot / any votes) and by the emulation (lane loops). */
+
+struct BinPairWarp
+{
+    Entry en;
+    int   bj = 0;
+    bool  jbinInRange = false;
+};
+
+NBS_HD void maskWarpSetup(const Grid& g, const Params& p, const Work& w, int pr, BinPairWarp& bw)
+{
+    entryDecode(g, p, w.binPairEntry[pr], bw.en);
+    bw.bj = w.binPairJ[pr];
+}
+
+/* classification of cluster pair (ci, cj): 0 = out, 1 = accepted from the bounding boxes, 2 = needs the atom check */
+NBS_HD int maskWarpClassify(const Grid& g, const Params& p, const BinPairWarp& bw, int cj, int ci)
+{
+    const int gcj = bw.bj * c_binCl + cj;
+    const int gci = bw.en.bi * c_binCl + ci;
+    if (g.clCount[gcj] == 0 || g.clCount[gci] == 0)
+    {
+        return 0;
+    }
+    if (bw.en.subDiag && bw.bj == bw.en.bi && ci > cj)
+    {
+        return 0;
+    }
+    const BB jbb = g.clBB[gcj];
+    if (bbDist2(g.binBB[bw.en.bi], bw.en.sh, jbb) >= p.rl2)
+    {
+        return 0;
+    }
+    const float d2 = bbDist2(g.clBB[gci], bw.en.sh, jbb);
+    if (d2 >= p.rl2)
+    {
+        return 0;
+    }
+    return d2 < p.rbb2 ? 1 : 2;
+}
+
+/* lane's share of the atom check of cluster pair (ci, cj): i-atom lane >> 2 against j-atoms 2 (lane & 3), + 1 */
+NBS_HD bool maskWarpAtomCheck(const Grid& g, const Params& p, const BinPairWarp& bw, int cj, int ci, int lane)
+{
+    const XQ xi = g.xq[(bw.en.bi * c_binCl + ci) * c_cl + (lane >> 2)];
+    if (xi.x == c_farAway)
+    {
+        return false;
+    }
+    const float px = xi.x + bw.en.sh[0], py = xi.y + bw.en.sh[1], pz = xi.z + bw.en.sh[2];
+    const int   j0 = (bw.bj * c_binCl + cj) * c_cl + (lane & 3) * 2;
+    const XQ    xa = g.xq[j0], xb = g.xq[j0 + 1];
+    return dist2(px - xa.x, py - xa.y, pz - xa.z) < p.rl2 || dist2(px - xb.x, py - xb.y, pz - xb.z) < p.rl2;
+}
+
+/* mask of j-cluster cj from the accept votes: vote0 bit l = pair (cj = l >> 2, ci = 2 (l & 3)), vote1: ci + 1 */
+NBS_HD unsigned int maskWarpCompose(unsigned int vote0, unsigned int vote1, int cj)
+{
+    const unsigned int a = (vote0 >> (cj * 4)) & 0xfu, b = (vote1 >> (cj * 4)) & 0xfu;
+    unsigned int       m = 0;
+    for (int k = 0; k < 4; k++)
+    {
+        m |= ((a >> k) & 1u) << (2 * k);
+        m |= ((b >> k) & 1u) << (2 * k + 1);
+    }
+    return m;
+}
+
+struct FBinPairMaskWarp
+{
+    Grid   g;
+    Params p;
+    Work   w;
+
+#if defined(__CUDACC__)
+    __device__ __forceinline__ void device(int pr, int lane) const
+    {
+        BinPairWarp bw;
+        maskWarpSetup(g, p, w, pr, bw);
+        const int    cj = lane >> 2, ci0 = (lane & 3) * 2;
+        const int    c0 = maskWarpClassify(g, p, bw, cj, ci0);
+        const int    c1 = maskWarpClassify(g, p, bw, cj, ci0 + 1);
+        unsigned int vote0 = __ballot_sync(0xffffffffu, c0 == 1);
+        unsigned int vote1 = __ballot_sync(0xffffffffu, c1 == 1);
+        unsigned int need0 = __ballot_sync(0xffffffffu, c0 == 2);
+        unsigned int need1 = __ballot_sync(0xffffffffu, c1 == 2);
+        while (need0 != 0)
+        {
+            const int b = __ffs(need0) - 1;
+            need0 &= need0 - 1;
+            if (__any_sync(0xffffffffu, maskWarpAtomCheck(g, p, bw, b >> 2, (b & 3) * 2, lane)))
+            {
+                vote0 |= 1u << b;
+            }
+        }
+        while (need1 != 0)
+        {
+            const int b = __ffs(need1) - 1;
+            need1 &= need1 - 1;
+            if (__any_sync(0xffffffffu, maskWarpAtomCheck(g, p, bw, b >> 2, (b & 3) * 2 + 1, lane)))
+            {
+                vote1 |= 1u << b;
+            }
+        }
+        if (lane < c_binCl)
+        {
+            w.binPairMask[pr * c_binCl + lane] = (unsigned char)maskWarpCompose(vote0, vote1, lane);
+        }
+    }
+#endif
+
+    /* the same warp, lane by lane (emulation) */
+    void host(int pr) const
+    {
+        BinPairWarp bw;
+        maskWarpSetup(g, p, w, pr, bw);
+        unsigned int vote0 = 0, vote1 = 0, need0 = 0, need1 = 0;
+        for (int lane = 0; lane < 32; lane++)
+        {
+            const int cj = lane >> 2, ci0 = (lane & 3) * 2;
+            const int c0 = maskWarpClassify(g, p, bw, cj, ci0);
+            const int c1 = maskWarpClassify(g, p, bw, cj, ci0 + 1);
+            vote0 |= (c0 == 1 ? 1u : 0u) << lane;
+            vote1 |= (c1 == 1 ? 1u : 0u) << lane;
+            need0 |= (c0 == 2 ? 1u : 0u) << lane;
+            need1 |= (c1 == 2 ? 1u : 0u) << lane;
+        }
+        for (int half = 0; half < 2; half++)
+        {
+            unsigned int  need = half ? need1 : need0;
+            unsigned int& vote = half ? vote1 : vote0;
+            for (int b = 0; b < 32; b++)
+            {
+                if (need & (1u << b))
+                {
+                    bool any = false;
+                    for (int lane = 0; lane < 32; lane++)
+                    {
+                        any = any || maskWarpAtomCheck(g, p, bw, b >> 2, (b & 3) * 2 + half, lane);
+                    }
+                    if (any)
+                    {
+                        vote |= 1u << b;
+                    }
+                }
+            }
+        }
+        for (int lane = 0; lane < c_binCl; lane++)
+        {
+            w.binPairMask[pr * c_binCl + lane] = (unsigned char)maskWarpCompose(vote0, vote1, lane);
+        }
+    }
+};
+
 /* ---- pass 4: j-clusters and cjPacked groups per entry ---- */
 
 NBS_HD void entryCountJ(const Work& w, int e)

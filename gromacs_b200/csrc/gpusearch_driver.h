@@ -10,6 +10,8 @@
  *   int  scan(const int* in, int* out, int n)                exclusive prefix sum
  *   int  readInt(const int* p, int* hostValue), readULL(...) synchronising read-back of one value
  *   int  forEach(int n, F f)                                 f(i) for i in [0, n), f copied by value
+ *   int  forEachWarp(int warps, F f)                         f.device(w, lane) on the 32 lanes of a warp (CUDA) or
+ *                                                            f.host(w), the same warp lane by lane (emulation)
  *   int  forEachBlock(int blocks, int threads, size_t scratchBytes, F f)
  *                                                            per block b: for s < f.numStages(b): f(b, s, t, scratch) for
  *                                                            t < f.numItems(b, s), a block barrier between stages
@@ -152,6 +154,8 @@ struct SearchState
     Buf<nbnxm_b200_sci_t>       sci;
     Buf<nbnxm_b200_cj_packed_t> cjp;
     Buf<nbnxm_b200_excl_t>      excl;
+    /* pass 3 as one warp per bin pair (FBinPairMaskWarp) instead of one thread per (bin pair, j-cluster) */
+    bool      cooperativeMasks = false;
     int       nsci = 0, ncjp = 0, nexcl = 0, numBinPairs = 0, numEntries = 0;
     long long numClusterPairsHost = 0;
 };
@@ -426,7 +430,14 @@ int buildPairlist(BE& be, SearchState<BE>& st, const XQ* xq, float rlist, int mi
     NBS_TRY(be.forEach(nE, FEntryBinPairs<true>{ g, p, w, numIBins }));
 
     /* pass 3: cluster-pair masks */
-    NBS_TRY(be.forEach(st.numBinPairs * c_binCl, FBinPairMask{ g, p, w }));
+    if (st.cooperativeMasks)
+    {
+        NBS_TRY(be.forEachWarp(st.numBinPairs, FBinPairMaskWarp{ g, p, w }));
+    }
+    else
+    {
+        NBS_TRY(be.forEach(st.numBinPairs * c_binCl, FBinPairMask{ g, p, w }));
+    }
 
     /* pass 4: sizes */
     NBS_TRY(be.forEach(nE, FEntryCountJ{ w }));

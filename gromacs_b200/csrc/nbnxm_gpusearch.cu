@@ -10,6 +10,8 @@
  * file provides the CUDA backend: the generic item kernel, a two-level exclusive scan, buffers and the C ABI.
  * All passes are integer / bounding-box work bound by memory latency and divergence, not by FP32 throughput.
  */
+#include <cstdlib>
+
 #include "../../include/nbnxm_b200_search.h"
 #include "gpusearch_driver.h"
 #include "nbnxm_handle.cuh"
@@ -24,6 +26,17 @@ __global__ void __launch_bounds__(256) search_items_kernel(const F f, int n)
     if (i < n)
     {
         f(i);
+    }
+}
+
+/* warp kernel: one warp per item, lanes cooperate through votes inside F::device */
+template<typename F>
+__global__ void __launch_bounds__(256) search_warps_kernel(const F f, int n)
+{
+    const int warp = blockIdx.x * 8 + (threadIdx.x >> 5);
+    if (warp < n)
+    {
+        f.device(warp, threadIdx.x & 31);
     }
 }
 
@@ -190,6 +203,15 @@ struct CudaSearchBackend
         return 0;
     }
     template<typename F>
+    int forEachWarp(int n, F f)
+    {
+        if (n <= 0) return 0;
+        search_warps_kernel<F><<<(n + 7) / 8, 256, 0, st>>>(f, n);
+        launches++;
+        CU(cudaGetLastError());
+        return 0;
+    }
+    template<typename F>
     int forEachBlock(int blocks, int threads, size_t scratchBytes, F f)
     {
         if (blocks <= 0) return 0;
@@ -241,6 +263,9 @@ int nbnxm_b200_gpu_search_create(nbnxm_b200_gpu_search_t** out, nbnxm_b200_t* nb
     s->be.h_value = static_cast<int*>(pinned);
     CU(cudaEventCreate(&s->evStart));
     CU(cudaEventCreate(&s->evStop));
+    /* opt-in until it has been run on a GPU (checked through the emulation only) */
+    const char* coop        = getenv("NBNXM_B200_SEARCH_COOP");
+    s->st.cooperativeMasks = coop != nullptr && coop[0] == '1';
     *out = s;
     return 0;
 }

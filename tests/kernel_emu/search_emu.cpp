@@ -85,6 +85,15 @@ struct HostBackend
         return 0;
     }
     template<typename F>
+    int forEachWarp(int n, F f)
+    {
+        for (int i = n - 1; i >= 0; i--)
+        {
+            f.host(i);
+        }
+        return 0;
+    }
+    template<typename F>
     int forEachBlock(int blocks, int /*threads*/, size_t scratchBytes, F f)
     {
         void* scratch = std::malloc(scratchBytes);
@@ -121,6 +130,12 @@ int search_emu_set_grid(const float* box, int ncx, int ncy, const int* first_bin
                         int natoms, const int* excl_index, const int* excl_atoms)
 {
     return nbs::setGrid(g_be, g_st, box, ncx, ncy, first_bin_of_column, atom_index, nbins, natoms, excl_index, excl_atoms);
+}
+
+int search_emu_set_cooperative_masks(int on)
+{
+    g_st.cooperativeMasks = on != 0;
+    return 0;
 }
 
 int search_emu_put_atoms_on_grid(const float* box, int ncx, int ncy, int natoms, const float* x, const int* excl_index,

@@ -281,3 +281,35 @@ def test_search_step_entirely_on_the_device_1536k():
         with open(os.path.join(out, "gpu_search_step_1536k.json"), "w") as fh:
             json.dump({"workload": "water1536k", "natoms": wl.box.natoms, "gpu_grid_ms": grid_ms, "gpu_list_ms": build_ms,
                        "host_grid_s": host_grid_s, "host_list_s": host_list_s, "host_threads": wl.grid.nthreads}, fh)
+
+
+@pytest.mark.skipif(os.environ.get("NBNXM_B200_TEST_UNVERIFIED") != "1",
+                    reason="the warp-cooperative mask pass has only been run through the CPU emulation so far (DESIGN.md 4.4); "
+                           "set NBNXM_B200_TEST_UNVERIFIED=1 to run it on the GPU")
+def test_cooperative_mask_pass_gives_the_same_list(monkeypatch):
+    """NBNXM_B200_SEARCH_COOP=1: pass 3 as one warp per bin pair; same list, and the build time next to the default"""
+    from gromacs_b200 import LOCAL, NbnxmGpu
+    from gromacs_b200.pairsearch import GpuPairSearch
+    from gromacs_b200.workload import make_workload
+    wl = make_workload("water1536k")
+    ref = wl.pairlist(min_sci=18944)
+    times = {}
+    for coop in ("0", "1"):
+        monkeypatch.setenv("NBNXM_B200_SEARCH_COOP", coop)
+        nb = NbnxmGpu(wl.params, wl.nbat)
+        try:
+            nb.gpu_init_atomdata(wl.nbat)
+            nb.gpu_copy_xq_to_gpu(wl.nbat, LOCAL)
+            search = GpuPairSearch(nb, wl.grid, wl.box.excl_index, wl.box.excl_atoms)
+            for _ in range(3):
+                search.build(wl.cfg["rlist_outer"], LOCAL, min_sci=18944)
+            times[coop] = search.build_ms
+            got = search.download()
+            search.free()
+        finally:
+            nb.gpu_free()
+        assert_same_list((got.sci, got.cjPacked, got.excl), (ref.sci, ref.cjPacked, ref.excl))
+    out = os.path.join(os.path.dirname(os.path.dirname(os.path.abspath(__file__))), "gpurun_out")
+    if os.path.isdir(out):
+        with open(os.path.join(out, "gpu_search_coop_1536k.json"), "w") as fh:
+            json.dump({"workload": "water1536k", "build_ms_thread_per_j_cluster": times["0"], "build_ms_warp_per_bin_pair": times["1"]}, fh)

@@ -16,10 +16,14 @@ from util import load_golden
 HERE = os.path.dirname(os.path.abspath(__file__))
 
 
-@pytest.fixture(scope="module")
-def emu():
+@pytest.fixture(scope="module", params=["thread-per-j-cluster masks", "warp-per-bin-pair masks"])
+def emu(request):
+    """both forms of pass 3 (cluster-pair masks): one thread per (bin pair, j-cluster), and the warp-cooperative one
+    (NBNXM_B200_SEARCH_COOP=1 in the library), run lane by lane"""
     subprocess.run(["make", "-s", "-C", os.path.join(HERE, "kernel_emu")], check=True)
-    return C.CDLL(os.path.join(HERE, "kernel_emu", "libsearch_emu.so"))
+    lib = C.CDLL(os.path.join(HERE, "kernel_emu", "libsearch_emu.so"))
+    lib.search_emu_set_cooperative_masks(int(request.param.startswith("warp")))
+    return lib
 
 
 def _p(a, ct):
