@@ -404,6 +404,8 @@ int nbnxm_b200_gpu_search_build(nbnxm_b200_gpu_search_t* s, int iloc, float rlis
     if (!s || iloc < 0 || iloc > 1) return fail("nbnxm_b200_gpu_search_build: bad argument");
     if (!s->st.haveGrid) return fail("nbnxm_b200_gpu_search_build: call nbnxm_b200_gpu_search_set_grid first");
     const nbs::Grid& g = s->st.g;
+    if (bin_end < 0) bin_end = g.nbins;
+    if (j_bin_hi < 0) j_bin_hi = g.nbins;
     if (bin_begin < 0 || bin_end > g.nbins || bin_begin > bin_end || j_bin_lo < 0 || j_bin_hi > g.nbins)
     {
         return fail("nbnxm_b200_gpu_search_build: bin range");

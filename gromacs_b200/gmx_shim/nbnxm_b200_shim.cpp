@@ -42,7 +42,10 @@
 #include "gromacs/timing/wallcycle.h"
 #include "gromacs/utility/fatalerror.h"
 
+#include "gromacs/utility/listoflists.h"
+
 #include "nbnxm_b200.h"
+#include "nbnxm_b200_search.h"
 
 namespace gmx
 {
@@ -56,6 +59,8 @@ struct NbnxmGpu
     /* the reference's streams the library runs on (owned by the DeviceStreamManager) */
     const DeviceStream* deviceStreams[2] = { nullptr, nullptr };
     gmx_wallclock_gpu_nbnxm_t timings;
+    /* the search step on the device (nbnxm_b200_gpu_search_*), created on first use */
+    nbnxm_b200_gpu_search_t* search = nullptr;
 };
 
 namespace
@@ -196,6 +201,11 @@ NbnxmGpu* gpu_init(const DeviceStreamManager& deviceStreamManager,
 
 void gpu_free(NbnxmGpu* nb)
 {
+    if (nb != nullptr && nb->search != nullptr)
+    {
+        nbnxm_b200_gpu_search_free(nb->search);
+        nb->search = nullptr;
+    }
     if (nb != nullptr)
     {
         nbnxm_b200_free(nb->handle);
@@ -363,6 +373,81 @@ void nbnxm_gpu_x_to_nbat_x(NbnxmGpu* gpu_nbv, DeviceBuffer<RVec> d_x, GpuEventSy
     }
     check(nbnxm_b200_x_to_nbat_x(gpu_nbv->handle, reinterpret_cast<const float*>(d_x), nullptr, toInt(locality)),
           "nbnxm_b200_x_to_nbat_x");
+}
+
+/* ---- the search step on the device: what nonbonded_verlet_t::putAtomsOnGrid (nbnxm.cpp:78),
+ * nbnxm_atomdata_t::setAtomProperties (atomdata.cpp:1107), PairlistSets::construct (pairlist.cpp:4056),
+ * gpu_init_atomdata and gpu_init_pairlist do between them, for a caller whose coordinates live in
+ * StatePropagatorDataGpu::getCoordinates().  New entry points next to the reference's (nothing in the
+ * reference calls them yet): nonbonded_verlet_t::putAtomsOnGrid / constructPairlist call them instead
+ * of their CPU bodies when the run keeps x on the device (useGpuXBufferOps). ---- */
+
+//! Static per-atom data of the topology: charges and types in atom order, LJ combination parameters per type, exclusions.
+void nbnxm_b200_gpu_set_atoms(NbnxmGpu*                 nb,
+                              ArrayRef<const real>      charges,
+                              ArrayRef<const int>       atomTypes,
+                              int                       numTypes,
+                              ArrayRef<const real>      ljCombPerType,
+                              const ListOfLists<int>&   exclusions)
+{
+    if (nb->search == nullptr)
+    {
+        check(nbnxm_b200_gpu_search_create(&nb->search, nb->handle), "nbnxm_b200_gpu_search_create");
+    }
+    static_assert(sizeof(real) == sizeof(float), "libnbnxm_b200 is a mixed-precision (float) backend");
+    check(nbnxm_b200_gpu_search_set_atoms(nb->search,
+                                          static_cast<int>(charges.size()),
+                                          charges.data(),
+                                          atomTypes.data(),
+                                          numTypes,
+                                          ljCombPerType.empty() ? nullptr : ljCombPerType.data(),
+                                          exclusions.listRangesView().data(),
+                                          exclusions.elementsView().data()),
+          "nbnxm_b200_gpu_search_set_atoms");
+}
+
+//! putAtomsOnGrid + setAtomProperties + gpu_init_atomdata for a rectangular unit cell, from the device coordinate buffer.
+void nbnxm_b200_gpu_put_atoms_on_grid(NbnxmGpu* nb, const matrix box, DeviceBuffer<RVec> d_x, GpuEventSynchronizer* xReadyOnDevice)
+{
+    GMX_RELEASE_ASSERT(nb->search != nullptr, "nbnxm_b200_gpu_set_atoms has to be called first");
+    GMX_RELEASE_ASSERT(box[YY][XX] == 0 && box[ZZ][XX] == 0 && box[ZZ][YY] == 0,
+                       "the device gridder handles rectangular unit cells");
+    if (xReadyOnDevice != nullptr)
+    {
+        xReadyOnDevice->enqueueWaitEvent(*nb->deviceStreams[0]);
+    }
+    const float boxDiag[3] = { box[XX][XX], box[YY][YY], box[ZZ][ZZ] };
+    check(nbnxm_b200_gpu_search_put_atoms_on_grid(
+                  nb->search, boxDiag, 1, reinterpret_cast<const float*>(d_x), nullptr, nullptr, nullptr, nullptr, nullptr),
+          "nbnxm_b200_gpu_search_put_atoms_on_grid");
+}
+
+//! PairlistSets::construct + gpu_init_pairlist for the local list of a single-domain run.
+void nbnxm_b200_gpu_construct_pairlist(NbnxmGpu* nb, InteractionLocality iloc, real rlist)
+{
+    GMX_RELEASE_ASSERT(nb->search != nullptr, "nbnxm_b200_gpu_put_atoms_on_grid has to be called first");
+    /* all bins against all bins (-1: up to the last bin), one zone */
+    check(nbnxm_b200_gpu_search_build(nb->search, toInt(iloc), rlist, nbnxm_b200_min_ci_balanced(nb->handle), 0, -1, 0, -1, 0, 0),
+          "nbnxm_b200_gpu_search_build");
+}
+
+//! GpuForceReduction::execute for the nonbonded forces: f_total[a] (+)= f_nbat[cell[a]] (+ f_other[a]); the atom -> slot
+//! map is the one nbnxm_b200_gpu_put_atoms_on_grid left on the device (or nbnxm_b200_init_reduce_f from GridSet::cells()).
+void nbnxm_b200_gpu_reduce_f(NbnxmGpu*          nb,
+                             DeviceBuffer<RVec> d_fTotal,
+                             DeviceBuffer<RVec> d_fToAdd,
+                             int                atomStart,
+                             int                numAtoms,
+                             bool               accumulate)
+{
+    check(nbnxm_b200_reduce_f(nb->handle,
+                              reinterpret_cast<float*>(d_fTotal),
+                              reinterpret_cast<const float*>(d_fToAdd),
+                              atomStart,
+                              numAtoms,
+                              accumulate ? 1 : 0,
+                              nullptr),
+          "nbnxm_b200_reduce_f");
 }
 
 int gpu_min_ci_balanced(NbnxmGpu* nb)

@@ -96,7 +96,8 @@ int nbnxm_b200_gpu_search_put_atoms_on_grid(nbnxm_b200_gpu_search_t* search, con
                                             void* x_ready_event, int* natoms_nbat, int* nbins, int* ncx, int* ncy);
 /* host copies of the grid order (GridSet::atomIndices, Grid::cxy_ind) and the device time of the last gridding (ms) */
 int nbnxm_b200_gpu_search_get_order(nbnxm_b200_gpu_search_t* search, int* atom_index, int* first_bin_of_column, float* grid_ms);
-/* arguments as nbnxm_b200_pairlist_build; the result becomes the handle's list for iloc (haveFreshList set) */
+/* arguments as nbnxm_b200_pairlist_build (bin_end / j_bin_hi < 0: up to the last bin of the grid); the result becomes
+ * the handle's list for iloc (haveFreshList set) */
 int nbnxm_b200_gpu_search_build(nbnxm_b200_gpu_search_t* search, int iloc, float rlist, int min_sci, int bin_begin,
                                 int bin_end, int j_bin_lo, int j_bin_hi, int inter_zone, int required_tx);
 /* sizes of the list built last, cluster pairs in it, device time of the build (ms, CUDA events) */
