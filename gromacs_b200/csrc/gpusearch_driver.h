@@ -132,7 +132,6 @@ struct SearchState
 
     Grid g{};
     bool haveGrid = false;
-    int  numExclAtoms = 0;
 
     Buf<int> colFirstBin, atomIndex, slotOfAtom, clCount, exclIndex, exclAtoms;
     Buf<BB>  clBB, binBB;
