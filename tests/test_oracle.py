@@ -122,3 +122,24 @@ def test_f32_port_matches_double_oracle(oracle):
     assert n32 == n
     assert relrms(f32.astype(np.float64), f) < 5e-6
     assert abs(e32[1] - e[1]) < 1e-4 * abs(e[1])
+
+
+@pytest.mark.parametrize("vdw", ["cutnone", "cutgeom", "cutlb", "fswitch", "pswitch", "ljpmegeom"])
+def test_oracle_lj_only_matches_reference_coulomb_none_refdata(oracle, vdw):
+    """ElecType::None (kernels without NBNxM electrostatics): the reference's golden XML for CoulombKernelType::None
+    (tests/golden/refdata/coulombnone.npz) against the oracle's plain cut-off flavor with the charges set to zero —
+    the oracle configuration the GPU's ElecNone flavor is checked against (tests/test_gpu_zz_elec_none.py)."""
+    import os
+    from util import GOLDEN
+    ref = np.load(os.path.join(GOLDEN, "refdata", "coulombnone.npz"))
+    d = load_golden("test243_ewald_" + vdw)
+    d0 = dict(d)
+    d0["nbat_xq"] = d["nbat_xq"].copy()
+    d0["nbat_xq"][:, 3] = 0
+    f, _, e, _ = oracle_forces(oracle, d0, oracle_params(oracle, d0, elec="Cut"))
+    fa = oracle.nbat_to_atom_order(f, d["nbat_atom_index"], d["sys_x"].shape[0])
+    assert ref["vcoul_" + vdw][0] == 0 and e[1] == 0
+    # refdata comes from double coordinates, ours are their float roundings: 3e-6 of the (smaller) LJ-only forces
+    assert relrms(fa, ref["f_" + vdw]) < 4e-6
+    assert maxrel(fa, ref["f_" + vdw]) < 1e-5
+    assert abs(e[0] - ref["vvdw_" + vdw][0]) < 2e-6 * abs(ref["vvdw_" + vdw][0]) + 1e-5
