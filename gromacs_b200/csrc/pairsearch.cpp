@@ -249,6 +249,13 @@ int nbnxm_b200_grid_info(const nbnxm_b200_grid_t* g, int* natoms_nbat, int* nbin
     return 0;
 }
 
+int nbnxm_b200_grid_box(const nbnxm_b200_grid_t* g, float* box)
+{
+    if (!g || !box) return fail("null grid");
+    for (int d = 0; d < 3; d++) box[d] = g->box[d];
+    return 0;
+}
+
 int nbnxm_b200_grid_get_order(const nbnxm_b200_grid_t* g, int* atom_index, int* first_bin_of_column)
 {
     if (!g) return fail("null grid");

@@ -43,17 +43,16 @@ class SlabPlan:
 
 
 def _reindex(pl, first_home_bin, first_halo_bin, num_home_bins, nclusters_total, halo):
-    """Global bin / cluster indices -> rank order (home bins first, then halo bins)."""
-    sci = pl.sci.copy()
-    cjp = pl.cjPacked.copy()
-    sci[:, 0] -= first_home_bin
-    cj = cjp[:, :4].astype(np.int64)
-    if halo:
-        cj = cj - first_halo_bin * 8 + num_home_bins * 8
-    else:
-        cj = cj - first_home_bin * 8
-    # unused slots of partially filled j-groups carry no mask bits and an unspecified index: keep them loadable
-    cjp[:, :4] = np.clip(cj, 0, nclusters_total - 1).astype(np.uint32)
+    """Global bin / cluster indices -> rank order (home bins first, then halo bins): nbnxm_b200_pairlist_reindex."""
+    import ctypes as C
+    from .nbnxm import load_library
+    sci = np.ascontiguousarray(pl.sci, np.int32).reshape(-1, 4).copy()
+    cjp = np.ascontiguousarray(pl.cjPacked, np.uint32).reshape(-1, 8).copy()
+    if load_library().nbnxm_b200_pairlist_reindex(
+            sci.ctypes.data_as(C.POINTER(C.c_int)), C.c_int(sci.shape[0]), cjp.ctypes.data_as(C.POINTER(C.c_uint32)),
+            C.c_int(cjp.shape[0]), C.c_int(first_home_bin), C.c_int(first_halo_bin), C.c_int(num_home_bins),
+            C.c_int(nclusters_total), C.c_int(int(halo))):
+        raise RuntimeError("nbnxm_b200_pairlist_reindex failed")
     return PairlistGpu(sci=sci, cjPacked=cjp, excl=pl.excl, na_ci=pl.na_ci, rlist=pl.rlist)
 
 

@@ -10,7 +10,8 @@ import numpy as np
 from .nbnxm import AtomData, NbnxmError, PairlistGpu, load_library
 
 SEARCH_SYMBOLS = [
-    "nbnxm_b200_grid_dims", "nbnxm_b200_grid_create", "nbnxm_b200_grid_create_slabs", "nbnxm_b200_grid_free", "nbnxm_b200_grid_info", "nbnxm_b200_grid_get_order",
+    "nbnxm_b200_grid_dims", "nbnxm_b200_grid_box", "nbnxm_b200_slab_bin_ranges", "nbnxm_b200_pairlist_reindex", "nbnxm_b200_chunk_plan",
+    "nbnxm_b200_grid_create", "nbnxm_b200_grid_create_slabs", "nbnxm_b200_grid_free", "nbnxm_b200_grid_info", "nbnxm_b200_grid_get_order",
     "nbnxm_b200_grid_fill_atomdata", "nbnxm_b200_pairlist_build", "nbnxm_b200_pairlist_sizes",
     "nbnxm_b200_pairlist_copy",
     "nbnxm_b200_gpu_search_create", "nbnxm_b200_gpu_search_free", "nbnxm_b200_gpu_search_set_grid",

@@ -1,10 +1,11 @@
 """Chunk plan for nbnxm_b200_do_force_step_pipelined: atoms cut into contiguous ranges of whole grid columns along x,
 the sci array grouped by the chunk of its i-atoms, and for every sci chunk the set of atom chunks its entries touch."""
+import ctypes as C
 from dataclasses import dataclass
 
 import numpy as np
 
-from .nbnxm import PairlistGpu
+from .nbnxm import NbnxmError, PairlistGpu, load_library
 
 
 @dataclass
@@ -17,36 +18,19 @@ class ChunkPlan:
 
 
 def make_chunk_plan(grid, plist: PairlistGpu, nchunks: int) -> ChunkPlan:
-    nchunks = int(max(1, min(nchunks, 32, grid.ncx)))
-    fb = np.asarray(grid.first_bin_of_column)
-    cols = [(grid.ncx * c) // nchunks for c in range(nchunks + 1)]
-    first_bin = np.array([int(fb[cx * grid.ncy]) for cx in cols], dtype=np.int64)
-    first_atom = (first_bin * 64).astype(np.int32)
-    sci = np.ascontiguousarray(plist.sci).reshape(-1, 4)
-    chunk_of_sci = np.searchsorted(first_bin, sci[:, 0], side="right") - 1
-    order = np.argsort(chunk_of_sci, kind="stable")
-    sci_sorted = np.ascontiguousarray(sci[order])
-    chunk_sorted = chunk_of_sci[order]
-    first_sci = np.searchsorted(chunk_sorted, np.arange(nchunks + 1), side="left").astype(np.int32)
-    # atom chunks touched by the j-clusters of every cjPacked group (outer list masks: a superset of what is evaluated)
-    cjp = np.ascontiguousarray(plist.cjPacked).view(np.uint32).reshape(-1, 8)
-    counts = (sci[:, 3] - sci[:, 2]).astype(np.int64)
-    owner_chunk = np.zeros(cjp.shape[0], np.int64)
-    starts = sci[:, 2].astype(np.int64)
-    # groups of an entry are contiguous [begin, end); entries do not overlap
-    idx = np.repeat(np.arange(sci.shape[0]), counts)
-    group_index = np.repeat(starts, counts) + (np.arange(counts.sum()) - np.repeat(np.cumsum(counts) - counts, counts))
-    owner_chunk[group_index] = chunk_of_sci[idx]
-    any_mask = cjp[:, 4] | cjp[:, 6]
-    needs = np.zeros(nchunks, np.uint32)
-    for k in range(nchunks):
-        needs[k] |= np.uint32(1 << k)
-    for jm in range(4):
-        valid = ((any_mask >> np.uint32(8 * jm)) & np.uint32(0xff)) != 0
-        cj_bin = (cjp[valid, jm].astype(np.int64) * 8) // 64
-        cj_chunk = np.searchsorted(first_bin, cj_bin, side="right") - 1
-        pairs = np.unique(owner_chunk[valid] * nchunks + cj_chunk)
-        for pr in pairs:
-            needs[int(pr) // nchunks] |= np.uint32(1 << (int(pr) % nchunks))
-    out = PairlistGpu(sci=sci_sorted, cjPacked=plist.cjPacked, excl=plist.excl, na_ci=plist.na_ci, rlist=plist.rlist)
-    return ChunkPlan(nchunks, first_atom, first_sci, needs, out)
+    """nbnxm_b200_chunk_plan (gromacs_b200/csrc/hostplan.cpp)"""
+    lib = load_library()
+    sci = np.ascontiguousarray(plist.sci, np.int32).reshape(-1, 4).copy()
+    cjp = np.ascontiguousarray(plist.cjPacked, np.uint32).reshape(-1, 8)
+    first_atom = np.zeros(33, np.int32)
+    first_sci = np.zeros(33, np.int32)
+    needs = np.zeros(32, np.uint32)
+    n = C.c_int()
+    p = lambda a, t: a.ctypes.data_as(C.POINTER(t))
+    if lib.nbnxm_b200_chunk_plan(grid._g, p(sci, C.c_int), C.c_int(sci.shape[0]), p(cjp, C.c_uint32), C.c_int(cjp.shape[0]),
+                                 C.c_int(int(nchunks)), C.byref(n), p(first_atom, C.c_int), p(first_sci, C.c_int),
+                                 p(needs, C.c_uint32)):
+        raise NbnxmError("nbnxm_b200_chunk_plan failed")
+    k = n.value
+    out = PairlistGpu(sci=sci, cjPacked=plist.cjPacked, excl=plist.excl, na_ci=plist.na_ci, rlist=plist.rlist)
+    return ChunkPlan(k, first_atom[:k + 1].copy(), first_sci[:k + 1].copy(), needs[:k].copy(), out)

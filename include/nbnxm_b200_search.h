@@ -36,6 +36,7 @@ int nbnxm_b200_grid_create_slabs(nbnxm_b200_grid_t** grid, const float* box, int
 int nbnxm_b200_grid_free(nbnxm_b200_grid_t* grid);
 /* number of nbat slots (atoms padded to whole 64-atom bins) and bins, grid columns along x and y */
 int nbnxm_b200_grid_info(const nbnxm_b200_grid_t* grid, int* natoms_nbat, int* nbins, int* ncx, int* ncy);
+int nbnxm_b200_grid_box(const nbnxm_b200_grid_t* grid, float* box3);
 /* atom_index[natoms_nbat]: nbat slot -> atom (-1 = filler) (GridSet::atomIndices);
  * first_bin_of_column[ncx*ncy + 1] (Grid::cellToBin_) */
 int nbnxm_b200_grid_get_order(const nbnxm_b200_grid_t* grid, int* atom_index, int* first_bin_of_column);
@@ -63,6 +64,22 @@ int nbnxm_b200_pairlist_sizes(const nbnxm_b200_grid_t* grid, int* nsci, int* ncj
                               long long* ncluster_pairs);
 int nbnxm_b200_pairlist_copy(const nbnxm_b200_grid_t* grid, nbnxm_b200_sci_t* sci, nbnxm_b200_cj_packed_t* cj_packed,
                              nbnxm_b200_excl_t* excl);
+
+/* ---- host-side planning (gromacs_b200/csrc/hostplan.cpp) ----
+ * x-slab decomposition over nslabs GPUs, one process per GPU: bins of slab r (home), of its one-sided halo (the first
+ * columns of slab (r+1) % nslabs within rlist, plus one column of slack) and the x shift of the home x halo pairs
+ * (-1 across the periodic boundary); the analogue of the reference's zone set-up, domdec/domdec_zones.cpp:55-83 */
+int nbnxm_b200_slab_bin_ranges(const nbnxm_b200_grid_t* grid, int nslabs, int r, float rlist, int* home_begin, int* home_end,
+                               int* halo_begin, int* halo_end, int* required_tx);
+/* a list built on the global grid -> one rank's atom order (home bins first, then halo bins), in place: sci.sci relative
+ * to the first home bin, j-clusters relative to the home range (halo = 0) or placed after it (halo = 1) */
+int nbnxm_b200_pairlist_reindex(nbnxm_b200_sci_t* sci, int nsci, nbnxm_b200_cj_packed_t* cj_packed, int ncj_packed, int first_home_bin,
+                                int first_halo_bin, int num_home_bins, int nclusters_total, int halo);
+/* chunk plan of nbnxm_b200_do_force_step_pipelined (include/nbnxm_b200.h): at most 32 chunks of whole grid columns;
+ * first_atom / first_sci: [nchunks + 1]; needs[k]: bit c set = entries of sci chunk k read or write atoms of chunk c;
+ * the sci array is grouped by chunk in place (entries of a chunk keep their order) */
+int nbnxm_b200_chunk_plan(const nbnxm_b200_grid_t* grid, nbnxm_b200_sci_t* sci, int nsci, const nbnxm_b200_cj_packed_t* cj_packed,
+                          int ncj_packed, int nchunks_requested, int* nchunks, int* first_atom, int* first_sci, unsigned int* needs);
 
 /* ---- the same list built on the GPU (gromacs_b200/csrc/nbnxm_gpusearch.cu) ----
  *
