@@ -1,21 +1,26 @@
-/* Per-thread bodies of the GPU pair-list builder (nbnxm_gpusearch.cu), written as host+device functions.
+/* Per-item bodies of the search step on the GPU (nbnxm_gpusearch.cu), written as host+device functions.
  *
- * The builder is a sequence of data-parallel passes with a prefix sum between them; every pass is "one thread per
- * work item, no intra-block cooperation", so each body below is a plain function of the item index.  The CUDA
- * kernels are thin wrappers (`index = blockIdx.x * blockDim.x + threadIdx.x`); tests/kernel_emu runs the same
- * bodies in a host loop so that the search logic is checked on a machine without a GPU (test infrastructure, not a
- * product path: the library itself only ever launches the kernels).
+ * Gridding (second half of this file) and pair-list construction (first half) are sequences of data-parallel passes
+ * with a prefix sum between them.  Three kinds of pass:
+ *   item passes   - one thread per work item, no cooperation: the body is a plain function of the item index;
+ *   block passes  - one block per column (the column sort): stages of independent items separated by block barriers,
+ *                   the body is a function of (block, stage, item) on the block's scratch memory;
+ *   warp passes   - one warp per item (the cooperative form of the mask pass): per-lane functions joined by warp votes.
+ * The CUDA kernels are thin wrappers (index arithmetic, barriers, votes); tests/kernel_emu runs the same bodies in
+ * host loops so that the search logic is checked on a machine without a GPU (test infrastructure, not a product path:
+ * the library itself only ever launches the kernels).
  *
- * What is built is what the reference's CPU search hands to gpu_init_pairlist, in its formats
- * (src/gromacs/nbnxm/pairlist.h:189-287): super-cluster entries from a bounding-box sweep over the column grid
+ * What is built is what the reference's CPU search hands to gpu_init_atomdata / gpu_init_pairlist, in its formats
+ * (src/gromacs/nbnxm/pairlist.h:189-287): atoms binned and sorted into columns, bins and clusters (Grid::putOnGrid,
+ * grid.cpp:1612; sortCellsGpuGeometry :1169), super-cluster entries from a bounding-box sweep over the column grid
  * (pairlist.cpp:2827-3310), cluster-pair masks with the bounding-box / atom-pair distance test
  * (make_cluster_list_supersub, pairlist.cpp:813-966), self + Newton exclusions on the diagonal (:651-688), topology
  * exclusions (:1561-1660) and splitting of long i-entries (:1769-1879).
  *
  * Arithmetic is spelled with explicit fmaf so that the host builder (pairsearch.cpp), the emulation and the device
- * produce the same bits; the lists are then equal entry for entry.
+ * produce the same bits; grid order and lists are then equal entry for entry.
  *
- * Work items:
+ * Work items of the list passes:
  *   entry slot e = (bin - binBegin) * 27 + s, s = (tz+1)*9 + (ty+1)*3 + (tx+1): one candidate i-entry (bin, shift);
  *   bin pair p: (entry, j-bin) whose bounding boxes are within rlist, listed per entry in ascending j-bin order
  *   (own bin first on the central shift), so that the j-clusters of an entry are sorted by cluster index.
