@@ -143,3 +143,42 @@ def test_oracle_lj_only_matches_reference_coulomb_none_refdata(oracle, vdw):
     assert relrms(fa, ref["f_" + vdw]) < 4e-6
     assert maxrel(fa, ref["f_" + vdw]) < 1e-5
     assert abs(e[0] - ref["vvdw_" + vdw][0]) < 2e-6 * abs(ref["vvdw_" + vdw][0]) + 1e-5
+
+
+@pytest.mark.parametrize("case", ["test243_ewald_cutnone_rl1.0_split", "bench1_ewald_cutgeom"])
+def test_prune_restatement_against_numpy_distances(oracle, case):
+    """The masks the prune restatement keeps, re-derived independently in numpy (double precision): bit jm*8+i of half w
+    survives iff some atom pair of i-cluster i and the 4 j-atoms of half w of j-cluster jm lies within the list radius
+    (nbnxm_cuda_kernel_pruneonly.cuh:223-321).  Pairs within 1e-6 (relative) of the radius may fall either way in
+    float32; everything else must agree, for the outer and the inner mask."""
+    d = load_golden(case)
+    rl = float(d["rlist"][0])
+    rin = 0.5 * (rl + float(d["ic_rcoulomb"][0]))
+    p = oracle_params(oracle, d, rlist_inner=rin)
+    cj0 = d["pl_cjPacked"].copy()
+    cj = cj0.copy()
+    outer = np.zeros(2 * cj.shape[0], np.uint32)
+    oracle.prune(p, d["pl_sci"], cj, outer, d["nbat_xq"], d["shift_vec"], fresh=True)
+    x = d["nbat_xq"][:, :3].astype(np.float64)
+    sv = d["shift_vec"].astype(np.float64)
+    checked = 0
+    for s in d["pl_sci"]:
+        xi = x[s[0] * 64:(s[0] + 1) * 64].reshape(8, 8, 3) + sv[s[1]]                  # [i-cluster, atom]
+        for g in range(s[2], s[3]):
+            for jm in range(4):
+                xj = x[int(cj0[g, jm]) * 8:int(cj0[g, jm]) * 8 + 8]
+                r2 = ((xi[:, :, None, :] - xj[None, None, :, :]) ** 2).sum(-1)            # [i-cluster, i-atom, j-atom]
+                for w in range(2):
+                    r2min = r2[:, :, 4 * w:4 * w + 4].min(axis=(1, 2))                      # per i-cluster
+                    for i in range(8):
+                        bit = 1 << (jm * 8 + i)
+                        if not (int(cj0[g, 4 + 2 * w]) & bit):
+                            assert not (int(outer[2 * g + w]) & bit) and not (int(cj[g, 4 + 2 * w]) & bit)
+                            continue
+                        for radius, kept in ((rl, int(outer[2 * g + w]) & bit), (rin, int(cj[g, 4 + 2 * w]) & bit)):
+                            if r2min[i] < radius * radius * (1 - 1e-6):
+                                assert kept, (g, jm, w, i, r2min[i], radius)
+                            elif r2min[i] > radius * radius * (1 + 1e-6):
+                                assert not kept, (g, jm, w, i, r2min[i], radius)
+                            checked += 1
+    assert checked > 1000
