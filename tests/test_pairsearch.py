@@ -138,3 +138,31 @@ def test_chunk_plan_covers_every_atom_an_entry_touches(nchunks):
                 for jm in range(4):
                     if ((int(g[4]) | int(g[6])) >> (8 * jm)) & 0xff:
                         assert plan.needs[c] & (1 << chunk_of_atom(int(g[jm]) * 8)), (c, jm, g)
+
+
+def test_search_abi_rejects_bad_arguments():
+    """the host-side search entry points fail with a status (never crash) on caller mistakes"""
+    import ctypes as C
+    from gromacs_b200 import load_library
+    from gromacs_b200.pairsearch import Grid
+    from gromacs_b200.slabs import slab_bin_ranges
+    from gromacs_b200.nbnxm import NbnxmError
+    lib = load_library()
+    d = load_golden("test243_ewald_cutnone")
+    g = C.c_void_p()
+    box = np.ascontiguousarray(d["sys_box"], np.float32)
+    x = np.ascontiguousarray(d["sys_x"], np.float32)
+    fp = lambda a: a.ctypes.data_as(C.POINTER(C.c_float))
+    assert lib.nbnxm_b200_grid_create(C.byref(g), fp(box), C.c_int(0), fp(x), C.c_int(1)) != 0          # no atoms
+    assert lib.nbnxm_b200_grid_create(C.byref(g), None, C.c_int(243), fp(x), C.c_int(1)) != 0            # no box
+    ncx, ncy = C.c_int(), C.c_int()
+    assert lib.nbnxm_b200_grid_dims(fp(box), C.c_int(243), C.c_int(0), C.byref(ncx), C.byref(ncy)) != 0  # no slabs
+    grid = Grid(d["sys_box"], d["sys_x"], nthreads=1)
+    with pytest.raises(NbnxmError):
+        grid.pairlist(0.6 * float(d["sys_box"].min()))                                                    # rlist > half the box
+    with pytest.raises(NbnxmError):
+        grid.pairlist(0.9, bins=(0, grid.nbins + 1))                                                      # bin range
+    with pytest.raises(ValueError):
+        slab_bin_ranges(grid, 2, 0, 0.9)                                                                   # slabs thinner than the halo
+    with pytest.raises(ValueError):
+        slab_bin_ranges(grid, 2, 2, 0.9)                                                                   # rank outside the slabs
