@@ -69,24 +69,50 @@ def host_cores():
         return os.cpu_count() or 1
 
 
+def host_has_avx512():
+    try:
+        with open("/proc/cpuinfo") as fh:
+            flags = fh.read()
+        return all(f in flags for f in (" avx512f", " avx512bw", " avx512vl", " avx512dq", " avx512cd"))
+    except Exception:
+        return False
+
+
 def run_reference_cpu(cfg, natoms_k, budget_s=20.0, threads=None):
-    """Time the reference's SIMD kernel on a bounded number of iterations (about budget_s of CPU work)."""
-    exe = os.path.join(ROOT, "oracle", "_ref", "bench_ref")
+    """Time the reference's SIMD kernel on a bounded number of iterations (about budget_s of CPU work).  Two builds of
+    the unmodified reference may be present (oracle/ref_harness/build_ref.sh): AVX2_256 and, where the host has
+    AVX-512, AVX_512; a short probe picks the faster one, which is then timed."""
     threads = threads or host_cores()
-    if not os.path.exists(exe):
+    exes = [("AVX2_256", os.path.join(ROOT, "oracle", "_ref", "bench_ref"))]
+    if host_has_avx512():
+        exes.append(("AVX_512", os.path.join(ROOT, "oracle", "_ref", "bench_ref_avx512")))
+    exes = [(n, e) for n, e in exes if os.path.exists(e)]
+    if not exes:
         return None
-    base = [exe, "--size", str(natoms_k), "--rc", str(cfg["rc"]), "--vdw", REF_VDW[cfg["vdw"]],
+    args = ["--size", str(natoms_k), "--rc", str(cfg["rc"]), "--vdw", REF_VDW[cfg["vdw"]],
             "--energy", "1" if cfg["energy"] else "0", "--nt", str(threads)]
     env = dict(os.environ, OMP_NUM_THREADS=str(threads), OMP_PROC_BIND="close", OMP_PLACES="cores")
 
-    def call(iters, warm):
-        out = subprocess.run(base + ["--iter", str(iters), "--warmup", str(warm)], env=env, check=True,
-                             capture_output=True, text=True).stdout.strip().splitlines()[-1]
+    def call(exe, kernel, iters, warm):
+        out = subprocess.run([exe] + args + ["--kernel", kernel, "--iter", str(iters), "--warmup", str(warm)], env=env,
+                             check=True, capture_output=True, text=True).stdout.strip().splitlines()[-1]
         return json.loads(out)
-    probe = call(2, 1)
-    iters = int(max(3, min(2000, budget_s / max(probe["sec_per_iter"], 1e-6))))
-    res = call(iters, 2)
+    # the reference's two SIMD kernel layouts (Cpu4xN_Simd_4xN, Cpu4xN_Simd_2xNN) in every build present
+    probes = []
+    for name, exe in exes:
+        for kernel in ("4xm", "2xmm"):
+            try:
+                probes.append((call(exe, kernel, 2, 1)["sec_per_iter"], name + " " + kernel, exe, kernel))
+            except Exception:      # a layout this SIMD width does not have, an instruction set the host lacks after all
+                pass
+    if not probes:
+        return None
+    sec, name, exe, kernel = min(probes)
+    iters = int(max(3, min(2000, budget_s / max(sec, 1e-6))))
+    res = call(exe, kernel, iters, 2)
     res["threads"] = threads
+    res["simd"] = name
+    res["simd_probed"] = {n: round(s, 6) for s, n, _, _ in probes}
     return res
 
 
@@ -210,7 +236,8 @@ def reference_arm(args):
         "vs_baseline": None, "dtype": "f32", "data": "synthetic",
         "config": {"workload": args.workload, "natoms": int(res["natoms"]), "rc_nm": cfg["rc"], "vdw": cfg["vdw"],
                    "energy_every_step": cfg["energy"],
-                   "note": "reference SIMD 4xM kernel (AVX2_256 build), its own CPU pair list with rlist = rc"},
+                   "note": "reference SIMD kernel (%s; probed s/iteration %s), its own CPU pair list with rlist = rc"
+                           % (res["simd"], json.dumps(res["simd_probed"]))},
         "cpu_baseline": {"value": value, "unit": UNIT, "cores": res["threads"], "kind": "reference",
                          "sample": "%d iterations of the full %d-atom system" % (res["iters"], int(res["natoms"]))},
         "e2e": {"value": value, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
@@ -427,7 +454,7 @@ def main():
         if res is not None:
             line["cpu_baseline"] = {"value": res["useful_pairs"] / res["sec_per_iter"] * 1e-9, "unit": UNIT,
                                     "cores": res["threads"], "kind": "reference",
-                                    "sample": "%d iterations of the reference SIMD 4xM kernel on the full system" % res["iters"]}
+                                    "sample": "%d iterations of the reference SIMD kernel (%s, the fastest of its builds / layouts here) on the full system" % (res["iters"], res["simd"])}
         else:
             r = run_port_cpu(wl, plist)
             frac = r["computed_pairs"] / max(1, pairs_first)

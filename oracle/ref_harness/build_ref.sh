@@ -37,3 +37,20 @@ mkdir -p "$OUT/lib"
 cp -L "$BLD/lib/libgromacs.so.12" "$BLD/lib/libmuparser.so.2" "$OUT/lib/"
 strip --strip-unneeded "$OUT/lib/libgromacs.so.12" || true
 echo "built $OUT/dump_nbnxm $OUT/bench_ref"
+# optional second flavour of the timing harness: the same sources against an AVX_512 build of the reference
+# (BLD512, configured like BLD but with -DGMX_SIMD=AVX_512); bench.py times both where the host supports AVX-512 and
+# reports the faster one, as SURVEY.md section 8d asks
+BLD512=${BLD512:-/tmp/gmxbuild512}
+if [ -f "$BLD512/lib/libgromacs.so" ]; then
+    INC512="-I$REF/src/include -I$BLD512/src/include -I$REF/src -I$REF/api/legacy/include -I$BLD512/api/legacy/include"
+    for m in math timing utility pbcutil topology serialization simd taskassignment; do
+        INC512="$INC512 -I$REF/src/gromacs/$m/include"
+    done
+    INC512="$INC512 -isystem $REF/src/external/thread_mpi/include -isystem $REF/src/external"
+    /usr/bin/g++ -O2 -std=c++17 -march=skylake-avx512 -fopenmp -DGMX_DOUBLE=0 -DHAVE_CONFIG_H $INC512 \
+        "$HERE/bench_ref.cpp" -L"$BLD512/lib" -lgromacs -Wl,-rpath,'$ORIGIN/lib512' -o "$OUT/bench_ref_avx512"
+    mkdir -p "$OUT/lib512"
+    cp -L "$BLD512/lib/libgromacs.so.12" "$BLD512/lib/libmuparser.so.2" "$OUT/lib512/"
+    strip --strip-unneeded "$OUT/lib512/libgromacs.so.12" || true
+    echo "built $OUT/bench_ref_avx512"
+fi
