@@ -93,21 +93,25 @@ def run_reference_cpu(cfg, natoms_k, budget_s=20.0, threads=None):
             "--energy", "1" if cfg["energy"] else "0", "--nt", str(threads)]
     env = dict(os.environ, OMP_NUM_THREADS=str(threads), OMP_PROC_BIND="close", OMP_PLACES="cores")
 
-    def call(exe, kernel, iters, warm):
-        out = subprocess.run([exe] + args + ["--kernel", kernel, "--iter", str(iters), "--warmup", str(warm)], env=env,
+    def call(exe, kernel, iters, warm, size=natoms_k):
+        a = list(args)
+        a[1] = str(size)
+        out = subprocess.run([exe] + a + ["--kernel", kernel, "--iter", str(iters), "--warmup", str(warm)], env=env,
                              check=True, capture_output=True, text=True).stdout.strip().splitlines()[-1]
         return json.loads(out)
-    # the reference's two SIMD kernel layouts (Cpu4xN_Simd_4xN, Cpu4xN_Simd_2xNN) in every build present
+    # the reference's two SIMD kernel layouts (Cpu4xN_Simd_4xN, Cpu4xN_Simd_2xNN) in every build present, ranked on a
+    # 96 k-atom box of the same flavor (seconds), so that the full-size system is set up only for the one that is timed
     probes = []
     for name, exe in exes:
         for kernel in ("4xm", "2xmm"):
             try:
-                probes.append((call(exe, kernel, 2, 1)["sec_per_iter"], name + " " + kernel, exe, kernel))
+                probes.append((call(exe, kernel, 5, 2, size=min(natoms_k, 32))["sec_per_iter"], name + " " + kernel, exe, kernel))
             except Exception:      # a layout this SIMD width does not have, an instruction set the host lacks after all
                 pass
     if not probes:
         return None
-    sec, name, exe, kernel = min(probes)
+    _, name, exe, kernel = min(probes)
+    sec = call(exe, kernel, 2, 1)["sec_per_iter"]
     iters = int(max(3, min(2000, budget_s / max(sec, 1e-6))))
     res = call(exe, kernel, iters, 2)
     res["threads"] = threads
@@ -236,7 +240,7 @@ def reference_arm(args):
         "vs_baseline": None, "dtype": "f32", "data": "synthetic",
         "config": {"workload": args.workload, "natoms": int(res["natoms"]), "rc_nm": cfg["rc"], "vdw": cfg["vdw"],
                    "energy_every_step": cfg["energy"],
-                   "note": "reference SIMD kernel (%s; probed s/iteration %s), its own CPU pair list with rlist = rc"
+                   "note": "reference SIMD kernel (%s; s/iteration of its builds / layouts on a 96 k-atom probe: %s), its own CPU pair list with rlist = rc"
                            % (res["simd"], json.dumps(res["simd_probed"]))},
         "cpu_baseline": {"value": value, "unit": UNIT, "cores": res["threads"], "kind": "reference",
                          "sample": "%d iterations of the full %d-atom system" % (res["iters"], int(res["natoms"]))},
