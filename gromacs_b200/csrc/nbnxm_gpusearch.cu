@@ -254,15 +254,21 @@ int nbnxm_b200_gpu_search_create(nbnxm_b200_gpu_search_t** out, nbnxm_b200_t* nb
 {
     if (!out || !nb) return fail("nbnxm_b200_gpu_search_create: null argument");
     CU(cudaSetDevice(nb->device));
+    void*       pinned = nullptr;
+    cudaEvent_t ev[2]  = { nullptr, nullptr };
+    if (cudaMallocHost(&pinned, 16) != cudaSuccess || cudaEventCreate(&ev[0]) != cudaSuccess || cudaEventCreate(&ev[1]) != cudaSuccess)
+    {
+        if (pinned) cudaFreeHost(pinned);
+        if (ev[0]) cudaEventDestroy(ev[0]);
+        return fail("nbnxm_b200_gpu_search_create: %s", cudaGetErrorString(cudaGetLastError()));
+    }
     nbnxm_b200_gpu_search* s = new nbnxm_b200_gpu_search();
     s->nb                    = nb;
     s->device                = nb->device;
     s->be.st                 = nb->stream[0];
-    void* pinned             = nullptr;
-    CU(cudaMallocHost(&pinned, 16));
-    s->be.h_value = static_cast<int*>(pinned);
-    CU(cudaEventCreate(&s->evStart));
-    CU(cudaEventCreate(&s->evStop));
+    s->be.h_value            = static_cast<int*>(pinned);
+    s->evStart               = ev[0];
+    s->evStop                = ev[1];
     /* opt-in until it has been run on a GPU (checked through the emulation only) */
     const char* coop        = getenv("NBNXM_B200_SEARCH_COOP");
     s->st.cooperativeMasks = coop != nullptr && coop[0] == '1';

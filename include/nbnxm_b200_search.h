@@ -91,6 +91,7 @@ int nbnxm_b200_chunk_plan(const nbnxm_b200_grid_t* grid, nbnxm_b200_sci_t* sci, 
  * nbnxm_b200_copy_xq_to_gpu -> nbnxm_b200_gpu_search_set_grid -> nbnxm_b200_gpu_search_build. */
 typedef struct nbnxm_b200_gpu_search nbnxm_b200_gpu_search_t;
 
+/* one search object per force handle; it runs on the handle's local stream and must be freed before the handle */
 int nbnxm_b200_gpu_search_create(nbnxm_b200_gpu_search_t** search, nbnxm_b200_t* nb);
 int nbnxm_b200_gpu_search_free(nbnxm_b200_gpu_search_t* search);
 /* the grid of nbnxm_b200_grid_get_order / nbnxm_b200_grid_info (nbins * 64 must equal the handle's natoms) and the
