@@ -140,7 +140,7 @@ def test_force_reduction_gathers_nbat_forces_into_atom_order():
     """nbnxm_b200_reduce_f (reduceKernel, mdlib/gpuforcereduction_impl_internal.cu:61-118): set / accumulate, with and
     without an extra rvec force, on an atom sub-range, against the copied-back nbat forces."""
     import torch
-    from gromacs_b200 import LOCAL, NbnxmGpu
+    from gromacs_b200 import LOCAL, NbnxmGpu, StepWorkload
     d, grid, nbat = golden_system("bench1_ewald_cutnone")
     plist = grid.pairlist(0.9, d["sys_excl_index"], d["sys_excl_atoms"])
     n = d["sys_x"].shape[0]
@@ -169,7 +169,7 @@ def test_force_reduction_gathers_nbat_forces_into_atom_order():
                 a0, na = 64, n - 100
                 nb.gpu_force_reduction_execute(d_total.data_ptr(), d_extra.data_ptr() if with_extra else None, a0, na,
                                                accumulate, stream)
-                nb.gpu_wait_finish_task(__import__("gromacs_b200").StepWorkload(), LOCAL)
+                nb.gpu_wait_finish_task(StepWorkload(), LOCAL)
                 torch.cuda.synchronize()
                 want = base.copy()
                 sl = slice(a0, a0 + na)
@@ -203,7 +203,7 @@ def test_search_step_entirely_on_the_device(case, rlist, min_sci):
     """grid order, atom data, list and forces from device-resident atom-order coordinates equal the host path's; the
     force reduction maps the forces back to atom order with the device-built atom -> slot map"""
     import torch
-    from gromacs_b200 import LOCAL, NbnxmGpu
+    from gromacs_b200 import LOCAL, NbnxmGpu, StepWorkload
     d, grid, nbat = golden_system(case)
     n = d["sys_x"].shape[0]
     ref = grid.pairlist(rlist, d["sys_excl_index"], d["sys_excl_atoms"], min_sci=min_sci)
@@ -223,7 +223,7 @@ def test_search_step_entirely_on_the_device(case, rlist, min_sci):
         d_total = torch.zeros((n, 3), dtype=torch.float32, device="cuda")
         torch.cuda.synchronize()
         nb.gpu_force_reduction_execute(d_total.data_ptr(), None, 0, n, False, nb.streams()[0])
-        nb.gpu_wait_finish_task(__import__("gromacs_b200").StepWorkload(), LOCAL)
+        nb.gpu_wait_finish_task(StepWorkload(), LOCAL)
         torch.cuda.synchronize()
         slots = np.nonzero(grid.atom_index >= 0)[0]
         f_atoms = np.zeros((n, 3))
