@@ -301,6 +301,11 @@ int nbnxm_b200_free(nbnxm_b200_t* nb)
     nb->xq.release(); nb->f4.release(); nb->f3.release(); nb->atomType.release(); nb->ljComb.release();
     nb->shiftVec.release(); nb->fshift.release(); nb->energy.release(); nb->nbfp.release();
     nb->nbfpComb.release(); nb->coulombTab.release(); nb->atomIndex.release(); nb->packedConsts.release(); nb->cell.release();
+    nb->fepQ.release(); nb->fepType.release(); nb->fepLjComb.release(); nb->fepDvdl.release();
+    for (nbnxm_b200::FepList& fl : nb->feplist)
+    {
+        fl.pairEntry.release(); fl.iinr.release(); fl.shift.release(); fl.jjnr.release(); fl.exclFep.release();
+    }
     for (PairList& pl : nb->plist)
     {
         pl.sci.release(); pl.sciSorted.release(); pl.sciCount.release(); pl.sciHistogram.release();
@@ -946,6 +951,8 @@ int nbnxm_b200_clear_outputs(nbnxm_b200_t* nb, int compute_virial)
     {
         CU(cudaMemsetAsync(nb->fshift.p, 0, sizeof(double) * 3 * c_numShiftVectors, st));
         CU(cudaMemsetAsync(nb->energy.p, 0, sizeof(double) * 2, st));
+        /* dV/dlambda of the perturbed kernels is cleared with the energies (clearing of dvdlLJ / dvdlElec next to eLJ / eElec) */
+        if (nb->fepDvdl.p) CU(cudaMemsetAsync(nb->fepDvdl.p, 0, sizeof(double) * 2, st));
     }
     return 0;
 }

@@ -161,6 +161,23 @@ struct nbnxm_b200
     std::vector<cudaEvent_t> chunkH2D, chunkKernel;
     cudaEvent_t              pipeStart = nullptr, pipeD2HDone = nullptr;
 
+    /* perturbed (FEP) pair kernels, nbnxm_fep.cu: end-state atom data, pair lists, coupling parameters, dV/dlambda */
+    struct FepList
+    {
+        nbb::DevBuf<int>           pairEntry, iinr, shift, jjnr;
+        nbb::DevBuf<unsigned char> exclFep;
+        int                        numI = 0, numPairs = 0;
+    };
+    FepList             feplist[2];
+    nbb::DevBuf<float>  fepQ;      /* 2 per atom */
+    nbb::DevBuf<int>    fepType;   /* 2 per atom */
+    nbb::DevBuf<float>  fepLjComb; /* 4 per atom */
+    nbb::DevBuf<double> fepDvdl;   /* VdW, Coulomb */
+    bool                haveFep = false, haveFepAtomdata = false;
+    float               fepAlphaCoul = 0, fepAlphaVdw = 0, fepSigma6WithInvalidSigma = 0, fepSigma6Minimum = 0;
+    float               fepLambdaCoul = 0, fepLambdaVdw = 0;
+    int                 fepLambdaPower = 1;
+
     nbb::HaloState* halo = nullptr;
     std::set<const void*> carveoutSet; /* kernels whose shared-memory carve-out preference was set */
 

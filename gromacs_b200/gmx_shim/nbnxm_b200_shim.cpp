@@ -28,6 +28,7 @@
 #include "gromacs/mdtypes/locality.h"
 #include "gromacs/mdtypes/simulation_workload.h"
 #include "gromacs/nbnxm/atomdata.h"
+#include "gromacs/nbnxm/atompairlist.h"
 #include "gromacs/nbnxm/gpu_data_mgmt.h"
 #include "gromacs/nbnxm/gridset.h"
 #include "gromacs/nbnxm/nbnxm.h"
@@ -61,6 +62,8 @@ struct NbnxmGpu
     gmx_wallclock_gpu_nbnxm_t timings;
     /* the search step on the device (nbnxm_b200_gpu_search_*), created on first use */
     nbnxm_b200_gpu_search_t* search = nullptr;
+    /* perturbed (FEP) pair kernels in use (copy_gpu_fepparams) */
+    bool haveFep = false;
 };
 
 namespace
@@ -239,6 +242,18 @@ void gpu_init_atomdata(NbnxmGpu* nb, const nbnxm_atomdata_t* nbat)
                                    nb->useLjCombRule ? nullptr : params.type.data(),
                                    nb->useLjCombRule ? params.lj_comb.data() : nullptr),
           "nbnxm_b200_init_atomdata");
+    /* end-state data of the perturbed kernels (NBAtomDataGpu::q4 / atomTypes4 / ljComb4), when the run has them */
+    if (nb->haveFep && !params.qA.empty())
+    {
+        check(nbnxm_b200_init_fep_atomdata(nb->handle,
+                                           params.qA.data(),
+                                           params.qB.data(),
+                                           nb->useLjCombRule ? nullptr : params.typeA.data(),
+                                           nb->useLjCombRule ? nullptr : params.typeB.data(),
+                                           nb->useLjCombRule ? params.ljCombA.data() : nullptr,
+                                           nb->useLjCombRule ? params.ljCombB.data() : nullptr),
+              "nbnxm_b200_init_fep_atomdata");
+    }
 }
 
 void gpu_upload_shiftvec(NbnxmGpu* nb, const nbnxm_atomdata_t* nbatom)
@@ -516,14 +531,72 @@ void gpu_pme_loadbal_update_param(nonbonded_verlet_t* nbv, const interaction_con
 
 /* Perturbed-interaction (FEP) kernels work on atom-pair lists and are a separate backend piece
  * (src/gromacs/nbnxm/cuda/nbfe_cuda.cu); not part of this path. */
-void copy_gpu_fepparams(NbnxmGpu*, bool, float, float, int, float, float, float, float, int,
-                        const EnumerationArray<FreeEnergyPerturbationCouplingType, std::vector<double>>&)
+/* ---- perturbed (free-energy) pair kernels: gpu_data_mgmt.h:75, :106, nbnxm_gpu.h:115 ---- */
+
+void copy_gpu_fepparams(NbnxmGpu*   nb,
+                        bool        bFepGpuNonBonded,
+                        float       alphaCoul,
+                        float       alphaVdw,
+                        int         lambdaPower,
+                        float       sigma6WithInvalidSigma,
+                        float       sigma6Minimum,
+                        float       lambdaCoul,
+                        float       lambdaVdw,
+                        int         nLambda,
+                        const EnumerationArray<FreeEnergyPerturbationCouplingType, std::vector<double>>& /*all_lambda*/)
 {
-    gmx_fatal(FARGS, "Perturbed (FEP) nonbonded kernels are not part of the nbnxm_b200 backend");
+    if (bFepGpuNonBonded && nLambda > 1)
+    {
+        gmx_fatal(FARGS, "Foreign-lambda energies of the perturbed nonbonded kernels are not part of the nbnxm_b200 backend");
+    }
+    nb->haveFep = bFepGpuNonBonded;
+    check(nbnxm_b200_copy_fepparams(nb->handle,
+                                    bFepGpuNonBonded ? 1 : 0,
+                                    alphaCoul,
+                                    alphaVdw,
+                                    lambdaPower,
+                                    sigma6WithInvalidSigma,
+                                    sigma6Minimum,
+                                    lambdaCoul,
+                                    lambdaVdw),
+          "nbnxm_b200_copy_fepparams");
 }
-void gpu_init_feppairlist(NbnxmGpu*, const AtomPairlist&, InteractionLocality, ArrayRef<const int>)
+
+void gpu_init_feppairlist(NbnxmGpu* nb, const AtomPairlist& h_feplist, InteractionLocality iloc, ArrayRef<const int> atomIndices)
 {
-    gmx_fatal(FARGS, "Perturbed (FEP) nonbonded kernels are not part of the nbnxm_b200 backend");
+    /* the list holds atom indices; the kernels work in nbat order (nbnxm_gpu_data_mgmt.cpp:887-915) */
+    std::vector<int> slotOfAtom(atomIndices.size(), 0);
+    for (int i = 0; i < atomIndices.ssize(); i++)
+    {
+        if (atomIndices[i] >= 0 && atomIndices[i] < atomIndices.ssize())
+        {
+            slotOfAtom[atomIndices[i]] = i;
+        }
+    }
+    ArrayRef<const AtomPairlist::IEntry> iList = h_feplist.iList();
+    ArrayRef<const AtomPairlist::JEntry> jList = h_feplist.flatJList();
+    std::vector<int>                     iinr(iList.size()), shift(iList.size()), jindex(iList.size() + 1, 0), jjnr(jList.size());
+    std::vector<unsigned char>           interacts(jList.size());
+    for (int i = 0; i < iList.ssize(); i++)
+    {
+        iinr[i]       = slotOfAtom[iList[i].atom];
+        shift[i]      = iList[i].shiftIndex;
+        jindex[i + 1] = jindex[i] + static_cast<int>(h_feplist.jList(i).size());
+    }
+    for (int j = 0; j < jList.ssize(); j++)
+    {
+        jjnr[j]      = slotOfAtom[jList[j].atom];
+        interacts[j] = jList[j].interacts ? 1 : 0;
+    }
+    check(nbnxm_b200_init_feppairlist(
+                  nb->handle, toInt(iloc), static_cast<int>(iinr.size()), iinr.data(), jindex.data(), jjnr.data(), shift.data(), interacts.data()),
+          "nbnxm_b200_init_feppairlist");
+}
+
+void gpu_launch_free_energy_kernel(NbnxmGpu* nb, const SimulationWorkload& /*simulationWork*/, const StepWorkload& stepWork, InteractionLocality iloc)
+{
+    check(nbnxm_b200_launch_free_energy_kernel(nb->handle, toInt(iloc), stepWork.computeEnergy ? 1 : 0, stepWork.computeVirial ? 1 : 0),
+          "nbnxm_b200_launch_free_energy_kernel");
 }
 
 } // namespace gmx

@@ -33,6 +33,8 @@ EXPORTED_SYMBOLS = [
     "nbnxm_b200_insert_nonlocal_dependency", "nbnxm_b200_setup_short_range_work",
     "nbnxm_b200_have_short_range_work", "nbnxm_b200_min_ci_balanced",
     "nbnxm_b200_is_kernel_ewald_analytical", "nbnxm_b200_get_timings", "nbnxm_b200_reset_timings",
+    "nbnxm_b200_copy_fepparams", "nbnxm_b200_init_fep_atomdata", "nbnxm_b200_init_feppairlist",
+    "nbnxm_b200_launch_free_energy_kernel", "nbnxm_b200_get_fep_dvdl",
     "nbnxm_b200_set_timing", "nbnxm_b200_init_reduce_f", "nbnxm_b200_reduce_f", "nbnxm_b200_get_device_buffers", "nbnxm_b200_get_streams",
     "nbnxm_b200_download_pairlist", "nbnxm_b200_set_pair_counting", "nbnxm_b200_get_pair_count",
     "nbnxm_b200_launch_count", "nbnxm_b200_pack_xq", "nbnxm_b200_unpack_xq", "nbnxm_b200_pack_f",
@@ -234,6 +236,39 @@ class NbnxmGpu:
 
     def nbnxm_gpu_x_to_nbat_x(self, d_x_ptr, xReadyOnDevice=None, aloc=LOCAL):
         self._check(self._lib.nbnxm_b200_x_to_nbat_x(self._h, C.c_void_p(d_x_ptr), C.c_void_p(xReadyOnDevice), C.c_int(aloc)))
+
+    # ---- perturbed (free-energy) pair kernels ------------------------------------------------------
+    def copy_gpu_fepparams(self, bFepGpuNonBonded, alphaCoul, alphaVdw, lambdaPower, sigma6WithInvalidSigma, sigma6Minimum,
+                           lambdaCoul, lambdaVdw):
+        """copy_gpu_fepparams (gpu_data_mgmt.h:75)"""
+        self._check(self._lib.nbnxm_b200_copy_fepparams(
+            self._h, C.c_int(int(bFepGpuNonBonded)), C.c_float(alphaCoul), C.c_float(alphaVdw), C.c_int(lambdaPower),
+            C.c_float(sigma6WithInvalidSigma), C.c_float(sigma6Minimum), C.c_float(lambdaCoul), C.c_float(lambdaVdw)))
+
+    def gpu_init_fep_atomdata(self, qA, qB, typeA=None, typeB=None, ljCombA=None, ljCombB=None):
+        """the end-state part of gpu_init_atomdata (q4 / atomTypes4 / ljComb4), nbat order"""
+        a = [_f32(qA), _f32(qB), _i32(typeA), _i32(typeB), _f32(ljCombA), _f32(ljCombB)]
+        self._check(self._lib.nbnxm_b200_init_fep_atomdata(
+            self._h, _ptr(a[0], C.c_float), _ptr(a[1], C.c_float), _ptr(a[2], C.c_int), _ptr(a[3], C.c_int),
+            _ptr(a[4], C.c_float), _ptr(a[5], C.c_float)))
+
+    def gpu_init_feppairlist(self, iinr, jindex, jjnr, shift, excl_fep=None, iloc=LOCAL):
+        """gpu_init_feppairlist (nbnxm_gpu_data_mgmt.cpp:880) with nbat atom indices"""
+        a = [_i32(iinr), _i32(jindex), _i32(jjnr), _i32(shift)]
+        ex = None if excl_fep is None else np.ascontiguousarray(excl_fep, np.uint8)
+        self._check(self._lib.nbnxm_b200_init_feppairlist(
+            self._h, C.c_int(iloc), C.c_int(a[0].shape[0]), _ptr(a[0], C.c_int), _ptr(a[1], C.c_int), _ptr(a[2], C.c_int),
+            _ptr(a[3], C.c_int), _ptr(ex, C.c_ubyte)))
+
+    def gpu_launch_free_energy_kernel(self, stepWork: StepWorkload, iloc=LOCAL):
+        self._check(self._lib.nbnxm_b200_launch_free_energy_kernel(
+            self._h, C.c_int(iloc), C.c_int(int(stepWork.computeEnergy)), C.c_int(int(stepWork.computeVirial))))
+
+    def gpu_get_fep_dvdl(self, clear=False):
+        """(dvdl_lj, dvdl_el) accumulated by the perturbed kernels' energy launches"""
+        a, b = C.c_float(0), C.c_float(0)
+        self._check(self._lib.nbnxm_b200_get_fep_dvdl(self._h, C.byref(a), C.byref(b), C.c_int(int(clear))))
+        return a.value, b.value
 
     def gpu_force_reduction_reinit(self, cell):
         """GpuForceReduction::reinit: cell[natoms] maps atoms to nbat slots (GridSet::cells())."""

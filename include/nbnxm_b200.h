@@ -188,6 +188,26 @@ int nbnxm_b200_set_timing(nbnxm_b200_t* nb, int enable);
  * d_f is float3-packed (natoms x 3), valid after nbnxm_b200_launch_cpyback's reduction stage
  * (use_gpu_f_buffer_ops = 1 keeps it on the device); d_xq is float4. */
 int nbnxm_b200_get_device_buffers(nbnxm_b200_t* nb, float** d_xq, float** d_f, int* natoms);
+/* ---- perturbed (free-energy) pair kernels (gromacs_b200/csrc/nbnxm_fep.cu) ----
+ * copy_gpu_fepparams, gpu_data_mgmt.h:75 (soft-core and coupling parameters; lambda_power 1 or 2) */
+int nbnxm_b200_copy_fepparams(nbnxm_b200_t* nb, int have_fep, float alpha_coul, float alpha_vdw, int lambda_power,
+                              float sigma6_with_invalid_sigma, float sigma6_minimum, float lambda_coul,
+                              float lambda_vdw);
+/* the end-state part of gpu_init_atomdata (NBAtomDataGpu::q4 / atomTypes4 / ljComb4): charges of states A and B and,
+ * as the VdW flavor needs, types or LJ combination parameters (2 per atom) of both states, nbat order, natoms of
+ * nbnxm_b200_init_atomdata */
+int nbnxm_b200_init_fep_atomdata(nbnxm_b200_t* nb, const float* q_a, const float* q_b, const int* type_a,
+                                 const int* type_b, const float* lj_comb_a, const float* lj_comb_b);
+/* gpu_init_feppairlist, nbnxm_gpu_data_mgmt.cpp:880: the perturbed atom-pair list in nbat indices (AtomPairlist:
+ * iinr[num_i], jindex[num_i + 1], jjnr / excl_fep per j-entry, shift[num_i]); excl_fep 0 = excluded pair */
+int nbnxm_b200_init_feppairlist(nbnxm_b200_t* nb, int iloc, int num_i, const int* iinr, const int* jindex,
+                                const int* jjnr, const int* shift, const unsigned char* excl_fep);
+/* gpu_launch_free_energy_kernel, nbnxm_gpu.h:115: adds into the same forces, shift forces and energies as
+ * nbnxm_b200_launch_kernel, on the same stream */
+int nbnxm_b200_launch_free_energy_kernel(nbnxm_b200_t* nb, int iloc, int compute_energy, int compute_virial);
+/* dV/dlambda accumulated by the energy launches (NBAtomDataGpu::dvdlLJ / dvdlElec); synchronises */
+int nbnxm_b200_get_fep_dvdl(nbnxm_b200_t* nb, float* dvdl_lj, float* dvdl_el, int clear);
+
 /* GpuForceReduction::reinit / execute (src/gromacs/mdlib/gpuforcereduction_impl.cpp, reduceKernel in
  * gpuforcereduction_impl_internal.cu:61-118): f_total[a] (+)= f_nbat[cell[a]] (+ rvec_force_to_add[a]) for the atoms
  * [atom_start, atom_start + num_atoms), all arrays but `cell` in device memory, rvecs as packed float3.  cell[natoms]:

@@ -1,0 +1,66 @@
+"""GPU parity of the perturbed (FEP) pair kernel through the C ABI (nbnxm_b200_copy_fepparams / _init_fep_atomdata /
+_init_feppairlist / _launch_free_energy_kernel) against the reference's golden data for its GPU FEP kernel and the
+pinned oracle.  The kernel body is checked on the CPU (tests/test_fep_emu.py); this launch path has not been run on a
+GPU yet, so the test is opt-in (NBNXM_B200_TEST_UNVERIFIED=1) until it has."""
+import os
+
+import numpy as np
+import pytest
+
+from test_oracle_fep import cases, fep_test_system
+
+pytestmark = [pytest.mark.gpu,
+              pytest.mark.skipif(os.environ.get("NBNXM_B200_TEST_UNVERIFIED") != "1",
+                                 reason="the FEP launch path has only been checked through the CPU emulation so far")]
+
+ELEC = {"cut": "Cut", "rf": "RF", "ewald": "EwaldAna"}
+VDW = {"cut": "Cut", "cutgeom": "CutCombGeom", "cutlb": "CutCombLB", "fswitch": "FSwitch", "pswitch": "PSwitch"}
+
+
+def run_gpu(p, x, q_a, q_b, type_a, type_b, lj_a, lj_b, shift_vec, lst):
+    from gromacs_b200 import LOCAL, AtomData, NbnxmGpu, StepWorkload, make_params
+    n = len(x)
+    npad = (n + 7) // 8 * 8
+    xq = np.full((npad, 4), -1.0e6, np.float32)
+    xq[:, 3] = 0
+    xq[:n, :3] = x
+    pad = lambda a, fill, dt: np.concatenate([np.asarray(a, dt), np.full((npad - n,) + np.asarray(a).shape[1:], fill, dt)])
+    params = make_params(ELEC[p.elec] + ("Twin" if p.twin and p.elec == "ewald" else ""), VDW[p.vdw], epsfac=p.epsfac,
+                         rcoulomb=p.rcoulomb_sq ** 0.5, rvdw=p.rvdw_sq ** 0.5, rlist_outer=max(p.rcoulomb_sq, p.rvdw_sq) ** 0.5,
+                         ewald_beta=p.ewald_beta, sh_ewald=p.sh_ewald, k_rf=0.5 * p.two_k_rf, c_rf=p.c_rf,
+                         rvdw_switch=p.rvdw_switch, disp=p.disp, rep=p.rep, sw=p.sw)
+    comb = p.vdw in ("cutgeom", "cutlb")
+    nbat = AtomData(xq=xq, type=pad(type_a, 0, np.int32), lj_comb=pad(lj_a, 0, np.float32) if comb else None,
+                    nbfp=np.ascontiguousarray(p.nbfp, np.float32), nbfp_comb=None, numTypes=p.ntypes,
+                    shift_vec=np.ascontiguousarray(shift_vec, np.float32))
+    nb = NbnxmGpu(params, nbat)
+    try:
+        sw = StepWorkload(computeEnergy=True, computeVirial=True)
+        nb.gpu_init_atomdata(nbat)
+        nb.gpu_upload_shiftvec(nbat)
+        nb.gpu_copy_xq_to_gpu(nbat, LOCAL)
+        nb.copy_gpu_fepparams(True, p.alpha_coul, p.alpha_vdw, p.lambda_power, p.sigma6_with_invalid_sigma, p.sigma6_minimum,
+                              p.lambda_coul, p.lambda_vdw)
+        nb.gpu_init_fep_atomdata(pad(q_a, 0, np.float32), pad(q_b, 0, np.float32), pad(type_a, 0, np.int32), pad(type_b, 0, np.int32),
+                                 pad(lj_a, 0, np.float32) if comb else None, pad(lj_b, 0, np.float32) if comb else None)
+        nb.gpu_init_feppairlist(lst["iinr"], lst["jindex"], lst["jjnr"], lst["shift"], lst["excl_fep"], LOCAL)
+        nb.gpu_clear_outputs(True)
+        nb.gpu_launch_free_energy_kernel(sw, LOCAL)
+        nb.gpu_launch_cpyback(nbat, sw, LOCAL)
+        fshift = np.zeros((45, 3), np.float32)
+        e_lj, e_el = nb.gpu_wait_finish_task(sw, LOCAL, shiftForces=fshift)
+        dvdl_lj, dvdl_el = nb.gpu_get_fep_dvdl()
+    finally:
+        nb.gpu_free()
+    return nbat.f[:n].astype(np.float64), fshift.astype(np.float64), e_lj, e_el, dvdl_lj, dvdl_el
+
+
+@pytest.mark.parametrize("name,ref", cases()[::13], ids=[c[0] for c in cases()[::13]])
+def test_fep_kernel_matches_reference_gpu_refdata(name, ref):
+    p, x, q_a, q_b, type_a, type_b, lj_a, lj_b, lst = fep_test_system(name)
+    f, fshift, e_lj, e_el, dvdl_lj, dvdl_el = run_gpu(p, x, q_a, q_b, type_a, type_b, lj_a, lj_b, np.zeros((45, 3)), lst)
+    scale = np.abs(ref[4:16]).max()
+    assert np.abs(f.reshape(-1) - ref[4:16]).max() <= 5e-6 * scale
+    assert np.abs(fshift[0] - ref[16:19]).max() <= 5e-6 * scale
+    for got, want, floor in ((e_lj, ref[0], 1.0), (e_el, ref[1], 100.0), (dvdl_el, ref[2], 100.0), (dvdl_lj, ref[3], 1.0)):
+        assert abs(got - want) <= 5e-6 * max(abs(want), floor), (name, got, want)
