@@ -85,3 +85,34 @@ def test_sm100a_kernels_keep_their_register_budget():
     for vdw, e in ((1, 0), (1, 1), (3, 1)):
         k = [n for n in packed if "packedILi4ELi%dELb%dEEE" % (vdw, e) in n]
         assert k and packed[k[0]][1] == 0, (vdw, e, k and packed[k[0]])
+
+
+def test_public_headers_are_plain_c_and_link():
+    """include/*.h compile as C99 (the boundary is a C ABI: no C++ types in the signatures) and a C program referencing an
+    entry point of every group links against the library"""
+    import shutil
+    import subprocess
+    import tempfile
+    cc = shutil.which("gcc") or shutil.which("cc")
+    if cc is None:
+        pytest.skip("no C compiler")
+    src = """
+#include "nbnxm_b200.h"
+#include "nbnxm_b200_search.h"
+int main(void)
+{
+    void* fn[] = { (void*)nbnxm_b200_init, (void*)nbnxm_b200_launch_kernel, (void*)nbnxm_b200_launch_kernel_pruneonly,
+                   (void*)nbnxm_b200_pairlist_build, (void*)nbnxm_b200_gpu_search_build, (void*)nbnxm_b200_reduce_f,
+                   (void*)nbnxm_b200_launch_free_energy_kernel, (void*)nbnxm_b200_chunk_plan };
+    return nbnxm_b200_last_error() == 0 || fn[0] == 0;
+}
+"""
+    with tempfile.TemporaryDirectory() as tmp:
+        path = os.path.join(tmp, "abi.c")
+        with open(path, "w") as fh:
+            fh.write(src)
+        subprocess.run([cc, "-std=c99", "-Wall", "-Wextra", "-Werror", "-pedantic", "-Wno-pedantic", "-fsyntax-only",
+                        "-I" + os.path.join(ROOT, "include"), path], check=True)
+        lib_dir = os.path.join(ROOT, "gromacs_b200")
+        subprocess.run([cc, "-std=c99", "-I" + os.path.join(ROOT, "include"), path, "-L" + lib_dir, "-l:libnbnxm_b200.so",
+                        "-Wl,-rpath," + lib_dir, "-o", os.path.join(tmp, "abi")], check=True)
