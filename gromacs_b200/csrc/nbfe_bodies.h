@@ -55,6 +55,7 @@ struct Params
     int   lambdaPower;
     int   calcEnergy, calcFshift;
     int   numTypes;
+    int   calcForces; /* 0: energies / dV/dlambda only (the foreign-lambda evaluation, nbfe_foreign_cuda_kernel.cuh) */
 };
 
 struct Atoms
@@ -381,7 +382,7 @@ NBFE_HD void pair(const Params& p, const Atoms& a, const List& l, int j)
         }
     }
 
-    if (fScalar != 0.0f)
+    if (p.calcForces && fScalar != 0.0f)
     {
         const float fx = rx * fScalar, fy = ry * fScalar, fz = rz * fScalar;
         addFloat(&a.f4[4 * aj], -fx);

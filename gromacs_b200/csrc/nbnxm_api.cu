@@ -301,7 +301,7 @@ int nbnxm_b200_free(nbnxm_b200_t* nb)
     nb->xq.release(); nb->f4.release(); nb->f3.release(); nb->atomType.release(); nb->ljComb.release();
     nb->shiftVec.release(); nb->fshift.release(); nb->energy.release(); nb->nbfp.release();
     nb->nbfpComb.release(); nb->coulombTab.release(); nb->atomIndex.release(); nb->packedConsts.release(); nb->cell.release();
-    nb->fepQ.release(); nb->fepType.release(); nb->fepLjComb.release(); nb->fepDvdl.release();
+    nb->fepQ.release(); nb->fepType.release(); nb->fepLjComb.release(); nb->fepDvdl.release(); nb->fepForeign.release();
     for (nbnxm_b200::FepList& fl : nb->feplist)
     {
         fl.pairEntry.release(); fl.iinr.release(); fl.shift.release(); fl.jjnr.release(); fl.exclFep.release();

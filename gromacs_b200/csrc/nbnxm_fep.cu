@@ -7,7 +7,9 @@
  * The kernel is one thread per pair of the atom-pair list around the host+device body in nbfe_bodies.h, which the CPU
  * tests run pair by pair against the pinned oracle (oracle/nbfe_oracle.py).  It adds into the same force accumulator,
  * shift forces and energies as the cluster-pair kernels, on the list's stream; dV/dlambda has its own accumulator.
- * Foreign-lambda energies (nbfe_foreign_cuda_kernel.cuh) are not implemented.
+ *   nbnxm_b200_launch_foreign_energy_kernel = the foreign-lambda launch of gpu_launch_free_energy_kernel
+ *                                          (kernel nbfe_foreign_cuda_kernel.cuh): the same pair evaluation at every
+ *                                          foreign lambda, energies and dV/dlambda only, one launch per lambda.
  */
 #include "nbfe_bodies.h"
 #include "nbnxm_handle.cuh"
@@ -147,14 +149,11 @@ int nbnxm_b200_init_feppairlist(nbnxm_b200_t* nb, int iloc, int num_i, const int
     return 0;
 }
 
-int nbnxm_b200_launch_free_energy_kernel(nbnxm_b200_t* nb, int iloc, int compute_energy, int compute_virial)
+/* kernel arguments of one launch at the coupling parameters (lambdaCoul, lambdaVdw) */
+static int fepLaunchArgs(nbnxm_b200_t* nb, int iloc, float lambdaCoul, float lambdaVdw, nbfe::Params* pOut, nbfe::Atoms* aOut, nbfe::List* lOut)
 {
-    if (!nb || iloc < 0 || iloc > 1) return fail("nbnxm_b200_launch_free_energy_kernel: bad argument");
-    if (!nb->haveFep) return fail("nbnxm_b200_launch_free_energy_kernel: call nbnxm_b200_copy_fepparams first");
-    if (!nb->haveFepAtomdata) return fail("nbnxm_b200_launch_free_energy_kernel: call nbnxm_b200_init_fep_atomdata first");
     const nbnxm_b200::FepList& fl = nb->feplist[iloc];
-    if (fl.numPairs == 0) return 0;
-    const nbnxm_b200_params_t& s = nb->params;
+    const nbnxm_b200_params_t& s  = nb->params;
     nbfe::Params               p{};
     switch (s.elec_type)
     {
@@ -167,7 +166,7 @@ int nbnxm_b200_launch_free_energy_kernel(nbnxm_b200_t* nb, int iloc, int compute
             p.elec = nbfe::ElecEwald;
             p.twin = 1;
             break;
-        default: return fail("nbnxm_b200_launch_free_energy_kernel: electrostatics type %d has no perturbed kernel", s.elec_type);
+        default: return fail("perturbed kernels: electrostatics type %d has no perturbed kernel", s.elec_type);
     }
     switch (s.vdw_type)
     {
@@ -176,7 +175,7 @@ int nbnxm_b200_launch_free_energy_kernel(nbnxm_b200_t* nb, int iloc, int compute
         case NBNXM_B200_VDW_CUT_COMB_LB: p.vdw = nbfe::VdwCombLB; break;
         case NBNXM_B200_VDW_FSWITCH: p.vdw = nbfe::VdwFSwitch; break;
         case NBNXM_B200_VDW_PSWITCH: p.vdw = nbfe::VdwPSwitch; break;
-        default: return fail("nbnxm_b200_launch_free_energy_kernel: VdW type %d (LJ-PME) has no perturbed kernel", s.vdw_type);
+        default: return fail("perturbed kernels: VdW type %d (LJ-PME) has no perturbed kernel", s.vdw_type);
     }
     p.epsfac = s.epsfac; p.c_rf = s.c_rf; p.two_k_rf = s.two_k_rf; p.beta = s.ewald_beta; p.sh_ewald = s.sh_ewald;
     p.rcoulomb_sq = s.rcoulomb_sq; p.rvdw_sq = s.rvdw_sq; p.rvdw_switch = s.rvdw_switch;
@@ -185,10 +184,9 @@ int nbnxm_b200_launch_free_energy_kernel(nbnxm_b200_t* nb, int iloc, int compute
     p.sw_c3 = s.sw_c3; p.sw_c4 = s.sw_c4; p.sw_c5 = s.sw_c5;
     p.alphaCoul = nb->fepAlphaCoul; p.alphaVdw = nb->fepAlphaVdw;
     p.sigma6WithInvalidSigma = nb->fepSigma6WithInvalidSigma; p.sigma6Minimum = nb->fepSigma6Minimum;
-    p.lambdaCoul = nb->fepLambdaCoul; p.lambdaVdw = nb->fepLambdaVdw; p.lambdaPower = nb->fepLambdaPower;
-    p.calcEnergy = compute_energy != 0;
-    p.calcFshift = compute_virial != 0;
+    p.lambdaCoul = lambdaCoul; p.lambdaVdw = lambdaVdw; p.lambdaPower = nb->fepLambdaPower;
     p.numTypes   = nb->numTypes;
+    p.calcForces = 1;
 
     nbfe::Atoms a{};
     a.xq       = reinterpret_cast<const float*>(nb->xq.p);
@@ -208,10 +206,69 @@ int nbnxm_b200_launch_free_energy_kernel(nbnxm_b200_t* nb, int iloc, int compute
     l.shift     = fl.shift.p;
     l.jjnr      = fl.jjnr.p;
     l.exclFep   = fl.exclFep.p;
+    *pOut = p;
+    *aOut = a;
+    *lOut = l;
+    return 0;
+}
+
+int nbnxm_b200_launch_free_energy_kernel(nbnxm_b200_t* nb, int iloc, int compute_energy, int compute_virial)
+{
+    if (!nb || iloc < 0 || iloc > 1) return fail("nbnxm_b200_launch_free_energy_kernel: bad argument");
+    if (!nb->haveFep) return fail("nbnxm_b200_launch_free_energy_kernel: call nbnxm_b200_copy_fepparams first");
+    if (!nb->haveFepAtomdata) return fail("nbnxm_b200_launch_free_energy_kernel: call nbnxm_b200_init_fep_atomdata first");
+    const nbnxm_b200::FepList& fl = nb->feplist[iloc];
+    if (fl.numPairs == 0) return 0;
+    nbfe::Params p;
+    nbfe::Atoms  a;
+    nbfe::List   l;
+    if (fepLaunchArgs(nb, iloc, nb->fepLambdaCoul, nb->fepLambdaVdw, &p, &a, &l)) return 1;
+    p.calcEnergy = compute_energy != 0;
+    p.calcFshift = compute_virial != 0;
     CU(cudaSetDevice(nb->device));
     nbb::nbfe_pair_kernel<<<(fl.numPairs + 127) / 128, 128, 0, nb->stream[iloc]>>>(p, a, l);
     nb->launches++;
     CU(cudaGetLastError());
+    return 0;
+}
+
+int nbnxm_b200_launch_foreign_energy_kernel(nbnxm_b200_t* nb, int iloc, int nlambda, const float* lambda_coul, const float* lambda_vdw)
+{
+    if (!nb || iloc < 0 || iloc > 1 || nlambda < 1 || !lambda_coul || !lambda_vdw) return fail("nbnxm_b200_launch_foreign_energy_kernel: bad argument");
+    if (!nb->haveFep || !nb->haveFepAtomdata) return fail("nbnxm_b200_launch_foreign_energy_kernel: perturbed kernels are not set up");
+    CU(cudaSetDevice(nb->device));
+    cudaStream_t st = nb->stream[iloc];
+    if (size_t(nlambda) * 4 > nb->fepForeign.alloc) CU(cudaStreamSynchronize(st));
+    CU(nb->fepForeign.reserve(size_t(nlambda) * 4));
+    CU(cudaMemsetAsync(nb->fepForeign.p, 0, sizeof(double) * 4 * nlambda, st));
+    nb->fepNumForeign = nlambda;
+    const nbnxm_b200::FepList& fl = nb->feplist[iloc];
+    if (fl.numPairs == 0) return 0;
+    for (int k = 0; k < nlambda; k++)
+    {
+        nbfe::Params p;
+        nbfe::Atoms  a;
+        nbfe::List   l;
+        if (fepLaunchArgs(nb, iloc, lambda_coul[k], lambda_vdw[k], &p, &a, &l)) return 1;
+        p.calcForces = 0;
+        p.calcFshift = 0;
+        p.calcEnergy = 1;
+        a.energy     = nb->fepForeign.p + 4 * k;     /* E_lj, E_el */
+        a.dvdl       = nb->fepForeign.p + 4 * k + 2; /* dV/dlambda: VdW, Coulomb */
+        nbb::nbfe_pair_kernel<<<(fl.numPairs + 127) / 128, 128, 0, st>>>(p, a, l);
+        nb->launches++;
+    }
+    CU(cudaGetLastError());
+    return 0;
+}
+
+int nbnxm_b200_get_fep_foreign(nbnxm_b200_t* nb, int nlambda, double* out)
+{
+    if (!nb || !out || nlambda < 1 || nlambda > nb->fepNumForeign) return fail("nbnxm_b200_get_fep_foreign: bad argument");
+    CU(cudaSetDevice(nb->device));
+    CU(cudaStreamSynchronize(nb->stream[0]));
+    if (nb->stream[1] != nb->stream[0]) CU(cudaStreamSynchronize(nb->stream[1]));
+    CU(cudaMemcpy(out, nb->fepForeign.p, sizeof(double) * 4 * nlambda, cudaMemcpyDeviceToHost));
     return 0;
 }
 

@@ -173,6 +173,8 @@ struct nbnxm_b200
     nbb::DevBuf<int>    fepType;   /* 2 per atom */
     nbb::DevBuf<float>  fepLjComb; /* 4 per atom */
     nbb::DevBuf<double> fepDvdl;   /* VdW, Coulomb */
+    nbb::DevBuf<double> fepForeign; /* per foreign lambda: E_lj, E_el, dV/dlambda VdW, Coulomb */
+    int                 fepNumForeign = 0;
     bool                haveFep = false, haveFepAtomdata = false;
     float               fepAlphaCoul = 0, fepAlphaVdw = 0, fepSigma6WithInvalidSigma = 0, fepSigma6Minimum = 0;
     float               fepLambdaCoul = 0, fepLambdaVdw = 0;

@@ -34,7 +34,8 @@ EXPORTED_SYMBOLS = [
     "nbnxm_b200_have_short_range_work", "nbnxm_b200_min_ci_balanced",
     "nbnxm_b200_is_kernel_ewald_analytical", "nbnxm_b200_get_timings", "nbnxm_b200_reset_timings",
     "nbnxm_b200_copy_fepparams", "nbnxm_b200_init_fep_atomdata", "nbnxm_b200_init_feppairlist",
-    "nbnxm_b200_launch_free_energy_kernel", "nbnxm_b200_get_fep_dvdl",
+    "nbnxm_b200_launch_free_energy_kernel", "nbnxm_b200_get_fep_dvdl", "nbnxm_b200_launch_foreign_energy_kernel",
+    "nbnxm_b200_get_fep_foreign",
     "nbnxm_b200_set_timing", "nbnxm_b200_init_reduce_f", "nbnxm_b200_reduce_f", "nbnxm_b200_get_device_buffers", "nbnxm_b200_get_streams",
     "nbnxm_b200_download_pairlist", "nbnxm_b200_set_pair_counting", "nbnxm_b200_get_pair_count",
     "nbnxm_b200_launch_count", "nbnxm_b200_pack_xq", "nbnxm_b200_unpack_xq", "nbnxm_b200_pack_f",
@@ -263,6 +264,16 @@ class NbnxmGpu:
     def gpu_launch_free_energy_kernel(self, stepWork: StepWorkload, iloc=LOCAL):
         self._check(self._lib.nbnxm_b200_launch_free_energy_kernel(
             self._h, C.c_int(iloc), C.c_int(int(stepWork.computeEnergy)), C.c_int(int(stepWork.computeVirial))))
+
+    def gpu_launch_foreign_energy_kernel(self, lambda_coul, lambda_vdw, iloc=LOCAL):
+        """energies and dV/dlambda of the perturbed pairs at foreign lambdas; returns float64[nlambda, 4]:
+        E_lj, E_el, dvdl_lj, dvdl_el"""
+        lc, lv = _f32(lambda_coul), _f32(lambda_vdw)
+        self._check(self._lib.nbnxm_b200_launch_foreign_energy_kernel(
+            self._h, C.c_int(iloc), C.c_int(lc.shape[0]), _ptr(lc, C.c_float), _ptr(lv, C.c_float)))
+        out = np.zeros((lc.shape[0], 4), np.float64)
+        self._check(self._lib.nbnxm_b200_get_fep_foreign(self._h, C.c_int(lc.shape[0]), _ptr(out, C.c_double)))
+        return out
 
     def gpu_get_fep_dvdl(self, clear=False):
         """(dvdl_lj, dvdl_el) accumulated by the perturbed kernels' energy launches"""

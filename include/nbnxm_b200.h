@@ -205,6 +205,12 @@ int nbnxm_b200_init_feppairlist(nbnxm_b200_t* nb, int iloc, int num_i, const int
 /* gpu_launch_free_energy_kernel, nbnxm_gpu.h:115: adds into the same forces, shift forces and energies as
  * nbnxm_b200_launch_kernel, on the same stream */
 int nbnxm_b200_launch_free_energy_kernel(nbnxm_b200_t* nb, int iloc, int compute_energy, int compute_virial);
+/* the foreign-lambda launch of gpu_launch_free_energy_kernel (kernel nbfe_foreign_cuda_kernel.cuh): the pairs of the list
+ * evaluated at nlambda other coupling parameters, energies only; results with nbnxm_b200_get_fep_foreign:
+ * out[4 * k + 0..3] = E_lj, E_el, dV/dlambda VdW, dV/dlambda Coulomb at lambda k (synchronises) */
+int nbnxm_b200_launch_foreign_energy_kernel(nbnxm_b200_t* nb, int iloc, int nlambda, const float* lambda_coul,
+                                            const float* lambda_vdw);
+int nbnxm_b200_get_fep_foreign(nbnxm_b200_t* nb, int nlambda, double* out);
 /* dV/dlambda accumulated by the energy launches (NBAtomDataGpu::dvdlLJ / dvdlElec); synchronises */
 int nbnxm_b200_get_fep_dvdl(nbnxm_b200_t* nb, float* dvdl_lj, float* dvdl_el, int clear);
 

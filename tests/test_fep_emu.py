@@ -20,7 +20,7 @@ class EmuParams(C.Structure):
                 + [(n, C.c_float) for n in ("epsfac", "c_rf", "two_k_rf", "beta", "sh_ewald", "rcoulomb_sq", "rvdw_sq", "rvdw_switch",
                                             "disp_c2", "disp_c3", "disp_cpot", "rep_c2", "rep_c3", "rep_cpot", "sw_c3", "sw_c4", "sw_c5",
                                             "alphaCoul", "alphaVdw", "sigma6WithInvalidSigma", "sigma6Minimum", "lambdaCoul", "lambdaVdw")]
-                + [(n, C.c_int) for n in ("lambdaPower", "calcEnergy", "calcFshift", "numTypes")])
+                + [(n, C.c_int) for n in ("lambdaPower", "calcEnergy", "calcFshift", "numTypes", "calcForces")])
 
 
 @pytest.fixture(scope="module")
@@ -42,12 +42,12 @@ def emu_params(p):
     e.alphaCoul, e.alphaVdw = p.alpha_coul, p.alpha_vdw
     e.sigma6WithInvalidSigma, e.sigma6Minimum = p.sigma6_with_invalid_sigma, p.sigma6_minimum
     e.lambdaCoul, e.lambdaVdw, e.lambdaPower = p.lambda_coul, p.lambda_vdw, p.lambda_power
-    e.calcEnergy = e.calcFshift = 1
+    e.calcEnergy = e.calcFshift = e.calcForces = 1
     e.numTypes = p.ntypes
     return e
 
 
-def run_emu(emu, p, x, q_a, q_b, type_a, type_b, lj_a, lj_b, shift_vec, iinr, jindex, jjnr, shift, excl_fep):
+def run_emu(emu, p, x, q_a, q_b, type_a, type_b, lj_a, lj_b, shift_vec, iinr, jindex, jjnr, shift, excl_fep, energies_only=False):
     n = len(x)
     xq = np.zeros((n, 4), np.float32)
     xq[:, :3] = x
@@ -64,6 +64,8 @@ def run_emu(emu, p, x, q_a, q_b, type_a, type_b, lj_a, lj_b, shift_vec, iinr, ji
     ex = np.ascontiguousarray(excl_fep, np.uint8)
     ptr = lambda a, ct: a.ctypes.data_as(C.POINTER(ct))
     e = emu_params(p)
+    if energies_only:
+        e.calcForces = e.calcFshift = 0
     assert emu.fep_emu_run(C.byref(e), ptr(xq, C.c_float), ptr(q, C.c_float), ptr(t, C.c_int), ptr(lj, C.c_float), ptr(nbfp, C.c_float),
                            ptr(sv, C.c_float), C.c_int(len(iinr)), ptr(iinr, C.c_int), ptr(jindex, C.c_int), ptr(jjnr, C.c_int),
                            ptr(shift, C.c_int), ptr(ex, C.c_ubyte), ptr(f4, C.c_float), ptr(fsh, C.c_double), ptr(en, C.c_double),
@@ -166,3 +168,18 @@ def test_body_matches_oracle_on_a_random_perturbed_system(emu, elec, vdw, lam, a
     for g, w in zip(got[2:], want[2:]):
         assert abs(g - w) <= 2e-5 * max(abs(w), 100.0), (g, w)
     assert np.abs(want[1]).max() > 0 and abs(want[4]) > 0
+
+
+def test_energy_only_mode_is_the_foreign_lambda_evaluation(emu):
+    """calcForces = 0 (nbnxm_b200_launch_foreign_energy_kernel, the reference's nbfe_foreign kernel): the energies and
+    dV/dlambda of the full evaluation at that lambda, no forces"""
+    import copy
+    name = [c[0] for c in cases() if "PME" in c[0] and "0_5_0_3_scCoulomb_Yes" in c[0] and "ljrule_None" in c[0]][0]
+    p, x, q_a, q_b, type_a, type_b, lj_a, lj_b, lst = fep_test_system(name)
+    for lam in (0.0, 0.25, 0.8):
+        q = copy.copy(p)
+        q.lambda_coul, q.lambda_vdw = lam, min(1.0, lam + 0.1)
+        full = run_emu(emu, q, x, q_a, q_b, type_a, type_b, lj_a, lj_b, np.zeros((1, 3)), **lst)
+        only = run_emu(emu, q, x, q_a, q_b, type_a, type_b, lj_a, lj_b, np.zeros((1, 3)), energies_only=True, **lst)
+        assert not only[0].any() and not only[1].any() and full[0].any()
+        assert only[2:] == full[2:]

@@ -64,3 +64,40 @@ def test_fep_kernel_matches_reference_gpu_refdata(name, ref):
     assert np.abs(fshift[0] - ref[16:19]).max() <= 5e-6 * scale
     for got, want, floor in ((e_lj, ref[0], 1.0), (e_el, ref[1], 100.0), (dvdl_el, ref[2], 100.0), (dvdl_lj, ref[3], 1.0)):
         assert abs(got - want) <= 5e-6 * max(abs(want), floor), (name, got, want)
+
+
+def test_foreign_lambda_energies_equal_the_full_evaluation_at_those_lambdas():
+    """nbnxm_b200_launch_foreign_energy_kernel against the oracle evaluated at each foreign lambda"""
+    import copy
+    from gromacs_b200 import LOCAL, AtomData, NbnxmGpu, StepWorkload, make_params
+    from oracle.nbfe_oracle import nbfe_forces
+    name = [c[0] for c in cases() if "Reaction_Field" in c[0] and "0_5_0_3_scCoulomb_Yes" in c[0] and "ljrule_None" in c[0]][0]
+    p, x, q_a, q_b, type_a, type_b, lj_a, lj_b, lst = fep_test_system(name)
+    lambdas = np.array([0.0, 0.2, 0.5, 0.9, 1.0], np.float32)
+    want = []
+    for lam in lambdas:
+        q = copy.copy(p)
+        q.lambda_coul = q.lambda_vdw = float(lam)
+        want.append(nbfe_forces(q, x, q_a, q_b, type_a, type_b, lj_a, lj_b, np.zeros((1, 3)), **lst)[2:])
+    want = np.array(want)
+    n, npad = 4, 8
+    xq = np.full((npad, 4), -1.0e6, np.float32)
+    xq[:, 3] = 0
+    xq[:n, :3] = x
+    pad = lambda a, dt: np.concatenate([np.asarray(a, dt), np.zeros(npad - n, dt)])
+    params = make_params("RF", "Cut", epsfac=p.epsfac, rcoulomb=1.0, rvdw=1.0, rlist_outer=1.0, k_rf=0.0, c_rf=p.c_rf, disp=p.disp,
+                         rep=p.rep)
+    nbat = AtomData(xq=xq, type=pad(type_a, np.int32), nbfp=np.ascontiguousarray(p.nbfp, np.float32), numTypes=p.ntypes,
+                    shift_vec=np.zeros((45, 3), np.float32))
+    nb = NbnxmGpu(params, nbat)
+    try:
+        nb.gpu_init_atomdata(nbat)
+        nb.gpu_upload_shiftvec(nbat)
+        nb.gpu_copy_xq_to_gpu(nbat, LOCAL)
+        nb.copy_gpu_fepparams(True, p.alpha_coul, p.alpha_vdw, p.lambda_power, p.sigma6_with_invalid_sigma, p.sigma6_minimum, 0.5, 0.5)
+        nb.gpu_init_fep_atomdata(pad(q_a, np.float32), pad(q_b, np.float32), pad(type_a, np.int32), pad(type_b, np.int32))
+        nb.gpu_init_feppairlist(lst["iinr"], lst["jindex"], lst["jjnr"], lst["shift"], lst["excl_fep"], LOCAL)
+        got = nb.gpu_launch_foreign_energy_kernel(lambdas, lambdas, LOCAL)
+    finally:
+        nb.gpu_free()
+    assert np.abs(got - want).max() <= 5e-6 * np.abs(want).max()
