@@ -267,3 +267,17 @@ def test_gridding_passes_refuse_a_column_taller_than_one_block(emu):
     x = (rng.random((9000, 3)) * box).astype(np.float32)
     nbins = C.c_int()
     assert emu.search_emu_put_atoms_on_grid(_p(box, C.c_float), 1, 1, x.shape[0], _p(x, C.c_float), None, None, C.byref(nbins)) == 1
+
+
+def test_gridding_passes_with_ties_everywhere(emu):
+    """coordinates on a coarse lattice (many equal z, y, x values, atoms on cell boundaries and on the upper box face):
+    the column sort is a total order (ties broken by atom index), so the device order still equals the host order"""
+    from gromacs_b200.pairsearch import Grid
+    rng = np.random.default_rng(3)
+    box = np.array([3.0, 3.0, 3.0], np.float32)
+    x = (rng.integers(0, 13, (4000, 3)) * 0.25).astype(np.float32)          # lattice 0, 0.25, ... 3.0 (= the box face)
+    x[:50] = x[50:100]                                                     # exact duplicates
+    grid = Grid(box, x, nthreads=3)
+    nbins, atom_index, first_bin = emu_grid(emu, box, x, grid.ncx, grid.ncy)
+    assert nbins == grid.nbins and np.array_equal(first_bin, grid.first_bin_of_column)
+    assert np.array_equal(atom_index, grid.atom_index)
