@@ -301,10 +301,7 @@ def main():
 
     nb = NbnxmGpu(wl.params, nbat, device=local_rank)
     min_sci = args.min_sci or nb.gpu_min_ci_balanced()
-    t_search = time.perf_counter()
     plist = wl.pairlist(min_sci=min_sci)
-    host_search_s = time.perf_counter() - t_search
-    list_bytes = int(plist.sci.nbytes + plist.cjPacked.nbytes + plist.excl.nbytes)
     # end-to-end path: coordinates go up and forces come down in chunks of grid columns, pipelined against the kernel
     # (nbnxm_b200_do_force_step_pipelined); the list is the same, with its sci entries grouped by chunk
     from gromacs_b200.pipeline import make_chunk_plan
@@ -395,34 +392,23 @@ def main():
         step(i, True)
     ms_e2e, _, _ = timed_run(True)
 
-    # the search step on either side of the path, untimed above: the same list built on the device from
-    # the resident coordinates (nbnxm_b200_gpu_search_build) next to the host builder + upload it replaces
+    # the search step on either side of the path, untimed above: grid and list built on the device
+    # (nbnxm_b200_gpu_search_put_atoms_on_grid / _build) next to the host gridder / builder + upload they replace.  Run in
+    # a process of its own (profiles/tools/search_profile.py, the script behind the numbers in DESIGN.md 4.4), so that
+    # nothing it does can touch the force-step measurement above.
     try:
-        from gromacs_b200.pairsearch import GpuPairSearch
-        gs = GpuPairSearch(nb, wl.grid, wl.box.excl_index, wl.box.excl_atoms)
-        build_ms = []
-        for _ in range(3):
-            sizes = gs.build(cfg["rlist_outer"], LOCAL, min_sci=min_sci)
-            build_ms.append(gs.build_ms)
-        gs.free()
-        search_rec = {"gpu_list_ms": min(build_ms[1:]), "host_list_s": host_search_s, "host_threads": wl.grid.nthreads,
-                      "list_bytes_not_uploaded": list_bytes,
-                      "same_sizes_as_host_list": list(sizes[:2]) == [int(plist.sci.shape[0]), int(plist.cjPacked.shape[0])]}
-        # ... and the gridding in front of it from atom-order coordinates in device memory
-        # (nbnxm_b200_gpu_search_put_atoms_on_grid); last, because it re-creates the handle's atom data
-        x_dev = torch.from_numpy(np.ascontiguousarray(wl.box.x, np.float32)).cuda()
-        torch.cuda.synchronize()
-        gs = GpuPairSearch(nb)
-        gs.set_atoms(wl.box.q, wl.box.type, nbat.numTypes, nbat.nbfp_comb, wl.box.excl_index, wl.box.excl_atoms)
-        grid_ms = []
-        for _ in range(3):
-            dims = gs.put_atoms_on_grid(wl.box.box, x_dev.data_ptr())
-            grid_ms.append(gs.get_order()[2])
-        gs.free()
-        search_rec.update({"gpu_grid_ms": min(grid_ms[1:]), "host_grid_s": wl.grid_seconds,
-                           "same_grid_as_host": list(dims) == [wl.grid.natoms_nbat, wl.grid.nbins, wl.grid.ncx, wl.grid.ncy]})
+        out = subprocess.run([sys.executable, os.path.join(ROOT, "profiles", "tools", "search_profile.py"), args.workload, "3",
+                              str(min_sci)], capture_output=True, text=True, timeout=600)
+        recs = [json.loads(l) for l in out.stdout.splitlines() if l.startswith("{")]
+        lst = next(r for r in recs if "gpu_build_ms" in r)
+        dev = next(r for r in recs if r.get("device_search_step"))
+        search_rec = {"gpu_grid_ms": min(dev["gpu_grid_ms"][1:]), "gpu_list_ms": min(dev["gpu_list_ms"][1:]),
+                      "host_grid_s": dev["host_grid_s"], "host_list_s": lst["host_build_s"], "host_threads": lst["host_threads"],
+                      "host_list_upload_s": lst["host_list_upload_s"], "list_bytes_not_uploaded": lst["list_bytes"],
+                      "same_grid_order_as_host": dev["same_order_as_host"],
+                      "same_list_sizes_as_host": bool(lst["same_sizes_as_host"] and dev["same_sizes_as_host"])}
     except Exception as e:      # reported, never fatal for the force-step measurement
-        search_rec = {"error": str(e)}
+        search_rec = {"error": str(e)[:200]}
 
     value = wl.useful_pairs / (ms_step * 1e-3) * 1e-9
     line = {
