@@ -105,7 +105,7 @@ def run_reference_cpu(cfg, natoms_k, budget_s=20.0, threads=None):
     for name, exe in exes:
         for kernel in ("4xm", "2xmm"):
             try:
-                probes.append((call(exe, kernel, 5, 2, size=min(natoms_k, 32))["sec_per_iter"], name + " " + kernel, exe, kernel))
+                probes.append((call(exe, kernel, 12, 3, size=min(natoms_k, 32))["sec_per_iter"], name + " " + kernel, exe, kernel))
             except Exception:      # a layout this SIMD width does not have, an instruction set the host lacks after all
                 pass
     if not probes:
