@@ -529,7 +529,8 @@ struct FBinPairMaskWarp
     }
 #endif
 
-    /* the same warp, lane by lane (emulation) */
+#if defined(NBS_EMULATION)
+    /* the same warp, lane by lane: compiled only into tests/kernel_emu (test infrastructure), never into the library */
     void host(int pr) const
     {
         BinPairWarp bw;
@@ -570,6 +571,7 @@ struct FBinPairMaskWarp
             w.binPairMask[pr * c_binCl + lane] = (unsigned char)maskWarpCompose(vote0, vote1, lane);
         }
     }
+#endif
 };
 
 /* ---- pass 4: j-clusters and cjPacked groups per entry ---- */

@@ -9,6 +9,7 @@
 #include <cstdlib>
 #include <cstring>
 
+#define NBS_EMULATION 1
 #include "../../gromacs_b200/csrc/gpusearch_driver.h"
 
 namespace
