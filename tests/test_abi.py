@@ -116,3 +116,13 @@ int main(void)
         lib_dir = os.path.join(ROOT, "gromacs_b200")
         subprocess.run([cc, "-std=c99", "-I" + os.path.join(ROOT, "include"), path, "-L" + lib_dir, "-l:libnbnxm_b200.so",
                         "-Wl,-rpath," + lib_dir, "-o", os.path.join(tmp, "abi")], check=True)
+
+
+def test_shim_compiles_against_the_reference_headers():
+    """the reference-side binding (gromacs_b200/gmx_shim/nbnxm_b200_shim.cpp) is a translation unit of the reference tree:
+    syntax-checked against the reference's own headers where they and a configured build tree exist (dev container)"""
+    import subprocess
+    if not (os.path.isdir("/root/reference/src/gromacs") and os.path.exists("/tmp/gmxbuild/src/include/config.h")):
+        pytest.skip("needs /root/reference and a configured CPU build tree of it")
+    out = subprocess.run([os.path.join(ROOT, "gromacs_b200", "gmx_shim", "check_shim.sh")], capture_output=True, text=True)
+    assert out.returncode == 0 and "ok" in out.stdout, out.stderr[-2000:]
