@@ -41,6 +41,10 @@ struct ThreadList
     std::vector<nbnxm_b200_cj_packed_t> cjp;
     std::vector<nbnxm_b200_excl_t>      excl;
     long long                           nClusterPairs = 0;
+
+    // perturbed atom-pair list split off the list above (nbnxm_b200_pairlist_split_fep)
+    std::vector<int>           fepIinr, fepShift, fepJindex, fepJjnr;
+    std::vector<unsigned char> fepInteracts;
 };
 
 thread_local char g_err[256] = "";
@@ -76,6 +80,10 @@ struct nbnxm_b200_grid
     std::vector<nbnxm_b200_cj_packed_t> cjp;
     std::vector<nbnxm_b200_excl_t>      excl;
     long long                           nClusterPairs = 0;
+
+    // perturbed atom-pair list split off the list above (nbnxm_b200_pairlist_split_fep)
+    std::vector<int>           fepIinr, fepShift, fepJindex, fepJjnr;
+    std::vector<unsigned char> fepInteracts;
 };
 
 extern "C" {
@@ -604,6 +612,129 @@ int nbnxm_b200_pairlist_copy(const nbnxm_b200_grid_t* g, nbnxm_b200_sci_t* sci, 
     if (sci && !g->sci.empty()) std::memcpy(sci, g->sci.data(), sizeof(*sci) * g->sci.size());
     if (cj_packed && !g->cjp.empty()) std::memcpy(cj_packed, g->cjp.data(), sizeof(*cj_packed) * g->cjp.size());
     if (excl && !g->excl.empty()) std::memcpy(excl, g->excl.data(), sizeof(*excl) * g->excl.size());
+    return 0;
+}
+
+/* make_fep_list for the GPU layout (src/gromacs/nbnxm/pairlist.cpp:1414): every atom pair of the list built last in
+ * which at least one atom is perturbed moves to an atom-pair list (i-atom, shift, j-atoms, "interacts" = its exclusion
+ * bit) and its bit in the cluster list is cleared.  The caller masks the perturbed atoms in the cluster kernels' atom
+ * data (charge 0, the non-interacting type: nbnxm_atomdata_mask_fep, atomdata.cpp:1039), so that a cleared bit
+ * contributes nothing there, and evaluates the atom-pair list with the perturbed kernel
+ * (nbnxm_b200_launch_free_energy_kernel).  Self pairs of perturbed atoms are listed as excluded pairs (the kernel
+ * halves their reaction-field / Ewald correction). */
+int nbnxm_b200_pairlist_split_fep(nbnxm_b200_grid_t* g, const unsigned char* perturbed)
+{
+    if (!g || !perturbed) return fail("pairlist_split_fep: null argument");
+    g->fepIinr.clear();
+    g->fepShift.clear();
+    g->fepJjnr.clear();
+    g->fepInteracts.clear();
+    g->fepJindex.assign(1, 0);
+    std::vector<int>           jOfI[c_binAtoms];
+    std::vector<unsigned char> intOfI[c_binAtoms];
+    /* exclusion entry of (group, half), private to the group so that bits can be cleared */
+    auto ownExcl = [&](int group, int half) -> nbnxm_b200_excl_t& {
+        nbnxm_b200_cj_packed_t& e = g->cjp[group];
+        if (e.imei[half].excl_ind == 0)
+        {
+            e.imei[half].excl_ind = int(g->excl.size());
+            g->excl.emplace_back();
+            for (unsigned& w : g->excl.back().pair) w = 0xffffffffu;
+        }
+        return g->excl[e.imei[half].excl_ind];
+    };
+    for (const nbnxm_b200_sci_t& s : g->sci)
+    {
+        const int  bi      = s.sci;
+        const bool central = (s.shift == c_central);
+        bool       any     = false;
+        for (int i = 0; i < c_binAtoms; i++)
+        {
+            jOfI[i].clear();
+            intOfI[i].clear();
+        }
+        for (int group = s.cj_packed_begin; group < s.cj_packed_end; group++)
+        {
+            for (int jm = 0; jm < 4; jm++)
+            {
+                const unsigned imask = g->cjp[group].imei[0].imask;
+                if (((imask >> (jm * 8)) & 0xffu) == 0) continue;
+                const int gcj = g->cjp[group].cj[jm];
+                for (int ci = 0; ci < c_binCl; ci++)
+                {
+                    const unsigned bit = 1u << (jm * 8 + ci);
+                    if (!(imask & bit)) continue;
+                    const int  gci      = bi * c_binCl + ci;
+                    const bool diagonal = central && gci == gcj;
+                    for (int ia = 0; ia < c_cl; ia++)
+                    {
+                        const int islot = gci * c_cl + ia;
+                        const int ai    = g->atomIndex[islot];
+                        if (ai < 0) continue;
+                        for (int ja = 0; ja < c_cl; ja++)
+                        {
+                            const int jslot = gcj * c_cl + ja;
+                            const int aj    = g->atomIndex[jslot];
+                            if (aj < 0 || !(perturbed[ai] || perturbed[aj])) continue;
+                            if (diagonal && ja < ia) continue; /* the mirrored pair owns it */
+                            const int half = ja / 4;
+                            const int word = (ja & 3) * c_cl + ia;
+                            const int iloc = ci * c_cl + ia;
+                            if (diagonal && ja == ia)
+                            {
+                                /* self pair: excluded by construction, listed for its exclusion correction */
+                                jOfI[iloc].push_back(jslot);
+                                intOfI[iloc].push_back(0);
+                                any = true;
+                                continue;
+                            }
+                            const int ex = g->cjp[group].imei[half].excl_ind;
+                            const bool interacts = (g->excl[ex].pair[word] & bit) != 0;
+                            jOfI[iloc].push_back(jslot);
+                            intOfI[iloc].push_back(interacts ? 1 : 0);
+                            any = true;
+                            if (interacts)
+                            {
+                                ownExcl(group, half).pair[word] &= ~bit;
+                            }
+                        }
+                    }
+                }
+            }
+        }
+        if (!any) continue;
+        for (int i = 0; i < c_binAtoms; i++)
+        {
+            if (jOfI[i].empty()) continue;
+            g->fepIinr.push_back(bi * c_binAtoms + i);
+            g->fepShift.push_back(s.shift);
+            g->fepJjnr.insert(g->fepJjnr.end(), jOfI[i].begin(), jOfI[i].end());
+            g->fepInteracts.insert(g->fepInteracts.end(), intOfI[i].begin(), intOfI[i].end());
+            g->fepJindex.push_back(int(g->fepJjnr.size()));
+        }
+    }
+    return 0;
+}
+
+int nbnxm_b200_pairlist_fep_sizes(const nbnxm_b200_grid_t* g, int* num_i, int* num_j)
+{
+    if (!g) return fail("null grid");
+    if (num_i) *num_i = int(g->fepIinr.size());
+    if (num_j) *num_j = int(g->fepJjnr.size());
+    return 0;
+}
+
+int nbnxm_b200_pairlist_fep_copy(const nbnxm_b200_grid_t* g, int* iinr, int* jindex, int* jjnr, int* shift, unsigned char* interacts)
+{
+    if (!g) return fail("null grid");
+    auto cp = [](auto* dst, const auto& v) {
+        if (dst && !v.empty()) std::memcpy(dst, v.data(), sizeof(v[0]) * v.size());
+    };
+    cp(iinr, g->fepIinr);
+    cp(jindex, g->fepJindex);
+    cp(jjnr, g->fepJjnr);
+    cp(shift, g->fepShift);
+    cp(interacts, g->fepInteracts);
     return 0;
 }
 

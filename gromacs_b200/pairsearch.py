@@ -10,6 +10,7 @@ import numpy as np
 from .nbnxm import AtomData, NbnxmError, PairlistGpu, load_library
 
 SEARCH_SYMBOLS = [
+    "nbnxm_b200_pairlist_split_fep", "nbnxm_b200_pairlist_fep_sizes", "nbnxm_b200_pairlist_fep_copy",
     "nbnxm_b200_grid_dims", "nbnxm_b200_grid_box", "nbnxm_b200_slab_bin_ranges", "nbnxm_b200_pairlist_reindex", "nbnxm_b200_chunk_plan",
     "nbnxm_b200_grid_create", "nbnxm_b200_grid_create_slabs", "nbnxm_b200_grid_free", "nbnxm_b200_grid_info", "nbnxm_b200_grid_get_order",
     "nbnxm_b200_grid_fill_atomdata", "nbnxm_b200_pairlist_build", "nbnxm_b200_pairlist_sizes",
@@ -88,6 +89,29 @@ class Grid:
         pl = PairlistGpu(sci=sci, cjPacked=cjp, excl=excl, na_ci=8, rlist=rlist)
         pl.nci_tot = ncp.value
         return pl
+
+
+def split_fep_pairlist(grid: Grid, perturbed):
+    """make_fep_list for the list `grid.pairlist()` built last: returns (cluster list with the perturbed pairs' bits
+    cleared, dict(iinr, jindex, jjnr, shift, excl_fep) in nbat indices for gpu_init_feppairlist)."""
+    lib = load_library()
+    pert = np.ascontiguousarray(perturbed, np.uint8)
+    if lib.nbnxm_b200_pairlist_split_fep(grid._g, _p(pert, C.c_ubyte)):
+        raise NbnxmError("nbnxm_b200_pairlist_split_fep failed")
+    ni, nj = C.c_int(), C.c_int()
+    lib.nbnxm_b200_pairlist_fep_sizes(grid._g, C.byref(ni), C.byref(nj))
+    iinr, jindex = np.zeros(ni.value, np.int32), np.zeros(ni.value + 1, np.int32)
+    jjnr, shift, inter = np.zeros(nj.value, np.int32), np.zeros(ni.value, np.int32), np.zeros(nj.value, np.uint8)
+    lib.nbnxm_b200_pairlist_fep_copy(grid._g, _p(iinr, C.c_int), _p(jindex, C.c_int), _p(jjnr, C.c_int), _p(shift, C.c_int),
+                                     _p(inter, C.c_ubyte))
+    nsci, ncj, nex, ncp = C.c_int(), C.c_int(), C.c_int(), C.c_longlong()
+    lib.nbnxm_b200_pairlist_sizes(grid._g, C.byref(nsci), C.byref(ncj), C.byref(nex), C.byref(ncp))
+    sci = np.zeros((nsci.value, 4), np.int32)
+    cjp = np.zeros((ncj.value, 8), np.uint32)
+    excl = np.zeros((nex.value, 32), np.uint32)
+    lib.nbnxm_b200_pairlist_copy(grid._g, _p(sci, C.c_int), _p(cjp, C.c_uint32), _p(excl, C.c_uint32))
+    return (PairlistGpu(sci=sci, cjPacked=cjp, excl=excl, na_ci=8),
+            dict(iinr=iinr, jindex=jindex, jjnr=jjnr, shift=shift, excl_fep=inter))
 
 
 class GpuPairSearch:

@@ -65,6 +65,17 @@ int nbnxm_b200_pairlist_sizes(const nbnxm_b200_grid_t* grid, int* nsci, int* ncj
 int nbnxm_b200_pairlist_copy(const nbnxm_b200_grid_t* grid, nbnxm_b200_sci_t* sci, nbnxm_b200_cj_packed_t* cj_packed,
                              nbnxm_b200_excl_t* excl);
 
+/* make_fep_list for the GPU layout (pairlist.cpp:1414): splits every atom pair with a perturbed atom off the list built
+ * last into an atom-pair list in nbat indices (the arguments of nbnxm_b200_init_feppairlist: iinr[num_i], jindex[num_i+1],
+ * jjnr / interacts[num_j], shift[num_i]) and clears its bit in the cluster list (fetch the modified list with
+ * nbnxm_b200_pairlist_sizes / _copy afterwards).  perturbed[natoms]: 1 for atoms whose charge or type differs between
+ * the end states.  The cluster kernels' atom data must mask these atoms (charge 0, type ntypes - 1:
+ * nbnxm_atomdata_mask_fep, atomdata.cpp:1039). */
+int nbnxm_b200_pairlist_split_fep(nbnxm_b200_grid_t* grid, const unsigned char* perturbed);
+int nbnxm_b200_pairlist_fep_sizes(const nbnxm_b200_grid_t* grid, int* num_i, int* num_j);
+int nbnxm_b200_pairlist_fep_copy(const nbnxm_b200_grid_t* grid, int* iinr, int* jindex, int* jjnr, int* shift,
+                                 unsigned char* interacts);
+
 /* ---- host-side planning (gromacs_b200/csrc/hostplan.cpp) ----
  * x-slab decomposition over nslabs GPUs, one process per GPU: bins of slab r (home), of its one-sided halo (the first
  * columns of slab (r+1) % nslabs within rlist, plus one column of slack) and the x shift of the home x halo pairs
