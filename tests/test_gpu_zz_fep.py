@@ -101,3 +101,62 @@ def test_foreign_lambda_energies_equal_the_full_evaluation_at_those_lambdas():
     finally:
         nb.gpu_free()
     assert np.abs(got - want).max() <= 5e-6 * np.abs(want).max()
+
+
+def test_cluster_and_perturbed_kernels_together_equal_brute_force(oracle):
+    """the whole perturbed path on the GPU: host builder + split, masked cluster kernel + perturbed kernel adding into the
+    same forces / energies, against brute force of the A-state system at lambda = 0 and of the B-state at lambda = 1"""
+    from gromacs_b200 import LOCAL, NbnxmGpu, StepWorkload
+    from gromacs_b200.pairsearch import Grid, split_fep_pairlist
+    from util import load_golden, oracle_params, product_params, relrms
+    d = load_golden("bench1_ewald_cutnone")
+    x, box = d["sys_x"], d["sys_box"]
+    n = x.shape[0]
+    nt = int(d["nbat_ntypes"][0])
+    q_a, t_a = d["sys_q"].astype(np.float32), d["sys_type"].astype(np.int32)
+    rng = np.random.default_rng(4)
+    perturbed = np.zeros(n, np.uint8)
+    q_b, t_b = q_a.copy(), t_a.copy()
+    for k, m in enumerate(rng.choice(n // 3, size=45, replace=False)):
+        atoms = np.arange(3 * m, 3 * m + 3)
+        perturbed[atoms] = 1
+        q_b[atoms] *= (0.0 if k % 3 == 0 else 0.5)
+        if k % 2 == 0:
+            t_b[atoms] = nt - 1
+    grid = Grid(box, x, nthreads=2)
+    ai = grid.atom_index
+    real = ai >= 0
+    nbat = grid.atomdata(x, np.where(perturbed, 0.0, q_a), np.where(perturbed, nt - 1, t_a), d["nbat_nbfp"], nt,
+                         nbfp_comb=d["nbat_nbfp_comb"])
+    grid.pairlist(1.0, d["sys_excl_index"], d["sys_excl_atoms"], min_sci=200)
+    plist, fep = split_fep_pairlist(grid, perturbed)
+
+    def nbat_order(a, fill):
+        out = np.full(ai.shape[0], fill, np.asarray(a).dtype)
+        out[real] = np.asarray(a)[ai[real]]
+        return out
+    p = oracle_params(oracle, d)
+    nb = NbnxmGpu(product_params(d, vdw="Cut"), nbat)
+    try:
+        sw = StepWorkload(computeEnergy=True, computeVirial=True)
+        nb.gpu_init_atomdata(nbat)
+        nb.gpu_init_pairlist(plist, LOCAL)
+        nb.setupGpuShortRangeWork(LOCAL)
+        nb.gpu_upload_shiftvec(nbat)
+        nb.gpu_copy_xq_to_gpu(nbat, LOCAL)
+        nb.gpu_init_fep_atomdata(nbat_order(q_a, 0.0), nbat_order(q_b, 0.0), nbat_order(t_a, nt - 1), nbat_order(t_b, nt - 1))
+        nb.gpu_init_feppairlist(fep["iinr"], fep["jindex"], fep["jjnr"], fep["shift"], fep["excl_fep"], LOCAL)
+        for lam, q_end, t_end in ((0.0, q_a, t_a), (1.0, q_b, t_b)):
+            nb.copy_gpu_fepparams(True, 0.0, 0.0, 1, 0.3 ** 6, 0.3 ** 6, lam, lam)
+            nb.gpu_clear_outputs(True)
+            nb.gpu_launch_kernel(sw, LOCAL)
+            nb.gpu_launch_free_energy_kernel(sw, LOCAL)
+            nb.gpu_launch_cpyback(nbat, sw, LOCAL)
+            e_lj, e_el = nb.gpu_wait_finish_task(sw, LOCAL)
+            f = oracle.nbat_to_atom_order(nbat.f.astype(np.float64), ai, n)
+            fb, eb = oracle.brute_force(p, x, q_end, t_end, d["nbat_nbfp"], d["nbat_nbfp_comb"], box, d["sys_excl_index"],
+                                        d["sys_excl_atoms"])
+            assert relrms(f, fb) <= 5e-6, (lam, relrms(f, fb))
+            assert abs(e_lj - eb[0]) <= 2e-6 * abs(eb[0]) + 2e-6 and abs(e_el - eb[1]) <= 2e-6 * abs(eb[1]), (lam, e_lj, e_el, eb)
+    finally:
+        nb.gpu_free()
