@@ -269,9 +269,10 @@ int nbnxm_b200_gpu_search_create(nbnxm_b200_gpu_search_t** out, nbnxm_b200_t* nb
     s->be.h_value            = static_cast<int*>(pinned);
     s->evStart               = ev[0];
     s->evStop                = ev[1];
-    /* opt-in until it has been run on a GPU (checked through the emulation only) */
+    /* the mask pass runs one warp per bin pair (2.0 ms against 3.1 ms for the 1.5 M-atom box, profiles/r02a_*);
+     * NBNXM_B200_SEARCH_COOP=0 selects the one-thread-per-j-cluster form for A/B runs */
     const char* coop        = getenv("NBNXM_B200_SEARCH_COOP");
-    s->st.cooperativeMasks = coop != nullptr && coop[0] == '1';
+    s->st.cooperativeMasks = !(coop != nullptr && coop[0] == '0');
     *out = s;
     return 0;
 }

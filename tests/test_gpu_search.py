@@ -283,11 +283,8 @@ def test_search_step_entirely_on_the_device_1536k():
                        "host_grid_s": host_grid_s, "host_list_s": host_list_s, "host_threads": wl.grid.nthreads}, fh)
 
 
-@pytest.mark.skipif(os.environ.get("NBNXM_B200_TEST_UNVERIFIED") != "1",
-                    reason="the warp-cooperative mask pass has only been run through the CPU emulation so far (DESIGN.md 4.4); "
-                           "set NBNXM_B200_TEST_UNVERIFIED=1 to run it on the GPU")
 def test_cooperative_mask_pass_gives_the_same_list(monkeypatch):
-    """NBNXM_B200_SEARCH_COOP=1: pass 3 as one warp per bin pair; same list, and the build time next to the default"""
+    """pass 3 as one warp per bin pair (the default) and as one thread per j-cluster (NBNXM_B200_SEARCH_COOP=0): same list; the build times go to gpurun_out"""
     from gromacs_b200 import LOCAL, NbnxmGpu
     from gromacs_b200.pairsearch import GpuPairSearch
     from gromacs_b200.workload import make_workload

@@ -1,17 +1,12 @@
 """GPU parity of the perturbed (FEP) pair kernel through the C ABI (nbnxm_b200_copy_fepparams / _init_fep_atomdata /
 _init_feppairlist / _launch_free_energy_kernel) against the reference's golden data for its GPU FEP kernel and the
-pinned oracle.  The kernel body is checked on the CPU (tests/test_fep_emu.py); this launch path has not been run on a
-GPU yet, so the test is opt-in (NBNXM_B200_TEST_UNVERIFIED=1) until it has."""
-import os
-
+pinned oracle.  The kernel body is also checked on the CPU (tests/test_fep_emu.py)."""
 import numpy as np
 import pytest
 
 from test_oracle_fep import cases, fep_test_system
 
-pytestmark = [pytest.mark.gpu,
-              pytest.mark.skipif(os.environ.get("NBNXM_B200_TEST_UNVERIFIED") != "1",
-                                 reason="the FEP launch path has only been checked through the CPU emulation so far")]
+pytestmark = pytest.mark.gpu
 
 ELEC = {"cut": "Cut", "rf": "RF", "ewald": "EwaldAna"}
 VDW = {"cut": "Cut", "cutgeom": "CutCombGeom", "cutlb": "CutCombLB", "fswitch": "FSwitch", "pswitch": "PSwitch"}
