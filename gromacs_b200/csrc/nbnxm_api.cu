@@ -22,7 +22,7 @@ void launch_prune(bool fresh, const AtomDataDev& ad, const ParamsDev& p, const P
 void launch_sci_sort(const PairlistDev& pl, cudaStream_t stream);
 void launch_count_pairs(const PairlistDev& pl, cudaStream_t stream);
 void launch_x_to_nbat_x(float4* xq, const float* x, const int* atomIndex, int first, int n, cudaStream_t s);
-void launch_f4_to_f3(const float4* f4, float* f3, int first, int n, cudaStream_t s);
+void launch_f4_to_f3(const float4* f4, float* f3, int first, int n, cudaStream_t s, bool accumulate = false);
 void launch_reduce_f(const float4* f4, const float* rvecToAdd, float* fTotal, const int* cell, int atomStart, int n, bool accumulate,
                      cudaStream_t s);
 void launch_pack_xq(const float4* xq, const int* index, int n, const float* shift, float4* out, cudaStream_t s);
@@ -320,6 +320,8 @@ int nbnxm_b200_free(nbnxm_b200_t* nb)
     if (nb->d2hStream) cudaStreamDestroy(nb->d2hStream);
     if (nb->pipeKernelStream) cudaStreamDestroy(nb->pipeKernelStream);
     if (nb->h_fshift) cudaFreeHost(nb->h_fshift);
+    if (nb->h_fshiftShared) cudaFreeHost(nb->h_fshiftShared);
+    nb->fshiftShared.release();
     if (nb->h_energy) cudaFreeHost(nb->h_energy);
     if (nb->nonlocalDone) cudaEventDestroy(nb->nonlocalDone);
     if (nb->localH2DDone) cudaEventDestroy(nb->localH2DDone);
@@ -488,7 +490,7 @@ int nbnxm_b200_copy_xq_to_gpu(nbnxm_b200_t* nb, int aloc, const float* xq)
     if (atomRange(nb, aloc, &begin, &count)) return 1;
     cudaStream_t st = nb->stream[aloc];
     /* skip the non-local copy if there is no non-local work (nbnxm_gpu_data_mgmt.cpp:1498-1516) */
-    if (aloc == 1 && !nb->haveWork[1] && nb->plist[1].numSci == 0)
+    if (aloc == 1 && !nb->haveWork[1] && nb->plist[1].numSci == 0 && nb->feplist[1].numPairs == 0)
     {
         nb->plist[1].haveFreshList = false;
         return 0;
@@ -826,7 +828,7 @@ int nbnxm_b200_do_force_step_pipelined(nbnxm_b200_t* nb, int step, const nbnxm_b
         const int first = chunk_first_atom[c], count = chunk_first_atom[c + 1] - first;
         if (count > 0)
         {
-            launch_f4_to_f3(nb->f4.p, nb->f3.p, first, count, nb->d2hStream);
+            launch_f4_to_f3(nb->f4.p, nb->f3.p, first, count, nb->d2hStream, nb->sharedOutputs);
             nb->launches++;
             CU(cudaMemcpyAsync(f_host + 3 * size_t(first), nb->f3.p + 3 * size_t(first), sizeof(float) * 3 * count,
                                cudaMemcpyDeviceToHost, nb->d2hStream));
@@ -854,7 +856,7 @@ int nbnxm_b200_launch_cpyback(nbnxm_b200_t* nb, int aloc, float* f, int compute_
     const int    iloc = aloc;
     cudaStream_t st   = nb->stream[iloc];
     /* don't launch non-local copy-back if there was no non-local work to do */
-    if (aloc == 1 && !nb->haveWork[1] && nb->plist[1].numSci == 0)
+    if (aloc == 1 && !nb->haveWork[1] && nb->plist[1].numSci == 0 && nb->feplist[1].numPairs == 0)
     {
         return 0;
     }
@@ -862,12 +864,12 @@ int nbnxm_b200_launch_cpyback(nbnxm_b200_t* nb, int aloc, float* f, int compute_
     if (atomRange(nb, aloc, &begin, &count)) return 1;
     /* the non-local kernel also writes forces of local atoms: the local copy-back has to wait for it
      * (nbnxm_gpu_data_mgmt.cpp:1313-1346) */
-    if (aloc == 0 && nb->localAndNonlocal && (nb->haveWork[1] || nb->plist[1].numSci > 0))
+    if (aloc == 0 && nb->localAndNonlocal && (nb->haveWork[1] || nb->plist[1].numSci > 0 || nb->feplist[1].numPairs > 0))
     {
         CU(cudaStreamWaitEvent(st, nb->nonlocalDone, 0));
     }
     beginRegion(nb, 7, st);
-    launch_f4_to_f3(nb->f4.p, nb->f3.p, begin, count, st);
+    launch_f4_to_f3(nb->f4.p, nb->f3.p, begin, count, st, nb->sharedOutputs);
     nb->launches++;
     if (!use_gpu_f_buffer_ops && count > 0)
     {
@@ -882,6 +884,10 @@ int nbnxm_b200_launch_cpyback(nbnxm_b200_t* nb, int aloc, float* f, int compute_
         if (compute_virial)
         {
             CU(cudaMemcpyAsync(nb->h_fshift, nb->fshift.p, sizeof(double) * 3 * c_numShiftVectors, cudaMemcpyDeviceToHost, st));
+            if (nb->sharedOutputs)
+            {
+                CU(cudaMemcpyAsync(nb->h_fshiftShared, nb->fshiftShared.p, sizeof(float) * 3 * c_numShiftVectors, cudaMemcpyDeviceToHost, st));
+            }
         }
         if (compute_energy)
         {
@@ -906,6 +912,10 @@ static int finishTask(nbnxm_b200_t* nb, int aloc, int compute_energy, int comput
         if (compute_virial && fshift)
         {
             for (int i = 0; i < 3 * c_numShiftVectors; i++) fshift[i] += static_cast<float>(nb->h_fshift[i]);
+            if (nb->sharedOutputs)
+            {
+                for (int i = 0; i < 3 * c_numShiftVectors; i++) fshift[i] += nb->h_fshiftShared[i];
+            }
         }
     }
     PairList& pl       = nb->plist[aloc];
@@ -947,6 +957,11 @@ int nbnxm_b200_clear_outputs(nbnxm_b200_t* nb, int compute_virial)
     CU(cudaSetDevice(nb->device));
     cudaStream_t st = nb->stream[0];
     if (nb->natoms > 0) CU(cudaMemsetAsync(nb->f4.p, 0, sizeof(float4) * nb->natoms, st));
+    if (nb->sharedOutputs)
+    {
+        if (nb->natoms > 0) CU(cudaMemsetAsync(nb->f3.p, 0, sizeof(float) * 3 * size_t(nb->natoms), st));
+        if (compute_virial) CU(cudaMemsetAsync(nb->fshiftShared.p, 0, sizeof(float) * 3 * c_numShiftVectors, st));
+    }
     if (compute_virial)
     {
         CU(cudaMemsetAsync(nb->fshift.p, 0, sizeof(double) * 3 * c_numShiftVectors, st));
@@ -960,7 +975,7 @@ int nbnxm_b200_clear_outputs(nbnxm_b200_t* nb, int compute_virial)
 int nbnxm_b200_setup_short_range_work(nbnxm_b200_t* nb, int iloc, int have_bonded_work)
 {
     if (!nb || iloc < 0 || iloc > 1) return fail("bad argument");
-    nb->haveWork[iloc] = (nb->plist[iloc].numSci > 0) || have_bonded_work;
+    nb->haveWork[iloc] = (nb->plist[iloc].numSci > 0) || (nb->feplist[iloc].numPairs > 0) || have_bonded_work;
     return 0;
 }
 int nbnxm_b200_have_short_range_work(const nbnxm_b200_t* nb, int iloc) { return (nb && iloc >= 0 && iloc <= 1) ? nb->haveWork[iloc] : 0; }
@@ -1006,6 +1021,22 @@ int nbnxm_b200_get_device_buffers(nbnxm_b200_t* nb, float** d_xq, float** d_f, i
     if (d_xq) *d_xq = reinterpret_cast<float*>(nb->xq.p);
     if (d_f) *d_f = nb->f3.p;
     if (natoms) *natoms = nb->natoms;
+    return 0;
+}
+int nbnxm_b200_get_shared_outputs(nbnxm_b200_t* nb, float** d_f, float** d_fshift)
+{
+    if (!nb) return fail("null handle");
+    CU(cudaSetDevice(nb->device));
+    if (!nb->sharedOutputs)
+    {
+        CU(nb->fshiftShared.reserve(3 * c_numShiftVectors));
+        CU(cudaMallocHost(&nb->h_fshiftShared, sizeof(float) * 3 * c_numShiftVectors));
+        CU(cudaMemsetAsync(nb->fshiftShared.p, 0, sizeof(float) * 3 * c_numShiftVectors, nb->stream[0]));
+        if (nb->natoms > 0) CU(cudaMemsetAsync(nb->f3.p, 0, sizeof(float) * 3 * size_t(nb->natoms), nb->stream[0]));
+        nb->sharedOutputs = true;
+    }
+    if (d_f) *d_f = nb->f3.p;
+    if (d_fshift) *d_fshift = nb->fshiftShared.p;
     return 0;
 }
 int nbnxm_b200_get_streams(nbnxm_b200_t* nb, void** local_stream, void** nonlocal_stream)

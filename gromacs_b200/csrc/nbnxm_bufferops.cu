@@ -35,15 +35,27 @@ __global__ void __launch_bounds__(256)
     }
 }
 
+template<bool ACCUMULATE>
 __global__ void __launch_bounds__(256) f4_to_f3_kernel(const float4* __restrict__ f4, float* __restrict__ f3, int first, int n)
 {
     const int i = blockIdx.x * blockDim.x + threadIdx.x;
     if (i < n)
     {
-        const float4 v       = f4[first + i];
-        f3[3 * (first + i)]     = v.x;
-        f3[3 * (first + i) + 1] = v.y;
-        f3[3 * (first + i) + 2] = v.z;
+        const float4 v = f4[first + i];
+        float*       o = f3 + 3 * size_t(first + i);
+        if (ACCUMULATE)
+        {
+            /* forces other device code (GPU listed forces) left in f3 since the clear stay */
+            o[0] += v.x;
+            o[1] += v.y;
+            o[2] += v.z;
+        }
+        else
+        {
+            o[0] = v.x;
+            o[1] = v.y;
+            o[2] = v.z;
+        }
     }
 }
 
@@ -134,9 +146,13 @@ void launch_x_to_nbat_x(float4* xq, const float* x, const int* atomIndex, int fi
 {
     if (n > 0) x_to_nbat_x_kernel<<<nblk(n), 256, 0, s>>>(xq, x, atomIndex, first, n);
 }
-void launch_f4_to_f3(const float4* f4, float* f3, int first, int n, cudaStream_t s)
+void launch_f4_to_f3(const float4* f4, float* f3, int first, int n, cudaStream_t s, bool accumulate)
 {
-    if (n > 0) f4_to_f3_kernel<<<nblk(n), 256, 0, s>>>(f4, f3, first, n);
+    if (n <= 0) return;
+    if (accumulate)
+        f4_to_f3_kernel<true><<<nblk(n), 256, 0, s>>>(f4, f3, first, n);
+    else
+        f4_to_f3_kernel<false><<<nblk(n), 256, 0, s>>>(f4, f3, first, n);
 }
 void launch_pack_xq(const float4* xq, const int* index, int n, const float* shift, float4* out, cudaStream_t s)
 {

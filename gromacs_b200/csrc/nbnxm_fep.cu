@@ -111,6 +111,8 @@ int nbnxm_b200_init_feppairlist(nbnxm_b200_t* nb, int iloc, int num_i, const int
     nbnxm_b200::FepList& fl = nb->feplist[iloc];
     cudaStream_t         st = nb->stream[iloc];
     CU(cudaStreamSynchronize(st));
+    /* jindex is an offset table starting at 0 (AtomPairlist::flatJList); anything else would leave j-entries unchecked */
+    if (num_i > 0 && jindex[0] != 0) return fail("nbnxm_b200_init_feppairlist: jindex[0] is %d, expected 0", jindex[0]);
     const int numPairs = num_i > 0 ? jindex[num_i] : 0;
     for (int n = 0; n < num_i; n++)
     {

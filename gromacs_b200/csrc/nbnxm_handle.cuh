@@ -126,6 +126,11 @@ struct nbnxm_b200
     nbb::DevBuf<float2> ljComb;
     nbb::DevBuf<float>  shiftVec;
     nbb::DevBuf<double> fshift, energy;
+    /* gpuGetNBAtomData (nbnxm_gpu_data_mgmt.cpp:1823): f3 and a float3[45] shift-force buffer other device code (GPU listed
+     * forces) adds into; once handed out, clear_outputs zeroes them and the copy-back stage adds the kernels' forces on top */
+    bool               sharedOutputs = false;
+    nbb::DevBuf<float> fshiftShared;
+    float*             h_fshiftShared = nullptr;
     nbb::DevBuf<float2> nbfp, nbfpComb;
     nbb::DevBuf<float>  coulombTab;
     nbb::DevBuf<float>  packedConsts; /* ParamsDev::packedConsts */

@@ -23,6 +23,7 @@
 #include "gromacs/gpu_utils/gpu_utils.h"
 #include "gromacs/gpu_utils/gpueventsynchronizer.h"
 #include "gromacs/hardware/device_information.h"
+#include "gromacs/listed_forces/listed_forces_gpu.h"
 #include "gromacs/mdtypes/enerdata.h"
 #include "gromacs/mdtypes/interaction_const.h"
 #include "gromacs/mdtypes/locality.h"
@@ -30,6 +31,7 @@
 #include "gromacs/nbnxm/atomdata.h"
 #include "gromacs/nbnxm/atompairlist.h"
 #include "gromacs/nbnxm/gpu_data_mgmt.h"
+#include "gromacs/nbnxm/gpu_types_common.h"
 #include "gromacs/nbnxm/gridset.h"
 #include "gromacs/nbnxm/nbnxm.h"
 #include "gromacs/nbnxm/nbnxm_enums.h"
@@ -64,6 +66,12 @@ struct NbnxmGpu
     nbnxm_b200_gpu_search_t* search = nullptr;
     /* perturbed (FEP) pair kernels in use (copy_gpu_fepparams) */
     bool haveFep = false;
+    /* coupling parameters of the foreign-lambda energies: entry 0 is the current lambda, then all_lambda
+     * (nbfe_foreign_cuda_kernel.cuh:218-229) */
+    std::vector<float> foreignLambdaCoul, foreignLambdaVdw;
+    bool               foreignLaunched = false;
+    /* what gpuGetNBAtomData hands to the GPU listed forces: views of the library's buffers */
+    NBAtomDataGpu atdat{};
 };
 
 namespace
@@ -171,11 +179,14 @@ NbnxmGpu* gpu_init(const DeviceStreamManager& deviceStreamManager,
                    bool                       bLocalAndNonlocal,
                    const std::optional<size_t> nLambda)
 {
+    auto*                      nb     = new NbnxmGpu();
     if (nLambda.has_value())
     {
-        gmx_fatal(FARGS, "Perturbed (FEP) nonbonded kernels are not part of the nbnxm_b200 backend");
+        /* a perturbed run (nbnxm_setup.cpp:578): room for the current lambda + nLambda foreign ones; the values
+         * arrive with copy_gpu_fepparams */
+        nb->foreignLambdaCoul.assign(*nLambda + 1, 0.0F);
+        nb->foreignLambdaVdw.assign(*nLambda + 1, 0.0F);
     }
-    auto*                      nb     = new NbnxmGpu();
     const auto&                params = nbat->params();
     const nbnxm_b200_params_t  p      = makeParams(*ic, listParams, params.ljCombinationRule);
     nb->useLjCombRule = (p.vdw_type == NBNXM_B200_VDW_CUT_COMB_GEOM || p.vdw_type == NBNXM_B200_VDW_CUT_COMB_LB);
@@ -199,6 +210,8 @@ NbnxmGpu* gpu_init(const DeviceStreamManager& deviceStreamManager,
                           localStream,
                           nonLocalStream),
           "nbnxm_b200_init");
+    /* decideGpuTimingsUsage (gpu_utils/gpu_utils.cpp:63): event timing of the kernels is off unless asked for */
+    check(nbnxm_b200_set_timing(nb->handle, decideGpuTimingsUsage() ? 1 : 0), "nbnxm_b200_set_timing");
     return nb;
 }
 
@@ -294,11 +307,11 @@ bool gpu_try_finish_task(NbnxmGpu*           nb,
                          AtomLocality        aloc,
                          real*               e_lj,
                          real*               e_el,
-                         double* /*dvdl_lj*/,
-                         double* /*dvdl_el*/,
-                         ArrayRef<RVec> shiftForces,
-                         ForeignLambdaTerms* /*foreign_term*/,
-                         GpuTaskCompletion completionKind)
+                         double*             dvdl_lj,
+                         double*             dvdl_el,
+                         ArrayRef<RVec>      shiftForces,
+                         ForeignLambdaTerms* foreign_term,
+                         GpuTaskCompletion   completionKind)
 {
     float* fshift = shiftForces.empty() ? nullptr : reinterpret_cast<float*>(shiftForces.data());
     if (completionKind == GpuTaskCompletion::Check)
@@ -306,32 +319,64 @@ bool gpu_try_finish_task(NbnxmGpu*           nb,
         int done = 0;
         check(nbnxm_b200_try_finish_task(nb->handle, toInt(aloc), stepWork.computeEnergy, stepWork.computeVirial, e_lj, e_el, fshift, &done),
               "nbnxm_b200_try_finish_task");
-        return done != 0;
+        if (done == 0)
+        {
+            return false;
+        }
     }
-    check(nbnxm_b200_wait_finish_task(nb->handle, toInt(aloc), stepWork.computeEnergy, stepWork.computeVirial, e_lj, e_el, fshift),
-          "nbnxm_b200_wait_finish_task");
+    else
+    {
+        check(nbnxm_b200_wait_finish_task(nb->handle, toInt(aloc), stepWork.computeEnergy, stepWork.computeVirial, e_lj, e_el, fshift),
+              "nbnxm_b200_wait_finish_task");
+    }
+    /* the perturbed kernels' dV/dlambda and foreign-lambda terms are staged with the energies and added once, at
+     * the local wait (gpu_reduce_staged_outputs / gpu_reduce_staged_foreign_term, gpu_common.h:141-199) */
+    if (nb->haveFep && aloc == AtomLocality::Local)
+    {
+        if (stepWork.computeEnergy && dvdl_lj != nullptr && dvdl_el != nullptr)
+        {
+            float dLj = 0, dEl = 0;
+            check(nbnxm_b200_get_fep_dvdl(nb->handle, &dLj, &dEl, 0), "nbnxm_b200_get_fep_dvdl");
+            *dvdl_lj += dLj;
+            *dvdl_el += dEl;
+        }
+        if (nb->foreignLaunched && foreign_term != nullptr)
+        {
+            const int           n = static_cast<int>(nb->foreignLambdaCoul.size());
+            std::vector<double> terms(4 * n);
+            check(nbnxm_b200_get_fep_foreign(nb->handle, n, terms.data()), "nbnxm_b200_get_fep_foreign");
+            for (int idx = 0; idx < n; idx++)
+            {
+                foreign_term->accumulate(idx, FreeEnergyPerturbationCouplingType::Vdw, terms[4 * idx], terms[4 * idx + 2]);
+                foreign_term->accumulate(idx, FreeEnergyPerturbationCouplingType::Coul, terms[4 * idx + 1], terms[4 * idx + 3]);
+            }
+        }
+        nb->foreignLaunched = false;
+    }
     return true;
 }
 
 float gpu_wait_finish_task(NbnxmGpu*           nb,
                            const StepWorkload& stepWork,
                            AtomLocality        aloc,
-                           const bool /*haveSoftCore*/,
-                           gmx_enerdata_t* enerd,
+                           const bool          haveSoftCore,
+                           gmx_enerdata_t*     enerd,
                            ArrayRef<RVec>  shiftForces,
                            gmx_wallcycle*  wcycle)
 {
     auto cycleCounter = (aloc == AtomLocality::Local) ? WallCycleCounter::WaitGpuNbL : WallCycleCounter::WaitGpuNbNL;
     wallcycle_start(wcycle, cycleCounter);
+    /* gpu_common.h:407-419: soft-core makes the lambda dependence non-linear */
+    auto& dvdl = haveSoftCore ? enerd->dvdl_nonlin : enerd->dvdl_lin;
     gpu_try_finish_task(nb,
                         stepWork,
                         aloc,
                         enerd->grpp.energyGroupPairTerms[NonBondedEnergyTerms::LJSR].data(),
                         enerd->grpp.energyGroupPairTerms[NonBondedEnergyTerms::CoulombSR].data(),
-                        nullptr,
-                        nullptr,
+                        &dvdl[FreeEnergyPerturbationCouplingType::Vdw],
+                        &dvdl[FreeEnergyPerturbationCouplingType::Coul],
                         shiftForces,
-                        nullptr,
+                        &enerd->foreignLambdaTerms,
                         GpuTaskCompletion::Wait);
     return static_cast<float>(wallcycle_stop(wcycle, cycleCounter));
 }
@@ -348,7 +393,7 @@ void nbnxmInsertNonlocalGpuDependency(NbnxmGpu* nb, InteractionLocality interact
 
 void setupGpuShortRangeWorkLow(NbnxmGpu* nb, const ListedForcesGpu* listedForcesGpu, InteractionLocality iLocality)
 {
-    const bool haveBonded = (listedForcesGpu != nullptr); /* the reference asks listedForcesGpu->haveInteractions() */
+    const bool haveBonded = (listedForcesGpu != nullptr && listedForcesGpu->haveInteractions());
     check(nbnxm_b200_setup_short_range_work(nb->handle, toInt(iLocality), haveBonded ? 1 : 0), "nbnxm_b200_setup_short_range_work");
 }
 
@@ -482,6 +527,21 @@ DeviceBuffer<RVec> gpu_get_f(NbnxmGpu* nb)
     return reinterpret_cast<DeviceBuffer<RVec>>(d_f);
 }
 
+NBAtomDataGpu* gpuGetNBAtomData(NbnxmGpu* nb)
+{
+    /* the GPU listed forces read xq and add into f and fShift (listed_forces_gpu_impl: d_xq_, d_f_, d_fShift_) */
+    float *d_xq = nullptr, *d_f = nullptr, *d_fshift = nullptr;
+    int    natoms = 0;
+    check(nbnxm_b200_get_device_buffers(nb->handle, &d_xq, nullptr, &natoms), "nbnxm_b200_get_device_buffers");
+    check(nbnxm_b200_get_shared_outputs(nb->handle, &d_f, &d_fshift), "nbnxm_b200_get_shared_outputs");
+    nb->atdat.numAtoms      = natoms;
+    nb->atdat.numAtomsAlloc = natoms;
+    nb->atdat.xq            = reinterpret_cast<DeviceBuffer<Float4>>(d_xq);
+    nb->atdat.f             = reinterpret_cast<DeviceBuffer<Float3>>(d_f);
+    nb->atdat.fShift        = reinterpret_cast<DeviceBuffer<Float3>>(d_fshift);
+    return &nb->atdat;
+}
+
 gmx_wallclock_gpu_nbnxm_t* gpu_get_timings(NbnxmGpu* nb)
 {
     if (nb == nullptr)
@@ -529,8 +589,6 @@ void gpu_pme_loadbal_update_param(nonbonded_verlet_t* nbv, const interaction_con
     check(nbnxm_b200_update_params(nb->handle, &p, tab, tabSize), "nbnxm_b200_update_params");
 }
 
-/* Perturbed-interaction (FEP) kernels work on atom-pair lists and are a separate backend piece
- * (src/gromacs/nbnxm/cuda/nbfe_cuda.cu); not part of this path. */
 /* ---- perturbed (free-energy) pair kernels: gpu_data_mgmt.h:75, :106, nbnxm_gpu.h:115 ---- */
 
 void copy_gpu_fepparams(NbnxmGpu*   nb,
@@ -543,13 +601,24 @@ void copy_gpu_fepparams(NbnxmGpu*   nb,
                         float       lambdaCoul,
                         float       lambdaVdw,
                         int         nLambda,
-                        const EnumerationArray<FreeEnergyPerturbationCouplingType, std::vector<double>>& /*all_lambda*/)
+                        const EnumerationArray<FreeEnergyPerturbationCouplingType, std::vector<double>>& all_lambda)
 {
-    if (bFepGpuNonBonded && nLambda > 1)
-    {
-        gmx_fatal(FARGS, "Foreign-lambda energies of the perturbed nonbonded kernels are not part of the nbnxm_b200 backend");
-    }
     nb->haveFep = bFepGpuNonBonded;
+    if (nLambda > 0)
+    {
+        nb->foreignLambdaCoul.assign(nLambda + 1, lambdaCoul);
+        nb->foreignLambdaVdw.assign(nLambda + 1, lambdaVdw);
+        for (int i = 0; i < nLambda; i++)
+        {
+            nb->foreignLambdaCoul[i + 1] = static_cast<float>(all_lambda[FreeEnergyPerturbationCouplingType::Coul][i]);
+            nb->foreignLambdaVdw[i + 1]  = static_cast<float>(all_lambda[FreeEnergyPerturbationCouplingType::Vdw][i]);
+        }
+    }
+    else
+    {
+        nb->foreignLambdaCoul.clear();
+        nb->foreignLambdaVdw.clear();
+    }
     check(nbnxm_b200_copy_fepparams(nb->handle,
                                     bFepGpuNonBonded ? 1 : 0,
                                     alphaCoul,
@@ -593,10 +662,21 @@ void gpu_init_feppairlist(NbnxmGpu* nb, const AtomPairlist& h_feplist, Interacti
           "nbnxm_b200_init_feppairlist");
 }
 
-void gpu_launch_free_energy_kernel(NbnxmGpu* nb, const SimulationWorkload& /*simulationWork*/, const StepWorkload& stepWork, InteractionLocality iloc)
+void gpu_launch_free_energy_kernel(NbnxmGpu* nb, const SimulationWorkload& simulationWork, const StepWorkload& stepWork, InteractionLocality iloc)
 {
     check(nbnxm_b200_launch_free_energy_kernel(nb->handle, toInt(iloc), stepWork.computeEnergy ? 1 : 0, stepWork.computeVirial ? 1 : 0),
           "nbnxm_b200_launch_free_energy_kernel");
+    /* the foreign-lambda launch (nbfe_cuda.cu:358-400): energies and dV/dlambda at the current and all foreign lambdas */
+    if (simulationWork.useGpuForeignNonbondedFE && stepWork.computeDhdl && !nb->foreignLambdaCoul.empty())
+    {
+        check(nbnxm_b200_launch_foreign_energy_kernel(nb->handle,
+                                                      toInt(iloc),
+                                                      static_cast<int>(nb->foreignLambdaCoul.size()),
+                                                      nb->foreignLambdaCoul.data(),
+                                                      nb->foreignLambdaVdw.data()),
+              "nbnxm_b200_launch_foreign_energy_kernel");
+        nb->foreignLaunched = true;
+    }
 }
 
 } // namespace gmx

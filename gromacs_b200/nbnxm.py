@@ -36,7 +36,7 @@ EXPORTED_SYMBOLS = [
     "nbnxm_b200_copy_fepparams", "nbnxm_b200_init_fep_atomdata", "nbnxm_b200_init_feppairlist",
     "nbnxm_b200_launch_free_energy_kernel", "nbnxm_b200_get_fep_dvdl", "nbnxm_b200_launch_foreign_energy_kernel",
     "nbnxm_b200_get_fep_foreign",
-    "nbnxm_b200_set_timing", "nbnxm_b200_init_reduce_f", "nbnxm_b200_reduce_f", "nbnxm_b200_get_device_buffers", "nbnxm_b200_get_streams",
+    "nbnxm_b200_set_timing", "nbnxm_b200_init_reduce_f", "nbnxm_b200_reduce_f", "nbnxm_b200_get_device_buffers", "nbnxm_b200_get_shared_outputs", "nbnxm_b200_get_streams",
     "nbnxm_b200_download_pairlist", "nbnxm_b200_set_pair_counting", "nbnxm_b200_get_pair_count",
     "nbnxm_b200_launch_count", "nbnxm_b200_pack_xq", "nbnxm_b200_unpack_xq", "nbnxm_b200_pack_f",
     "nbnxm_b200_unpack_add_f", "nbnxm_b200_measure_fp32_peak",
@@ -381,6 +381,13 @@ class NbnxmGpu:
         xq, f, n = C.c_void_p(), C.c_void_p(), C.c_int()
         self._check(self._lib.nbnxm_b200_get_device_buffers(self._h, C.byref(xq), C.byref(f), C.byref(n)))
         return xq.value, f.value, n.value
+
+    def gpuGetNBAtomData(self):
+        """(d_f, d_fshift): the outputs other device code may add into (gpuGetNBAtomData, nbnxm_gpu_data_mgmt.cpp:1823); from
+        this call on gpu_clear_outputs zeroes them and the copy-back adds the kernels' forces on top."""
+        f, fs = C.c_void_p(), C.c_void_p()
+        self._check(self._lib.nbnxm_b200_get_shared_outputs(self._h, C.byref(f), C.byref(fs)))
+        return f.value, fs.value
 
     def streams(self):
         a, b = C.c_void_p(), C.c_void_p()

@@ -188,6 +188,11 @@ int nbnxm_b200_set_timing(nbnxm_b200_t* nb, int enable);
  * d_f is float3-packed (natoms x 3), valid after nbnxm_b200_launch_cpyback's reduction stage
  * (use_gpu_f_buffer_ops = 1 keeps it on the device); d_xq is float4. */
 int nbnxm_b200_get_device_buffers(nbnxm_b200_t* nb, float** d_xq, float** d_f, int* natoms);
+/* gpuGetNBAtomData, nbnxm_gpu_data_mgmt.cpp:1823, for callers that ADD to the outputs on the device (GPU listed forces,
+ * sim_util.cpp:1450): d_f (float3-packed) and d_fshift (float3[45]).  From this call on nbnxm_b200_clear_outputs zeroes
+ * both, the copy-back stage adds the kernels' forces on top of what is in d_f, and the shift forces of d_fshift are
+ * added to the ones nbnxm_b200_{try,wait}_finish_task return. */
+int nbnxm_b200_get_shared_outputs(nbnxm_b200_t* nb, float** d_f, float** d_fshift);
 /* ---- perturbed (free-energy) pair kernels (gromacs_b200/csrc/nbnxm_fep.cu) ----
  * copy_gpu_fepparams, gpu_data_mgmt.h:75 (soft-core and coupling parameters; lambda_power 1 or 2) */
 int nbnxm_b200_copy_fepparams(nbnxm_b200_t* nb, int have_fep, float alpha_coul, float alpha_vdw, int lambda_power,
