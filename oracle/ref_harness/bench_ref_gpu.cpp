@@ -28,6 +28,7 @@
 
 #include "gromacs/gpu_utils/device_stream_manager.h"
 #include "gromacs/gpu_utils/gpu_utils.h"
+#include "gromacs/gmxlib/nrnb.h"
 #include "gromacs/gpu_utils/hostallocator.h"
 #include "gromacs/hardware/device_information.h"
 #include "gromacs/hardware/device_management.h"
@@ -156,6 +157,8 @@ int main(int argc, char** argv)
     ks.ewaldExclusionType = EwaldExclusionType::Analytical;
     PairlistParams plp(ks.kernelType, PairlistType::Hierarchical8x8x8, false, rlistOuter, false);
     plp.lifetime = 99;
+    /* not set by the constructor (pairlistparams.cpp:56-70); init_nb_verlet assigns it (nbnxm_setup.cpp:519) */
+    plp.haveNonbondedFEGpu_ = false;
     if (dynamicPruning)
     {
         /* pairlist_tuning.cpp:570-590, :685: inner radius, pruning interval, rolling parts = nstlistPrune / 2 */
@@ -185,7 +188,8 @@ int main(int argc, char** argv)
     nbv->setAtomProperties(sys.atomTypes, sys.charges, sys.atomInfoAllVdw);
     gpu_init_atomdata(nbv->gpuNbv(), &nbv->nbat());
     t0 = now();
-    nbv->constructPairlist(InteractionLocality::Local, sys.excls, false, 0, nullptr);
+    t_nrnb nrnb; /* the GPU branch of constructPairlist counts the search in it */
+    nbv->constructPairlist(InteractionLocality::Local, sys.excls, false, 0, &nrnb);
     const double tList = now() - t0;
     nbv->setupGpuShortRangeWork(nullptr, InteractionLocality::Local);
     gpu_upload_shiftvec(nbv->gpuNbv(), &nbv->nbat());

@@ -33,9 +33,4 @@ run water12m          --size 4096 --rc 1.2 --vdw cut     --rlist-outer 1.35 --rl
 LD_LIBRARY_PATH=oracle/_ref/cuda/lib:$LD_LIBRARY_PATH timeout 600 ncu --metrics gpu__time_duration.sum --clock-control none -c 200 --csv \
     --log-file gpurun_out/r02b_stock_launches_1536k.csv $H --size 512 --rc 1.0 --vdw cut --rlist-outer 1.18 --rlist-inner 1.002 \
     --dynamic-pruning 1 --iter 14 --warmup 2 --nt $NT > /dev/null 2>&1
-# our own bench lines on the same box for the same workloads
-for wl in water96k_fswitch water384k_ljpme water384k_pswitch water1536k; do
-    timeout 600 python bench.py --workload $wl --steps 40 --warmup 12 > gpurun_out/r02b_bench_$wl.json 2> gpurun_out/r02b_bench_$wl.err
-done
-timeout 900 python bench.py --steps 20 --warmup 12 > gpurun_out/r02b_bench_water12m.json 2> gpurun_out/r02b_bench_water12m.err
 cat gpurun_out/r02b_summary.log; cat gpurun_out/r02b_compare.jsonl
