@@ -249,6 +249,39 @@ def reference_arm(args):
     emit(line)
 
 
+def parity_sample(nb, wl, plist, sw):
+    """Part of the cpu_baseline leg (the one place bench.py uses oracle/, as the checker): a sample of the sci entries of
+    the PRUNED production list - every n-th entry, about 600 of them - through the double-precision oracle and through
+    the CUDA path (same handle, same kernels), forces and energies compared.  tests/test_gpu_benched_configs.py holds
+    the full-size checks; this puts a correctness figure on the bench line itself."""
+    import numpy as np
+    from oracle import oracle_py as O
+    from gromacs_b200 import LOCAL, PairlistGpu, StepWorkload
+    O.build()
+    cj_pruned, _, _, _, _ = nb.download_pairlist()
+    stride = max(1, plist.sci.shape[0] // 600)
+    sub = PairlistGpu(sci=plist.sci[::stride], cjPacked=cj_pruned, excl=plist.excl)
+    g = wl.nbat
+    po = O.OrcParams()
+    for name, _ in wl.params._fields_:
+        if hasattr(po, name):
+            setattr(po, name, getattr(wl.params, name))
+    po.ntypes = g.numTypes
+    f_ref, _, e_ref, npairs = O.forces(po, sub.sci, sub.cjPacked, sub.excl, g.xq, g.type, g.lj_comb, g.nbfp, g.nbfp_comb,
+                                       g.shift_vec)
+    swe = StepWorkload(computeEnergy=True, computeVirial=True, useGpuFBufferOps=False)
+    nb.gpu_init_pairlist(sub, LOCAL)
+    nb.do_force_step(0, swe, have_halo=False, dynamic_pruning=bool(wl.cfg["dynamic_pruning"]), num_parts=3, xq_host=g.xq, f_host=g.f)
+    e_lj, e_el = nb.gpu_wait_finish_task(swe, LOCAL)
+    f = np.asarray(g.f, np.float64)
+    return {"vs_oracle_sample": {"sci_entries": int(sub.sci.shape[0]), "of": int(plist.sci.shape[0]), "pairs_in_range": int(npairs),
+                                 "f_relrms": float(np.sqrt(((f - f_ref) ** 2).sum() / (f_ref ** 2).sum())),
+                                 "f_maxcomp_rel": float(np.abs(f - f_ref).max() / np.abs(f_ref).max()),
+                                 "e_lj_rel": float(abs(e_lj - e_ref[0]) / abs(e_ref[0])),
+                                 "e_el_rel": float(abs(e_el - e_ref[1]) / abs(e_ref[1]))},
+            "tolerance": {"f_relrms": 5e-6, "f_maxcomp_rel": 1e-4, "e_rel": 1e-6}}
+
+
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
@@ -330,10 +363,18 @@ def main():
         if host_io:
             return nb.gpu_wait_finish_task(sw, LOCAL)
 
-    # search step + first-pass prune + a full rolling cycle, untimed
+    # search step + first-pass prune + a full rolling cycle, untimed (the first-pass prune is timed by the library for
+    # `value_with_search` below)
+    outer_list_pairs = 32 * int(np.unpackbits(np.ascontiguousarray(plist.cjPacked[:, [4, 6]]).view(np.uint8)).sum(dtype=np.int64))
     nb.set_pair_counting(True)
+    nb.gpu_reset_timings()
+    nb.set_timing(True)
     step(0, False)
     nb.gpu_wait_finish_task(sw, LOCAL)
+    t0 = nb.gpu_get_timings()
+    first_prune_ms = t0.prune_ms / max(1, t0.prune_count)
+    nb.set_timing(False)
+    nb.gpu_reset_timings()
     pairs_first = nb.get_pair_count(LOCAL)
     for i in range(max(args.warmup, 2 * num_parts)):
         step(i, False)
@@ -411,6 +452,17 @@ def main():
         search_rec = {"error": str(e)[:200]}
 
     value = wl.useful_pairs / (ms_step * 1e-3) * 1e-9
+    # the search step amortised over the list's lifetime (nstlist 100): device gridding + device list build + first-pass
+    # prune of the fresh list once per 100 force steps
+    nstlist = 100
+    if "gpu_grid_ms" in search_rec:
+        search_ms = search_rec["gpu_grid_ms"] + search_rec["gpu_list_ms"] + first_prune_ms
+        search_rec["first_pass_prune_ms"] = first_prune_ms
+        search_rec["nstlist"] = nstlist
+        search_rec["ms_per_step_with_search"] = (nstlist * ms_step + search_ms) / nstlist
+        value_with_search = wl.useful_pairs / (search_rec["ms_per_step_with_search"] * 1e-3) * 1e-9
+    else:
+        value_with_search = None
     line = {
         "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": 1, "steps": args.steps, "warmup": args.warmup,
         "ms_per_step": ms_step, "higher_is_better": True, "scaling": "strong", "vs_baseline": None, "dtype": "f32",
@@ -422,9 +474,11 @@ def main():
                    "l2": "256 MiB flush between steps, outside the per-step CUDA-event intervals" if flush is not None else "no flush",
                    "timing": "mean of per-step CUDA-event intervals on the library's local stream"},
         "us_per_force_step": ms_step * 1e3,
+        "value_with_search": value_with_search,
         "computed_pairs_per_step": computed_pairs,
         "computed_gpairs_per_s": computed_pairs / (ms_step * 1e-3) * 1e-9,
-        "unpruned_pairs_first_step": pairs_first,
+        "outer_list_pairs": outer_list_pairs,
+        "pairs_after_first_pass_prune": pairs_first,
         "gpu_launches": launches,
         "search_step": search_rec,
         "clocks": clock_rec,
@@ -440,6 +494,7 @@ def main():
                      "peak_source": "measured live: pure-FFMA kernel (nbnxm_b200_measure_fp32_peak); nominal 148 SM x 128 x 2 x 1.965 GHz = 74.45"},
     }
     if not args.no_cpu_baseline:
+        line["parity"] = parity_sample(nb, wl, plist, sw)
         res = run_reference_cpu(cfg, cfg["k"], budget_s=15.0)
         if res is not None:
             line["cpu_baseline"] = {"value": res["useful_pairs"] / res["sec_per_iter"] * 1e-9, "unit": UNIT,

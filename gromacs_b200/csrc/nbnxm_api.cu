@@ -19,7 +19,7 @@
 namespace nbb
 {
 void launch_prune(bool fresh, const AtomDataDev& ad, const ParamsDev& p, const PairlistDev& pl, int numParts, cudaStream_t stream);
-void launch_sci_sort(const PairlistDev& pl, cudaStream_t stream);
+int  launch_sci_sort(const PairlistDev& pl, cudaStream_t stream);
 void launch_count_pairs(const PairlistDev& pl, cudaStream_t stream);
 void launch_x_to_nbat_x(float4* xq, const float* x, const int* atomIndex, int first, int n, cudaStream_t s);
 void launch_f4_to_f3(const float4* f4, float* f3, int first, int n, cudaStream_t s, bool accumulate = false);
@@ -168,6 +168,12 @@ int collectTimings(nbnxm_b200* nb)
         float ms = 0;
         CU(cudaEventElapsedTime(&ms, r.start, r.stop));
         nbnxm_b200_timings_t& t = nb->timings;
+        if (r.kind & 16)
+        {
+            t.force_nonlocal_ms += ms;
+            t.force_nonlocal_count++;
+            r.kind &= 15;
+        }
         switch (r.kind)
         {
             case 0: case 1: case 2: case 3:
@@ -638,8 +644,7 @@ int nbnxm_b200_launch_kernel_pruneonly(nbnxm_b200_t* nb, int iloc, int num_parts
     nb->launches++;
     if (pl.haveFreshList)
     {
-        launch_sci_sort(pl.dev(false), st);
-        nb->launches += 2;
+        nb->launches += launch_sci_sort(pl.dev(false), st);
         pl.haveFreshList = false;
         pl.didPrune      = true;
     }
@@ -678,7 +683,7 @@ int nbnxm_b200_launch_kernel(nbnxm_b200_t* nb, int iloc, int compute_energy, int
     {
         return fail("nbnxm_b200_launch_kernel: no kernel for elec_type %d vdw_type %d", nb->params.elec_type, nb->params.vdw_type);
     }
-    beginRegion(nb, (doPrune ? 2 : 0) + (compute_energy ? 1 : 0), st);
+    beginRegion(nb, (doPrune ? 2 : 0) + (compute_energy ? 1 : 0) + (iloc == 1 ? 16 : 0), st);
     if (nb->pairCounting)
     {
         /* diagnostics: the pairs this launch is about to evaluate (masks as the force kernel will read them) */
@@ -696,8 +701,7 @@ int nbnxm_b200_launch_kernel(nbnxm_b200_t* nb, int iloc, int compute_energy, int
     nb->launches++;
     if (doPrune)
     {
-        launch_sci_sort(pl.dev(false), st);
-        nb->launches += 2;
+        nb->launches += launch_sci_sort(pl.dev(false), st);
         pl.didPrune      = true;
         pl.haveFreshList = false;
     }

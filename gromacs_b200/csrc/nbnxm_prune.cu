@@ -14,6 +14,8 @@
  * i-atoms (il of every i-cluster) in registers and tests j-atoms jl (half 0) and jl+4 (half 1), so both
  * halves are pruned by the same warp with two warp votes per cluster pair.
  */
+#include <cstdlib>
+
 #include "nbnxm_device.cuh"
 
 namespace nbb
@@ -242,6 +244,51 @@ __global__ void __launch_bounds__(256) nbnxm_sci_bucket_sort_kernel(const Pairli
     }
 }
 
+/* Locality-preserving form of the sort for lists far larger than the GPU holds at once: the entries are sorted by
+ * decreasing pair count within tiles of c_sciSortTile consecutive entries of the (spatially ordered) sci array, so CTAs
+ * that run at the same time work on neighbouring super-clusters and share their j-atoms in L2, while every tile - the
+ * last one in particular, which forms the tail of the launch - still runs its longest entries first.  Any permutation
+ * of sci is a valid result (nbnxm_cuda_kernel_sci_sort.cuh:41-58); the reference notes that the global order stops
+ * paying above ~400 k atoms (gpu_types_common.h:77-82).  One CTA per tile: (bucket << 12 | index) keys, bitonic network
+ * in shared memory; ties keep the list order, so the result is deterministic. */
+constexpr int c_sciSortTile = 4096;
+
+__global__ void __launch_bounds__(1024) nbnxm_sci_tile_sort_kernel(const PairlistDev pl)
+{
+    __shared__ unsigned int key[c_sciSortTile];
+    const int               first = blockIdx.x * c_sciSortTile;
+    const int               n     = min(c_sciSortTile, pl.numSci - first);
+    for (int i = threadIdx.x; i < c_sciSortTile; i += 1024)
+    {
+        key[i] = i < n ? (static_cast<unsigned int>(pl.sciCount[first + i]) << 12) | static_cast<unsigned int>(i) : 0xffffffffu;
+    }
+    __syncthreads();
+    for (int k = 2; k <= c_sciSortTile; k <<= 1)
+    {
+        for (int j = k >> 1; j > 0; j >>= 1)
+        {
+            for (int t = threadIdx.x; t < c_sciSortTile / 2; t += 1024)
+            {
+                const int          lo  = 2 * t - (t & (j - 1)); /* index with bit j clear */
+                const int          hi  = lo + j;
+                const bool         up  = (lo & k) == 0;
+                const unsigned int a   = key[lo];
+                const unsigned int b   = key[hi];
+                if ((a > b) == up)
+                {
+                    key[lo] = b;
+                    key[hi] = a;
+                }
+            }
+            __syncthreads();
+        }
+    }
+    for (int i = threadIdx.x; i < n; i += 1024)
+    {
+        pl.sciSorted[first + i] = pl.sci[first + (key[i] & (c_sciSortTile - 1))];
+    }
+}
+
 /* diagnostics: 32 atom pairs per set imask bit over the cjPacked ranges of all sci entries */
 __global__ void __launch_bounds__(256) nbnxm_count_pairs_kernel(const PairlistDev pl)
 {
@@ -287,10 +334,26 @@ void launch_prune(bool fresh, const AtomDataDev& ad, const ParamsDev& p, const P
     }
 }
 
-void launch_sci_sort(const PairlistDev& pl, cudaStream_t stream)
+bool sci_sort_is_tiled(int numSci)
 {
+    /* NBNXM_B200_SCI_SORT=global / tiled for A/B runs; default: tiles once the list is many times what the GPU holds at once
+     * (148 SMs x 20 one-warp CTAs) and the atom data no longer fits L2 */
+    static const char* mode = getenv("NBNXM_B200_SCI_SORT");
+    if (mode != nullptr && mode[0] == 'g') return false;
+    if (mode != nullptr && mode[0] == 't') return true;
+    return numSci > 65536;
+}
+
+int launch_sci_sort(const PairlistDev& pl, cudaStream_t stream)
+{
+    if (sci_sort_is_tiled(pl.numSci))
+    {
+        nbnxm_sci_tile_sort_kernel<<<(pl.numSci + c_sciSortTile - 1) / c_sciSortTile, 1024, 0, stream>>>(pl);
+        return 1;
+    }
     nbnxm_sci_histogram_scan_kernel<<<1, 1024, 0, stream>>>(pl.sciHistogram, pl.sciOffset);
     nbnxm_sci_bucket_sort_kernel<<<(pl.numSci + 255) / 256, 256, 0, stream>>>(pl);
+    return 2; /* kernels launched */
 }
 
 } // namespace nbb

@@ -70,7 +70,8 @@ class Timings(C.Structure):
     _fields_ = [("force_ms", (C.c_double * 2) * 2), ("force_count", (C.c_int * 2) * 2),
                 ("prune_ms", C.c_double), ("rolling_prune_ms", C.c_double),
                 ("prune_count", C.c_int), ("rolling_prune_count", C.c_int),
-                ("xq_h2d_ms", C.c_double), ("f_d2h_ms", C.c_double), ("pairlist_h2d_ms", C.c_double)]
+                ("xq_h2d_ms", C.c_double), ("f_d2h_ms", C.c_double), ("pairlist_h2d_ms", C.c_double),
+                ("force_nonlocal_ms", C.c_double), ("force_nonlocal_count", C.c_int)]
 
 
 _lib = None

@@ -23,6 +23,7 @@ FLOPS_PER_PAIR = {"cut": (66, 107), "fswitch": (78, 129), "pswitch": (93, 127), 
 CONFIGS = {
     "bench3k": dict(k=1, rc=0.9, vdw="cut", energy=False, rlist_outer=0.9, rlist_inner=0.9, dynamic_pruning=False),
     "water48k_test": dict(k=16, rc=0.9, vdw="cut", energy=True, rlist_outer=0.95, rlist_inner=0.95, dynamic_pruning=False),
+    "water384k_test": dict(k=128, rc=0.9, vdw="cut", energy=True, rlist_outer=0.95, rlist_inner=0.95, dynamic_pruning=False),
     "water96k_fswitch": dict(k=32, rc=1.0, vdw="fswitch", energy=True, rlist_outer=1.18, rlist_inner=1.002, dynamic_pruning=True),
     "water384k_ljpme": dict(k=128, rc=1.0, vdw="ljpme", energy=False, rlist_outer=1.18, rlist_inner=1.002, dynamic_pruning=True),
     "water384k_pswitch": dict(k=128, rc=1.0, vdw="pswitch", energy=False, rlist_outer=1.18, rlist_inner=1.002, dynamic_pruning=True),

@@ -108,6 +108,10 @@ typedef struct
     double prune_ms, rolling_prune_ms;
     int    prune_count, rolling_prune_count;
     double xq_h2d_ms, f_d2h_ms, pairlist_h2d_ms;
+    /* the non-local share of force_ms / force_count (all flavors): the two localities run on different streams at the
+     * same time, so their launch times must not be added up to a "kernel time per step" */
+    double force_nonlocal_ms;
+    int    force_nonlocal_count;
 } nbnxm_b200_timings_t;
 
 const char* nbnxm_b200_last_error(void);

@@ -169,7 +169,9 @@ int main(int argc, char** argv)
     }
     const bool ljpme = (vdw == "ljpme");
     auto       nbat  = std::make_unique<nbnxm_atomdata_t>(pol, MDLogger(), ks.kernelType,
-                                                   (vdw == "cut") ? gmx::LJCombinationRule::Geometric : gmx::LJCombinationRule::None,
+                                                   (vdw == "cut")     ? gmx::LJCombinationRule::Geometric
+                                                   : (vdw == "cutlb") ? gmx::LJCombinationRule::LorentzBerthelot
+                                                                      : gmx::LJCombinationRule::None,
                                                    ljpme ? gmx::LJCombinationRule::Geometric : gmx::LJCombinationRule::None,
                                                    sys.nonbondedParameters, true, 1, 1);
     NbnxmGpu*  nbnxmGpu = gpu_init(deviceStreamManager, &ic, plp, nbat.get(), false, std::nullopt);
@@ -221,7 +223,8 @@ int main(int argc, char** argv)
         {
             v = { 0, 0, 0 };
         }
-        gpu_try_finish_task(nbv->gpuNbv(), sw, AtomLocality::Local, &eLJ, &eEl, nullptr, nullptr, fshift, nullptr, GpuTaskCompletion::Wait);
+        double dvdlLj = 0, dvdlEl = 0; /* gpu_reduce_staged_outputs adds to them on every energy step (gpu_common.h:151-161) */
+        gpu_try_finish_task(nbv->gpuNbv(), sw, AtomLocality::Local, &eLJ, &eEl, &dvdlLj, &dvdlEl, fshift, nullptr, GpuTaskCompletion::Wait);
     };
 
     int64_t step = 0;

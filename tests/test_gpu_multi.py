@@ -1,5 +1,7 @@
-"""Multi-GPU parity (needs >= 2 GPUs on the box; skipped otherwise): the x-slab step with the library's NCCL halo
-exchange and with its peer-memory halo (no transport), one process per GPU, against the oracle on the whole system."""
+"""Multi-GPU parity (needs >= 2 GPUs on the box; skipped otherwise): the x-slab step as bench.py runs it - dynamic pruning
+with the rolling prune alternating between the local and the non-local list (prunekerneldispatch.cpp:123-128), the
+non-local prune reading halo coordinates - with the library's NCCL halo exchange and with its peer-memory halo (no
+transport), one process per GPU, 2 / 4 / 8 ranks, over 8 steps with moving atoms, against the oracle on the whole system."""
 import os
 import socket
 
@@ -15,6 +17,11 @@ def _free_port():
     port = s.getsockname()[1]
     s.close()
     return port
+
+
+def _workload_name(world):
+    """slabs must be at least one halo wide: 12.4 nm of x for up to 4 ranks, 24.9 nm for 8"""
+    return "water48k_test" if world <= 4 else "water384k_test"
 
 
 def _worker(rank, world, port, out, peer):
@@ -33,13 +40,14 @@ def _worker(rank, world, port, out, peer):
         if rank == 0:
             idt.copy_(torch.frombuffer(bytearray(HaloExchange.unique_id(lib)), dtype=torch.uint8))
         dist.broadcast(idt, 0)
-        wl = make_workload("water48k_test", nthreads=4)
+        wl = make_workload(_workload_name(world), nthreads=4, nslabs=world)
+        _dynamic_pruning_params(wl)
         nb = NbnxmGpu(wl.params, wl.nbat, device=rank, bLocalAndNonlocal=True)
         halo = HaloExchange(nb, idt.cpu().numpy().tobytes(), rank, world)
         plan = make_slab_plan(wl, rank, world, min_sci=2000)
         # the halo part of the host coordinates is never uploaded: it has to arrive through the exchange
         plan.nbat.xq[plan.recv_first:] = 0
-        step = SlabStep(nb, halo, plan, energy=True, dynamic_pruning=False)
+        step = SlabStep(nb, halo, plan, energy=True, dynamic_pruning=True, num_parts=3)
         step.search_step()
         if peer:
             # no transport: the non-local kernel reads the neighbour's coordinates / adds to its forces over NVLink
@@ -50,9 +58,12 @@ def _worker(rank, world, port, out, peer):
             halo.enable_peer_memory(gather, rank, world)
             dist.barrier()
         results = []
-        for i in range(3):
+        nloc = plan.nbat.numLocalAtoms
+        for i, disp in enumerate(_displacements(wl.nbat.numAtoms())):
+            # every rank moves its home atoms; halo coordinates only ever arrive through the exchange
+            plan.nbat.xq[:nloc, :3] += disp[plan.home_slice]
             e_lj, e_el = step(i, host_io=True)
-            results.append((plan.nbat.f[:plan.nbat.numLocalAtoms].astype(np.float64).copy(), e_lj, e_el))
+            results.append((plan.nbat.f[:nloc].astype(np.float64).copy(), e_lj, e_el))
         assert halo.peer_error() == 0
         parts = [None] * world
         dist.all_gather_object(parts, (plan.home_slice.start, results))
@@ -65,8 +76,26 @@ def _worker(rank, world, port, out, peer):
         dist.destroy_process_group()
 
 
+NSTEPS = 8
+
+
+def _displacements(natoms):
+    """the same small random walk on every rank and in the checker, in the global grid order"""
+    rng = np.random.default_rng(2027)
+    for _ in range(NSTEPS):
+        yield rng.normal(0.0, 3e-4, (natoms, 3)).astype(np.float32)
+
+
+def _dynamic_pruning_params(wl):
+    """rlistInner 0.905 inside the 0.95 nm outer list, as the single-GPU tests use it"""
+    import copy
+    wl.params = copy.copy(wl.params)
+    wl.params.use_dynamic_pruning = 1
+    wl.params.rlist_inner_sq = np.float32(0.905 ** 2)
+
+
 @pytest.mark.parametrize("peer", [False, True], ids=["nccl", "peer"])
-@pytest.mark.parametrize("world", [2, 4])
+@pytest.mark.parametrize("world", [2, 4, 8])
 def test_x_slab_step_matches_oracle(oracle, world, peer):
     import torch
     if torch.cuda.device_count() < world:
@@ -83,22 +112,28 @@ def test_x_slab_step_matches_oracle(oracle, world, peer):
     for pr in procs:
         pr.join(120)
         assert pr.exitcode == 0
-    wl = make_workload("water48k_test", nthreads=4)
+    wl = make_workload(_workload_name(world), nthreads=4, nslabs=world)
     p = oracle.OrcParams()
     for name, _ in wl.params._fields_:
         if hasattr(p, name):
             setattr(p, name, getattr(wl.params, name))
     p.ntypes = wl.nbat.numTypes
     whole, g = wl.pairlist(), wl.nbat
-    f_ref, _, e_ref, _ = oracle.forces(p, whole.sci, whole.cjPacked, whole.excl, g.xq, g.type, g.lj_comb, g.nbfp,
-                                       g.nbfp_comb, g.shift_vec)
-    for i in range(3):
+    xq = g.xq.copy()
+    for i, disp in enumerate(_displacements(g.numAtoms())):
+        xq[:, :3] += disp
+        # list step, mid-cycle, and after local and non-local lists were both rolled over (the big box: last step only)
+        if i not in ((0, 3, NSTEPS - 1) if world <= 4 else (NSTEPS - 1,)):
+            continue
+        f_ref, _, e_ref, _ = oracle.forces(p, whole.sci, whole.cjPacked, whole.excl, xq, g.type, g.lj_comb, g.nbfp,
+                                           g.nbfp_comb, g.shift_vec)
         f = np.zeros_like(f_ref)
         e = np.zeros(2)
         for start, results in parts:
             fpart, e_lj, e_el = results[i]
             f[start:start + fpart.shape[0]] += fpart
             e += (e_lj, e_el)
-        assert np.sqrt(((f - f_ref) ** 2).sum() / (f_ref ** 2).sum()) <= 5e-6
+        assert np.sqrt(((f - f_ref) ** 2).sum() / (f_ref ** 2).sum()) <= 5e-6, "step %d" % i
         assert np.abs(f - f_ref).max() <= 1e-4 * np.abs(f_ref).max()
-        assert abs(e[1] - e_ref[1]) <= 2e-6 * abs(e_ref[1]), (e, e_ref)
+        assert abs(e[1] - e_ref[1]) <= 1e-6 * abs(e_ref[1]), (i, e, e_ref)
+        assert abs(e[0] - e_ref[0]) <= 1e-6 * abs(e_ref[0]), (i, e, e_ref)

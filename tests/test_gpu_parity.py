@@ -5,6 +5,7 @@ forces within 1e-6 relative, pruned masks bit-exact."""
 import numpy as np
 import pytest
 
+from test_tolerance_evidence import reference_simd_errors
 from util import (golden_cases, load_golden, maxrel, oracle_forces, oracle_params, product_inputs, product_params,
                   relrms)
 
@@ -16,9 +17,10 @@ E_REL = 1e-6
 # With the Lorentz-Berthelot rule C6/C12 are rebuilt per pair in float32 from sigma and epsilon, exactly as
 # the reference GPU kernel does; the fixed rounding of the O-O parameters is a systematic ~1e-6 term.
 E_REL_LJ_LB = 2e-6
-# The shift forces are sums of float32 pair forces with heavy cancellation; 1e-6 of the largest virial
-# element is below what float32 pair arithmetic can deliver on the 3000-atom box, see DESIGN.md.
-VIR_REL = 1e-5
+# The shift forces are sums of float32 pair forces with heavy cancellation: the reference's own float SIMD kernel is
+# 2e-6 ... 4e-6 away from the double oracle on these fixtures (tests/test_tolerance_evidence.py).  The CUDA kernels are
+# held to 1e-6 or, where that is below the reference float kernel's own error on the same fixture, to that error.
+VIR_REL = 1e-6
 
 
 def virial(shift_vec, fshift):
@@ -41,6 +43,17 @@ def run_step(nb, nbat, plist, energy, virial, fresh_list=True):
     fshift = np.zeros((45, 3), np.float32)
     e_lj, e_el = nb.gpu_wait_finish_task(sw, LOCAL, shiftForces=fshift)
     return nbat.f.astype(np.float64).copy(), e_lj, e_el, fshift.astype(np.float64)
+
+
+def record_tolerance(case, variant, vir, e_lj, e_el, simd):
+    """keeps the measured errors next to the reference float kernel's own (gpurun_out/parity_errors.jsonl)"""
+    import json
+    import os
+    out = os.path.join(os.path.dirname(os.path.dirname(os.path.abspath(__file__))), "gpurun_out")
+    os.makedirs(out, exist_ok=True)
+    with open(os.path.join(out, "parity_errors.jsonl"), "a") as fh:
+        fh.write(json.dumps({"case": case, "kernel": variant, "virial_rel": vir, "e_lj_rel": e_lj, "e_el_rel": e_el,
+                             "ref_simd_virial_rel": simd[0], "ref_simd_e_lj_rel": simd[1], "ref_simd_e_el_rel": simd[2]}) + "\n")
 
 
 def check_forces(f, ref):
@@ -81,7 +94,10 @@ def test_force_energy_virial_parity(oracle, case, kernel_variant):
         assert abs(e_el - e_ref[1]) <= E_REL * abs(e_ref[1]), (e_el, e_ref[1])
         # virial contribution of the shift forces: -1/2 sum_s shift_vec[s] (x) fshift[s]
         vir, vir_ref = virial(d["shift_vec"], fsh), virial(d["shift_vec"], fsh_ref)
-        assert np.abs(vir - vir_ref).max() <= VIR_REL * np.abs(vir_ref).max(), (vir, vir_ref)
+        vir_err    = float(np.abs(vir - vir_ref).max() / np.abs(vir_ref).max())
+        simd_errs  = reference_simd_errors(oracle, d)
+        record_tolerance(case, kernel_variant, vir_err, abs(e_lj - e_ref[0]) / abs(e_ref[0]), abs(e_el - e_ref[1]) / abs(e_ref[1]), simd_errs)
+        assert vir_err <= max(VIR_REL, simd_errs[0]), (vir_err, simd_errs[0])
         assert np.all(fsh[22] == 0)
         # step 3: F-only kernel on the sorted list
         f, _, _, _ = run_step(nb, nbat, plist, energy=False, virial=False, fresh_list=False)
