@@ -271,7 +271,7 @@ def parity_sample(nb, wl, plist, sw):
                                        g.shift_vec)
     swe = StepWorkload(computeEnergy=True, computeVirial=True, useGpuFBufferOps=False)
     nb.gpu_init_pairlist(sub, LOCAL)
-    nb.do_force_step(0, swe, have_halo=False, dynamic_pruning=bool(wl.cfg["dynamic_pruning"]), num_parts=3, xq_host=g.xq, f_host=g.f)
+    nb.do_force_step(0, swe, have_halo=False, dynamic_pruning=bool(wl.cfg["dynamic_pruning"]), num_parts=1, xq_host=g.xq, f_host=g.f)
     e_lj, e_el = nb.gpu_wait_finish_task(swe, LOCAL)
     f = np.asarray(g.f, np.float64)
     return {"vs_oracle_sample": {"sci_entries": int(sub.sci.shape[0]), "of": int(plist.sci.shape[0]), "pairs_in_range": int(npairs),
@@ -309,7 +309,7 @@ def main():
     import torch
     from gromacs_b200 import LOCAL, NbnxmGpu, StepWorkload
     from gromacs_b200.nbnxm import measure_fp32_peak
-    from gromacs_b200.workload import make_workload
+    from gromacs_b200.workload import make_workload, rolling_prune_parts
 
     rank = int(os.environ.get("RANK", "0"))
     world = int(os.environ.get("WORLD_SIZE", "1"))
@@ -348,7 +348,7 @@ def main():
     nb.gpu_upload_shiftvec(nbat)
     nb.gpu_copy_xq_to_gpu(nbat, LOCAL)
     local_stream = torch.cuda.ExternalStream(nb.streams()[0])
-    num_parts = 3          # nstlistPrune 6 -> numRollingPruningParts = nstlistPrune / 2 (pairlist_tuning.cpp:685)
+    num_parts = rolling_prune_parts(cfg)   # numRollingPruningParts = nstlistPrune / 2 (pairlist_tuning.cpp:685)
     flush = None if args.no_l2_flush else torch.empty(256 << 20, dtype=torch.uint8, device="cuda")
 
     def step(i, host_io):
@@ -447,7 +447,8 @@ def main():
                       "host_grid_s": dev["host_grid_s"], "host_list_s": lst["host_build_s"], "host_threads": lst["host_threads"],
                       "host_list_upload_s": lst["host_list_upload_s"], "list_bytes_not_uploaded": lst["list_bytes"],
                       "same_grid_order_as_host": dev["same_order_as_host"],
-                      "same_list_sizes_as_host": bool(lst["same_sizes_as_host"] and dev["same_sizes_as_host"])}
+                      "same_list_sizes_as_host": bool(lst["same_sizes_as_host"] and dev["same_sizes_as_host"]),
+                      "same_list_entries_as_host": lst.get("same_entries_as_host")}
     except Exception as e:      # reported, never fatal for the force-step measurement
         search_rec = {"error": str(e)[:200]}
 

@@ -301,8 +301,10 @@ int putAtomsOnGrid(BE& be, SearchState<BE>& st, const float* box, int ncx, int n
     NBS_TRY(be.scan(gb.colCount, gb.colAtomStart, ncol + 1));
     NBS_TRY(be.scan(gb.colBins, gb.colFirstBin, ncol + 1));
     int nbins = 0;
-    NBS_TRY(be.readInt(gb.colFirstBin + ncol, &nbins));
-    NBS_TRY(be.readInt(gb.maxColCount, &st.maxColumnAtoms));
+    {
+        unsigned long long unused = 0; /* both sizes with one synchronisation */
+        NBS_TRY(be.readInts2ULL(gb.colFirstBin + ncol, &nbins, gb.maxColCount, &st.maxColumnAtoms, nullptr, &unused));
+    }
     if (st.maxColumnAtoms > c_maxColumnAtoms)
     {
         return be.fail("gridding on the device: a grid column holds more atoms than one block sorts (8192); use the host gridder");
@@ -441,12 +443,11 @@ int buildPairlist(BE& be, SearchState<BE>& st, const XQ* xq, float rlist, int mi
     /* pass 4: sizes */
     NBS_TRY(be.forEach(nE, FEntryCountJ{ w }));
     NBS_TRY(be.scan(w.entryGroups, w.entryCjOff, nE + 1));
-    NBS_TRY(be.readInt(w.entryCjOff + nE, &st.ncjp));
     NBS_TRY(be.scan(w.entryNonEmpty, w.entryCompactOff, nE + 1));
-    NBS_TRY(be.readInt(w.entryCompactOff + nE, &st.numEntries));
     {
+        /* the three sizes of this stage with one synchronisation */
         unsigned long long ncp = 0;
-        NBS_TRY(be.readULL(w.numClusterPairs, &ncp));
+        NBS_TRY(be.readInts2ULL(w.entryCjOff + nE, &st.ncjp, w.entryCompactOff + nE, &st.numEntries, w.numClusterPairs, &ncp));
         st.numClusterPairsHost = (long long)ncp;
     }
     if (st.ncjp == 0)

@@ -127,7 +127,7 @@ struct CudaSearchBackend
     cudaStream_t st       = nullptr;
     long long    launches = 0;
     DevBuf<int>  tileSums, tileOffsets;
-    int*         h_value = nullptr; /* pinned, 8 bytes */
+    int*         h_value = nullptr; /* pinned, 64 bytes: up to four values per read-back */
 
     int fail(const char* msg) { return nbb::fail("%s", msg); }
 
@@ -184,6 +184,18 @@ struct CudaSearchBackend
         CU(cudaMemcpyAsync(h_value, p, sizeof(int), cudaMemcpyDeviceToHost, st));
         CU(cudaStreamSynchronize(st));
         *v = *reinterpret_cast<int*>(h_value);
+        return 0;
+    }
+    /* several scalars with ONE stream synchronisation: two ints and one 64-bit count */
+    int readInts2ULL(const int* p0, int* v0, const int* p1, int* v1, const unsigned long long* p2, unsigned long long* v2)
+    {
+        CU(cudaMemcpyAsync(h_value, p0, sizeof(int), cudaMemcpyDeviceToHost, st));
+        CU(cudaMemcpyAsync(h_value + 1, p1, sizeof(int), cudaMemcpyDeviceToHost, st));
+        if (p2) CU(cudaMemcpyAsync(h_value + 2, p2, sizeof(unsigned long long), cudaMemcpyDeviceToHost, st));
+        CU(cudaStreamSynchronize(st));
+        *v0 = h_value[0];
+        *v1 = h_value[1];
+        if (p2) *v2 = *reinterpret_cast<unsigned long long*>(h_value + 2);
         return 0;
     }
     int readULL(const unsigned long long* p, unsigned long long* v)
@@ -256,7 +268,7 @@ int nbnxm_b200_gpu_search_create(nbnxm_b200_gpu_search_t** out, nbnxm_b200_t* nb
     CU(cudaSetDevice(nb->device));
     void*       pinned = nullptr;
     cudaEvent_t ev[2]  = { nullptr, nullptr };
-    if (cudaMallocHost(&pinned, 16) != cudaSuccess || cudaEventCreate(&ev[0]) != cudaSuccess || cudaEventCreate(&ev[1]) != cudaSuccess)
+    if (cudaMallocHost(&pinned, 64) != cudaSuccess || cudaEventCreate(&ev[0]) != cudaSuccess || cudaEventCreate(&ev[1]) != cudaSuccess)
     {
         if (pinned) cudaFreeHost(pinned);
         if (ev[0]) cudaEventDestroy(ev[0]);

@@ -274,7 +274,7 @@ def bench_multi_gpu(args, rank, world, local_rank):
     import torch
     import torch.distributed as dist
     from .nbnxm import load_library, measure_fp32_peak
-    from .workload import make_workload
+    from .workload import make_workload, rolling_prune_parts
 
     torch.cuda.set_device(local_rank)
     dist.init_process_group(backend="nccl", device_id=torch.device("cuda", local_rank))
@@ -299,7 +299,7 @@ def bench_multi_gpu(args, rank, world, local_rank):
     f_pin = torch.zeros((nbat.numAtoms(), 3), dtype=torch.float32).pin_memory()
     nbat.f = f_pin.numpy()
 
-    num_parts = 3
+    num_parts = rolling_prune_parts(cfg)
     step = SlabStep(nb, halo, plan, energy, cfg["dynamic_pruning"], num_parts)
     step.search_step()
     if getattr(args, "halo", "peer") == "peer":

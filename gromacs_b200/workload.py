@@ -17,18 +17,23 @@ from .pairsearch import Grid
 # accountFlops (src/gromacs/nbnxm/kerneldispatch.cpp:396-452); (F-only, F+E)
 FLOPS_PER_PAIR = {"cut": (66, 107), "fswitch": (78, 129), "pswitch": (93, 127), "ljpme": (102, 140)}
 
-# BASELINE.json configs -> (size factor k, rc, VdW flavor, energy every step, rlistOuter, rlistInner)
-# rlist values follow the reference's dynamic-pruning set-up for nstlist 100:
-# outer buffer ~0.18 nm, inner list pruned every few steps with a ~2e-3 nm buffer.
+# BASELINE.json configs -> (size factor k, rc, VdW flavor, energy every step, rlistOuter, rlistInner, nstlistPrune)
+# The list radii and the pruning interval of the benchmark configurations are the REFERENCE's: its own pair-list tuning
+# (increaseNstlist + setupDynamicPairlistPruning, nbnxm/pairlist_tuning.cpp:455-700) run on SPC/E water at 300 K, dt 2 fs,
+# nstlist 100, default verlet-buffer-tolerance, for the GPU list - tests/golden/make_pairlist_tuning.sh asks a build of the
+# reference and tests/golden/pairlist_tuning.json keeps its answer (tests/test_hostplan.py checks this table against it):
+#   rc 1.0: outer 1.172, inner 1.003, pruned every 10 steps;  rc 1.2: outer 1.358, inner 1.201, every 10 steps.
+# numRollingPruningParts = nstlistPrune / 2 (pairlist_tuning.cpp:685).  The *_test entries are small cases for the tests.
 CONFIGS = {
     "bench3k": dict(k=1, rc=0.9, vdw="cut", energy=False, rlist_outer=0.9, rlist_inner=0.9, dynamic_pruning=False),
     "water48k_test": dict(k=16, rc=0.9, vdw="cut", energy=True, rlist_outer=0.95, rlist_inner=0.95, dynamic_pruning=False),
+    "water24k_test": dict(k=8, rc=0.9, vdw="cut", energy=True, rlist_outer=0.95, rlist_inner=0.95, dynamic_pruning=False),
     "water384k_test": dict(k=128, rc=0.9, vdw="cut", energy=True, rlist_outer=0.95, rlist_inner=0.95, dynamic_pruning=False),
-    "water96k_fswitch": dict(k=32, rc=1.0, vdw="fswitch", energy=True, rlist_outer=1.18, rlist_inner=1.002, dynamic_pruning=True),
-    "water384k_ljpme": dict(k=128, rc=1.0, vdw="ljpme", energy=False, rlist_outer=1.18, rlist_inner=1.002, dynamic_pruning=True),
-    "water384k_pswitch": dict(k=128, rc=1.0, vdw="pswitch", energy=False, rlist_outer=1.18, rlist_inner=1.002, dynamic_pruning=True),
-    "water1536k": dict(k=512, rc=1.0, vdw="cut", energy=False, rlist_outer=1.18, rlist_inner=1.002, dynamic_pruning=True),
-    "water12m": dict(k=4096, rc=1.2, vdw="cut", energy=False, rlist_outer=1.35, rlist_inner=1.202, dynamic_pruning=True),
+    "water96k_fswitch": dict(k=32, rc=1.0, vdw="fswitch", energy=True, rlist_outer=1.172, rlist_inner=1.003, nstlist_prune=10, dynamic_pruning=True),
+    "water384k_ljpme": dict(k=128, rc=1.0, vdw="ljpme", energy=False, rlist_outer=1.172, rlist_inner=1.003, nstlist_prune=10, dynamic_pruning=True),
+    "water384k_pswitch": dict(k=128, rc=1.0, vdw="pswitch", energy=False, rlist_outer=1.172, rlist_inner=1.003, nstlist_prune=10, dynamic_pruning=True),
+    "water1536k": dict(k=512, rc=1.0, vdw="cut", energy=False, rlist_outer=1.172, rlist_inner=1.003, nstlist_prune=10, dynamic_pruning=True),
+    "water12m": dict(k=4096, rc=1.2, vdw="cut", energy=False, rlist_outer=1.358, rlist_inner=1.201, nstlist_prune=10, dynamic_pruning=True),
 }
 
 
@@ -72,6 +77,11 @@ def make_interaction_params(vdw, rc, rlist_outer, rlist_inner, dynamic_pruning, 
         return make_params("EwaldAna", "EwaldGeom", disp=(0.0, 0.0, cd), rep=(0.0, 0.0, cr), ewaldcoeff_lj=blj,
                            sh_lj_ewald=sh_lj, **kw)
     raise ValueError(vdw)
+
+
+def rolling_prune_parts(cfg):
+    """numRollingPruningParts = nstlistPrune / c_nbnxmGpuRollingListPruningInterval (pairlist_tuning.cpp:685)"""
+    return max(1, cfg.get("nstlist_prune", 6) // 2)
 
 
 def make_workload(name, nthreads=None, energy=None, nslabs=1) -> Workload:

@@ -27,6 +27,30 @@ ms = []
 for _ in range(builds):
     sizes = search.build(wl.cfg["rlist_outer"], LOCAL, min_sci=min_sci)
     ms.append(search.build_ms)
+# entry-for-entry comparison with the host builder's list (all threads: same sci / cjPacked bits, the exclusion entries
+# are numbered in another order, so they are compared through the groups that point at them)
+import numpy as np  # noqa: E402
+got = search.download()
+
+
+def same_entries(a, b):
+    sa, sb = np.asarray(a.sci).reshape(-1, 4), np.asarray(b.sci).reshape(-1, 4)
+    ca, cb = np.asarray(a.cjPacked).reshape(-1, 8), np.asarray(b.cjPacked).reshape(-1, 8)
+    if sa.shape != sb.shape or ca.shape != cb.shape or not np.array_equal(sa, sb):
+        return False
+    if not np.array_equal(ca[:, [0, 1, 2, 3, 4, 6]], cb[:, [0, 1, 2, 3, 4, 6]]):
+        return False
+    ea, eb = np.asarray(a.excl).reshape(-1, 32), np.asarray(b.excl).reshape(-1, 32)
+    for h in (5, 7):
+        ia, ib = ca[:, h], cb[:, h]
+        m = ia != 0
+        if not np.array_equal(m, ib != 0) or not np.array_equal(ea[ia[m]], eb[ib[m]]):
+            return False
+    return True
+
+
+entries_equal = bool(same_entries(got, ref))
+del got
 # the host path for comparison: upload of the host builder's list (gpu_init_pairlist from pageable numpy arrays)
 from gromacs_b200 import StepWorkload  # noqa: E402
 nb.gpu_wait_finish_task(StepWorkload(), LOCAL)
@@ -36,7 +60,7 @@ nb.gpu_wait_finish_task(StepWorkload(), LOCAL)
 h2d_s = time.time() - t0
 print(json.dumps({"host_list_upload_s": h2d_s, "workload": name, "natoms": wl.box.natoms, "rlist": wl.cfg["rlist_outer"], "nsci": sizes[0],
                   "ncj_packed": sizes[1], "nexcl": sizes[2], "same_sizes_as_host": sizes == (ref.sci.shape[0], ref.cjPacked.shape[0], ref.excl.shape[0]),
-                  "gpu_build_ms": ms, "host_build_s": host_s, "host_threads": wl.grid.nthreads,
+                  "same_entries_as_host": entries_equal, "gpu_build_ms": ms, "host_build_s": host_s, "host_threads": wl.grid.nthreads,
                   "list_bytes": int(ref.sci.nbytes + ref.cjPacked.nbytes + ref.excl.nbytes)}))
 search.free()
 # the whole search step on the device: gridding from atom-order coordinates in device memory, then the list

@@ -70,6 +70,13 @@ struct HostBackend
         *v = *p;
         return 0;
     }
+    int readInts2ULL(const int* p0, int* v0, const int* p1, int* v1, const unsigned long long* p2, unsigned long long* v2)
+    {
+        *v0 = *p0;
+        *v1 = *p1;
+        if (p2) *v2 = *p2;
+        return 0;
+    }
     int readULL(const unsigned long long* p, unsigned long long* v)
     {
         *v = *p;

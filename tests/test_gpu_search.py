@@ -310,3 +310,36 @@ def test_cooperative_mask_pass_gives_the_same_list(monkeypatch):
     if os.path.isdir(out):
         with open(os.path.join(out, "gpu_search_coop_1536k.json"), "w") as fh:
             json.dump({"workload": "water1536k", "build_ms_thread_per_j_cluster": times["0"], "build_ms_warp_per_bin_pair": times["1"]}, fh)
+
+
+@pytest.mark.parametrize("name,rlist", [("bench3k", 0.9), ("water24k_test", 0.95)])
+def test_device_list_against_brute_force(oracle, name, rlist):
+    """Independent of every product-side builder: the list built on the device, downloaded and walked by the double
+    oracle, must give the forces and energies of the oracle's O(N^2) brute force over all atom pairs with the minimum
+    image convention (no list at all) - a missing cluster pair, a wrong shift or a wrong exclusion bit shows up here."""
+    from gromacs_b200 import LOCAL, NbnxmGpu
+    from gromacs_b200.pairsearch import GpuPairSearch
+    from gromacs_b200.workload import make_workload
+    wl = make_workload(name, nthreads=4)
+    g, b = wl.nbat, wl.box
+    nb = NbnxmGpu(wl.params, g)
+    try:
+        nb.gpu_init_atomdata(g)
+        nb.gpu_upload_shiftvec(g)
+        nb.gpu_copy_xq_to_gpu(g, LOCAL)
+        search = GpuPairSearch(nb, wl.grid, b.excl_index, b.excl_atoms)
+        search.build(rlist, LOCAL, min_sci=0)
+        got = search.download()
+        search.free()
+    finally:
+        nb.gpu_free()
+    p = oracle.OrcParams()
+    for field, _ in wl.params._fields_:
+        if hasattr(p, field):
+            setattr(p, field, getattr(wl.params, field))
+    p.ntypes = g.numTypes
+    f_list, _, e_list, _ = oracle.forces(p, got.sci, got.cjPacked, got.excl, g.xq, g.type, g.lj_comb, g.nbfp, g.nbfp_comb, g.shift_vec)
+    f_list = oracle.nbat_to_atom_order(f_list, wl.grid.atom_index, b.natoms)
+    f_bf, e_bf = oracle.brute_force(p, b.x, b.q, b.type, g.nbfp, g.nbfp_comb, b.box, b.excl_index, b.excl_atoms)
+    assert relrms(f_list, f_bf) <= 1e-6, relrms(f_list, f_bf)
+    assert abs(e_list[0] - e_bf[0]) <= 1e-6 * abs(e_bf[0]) and abs(e_list[1] - e_bf[1]) <= 1e-6 * abs(e_bf[1])
