@@ -194,6 +194,8 @@ int main(int argc, char** argv)
     nbv->constructPairlist(InteractionLocality::Local, sys.excls, false, 0, &nrnb);
     const double tList = now() - t0;
     nbv->setupGpuShortRangeWork(nullptr, InteractionLocality::Local);
+    /* the periodic shift vectors into the atom data (do_force: nbnxm_atomdata_copy_shiftvec, sim_util.cpp), then to the device */
+    nbnxm_atomdata_copy_shiftvec(false, sys.forceRec.shift_vec, &nbv->nbat());
     gpu_upload_shiftvec(nbv->gpuNbv(), &nbv->nbat());
 
     STAGE("steps");

@@ -170,7 +170,11 @@ def test_shared_outputs_keep_what_other_kernels_added(oracle):
             fsh = np.zeros((45, 3), np.float32)
             nb.gpu_wait_finish_task(sw, LOCAL, shiftForces=fsh)
             assert relrms(nbat.f.astype(np.float64), f_ref + extra_f) <= 5e-6
-            assert np.abs(fsh - (fsh_ref + extra_fs)).max() <= 1e-5 * np.abs(fsh_ref + extra_fs).max()
+            # the kernels leave the central shift (index 22) alone (nbnxm_cuda_kernel.cuh:700-717); the oracle, like the CPU
+            # kernels, sums it up: compare the other 44, and expect only the foreign contribution at 22
+            want = fsh_ref + extra_fs
+            want[22] = extra_fs[22]
+            assert np.abs(fsh - want).max() <= 1e-5 * np.abs(want).max()
     finally:
         nb.gpu_free()
 
