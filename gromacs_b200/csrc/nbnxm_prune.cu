@@ -249,10 +249,11 @@ __global__ void __launch_bounds__(256) nbnxm_sci_bucket_sort_kernel(const Pairli
  * that run at the same time work on neighbouring super-clusters and share their j-atoms in L2, while every tile - the
  * last one in particular, which forms the tail of the launch - still runs its longest entries first.  Any permutation
  * of sci is a valid result (nbnxm_cuda_kernel_sci_sort.cuh:41-58); the reference notes that the global order stops
- * paying above ~400 k atoms (gpu_types_common.h:77-82).  One CTA per tile: (bucket << 12 | index) keys, bitonic network
+ * paying above ~400 k atoms (gpu_types_common.h:77-82).  One CTA per tile: (bucket << 13 | index) keys, bitonic network
  * in shared memory; ties keep the list order, so the result is deterministic. */
 constexpr int c_sciSortTile = 4096;
 
+template<int c_sciSortTile>
 __global__ void __launch_bounds__(1024) nbnxm_sci_tile_sort_kernel(const PairlistDev pl)
 {
     __shared__ unsigned int key[c_sciSortTile];
@@ -260,7 +261,7 @@ __global__ void __launch_bounds__(1024) nbnxm_sci_tile_sort_kernel(const Pairlis
     const int               n     = min(c_sciSortTile, pl.numSci - first);
     for (int i = threadIdx.x; i < c_sciSortTile; i += 1024)
     {
-        key[i] = i < n ? (static_cast<unsigned int>(pl.sciCount[first + i]) << 12) | static_cast<unsigned int>(i) : 0xffffffffu;
+        key[i] = i < n ? (static_cast<unsigned int>(pl.sciCount[first + i]) << 13) | static_cast<unsigned int>(i) : 0xffffffffu;
     }
     __syncthreads();
     for (int k = 2; k <= c_sciSortTile; k <<= 1)
@@ -348,7 +349,16 @@ int launch_sci_sort(const PairlistDev& pl, cudaStream_t stream)
 {
     if (sci_sort_is_tiled(pl.numSci))
     {
-        nbnxm_sci_tile_sort_kernel<<<(pl.numSci + c_sciSortTile - 1) / c_sciSortTile, 1024, 0, stream>>>(pl);
+        /* NBNXM_B200_SCI_SORT_TILE=8192 for A/B runs of the tile size */
+        static const char* tile = getenv("NBNXM_B200_SCI_SORT_TILE");
+        if (tile != nullptr && atoi(tile) == 8192)
+        {
+            nbnxm_sci_tile_sort_kernel<8192><<<(pl.numSci + 8191) / 8192, 1024, 0, stream>>>(pl);
+        }
+        else
+        {
+            nbnxm_sci_tile_sort_kernel<c_sciSortTile><<<(pl.numSci + c_sciSortTile - 1) / c_sciSortTile, 1024, 0, stream>>>(pl);
+        }
         return 1;
     }
     nbnxm_sci_histogram_scan_kernel<<<1, 1024, 0, stream>>>(pl.sciHistogram, pl.sciOffset);
