@@ -321,6 +321,8 @@ int nbnxm_b200_free(nbnxm_b200_t* nb)
     for (cudaEvent_t ev : nb->chunkH2D) cudaEventDestroy(ev);
     for (cudaEvent_t ev : nb->chunkKernel) cudaEventDestroy(ev);
     if (nb->pipeStart) cudaEventDestroy(nb->pipeStart);
+    if (nb->tlStart) cudaEventDestroy(nb->tlStart);
+    for (cudaEvent_t ev : nb->tlEvents) cudaEventDestroy(ev);
     if (nb->pipeD2HDone) cudaEventDestroy(nb->pipeD2HDone);
     if (nb->h2dStream) cudaStreamDestroy(nb->h2dStream);
     if (nb->d2hStream) cudaStreamDestroy(nb->d2hStream);
@@ -772,6 +774,19 @@ int nbnxm_b200_do_force_step_pipelined(nbnxm_b200_t* nb, int step, const nbnxm_b
         nb->chunkH2D.push_back(a);
         nb->chunkKernel.push_back(b);
     }
+    const bool tl = nb->pipeTimeline;
+    if (tl)
+    {
+        if (!nb->tlStart) CU(cudaEventCreate(&nb->tlStart));
+        while (int(nb->tlEvents.size()) < 4 * nchunks)
+        {
+            cudaEvent_t ev;
+            CU(cudaEventCreate(&ev));
+            nb->tlEvents.push_back(ev);
+        }
+        nb->tlChunks = nchunks;
+        CU(cudaEventRecord(nb->tlStart, st));
+    }
     /* everything of the previous step on the local stream (kernels reading xq, copies of f) comes first */
     if (nbnxm_b200_clear_outputs(nb, v)) return 1;
     CU(cudaEventRecord(nb->pipeStart, st));
@@ -786,6 +801,7 @@ int nbnxm_b200_do_force_step_pipelined(nbnxm_b200_t* nb, int step, const nbnxm_b
                                nb->h2dStream));
         }
         CU(cudaEventRecord(nb->chunkH2D[c], nb->h2dStream));
+        if (tl) CU(cudaEventRecord(nb->tlEvents[4 * c], nb->h2dStream));
     }
     /* sci chunks in the order in which their coordinates are complete: by the last atom chunk they need */
     int order[32], lastNeeded[32];
@@ -807,8 +823,10 @@ int nbnxm_b200_do_force_step_pipelined(nbnxm_b200_t* nb, int step, const nbnxm_b
         cudaStream_t ks = (n & 1) ? nb->pipeKernelStream : st;
         for (int c = 0; c < nchunks; c++)
             if (chunk_needs[k] & (1u << c)) CU(cudaStreamWaitEvent(ks, nb->chunkH2D[c], 0));
+        if (tl) CU(cudaEventRecord(nb->tlEvents[4 * k + 1], ks));
         if (launchKernelRange(nb, chunk_first_sci[k], chunk_first_sci[k + 1] - chunk_first_sci[k], e, v, ks)) return 1;
         CU(cudaEventRecord(nb->chunkKernel[k], ks));
+        if (tl) CU(cudaEventRecord(nb->tlEvents[4 * k + 2], ks));
     }
     /* what follows on the local stream (rolling prune, energy copies) comes after every chunk kernel */
     for (int n = 1; n < nchunks; n += 2) CU(cudaStreamWaitEvent(st, nb->chunkKernel[order[n]], 0));
@@ -837,6 +855,7 @@ int nbnxm_b200_do_force_step_pipelined(nbnxm_b200_t* nb, int step, const nbnxm_b
             CU(cudaMemcpyAsync(f_host + 3 * size_t(first), nb->f3.p + 3 * size_t(first), sizeof(float) * 3 * count,
                                cudaMemcpyDeviceToHost, nb->d2hStream));
         }
+        if (tl) CU(cudaEventRecord(nb->tlEvents[4 * c + 3], nb->d2hStream));
     }
     CU(cudaEventRecord(nb->pipeD2HDone, nb->d2hStream));
     if (fl->dynamic_pruning && step % 2 == 1)
@@ -1027,6 +1046,27 @@ int nbnxm_b200_get_device_buffers(nbnxm_b200_t* nb, float** d_xq, float** d_f, i
     if (natoms) *natoms = nb->natoms;
     return 0;
 }
+int nbnxm_b200_set_pipeline_timeline(nbnxm_b200_t* nb, int enable)
+{
+    if (!nb) return fail("null handle");
+    nb->pipeTimeline = enable != 0;
+    return 0;
+}
+
+int nbnxm_b200_get_pipeline_timeline(nbnxm_b200_t* nb, int max_chunks, int* nchunks, float* ms)
+{
+    if (!nb || !nchunks || !ms) return fail("nbnxm_b200_get_pipeline_timeline: null argument");
+    if (!nb->tlStart || nb->tlChunks == 0 || nb->tlChunks > max_chunks) return fail("nbnxm_b200_get_pipeline_timeline: no timeline recorded");
+    CU(cudaSetDevice(nb->device));
+    CU(cudaDeviceSynchronize());
+    *nchunks = nb->tlChunks;
+    for (int n = 0; n < 4 * nb->tlChunks; n++)
+    {
+        CU(cudaEventElapsedTime(ms + n, nb->tlStart, nb->tlEvents[n]));
+    }
+    return 0;
+}
+
 int nbnxm_b200_get_shared_outputs(nbnxm_b200_t* nb, float** d_f, float** d_fshift)
 {
     if (!nb) return fail("null handle");

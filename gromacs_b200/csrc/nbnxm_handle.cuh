@@ -165,6 +165,12 @@ struct nbnxm_b200
     cudaStream_t             h2dStream = nullptr, d2hStream = nullptr, pipeKernelStream = nullptr;
     std::vector<cudaEvent_t> chunkH2D, chunkKernel;
     cudaEvent_t              pipeStart = nullptr, pipeD2HDone = nullptr;
+    /* optional timeline of one pipelined step (nbnxm_b200_set_pipeline_timeline): per chunk the ends of its H2D copy, the start
+     * and end of its kernel and the end of its D2H copy, as timing events against tlStart */
+    bool                     pipeTimeline = false;
+    int                      tlChunks     = 0;
+    cudaEvent_t              tlStart      = nullptr;
+    std::vector<cudaEvent_t> tlEvents; /* 4 per chunk */
 
     /* perturbed (FEP) pair kernels, nbnxm_fep.cu: end-state atom data, pair lists, coupling parameters, dV/dlambda */
     struct FepList

@@ -24,7 +24,7 @@ VDW_TYPES = {"Cut": 0, "CutCombGeom": 1, "CutCombLB": 2, "FSwitch": 3, "PSwitch"
 
 # every symbol include/nbnxm_b200.h declares
 EXPORTED_SYMBOLS = [
-    "nbnxm_b200_last_error", "nbnxm_b200_init", "nbnxm_b200_free", "nbnxm_b200_update_params", "nbnxm_b200_do_force_step", "nbnxm_b200_do_force_step_pipelined", "nbnxm_b200_peer_blob_size", "nbnxm_b200_peer_export", "nbnxm_b200_peer_import",
+    "nbnxm_b200_last_error", "nbnxm_b200_init", "nbnxm_b200_free", "nbnxm_b200_update_params", "nbnxm_b200_do_force_step", "nbnxm_b200_do_force_step_pipelined", "nbnxm_b200_set_pipeline_timeline", "nbnxm_b200_get_pipeline_timeline", "nbnxm_b200_peer_blob_size", "nbnxm_b200_peer_export", "nbnxm_b200_peer_import",
     "nbnxm_b200_peer_close", "nbnxm_b200_peer_error",
     "nbnxm_b200_init_pairlist", "nbnxm_b200_init_pairlist_device", "nbnxm_b200_init_atomdata", "nbnxm_b200_init_atomdata_device", "nbnxm_b200_upload_shiftvec",
     "nbnxm_b200_copy_xq_to_gpu", "nbnxm_b200_init_x_to_nbat_x", "nbnxm_b200_x_to_nbat_x",
@@ -346,6 +346,16 @@ class NbnxmGpu:
         self._check(self._lib.nbnxm_b200_do_force_step_pipelined(
             self._h, C.c_int(step), C.byref(fl), _ptr(xq_host, C.c_float), _ptr(f_host, C.c_float), C.c_int(plan.nchunks),
             _ptr(plan.first_atom, C.c_int), _ptr(plan.first_sci, C.c_int), _ptr(plan.needs, C.c_uint32)))
+
+    def set_pipeline_timeline(self, enable=True):
+        self._check(self._lib.nbnxm_b200_set_pipeline_timeline(self._h, C.c_int(int(enable))))
+
+    def pipeline_timeline(self):
+        """float32[nchunks, 4]: H2D end, kernel start, kernel end, D2H end of each chunk of the last pipelined step, in ms"""
+        ms = np.zeros((32, 4), np.float32)
+        n = C.c_int(0)
+        self._check(self._lib.nbnxm_b200_get_pipeline_timeline(self._h, C.c_int(32), C.byref(n), _ptr(ms, C.c_float)))
+        return ms[:n.value].copy()
 
     def gpu_clear_outputs(self, computeVirial=True):
         self._check(self._lib.nbnxm_b200_clear_outputs(self._h, C.c_int(int(computeVirial))))

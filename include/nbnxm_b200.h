@@ -327,6 +327,11 @@ int nbnxm_b200_do_force_step(nbnxm_b200_t* nb, int step, const nbnxm_b200_step_f
 int nbnxm_b200_do_force_step_pipelined(nbnxm_b200_t* nb, int step, const nbnxm_b200_step_flags_t* flags, const float* xq_host,
                                        float* f_host, int nchunks, const int* chunk_first_atom, const int* chunk_first_sci,
                                        const unsigned int* chunk_needs);
+/* Diagnostics: with the timeline enabled, a pipelined step records CUDA timing events per chunk; get_pipeline_timeline
+ * synchronises the device and returns, for each of *nchunks chunks, ms[4 * c + 0..3] = end of its H2D copy, start and end of
+ * its force kernel, end of its D2H copy, in ms after the start of the step. */
+int nbnxm_b200_set_pipeline_timeline(nbnxm_b200_t* nb, int enable);
+int nbnxm_b200_get_pipeline_timeline(nbnxm_b200_t* nb, int max_chunks, int* nchunks, float* ms);
 
 #ifdef __cplusplus
 }
