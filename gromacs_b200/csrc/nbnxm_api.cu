@@ -322,11 +322,12 @@ int nbnxm_b200_free(nbnxm_b200_t* nb)
     for (cudaEvent_t ev : nb->chunkKernel) cudaEventDestroy(ev);
     if (nb->pipeStart) cudaEventDestroy(nb->pipeStart);
     if (nb->tlStart) cudaEventDestroy(nb->tlStart);
+    if (nb->pipePruneDone) cudaEventDestroy(nb->pipePruneDone);
     for (cudaEvent_t ev : nb->tlEvents) cudaEventDestroy(ev);
     if (nb->pipeD2HDone) cudaEventDestroy(nb->pipeD2HDone);
     if (nb->h2dStream) cudaStreamDestroy(nb->h2dStream);
     if (nb->d2hStream) cudaStreamDestroy(nb->d2hStream);
-    if (nb->pipeKernelStream) cudaStreamDestroy(nb->pipeKernelStream);
+    for (cudaStream_t ps : nb->pipeKernelStream) if (ps) cudaStreamDestroy(ps);
     if (nb->h_fshift) cudaFreeHost(nb->h_fshift);
     if (nb->h_fshiftShared) cudaFreeHost(nb->h_fshiftShared);
     nb->fshiftShared.release();
@@ -613,12 +614,20 @@ int nbnxm_b200_reduce_f(nbnxm_b200_t* nb, float* d_f_total, const float* d_rvec_
     return 0;
 }
 
+static int launchPruneOnly(nbnxm_b200_t* nb, int iloc, int num_parts, cudaStream_t other);
+
 int nbnxm_b200_launch_kernel_pruneonly(nbnxm_b200_t* nb, int iloc, int num_parts)
+{
+    return launchPruneOnly(nb, iloc, num_parts, nullptr);
+}
+
+/* on `other` instead of the locality's own stream when given (the pipelined step overlaps the rolling prune with its force kernels) */
+static int launchPruneOnly(nbnxm_b200_t* nb, int iloc, int num_parts, cudaStream_t other)
 {
     if (!nb || iloc < 0 || iloc > 1 || num_parts < 1) return fail("nbnxm_b200_launch_kernel_pruneonly: bad argument");
     CU(cudaSetDevice(nb->device));
     PairList&    pl = nb->plist[iloc];
-    cudaStream_t st = nb->stream[iloc];
+    cudaStream_t st = other ? other : nb->stream[iloc];
     if (pl.haveFreshList)
     {
         if (num_parts != 1) return fail("With first pruning we expect 1 part");
@@ -762,7 +771,10 @@ int nbnxm_b200_do_force_step_pipelined(nbnxm_b200_t* nb, int step, const nbnxm_b
     {
         CU(cudaStreamCreateWithFlags(&nb->h2dStream, cudaStreamNonBlocking));
         CU(cudaStreamCreateWithFlags(&nb->d2hStream, cudaStreamNonBlocking));
-        CU(cudaStreamCreateWithFlags(&nb->pipeKernelStream, cudaStreamNonBlocking));
+        for (cudaStream_t& ps : nb->pipeKernelStream) CU(cudaStreamCreateWithFlags(&ps, cudaStreamNonBlocking));
+        /* streams the chunk kernels rotate over: 2 (default) ... 4, NBNXM_B200_PIPE_STREAMS for A/B runs */
+        const char* ns       = getenv("NBNXM_B200_PIPE_STREAMS");
+        nb->pipeKernelStreams = ns ? std::max(1, std::min(3, atoi(ns) - 1)) : 1;
         CU(cudaEventCreateWithFlags(&nb->pipeStart, cudaEventDisableTiming));
         CU(cudaEventCreateWithFlags(&nb->pipeD2HDone, cudaEventDisableTiming));
     }
@@ -803,6 +815,18 @@ int nbnxm_b200_do_force_step_pipelined(nbnxm_b200_t* nb, int step, const nbnxm_b
         CU(cudaEventRecord(nb->chunkH2D[c], nb->h2dStream));
         if (tl) CU(cudaEventRecord(nb->tlEvents[4 * c], nb->h2dStream));
     }
+    /* The rolling prune of this step goes behind the last coordinate copy on the copy stream, i.e. next to the force kernels
+     * instead of after them, where it would sit between the last kernel and the last force copies.  Running it while force
+     * kernels read the same masks is safe: it only drops cluster pairs whose atom pairs are all beyond rlistInner >= the
+     * cut-off at these very coordinates, or re-admits pairs that came inside rlistInner - a kernel that sees a mask word
+     * before or after the update evaluates the same interactions within the cut-off; mask words are written whole. */
+    const bool pruneThisStep = fl->dynamic_pruning && step % 2 == 1;
+    if (pruneThisStep)
+    {
+        if (!nb->pipePruneDone) CU(cudaEventCreateWithFlags(&nb->pipePruneDone, cudaEventDisableTiming));
+        if (launchPruneOnly(nb, 0, fl->rolling_prune_parts, nb->h2dStream)) return 1;
+        CU(cudaEventRecord(nb->pipePruneDone, nb->h2dStream));
+    }
     /* sci chunks in the order in which their coordinates are complete: by the last atom chunk they need */
     int order[32], lastNeeded[32];
     for (int k = 0; k < nchunks; k++)
@@ -816,11 +840,12 @@ int nbnxm_b200_do_force_step_pipelined(nbnxm_b200_t* nb, int step, const nbnxm_b
         for (int b = a; b > 0 && lastNeeded[order[b]] < lastNeeded[order[b - 1]]; b--) std::swap(order[b], order[b - 1]);
     /* the chunk kernels alternate between two streams so that the tail of one overlaps the head of the next (their
      * force reductions are atomic) */
-    CU(cudaStreamWaitEvent(nb->pipeKernelStream, nb->pipeStart, 0));
+    for (int i = 0; i < nb->pipeKernelStreams; i++) CU(cudaStreamWaitEvent(nb->pipeKernelStream[i], nb->pipeStart, 0));
     for (int n = 0; n < nchunks; n++)
     {
         const int    k  = order[n];
-        cudaStream_t ks = (n & 1) ? nb->pipeKernelStream : st;
+        const int    slot = n % (nb->pipeKernelStreams + 1);
+        cudaStream_t ks   = slot == 0 ? st : nb->pipeKernelStream[slot - 1];
         for (int c = 0; c < nchunks; c++)
             if (chunk_needs[k] & (1u << c)) CU(cudaStreamWaitEvent(ks, nb->chunkH2D[c], 0));
         if (tl) CU(cudaEventRecord(nb->tlEvents[4 * k + 1], ks));
@@ -829,7 +854,8 @@ int nbnxm_b200_do_force_step_pipelined(nbnxm_b200_t* nb, int step, const nbnxm_b
         if (tl) CU(cudaEventRecord(nb->tlEvents[4 * k + 2], ks));
     }
     /* what follows on the local stream (rolling prune, energy copies) comes after every chunk kernel */
-    for (int n = 1; n < nchunks; n += 2) CU(cudaStreamWaitEvent(st, nb->chunkKernel[order[n]], 0));
+    for (int n = 0; n < nchunks; n++)
+        if (n % (nb->pipeKernelStreams + 1) != 0) CU(cudaStreamWaitEvent(st, nb->chunkKernel[order[n]], 0));
     /* forces of an atom chunk are final once every sci chunk that touches it has run: atom chunks in that order */
     int position[32], readyAt[32], chunkOrder[32];
     for (int n = 0; n < nchunks; n++) position[order[n]] = n;
@@ -858,10 +884,7 @@ int nbnxm_b200_do_force_step_pipelined(nbnxm_b200_t* nb, int step, const nbnxm_b
         if (tl) CU(cudaEventRecord(nb->tlEvents[4 * c + 3], nb->d2hStream));
     }
     CU(cudaEventRecord(nb->pipeD2HDone, nb->d2hStream));
-    if (fl->dynamic_pruning && step % 2 == 1)
-    {
-        if (nbnxm_b200_launch_kernel_pruneonly(nb, 0, fl->rolling_prune_parts)) return 1;
-    }
+    if (pruneThisStep) CU(cudaStreamWaitEvent(st, nb->pipePruneDone, 0));
     if (v) CU(cudaMemcpyAsync(nb->h_fshift, nb->fshift.p, sizeof(double) * 3 * c_numShiftVectors, cudaMemcpyDeviceToHost, st));
     if (e) CU(cudaMemcpyAsync(nb->h_energy, nb->energy.p, sizeof(double) * 2, cudaMemcpyDeviceToHost, st));
     /* gpu_wait_finish_task synchronises the local stream: make it cover the force copies */

@@ -396,6 +396,13 @@ __device__ __forceinline__ V pair_w(const ParamsDev&    p,
     return W;
 }
 
+/* Staging of the cjPacked groups of an entry: through the bulk-copy engine (cp.async.bulk + mbarrier, two-stage ring; the
+ * default - north star: "staged in shared memory via TMA or cp.async.bulk") or, with -DNBNXM_PACKED_LDG_DESC, by coalesced
+ * 16-byte loads + st.shared of all lanes.  A/B on a B200 (profiles/r02k_*): 12.3 M atoms 12 847.5 -> 12 835.9 us, 1.5 M atoms
+ * 1096.4 -> 1096.2 us, 96 k atoms F+E 176.0 -> 173.2 us; long_scoreboard 0.12 -> 0.08 per issue, +0.7 % instructions. */
+#if !defined(NBNXM_PACKED_LDG_DESC) && !defined(NBNXM_PACKED_TMA_DESC)
+#    define NBNXM_PACKED_TMA_DESC 1
+#endif
 constexpr int c_descChunk = 64; /* cjPacked groups staged in shared memory at a time */
 constexpr int c_fjRow = 9; /* float4 per j-atom slot in PackedShared::fj: 8 partial forces + 1 of padding */
 
@@ -419,7 +426,47 @@ struct PackedShared
     float nbC12[c_packedMaxTypes * c_packedMaxTypes];
     /* the cjPacked groups of the current chunk of the sci entry, as in the list: cj[4], (imask, excl_ind) x 2 */
     uint4 desc[2 * c_descChunk];
+#ifdef NBNXM_PACKED_TMA_DESC
+    /* one mbarrier per half of desc: the halves form a two-stage ring filled by cp.async.bulk */
+    unsigned long long descBar[2];
+#endif
 };
+
+#ifdef NBNXM_PACKED_TMA_DESC
+/* The cjPacked groups of an entry reach shared memory through the bulk-copy engine: cp.async.bulk global -> shared with
+ * mbarrier completion, two stages of c_descStage groups, issued by one lane, the first two stages as soon as the entry is
+ * known (before the i-atoms are staged). */
+constexpr int c_descStage = c_descChunk / 2;
+__device__ __forceinline__ void mbar_init(const unsigned bar, const unsigned count)
+{
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(bar), "r"(count) : "memory");
+}
+__device__ __forceinline__ void mbar_fence_init()
+{
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+}
+__device__ __forceinline__ void bulk_load(const unsigned dst, const void* src, const unsigned bytes, const unsigned bar)
+{
+    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar), "r"(bytes) : "memory");
+    asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(dst), "l"(src),
+                 "r"(bytes), "r"(bar)
+                 : "memory");
+}
+__device__ __forceinline__ void mbar_wait(const unsigned bar, const unsigned parity)
+{
+    asm volatile(
+            "{\n"
+            ".reg .pred p;\n"
+            "NBNXM_MBAR_WAIT:\n"
+            "mbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1;\n"
+            "@p bra NBNXM_MBAR_DONE;\n"
+            "bra NBNXM_MBAR_WAIT;\n"
+            "NBNXM_MBAR_DONE:\n"
+            "}\n" ::"r"(bar),
+            "r"(parity)
+            : "memory");
+}
+#endif
 
 /* 32-bit shared-memory addresses and explicit ld/st.shared: with generic pointers into the shared struct ptxas
  * re-derives the shared window base (S2UR SR_CgaCtaId, ULEA) and the lane offsets in front of the accesses of every
@@ -799,6 +846,25 @@ __global__ void __launch_bounds__(32, ENERGY ? NBNXM_PACKED_MIN_BLOCKS_ENERGY : 
             __shfl_sync(c_full, smem_u32(reinterpret_cast<float*>(sm.jxy) + ((lane >> 3) * 4 + (lane & 3)) * 4 + ((lane >> 2) & 1)), lane);
     /* the cjPacked groups of the current chunk: cj[4], then (imask, excl_ind) x 2 */
     const unsigned descAddr = __shfl_sync(c_full, smem_u32(sm.desc), lane);
+#ifdef NBNXM_PACKED_TMA_DESC
+    const unsigned barAddr   = __shfl_sync(c_full, smem_u32(sm.descBar), lane);
+    const int      numStages = (s.cj_packed_end - s.cj_packed_begin + c_descStage - 1) / c_descStage;
+    auto           issueStage = [&](const int c) {
+        const int begin = s.cj_packed_begin + c * c_descStage;
+        const int n     = min(c_descStage, s.cj_packed_end - begin);
+        bulk_load(descAddr + (c & 1) * (32 * c_descStage), pl.cjPacked + begin, 32u * n, barAddr + 8 * (c & 1));
+    };
+    if (lane == 0)
+    {
+        mbar_init(barAddr, 1);
+        mbar_init(barAddr + 8, 1);
+        mbar_fence_init();
+        /* the first two stages are on their way while the i-atoms are staged */
+        if (numStages > 0) issueStage(0);
+        if (numStages > 1) issueStage(1);
+    }
+    __syncwarp();
+#endif
     /* il and jl can be read back from the low bits of these addresses (the struct is 128-byte aligned): cheaper than
      * holding them in registers for the few places that need them */
 #define NBNXM_IL_FROM_ADDR ((xqiAddr >> 4) & 7u)
@@ -872,27 +938,38 @@ __global__ void __launch_bounds__(32, ENERGY ? NBNXM_PACKED_MIN_BLOCKS_ENERGY : 
      * so that masks and j-cluster indices of the coming groups are a shared-memory read away.  Within a chunk the
      * 32 j-atoms of a group - lane L fetches atom (L & 7) of j-cluster (L >> 3), one coalesced 16-byte load per lane -
      * and the exclusion mask words are fetched one group ahead. */
+#ifdef NBNXM_PACKED_TMA_DESC
+    for (int stageIdx = 0; stageIdx < numStages; stageIdx++)
+    {
+        const int      chunkBegin = s.cj_packed_begin + stageIdx * c_descStage;
+        const int      numInChunk = min(c_descStage, s.cj_packed_end - chunkBegin);
+        const unsigned descCur    = descAddr + (stageIdx & 1) * (32 * c_descStage);
+        (void)cjGroups;
+        mbar_wait(barAddr + 8 * (stageIdx & 1), (stageIdx >> 1) & 1);
+#else
     for (int chunkBegin = s.cj_packed_begin; chunkBegin < s.cj_packed_end; chunkBegin += c_descChunk)
     {
-        const int numInChunk = min(c_descChunk, s.cj_packed_end - chunkBegin);
+        const int      numInChunk = min(c_descChunk, s.cj_packed_end - chunkBegin);
+        const unsigned descCur    = descAddr;
         __syncwarp();
         for (int t = lane; t < 2 * numInChunk; t += 32)
         {
             sts128u(descAddr + 16 * t, cjGroups[2 * chunkBegin + t]);
         }
         __syncwarp();
+#endif
 
         float4   xjNext = make_float4(0.0f, 0.0f, 0.0f, 0.0f);
         float2   pjNext = make_float2(0.0f, 0.0f);
         unsigned wex0Next = c_full, wex1Next = c_full;
         bool     fetchedNext = false;
         auto     fetchGroup = [&](const int g) {
-            const uint4 me = lds128u(descAddr + 32 * g + 16);
+            const uint4 me = lds128u(descCur + 32 * g + 16);
             /* unused slots of a partially filled group have no mask bits and an unspecified index */
             fetchedNext = (((me.x | me.z) >> (8u * NBNXM_JL_FROM_ADDR)) & 0xffu) != 0u;
             if (fetchedNext)
             {
-                const int aj = lds32i(descAddr + 32 * g + 4u * NBNXM_JL_FROM_ADDR) * c_clusterSize + NBNXM_IL_FROM_ADDR;
+                const int aj = lds32i(descCur + 32 * g + 4u * NBNXM_JL_FROM_ADDR) * c_clusterSize + NBNXM_IL_FROM_ADDR;
                 xjNext       = ad.xqJ[aj];
                 if (Fl::ljComb)
                 {
@@ -919,7 +996,7 @@ __global__ void __launch_bounds__(32, ENERGY ? NBNXM_PACKED_MIN_BLOCKS_ENERGY : 
 
         for (int g = 0; g < numInChunk; g++)
         {
-            const uint4    mev   = lds128u(descAddr + 32 * g + 16);
+            const uint4    mev   = lds128u(descCur + 32 * g + 16);
             const unsigned wex0 = wex0Next, wex1 = wex1Next;
             const bool     fetched = fetchedNext;
             __syncwarp();
@@ -1091,7 +1168,7 @@ __global__ void __launch_bounds__(32, ENERGY ? NBNXM_PACKED_MIN_BLOCKS_ENERGY : 
                 if (mEx != 0u)
                 {
                     /* the i-cluster this j-cluster is, if any */
-                    const int ciDiag = lds32i(descAddr + 32 * g + 4 * jm) - s.sci * c_superClusterSize;
+                    const int ciDiag = lds32i(descCur + 32 * g + 4 * jm) - s.sci * c_superClusterSize;
                     /* j <= i within the same cluster on the central shift: the "Newton" half of the diagonal cluster
                      * pair and the self pair (nbnxm_cuda_kernel.cuh:421-423) */
                     const bool selfLo = centralShift && NBNXM_JL_FROM_ADDR <= NBNXM_IL_FROM_ADDR;
@@ -1169,11 +1246,16 @@ __global__ void __launch_bounds__(32, ENERGY ? NBNXM_PACKED_MIN_BLOCKS_ENERGY : 
                         sz += v.z;
                     }
                     /* the atom this lane fetched for the group */
-                    const int ajOwn = lds32i(descAddr + 32 * g + 4u * NBNXM_JL_FROM_ADDR) * c_clusterSize + NBNXM_IL_FROM_ADDR;
+                    const int ajOwn = lds32i(descCur + 32 * g + 4u * NBNXM_JL_FROM_ADDR) * c_clusterSize + NBNXM_IL_FROM_ADDR;
                     red_add_v4(ad.f4J + ajOwn, -sx, -sy, -sz);
                 }
             }
         }
+#ifdef NBNXM_PACKED_TMA_DESC
+        /* every lane is done with this stage: refill it with the stage after the next */
+        __syncwarp();
+        if (lane == 0 && stageIdx + 2 < numStages) issueStage(stageIdx + 2);
+#endif
     }
 
     /* i forces: reduce over the 4 jl-lanes, one v4 reduction per i-atom; shift force from the per-lane partial

@@ -459,6 +459,119 @@ int nbnxm_b200_gpu_search_build(nbnxm_b200_gpu_search_t* s, int iloc, float rlis
     return 0;
 }
 
+/* ---- x-slab lists on the device (multi-GPU search step without the host) ---- */
+
+namespace nbb
+{
+/* global bin / cluster indices -> one rank's order (home bins first, then halo bins): nbnxm_b200_pairlist_reindex on the device */
+__global__ void __launch_bounds__(256) search_reindex_kernel(nbnxm_b200_sci_t* __restrict__ sci, int nsci, nbnxm_b200_cj_packed_t* __restrict__ cjp,
+                                                             int ncjp, int firstHomeBin, long long cjOffset, int numClustersTotal)
+{
+    const int i = blockIdx.x * 256 + threadIdx.x;
+    if (i < nsci)
+    {
+        sci[i].sci -= firstHomeBin;
+    }
+    if (i < ncjp)
+    {
+#pragma unroll
+        for (int jm = 0; jm < 4; jm++)
+        {
+            /* unused slots of partially filled j-groups carry no mask bits and an unspecified index: keep them loadable */
+            const long long cj = static_cast<long long>(cjp[i].cj[jm]) + cjOffset;
+            cjp[i].cj[jm]      = static_cast<int>(cj < 0 ? 0 : (cj > numClustersTotal - 1 ? numClustersTotal - 1 : cj));
+        }
+    }
+}
+} // namespace nbb
+
+int nbnxm_b200_gpu_search_gather_slab(nbnxm_b200_gpu_search_t* s, nbnxm_b200_t* target, int home_begin, int home_end, int halo_begin,
+                                      int halo_end)
+{
+    if (!s || !target || !s->st.haveGrid) return fail("nbnxm_b200_gpu_search_gather_slab: bad argument");
+    const nbs::Grid& g = s->st.g;
+    if (home_begin < 0 || home_end > g.nbins || home_begin > home_end || halo_begin < 0 || halo_end > g.nbins || halo_begin > halo_end)
+    {
+        return fail("nbnxm_b200_gpu_search_gather_slab: bin range");
+    }
+    nbnxm_b200* nb = s->nb;
+    if (nb->device != target->device) return fail("nbnxm_b200_gpu_search_gather_slab: both handles must live on the same device");
+    CU(cudaSetDevice(nb->device));
+    const int nhome = (home_end - home_begin) * nbs::c_binAtoms, nhalo = (halo_end - halo_begin) * nbs::c_binAtoms;
+    if (nbnxm_b200_init_atomdata_device(target, nhome + nhalo, nhome)) return 1;
+    CU(cudaStreamSynchronize(s->be.st)); /* the gridding wrote the source arrays on the search stream */
+    cudaStream_t st = target->stream[0];
+    struct Range
+    {
+        int src, dst, n;
+    } ranges[2] = { { home_begin * nbs::c_binAtoms, 0, nhome }, { halo_begin * nbs::c_binAtoms, nhome, nhalo } };
+    for (const Range& r : ranges)
+    {
+        if (r.n == 0) continue;
+        CU(cudaMemcpyAsync(target->xq.p + r.dst, nb->xq.p + r.src, sizeof(float4) * r.n, cudaMemcpyDeviceToDevice, st));
+        if (nb->atomType.p && target->atomType.p)
+        {
+            CU(cudaMemcpyAsync(target->atomType.p + r.dst, nb->atomType.p + r.src, sizeof(int) * r.n, cudaMemcpyDeviceToDevice, st));
+        }
+        if (nb->ljComb.p && target->ljComb.p)
+        {
+            CU(cudaMemcpyAsync(target->ljComb.p + r.dst, nb->ljComb.p + r.src, sizeof(float2) * r.n, cudaMemcpyDeviceToDevice, st));
+        }
+    }
+    CU(cudaStreamSynchronize(st));
+    return 0;
+}
+
+int nbnxm_b200_gpu_search_build_slab(nbnxm_b200_gpu_search_t* s, nbnxm_b200_t* target, int iloc, float rlist, int min_sci, int home_begin,
+                                     int home_end, int halo_begin, int halo_end, int required_tx)
+{
+    if (!s || !target || iloc < 0 || iloc > 1) return fail("nbnxm_b200_gpu_search_build_slab: bad argument");
+    if (!s->st.haveGrid) return fail("nbnxm_b200_gpu_search_build_slab: put the atoms on the grid first");
+    const nbs::Grid& g = s->st.g;
+    if (home_begin < 0 || home_end > g.nbins || home_begin > home_end || halo_begin < 0 || halo_end > g.nbins || halo_begin > halo_end)
+    {
+        return fail("nbnxm_b200_gpu_search_build_slab: bin range");
+    }
+    for (int d = 0; d < 3; d++)
+    {
+        if (2 * rlist >= g.box[d]) return fail("nbnxm_b200_gpu_search_build_slab: rlist %g must be shorter than half the box (%g)", rlist, g.box[d]);
+    }
+    nbnxm_b200* nb = s->nb;
+    if (nb->device != target->device) return fail("nbnxm_b200_gpu_search_build_slab: both handles must live on the same device");
+    CU(cudaSetDevice(nb->device));
+    CU(cudaEventRecord(s->evStart, s->be.st));
+    /* local: home x home, half shell; non-local: home x halo, every y / z shift, the periodic x image in required_tx */
+    const int jLo = iloc == 0 ? home_begin : halo_begin, jHi = iloc == 0 ? home_end : halo_end;
+    if (nbs::buildPairlist(s->be, s->st, reinterpret_cast<const nbs::XQ*>(nb->xq.p), rlist, min_sci, home_begin, home_end, jLo, jHi,
+                           iloc == 1 ? 1 : 0, iloc == 1 ? required_tx : 0))
+    {
+        return 1;
+    }
+    const int       numHome  = home_end - home_begin;
+    const int       ncl      = (numHome + (halo_end - halo_begin)) * nbs::c_binCl;
+    const long long cjOffset = iloc == 1 ? static_cast<long long>(numHome - halo_begin) * nbs::c_binCl
+                                         : -static_cast<long long>(home_begin) * nbs::c_binCl;
+    const int       n        = s->st.nsci > s->st.ncjp ? s->st.nsci : s->st.ncjp;
+    if (n > 0)
+    {
+        nbb::search_reindex_kernel<<<(n + 255) / 256, 256, 0, s->be.st>>>(s->st.sci.p, s->st.nsci, s->st.cjp.p, s->st.ncjp, home_begin,
+                                                                          cjOffset, ncl);
+        s->be.launches++;
+    }
+    CU(cudaEventRecord(s->evStop, s->be.st));
+    CU(cudaStreamSynchronize(s->be.st));
+    CU(cudaGetLastError());
+    CU(cudaEventElapsedTime(&s->lastBuildMs, s->evStart, s->evStop));
+    target->launches += s->be.launches;
+    s->be.launches = 0;
+    if (nbnxm_b200_init_pairlist_device(target, iloc, s->st.sci.p, s->st.nsci, s->st.cjp.p, s->st.ncjp, s->st.excl.p, s->st.nexcl, nbs::c_cl))
+    {
+        return 1;
+    }
+    CU(cudaStreamSynchronize(target->stream[iloc]));
+    return 0;
+}
+
 int nbnxm_b200_gpu_search_sizes(const nbnxm_b200_gpu_search_t* s, int* nsci, int* ncj_packed, int* nexcl, long long* ncluster_pairs,
                                 float* build_ms)
 {

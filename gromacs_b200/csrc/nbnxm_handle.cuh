@@ -162,9 +162,11 @@ struct nbnxm_b200
     long long                launches     = 0;
 
     /* copy streams and events of the chunk-pipelined step (nbnxm_b200_do_force_step_pipelined), created on first use */
-    cudaStream_t             h2dStream = nullptr, d2hStream = nullptr, pipeKernelStream = nullptr;
+    cudaStream_t             h2dStream = nullptr, d2hStream = nullptr;
+    cudaStream_t             pipeKernelStream[3] = { nullptr, nullptr, nullptr }; /* the chunk kernels rotate over the local stream and these */
+    int                      pipeKernelStreams   = 1;                       /* how many of them are in use (NBNXM_B200_PIPE_STREAMS - 1) */
     std::vector<cudaEvent_t> chunkH2D, chunkKernel;
-    cudaEvent_t              pipeStart = nullptr, pipeD2HDone = nullptr;
+    cudaEvent_t              pipeStart = nullptr, pipeD2HDone = nullptr, pipePruneDone = nullptr;
     /* optional timeline of one pipelined step (nbnxm_b200_set_pipeline_timeline): per chunk the ends of its H2D copy, the start
      * and end of its kernel and the end of its D2H copy, as timing events against tlStart */
     bool                     pipeTimeline = false;

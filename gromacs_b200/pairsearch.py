@@ -18,6 +18,7 @@ SEARCH_SYMBOLS = [
     "nbnxm_b200_gpu_search_create", "nbnxm_b200_gpu_search_free", "nbnxm_b200_gpu_search_set_grid",
     "nbnxm_b200_gpu_search_build", "nbnxm_b200_gpu_search_sizes", "nbnxm_b200_gpu_search_download",
     "nbnxm_b200_gpu_search_set_atoms", "nbnxm_b200_gpu_search_put_atoms_on_grid", "nbnxm_b200_gpu_search_get_order",
+    "nbnxm_b200_gpu_search_gather_slab", "nbnxm_b200_gpu_search_build_slab",
 ]
 
 
@@ -194,6 +195,28 @@ class GpuPairSearch:
         self.build_ms, self.nci_tot, self.rlist = ms.value, ncp.value, rlist
         self._sizes = (nsci.value, ncj.value, nex.value)
         self._nb._set_list_sizes(iloc, nsci.value, ncj.value)
+        return self._sizes
+
+    def gather_slab(self, target, home, halo):
+        """Atom data of one x-slab (home bins, then halo bins) from this search object's whole-system grid into the rank's
+        handle `target`, device to device (nbnxm_b200_gpu_search_gather_slab)."""
+        self._nb._check(self._lib.nbnxm_b200_gpu_search_gather_slab(
+            self._s, target._h, C.c_int(home[0]), C.c_int(home[1]), C.c_int(halo[0]), C.c_int(halo[1])))
+        target._natoms = (home[1] - home[0] + halo[1] - halo[0]) * 64
+
+    def build_slab(self, target, iloc, rlist, home, halo, required_tx=0, min_sci=0):
+        """Local (iloc 0: home x home) or non-local (iloc 1: home x halo) list of one x-slab, built on the device from the
+        whole-system grid, re-indexed to the rank's order and installed in `target` (nbnxm_b200_gpu_search_build_slab);
+        returns (nsci, ncj_packed, nexcl)."""
+        self._nb._check(self._lib.nbnxm_b200_gpu_search_build_slab(
+            self._s, target._h, C.c_int(iloc), C.c_float(rlist), C.c_int(min_sci), C.c_int(home[0]), C.c_int(home[1]),
+            C.c_int(halo[0]), C.c_int(halo[1]), C.c_int(required_tx)))
+        nsci, ncj, nex, ncp, ms = C.c_int(), C.c_int(), C.c_int(), C.c_longlong(), C.c_float()
+        self._nb._check(self._lib.nbnxm_b200_gpu_search_sizes(self._s, C.byref(nsci), C.byref(ncj), C.byref(nex),
+                                                             C.byref(ncp), C.byref(ms)))
+        self.build_ms, self.nci_tot, self.rlist = ms.value, ncp.value, rlist
+        self._sizes = (nsci.value, ncj.value, nex.value)
+        target._set_list_sizes(iloc, nsci.value, ncj.value)
         return self._sizes
 
     def download(self) -> PairlistGpu:

@@ -25,3 +25,21 @@ def slab_bin_ranges(grid, nslabs, r, rlist):
         raise ValueError("slabs too thin for a one-sided halo (or bad arguments): %d slabs, rlist %g" % (nslabs, rlist))
     h0, h1, l0, l1, tx = [x.value for x in v]
     return (h0, h1), (l0, l1), tx
+
+
+def slab_bin_ranges_from_columns(box_x, ncx, ncy, first_bin_of_column, nslabs, r, rlist):
+    """slab_bin_ranges from the column table alone (e.g. GpuPairSearch.get_order() after gridding on the device): the same
+    arithmetic as nbnxm_b200_slab_bin_ranges (hostplan.cpp) without a host grid object."""
+    import math
+    fb = first_bin_of_column
+    if nslabs < 2:
+        return (0, int(fb[ncx * ncy])), (0, 0), 0
+    cx0, cx1 = slab_columns(ncx, nslabs, r)
+    nx0, nx1 = slab_columns(ncx, nslabs, (r + 1) % nslabs)
+    cell = float(box_x) / ncx
+    ncol_halo = min(nx1 - nx0, int(math.ceil(float(rlist) / cell)) + 1)
+    if nslabs == 2 and (cx1 - cx0) < 2 * ncol_halo:
+        raise ValueError("slabs too thin for a one-sided halo: %d slabs, rlist %g" % (nslabs, rlist))
+    home = (int(fb[cx0 * ncy]), int(fb[cx1 * ncy]))
+    halo = (int(fb[nx0 * ncy]), int(fb[(nx0 + ncol_halo) * ncy]))
+    return home, halo, (-1 if r == nslabs - 1 else 0)

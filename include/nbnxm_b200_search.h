@@ -129,6 +129,18 @@ int nbnxm_b200_gpu_search_get_order(nbnxm_b200_gpu_search_t* search, int* atom_i
  * the handle's list for iloc (haveFreshList set) */
 int nbnxm_b200_gpu_search_build(nbnxm_b200_gpu_search_t* search, int iloc, float rlist, int min_sci, int bin_begin,
                                 int bin_end, int j_bin_lo, int j_bin_hi, int inter_zone, int required_tx);
+/* The search step of one x-slab of a multi-GPU run on the device (what gromacs_b200/multigpu.py's make_slab_plan does with the
+ * host builder and nbnxm_b200_pairlist_reindex): `search` holds the grid of the whole system (put_atoms_on_grid with nslabs =
+ * the number of ranks); `target` is the rank's handle on the same device.
+ *   gather_slab: sizes target's atom buffers for (home bins + halo bins) * 64 atoms, home atoms local, and copies xq / types /
+ *                lj_comb of the two bin ranges there, device to device.
+ *   build_slab : iloc 0 = home x home (half shell), iloc 1 = home x halo (inter-zone mode, every y / z shift, required_tx = the
+ *                x shift of the i-atoms, -1 across the periodic boundary); the list is re-indexed to the rank's order on the
+ *                device and becomes target's list for iloc.  Bin ranges as nbnxm_b200_slab_bin_ranges gives them. */
+int nbnxm_b200_gpu_search_gather_slab(nbnxm_b200_gpu_search_t* search, nbnxm_b200_t* target, int home_begin, int home_end,
+                                      int halo_begin, int halo_end);
+int nbnxm_b200_gpu_search_build_slab(nbnxm_b200_gpu_search_t* search, nbnxm_b200_t* target, int iloc, float rlist, int min_sci,
+                                     int home_begin, int home_end, int halo_begin, int halo_end, int required_tx);
 /* sizes of the list built last, cluster pairs in it, device time of the build (ms, CUDA events) */
 int nbnxm_b200_gpu_search_sizes(const nbnxm_b200_gpu_search_t* search, int* nsci, int* ncj_packed, int* nexcl,
                                 long long* ncluster_pairs, float* build_ms);

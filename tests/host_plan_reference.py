@@ -47,7 +47,12 @@ def reindex(pl, first_home_bin, first_halo_bin, num_home_bins, nclusters_total, 
 def make_chunk_plan(grid, plist, nchunks):
     nchunks = int(max(1, min(nchunks, 32, grid.ncx)))
     fb = np.asarray(grid.first_bin_of_column)
-    cols = [(grid.ncx * c) // nchunks for c in range(nchunks + 1)]
+    # tapered widths: weights 1, 1, 2, 3, 4, ..., 4, 3, 2, 1, 1 with eight chunks or more (hostplan.cpp)
+    wsum = [0]
+    for c in range(nchunks):
+        d = min(c, nchunks - 1 - c)
+        wsum.append(wsum[-1] + (4 if nchunks < 8 else (1 if d < 2 else (2 if d == 2 else (3 if d == 3 else 4)))))
+    cols = [(grid.ncx * wsum[c]) // wsum[nchunks] for c in range(nchunks + 1)]
     first_bin = np.array([int(fb[cx * grid.ncy]) for cx in cols], dtype=np.int64)
     first_atom = (first_bin * 64).astype(np.int32)
     sci = np.ascontiguousarray(plist.sci).reshape(-1, 4)

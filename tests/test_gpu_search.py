@@ -343,3 +343,73 @@ def test_device_list_against_brute_force(oracle, name, rlist):
     f_bf, e_bf = oracle.brute_force(p, b.x, b.q, b.type, g.nbfp, g.nbfp_comb, b.box, b.excl_index, b.excl_atoms)
     assert relrms(f_list, f_bf) <= 1e-6, relrms(f_list, f_bf)
     assert abs(e_list[0] - e_bf[0]) <= 1e-6 * abs(e_bf[0]) and abs(e_list[1] - e_bf[1]) <= 1e-6 * abs(e_bf[1])
+
+
+@pytest.mark.parametrize("world", [2, 4])
+def test_device_slab_lists_equal_the_host_plan(world):
+    """The search step of a multi-GPU run without the host: the whole system gridded on the device, then for every rank its
+    atom data gathered and its local (home x home) and non-local (home x halo) lists built, re-indexed and installed on the
+    device (nbnxm_b200_gpu_search_gather_slab / _build_slab) - against gromacs_b200.multigpu.make_slab_plan, which does the
+    same with the host gridder, the host builder and nbnxm_b200_pairlist_reindex.  Lists entry for entry; forces of both
+    kernels on the device-built data against the host-built data (halo coordinates resident: one GPU plays every rank)."""
+    import torch
+    from gromacs_b200 import LOCAL, NONLOCAL, NbnxmGpu, StepWorkload
+    from gromacs_b200.multigpu import make_slab_plan
+    from gromacs_b200.pairsearch import GpuPairSearch
+    from gromacs_b200.slabs import slab_bin_ranges_from_columns
+    from gromacs_b200.workload import make_workload
+    wl = make_workload("water48k_test", nthreads=4, nslabs=world)
+    rlist, b = wl.cfg["rlist_outer"], wl.box
+    whole = NbnxmGpu(wl.params, wl.nbat)            # holds the grid of the whole system on the device
+    search = GpuPairSearch(whole)
+    search.set_atoms(b.q, b.type, wl.nbat.numTypes, wl.nbat.nbfp_comb, b.excl_index, b.excl_atoms)
+    x_dev = torch.from_numpy(np.ascontiguousarray(b.x, np.float32)).cuda()
+    torch.cuda.synchronize()
+    _, nbins, ncx, ncy = search.put_atoms_on_grid(b.box, x_dev.data_ptr(), nslabs=world)
+    _, first_bin, _ = search.get_order()
+    assert (ncx, ncy, nbins) == (wl.grid.ncx, wl.grid.ncy, wl.grid.nbins)
+    sw = StepWorkload()
+
+    def forces(nb, nbat):
+        nb.gpu_upload_shiftvec(nbat)
+        nb.setupGpuShortRangeWork(LOCAL)
+        nb.setupGpuShortRangeWork(NONLOCAL)
+        nb.gpu_clear_outputs(True)
+        nb.gpu_launch_kernel(sw, LOCAL)
+        nb.gpu_launch_kernel(sw, NONLOCAL)
+        nb.gpu_launch_cpyback(nbat, StepWorkload(useGpuFBufferOps=True), NONLOCAL)
+        nb.gpu_launch_cpyback(nbat, sw, LOCAL)
+        nb.gpu_wait_finish_task(sw, NONLOCAL)
+        nb.gpu_wait_finish_task(sw, LOCAL)
+        return nbat.f[:nbat.numLocalAtoms].astype(np.float64).copy()
+
+    try:
+        for rank in range(world):
+            plan = make_slab_plan(wl, rank, world, min_sci=2000)
+            home, halo, tx = slab_bin_ranges_from_columns(b.box[0], ncx, ncy, first_bin, world, rank, rlist)
+            assert (home, halo) == (plan.home_bins, plan.halo_bins)
+            # host path
+            nb_h = NbnxmGpu(wl.params, plan.nbat, bLocalAndNonlocal=True)
+            nb_h.gpu_init_atomdata(plan.nbat)
+            nb_h.gpu_init_pairlist(plan.local, LOCAL)
+            nb_h.gpu_init_pairlist(plan.nonlocal_, NONLOCAL)
+            nb_h.gpu_copy_xq_to_gpu(plan.nbat, LOCAL)
+            nb_h.gpu_copy_xq_to_gpu(plan.nbat, NONLOCAL)
+            f_host = forces(nb_h, plan.nbat)
+            nb_h.gpu_free()
+            # device path
+            nb_d = NbnxmGpu(wl.params, plan.nbat, bLocalAndNonlocal=True)
+            search.gather_slab(nb_d, home, halo)
+            sizes = search.build_slab(nb_d, LOCAL, rlist, home, halo, min_sci=2000)
+            assert sizes == (plan.local.sci.shape[0], plan.local.cjPacked.shape[0], plan.local.excl.shape[0])
+            got = search.download()
+            assert_same_list((got.sci, got.cjPacked, got.excl), (plan.local.sci, plan.local.cjPacked, plan.local.excl))
+            search.build_slab(nb_d, NONLOCAL, rlist, home, halo, required_tx=tx, min_sci=1000)
+            got = search.download()
+            assert_same_list((got.sci, got.cjPacked, got.excl), (plan.nonlocal_.sci, plan.nonlocal_.cjPacked, plan.nonlocal_.excl))
+            f_dev = forces(nb_d, plan.nbat)
+            nb_d.gpu_free()
+            assert relrms(f_dev, f_host) < 1e-6, (rank, relrms(f_dev, f_host))
+    finally:
+        search.free()
+        whole.gpu_free()
