@@ -296,6 +296,8 @@ def main():
                     help="N = 1: chunks of the pipelined end-to-end step (1 = plain copy-compute-copy sequence; "
                          "0 = one chunk per 250k atoms, at most 24: measured 22.0 / 17.9 / 15.9 / 14.9 / 14.9 ms per step "
                          "with 1 / 8 / 16 / 24 / 32 chunks on the 12.3 M-atom box)")
+    ap.add_argument("--slab-lists", default="device", choices=["device", "host"],
+                    help="N > 1: where the search step of every rank runs (device: gridding and both lists on the rank's GPU)")
     ap.add_argument("--halo", default="peer", choices=["peer", "nccl"],
                     help="N > 1: peer-memory halo over NVLink (no transport calls) or ncclSend/ncclRecv")
     args = ap.parse_args()

@@ -88,6 +88,93 @@ def make_slab_plan(wl, rank, nranks, min_sci=0):
                     nhome * 64, nhalo * 64, hs, ls)
 
 
+class _DeviceArray:
+    """__cuda_array_interface__ view of a raw float32 device buffer of the library"""
+
+    def __init__(self, ptr, shape):
+        self.__cuda_array_interface__ = {"shape": tuple(shape), "typestr": "<f4", "data": (int(ptr), False), "strides": None,
+                                         "version": 3}
+
+
+class DeviceSlabSearch:
+    """The search step of one rank without the host (the multi-GPU form of SURVEY 8f #1): the whole system is put on the grid
+    on this rank's GPU (nbnxm_b200_gpu_search_put_atoms_on_grid, 15 ms for 12.3 M atoms against 0.3 s on 16 host threads),
+    the rank's atoms (home bins, then the halo bins of the +x neighbour) are gathered into its handle and its local and
+    non-local lists are built, re-indexed and installed on the device (nbnxm_b200_gpu_search_gather_slab / _build_slab).
+    No rank grids or searches anything on the host; make_slab_plan (host gridder + host builder) stays as the reference the
+    tests compare this with (tests/test_gpu_search.py::test_device_slab_lists_equal_the_host_plan)."""
+
+    def __init__(self, wl, device):
+        import torch
+        from .pairsearch import GpuPairSearch
+        self.wl = wl
+        b = wl.box
+        self.whole = NbnxmGpu(wl.params, wl.nbat, device=device)
+        self.search = GpuPairSearch(self.whole)
+        self.search.set_atoms(b.q, b.type, wl.nbat.numTypes, wl.nbat.nbfp_comb, b.excl_index, b.excl_atoms)
+        self.x_dev = torch.from_numpy(np.ascontiguousarray(b.x, np.float32)).cuda()
+        torch.cuda.synchronize()
+
+    def search_step(self, nb, rank, nranks, min_sci=0):
+        """putAtomsOnGrid + constructPairlist(Local) + constructPairlist(NonLocal) + gpu_init_* of rank `rank` into handle `nb`;
+        returns the SlabPlan (ranges and host buffers; the lists stay on the device)."""
+        import torch
+        from .slabs import slab_bin_ranges_from_columns
+        wl, b = self.wl, self.wl.box
+        rlist = wl.cfg["rlist_outer"]
+        _, nbins, ncx, ncy = self.search.put_atoms_on_grid(b.box, self.x_dev.data_ptr(), nslabs=nranks)
+        _, first_bin, self.grid_ms = self.search.get_order()
+        home, halo, tx = slab_bin_ranges_from_columns(b.box[0], ncx, ncy, first_bin, nranks, rank, rlist)
+        _, halo_prev, _ = slab_bin_ranges_from_columns(b.box[0], ncx, ncy, first_bin, nranks, (rank - 1) % nranks, rlist)
+        if nranks > 1:
+            assert halo_prev[0] == home[0], "the -x neighbour's halo must start at our first column"
+        self.search.gather_slab(nb, home, halo)
+        self.list_ms = 0.0
+        self.search.build_slab(nb, LOCAL, rlist, home, halo, min_sci=min_sci)
+        self.list_ms += self.search.build_ms
+        self.search.build_slab(nb, NONLOCAL, rlist, home, halo, required_tx=tx, min_sci=min_sci // 2)
+        self.list_ms += self.search.build_ms
+        nhome, nhalo = home[1] - home[0], halo[1] - halo[0]
+        # the host's copy of the rank's coordinates in grid order (nbat->x()), for callers that keep x on the host
+        d_xq, _, n = nb.device_buffers()
+        xq = torch.as_tensor(_DeviceArray(d_xq, (n, 4)), device="cuda").cpu().numpy().copy()
+        g = wl.nbat
+        nbat = AtomData(xq=xq, type=None, lj_comb=None, nbfp=g.nbfp, nbfp_comb=g.nbfp_comb, numTypes=g.numTypes,
+                        shift_vec=g.shift_vec, numLocalAtoms=nhome * 64)
+        hs, ls = slice(home[0] * 64, home[1] * 64), slice(halo[0] * 64, halo[1] * 64)
+        return SlabPlan(rank, nranks, home, halo, nbat, None, None, 0, (halo_prev[1] - halo_prev[0]) * 64 if nranks > 1 else 0,
+                        nhome * 64, nhalo * 64, hs, ls)
+
+    def whole_system_forces(self, min_sci=0):
+        """single-domain F+E step of the whole system on this GPU (list built on the device, unpruned): forces in the global
+        grid order and (e_lj, e_el) - the reference of the multi-GPU parity figure"""
+        import copy
+        wl = self.wl
+        whole = self.whole
+        n = self.search.nbins * 64
+        f = np.zeros((n, 3), np.float32)
+        stub = AtomData(xq=np.zeros((n, 4), np.float32), nbfp=wl.nbat.nbfp, nbfp_comb=wl.nbat.nbfp_comb, numTypes=wl.nbat.numTypes,
+                        shift_vec=wl.nbat.shift_vec)
+        stub.f = f
+        p1 = copy.copy(wl.params)
+        p1.use_dynamic_pruning = 0
+        whole.gpu_pme_loadbal_update_param(p1)
+        self.search.build(wl.cfg["rlist_outer"], LOCAL, min_sci=min_sci)
+        sw = StepWorkload(computeEnergy=True, computeVirial=True, useGpuFBufferOps=False)
+        whole.setupGpuShortRangeWork(LOCAL)
+        whole.gpu_upload_shiftvec(stub)
+        whole.gpu_clear_outputs(True)
+        whole.gpu_launch_kernel(sw, LOCAL)
+        whole.gpu_launch_cpyback(stub, sw, LOCAL)
+        e = whole.gpu_wait_finish_task(sw, LOCAL)
+        return f, e
+
+    def free(self):
+        self.search.free()
+        self.whole.gpu_free()
+        self.x_dev = None
+
+
 # ---- the halo part of the C ABI -------------------------------------------------------------------
 
 class HaloExchange:
@@ -154,6 +241,14 @@ class SlabStep:
 
     def search_step(self):
         nb, plan = self.nb, self.plan
+        if plan.local is None:
+            # atom data and both lists were built and installed on the device (DeviceSlabSearch.search_step)
+            nb.setupGpuShortRangeWork(LOCAL)
+            nb.setupGpuShortRangeWork(NONLOCAL)
+            nb.gpu_upload_shiftvec(plan.nbat)
+            if self.multi and self.halo is not None:
+                self.halo.reinitHalo(plan)
+            return
         nb.gpu_init_atomdata(plan.nbat)
         nb.gpu_init_pairlist(plan.local, LOCAL)
         nb.gpu_init_pairlist(plan.nonlocal_, NONLOCAL)
@@ -215,7 +310,7 @@ class SlabStep:
         return self.nb.gpu_wait_finish_task(self.sw, LOCAL)
 
 
-def parity_vs_single_gpu(wl, plan, nb, halo, step, cfg, num_parts, rank, world, local_rank, args):
+def parity_vs_single_gpu(wl, plan, nb, halo, step, cfg, num_parts, rank, world, local_rank, args, dsearch=None):
     """Correctness figure of the N-GPU step on the bench line: the forces every rank holds for its home atoms after an
     end-to-end step (dynamically pruned local + non-local lists, halo transport as benchmarked) and the energies of one
     extra F+E step, against the single-GPU path on the whole system (rank 0 runs it on its GPU through the same library:
@@ -224,7 +319,10 @@ def parity_vs_single_gpu(wl, plan, nb, halo, step, cfg, num_parts, rank, world, 
     import copy
     import torch
     import torch.distributed as dist
-    n_all = wl.nbat.numAtoms()
+    n_all = torch.tensor([dsearch.search.nbins * 64 if dsearch is not None else (wl.nbat.numAtoms() if wl.grid is not None else 0)],
+                         dtype=torch.int64, device="cuda")
+    dist.broadcast(n_all, 0)
+    n_all = int(n_all.item())
     f_full = torch.zeros((n_all, 3), dtype=torch.float32, device="cuda")
     e_full = torch.zeros(2, dtype=torch.float64, device="cuda")
     # N ranks: forces of the last end-to-end step are in plan.nbat.f; one F+E step for the energies
@@ -233,7 +331,11 @@ def parity_vs_single_gpu(wl, plan, nb, halo, step, cfg, num_parts, rank, world, 
     f_mine = np.array(plan.nbat.f[:plan.nbat.numLocalAtoms], np.float64)
     e_n = torch.tensor([e_lj, e_el], dtype=torch.float64, device="cuda")
     dist.all_reduce(e_n)
-    if rank == 0:
+    if rank == 0 and dsearch is not None:
+        f1, e1 = dsearch.whole_system_forces(min_sci=args.min_sci or nb.gpu_min_ci_balanced())
+        f_full.copy_(torch.from_numpy(f1))
+        e_full.copy_(torch.tensor(e1, dtype=torch.float64))
+    elif rank == 0:
         p1 = copy.copy(wl.params)
         p1.use_dynamic_pruning = 0
         g = wl.nbat
@@ -286,12 +388,25 @@ def bench_multi_gpu(args, rank, world, local_rank):
     uid = bytes(idt.cpu().numpy().tobytes())
 
     ncores = len(os.sched_getaffinity(0))
-    wl = make_workload(args.workload, nthreads=max(1, ncores // world), nslabs=world)
+    device_lists = getattr(args, "slab_lists", "device") == "device"
+    # device_lists: nothing of the search step runs on the host - every rank grids the system and builds its two lists on
+    # its own GPU (DeviceSlabSearch); "host": one host grid, the host builder per slab (make_slab_plan)
+    wl = make_workload(args.workload, nthreads=max(1, ncores // world), nslabs=world, host_grid=not device_lists)
     cfg = wl.cfg
     energy = cfg["energy"]
     nb = NbnxmGpu(wl.params, wl.nbat, device=local_rank, bLocalAndNonlocal=True)
     halo = HaloExchange(nb, uid, rank, world)
-    plan = make_slab_plan(wl, rank, world, min_sci=args.min_sci or nb.gpu_min_ci_balanced())
+    dsearch = None
+    if device_lists:
+        dsearch = DeviceSlabSearch(wl, local_rank)
+        plan = dsearch.search_step(nb, rank, world, min_sci=args.min_sci or nb.gpu_min_ci_balanced())
+        search_rec = {"where": "device, every rank", "gpu_grid_ms_whole_system": dsearch.grid_ms, "gpu_lists_ms_this_rank": dsearch.list_ms}
+        if rank != 0:
+            dsearch.free()      # rank 0 keeps the whole-system grid for the parity figure
+            dsearch = None
+    else:
+        plan = make_slab_plan(wl, rank, world, min_sci=args.min_sci or nb.gpu_min_ci_balanced())
+        search_rec = {"where": "host: one grid of the whole system, host builder per slab"}
     nbat = plan.nbat
     xq_pin = torch.empty((nbat.numAtoms(), 4), dtype=torch.float32).pin_memory()
     xq_pin.numpy()[:] = nbat.xq
@@ -399,7 +514,9 @@ def bench_multi_gpu(args, rank, world, local_rank):
     dist.all_reduce(sizes)
     n_home, n_halo, _ = [int(v) for v in sizes.tolist()]
 
-    parity = parity_vs_single_gpu(wl, plan, nb, halo, step, cfg, num_parts, rank, world, local_rank, args)
+    parity = parity_vs_single_gpu(wl, plan, nb, halo, step, cfg, num_parts, rank, world, local_rank, args, dsearch)
+    if dsearch is not None:
+        dsearch.free()
 
     if rank == 0:
         # fraction of the N-GPU FP32 peak the whole step reaches (kernels of both streams, halo waits and launch gaps included)
@@ -416,6 +533,7 @@ def bench_multi_gpu(args, rank, world, local_rank):
                        "l2": "256 MiB flush between steps, outside the per-step CUDA-event intervals" if flush is not None else "no flush",
                        "timing": "mean of per-step CUDA-event intervals on each rank's local stream, max over ranks"},
             "us_per_force_step": ms_step * 1e3,
+            "search_step": search_rec,
             "computed_pairs_per_step": computed_pairs,
             "computed_gpairs_per_s": computed_pairs / (ms_step * 1e-3) * 1e-9,
             "gpu_launches": launches,

@@ -84,17 +84,25 @@ def rolling_prune_parts(cfg):
     return max(1, cfg.get("nstlist_prune", 6) // 2)
 
 
-def make_workload(name, nthreads=None, energy=None, nslabs=1) -> Workload:
+def make_workload(name, nthreads=None, energy=None, nslabs=1, host_grid=True) -> Workload:
+    """host_grid=False: no gridding on the host (grid is None, nbat carries the parameter tables only): for callers that put
+    the atoms on the grid on the device (GpuPairSearch.put_atoms_on_grid)."""
     cfg = dict(CONFIGS[name])
     if energy is not None:
         cfg["energy"] = energy
     box = S.benchmark_system(cfg["k"])
-    t_grid = time.perf_counter()
-    grid = Grid(box.box, box.x, nthreads=nthreads, nslabs=nslabs)
-    t_grid = time.perf_counter() - t_grid
     nbfp, nt = S.spce_nbfp()
     comb = S.geometric_comb_params(nbfp, nt)
-    nbat = grid.atomdata(box.x, box.q, box.type, nbfp, nt, nbfp_comb=comb, lj_comb_per_type=comb)
+    t_grid = time.perf_counter()
+    if host_grid:
+        grid = Grid(box.box, box.x, nthreads=nthreads, nslabs=nslabs)
+        nbat = grid.atomdata(box.x, box.q, box.type, nbfp, nt, nbfp_comb=comb, lj_comb_per_type=comb)
+    else:
+        from .nbnxm import AtomData
+        from .pairsearch import shift_vectors
+        grid = None
+        nbat = AtomData(xq=np.zeros((0, 4), np.float32), nbfp=nbfp, nbfp_comb=comb, numTypes=nt, shift_vec=shift_vectors(box.box))
+    t_grid = time.perf_counter() - t_grid
     params = make_interaction_params(cfg["vdw"], cfg["rc"], cfg["rlist_outer"], cfg["rlist_inner"], cfg["dynamic_pruning"])
     n = box.natoms
     density = n / float(np.prod(box.box.astype(np.float64)))
