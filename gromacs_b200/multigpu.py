@@ -400,7 +400,11 @@ def bench_multi_gpu(args, rank, world, local_rank):
     if device_lists:
         dsearch = DeviceSlabSearch(wl, local_rank)
         plan = dsearch.search_step(nb, rank, world, min_sci=args.min_sci or nb.gpu_min_ci_balanced())
-        search_rec = {"where": "device, every rank", "gpu_grid_ms_whole_system": dsearch.grid_ms, "gpu_lists_ms_this_rank": dsearch.list_ms}
+        first = (dsearch.grid_ms, dsearch.list_ms)
+        # once more with every buffer in place: what a search step costs from the second list on
+        plan = dsearch.search_step(nb, rank, world, min_sci=args.min_sci or nb.gpu_min_ci_balanced())
+        search_rec = {"where": "device, every rank", "gpu_grid_ms_whole_system": dsearch.grid_ms, "gpu_lists_ms_this_rank": dsearch.list_ms,
+                      "first_call_with_allocations_ms": {"grid": first[0], "lists": first[1]}}
         if rank != 0:
             dsearch.free()      # rank 0 keeps the whole-system grid for the parity figure
             dsearch = None
