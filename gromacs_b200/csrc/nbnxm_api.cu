@@ -323,6 +323,7 @@ int nbnxm_b200_free(nbnxm_b200_t* nb)
     if (nb->pipeStart) cudaEventDestroy(nb->pipeStart);
     if (nb->tlStart) cudaEventDestroy(nb->tlStart);
     if (nb->pipePruneDone) cudaEventDestroy(nb->pipePruneDone);
+    if (nb->pipeAllH2D) cudaEventDestroy(nb->pipeAllH2D);
     for (cudaEvent_t ev : nb->tlEvents) cudaEventDestroy(ev);
     if (nb->pipeD2HDone) cudaEventDestroy(nb->pipeD2HDone);
     if (nb->h2dStream) cudaStreamDestroy(nb->h2dStream);
@@ -752,14 +753,20 @@ int nbnxm_b200_do_force_step_pipelined(nbnxm_b200_t* nb, int step, const nbnxm_b
         return fail("nbnxm_b200_do_force_step_pipelined: null argument");
     }
     if (nchunks < 1 || nchunks > 32) return fail("nbnxm_b200_do_force_step_pipelined: 1..32 chunks");
-    if (fl->have_halo) return fail("nbnxm_b200_do_force_step_pipelined: single-rank path only");
+    /* a slab of a multi-GPU run: the chunks cover the home atoms and the local list; the non-local list runs on its own stream
+     * against the +x neighbour's memory (peer-memory halo only) */
+    const bool slab = fl->have_halo != 0;
+    if (slab && (fl->have_halo != 3 || !nbb::peer_halo_enabled(nb)))
+    {
+        return fail("nbnxm_b200_do_force_step_pipelined: with a halo only the peer-memory transport is pipelined");
+    }
     PairList& pl = nb->plist[0];
-    if (chunk_first_atom[0] != 0 || chunk_first_atom[nchunks] != nb->natoms || chunk_first_sci[0] != 0
+    if (chunk_first_atom[0] != 0 || chunk_first_atom[nchunks] != (slab ? nb->natomsLocal : nb->natoms) || chunk_first_sci[0] != 0
         || chunk_first_sci[nchunks] != pl.numSci)
     {
-        return fail("nbnxm_b200_do_force_step_pipelined: the chunks must cover all atoms and all sci entries");
+        return fail("nbnxm_b200_do_force_step_pipelined: the chunks must cover all (home) atoms and all sci entries of the local list");
     }
-    if (pl.haveFreshList || pl.numSci == 0)
+    if (pl.haveFreshList || pl.numSci == 0 || (slab && nb->plist[1].haveFreshList))
     {
         /* the first-pass prune of a fresh list needs every coordinate: plain sequence on search steps */
         return nbnxm_b200_do_force_step(nb, step, fl, xq_host, f_host);
@@ -767,6 +774,7 @@ int nbnxm_b200_do_force_step_pipelined(nbnxm_b200_t* nb, int step, const nbnxm_b
     CU(cudaSetDevice(nb->device));
     const int    e = fl->compute_energy, v = fl->compute_virial;
     cudaStream_t st = nb->stream[0];
+    const int    peerStep = slab ? nbb::peer_next_step(nb) : 0;
     if (!nb->h2dStream)
     {
         CU(cudaStreamCreateWithFlags(&nb->h2dStream, cudaStreamNonBlocking));
@@ -820,7 +828,26 @@ int nbnxm_b200_do_force_step_pipelined(nbnxm_b200_t* nb, int step, const nbnxm_b
      * kernels read the same masks is safe: it only drops cluster pairs whose atom pairs are all beyond rlistInner >= the
      * cut-off at these very coordinates, or re-admits pairs that came inside rlistInner - a kernel that sees a mask word
      * before or after the update evaluates the same interactions within the cut-off; mask words are written whole. */
-    const bool pruneThisStep = fl->dynamic_pruning && step % 2 == 1;
+    if (slab)
+    {
+        /* coordinates in place and accumulator cleared (the copy stream waited for the clear): the -x neighbour's non-local
+         * kernel may read them and add to our forces */
+        if (nbb::peer_publish_ready(nb, peerStep, nb->h2dStream)) return 1;
+        if (!nb->pipeAllH2D) CU(cudaEventCreateWithFlags(&nb->pipeAllH2D, cudaEventDisableTiming));
+        CU(cudaEventRecord(nb->pipeAllH2D, nb->h2dStream));
+        /* the non-local stream: our i-atoms and the neighbour's j-atoms must be there; kernel, rolling prune of the non-local
+         * list on odd steps (prunekerneldispatch.cpp:123-128), then the neighbour may use its forces */
+        cudaStream_t sn = nb->stream[1];
+        CU(cudaStreamWaitEvent(sn, nb->pipeStart, 0));
+        CU(cudaStreamWaitEvent(sn, nb->pipeAllH2D, 0));
+        if (nbb::peer_wait_neighbour_ready(nb, peerStep, sn)) return 1;
+        if (nbnxm_b200_launch_kernel(nb, 1, e, v)) return 1;
+        if (fl->dynamic_pruning && step % 2 == 1 && nbnxm_b200_launch_kernel_pruneonly(nb, 1, fl->rolling_prune_parts)) return 1;
+        if (nbb::peer_publish_forces_done(nb, peerStep, sn)) return 1;
+        CU(cudaEventRecord(nb->nonlocalDone, sn));
+    }
+    /* single rank: rolling prune on odd steps; slab: the local list on even steps */
+    const bool pruneThisStep = fl->dynamic_pruning && (slab ? step % 2 == 0 : step % 2 == 1);
     if (pruneThisStep)
     {
         if (!nb->pipePruneDone) CU(cudaEventCreateWithFlags(&nb->pipePruneDone, cudaEventDisableTiming));
@@ -866,11 +893,27 @@ int nbnxm_b200_do_force_step_pipelined(nbnxm_b200_t* nb, int step, const nbnxm_b
         for (int k = 0; k < nchunks; k++)
             if (chunk_needs[k] & (1u << c)) readyAt[c] = std::max(readyAt[c], position[k]);
     }
+    int sendFirst = 0, sendCount = 0;
+    if (slab)
+    {
+        /* chunks the -x neighbour adds forces to come last, behind its "done" flag; our own non-local kernel adds to home i-atoms
+         * near the +x face: every copy waits for it (it is short and starts early) */
+        nbb::peer_send_range(nb, &sendFirst, &sendCount);
+        for (int c = 0; c < nchunks; c++)
+            if (chunk_first_atom[c] < sendFirst + sendCount && chunk_first_atom[c + 1] > sendFirst) readyAt[c] += nchunks;
+        CU(cudaStreamWaitEvent(nb->d2hStream, nb->nonlocalDone, 0));
+    }
     for (int a = 1; a < nchunks; a++)
         for (int b = a; b > 0 && readyAt[chunkOrder[b]] < readyAt[chunkOrder[b - 1]]; b--) std::swap(chunkOrder[b], chunkOrder[b - 1]);
+    bool waitedForNeighbour = false;
     for (int n = 0; n < nchunks; n++)
     {
         const int c = chunkOrder[n];
+        if (slab && !waitedForNeighbour && readyAt[c] >= nchunks)
+        {
+            if (nbb::peer_wait_forces_from_neighbour(nb, peerStep, nb->d2hStream)) return 1;
+            waitedForNeighbour = true;
+        }
         for (int k = 0; k < nchunks; k++)
             if (chunk_needs[k] & (1u << c)) CU(cudaStreamWaitEvent(nb->d2hStream, nb->chunkKernel[k], 0));
         const int first = chunk_first_atom[c], count = chunk_first_atom[c + 1] - first;
@@ -883,7 +926,11 @@ int nbnxm_b200_do_force_step_pipelined(nbnxm_b200_t* nb, int step, const nbnxm_b
         }
         if (tl) CU(cudaEventRecord(nb->tlEvents[4 * c + 3], nb->d2hStream));
     }
+    /* the handshake completes every step, whatever the chunks look like */
+    if (slab && !waitedForNeighbour && nbb::peer_wait_forces_from_neighbour(nb, peerStep, nb->d2hStream)) return 1;
     CU(cudaEventRecord(nb->pipeD2HDone, nb->d2hStream));
+    /* energies and shift forces of the non-local kernel are in the same accumulators as the local ones */
+    if (slab) CU(cudaStreamWaitEvent(st, nb->nonlocalDone, 0));
     if (pruneThisStep) CU(cudaStreamWaitEvent(st, nb->pipePruneDone, 0));
     if (v) CU(cudaMemcpyAsync(nb->h_fshift, nb->fshift.p, sizeof(double) * 3 * c_numShiftVectors, cudaMemcpyDeviceToHost, st));
     if (e) CU(cudaMemcpyAsync(nb->h_energy, nb->energy.p, sizeof(double) * 2, cudaMemcpyDeviceToHost, st));

@@ -145,6 +145,42 @@ __global__ void __launch_bounds__(256) halo_add_f_kernel(float4* __restrict__ f4
     }
 }
 
+bool peer_halo_enabled(const nbnxm_b200* nb) { return nb && nb->halo && nb->halo->peerEnabled; }
+int  peer_next_step(nbnxm_b200* nb) { return ++nb->halo->peerStep; }
+int  peer_publish_ready(nbnxm_b200* nb, int n, cudaStream_t s)
+{
+    flag_set_kernel<<<1, 1, 0, s>>>(nb->halo->flags.p + 0, n);
+    nb->launches++;
+    CU(cudaGetLastError());
+    return 0;
+}
+int peer_wait_neighbour_ready(nbnxm_b200* nb, int n, cudaStream_t s)
+{
+    flag_wait_kernel<<<1, 1, 0, s>>>(nb->halo->upFlags + 0, n, nb->halo->flags.p + 2);
+    nb->launches++;
+    CU(cudaGetLastError());
+    return 0;
+}
+int peer_publish_forces_done(nbnxm_b200* nb, int n, cudaStream_t s)
+{
+    flag_set_kernel<<<1, 1, 0, s>>>(nb->halo->upFlags + 1, n);
+    nb->launches++;
+    CU(cudaGetLastError());
+    return 0;
+}
+int peer_wait_forces_from_neighbour(nbnxm_b200* nb, int n, cudaStream_t s)
+{
+    flag_wait_kernel<<<1, 1, 0, s>>>(nb->halo->flags.p + 1, n, nb->halo->flags.p + 2);
+    nb->launches++;
+    CU(cudaGetLastError());
+    return 0;
+}
+void peer_send_range(const nbnxm_b200* nb, int* first, int* count)
+{
+    *first = nb->halo->sendFirst;
+    *count = nb->halo->sendCount;
+}
+
 } // namespace nbb
 
 using namespace nbb;

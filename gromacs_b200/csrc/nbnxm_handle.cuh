@@ -166,7 +166,7 @@ struct nbnxm_b200
     cudaStream_t             pipeKernelStream[3] = { nullptr, nullptr, nullptr }; /* the chunk kernels rotate over the local stream and these */
     int                      pipeKernelStreams   = 1;                       /* how many of them are in use (NBNXM_B200_PIPE_STREAMS - 1) */
     std::vector<cudaEvent_t> chunkH2D, chunkKernel;
-    cudaEvent_t              pipeStart = nullptr, pipeD2HDone = nullptr, pipePruneDone = nullptr;
+    cudaEvent_t              pipeStart = nullptr, pipeD2HDone = nullptr, pipePruneDone = nullptr, pipeAllH2D = nullptr;
     /* optional timeline of one pipelined step (nbnxm_b200_set_pipeline_timeline): per chunk the ends of its H2D copy, the start
      * and end of its kernel and the end of its D2H copy, as timing events against tlStart */
     bool                     pipeTimeline = false;
@@ -219,5 +219,24 @@ struct nbnxm_b200
         return a;
     }
 };
+
+/* Hooks of the peer-memory halo (nbnxm_halo.cu) for the chunk-pipelined step of a slab (nbnxm_api.cu):
+ * the step counter handshake of peerForceStep, one call per edge. */
+namespace nbb
+{
+bool peer_halo_enabled(const nbnxm_b200* nb);
+/* next step number of this rank's handshake (every rank counts its steps alike) */
+int peer_next_step(nbnxm_b200* nb);
+/* flags[0] = n on `s`: our coordinates are in place and our accumulator is cleared for step n */
+int peer_publish_ready(nbnxm_b200* nb, int n, cudaStream_t s);
+/* on `s`: wait until the +x neighbour has published step n */
+int peer_wait_neighbour_ready(nbnxm_b200* nb, int n, cudaStream_t s);
+/* on `s`: tell the +x neighbour that our additions to its forces for step n are complete */
+int peer_publish_forces_done(nbnxm_b200* nb, int n, cudaStream_t s);
+/* on `s`: wait until the -x neighbour has finished adding forces to us for step n */
+int peer_wait_forces_from_neighbour(nbnxm_b200* nb, int n, cudaStream_t s);
+/* the home atoms the -x neighbour adds forces to */
+void peer_send_range(const nbnxm_b200* nb, int* first, int* count);
+} // namespace nbb
 
 #endif

@@ -132,6 +132,9 @@ class DeviceSlabSearch:
         self.list_ms = 0.0
         self.search.build_slab(nb, LOCAL, rlist, home, halo, min_sci=min_sci)
         self.list_ms += self.search.build_ms
+        # what the chunk plan of the pipelined end-to-end step needs of the local list: the i-bin of every entry
+        self.local_sci = self.search.download_sci()
+        self.columns = (float(b.box[0]), ncx, ncy, first_bin)
         self.search.build_slab(nb, NONLOCAL, rlist, home, halo, required_tx=tx, min_sci=min_sci // 2)
         self.list_ms += self.search.build_ms
         nhome, nhalo = home[1] - home[0], halo[1] - halo[0]
@@ -238,6 +241,7 @@ class SlabStep:
         self.energy, self.dynamic_pruning, self.num_parts = energy, dynamic_pruning, num_parts
         self.sw = StepWorkload(computeEnergy=energy, computeVirial=energy, useGpuFBufferOps=True)
         self.multi = plan.nranks > 1
+        self.chunk_plan = None      # set to a pipeline.ChunkPlan: steps with host buffers run chunk-pipelined (peer halo only)
 
     def search_step(self):
         nb, plan = self.nb, self.plan
@@ -264,6 +268,11 @@ class SlabStep:
         gpu_* calls as `sequence()` below in one foreign call."""
         nb, sw = self.nb, self.sw
         sw.useGpuFBufferOps = not host_io
+        if host_io and self.multi and self.chunk_plan is not None and self.halo is not None and self.halo.peer:
+            nb.do_force_step_pipelined(step, sw, self.chunk_plan, self.plan.nbat.xq, self.plan.nbat.f,
+                                       dynamic_pruning=self.dynamic_pruning, num_parts=self.num_parts, have_halo=3)
+            nb.gpu_wait_finish_task(sw, NONLOCAL)
+            return nb.gpu_wait_finish_task(sw, LOCAL)
         nb.do_force_step(step, sw, have_halo=(2 if self.halo is None else (3 if self.halo.peer else 1)) if self.multi else 0, dynamic_pruning=self.dynamic_pruning, num_parts=self.num_parts,
                          xq_host=self.plan.nbat.xq if host_io else None, f_host=self.plan.nbat.f if host_io else None)
         if host_io:
@@ -327,6 +336,7 @@ def parity_vs_single_gpu(wl, plan, nb, halo, step, cfg, num_parts, rank, world, 
     e_full = torch.zeros(2, dtype=torch.float64, device="cuda")
     # N ranks: forces of the last end-to-end step are in plan.nbat.f; one F+E step for the energies
     estep = SlabStep(nb, halo, plan, True, cfg["dynamic_pruning"], num_parts)
+    estep.chunk_plan = step.chunk_plan      # the pipelined end-to-end step, where the bench used it
     e_lj, e_el = estep(1, host_io=True)
     f_mine = np.array(plan.nbat.f[:plan.nbat.numLocalAtoms], np.float64)
     e_n = torch.tensor([e_lj, e_el], dtype=torch.float64, device="cuda")
@@ -401,6 +411,7 @@ def bench_multi_gpu(args, rank, world, local_rank):
         dsearch = DeviceSlabSearch(wl, local_rank)
         plan = dsearch.search_step(nb, rank, world, min_sci=args.min_sci or nb.gpu_min_ci_balanced())
         first = (dsearch.grid_ms, dsearch.list_ms)
+        slab_local_sci, slab_columns_info = dsearch.local_sci, dsearch.columns
         # once more with every buffer in place: what a search step costs from the second list on
         plan = dsearch.search_step(nb, rank, world, min_sci=args.min_sci or nb.gpu_min_ci_balanced())
         search_rec = {"where": "device, every rank", "gpu_grid_ms_whole_system": dsearch.grid_ms, "gpu_lists_ms_this_rank": dsearch.list_ms,
@@ -511,9 +522,29 @@ def bench_multi_gpu(args, rank, world, local_rank):
     k_loc_ms, k_nl_ms, hx, hf = [float(v) for v in kt.tolist()]
     fp32_peak = measure_fp32_peak(local_rank)
 
+    # end to end: coordinates up, forces down every step; with the peer-memory halo the step is chunk-pipelined like the
+    # single-rank one (the plain copy - compute - copy sequence first, for the record)
     for i in range(args.warmup):
         step(i, True)
-    ms_e2e, _ = timed_run(True)
+    ms_e2e_plain, _ = timed_run(True)
+    e2e_pipeline = "none: copy, compute, copy"
+    ms_e2e = ms_e2e_plain
+    nchunks = getattr(args, "e2e_chunks", 0) or max(1, min(16, plan.nbat.numLocalAtoms // 200000))
+    if halo.peer and nchunks > 1 and getattr(args, "e2e_chunks", 0) != 1:
+        from .pipeline import make_slab_chunk_plan
+        if device_lists:
+            box_x, ncx, ncy, first_bin = slab_columns_info
+            sci_local = slab_local_sci
+        else:
+            box_x, ncx, ncy, first_bin = float(wl.grid.box[0]), wl.grid.ncx, wl.grid.ncy, wl.grid.first_bin_of_column
+            sci_local = plan.local.sci
+        step.chunk_plan = make_slab_chunk_plan(box_x, ncx, ncy, first_bin, world, rank, cfg["rlist_outer"], sci_local, nchunks)
+        for i in range(args.warmup):
+            step(i, True)
+        ms_e2e, _ = timed_run(True)
+        e2e_pipeline = ("%d chunks of grid columns per rank: H2D, local force kernels and D2H of different chunks overlap, the "
+                        "non-local kernel runs against the neighbour's memory beside them (nbnxm_b200_do_force_step_pipelined)"
+                        % step.chunk_plan.nchunks)
     sizes = torch.tensor([plan.nbat.numLocalAtoms, plan.recv_count, plan.send_count], dtype=torch.float64, device="cuda")
     dist.all_reduce(sizes)
     n_home, n_halo, _ = [int(v) for v in sizes.tolist()]
@@ -548,6 +579,7 @@ def bench_multi_gpu(args, rank, world, local_rank):
                      {"x_exchange_us": hx * 1e3, "f_exchange_us": hf * 1e3, "transport": "ncclSend/ncclRecv",
                       "bytes_per_step_total": int(n_halo * 32)}),
             "e2e": {"value": wl.useful_pairs / (ms_e2e * 1e-3) * 1e-9, "unit": UNIT, "ms_per_step": ms_e2e,
+                    "pipeline": e2e_pipeline, "ms_per_step_copy_compute_copy": ms_e2e_plain,
                     "h2d_bytes_per_step": int(n_home * 16),
                     "d2h_bytes_per_step": int(n_home * 12 + (16 + 45 * 24 if energy else 0) * world)},
             "parity": parity,

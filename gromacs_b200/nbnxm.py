@@ -339,10 +339,12 @@ class NbnxmGpu:
         f = _ptr(f_host, C.c_float) if f_host is not None else None
         self._check(self._lib.nbnxm_b200_do_force_step(self._h, C.c_int(step), C.byref(fl), xq, f))
 
-    def do_force_step_pipelined(self, step, stepWork: StepWorkload, plan, xq_host, f_host, dynamic_pruning=False, num_parts=1):
+    def do_force_step_pipelined(self, step, stepWork: StepWorkload, plan, xq_host, f_host, dynamic_pruning=False, num_parts=1,
+                                have_halo=0):
         """nbnxm_b200_do_force_step_pipelined with a ChunkPlan (gromacs_b200/pipeline.py); the pair list uploaded with
-        gpu_init_pairlist must be plan.plist."""
-        fl = StepFlags(int(stepWork.computeEnergy), int(stepWork.computeVirial), 0, int(dynamic_pruning), int(num_parts))
+        gpu_init_pairlist must be plan.plist.  have_halo=3: a slab of a multi-GPU run with the peer-memory halo (the chunks
+        cover the home atoms and the local list)."""
+        fl = StepFlags(int(stepWork.computeEnergy), int(stepWork.computeVirial), int(have_halo), int(dynamic_pruning), int(num_parts))
         self._check(self._lib.nbnxm_b200_do_force_step_pipelined(
             self._h, C.c_int(step), C.byref(fl), _ptr(xq_host, C.c_float), _ptr(f_host, C.c_float), C.c_int(plan.nchunks),
             _ptr(plan.first_atom, C.c_int), _ptr(plan.first_sci, C.c_int), _ptr(plan.needs, C.c_uint32)))

@@ -219,6 +219,12 @@ class GpuPairSearch:
         target._set_list_sizes(iloc, nsci.value, ncj.value)
         return self._sizes
 
+    def download_sci(self):
+        """int32[nsci, 4]: the sci entries of the list built last (16 bytes each; the cjPacked groups stay on the device)"""
+        sci = np.zeros((self._sizes[0], 4), np.int32)
+        self._nb._check(self._lib.nbnxm_b200_gpu_search_download(self._s, _p(sci, C.c_int), None, None))
+        return sci
+
     def download(self) -> PairlistGpu:
         """Host copy of the list built last."""
         nsci, ncj, nex = self._sizes

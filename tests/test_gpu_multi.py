@@ -57,6 +57,13 @@ def _worker(rank, world, port, out, peer):
                 return parts
             halo.enable_peer_memory(gather, rank, world)
             dist.barrier()
+        if peer == "pipelined":
+            # coordinates up and forces down in chunks of grid columns, overlapped with the kernels (the bench's e2e path)
+            from gromacs_b200.pipeline import make_slab_chunk_plan
+            g = wl.grid
+            step.chunk_plan = make_slab_chunk_plan(g.box[0], g.ncx, g.ncy, g.first_bin_of_column, world, rank, wl.cfg["rlist_outer"],
+                                                   plan.local.sci, 6)
+            assert step.chunk_plan.nchunks > 1
         results = []
         nloc = plan.nbat.numLocalAtoms
         for i, disp in enumerate(_displacements(wl.nbat.numAtoms())):
@@ -94,7 +101,7 @@ def _dynamic_pruning_params(wl):
     wl.params.rlist_inner_sq = np.float32(0.905 ** 2)
 
 
-@pytest.mark.parametrize("peer", [False, True], ids=["nccl", "peer"])
+@pytest.mark.parametrize("peer", [False, True, "pipelined"], ids=["nccl", "peer", "peer-pipelined"])
 @pytest.mark.parametrize("world", [2, 4, 8])
 def test_x_slab_step_matches_oracle(oracle, world, peer):
     import torch
