@@ -529,8 +529,10 @@ def bench_multi_gpu(args, rank, world, local_rank):
     ms_e2e_plain, _ = timed_run(True)
     e2e_pipeline = "none: copy, compute, copy"
     ms_e2e = ms_e2e_plain
-    nchunks = getattr(args, "e2e_chunks", 0) or max(1, min(16, plan.nbat.numLocalAtoms // 200000))
-    if halo.peer and nchunks > 1 and getattr(args, "e2e_chunks", 0) != 1:
+    # one chunk per 250 k home atoms as in the single-rank step; below four chunks the plain sequence is as fast (measured:
+    # 768 k atoms per rank, 3 chunks: 1.070 against 1.062 ms; 6.1 M atoms per rank, 16 chunks: 7.74 against 9.89 ms)
+    nchunks = getattr(args, "e2e_chunks", 0) or max(1, min(24, plan.nbat.numLocalAtoms // 250000))
+    if halo.peer and nchunks >= 4:
         from .pipeline import make_slab_chunk_plan
         if device_lists:
             box_x, ncx, ncy, first_bin = slab_columns_info
