@@ -294,7 +294,7 @@ def main():
     ap.add_argument("--min-sci", type=int, default=0, help="override gpu_min_ci_balanced (list splitting target)")
     ap.add_argument("--e2e-chunks", type=int, default=0,
                     help="N = 1: chunks of the pipelined end-to-end step (1 = plain copy-compute-copy sequence; "
-                         "0 = one chunk per 250k atoms, at most 24: measured 22.0 / 17.9 / 15.9 / 14.9 / 14.9 ms per step "
+                         "0 = one chunk per 250k atoms, at most 32: measured 22.0 / 17.9 / 15.9 / 14.6 / 14.4 ms per step "
                          "with 1 / 8 / 16 / 24 / 32 chunks on the 12.3 M-atom box)")
     ap.add_argument("--slab-lists", default="device", choices=["device", "host"],
                     help="N > 1: where the search step of every rank runs (device: gridding and both lists on the rank's GPU)")
@@ -340,7 +340,7 @@ def main():
     # end-to-end path: coordinates go up and forces come down in chunks of grid columns, pipelined against the kernel
     # (nbnxm_b200_do_force_step_pipelined); the list is the same, with its sci entries grouped by chunk
     from gromacs_b200.pipeline import make_chunk_plan
-    nchunks = args.e2e_chunks if args.e2e_chunks > 0 else max(1, min(24, wl.box.natoms // 250000))
+    nchunks = args.e2e_chunks if args.e2e_chunks > 0 else max(1, min(32, wl.box.natoms // 250000))
     chunks = make_chunk_plan(wl.grid, plist, nchunks) if nchunks > 1 else None
     if chunks is not None:
         plist = chunks.plist
