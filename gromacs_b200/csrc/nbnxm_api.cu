@@ -812,8 +812,28 @@ int nbnxm_b200_do_force_step_pipelined(nbnxm_b200_t* nb, int step, const nbnxm_b
     CU(cudaEventRecord(nb->pipeStart, st));
     CU(cudaStreamWaitEvent(nb->h2dStream, nb->pipeStart, 0));
     CU(cudaStreamWaitEvent(nb->d2hStream, nb->pipeStart, 0));
+    /* Coordinate chunks go up in the order in which the sci chunks 0, 1, 2, ... first need them: the chunks at the far end of x
+     * that the first sci chunks read through the periodic boundary follow the first few directly, so that no sci chunk has to
+     * wait for the end of the upload (with the plain order 0 ... n-1 the sci chunks next to the boundary ran last and kept a
+     * quarter of the force copies behind the last kernel, profiles/r02j_timeline_12m_32.jsonl) */
+    int h2dOrder[32], h2dPos[32], numOrdered = 0;
+    for (int c = 0; c < nchunks; c++) h2dPos[c] = -1;
+    for (int k = 0; k < nchunks; k++)
+        for (int c = 0; c < nchunks; c++)
+            if ((chunk_needs[k] & (1u << c)) && h2dPos[c] < 0)
+            {
+                h2dPos[c]             = numOrdered;
+                h2dOrder[numOrdered++] = c;
+            }
     for (int c = 0; c < nchunks; c++)
+        if (h2dPos[c] < 0)
+        {
+            h2dPos[c]             = numOrdered;
+            h2dOrder[numOrdered++] = c;
+        }
+    for (int n = 0; n < nchunks; n++)
     {
+        const int c     = h2dOrder[n];
         const int first = chunk_first_atom[c], count = chunk_first_atom[c + 1] - first;
         if (count > 0)
         {
@@ -854,14 +874,14 @@ int nbnxm_b200_do_force_step_pipelined(nbnxm_b200_t* nb, int step, const nbnxm_b
         if (launchPruneOnly(nb, 0, fl->rolling_prune_parts, nb->h2dStream)) return 1;
         CU(cudaEventRecord(nb->pipePruneDone, nb->h2dStream));
     }
-    /* sci chunks in the order in which their coordinates are complete: by the last atom chunk they need */
+    /* sci chunks in the order in which their coordinates are complete: by the last of the atom chunks they need to arrive */
     int order[32], lastNeeded[32];
     for (int k = 0; k < nchunks; k++)
     {
         order[k]      = k;
         lastNeeded[k] = 0;
         for (int c = 0; c < nchunks; c++)
-            if (chunk_needs[k] & (1u << c)) lastNeeded[k] = c;
+            if (chunk_needs[k] & (1u << c)) lastNeeded[k] = std::max(lastNeeded[k], h2dPos[c]);
     }
     for (int a = 1; a < nchunks; a++)
         for (int b = a; b > 0 && lastNeeded[order[b]] < lastNeeded[order[b - 1]]; b--) std::swap(order[b], order[b - 1]);
