@@ -41,10 +41,6 @@ struct ThreadList
     std::vector<nbnxm_b200_cj_packed_t> cjp;
     std::vector<nbnxm_b200_excl_t>      excl;
     long long                           nClusterPairs = 0;
-
-    // perturbed atom-pair list split off the list above (nbnxm_b200_pairlist_split_fep)
-    std::vector<int>           fepIinr, fepShift, fepJindex, fepJjnr;
-    std::vector<unsigned char> fepInteracts;
 };
 
 thread_local char g_err[256] = "";
@@ -84,6 +80,8 @@ struct nbnxm_b200_grid
     // perturbed atom-pair list split off the list above (nbnxm_b200_pairlist_split_fep)
     std::vector<int>           fepIinr, fepShift, fepJindex, fepJjnr;
     std::vector<unsigned char> fepInteracts;
+    float                      lastRlist    = 0.0f;  // radius of the list built last
+    bool                       fepSplitDone = false; // the split clears bits of the list: it must not run twice on one list
 };
 
 extern "C" {
@@ -310,6 +308,8 @@ int nbnxm_b200_pairlist_build(nbnxm_b200_grid_t* g, float rlist, const int* excl
         if (2 * rlist >= g->box[d]) return fail("pairlist_build: rlist %g must be shorter than half the box (%g)", rlist, g->box[d]);
     }
     if (nthreads < 1) nthreads = 1;
+    g->lastRlist    = rlist;
+    g->fepSplitDone = false;
     const float rl2 = rlist * rlist;
     /* bounding-box-only acceptance distance: rlist minus half the average x/y diagonal of a cluster
      * (pairlist.cpp: boundingbox_only_distance2) */
@@ -625,6 +625,15 @@ int nbnxm_b200_pairlist_copy(const nbnxm_b200_grid_t* g, nbnxm_b200_sci_t* sci, 
 int nbnxm_b200_pairlist_split_fep(nbnxm_b200_grid_t* g, const unsigned char* perturbed)
 {
     if (!g || !perturbed) return fail("pairlist_split_fep: null argument");
+    if (g->fepSplitDone)
+    {
+        /* the bits of the moved pairs are gone from the cluster list: a second pass would list them as excluded pairs */
+        return fail("pairlist_split_fep: the list built last has already been split; build a new list first");
+    }
+    g->fepSplitDone = true;
+    /* like make_fep_list (pairlist.cpp:1519, rlist_fep2), interacting pairs beyond the list radius leave the cluster list
+     * without entering the perturbed one: they are beyond the cut-off for the life of the list */
+    const float rlist2 = g->lastRlist * g->lastRlist;
     g->fepIinr.clear();
     g->fepShift.clear();
     g->fepJjnr.clear();
@@ -648,6 +657,8 @@ int nbnxm_b200_pairlist_split_fep(nbnxm_b200_grid_t* g, const unsigned char* per
         const int  bi      = s.sci;
         const bool central = (s.shift == c_central);
         bool       any     = false;
+        const float sh[3]  = { float(s.shift % 5 - 2) * g->box[0], float((s.shift / 5) % 3 - 1) * g->box[1],
+                               float(s.shift / 15 - 1) * g->box[2] }; // pbcutil/ishift.h
         for (int i = 0; i < c_binAtoms; i++)
         {
             jOfI[i].clear();
@@ -690,13 +701,17 @@ int nbnxm_b200_pairlist_split_fep(nbnxm_b200_grid_t* g, const unsigned char* per
                             }
                             const int ex = g->cjp[group].imei[half].excl_ind;
                             const bool interacts = (g->excl[ex].pair[word] & bit) != 0;
-                            jOfI[iloc].push_back(jslot);
-                            intOfI[iloc].push_back(interacts ? 1 : 0);
-                            any = true;
                             if (interacts)
                             {
                                 ownExcl(group, half).pair[word] &= ~bit;
+                                const float dx = g->xs[3 * islot] + sh[0] - g->xs[3 * jslot];
+                                const float dy = g->xs[3 * islot + 1] + sh[1] - g->xs[3 * jslot + 1];
+                                const float dz = g->xs[3 * islot + 2] + sh[2] - g->xs[3 * jslot + 2];
+                                if (dx * dx + dy * dy + dz * dz >= rlist2) continue;
                             }
+                            jOfI[iloc].push_back(jslot);
+                            intOfI[iloc].push_back(interacts ? 1 : 0);
+                            any = true;
                         }
                     }
                 }

@@ -63,3 +63,23 @@ def test_cluster_list_plus_fep_list_equals_brute_force_at_both_end_states(oracle
         assert relrms(f, fb) < 2e-6, (lam, relrms(f, fb))
         assert abs(e_cl[0] + e_lj - eb[0]) <= 2e-6 * abs(eb[0]) + 1e-5, (lam, e_cl[0] + e_lj, eb[0])
         assert abs(e_cl[1] + e_el - eb[1]) <= 2e-6 * abs(eb[1]), (lam, e_cl[1] + e_el, eb[1])
+
+
+def test_split_runs_once_per_list():
+    """the split clears the moved pairs' bits in the cluster list, so a second pass over the same list would re-list them as
+    excluded pairs: it is refused until a new list has been built"""
+    import ctypes as C
+    from gromacs_b200.nbnxm import load_library
+    from gromacs_b200.pairsearch import split_fep_pairlist as split_fep_list
+    from gromacs_b200.workload import make_workload
+    wl = make_workload("bench3k", nthreads=2)
+    wl.pairlist(min_sci=0)
+    pert = np.zeros(wl.box.natoms, np.uint8)
+    pert[:30] = 1
+    _, fep = split_fep_list(wl.grid, pert)
+    assert fep["jjnr"].size > 0
+    lib = load_library()
+    assert lib.nbnxm_b200_pairlist_split_fep(wl.grid._g, pert.ctypes.data_as(C.POINTER(C.c_ubyte))) != 0
+    wl.pairlist(min_sci=0)          # a new list: the split is allowed again and gives the same perturbed list
+    _, fep2 = split_fep_list(wl.grid, pert)
+    assert np.array_equal(fep2["jjnr"], fep["jjnr"]) and np.array_equal(fep2["excl_fep"], fep["excl_fep"])
