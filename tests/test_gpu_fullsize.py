@@ -176,10 +176,20 @@ def test_pipelined_step_matches_plain_step(energy):
             nb.gpu_upload_shiftvec(nbat)
             for step in range(4):
                 if pipelined:
+                    nb.set_pipeline_timeline(step == 3)
                     nb.do_force_step_pipelined(step, sw, plan, nbat.xq, nbat.f, dynamic_pruning=True, num_parts=3)
                 else:
                     nb.do_force_step(step, sw, dynamic_pruning=True, num_parts=3, xq_host=nbat.xq, f_host=nbat.f)
                 e = nb.gpu_wait_finish_task(sw, LOCAL)
+            if pipelined:
+                # the recorded timeline of the last step: every chunk's kernel starts after the chunks it reads have arrived
+                # and its forces come down after its kernel
+                t = nb.pipeline_timeline()
+                assert t.shape == (plan.nchunks, 4) and np.all(t >= 0)
+                for k in range(plan.nchunks):
+                    needed = [c for c in range(plan.nchunks) if int(plan.needs[k]) >> c & 1]
+                    assert t[k, 1] >= max(t[c, 0] for c in needed) - 1e-3
+                    assert t[k, 2] >= t[k, 1] and t[k, 3] >= t[k, 2] - 1e-3
             out.append((nbat.f.astype(np.float64).copy(), e))
         finally:
             nb.gpu_free()
