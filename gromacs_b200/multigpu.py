@@ -578,7 +578,10 @@ def bench_multi_gpu(args, rank, world, local_rank):
             "halo": ({"transport": "peer memory over NVLink: the non-local kernel reads the +x neighbour's xq and reduces "
                                    "forces into its accumulator (CUDA IPC mapping, step counters in device memory), no transport calls",
                       "bytes_per_step_total": int(n_halo * 32)} if halo.peer else
-                     {"x_exchange_us": hx * 1e3, "f_exchange_us": hf * 1e3, "transport": "ncclSend/ncclRecv",
+                     {"x_exchange_wait_and_transfer_us": hx * 1e3, "f_exchange_wait_and_transfer_us": hf * 1e3,
+                      "note": "CUDA events around the ncclGroup{Send, Recv} of the slowest rank: they include the wait for the "
+                              "neighbour to reach its matching call (rank skew), not only the transfer",
+                      "transport": "ncclSend/ncclRecv",
                       "bytes_per_step_total": int(n_halo * 32)}),
             "e2e": {"value": wl.useful_pairs / (ms_e2e * 1e-3) * 1e-9, "unit": UNIT, "ms_per_step": ms_e2e,
                     "pipeline": e2e_pipeline, "ms_per_step_copy_compute_copy": ms_e2e_plain,
