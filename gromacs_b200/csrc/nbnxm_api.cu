@@ -77,6 +77,7 @@ int fillParamsDev(nbnxm_b200* nb)
     d.rep_c2 = s.rep_c2; d.rep_c3 = s.rep_c3; d.rep_cpot = s.rep_cpot;
     d.sw_c3 = s.sw_c3; d.sw_c4 = s.sw_c4; d.sw_c5 = s.sw_c5;
     d.coulomb_tab_scale = s.coulomb_tab_scale;
+    double pmeNumD[7] = {}, pmeDenD[5] = {};
     {
         /* pmeCorrF coefficients (src/gromacs/nbnxm/nbnxm_kernel_utils.h:216-250), powers of beta folded in */
         const double cn[7] = { -0.75225204789749321333, 0.069670166153766424023, -0.019278317264888380590,
@@ -88,10 +89,17 @@ int fillParamsDev(nbnxm_b200* nb)
         double       pw = 1.0;
         for (int k = 0; k < 7; k++)
         {
-            d.pmeNum[k] = static_cast<float>(cn[k] * pw * b2 * b);
-            if (k < 5) d.pmeDen[k] = static_cast<float>(cd[k] * pw);
+            pmeNumD[k]  = cn[k] * pw * b2 * b;
+            d.pmeNum[k] = static_cast<float>(pmeNumD[k]);
+            if (k < 5)
+            {
+                pmeDenD[k]  = cd[k] * pw;
+                d.pmeDen[k] = static_cast<float>(pmeDenD[k]);
+            }
             pw *= b2;
         }
+        /* no Ewald electrostatics: beta = 0, the packed constants are not read */
+        if (pmeNumD[6] == 0.0) pmeNumD[6] = 1.0;
     }
     d.nbfp       = nb->nbfp.p;
     d.nbfpComb   = nb->nbfpComb.p;
@@ -101,8 +109,14 @@ int fillParamsDev(nbnxm_b200* nb)
          * kernels of earlier steps may still be reading the previous values */
         float h[pcCount] = {};
         h[pcRc2] = d.rcoulomb_sq;
+#ifdef NBNXM_PACKED_PLAIN_PMECORR
         for (int k = 0; k < 7; k++) h[pcNum0 + k] = d.pmeNum[k];
         for (int k = 0; k < 5; k++) h[pcDen0 + k] = d.pmeDen[k];
+#else
+        /* the packed kernel evaluates num / den with both polynomials divided by num[6] (nbnxm_force_kernel_packed.cuh, pair_w) */
+        for (int k = 0; k < 7; k++) h[pcNum0 + k] = static_cast<float>(pmeNumD[k] / pmeNumD[6]);
+        for (int k = 0; k < 5; k++) h[pcDen0 + k] = static_cast<float>(pmeDenD[k] / pmeNumD[6]);
+#endif
         h[pcRvdw2] = d.rvdw_sq; h[pcBeta] = d.ewald_beta; h[pcEpsfac] = d.epsfac; h[pcRvdwSwitch] = d.rvdw_switch;
         h[pcDispC2] = d.disp_c2; h[pcDispC3] = d.disp_c3; h[pcRepC2] = d.rep_c2; h[pcRepC3] = d.rep_c3;
         h[pcDispC2Third] = d.disp_c2 * (1.0f / 3.0f); h[pcDispC3Quarter] = d.disp_c3 * 0.25f;
@@ -236,8 +250,17 @@ int nbnxm_b200_init(nbnxm_b200_t** out, int device, const nbnxm_b200_params_t* p
     }
     else
     {
-        CU(cudaStreamCreateWithFlags(&nb->stream[0], cudaStreamNonBlocking));
+        /* one level above the lowest priority, which is left to the background rolling prune */
+        int lo = 0, hi = 0;
+        CU(cudaDeviceGetStreamPriorityRange(&lo, &hi));
+        nb->kernelPriority = (lo - 1 >= hi) ? lo - 1 : lo;
+        CU(cudaStreamCreateWithPriority(&nb->stream[0], cudaStreamNonBlocking, nb->kernelPriority));
         nb->ownStream[0] = true;
+    }
+    {
+        /* measured about neutral (profiles/r02aa_background_prune_ab.txt): off unless asked for */
+        const char* bp       = getenv("NBNXM_B200_BACKGROUND_PRUNE");
+        nb->backgroundPrune = (bp && atoi(bp) != 0);
     }
     if (nb->localAndNonlocal)
     {
@@ -326,6 +349,8 @@ int nbnxm_b200_free(nbnxm_b200_t* nb)
     if (nb->pipeAllH2D) cudaEventDestroy(nb->pipeAllH2D);
     for (cudaEvent_t ev : nb->tlEvents) cudaEventDestroy(ev);
     if (nb->pipeD2HDone) cudaEventDestroy(nb->pipeD2HDone);
+    if (nb->pruneFork) cudaEventDestroy(nb->pruneFork);
+    if (nb->pruneStream) cudaStreamDestroy(nb->pruneStream);
     if (nb->h2dStream) cudaStreamDestroy(nb->h2dStream);
     if (nb->d2hStream) cudaStreamDestroy(nb->d2hStream);
     for (cudaStream_t ps : nb->pipeKernelStream) if (ps) cudaStreamDestroy(ps);
@@ -622,6 +647,48 @@ int nbnxm_b200_launch_kernel_pruneonly(nbnxm_b200_t* nb, int iloc, int num_parts
     return launchPruneOnly(nb, iloc, num_parts, nullptr);
 }
 
+} // extern "C"
+
+namespace nbb
+{
+/* creates the stream of the background rolling prune (lowest priority) and its fork event on first use */
+int backgroundPruneStream(nbnxm_b200* nb)
+{
+    if (nb->pruneStream) return 0;
+    int lo = 0, hi = 0;
+    CU(cudaDeviceGetStreamPriorityRange(&lo, &hi));
+    CU(cudaStreamCreateWithPriority(&nb->pruneStream, cudaStreamNonBlocking, lo));
+    CU(cudaEventCreateWithFlags(&nb->pruneFork, cudaEventDisableTiming));
+    if (!nb->pipePruneDone) CU(cudaEventCreateWithFlags(&nb->pipePruneDone, cudaEventDisableTiming));
+    return 0;
+}
+
+/* The rolling prune of the local list as background work of a force step (single rank, nbnxm_b200_do_force_step): forked from
+ * the local stream - coordinates in place, previous step done - onto the lowest-priority stream, launched BEFORE the force
+ * kernel so that both are pending together; the local stream joins it with nbb::join_background_prune before the copy-back.
+ * Masks the force kernel reads while they are updated: see nbnxm_b200_do_force_step_pipelined. */
+int launch_background_prune(nbnxm_b200* nb, int num_parts)
+{
+    if (backgroundPruneStream(nb)) return 1;
+    CU(cudaEventRecord(nb->pruneFork, nb->stream[0]));
+    CU(cudaStreamWaitEvent(nb->pruneStream, nb->pruneFork, 0));
+    if (launchPruneOnly(nb, 0, num_parts, nb->pruneStream)) return 1;
+    CU(cudaEventRecord(nb->pipePruneDone, nb->pruneStream));
+    return 0;
+}
+int join_background_prune(nbnxm_b200* nb)
+{
+    CU(cudaStreamWaitEvent(nb->stream[0], nb->pipePruneDone, 0));
+    return 0;
+}
+bool background_prune_possible(const nbnxm_b200* nb)
+{
+    return nb->backgroundPrune && !nb->plist[0].haveFreshList && nb->plist[0].numSci > 0;
+}
+} // namespace nbb
+
+extern "C" {
+
 /* on `other` instead of the locality's own stream when given (the pipelined step overlaps the rolling prune with its force kernels) */
 static int launchPruneOnly(nbnxm_b200_t* nb, int iloc, int num_parts, cudaStream_t other)
 {
@@ -777,9 +844,13 @@ int nbnxm_b200_do_force_step_pipelined(nbnxm_b200_t* nb, int step, const nbnxm_b
     const int    peerStep = slab ? nbb::peer_next_step(nb) : 0;
     if (!nb->h2dStream)
     {
+        /* the pack kernels of the force copies must not queue behind pending force CTAs: highest priority; the chunk kernels
+         * like the local stream */
+        int lo = 0, hi = 0;
+        CU(cudaDeviceGetStreamPriorityRange(&lo, &hi));
         CU(cudaStreamCreateWithFlags(&nb->h2dStream, cudaStreamNonBlocking));
-        CU(cudaStreamCreateWithFlags(&nb->d2hStream, cudaStreamNonBlocking));
-        for (cudaStream_t& ps : nb->pipeKernelStream) CU(cudaStreamCreateWithFlags(&ps, cudaStreamNonBlocking));
+        CU(cudaStreamCreateWithPriority(&nb->d2hStream, cudaStreamNonBlocking, hi));
+        for (cudaStream_t& ps : nb->pipeKernelStream) CU(cudaStreamCreateWithPriority(&ps, cudaStreamNonBlocking, nb->kernelPriority));
         /* streams the chunk kernels rotate over: 2 (default) ... 4, NBNXM_B200_PIPE_STREAMS for A/B runs */
         const char* ns       = getenv("NBNXM_B200_PIPE_STREAMS");
         nb->pipeKernelStreams = ns ? std::max(1, std::min(3, atoi(ns) - 1)) : 1;
@@ -871,8 +942,18 @@ int nbnxm_b200_do_force_step_pipelined(nbnxm_b200_t* nb, int step, const nbnxm_b
     if (pruneThisStep)
     {
         if (!nb->pipePruneDone) CU(cudaEventCreateWithFlags(&nb->pipePruneDone, cudaEventDisableTiming));
-        if (launchPruneOnly(nb, 0, fl->rolling_prune_parts, nb->h2dStream)) return 1;
-        CU(cudaEventRecord(nb->pipePruneDone, nb->h2dStream));
+        /* behind the last coordinate copy; on the background stream (lowest priority) it runs beside the force kernels in what
+         * they leave of every SM, on the copy stream (NBNXM_B200_BACKGROUND_PRUNE=0) it takes the GPU for its duration */
+        cudaStream_t ps = nb->h2dStream;
+        if (nb->backgroundPrune)
+        {
+            if (nbb::backgroundPruneStream(nb)) return 1;
+            ps = nb->pruneStream;
+            CU(cudaEventRecord(nb->pruneFork, nb->h2dStream));
+            CU(cudaStreamWaitEvent(ps, nb->pruneFork, 0));
+        }
+        if (launchPruneOnly(nb, 0, fl->rolling_prune_parts, ps)) return 1;
+        CU(cudaEventRecord(nb->pipePruneDone, ps));
     }
     /* sci chunks in the order in which their coordinates are complete: by the last of the atom chunks they need to arrive */
     int order[32], lastNeeded[32];

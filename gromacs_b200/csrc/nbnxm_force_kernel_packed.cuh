@@ -134,6 +134,19 @@ __device__ __forceinline__ f32x2 vmax0(const f32x2 x) { return pk(fmaxf(lo(x), 0
 __device__ __forceinline__ float vless(const float x, const float c) { return x < c ? 1.0f : 0.0f; }
 __device__ __forceinline__ f32x2 vless(const f32x2 x, const float c) { return pk(lo(x) < c ? 1.0f : 0.0f, hi(x) < c ? 1.0f : 0.0f); }
 
+/* v where a < b, else 0: spelled as setp + selp so that ptxas emits FSETP + FSEL (the C conditional compiles to a zeroed
+ * register, a predicate and a predicated move per value) */
+__device__ __forceinline__ float sel_lt(const float a, const float b, const float v)
+{
+#ifdef NBNXM_PACKED_NO_SELP
+    return a < b ? v : 0.0f;
+#else
+    float r;
+    asm("{\n.reg .pred p;\nsetp.lt.f32 p, %1, %2;\nselp.f32 %0, %3, 0f00000000, p;\n}" : "=f"(r) : "f"(a), "f"(b), "f"(v));
+    return r;
+#endif
+}
+
 /* flavors the packed kernel covers */
 template<int ELEC, int VDW>
 struct PackedFlavor
@@ -194,7 +207,7 @@ __device__ __forceinline__ void load_packed_consts(PackedConsts& k, const float*
 #pragma unroll
         for (int n = 0; n < 7; n++) k.num[n] = __ldg(g + pcNum0 + n);
 #pragma unroll
-        for (int n = 1; n < 5; n++) k.den[n] = __ldg(g + pcDen0 + n);
+        for (int n = 0; n < 5; n++) k.den[n] = __ldg(g + pcDen0 + n);
         if (ENERGY)
         {
             k.beta     = __ldg(g + pcBeta);
@@ -364,17 +377,28 @@ __device__ __forceinline__ V pair_w(const ParamsDev&    p,
     if (Fl::ewaldAna)
     {
         /* F/r += qq (invR3 + beta^3 pmeCorrF(beta^2 r2)), i.e. W += qq (invR + r2 num(r2) / den(r2)) */
+#ifdef NBNXM_PACKED_PLAIN_PMECORR
         V den = vfma(r2, vbc<V>(k.den[4]), vbc<V>(k.den[3]));
         den   = vfma(den, r2, vbc<V>(k.den[2]));
         den   = vfma(den, r2, vbc<V>(k.den[1]));
         den   = vfma(den, r2, vbc<V>(1.0f));
         V num = vfma(r2, vbc<V>(k.num[6]), vbc<V>(k.num[5]));
+#else
+        /* both polynomials divided by the leading coefficient of the numerator (host, fillParamsDev): its first Horner step
+         * is an addition with ONE constant operand - an FFMA2 takes a single uniform-register operand, the second constant
+         * of r2 num[6] + num[5] cost a move into a vector register per pair body */
+        V den = vfma(r2, vbc<V>(k.den[4]), vbc<V>(k.den[3]));
+        den   = vfma(den, r2, vbc<V>(k.den[2]));
+        den   = vfma(den, r2, vbc<V>(k.den[1]));
+        den   = vfma(den, r2, vbc<V>(k.den[0]));
+        V num = vadd(r2, vbc<V>(k.num[5]));
+#endif
         num   = vfma(num, r2, vbc<V>(k.num[4]));
         num   = vfma(num, r2, vbc<V>(k.num[3]));
         num   = vfma(num, r2, vbc<V>(k.num[2]));
         num   = vfma(num, r2, vbc<V>(k.num[1]));
         num   = vfma(num, r2, vbc<V>(k.num[0]));
-        /* den >= 1: the plain approximate reciprocal needs no range fix-up */
+        /* |den| >= 1 / |num[6]| > 1 (den >= 1 in the plain form): the plain approximate reciprocal needs no range fix-up */
         const V corr = vmul(num, vrcp(den));
         W            = vfma(qqF, vfma(corr, r2, invRi), W);
         if (ENERGY)
@@ -604,8 +628,8 @@ __device__ __forceinline__ void body_both(const ParamsDev&    p,
     f32x2       invR2, e0, e1;
     const f32x2 W  = pair_w<f32x2, ELEC, VDW, false, false>(p, k, r2, vmul(pk(xi.w, xi.w), j.q), c6n, c12, c6grid, 0ull, invR2, e0, e1);
     const f32x2 F  = vmul(W, invR2);
-    const float F0 = (lo(r2) < k.rc2) ? lo(F) : 0.0f;
-    const float F1 = (hi(r2) < k.rc2) ? hi(F) : 0.0f;
+    const float F0 = sel_lt(lo(r2), k.rc2, lo(F));
+    const float F1 = sel_lt(hi(r2), k.rc2, hi(F));
     fi[0]          = fmaf(F0, lo(dx), fmaf(F1, hi(dx), fi[0]));
     fi[1]          = fmaf(F0, lo(dy), fmaf(F1, hi(dy), fi[1]));
     fi[2]          = fmaf(F0, lo(dz), fmaf(F1, hi(dz), fi[2]));
@@ -657,7 +681,7 @@ __device__ __forceinline__ void body_single(const ParamsDev&    p,
     float       invR2, e0, e1;
     const float c6grid = Fl::ljEwaldGeom ? pi.z * l1 : 0.0f;
     const float W = pair_w<float, ELEC, VDW, false, false>(p, k, r2, xi.w * qj, c6n, c12, c6grid, 0.0f, invR2, e0, e1);
-    const float F = (r2 < k.rc2) ? W * invR2 : 0.0f;
+    const float F = sel_lt(r2, k.rc2, W * invR2);
     fi[0]         = fmaf(F, dx, fi[0]);
     fi[1]         = fmaf(F, dy, fi[1]);
     fi[2]         = fmaf(F, dz, fi[2]);

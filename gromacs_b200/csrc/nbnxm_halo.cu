@@ -481,13 +481,21 @@ int nbnxm_b200_do_force_step(nbnxm_b200_t* nb, int step, const nbnxm_b200_step_f
         if (nbnxm_b200_insert_nonlocal_dependency(nb, 0)) return 1;
         if (fl->have_halo == 1 && nbnxm_b200_halo_exchange_x(nb)) return 1;
     }
+    /* single rank: the rolling prune of odd steps runs beside the force kernel as background work (lowest-priority stream,
+     * launched first so that both are pending together) instead of after it; in line after a fresh list's first-pass prune */
+    const bool backgroundPrune = !fl->have_halo && fl->dynamic_pruning && step % 2 == 1 && nbb::background_prune_possible(nb);
+    if (backgroundPrune && nbb::launch_background_prune(nb, fl->rolling_prune_parts)) return 1;
     if (nbnxm_b200_launch_kernel(nb, 0, e, v)) return 1;
     if (fl->have_halo)
     {
         if (nbnxm_b200_launch_kernel(nb, 1, e, v)) return 1;
         if (fl->have_halo == 1 && nbnxm_b200_halo_exchange_f(nb)) return 1;
     }
-    if (fl->dynamic_pruning)
+    if (backgroundPrune)
+    {
+        if (nbb::join_background_prune(nb)) return 1;
+    }
+    else if (fl->dynamic_pruning)
     {
         if (!fl->have_halo)
         {

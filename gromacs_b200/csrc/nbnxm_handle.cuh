@@ -167,6 +167,14 @@ struct nbnxm_b200
     int                      pipeKernelStreams   = 1;                       /* how many of them are in use (NBNXM_B200_PIPE_STREAMS - 1) */
     std::vector<cudaEvent_t> chunkH2D, chunkKernel;
     cudaEvent_t              pipeStart = nullptr, pipeD2HDone = nullptr, pipePruneDone = nullptr, pipeAllH2D = nullptr;
+    /* the rolling prune as background work (NBNXM_B200_BACKGROUND_PRUNE=1; off by default): a stream of the lowest priority next
+     * to kernel streams one level above it.  Measured on a B200: CTAs of the lower-priority launch are not dispatched into the
+     * registers the force CTAs leave on an SM while force CTAs are pending - the prune runs in the force kernel's tail only,
+     * 0.1 ... 0.3 % per step (profiles/r02aa_background_prune_ab.txt); created on first use (nbb::backgroundPruneStream) */
+    cudaStream_t             pruneStream = nullptr;
+    cudaEvent_t              pruneFork   = nullptr;
+    int                      kernelPriority = 0; /* priority of the streams we create for force kernels */
+    bool                     backgroundPrune = false;
     /* optional timeline of one pipelined step (nbnxm_b200_set_pipeline_timeline): per chunk the ends of its H2D copy, the start
      * and end of its kernel and the end of its D2H copy, as timing events against tlStart */
     bool                     pipeTimeline = false;
@@ -224,6 +232,11 @@ struct nbnxm_b200
  * the step counter handshake of peerForceStep, one call per edge. */
 namespace nbb
 {
+/* the rolling prune of the local list as background work beside the force kernel (nbnxm_api.cu) */
+int  backgroundPruneStream(nbnxm_b200* nb);
+bool background_prune_possible(const nbnxm_b200* nb);
+int  launch_background_prune(nbnxm_b200* nb, int num_parts);
+int  join_background_prune(nbnxm_b200* nb);
 bool peer_halo_enabled(const nbnxm_b200* nb);
 /* next step number of this rank's handshake (every rank counts its steps alike) */
 int peer_next_step(nbnxm_b200* nb);
