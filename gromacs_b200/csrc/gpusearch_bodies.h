@@ -29,6 +29,7 @@
 #define NBNXM_B200_GPUSEARCH_BODIES_H
 
 #include <math.h>
+#include <string.h>
 
 #include "../../include/nbnxm_b200.h"
 
@@ -1034,6 +1035,247 @@ struct ColumnSort
             const int slot       = g.colFirstBin[c] * c_binAtoms + t;
             g.atomIndex[slot]    = idx[t];
             g.slotOfAtom[idx[t]] = slot;
+        }
+    }
+};
+
+/* pass G4, bucket form (the default): the same total order as the bitonic networks above - z ascending over the column, then
+ * every 32 along +-y, then every 16 along +-x, ties by atom index - from counting instead of compare-exchange networks:
+ *   z: the atoms of the column go into numBuckets(n) ~ n / 8 buckets by a monotone function of z (spread over the column's own
+ *      z range), bucket sizes are scanned, atoms scattered to their bucket in any order, and every atom's rank inside its
+ *      bucket (the number of atoms of the bucket that come before it) gives its final place;
+ *   y, x: the rank of an atom among the 32 (16) atoms of its segment, direction by segment parity.
+ * 13 stages with a block barrier each instead of ~120, no padding to a power of two, ~60 comparisons per atom of a liquid
+ * instead of ~110 compare-exchanges per padded slot with the stage decoded per item.  A column whose atoms crowd into few
+ * buckets (all z equal) costs bucket size comparisons per atom: slower, same order.
+ * Scratch per block: keyA, idxA, keyB, idxB [scratchPad each], count[c_maxBuckets + 1], start[c_maxBuckets + 1], range[2]. */
+constexpr int c_maxBuckets = 1024;
+constexpr int c_scanChunk  = 32; /* bucket counts scanned in chunks of 32, then the 32 chunk totals, then added back */
+
+NBS_HD int floatBits(float v)
+{
+#if defined(__CUDA_ARCH__)
+    return __float_as_int(v);
+#else
+    int i;
+    memcpy(&i, &v, sizeof(i));
+    return i;
+#endif
+}
+NBS_HD float bitsFloat(int i)
+{
+#if defined(__CUDA_ARCH__)
+    return __int_as_float(i);
+#else
+    float v;
+    memcpy(&v, &i, sizeof(v));
+    return v;
+#endif
+}
+/* int whose signed order is the order of the floats (finite values) */
+NBS_HD int   floatOrderedInt(float v) { const int i = floatBits(v); return i >= 0 ? i : (i ^ 0x7fffffff); }
+NBS_HD float orderedIntFloat(int i) { return bitsFloat(i >= 0 ? i : (i ^ 0x7fffffff)); }
+
+NBS_HD void atomicMinInt(int* p, int v)
+{
+#if defined(__CUDA_ARCH__)
+    atomicMin(p, v);
+#else
+    if (v < *p)
+    {
+        *p = v;
+    }
+#endif
+}
+
+struct ColumnBucketSort
+{
+    GridBuild g;
+    int       scratchPad; /* elements per key / index array of the scratch (>= the tallest column) */
+
+    static size_t scratchBytes(int pad) { return sizeof(int) * (size_t(4) * pad + 2 * (c_maxBuckets + 1) + 2); }
+
+    NBS_HD static int numBuckets(int n)
+    {
+        const int nb = (n + 7) / 8;
+        return nb > c_maxBuckets ? c_maxBuckets : nb;
+    }
+
+    NBS_HD int numStages(int c) const { return g.colCount[c] == 0 ? 0 : 13; }
+
+    NBS_HD int numItems(int c, int s) const
+    {
+        const int n  = g.colCount[c];
+        const int nb = numBuckets(n);
+        switch (s)
+        {
+            case 0: return n > nb + 1 ? n : nb + 1;
+            case 3: return (nb + c_scanChunk - 1) / c_scanChunk;
+            case 4: return 1;
+            case 5: return nb + 1;
+            default: return n;
+        }
+    }
+
+    /* bucket of z: monotone in z (the subtraction, the multiplication by a positive factor and the conversion are) */
+    NBS_HD static int bucketOf(float z, float zmin, float scale, int nb)
+    {
+        const int b = int((z - zmin) * scale);
+        return b < 0 ? 0 : (b > nb - 1 ? nb - 1 : b);
+    }
+
+    /* (ka, ia) before (kb, ib) */
+    NBS_HD static bool before(float ka, int ia, float kb, int ib) { return (ka < kb) || (ka == kb && ia < ib); }
+
+    NBS_HD void operator()(int c, int s, int t, void* scratch) const
+    {
+        const int n     = g.colCount[c];
+        const int nb    = numBuckets(n);
+        float*    keyA  = static_cast<float*>(scratch);
+        int*      idxA  = reinterpret_cast<int*>(keyA + scratchPad);
+        float*    keyB  = reinterpret_cast<float*>(idxA + scratchPad);
+        int*      idxB  = reinterpret_cast<int*>(keyB + scratchPad);
+        int*      count = idxB + scratchPad;          /* [nb + 1] */
+        int*      start = count + c_maxBuckets + 1;   /* [nb + 1] */
+        int*      range = start + c_maxBuckets + 1;   /* ordered ints of the smallest and the largest z */
+        switch (s)
+        {
+            case 0: /* load z keys, clear the bucket counters, initialise the z range */
+                if (t < n)
+                {
+                    const int a = g.colAtoms[g.colAtomStart[c] + t];
+                    idxA[t]     = a;
+                    keyA[t]     = g.x[3 * a + 2];
+                }
+                if (t <= nb)
+                {
+                    count[t] = 0;
+                }
+                if (t == 0)
+                {
+                    range[0] = 0x7fffffff;
+                    range[1] = -0x7fffffff - 1;
+                }
+                break;
+            case 1: /* z range of the column; the plain reads only filter, the atomics decide */
+            {
+                const int o = floatOrderedInt(keyA[t]);
+                if (o < range[0]) atomicMinInt(&range[0], o);
+                if (o > range[1]) atomicMaxInt(&range[1], o);
+                break;
+            }
+            case 2: /* bucket sizes */
+            {
+                const float zmin = orderedIntFloat(range[0]), zmax = orderedIntFloat(range[1]);
+                const float scale = zmax > zmin ? float(nb) / (zmax - zmin) : 0.0f;
+                atomicAddInt(&count[bucketOf(keyA[t], zmin, scale, nb)], 1);
+                break;
+            }
+            case 3: /* exclusive scan of the sizes, chunk by chunk; the chunk total goes to start[chunk end] for stage 4 */
+            {
+                const int b0 = t * c_scanChunk, b1 = b0 + c_scanChunk < nb ? b0 + c_scanChunk : nb;
+                int       sum = 0;
+                for (int b = b0; b < b1; b++)
+                {
+                    const int v = count[b];
+                    start[b]    = sum;
+                    sum += v;
+                }
+                keyB[t] = bitsFloat(sum); /* chunk totals parked in keyB (not in use yet) */
+                break;
+            }
+            case 4: /* scan of the chunk totals */
+            {
+                const int nchunks = (nb + c_scanChunk - 1) / c_scanChunk;
+                int       sum     = 0;
+                for (int k = 0; k < nchunks; k++)
+                {
+                    const int v = floatBits(keyB[k]);
+                    keyB[k]     = bitsFloat(sum);
+                    sum += v;
+                }
+                break;
+            }
+            case 5: /* add the chunk offsets; start[nb] = n */
+                if (t < nb)
+                {
+                    start[t] += floatBits(keyB[t / c_scanChunk]);
+                }
+                else
+                {
+                    start[nb] = n;
+                }
+                break;
+            case 6: /* scatter into the buckets, any order inside a bucket (count[] runs back down to 0) */
+            {
+                const float zmin = orderedIntFloat(range[0]), zmax = orderedIntFloat(range[1]);
+                const float scale = zmax > zmin ? float(nb) / (zmax - zmin) : 0.0f;
+                const int   b   = bucketOf(keyA[t], zmin, scale, nb);
+                const int   pos = start[b] + atomicAddInt(&count[b], -1) - 1;
+                keyB[pos]       = keyA[t];
+                idxB[pos]       = idxA[t];
+                break;
+            }
+            case 7: /* rank inside the bucket -> place in the column */
+            {
+                const float zmin = orderedIntFloat(range[0]), zmax = orderedIntFloat(range[1]);
+                const float scale = zmax > zmin ? float(nb) / (zmax - zmin) : 0.0f;
+                const float k = keyB[t];
+                const int   a = idxB[t];
+                const int   b = bucketOf(k, zmin, scale, nb);
+                int         r = 0;
+                for (int q = start[b]; q < start[b + 1]; q++)
+                {
+                    r += before(keyB[q], idxB[q], k, a) ? 1 : 0;
+                }
+                idxA[start[b] + r] = a;
+                break;
+            }
+            case 8: /* y keys, direction by the parity of the 32-atom segment */
+            {
+                const float v = g.x[3 * idxA[t] + 1];
+                keyA[t]       = ((t / 32) & 1) ? -v : v;
+                break;
+            }
+            case 9: /* rank inside the segment of 32 */
+            {
+                const int   q0 = t & ~31, q1 = q0 + 32 < n ? q0 + 32 : n;
+                const float k  = keyA[t];
+                const int   a  = idxA[t];
+                int         r  = 0;
+                for (int q = q0; q < q1; q++)
+                {
+                    r += before(keyA[q], idxA[q], k, a) ? 1 : 0;
+                }
+                idxB[q0 + r] = a;
+                break;
+            }
+            case 10: /* x keys, direction by the parity of the 16-atom segment */
+            {
+                const float v = g.x[3 * idxB[t]];
+                keyB[t]       = ((t / 16) & 1) ? -v : v;
+                break;
+            }
+            case 11: /* rank inside the segment of 16 */
+            {
+                const int   q0 = t & ~15, q1 = q0 + 16 < n ? q0 + 16 : n;
+                const float k  = keyB[t];
+                const int   a  = idxB[t];
+                int         r  = 0;
+                for (int q = q0; q < q1; q++)
+                {
+                    r += before(keyB[q], idxB[q], k, a) ? 1 : 0;
+                }
+                idxA[q0 + r] = a;
+                break;
+            }
+            default: /* 12: store */
+            {
+                const int slot      = g.colFirstBin[c] * c_binAtoms + t;
+                g.atomIndex[slot]   = idxA[t];
+                g.slotOfAtom[idxA[t]] = slot;
+                break;
+            }
         }
     }
 };

@@ -122,7 +122,7 @@ struct FAtomFill
     NBS_HD void operator()(int i) const { fillAtomSlot(f, i); }
 };
 
-constexpr int c_maxColumnAtoms = 8192; /* one block sorts a column in 64 KB of shared memory */
+constexpr int c_maxColumnAtoms = 8192; /* one block sorts a column in its shared memory (136 KB of scratch at this height) */
 
 template<typename BE>
 struct SearchState
@@ -155,6 +155,7 @@ struct SearchState
     Buf<nbnxm_b200_excl_t>      excl;
     /* pass 3 as one warp per bin pair (FBinPairMaskWarp) instead of one thread per (bin pair, j-cluster) */
     bool      cooperativeMasks = false;
+    bool      bitonicColumnSort = false; /* the column sort as bitonic networks (ColumnSort) instead of buckets + ranks */
     int       nsci = 0, ncjp = 0, nexcl = 0, numBinPairs = 0, numEntries = 0;
     long long numClusterPairsHost = 0;
 };
@@ -316,9 +317,18 @@ int putAtomsOnGrid(BE& be, SearchState<BE>& st, const float* box, int ncx, int n
     gb.atomIndex  = st.atomIndex.p;
     gb.slotOfAtom = st.slotOfAtom.p;
     NBS_TRY(be.forEach(natoms, FGridScatterAtom{ gb }));
-    const int nPad    = nextPow2AtLeast32(st.maxColumnAtoms);
-    const int threads = nPad / 2 < 1024 ? nPad / 2 : 1024;
-    NBS_TRY(be.forEachBlock(ncol, threads, size_t(nPad) * (sizeof(float) + sizeof(int)), ColumnSort{ gb, nPad }));
+    if (st.bitonicColumnSort)
+    {
+        const int nPad    = nextPow2AtLeast32(st.maxColumnAtoms);
+        const int threads = nPad / 2 < 1024 ? nPad / 2 : 1024;
+        NBS_TRY(be.forEachBlock(ncol, threads, size_t(nPad) * (sizeof(float) + sizeof(int)), ColumnSort{ gb, nPad }));
+    }
+    else
+    {
+        const int pad     = (st.maxColumnAtoms + 31) / 32 * 32;
+        const int threads = pad < 1024 ? (pad < 32 ? 32 : pad) : 1024;
+        NBS_TRY(be.forEachBlock(ncol, threads, ColumnBucketSort::scratchBytes(pad), ColumnBucketSort{ gb, pad }));
+    }
     NBS_TRY(setGridPointers(be, st, box, ncx, ncy, nbins, natoms));
     *nbinsOut = nbins;
     return 0;

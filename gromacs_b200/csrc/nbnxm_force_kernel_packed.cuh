@@ -1259,19 +1259,20 @@ __global__ void __launch_bounds__(32, ENERGY ? NBNXM_PACKED_MIN_BLOCKS_ENERGY : 
             {
                 if (fetched)
                 {
-                    const float4 v0 = lds128(sumAddr);
-                    float        sx = v0.x, sy = v0.y, sz = v0.z;
+                    /* x and y as one packed sum: two instead of three additions per partial force, same roundings */
+                    const float4 v0  = lds128(sumAddr);
+                    f32x2        sxy = pk(v0.x, v0.y);
+                    float        sz  = v0.z;
 #pragma unroll
                     for (int kx = 1; kx < c_clusterSize; kx++)
                     {
                         const float4 v = lds128(sumAddr + 16 * kx);
-                        sx += v.x;
-                        sy += v.y;
+                        sxy            = vadd(sxy, pk(v.x, v.y));
                         sz += v.z;
                     }
                     /* the atom this lane fetched for the group */
                     const int ajOwn = lds32i(descCur + 32 * g + 4u * NBNXM_JL_FROM_ADDR) * c_clusterSize + NBNXM_IL_FROM_ADDR;
-                    red_add_v4(ad.f4J + ajOwn, -sx, -sy, -sz);
+                    red_add_v4(ad.f4J + ajOwn, -lo(sxy), -hi(sxy), -sz);
                 }
             }
         }

@@ -285,6 +285,9 @@ int nbnxm_b200_gpu_search_create(nbnxm_b200_gpu_search_t** out, nbnxm_b200_t* nb
      * NBNXM_B200_SEARCH_COOP=0 selects the one-thread-per-j-cluster form for A/B runs */
     const char* coop        = getenv("NBNXM_B200_SEARCH_COOP");
     s->st.cooperativeMasks = !(coop != nullptr && coop[0] == '0');
+    /* column sort of the gridding: buckets + ranks; NBNXM_B200_SEARCH_BITONIC_SORT=1 selects the bitonic networks for A/B runs */
+    const char* bitonic      = getenv("NBNXM_B200_SEARCH_BITONIC_SORT");
+    s->st.bitonicColumnSort = (bitonic != nullptr && bitonic[0] == '1');
     *out = s;
     return 0;
 }

@@ -140,6 +140,12 @@ int search_emu_set_grid(const float* box, int ncx, int ncy, const int* first_bin
     return nbs::setGrid(g_be, g_st, box, ncx, ncy, first_bin_of_column, atom_index, nbins, natoms, excl_index, excl_atoms);
 }
 
+int search_emu_set_bitonic_column_sort(int on)
+{
+    g_st.bitonicColumnSort = on != 0;
+    return 0;
+}
+
 int search_emu_set_cooperative_masks(int on)
 {
     g_st.cooperativeMasks = on != 0;

@@ -16,13 +16,15 @@ from util import load_golden
 HERE = os.path.dirname(os.path.abspath(__file__))
 
 
-@pytest.fixture(scope="module", params=["thread-per-j-cluster masks", "warp-per-bin-pair masks"])
+@pytest.fixture(scope="module", params=["thread-per-j-cluster masks, bitonic column sort", "warp-per-bin-pair masks, bucket column sort"])
 def emu(request):
     """both forms of pass 3 (cluster-pair masks): one thread per (bin pair, j-cluster), and the warp-cooperative one
-    (NBNXM_B200_SEARCH_COOP=1 in the library), run lane by lane"""
+    (the library's default; NBNXM_B200_SEARCH_COOP=0 selects the other), run lane by lane; and both forms of the column
+    sort of the gridding: bitonic networks (NBNXM_B200_SEARCH_BITONIC_SORT=1 in the library) and buckets + ranks (default)"""
     subprocess.run(["make", "-s", "-C", os.path.join(HERE, "kernel_emu")], check=True)
     lib = C.CDLL(os.path.join(HERE, "kernel_emu", "libsearch_emu.so"))
     lib.search_emu_set_cooperative_masks(int(request.param.startswith("warp")))
+    lib.search_emu_set_bitonic_column_sort(int("bitonic" in request.param))
     return lib
 
 
@@ -278,6 +280,37 @@ def test_gridding_passes_with_ties_everywhere(emu):
     x = (rng.integers(0, 13, (4000, 3)) * 0.25).astype(np.float32)          # lattice 0, 0.25, ... 3.0 (= the box face)
     x[:50] = x[50:100]                                                     # exact duplicates
     grid = Grid(box, x, nthreads=3)
+    nbins, atom_index, first_bin = emu_grid(emu, box, x, grid.ncx, grid.ncy)
+    assert nbins == grid.nbins and np.array_equal(first_bin, grid.first_bin_of_column)
+    assert np.array_equal(atom_index, grid.atom_index)
+
+
+@pytest.mark.parametrize("kind", ["tall uniform", "all z equal", "clustered z", "two atoms", "lattice z", "signed zeros"])
+def test_column_sort_corner_cases(emu, kind):
+    """the column sort where its bucket form is stressed: a column of ~7000 atoms (bucket count near its cap), every atom at
+    the same z (one bucket holds the column), z crowded into 1 % of the range, a two-atom system, z on a coarse lattice
+    and +-0 keys: the order is the host gridder's in every case"""
+    from gromacs_b200.pairsearch import Grid
+    rng = np.random.default_rng(7)
+    box = np.array([1.2, 1.2, 60.0], np.float32)
+    n = 7000
+    x = rng.random((n, 3)) * box
+    if kind == "all z equal":
+        x[:, 2] = 30.0
+    elif kind == "clustered z":
+        x[:, 2] = np.where(rng.random(n) < 0.9, 5.0 + rng.random(n) * 0.01, x[:, 2])
+    elif kind == "two atoms":
+        box = np.array([3.0, 3.0, 3.0], np.float32)
+        x = rng.random((2, 3)) * box
+    elif kind == "lattice z":
+        x[:, 2] = np.minimum(np.round(x[:, 2] * 4) / 4, 59.75)
+    elif kind == "signed zeros":
+        box = np.array([3.0, 3.0, 3.0], np.float32)
+        x = rng.random((5000, 3)) * box
+        x[::7, 2] = -0.0
+        x[1::7, 2] = 0.0
+    x = np.ascontiguousarray(x, np.float32)
+    grid = Grid(box, x, nthreads=2)
     nbins, atom_index, first_bin = emu_grid(emu, box, x, grid.ncx, grid.ncy)
     assert nbins == grid.nbins and np.array_equal(first_bin, grid.first_bin_of_column)
     assert np.array_equal(atom_index, grid.atom_index)
