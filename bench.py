@@ -290,6 +290,8 @@ def main():
     ap.add_argument("--workload", default=None)
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--energy", type=int, default=None, choices=[0, 1],
+                    help="N = 1: force + energy (+ virial) kernel on every step (1) or never (0) instead of what the workload says")
     ap.add_argument("--no-l2-flush", action="store_true")
     ap.add_argument("--min-sci", type=int, default=0, help="override gpu_min_ci_balanced (list splitting target)")
     ap.add_argument("--e2e-chunks", type=int, default=0,
@@ -323,7 +325,7 @@ def main():
         sys.exit("launch multi-GPU runs with torch.distributed.run (one rank per GPU)")
 
     torch.cuda.set_device(local_rank)
-    wl = make_workload(args.workload)
+    wl = make_workload(args.workload, energy=None if args.energy is None else bool(args.energy))
     cfg, nbat = wl.cfg, wl.nbat
     energy = cfg["energy"]
     sw = StepWorkload(computeEnergy=energy, computeVirial=energy, useGpuFBufferOps=True)

@@ -128,6 +128,7 @@ int fillParamsDev(nbnxm_b200* nb)
         {
             const float c2 = d.ewaldcoeff_lj * d.ewaldcoeff_lj;
             h[pcLjeCoeff2] = c2; h[pcLjeCoeff6Sixth] = c2 * c2 * c2 * c_oneSixth; h[pcShLjEwald] = d.sh_lj_ewald;
+            h[pcTwoBetaOverSqrtPi] = static_cast<float>(2.0 * double(d.ewald_beta) * 0.56418958354775628695);
         }
         CU(nb->packedConsts.reserve(pcCount));
         if (nb->stream[0]) CU(cudaStreamSynchronize(nb->stream[0]));

@@ -71,7 +71,7 @@ enum PackedConstIndex
 {
     pcRc2 = 0, pcNum0 = 1, pcDen0 = 8, pcRvdw2 = 13, pcBeta, pcEpsfac, pcRvdwSwitch, pcDispC2, pcDispC3, pcRepC2, pcRepC3,
     pcDispC2Third, pcDispC3Quarter, pcRepC2Third, pcRepC3Quarter, pcDispCpot, pcRepCpot, pcSwC3, pcSwC4, pcSwC5, pcSwC3x3,
-    pcSwC4x4, pcSwC5x5, pcCrf, pcTwoKrf, pcHalfTwoKrf, pcShEwald, pcLjeCoeff2, pcLjeCoeff6Sixth, pcShLjEwald, pcCount
+    pcSwC4x4, pcSwC5x5, pcCrf, pcTwoKrf, pcHalfTwoKrf, pcShEwald, pcLjeCoeff2, pcLjeCoeff6Sixth, pcShLjEwald, pcTwoBetaOverSqrtPi, pcCount
 };
 
 struct PairlistDev

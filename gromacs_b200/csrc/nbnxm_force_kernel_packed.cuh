@@ -80,6 +80,11 @@ __device__ __forceinline__ f32x2 vfma(const f32x2 a, const f32x2 b, const f32x2 
     asm("fma.rn.f32x2 %0, %1, %2, %3;" : "=l"(d) : "l"(a), "l"(b), "l"(c));
     return d;
 }
+/* acc += a b with the accumulator as a read-write operand (one virtual register in the PTX) */
+__device__ __forceinline__ void vfma_acc(f32x2& acc, const f32x2 a, const f32x2 b)
+{
+    asm("fma.rn.f32x2 %0, %1, %2, %0;" : "+l"(acc) : "l"(a), "l"(b));
+}
 __device__ __forceinline__ f32x2 vmul(const f32x2 a, const f32x2 b)
 {
     f32x2 d;
@@ -161,7 +166,7 @@ struct PackedFlavor
  * 2.6e-9 on [0, 3.6]; in float32 about 3e-7 absolute, like erfcf), times exp(-x^2) with the rounding error of x^2
  * compensated.  15 FP32 operations and 2 MUFU per value, against ~55 instructions for erfcf. */
 template<typename V>
-__device__ __forceinline__ V erfc_poly(const V x)
+__device__ __forceinline__ V erfc_poly(const V x, V& expMinusX2)
 {
     const V t = vrcp(vfma(x, vbc<V>(0.5f), vbc<V>(1.0f)));
     V       q = vfma(t, vbc<V>(-1.744380291e-02f), vbc<V>(4.996527726e-02f));
@@ -179,6 +184,7 @@ __device__ __forceinline__ V erfc_poly(const V x)
     const V nl = vfma(nx, x, h);
     V       e  = vex2(vmul(h, vbc<V>(-1.4426950408889634f)));
     e          = vfma(e, nl, e);
+    expMinusX2 = e;
     return vmul(q, e);
 }
 
@@ -193,7 +199,16 @@ struct PackedConsts
     float rvdw_switch, disp_c2, disp_c3, rep_c2, rep_c3, disp_c2_3, disp_c3_4, rep_c2_3, rep_c3_4, disp_cpot, rep_cpot;
     float sw_c3, sw_c4, sw_c5, sw_c3x3, sw_c4x4, sw_c5x5, c_rf, two_k_rf, half_two_k_rf, sh_ewald;
     float lje_coeff2, lje_coeff6_6, sh_lj_ewald; /* LJ-PME: ewaldcoeff_lj^2, ewaldcoeff_lj^6 / 6, potential shift */
+    float two_beta_over_sqrt_pi;                  /* energy kernels: coefficient of exp(-beta^2 r^2) in the real-space force */
 };
+
+/* energy kernels take the Ewald real-space force of pairs without exclusions from the erfc / exp of the energy
+ * (-DNBNXM_PACKED_ENERGY_PMECORR: the rational correction everywhere, for A/B runs) */
+#ifdef NBNXM_PACKED_ENERGY_PMECORR
+constexpr bool c_ewaldForceFromErfc = false;
+#else
+constexpr bool c_ewaldForceFromErfc = true;
+#endif
 
 template<int ELEC, int VDW, bool ENERGY>
 __device__ __forceinline__ void load_packed_consts(PackedConsts& k, const float* __restrict__ g)
@@ -212,6 +227,7 @@ __device__ __forceinline__ void load_packed_consts(PackedConsts& k, const float*
         {
             k.beta     = __ldg(g + pcBeta);
             k.sh_ewald = __ldg(g + pcShEwald);
+            k.two_beta_over_sqrt_pi = __ldg(g + pcTwoBetaOverSqrtPi);
         }
     }
     if (ENERGY || Fl::ljPSwitch)
@@ -374,7 +390,20 @@ __device__ __forceinline__ V pair_w(const ParamsDev&    p,
         W = vfma(qqF, vfma(r2, vbc<V>(-k.two_k_rf), invRi), W);
         if (ENERGY) eEl = vmul(qq, vadd(invRi, vfma(r2, vbc<V>(k.half_two_k_rf), vbc<V>(-k.c_rf))));
     }
-    if (Fl::ewaldAna)
+    if (Fl::ewaldAna && ENERGY && !EXCL && c_ewaldForceFromErfc)
+    {
+        /* Energy kernels, pairs without exclusions: erfc(beta r) and exp(-beta^2 r^2) are evaluated for the energy anyway, and
+         * the real-space force is made of the same two: F/r = qq (erfc(beta r) / r + 2 beta / sqrt(pi) exp(-beta^2 r^2)) / r^2,
+         * i.e. W += qq (erfc invR + 2 beta / sqrt(pi) exp).  Saves the rational correction (10 packed FMAs and a reciprocal per
+         * two pairs); erfc_poly is good to 3e-7 absolute, which this term inherits relative to qq / r^3 (the force-only kernels
+         * carry the 1e-7 of their approximate rsqrt in the same place).  Excluded pairs keep the correction form, which has no
+         * cancellation at small r. */
+        V           expm;
+        const V     ec = erfc_poly(vmul(r, vbc<V>(k.beta)), expm);
+        W              = vfma(qqF, vfma(ec, invR, vmul(expm, vbc<V>(k.two_beta_over_sqrt_pi))), W);
+        eEl            = vmul(qq, vfma(invR, ec, vbc<V>(-k.sh_ewald)));
+    }
+    else if (Fl::ewaldAna)
     {
         /* F/r += qq (invR3 + beta^3 pmeCorrF(beta^2 r2)), i.e. W += qq (invR + r2 num(r2) / den(r2)) */
 #ifdef NBNXM_PACKED_PLAIN_PMECORR
@@ -404,7 +433,8 @@ __device__ __forceinline__ V pair_w(const ParamsDev&    p,
         if (ENERGY)
         {
             /* qq (invR (erfc(beta r) - (1 - intBit)) - intBit sh_ewald); excluded pairs get -erf(beta r)/r */
-            const V ec = erfc_poly(vmul(r, vbc<V>(k.beta)));
+            V       expm;
+            const V ec = erfc_poly(vmul(r, vbc<V>(k.beta)), expm);
             if (EXCL)
             {
                 eEl = vmul(qq, vfma(invR, vadd(ec, vsub(intBit, vbc<V>(1.0f))), vmul(intBit, vbc<V>(-k.sh_ewald))));
@@ -808,8 +838,8 @@ __device__ __forceinline__ f32x2 body_general(const ParamsDev&    p,
     const f32x2 wm = pk(w0 ? 1.0f : 0.0f, w1 ? 1.0f : 0.0f);
     if (ENERGY)
     {
-        eLJacc = vfma(ePairLJ, wm, eLJacc);
-        eElacc = vfma(ePairEl, wm, eElacc);
+        vfma_acc(eLJacc, ePairLJ, wm);
+        vfma_acc(eElacc, ePairEl, wm);
     }
     return vmul(W, vmul(invR2, wm));
 }
@@ -1117,9 +1147,9 @@ __global__ void __launch_bounds__(32, ENERGY ? NBNXM_PACKED_MIN_BLOCKS_ENERGY : 
                                 fi[ci][0] = fmaf(lo(F), lo(dx), fmaf(hi(F), hi(dx), fi[ci][0]));
                                 fi[ci][1] = fmaf(lo(F), lo(dy), fmaf(hi(F), hi(dy), fi[ci][1]));
                                 fi[ci][2] = fmaf(lo(F), lo(dz), fmaf(hi(F), hi(dz), fi[ci][2]));
-                                pjx       = vfma(F, dx, pjx);
-                                pjy       = vfma(F, dy, pjy);
-                                pjz       = vfma(F, dz, pjz);
+                                vfma_acc(pjx, F, dx);
+                                vfma_acc(pjy, F, dy);
+                                vfma_acc(pjz, F, dz);
                             }
                             else
                             {
