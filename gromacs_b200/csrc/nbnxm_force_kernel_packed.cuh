@@ -785,7 +785,7 @@ __device__ __forceinline__ float body_single_general(const ParamsDev&    p,
 
 /* One (i-cluster, j-cluster) pair, general: list mask bits per half, optional exclusion masks, optional energies.
  * Returns the masked F/r of the two pairs and the distance vectors. */
-template<int ELEC, int VDW, bool ENERGY, bool EXCL>
+template<int ELEC, int VDW, bool ENERGY, bool EXCL, bool RAW_ENERGIES = false>
 __device__ __forceinline__ f32x2 body_general(const ParamsDev&    p,
                                               const PackedConsts& k,
                                               const PackedShared& sm,
@@ -801,8 +801,9 @@ __device__ __forceinline__ f32x2 body_general(const ParamsDev&    p,
                                               f32x2&              dx,
                                               f32x2&              dy,
                                               f32x2&              dz,
-                                              f32x2&              eLJacc,
-                                              f32x2&              eElacc)
+                                              f32x2&              eLJacc, /* RAW_ENERGIES: the pair energies, unmasked */
+                                              f32x2&              eElacc,
+                                              f32x2*              wmOut = nullptr) /* RAW_ENERGIES: the 1 / 0 masks of the pairs */
 {
     using Fl = Flavor<ELEC, VDW, ENERGY>;
     dx       = vsub(pk(xi.x, xi.x), j.x);
@@ -836,7 +837,13 @@ __device__ __forceinline__ f32x2 body_general(const ParamsDev&    p,
     const f32x2 W = pair_w<f32x2, ELEC, VDW, ENERGY, EXCL>(p, k, r2c, vmul(pk(xi.w, xi.w), j.q), c6n, c12, c6grid, intBit, invR2, ePairLJ, ePairEl);
     /* masking by multiplication: every quantity is finite (r2 is clamped), and the energy sums become FMAs */
     const f32x2 wm = pk(w0 ? 1.0f : 0.0f, w1 ? 1.0f : 0.0f);
-    if (ENERGY)
+    if (ENERGY && RAW_ENERGIES)
+    {
+        eLJacc = ePairLJ;
+        eElacc = ePairEl;
+        *wmOut = wm;
+    }
+    else if (ENERGY)
     {
         vfma_acc(eLJacc, ePairLJ, wm);
         vfma_acc(eElacc, ePairEl, wm);
@@ -1132,6 +1139,7 @@ __global__ void __launch_bounds__(32, ENERGY ? NBNXM_PACKED_MIN_BLOCKS_ENERGY : 
                     /* cluster pairs with both halves in the list: packed bodies (with energies: packed j-force accumulators) */
                     const unsigned mBoth = m0 & m1 & mFast;
                     f32x2          pjx = 0ull, pjy = 0ull, pjz = 0ull;
+                    float          eLJb = 0.0f, eElb = 0.0f;
 #pragma unroll
                     for (int ci = 0; ci < c_superClusterSize; ci++)
                     {
@@ -1142,6 +1150,7 @@ __global__ void __launch_bounds__(32, ENERGY ? NBNXM_PACKED_MIN_BLOCKS_ENERGY : 
                             if (ENERGY)
                             {
                                 f32x2       dx, dy, dz;
+#ifdef NBNXM_PACKED_ENERGY_PACKED_ACC
                                 const f32x2 F = body_general<ELEC, VDW, ENERGY, false>(p, k, sm, xi, pi, j, true, true, true, true,
                                                                                       false, false, dx, dy, dz, eLJj, eElj);
                                 fi[ci][0] = fmaf(lo(F), lo(dx), fmaf(hi(F), hi(dx), fi[ci][0]));
@@ -1150,6 +1159,25 @@ __global__ void __launch_bounds__(32, ENERGY ? NBNXM_PACKED_MIN_BLOCKS_ENERGY : 
                                 vfma_acc(pjx, F, dx);
                                 vfma_acc(pjy, F, dy);
                                 vfma_acc(pjz, F, dz);
+#else
+                                /* scalar accumulators for the j forces and the energies of the j-cluster: ptxas gives packed
+                                 * accumulators of this conditional chain a temporary and two moves per update (10 MOV per body) */
+                                f32x2       eLJp, eElp, wm;
+                                const f32x2 F = body_general<ELEC, VDW, ENERGY, false, true>(p, k, sm, xi, pi, j, true, true, true, true,
+                                                                                            false, false, dx, dy, dz, eLJp, eElp, &wm);
+                                const float F0 = lo(F), F1 = hi(F);
+                                fi[ci][0] = fmaf(F0, lo(dx), fmaf(F1, hi(dx), fi[ci][0]));
+                                fi[ci][1] = fmaf(F0, lo(dy), fmaf(F1, hi(dy), fi[ci][1]));
+                                fi[ci][2] = fmaf(F0, lo(dz), fmaf(F1, hi(dz), fi[ci][2]));
+                                fj.xA     = fmaf(F0, lo(dx), fj.xA);
+                                fj.yA     = fmaf(F0, lo(dy), fj.yA);
+                                fj.zA     = fmaf(F0, lo(dz), fj.zA);
+                                fj.xB     = fmaf(F1, hi(dx), fj.xB);
+                                fj.yB     = fmaf(F1, hi(dy), fj.yB);
+                                fj.zB     = fmaf(F1, hi(dz), fj.zB);
+                                eLJb      = fmaf(lo(eLJp), lo(wm), fmaf(hi(eLJp), hi(wm), eLJb));
+                                eElb      = fmaf(lo(eElp), lo(wm), fmaf(hi(eElp), hi(wm), eElb));
+#endif
                             }
                             else
                             {
@@ -1157,6 +1185,7 @@ __global__ void __launch_bounds__(32, ENERGY ? NBNXM_PACKED_MIN_BLOCKS_ENERGY : 
                             }
                         }
                     }
+#ifdef NBNXM_PACKED_ENERGY_PACKED_ACC
                     if (ENERGY)
                     {
                         fj.xA = lo(pjx);
@@ -1166,6 +1195,16 @@ __global__ void __launch_bounds__(32, ENERGY ? NBNXM_PACKED_MIN_BLOCKS_ENERGY : 
                         fj.yB = hi(pjy);
                         fj.zB = hi(pjz);
                     }
+#else
+                    (void)pjx;
+                    (void)pjy;
+                    (void)pjz;
+                    if (ENERGY)
+                    {
+                        eLJ += eLJb;
+                        eEl += eElb;
+                    }
+#endif
                     /* cluster pairs with one half only (about one in four after pruning): a scalar body on that half,
                      * one loop body for all i-clusters (the unrolled form would not fit the instruction cache) */
                     unsigned mSingle = mFast & ~mBoth;
