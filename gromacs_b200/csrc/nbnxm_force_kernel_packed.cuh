@@ -152,6 +152,16 @@ __device__ __forceinline__ float sel_lt(const float a, const float b, const floa
 #endif
 }
 
+/* v where a < b and the pair's half is in the list, else 0 */
+__device__ __forceinline__ float sel_lt_listed(const float a, const float b, const float v, const unsigned listed)
+{
+    float r;
+    asm("{\n.reg .pred p, q;\nsetp.ne.u32 q, %4, 0;\nsetp.lt.and.f32 p, %1, %2, q;\nselp.f32 %0, %3, 0f00000000, p;\n}"
+        : "=f"(r)
+        : "f"(a), "f"(b), "f"(v), "r"(listed));
+    return r;
+}
+
 /* flavors the packed kernel covers */
 template<int ELEC, int VDW>
 struct PackedFlavor
@@ -631,7 +641,7 @@ __device__ __forceinline__ void lj_params_packed(const PackedShared& sm, const f
 }
 
 /* One (i-cluster, j-cluster) pair with BOTH halves in the list and no exclusion masks, force only: the hot body. */
-template<int ELEC, int VDW>
+template<int ELEC, int VDW, bool LISTBITS = false>
 __device__ __forceinline__ void body_both(const ParamsDev&    p,
                                           const PackedConsts& k,
                                           const PackedShared& sm,
@@ -639,7 +649,9 @@ __device__ __forceinline__ void body_both(const ParamsDev&    p,
                                           const float4        pi,
                                           const PackedJ&      j,
                                           float (&fi)[3],
-                                          FjAcc& fj)
+                                          FjAcc& fj,
+                                          const unsigned listed0 = 1u, /* LISTBITS: non-zero where the half is in the list */
+                                          const unsigned listed1 = 1u)
 {
     const f32x2 dx = vsub(pk(xi.x, xi.x), j.x), dy = vsub(pk(xi.y, xi.y), j.y), dz = vsub(pk(xi.z, xi.z), j.z);
     f32x2       r2;
@@ -658,8 +670,8 @@ __device__ __forceinline__ void body_both(const ParamsDev&    p,
     f32x2       invR2, e0, e1;
     const f32x2 W  = pair_w<f32x2, ELEC, VDW, false, false>(p, k, r2, vmul(pk(xi.w, xi.w), j.q), c6n, c12, c6grid, 0ull, invR2, e0, e1);
     const f32x2 F  = vmul(W, invR2);
-    const float F0 = sel_lt(lo(r2), k.rc2, lo(F));
-    const float F1 = sel_lt(hi(r2), k.rc2, hi(F));
+    const float F0 = LISTBITS ? sel_lt_listed(lo(r2), k.rc2, lo(F), listed0) : sel_lt(lo(r2), k.rc2, lo(F));
+    const float F1 = LISTBITS ? sel_lt_listed(hi(r2), k.rc2, hi(F), listed1) : sel_lt(hi(r2), k.rc2, hi(F));
     fi[0]          = fmaf(F0, lo(dx), fmaf(F1, hi(dx), fi[0]));
     fi[1]          = fmaf(F0, lo(dy), fmaf(F1, hi(dy), fi[1]));
     fi[2]          = fmaf(F0, lo(dz), fmaf(F1, hi(dz), fi[2]));
@@ -1136,8 +1148,16 @@ __global__ void __launch_bounds__(32, ENERGY ? NBNXM_PACKED_MIN_BLOCKS_ENERGY : 
                 }
                 else
                 {
-                    /* cluster pairs with both halves in the list: packed bodies (with energies: packed j-force accumulators) */
-                    const unsigned mBoth = m0 & m1 & mFast;
+                    /* Kernels with a long pair body (energies, potential switch): every cluster pair without exclusions runs the
+                     * packed body, a half that is not in the list masked like a pair beyond the cut-off (3 ... 5 instructions on top
+                     * of 81 ... 103) - the loop body for cluster pairs with one half that stood here took 157 ... 162 instructions
+                     * per trip for 32 pairs (-DNBNXM_PACKED_SINGLE_LOOP brings it back for A/B runs) */
+#ifdef NBNXM_PACKED_SINGLE_LOOP
+                    constexpr bool c_singleAsBoth = false;
+#else
+                    constexpr bool c_singleAsBoth = true;
+#endif
+                    const unsigned mBoth = c_singleAsBoth ? mFast : (m0 & m1 & mFast);
                     f32x2          pjx = 0ull, pjy = 0ull, pjz = 0ull;
                     float          eLJb = 0.0f, eElb = 0.0f;
 #pragma unroll
@@ -1163,7 +1183,8 @@ __global__ void __launch_bounds__(32, ENERGY ? NBNXM_PACKED_MIN_BLOCKS_ENERGY : 
                                 /* scalar accumulators for the j forces and the energies of the j-cluster: ptxas gives packed
                                  * accumulators of this conditional chain a temporary and two moves per update (10 MOV per body) */
                                 f32x2       eLJp, eElp, wm;
-                                const f32x2 F = body_general<ELEC, VDW, ENERGY, false, true>(p, k, sm, xi, pi, j, true, true, true, true,
+                                const bool  l0 = !c_singleAsBoth || ((m0 >> ci) & 1u) != 0u, l1 = !c_singleAsBoth || ((m1 >> ci) & 1u) != 0u;
+                                const f32x2 F = body_general<ELEC, VDW, ENERGY, false, true>(p, k, sm, xi, pi, j, l0, l1, true, true,
                                                                                             false, false, dx, dy, dz, eLJp, eElp, &wm);
                                 const float F0 = lo(F), F1 = hi(F);
                                 fi[ci][0] = fmaf(F0, lo(dx), fmaf(F1, hi(dx), fi[ci][0]));
@@ -1181,7 +1202,7 @@ __global__ void __launch_bounds__(32, ENERGY ? NBNXM_PACKED_MIN_BLOCKS_ENERGY : 
                             }
                             else
                             {
-                                body_both<ELEC, VDW>(p, k, sm, xi, pi, j, fi[ci], fj);
+                                body_both<ELEC, VDW, c_singleAsBoth>(p, k, sm, xi, pi, j, fi[ci], fj, m0 & (1u << ci), m1 & (1u << ci));
                             }
                         }
                     }
