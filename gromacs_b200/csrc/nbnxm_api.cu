@@ -255,6 +255,14 @@ int nbnxm_b200_init(nbnxm_b200_t** out, int device, const nbnxm_b200_params_t* p
         int lo = 0, hi = 0;
         CU(cudaDeviceGetStreamPriorityRange(&lo, &hi));
         nb->kernelPriority = (lo - 1 >= hi) ? lo - 1 : lo;
+        /* Priority tiers (kernel streams above the lowest priority, the force copy-down stream at the highest) only with
+         * NBNXM_B200_STREAM_PRIORITIES=1, which the background rolling prune needs to mean anything.  Measured at 2 ranks on the
+         * 12.3 M-atom box: with tiers the end-to-end slab step takes 9.28 ms against 7.87 ms without - the one-thread kernels
+         * that publish "coordinates in place" sit on the copy stream and queue behind every pending force CTA of a higher tier
+         * (profiles/r02ag_slab_e2e_chunks_priorities_ab.txt) */
+        const char* sp = getenv("NBNXM_B200_STREAM_PRIORITIES");
+        nb->flatPriorities = !(sp && atoi(sp) != 0);
+        if (nb->flatPriorities) nb->kernelPriority = lo;
         CU(cudaStreamCreateWithPriority(&nb->stream[0], cudaStreamNonBlocking, nb->kernelPriority));
         nb->ownStream[0] = true;
     }
@@ -850,7 +858,7 @@ int nbnxm_b200_do_force_step_pipelined(nbnxm_b200_t* nb, int step, const nbnxm_b
         int lo = 0, hi = 0;
         CU(cudaDeviceGetStreamPriorityRange(&lo, &hi));
         CU(cudaStreamCreateWithFlags(&nb->h2dStream, cudaStreamNonBlocking));
-        CU(cudaStreamCreateWithPriority(&nb->d2hStream, cudaStreamNonBlocking, hi));
+        CU(cudaStreamCreateWithPriority(&nb->d2hStream, cudaStreamNonBlocking, nb->flatPriorities ? lo : hi));
         for (cudaStream_t& ps : nb->pipeKernelStream) CU(cudaStreamCreateWithPriority(&ps, cudaStreamNonBlocking, nb->kernelPriority));
         /* streams the chunk kernels rotate over: 2 (default) ... 4, NBNXM_B200_PIPE_STREAMS for A/B runs */
         const char* ns       = getenv("NBNXM_B200_PIPE_STREAMS");

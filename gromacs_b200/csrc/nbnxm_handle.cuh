@@ -174,6 +174,7 @@ struct nbnxm_b200
     cudaStream_t             pruneStream = nullptr;
     cudaEvent_t              pruneFork   = nullptr;
     int                      kernelPriority = 0; /* priority of the streams we create for force kernels */
+    bool                     flatPriorities = true;
     bool                     backgroundPrune = false;
     /* optional timeline of one pipelined step (nbnxm_b200_set_pipeline_timeline): per chunk the ends of its H2D copy, the start
      * and end of its kernel and the end of its D2H copy, as timing events against tlStart */
