@@ -7,6 +7,7 @@
  * Integer bookkeeping only; no device code.
  */
 #include <algorithm>
+#include <cstdlib>
 #include <cmath>
 #include <cstdio>
 #include <cstring>
@@ -105,7 +106,21 @@ int nbnxm_b200_chunk_plan(const nbnxm_b200_grid_t* grid, nbnxm_b200_sci_t* sci, 
     }
     int nbins = 0, ncx = 0, ncy = 0;
     nbnxm_b200_grid_info(grid, nullptr, &nbins, &ncx, &ncy);
-    const int        nchunks = std::max(1, std::min(std::min(nchunks_requested, 32), ncx));
+    /* NBNXM_B200_CHUNK_WEIGHTS="w0,w1,...": relative chunk widths for A/B runs (their number replaces nchunks_requested) */
+    std::vector<int> weightOverride;
+    if (const char* ws = getenv("NBNXM_B200_CHUNK_WEIGHTS"))
+    {
+        for (const char* q = ws; *q != 0;)
+        {
+            char*      end = nullptr;
+            const long v   = strtol(q, &end, 10);
+            if (end == q) break;
+            if (v > 0) weightOverride.push_back(int(v));
+            q = (*end == ',') ? end + 1 : end;
+        }
+        if (weightOverride.size() > 32 || int(weightOverride.size()) > ncx) weightOverride.clear();
+    }
+    const int        nchunks = weightOverride.empty() ? std::max(1, std::min(std::min(nchunks_requested, 32), ncx)) : int(weightOverride.size());
     std::vector<int> firstBinOfColumn(size_t(ncx) * ncy + 1);
     nbnxm_b200_grid_get_order(grid, nullptr, firstBinOfColumn.data());
     /* Tapered chunk widths: the first kernel of a step cannot start before the chunks it reads have arrived, and the last
@@ -119,7 +134,7 @@ int nbnxm_b200_chunk_plan(const nbnxm_b200_grid_t* grid, nbnxm_b200_sci_t* sci, 
     {
         const int d  = std::min(c, nchunks - 1 - c);
         const int w  = nchunks < 8 ? 4 : (d < 2 ? 1 : (d == 2 ? 2 : (d == 3 ? 3 : 4)));
-        weightSum[c + 1] = weightSum[c] + w;
+        weightSum[c + 1] = weightSum[c] + (weightOverride.empty() ? w : weightOverride[c]);
     }
     std::vector<int> firstBin(nchunks + 1);
     for (int c = 0; c <= nchunks; c++)
