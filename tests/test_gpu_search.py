@@ -413,3 +413,44 @@ def test_device_slab_lists_equal_the_host_plan(world):
     finally:
         search.free()
         whole.gpu_free()
+
+
+@pytest.mark.parametrize("kind", ["tall uniform", "all z equal", "clustered z", "lattice z"])
+def test_column_sort_forms_on_stressed_columns(monkeypatch, kind):
+    """the gridding's column sort on the device in both forms - buckets + ranks (default) and bitonic networks
+    (NBNXM_B200_SEARCH_BITONIC_SORT=1) - on columns of ~7000 atoms: uniform z (bucket count near its cap), every atom at the same z
+    (one bucket holds the column), z crowded into 1 % of the range, z on a coarse lattice (ties): the host gridder's order in
+    every case (the emulation checks the same systems on the CPU, tests/test_gpusearch_emu.py)"""
+    import torch
+    from gromacs_b200 import NbnxmGpu
+    from gromacs_b200.pairsearch import Grid, GpuPairSearch
+    d, _, nbat = golden_system("bench1_ewald_cutnone")
+    rng = np.random.default_rng(7)
+    box = np.array([1.2, 1.2, 60.0], np.float32)
+    n = 7000
+    x = rng.random((n, 3)) * box
+    if kind == "all z equal":
+        x[:, 2] = 30.0
+    elif kind == "clustered z":
+        x[:, 2] = np.where(rng.random(n) < 0.9, 5.0 + rng.random(n) * 0.01, x[:, 2])
+    elif kind == "lattice z":
+        x[:, 2] = np.minimum(np.round(x[:, 2] * 4) / 4, 59.75)
+    x = np.ascontiguousarray(x, np.float32)
+    grid = Grid(box, x, nthreads=2)
+    q = np.zeros(n, np.float32)
+    t = np.zeros(n, np.int32)
+    for bitonic in ("0", "1"):
+        monkeypatch.setenv("NBNXM_B200_SEARCH_BITONIC_SORT", bitonic)
+        nb = NbnxmGpu(product_params(d, vdw="Cut"), nbat)
+        try:
+            x_dev = torch.from_numpy(x).cuda()
+            torch.cuda.synchronize()
+            search = GpuPairSearch(nb)
+            search.set_atoms(q, t, int(d["nbat_ntypes"][0]), None, None, None)
+            dims = search.put_atoms_on_grid(box, x_dev.data_ptr())
+            atom_index, first_bin, _ = search.get_order()
+            search.free()
+        finally:
+            nb.gpu_free()
+        assert dims == (grid.natoms_nbat, grid.nbins, grid.ncx, grid.ncy)
+        assert np.array_equal(first_bin, grid.first_bin_of_column) and np.array_equal(atom_index, grid.atom_index)
