@@ -115,8 +115,8 @@ int nbnxm_b200_gpu_search_set_grid(nbnxm_b200_gpu_search_t* search, const float*
  * set_atoms (once per topology): charges, types (atom order), per-type LJ combination parameters (ntypes x 2, for the
  * CutComb* flavors) and the topology exclusions (CSR in atom order); any array may be NULL.
  * put_atoms_on_grid (every search step): d_x = natoms rvecs in device memory, atom order, inside the box; bins the
- * atoms into the columns of nbnxm_b200_grid_dims, sorts every column (one block per column, bitonic networks in
- * shared memory; a column may hold at most 8192 atoms), sizes the handle's atom buffers for the new grid and writes
+ * atoms into the columns of nbnxm_b200_grid_dims, sorts every column (one block per column in its shared
+ * memory, buckets along z + ranks; a column may hold at most 8192 atoms), sizes the handle's atom buffers for the new grid and writes
  * xq / types / lj_comb in nbat order, the slot -> atom map used by nbnxm_b200_x_to_nbat_x and the atom -> slot map
  * used by nbnxm_b200_reduce_f.  The order equals nbnxm_b200_grid_create's.  Follow with nbnxm_b200_gpu_search_build. */
 int nbnxm_b200_gpu_search_set_atoms(nbnxm_b200_gpu_search_t* search, int natoms, const float* q, const int* type, int ntypes,
