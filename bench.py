@@ -227,7 +227,7 @@ def reference_arm(args):
             "ms_per_step": r["sec"] * 1e3, "higher_is_better": True, "scaling": "strong", "vs_baseline": None, "dtype": "f32",
             "data": "synthetic",
             "config": {"workload": args.workload, "natoms": wl.box.natoms, "rc_nm": cfg["rc"], "vdw": cfg["vdw"],
-                       "energy_every_step": cfg["energy"],
+                       "elec": "ewald_analytical", "energy_every_step": cfg["energy"],
                        "note": "oracle port (oracle/nbnxm_oracle.c, float32, OpenMP) on the GPU-layout list: oracle/_ref is not built here"},
             "cpu_baseline": {"value": value, "unit": UNIT, "cores": r["threads"], "kind": "port",
                              "sample": "%d of %d sci entries of the outer list" % (r["sample_sci"], r["nsci"])},
@@ -239,7 +239,7 @@ def reference_arm(args):
         "warmup": 2, "ms_per_step": res["sec_per_iter"] * 1e3, "higher_is_better": True, "scaling": "strong",
         "vs_baseline": None, "dtype": "f32", "data": "synthetic",
         "config": {"workload": args.workload, "natoms": int(res["natoms"]), "rc_nm": cfg["rc"], "vdw": cfg["vdw"],
-                   "energy_every_step": cfg["energy"],
+                   "elec": "ewald_analytical", "energy_every_step": cfg["energy"],
                    "note": "reference SIMD kernel (%s; s/iteration of its builds / layouts on a 96 k-atom probe: %s), its own CPU pair list with rlist = rc"
                            % (res["simd"], json.dumps(res["simd_probed"]))},
         "cpu_baseline": {"value": value, "unit": UNIT, "cores": res["threads"], "kind": "reference",
