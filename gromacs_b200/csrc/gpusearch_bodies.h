@@ -800,6 +800,162 @@ NBS_HD void assignExclIndex(const Work& w, int item)
     }
 }
 
+/* ---- pass 8: perturbed (free-energy) pairs leave the cluster list for an atom-pair list (make_fep_list, pairlist.cpp:1414-1560,
+ * for the GPU layout; the device form of nbnxm_b200_pairlist_split_fep, pairsearch.cpp).  Item = sci entry * 64 + i-atom: the
+ * pairs of that i-atom with a perturbed partner, in the order of the entry's j-clusters.  MARK: flags the (cjPacked, half) mask
+ * words that lose a bit (they need an exclusion entry of their own, like words with topology exclusions) and counts the pairs
+ * that get listed; FILL: clears the bits and writes the pairs.  Whether a pair interacts comes from the topology exclusions
+ * themselves, not from the mask bits, which other items of the fill pass are clearing at the same time.  Like make_fep_list
+ * (rlist_fep2), interacting pairs beyond the list radius leave the cluster list without entering the perturbed one. ---- */
+
+struct FepWork
+{
+    const unsigned char* slotPert;  /* per nbat slot: atom is perturbed (0 for fillers) */
+    const unsigned char* clPert;    /* per cluster: any of its atoms is */
+    int*                 count;     /* per item (+1): listed pairs */
+    int*                 off;       /* scan */
+    int*                 nonEmpty;  /* per item (+1) */
+    int*                 iOff;      /* scan: index of the item's i-entry */
+    int*                 pairEntry; /* the list: i-entry of every pair, j-atom slot, interacts (1) / excluded (0) */
+    int*                 jjnr;
+    unsigned char*       interacts;
+    int*                 iinr; /* per i-entry: i-atom slot, shift index */
+    int*                 shift;
+};
+
+/* per slot / cluster flags from the per-atom flags (atom order) */
+struct FepFlags
+{
+    const unsigned char* perturbed; /* atom order */
+    const int*           atomIndex;
+    unsigned char*       slotPert;
+    unsigned char*       clPert;
+};
+
+NBS_HD void clusterPerturbedFlags(const FepFlags& f, int cluster)
+{
+    unsigned char any = 0;
+    for (int i = 0; i < c_cl; i++)
+    {
+        const int           slot = cluster * c_cl + i;
+        const int           a    = f.atomIndex[slot];
+        const unsigned char v    = (a >= 0 && f.perturbed[a]) ? 1 : 0;
+        f.slotPert[slot]         = v;
+        any |= v;
+    }
+    f.clPert[cluster] = any;
+}
+
+/* does the exclusion pass clear the bit of the pair (ai, aj)?  An atom's own entry in its exclusion list is skipped there
+ * (entryExclusions), so an atom and its periodic image interact */
+NBS_HD bool topologyExcluded(const Grid& g, int ai, int aj)
+{
+    if (g.exclIndex == nullptr || g.exclAtoms == nullptr || ai == aj)
+    {
+        return false;
+    }
+    for (int x = g.exclIndex[ai]; x < g.exclIndex[ai + 1]; x++)
+    {
+        if (g.exclAtoms[x] == aj)
+        {
+            return true;
+        }
+    }
+    return false;
+}
+
+template<bool FILL>
+NBS_HD void fepPairsOfIAtom(const Grid& g, const Params& p, const Work& w, const FepWork& f, int item)
+{
+    const int              isci  = item >> 6;
+    const int              i     = item & 63;
+    const nbnxm_b200_sci_t s     = w.sci[isci];
+    const int              ci    = i / c_cl, ia = i & (c_cl - 1);
+    const int              islot = s.sci * c_binAtoms + i;
+    const int              ai    = g.atomIndex[islot];
+    int                    n     = 0;
+    const int              out0  = FILL ? f.off[item] : 0;
+    const int              ient  = FILL ? f.iOff[item] : 0;
+    if (ai >= 0)
+    {
+        const bool  central = (s.shift == c_central);
+        const bool  iPert   = f.slotPert[islot] != 0;
+        const float sh[3]   = { float(s.shift % 5 - 2) * g.box[0], float((s.shift / 5) % 3 - 1) * g.box[1],
+                                float(s.shift / 15 - 1) * g.box[2] }; /* pbcutil/ishift.h */
+        const XQ    xi      = g.xq[islot];
+        for (int group = s.cj_packed_begin; group < s.cj_packed_end; group++)
+        {
+            const unsigned int imask = w.cjp[group].imei[0].imask;
+            for (int jm = 0; jm < 4; jm++)
+            {
+                const unsigned int bit = 1u << (jm * 8 + ci);
+                if (!(imask & bit))
+                {
+                    continue;
+                }
+                const int gcj = w.cjp[group].cj[jm];
+                if (!iPert && !f.clPert[gcj])
+                {
+                    continue;
+                }
+                const bool diagonal = central && gcj == s.sci * c_binCl + ci;
+                for (int ja = 0; ja < c_cl; ja++)
+                {
+                    const int jslot = gcj * c_cl + ja;
+                    const int aj    = g.atomIndex[jslot];
+                    if (aj < 0 || !(iPert || f.slotPert[jslot]))
+                    {
+                        continue;
+                    }
+                    if (diagonal && ja < ia)
+                    {
+                        continue; /* the mirrored pair owns it */
+                    }
+                    const int half      = ja / 4;
+                    bool      interacts = false;
+                    if (!(diagonal && ja == ia)) /* the self pair is excluded by construction, listed for its correction */
+                    {
+                        interacts = !topologyExcluded(g, ai, aj);
+                        if (interacts)
+                        {
+                            if (!FILL)
+                            {
+                                w.exclFlag[group * 2 + half] = 1;
+                            }
+                            else
+                            {
+                                atomicAndU32(&w.excl[w.cjp[group].imei[half].excl_ind].pair[(ja & 3) * c_cl + ia], ~bit);
+                            }
+                            const XQ xj = g.xq[jslot];
+                            if (!(dist2(xi.x + sh[0] - xj.x, xi.y + sh[1] - xj.y, xi.z + sh[2] - xj.z) < p.rl2))
+                            {
+                                continue;
+                            }
+                        }
+                    }
+                    if (FILL)
+                    {
+                        f.pairEntry[out0 + n] = ient;
+                        f.jjnr[out0 + n]      = jslot;
+                        f.interacts[out0 + n] = interacts ? 1 : 0;
+                    }
+                    n++;
+                }
+            }
+        }
+    }
+    if (!FILL)
+    {
+        f.count[item]    = n;
+        f.nonEmpty[item] = n > 0 ? 1 : 0;
+    }
+    else if (n > 0)
+    {
+        f.iinr[ient]  = islot;
+        f.shift[ient] = s.shift;
+    }
+}
+
 /* ======================================================================================================================
  * Gridding on the device: atoms (atom order, rvec) -> columns -> nbat order (Grid::putOnGrid, grid.cpp:1612;
  * sortCellsGpuGeometry :1169), the same order as the host gridder nbnxm_b200_grid_create (pairsearch.cpp): columns
@@ -819,6 +975,7 @@ struct GridBuild
     int*         colFirstBin;  /* scan (+1) */
     int*         colFill;      /* scatter counters */
     int*         colAtoms;     /* atoms grouped by column */
+    int*         rankOfAtom;   /* block form of the scatter: place of the atom among the atoms of its block in its column */
     int*         maxColCount;  /* scalar */
     int*         atomIndex;    /* nbat slot -> atom, prefilled with -1 */
     int*         slotOfAtom;   /* atom -> nbat slot */
@@ -847,14 +1004,19 @@ NBS_HD void atomicMaxInt(int* p, int v)
 #endif
 }
 
-/* pass G1: column of atom a */
-NBS_HD void gridColumnOfAtom(const GridBuild& g, int a)
+NBS_HD int gridColumn(const GridBuild& g, int a)
 {
     int cx = int(g.x[3 * a] / g.cellSize[0]);
     int cy = int(g.x[3 * a + 1] / g.cellSize[1]);
     cx     = cx < 0 ? 0 : (cx > g.ncx - 1 ? g.ncx - 1 : cx);
     cy     = cy < 0 ? 0 : (cy > g.ncy - 1 ? g.ncy - 1 : cy);
-    const int col  = cx * g.ncy + cy; /* x-major, grid.h:100 */
+    return cx * g.ncy + cy; /* x-major, grid.h:100 */
+}
+
+/* pass G1: column of atom a */
+NBS_HD void gridColumnOfAtom(const GridBuild& g, int a)
+{
+    const int col  = gridColumn(g, a);
     g.colOfAtom[a] = col;
     atomicAddInt(&g.colCount[col], 1);
 }
@@ -874,6 +1036,84 @@ NBS_HD void gridScatterAtom(const GridBuild& g, int a)
     const int pos = atomicAddInt(&g.colFill[col], 1);
     g.colAtoms[g.colAtomStart[col] + pos] = a;
 }
+
+/* Passes G1 and G3 as block passes: one block per c_gridBlockAtoms consecutive atoms with the column counters of the block in
+ * its scratch memory, so that the atomics of 12 M atoms onto a few thousand global counters (2.2 + 2.1 of the 4.8 ms of a
+ * gridding at 12.3 M atoms) become shared-memory atomics plus one global atomic per (block, column it touches).  Same results:
+ * the column counts are sums, the order of the atoms inside a column is arbitrary at this point (the sort makes it unique). */
+constexpr int c_gridBlockAtoms = 4096;
+
+struct ColumnCountBlock
+{
+    GridBuild g;
+    int       ncol;
+
+    NBS_HD int numStages(int) const { return 3; }
+    NBS_HD int numAtoms(int b) const
+    {
+        const int n = g.natoms - b * c_gridBlockAtoms;
+        return n < c_gridBlockAtoms ? n : c_gridBlockAtoms;
+    }
+    NBS_HD int numItems(int b, int s) const { return s == 1 ? numAtoms(b) : ncol; }
+    NBS_HD void operator()(int b, int s, int t, void* scratch) const
+    {
+        int* hist = static_cast<int*>(scratch);
+        if (s == 0)
+        {
+            hist[t] = 0;
+        }
+        else if (s == 1)
+        {
+            const int a    = b * c_gridBlockAtoms + t;
+            const int col  = gridColumn(g, a);
+            g.colOfAtom[a] = col;
+            atomicAddInt(&hist[col], 1);
+        }
+        else if (hist[t] != 0)
+        {
+            atomicAddInt(&g.colCount[t], hist[t]);
+        }
+    }
+};
+
+struct ColumnScatterBlock
+{
+    GridBuild g;
+    int       ncol;
+
+    NBS_HD int numStages(int) const { return 4; }
+    NBS_HD int numAtoms(int b) const
+    {
+        const int n = g.natoms - b * c_gridBlockAtoms;
+        return n < c_gridBlockAtoms ? n : c_gridBlockAtoms;
+    }
+    NBS_HD int numItems(int b, int s) const { return (s == 1 || s == 3) ? numAtoms(b) : ncol; }
+    NBS_HD void operator()(int b, int s, int t, void* scratch) const
+    {
+        int* hist = static_cast<int*>(scratch);
+        if (s == 0)
+        {
+            hist[t] = 0;
+        }
+        else if (s == 1)
+        {
+            const int a     = b * c_gridBlockAtoms + t;
+            g.rankOfAtom[a] = atomicAddInt(&hist[g.colOfAtom[a]], 1);
+        }
+        else if (s == 2)
+        {
+            /* the block's atoms of column t get hist[t] consecutive places in the column: hist[t] becomes the first of them */
+            const int v = hist[t];
+            hist[t]     = v != 0 ? atomicAddInt(&g.colFill[t], v) : 0;
+        }
+        else
+        {
+            const int a   = b * c_gridBlockAtoms + t;
+            const int col = g.colOfAtom[a];
+            g.colAtoms[g.colAtomStart[col] + hist[col] + g.rankOfAtom[a]] = a;
+        }
+    }
+};
 
 /* pass G4: one block per column, bitonic networks in the block's scratch memory (key[nPad], idx[nPad]); the stages
  * are separated by block barriers, every item of a stage touches its own elements only */
@@ -1289,6 +1529,8 @@ struct AtomFill
     const float* q;             /* atom order, may be null */
     const int*   type;          /* atom order, may be null */
     const float* ljCombPerType; /* ntypes x 2, may be null */
+    const unsigned char* perturbed; /* atom order, may be null: these atoms are masked out of the cluster kernels' atom data
+                                       (charge 0, type ntypes - 1: nbnxm_atomdata_mask_fep, atomdata.cpp:1039) */
     int          ntypes;
     XQ*          xq;
     int*         typeNbat;   /* may be null */
@@ -1302,9 +1544,10 @@ NBS_HD void fillAtomSlot(const AtomFill& f, int slot)
     v.x = a >= 0 ? f.x[3 * a] : c_farAway;
     v.y = a >= 0 ? f.x[3 * a + 1] : c_farAway;
     v.z = a >= 0 ? f.x[3 * a + 2] : c_farAway;
-    v.q = (a >= 0 && f.q != nullptr) ? f.q[a] : 0.0f;
+    const bool masked = (a >= 0 && f.perturbed != nullptr && f.perturbed[a] != 0);
+    v.q = (a >= 0 && f.q != nullptr && !masked) ? f.q[a] : 0.0f;
     f.xq[slot]  = v;
-    const int t = (a >= 0 && f.type != nullptr) ? f.type[a] : f.ntypes - 1;
+    const int t = (a >= 0 && f.type != nullptr && !masked) ? f.type[a] : f.ntypes - 1;
     if (f.typeNbat != nullptr)
     {
         f.typeNbat[slot] = t;

@@ -101,6 +101,21 @@ struct FAssignExclIndex
     NBS_HD void operator()(int i) const { assignExclIndex(w, i); }
 };
 
+struct FClusterPerturbed
+{
+    FepFlags f;
+    NBS_HD void operator()(int i) const { clusterPerturbedFlags(f, i); }
+};
+template<bool FILL>
+struct FFepPairs
+{
+    Grid    g;
+    Params  p;
+    Work    w;
+    FepWork f;
+    NBS_HD void operator()(int i) const { fepPairsOfIAtom<FILL>(g, p, w, f, i); }
+};
+
 struct FGridColumnOfAtom
 {
     GridBuild g;
@@ -137,7 +152,7 @@ struct SearchState
     Buf<BB>  clBB, binBB;
 
     /* gridding on the device */
-    Buf<int>   colOfAtom, colCount, colAtomStart, colBins, colFill, colAtoms, maxColCount;
+    Buf<int>   colOfAtom, colCount, colAtomStart, colBins, colFill, colAtoms, maxColCount, rankOfAtom;
     Buf<float> qAtom, ljCombPerType; /* static per-atom / per-type properties, atom order */
     Buf<int>   typeAtom;
     int        ntypes = 0, maxColumnAtoms = 0;
@@ -156,6 +171,14 @@ struct SearchState
     /* pass 3 as one warp per bin pair (FBinPairMaskWarp) instead of one thread per (bin pair, j-cluster) */
     bool      cooperativeMasks = false;
     bool      bitonicColumnSort = false; /* the column sort as bitonic networks (ColumnSort) instead of buckets + ranks */
+    bool      globalColumnAtomics = false; /* passes G1 / G3 one thread per atom with global atomics instead of block passes */
+
+    /* perturbed (free-energy) atoms: when set, buildPairlist moves their pairs from the cluster list to an atom-pair list
+     * (pass 8) and fillAtomData masks them out of the cluster kernels' atom data */
+    bool               havePerturbed = false;
+    Buf<unsigned char> perturbedAtom, slotPert, clPert, fepInteracts;
+    Buf<int>           fepCount, fepOff, fepNonEmpty, fepIOff, fepPairEntry, fepJjnr, fepIinr, fepShift;
+    int                numFepI = 0, numFepPairs = 0;
     int       nsci = 0, ncjp = 0, nexcl = 0, numBinPairs = 0, numEntries = 0;
     long long numClusterPairsHost = 0;
 };
@@ -297,7 +320,19 @@ int putAtomsOnGrid(BE& be, SearchState<BE>& st, const float* box, int ncx, int n
     gb.colFill      = st.colFill.p;
     gb.colAtoms     = st.colAtoms.p;
     gb.maxColCount  = st.maxColCount.p;
-    NBS_TRY(be.forEach(natoms, FGridColumnOfAtom{ gb }));
+    /* column counters of a block of atoms in shared memory where they fit (200 KB: 51 200 columns) */
+    const bool blockCounters = !st.globalColumnAtomics && size_t(ncol) * sizeof(int) <= size_t(200) * 1024 && natoms > 0;
+    const int  gridBlocks    = (natoms + c_gridBlockAtoms - 1) / c_gridBlockAtoms;
+    if (blockCounters)
+    {
+        NBS_TRY(be.reserve(st.rankOfAtom, natoms));
+        gb.rankOfAtom = st.rankOfAtom.p;
+        NBS_TRY(be.forEachBlock(gridBlocks, 1024, size_t(ncol) * sizeof(int), ColumnCountBlock{ gb, ncol }));
+    }
+    else
+    {
+        NBS_TRY(be.forEach(natoms, FGridColumnOfAtom{ gb }));
+    }
     NBS_TRY(be.forEach(ncol, FGridColumnBins{ gb }));
     NBS_TRY(be.scan(gb.colCount, gb.colAtomStart, ncol + 1));
     NBS_TRY(be.scan(gb.colBins, gb.colFirstBin, ncol + 1));
@@ -316,7 +351,14 @@ int putAtomsOnGrid(BE& be, SearchState<BE>& st, const float* box, int ncx, int n
     NBS_TRY(be.ones(st.atomIndex.p, sizeof(int) * nslots)); /* -1: filler */
     gb.atomIndex  = st.atomIndex.p;
     gb.slotOfAtom = st.slotOfAtom.p;
-    NBS_TRY(be.forEach(natoms, FGridScatterAtom{ gb }));
+    if (blockCounters)
+    {
+        NBS_TRY(be.forEachBlock(gridBlocks, 1024, size_t(ncol) * sizeof(int), ColumnScatterBlock{ gb, ncol }));
+    }
+    else
+    {
+        NBS_TRY(be.forEach(natoms, FGridScatterAtom{ gb }));
+    }
     if (st.bitonicColumnSort)
     {
         const int nPad    = nextPow2AtLeast32(st.maxColumnAtoms);
@@ -344,6 +386,7 @@ int fillAtomData(BE& be, SearchState<BE>& st, const float* x, XQ* xq, int* typeN
     f.q             = st.haveQ ? st.qAtom.p : nullptr;
     f.type          = st.haveType ? st.typeAtom.p : nullptr;
     f.ljCombPerType = st.haveLjComb ? st.ljCombPerType.p : nullptr;
+    f.perturbed     = st.havePerturbed ? st.perturbedAtom.p : nullptr;
     f.ntypes        = st.ntypes;
     f.xq            = xq;
     f.typeNbat      = typeNbat;
@@ -374,6 +417,7 @@ int buildPairlist(BE& be, SearchState<BE>& st, const XQ* xq, float rlist, int mi
     const int numIBins = binEnd - binBegin;
     const int nE       = numIBins * c_numSlots;
     st.nsci = st.ncjp = st.numBinPairs = st.numEntries = 0;
+    st.numFepI = st.numFepPairs = 0;
     st.nexcl               = 1;
     st.numClusterPairsHost = 0;
 
@@ -495,6 +539,32 @@ int buildPairlist(BE& be, SearchState<BE>& st, const XQ* xq, float rlist, int mi
     /* passes 6 / 7: exclusion masks */
     int numExclExtra = 0;
     NBS_TRY(be.forEach(st.numEntries * c_binAtoms, FEntryExclusions<false>{ g, p, w }));
+    /* pass 8, mark: mask words that lose the bits of perturbed pairs get an exclusion entry of their own as well */
+    FepWork   fw{};
+    const int numFepItems = st.havePerturbed ? st.nsci * c_binAtoms : 0;
+    if (st.havePerturbed)
+    {
+        if (st.nsci >= (1 << 25))
+        {
+            return be.fail("pair search: too many sci entries for the perturbed-pair pass");
+        }
+        NBS_TRY(be.reserve(st.slotPert, size_t(g.nbins) * c_binAtoms));
+        NBS_TRY(be.reserve(st.clPert, size_t(g.nbins) * c_binCl));
+        NBS_TRY(be.reserve(st.fepCount, numFepItems + 1));
+        NBS_TRY(be.reserve(st.fepOff, numFepItems + 1));
+        NBS_TRY(be.reserve(st.fepNonEmpty, numFepItems + 1));
+        NBS_TRY(be.reserve(st.fepIOff, numFepItems + 1));
+        NBS_TRY(be.zero(st.fepCount.p + numFepItems, sizeof(int)));
+        NBS_TRY(be.zero(st.fepNonEmpty.p + numFepItems, sizeof(int)));
+        NBS_TRY(be.forEach(g.nbins * c_binCl, FClusterPerturbed{ FepFlags{ st.perturbedAtom.p, g.atomIndex, st.slotPert.p, st.clPert.p } }));
+        fw.slotPert = st.slotPert.p;
+        fw.clPert   = st.clPert.p;
+        fw.count    = st.fepCount.p;
+        fw.off      = st.fepOff.p;
+        fw.nonEmpty = st.fepNonEmpty.p;
+        fw.iOff     = st.fepIOff.p;
+        NBS_TRY(be.forEach(numFepItems, FFepPairs<false>{ g, p, w, fw }));
+    }
     NBS_TRY(be.scan(w.exclFlag, w.exclOff, st.ncjp * 2 + 1));
     NBS_TRY(be.readInt(w.exclOff + st.ncjp * 2, &numExclExtra));
     st.nexcl = 1 + numExclExtra;
@@ -506,6 +576,43 @@ int buildPairlist(BE& be, SearchState<BE>& st, const XQ* xq, float rlist, int mi
         NBS_TRY(be.forEach(st.ncjp * 2, FAssignExclIndex{ w }));
         NBS_TRY(be.forEach(st.numEntries * c_binAtoms, FEntryExclusions<true>{ g, p, w }));
     }
+    if (st.havePerturbed)
+    {
+        /* pass 8, fill: sizes of the perturbed list, then its pairs; their bits leave the cluster list */
+        NBS_TRY(be.scan(fw.count, fw.off, numFepItems + 1));
+        NBS_TRY(be.scan(fw.nonEmpty, fw.iOff, numFepItems + 1));
+        unsigned long long unused = 0;
+        NBS_TRY(be.readInts2ULL(fw.off + numFepItems, &st.numFepPairs, fw.iOff + numFepItems, &st.numFepI, nullptr, &unused));
+        NBS_TRY(be.reserve(st.fepPairEntry, st.numFepPairs + 1));
+        NBS_TRY(be.reserve(st.fepJjnr, st.numFepPairs + 1));
+        NBS_TRY(be.reserve(st.fepInteracts, st.numFepPairs + 1));
+        NBS_TRY(be.reserve(st.fepIinr, st.numFepI + 1));
+        NBS_TRY(be.reserve(st.fepShift, st.numFepI + 1));
+        fw.pairEntry = st.fepPairEntry.p;
+        fw.jjnr      = st.fepJjnr.p;
+        fw.interacts = st.fepInteracts.p;
+        fw.iinr      = st.fepIinr.p;
+        fw.shift     = st.fepShift.p;
+        if (st.numFepPairs > 0)
+        {
+            NBS_TRY(be.forEach(numFepItems, FFepPairs<true>{ g, p, w, fw }));
+        }
+    }
+    return 0;
+}
+
+/* per-atom perturbed flags (atom order, host memory; null: no perturbed atoms) for the builds and griddings that follow */
+template<typename BE>
+int setPerturbed(BE& be, SearchState<BE>& st, int natoms, const unsigned char* perturbed)
+{
+    st.havePerturbed = false;
+    if (perturbed == nullptr || natoms <= 0)
+    {
+        return 0;
+    }
+    NBS_TRY(be.reserve(st.perturbedAtom, natoms));
+    NBS_TRY(be.upload(st.perturbedAtom.p, perturbed, natoms));
+    st.havePerturbed = true;
     return 0;
 }
 

@@ -151,6 +151,36 @@ int nbnxm_b200_init_feppairlist(nbnxm_b200_t* nb, int iloc, int num_i, const int
     return 0;
 }
 
+int nbnxm_b200_init_feppairlist_device(nbnxm_b200_t* nb, int iloc, int num_i, int num_pairs, const int* d_iinr, const int* d_shift,
+                                       const int* d_pair_entry, const int* d_jjnr, const unsigned char* d_interacts)
+{
+    if (!nb || iloc < 0 || iloc > 1 || num_i < 0 || num_pairs < 0) return fail("nbnxm_b200_init_feppairlist_device: bad argument");
+    if (num_pairs > 0 && (!d_iinr || !d_shift || !d_pair_entry || !d_jjnr || !d_interacts || num_i == 0))
+    {
+        return fail("nbnxm_b200_init_feppairlist_device: null list array");
+    }
+    CU(cudaSetDevice(nb->device));
+    nbnxm_b200::FepList& fl = nb->feplist[iloc];
+    cudaStream_t         st = nb->stream[iloc];
+    CU(cudaStreamSynchronize(st)); /* kernels of earlier steps may still read the previous list */
+    CU(fl.pairEntry.reserve(num_pairs + 1));
+    CU(fl.jjnr.reserve(num_pairs + 1));
+    CU(fl.exclFep.reserve(num_pairs + 1));
+    CU(fl.iinr.reserve(num_i + 1));
+    CU(fl.shift.reserve(num_i + 1));
+    if (num_pairs > 0)
+    {
+        CU(cudaMemcpyAsync(fl.pairEntry.p, d_pair_entry, sizeof(int) * num_pairs, cudaMemcpyDeviceToDevice, st));
+        CU(cudaMemcpyAsync(fl.jjnr.p, d_jjnr, sizeof(int) * num_pairs, cudaMemcpyDeviceToDevice, st));
+        CU(cudaMemcpyAsync(fl.exclFep.p, d_interacts, num_pairs, cudaMemcpyDeviceToDevice, st));
+        CU(cudaMemcpyAsync(fl.iinr.p, d_iinr, sizeof(int) * num_i, cudaMemcpyDeviceToDevice, st));
+        CU(cudaMemcpyAsync(fl.shift.p, d_shift, sizeof(int) * num_i, cudaMemcpyDeviceToDevice, st));
+    }
+    fl.numI     = num_pairs > 0 ? num_i : 0;
+    fl.numPairs = num_pairs;
+    return 0;
+}
+
 /* kernel arguments of one launch at the coupling parameters (lambdaCoul, lambdaVdw) */
 static int fepLaunchArgs(nbnxm_b200_t* nb, int iloc, float lambdaCoul, float lambdaVdw, nbfe::Params* pOut, nbfe::Atoms* aOut, nbfe::List* lOut)
 {

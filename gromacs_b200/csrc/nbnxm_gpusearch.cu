@@ -11,6 +11,7 @@
  * All passes are integer / bounding-box work bound by memory latency and divergence, not by FP32 throughput.
  */
 #include <cstdlib>
+#include <vector>
 
 #include "../../include/nbnxm_b200_search.h"
 #include "gpusearch_driver.h"
@@ -288,6 +289,10 @@ int nbnxm_b200_gpu_search_create(nbnxm_b200_gpu_search_t** out, nbnxm_b200_t* nb
     /* column sort of the gridding: buckets + ranks; NBNXM_B200_SEARCH_BITONIC_SORT=1 selects the bitonic networks for A/B runs */
     const char* bitonic      = getenv("NBNXM_B200_SEARCH_BITONIC_SORT");
     s->st.bitonicColumnSort = (bitonic != nullptr && bitonic[0] == '1');
+    /* column counts and scatter of the gridding: counters of a block of atoms in shared memory;
+     * NBNXM_B200_SEARCH_GLOBAL_ATOMICS=1 selects one thread per atom with global atomics for A/B runs */
+    const char* globalAtomics   = getenv("NBNXM_B200_SEARCH_GLOBAL_ATOMICS");
+    s->st.globalColumnAtomics = (globalAtomics != nullptr && globalAtomics[0] == '1');
     *out = s;
     return 0;
 }
@@ -303,7 +308,8 @@ int nbnxm_b200_gpu_search_free(nbnxm_b200_gpu_search_t* s)
                     t.entryNumBinPairs, t.entryBinPairOff, t.binPairJ, t.binPairEntry, t.binPairMask, t.entryNumJ,
                     t.entryGroups, t.entryCjOff, t.entryNumSci, t.entrySciOff, t.entryNonEmpty, t.entryCompactOff,
                     t.compactEntry, t.exclFlag, t.exclOff, t.numClusterPairs, t.sci, t.cjp, t.excl, s->be.tileSums, s->be.tileOffsets,
-                    t.colOfAtom, t.colCount, t.colAtomStart, t.colBins, t.colFill, t.colAtoms, t.maxColCount, t.qAtom, t.ljCombPerType,
+                    t.colOfAtom, t.colCount, t.colAtomStart, t.colBins, t.colFill, t.colAtoms, t.maxColCount, t.rankOfAtom, t.perturbedAtom, t.slotPert, t.clPert, t.fepInteracts, t.fepCount, t.fepOff, t.fepNonEmpty,
+                    t.fepIOff, t.fepPairEntry, t.fepJjnr, t.fepIinr, t.fepShift, t.qAtom, t.ljCombPerType,
                     t.typeAtom);
     if (s->be.h_value) cudaFreeHost(s->be.h_value);
     if (s->evStart) cudaEventDestroy(s->evStart);
@@ -457,8 +463,59 @@ int nbnxm_b200_gpu_search_build(nbnxm_b200_gpu_search_t* s, int iloc, float rlis
     {
         return 1;
     }
+    /* the perturbed pairs that left the cluster list: gpu_init_feppairlist without the host */
+    if (s->st.havePerturbed
+        && nbnxm_b200_init_feppairlist_device(nb, iloc, s->st.numFepI, s->st.numFepPairs, s->st.fepIinr.p, s->st.fepShift.p,
+                                              s->st.fepPairEntry.p, s->st.fepJjnr.p, s->st.fepInteracts.p))
+    {
+        return 1;
+    }
     /* the copies run on the list's stream; the next build (local stream) overwrites their source */
-    if (nb->stream[iloc] != s->be.st) CU(cudaStreamSynchronize(nb->stream[iloc]));
+    if (nb->stream[iloc] != s->be.st || s->st.havePerturbed) CU(cudaStreamSynchronize(nb->stream[iloc]));
+    return 0;
+}
+
+int nbnxm_b200_gpu_search_set_perturbed(nbnxm_b200_gpu_search_t* s, int natoms, const unsigned char* perturbed)
+{
+    if (!s || natoms < 0) return fail("nbnxm_b200_gpu_search_set_perturbed: bad argument");
+    CU(cudaSetDevice(s->nb->device));
+    if (perturbed != nullptr && s->st.haveGrid && natoms != s->st.g.natoms)
+    {
+        return fail("nbnxm_b200_gpu_search_set_perturbed: %d flags for a grid of %d atoms", natoms, s->st.g.natoms);
+    }
+    if (nbs::setPerturbed(s->be, s->st, natoms, perturbed)) return 1;
+    CU(cudaStreamSynchronize(s->be.st)); /* the caller's array may go out of scope */
+    return 0;
+}
+
+int nbnxm_b200_gpu_search_fep_sizes(const nbnxm_b200_gpu_search_t* s, int* num_i, int* num_j)
+{
+    if (!s) return fail("null search handle");
+    if (num_i) *num_i = s->st.numFepI;
+    if (num_j) *num_j = s->st.numFepPairs;
+    return 0;
+}
+
+int nbnxm_b200_gpu_search_fep_download(nbnxm_b200_gpu_search_t* s, int* iinr, int* jindex, int* jjnr, int* shift, unsigned char* interacts)
+{
+    if (!s || !jindex) return fail("nbnxm_b200_gpu_search_fep_download: null argument");
+    CU(cudaSetDevice(s->nb->device));
+    CU(cudaStreamSynchronize(s->be.st));
+    const int ni = s->st.numFepI, np = s->st.numFepPairs;
+    if (iinr && ni > 0) CU(cudaMemcpy(iinr, s->st.fepIinr.p, sizeof(int) * ni, cudaMemcpyDeviceToHost));
+    if (shift && ni > 0) CU(cudaMemcpy(shift, s->st.fepShift.p, sizeof(int) * ni, cudaMemcpyDeviceToHost));
+    if (jjnr && np > 0) CU(cudaMemcpy(jjnr, s->st.fepJjnr.p, sizeof(int) * np, cudaMemcpyDeviceToHost));
+    if (interacts && np > 0) CU(cudaMemcpy(interacts, s->st.fepInteracts.p, np, cudaMemcpyDeviceToHost));
+    /* jindex from the i-entry of every pair (entries are consecutive and none is empty) */
+    std::vector<int> pairEntry(np);
+    if (np > 0) CU(cudaMemcpy(pairEntry.data(), s->st.fepPairEntry.p, sizeof(int) * np, cudaMemcpyDeviceToHost));
+    for (int n = 0; n <= ni; n++) jindex[n] = 0;
+    for (int k = 0; k < np; k++)
+    {
+        if (pairEntry[k] < 0 || pairEntry[k] >= ni) return fail("nbnxm_b200_gpu_search_fep_download: pair %d names i-entry %d of %d", k, pairEntry[k], ni);
+        jindex[pairEntry[k] + 1]++;
+    }
+    for (int n = 0; n < ni; n++) jindex[n + 1] += jindex[n];
     return 0;
 }
 
@@ -530,6 +587,7 @@ int nbnxm_b200_gpu_search_build_slab(nbnxm_b200_gpu_search_t* s, nbnxm_b200_t* t
 {
     if (!s || !target || iloc < 0 || iloc > 1) return fail("nbnxm_b200_gpu_search_build_slab: bad argument");
     if (!s->st.haveGrid) return fail("nbnxm_b200_gpu_search_build_slab: put the atoms on the grid first");
+    if (s->st.havePerturbed) return fail("nbnxm_b200_gpu_search_build_slab: the perturbed-pair split is not available for slab lists");
     const nbs::Grid& g = s->st.g;
     if (home_begin < 0 || home_end > g.nbins || home_begin > home_end || halo_begin < 0 || halo_end > g.nbins || halo_begin > halo_end)
     {

@@ -707,7 +707,8 @@ int nbnxm_b200_pairlist_split_fep(nbnxm_b200_grid_t* g, const unsigned char* per
                                 const float dx = g->xs[3 * islot] + sh[0] - g->xs[3 * jslot];
                                 const float dy = g->xs[3 * islot + 1] + sh[1] - g->xs[3 * jslot + 1];
                                 const float dz = g->xs[3 * islot + 2] + sh[2] - g->xs[3 * jslot + 2];
-                                if (dx * dx + dy * dy + dz * dz >= rlist2) continue;
+                                /* the device form of the split (gpusearch_bodies.h, fepPairsOfIAtom) decides on the same bits */
+                                if (!(nbs::dist2(dx, dy, dz) < rlist2)) continue;
                             }
                             jOfI[iloc].push_back(jslot);
                             intOfI[iloc].push_back(interacts ? 1 : 0);

@@ -33,7 +33,7 @@ EXPORTED_SYMBOLS = [
     "nbnxm_b200_insert_nonlocal_dependency", "nbnxm_b200_setup_short_range_work",
     "nbnxm_b200_have_short_range_work", "nbnxm_b200_min_ci_balanced",
     "nbnxm_b200_is_kernel_ewald_analytical", "nbnxm_b200_get_timings", "nbnxm_b200_reset_timings",
-    "nbnxm_b200_copy_fepparams", "nbnxm_b200_init_fep_atomdata", "nbnxm_b200_init_feppairlist",
+    "nbnxm_b200_copy_fepparams", "nbnxm_b200_init_fep_atomdata", "nbnxm_b200_init_feppairlist", "nbnxm_b200_init_feppairlist_device",
     "nbnxm_b200_launch_free_energy_kernel", "nbnxm_b200_get_fep_dvdl", "nbnxm_b200_launch_foreign_energy_kernel",
     "nbnxm_b200_get_fep_foreign",
     "nbnxm_b200_set_timing", "nbnxm_b200_init_reduce_f", "nbnxm_b200_reduce_f", "nbnxm_b200_get_device_buffers", "nbnxm_b200_get_shared_outputs", "nbnxm_b200_get_streams",

@@ -18,6 +18,7 @@ SEARCH_SYMBOLS = [
     "nbnxm_b200_gpu_search_create", "nbnxm_b200_gpu_search_free", "nbnxm_b200_gpu_search_set_grid",
     "nbnxm_b200_gpu_search_build", "nbnxm_b200_gpu_search_sizes", "nbnxm_b200_gpu_search_download",
     "nbnxm_b200_gpu_search_set_atoms", "nbnxm_b200_gpu_search_put_atoms_on_grid", "nbnxm_b200_gpu_search_get_order",
+    "nbnxm_b200_gpu_search_set_perturbed", "nbnxm_b200_gpu_search_fep_sizes", "nbnxm_b200_gpu_search_fep_download",
     "nbnxm_b200_gpu_search_gather_slab", "nbnxm_b200_gpu_search_build_slab",
 ]
 
@@ -149,6 +150,26 @@ class GpuPairSearch:
         self._nb._check(self._lib.nbnxm_b200_gpu_search_set_atoms(
             self._s, C.c_int(self.natoms), _p(q, C.c_float), _p(t, C.c_int), C.c_int(ntypes), _p(lj, C.c_float),
             _p(ei, C.c_int), _p(ea, C.c_int)))
+
+    def set_perturbed(self, perturbed):
+        """make_fep_list on the device (nbnxm_b200_gpu_search_set_perturbed): perturbed[natoms] flags in atom order, or None to
+        switch the split off.  The builds that follow move the pairs of these atoms to the handle's perturbed list."""
+        if perturbed is None:
+            self._nb._check(self._lib.nbnxm_b200_gpu_search_set_perturbed(self._s, C.c_int(0), None))
+            return
+        pert = np.ascontiguousarray(perturbed, np.uint8)
+        self._nb._check(self._lib.nbnxm_b200_gpu_search_set_perturbed(self._s, C.c_int(pert.shape[0]), _p(pert, C.c_ubyte)))
+
+    def fep_download(self):
+        """the perturbed list built last, in the form of split_fep_pairlist: dict(iinr, jindex, jjnr, shift, excl_fep)"""
+        ni, nj = C.c_int(), C.c_int()
+        self._nb._check(self._lib.nbnxm_b200_gpu_search_fep_sizes(self._s, C.byref(ni), C.byref(nj)))
+        iinr, shift = np.zeros(ni.value, np.int32), np.zeros(ni.value, np.int32)
+        jindex = np.zeros(ni.value + 1, np.int32)
+        jjnr, inter = np.zeros(nj.value, np.int32), np.zeros(nj.value, np.uint8)
+        self._nb._check(self._lib.nbnxm_b200_gpu_search_fep_download(self._s, _p(iinr, C.c_int), _p(jindex, C.c_int), _p(jjnr, C.c_int),
+                                                                     _p(shift, C.c_int), _p(inter, C.c_ubyte)))
+        return dict(iinr=iinr, jindex=jindex, jjnr=jjnr, shift=shift, excl_fep=inter)
 
     def put_atoms_on_grid(self, box, d_x_ptr, nslabs=1, x_ready_event=None):
         """putAtomsOnGrid + setAtomProperties + gpu_init_atomdata on the device from natoms rvecs in device memory;

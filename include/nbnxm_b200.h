@@ -211,6 +211,12 @@ int nbnxm_b200_init_fep_atomdata(nbnxm_b200_t* nb, const float* q_a, const float
  * iinr[num_i], jindex[num_i + 1], jjnr / excl_fep per j-entry, shift[num_i]); excl_fep 0 = excluded pair */
 int nbnxm_b200_init_feppairlist(nbnxm_b200_t* nb, int iloc, int num_i, const int* iinr, const int* jindex,
                                 const int* jjnr, const int* shift, const unsigned char* excl_fep);
+/* the same list from device memory, in the layout the kernel reads (the device builder's perturbed-pair pass,
+ * nbnxm_b200_gpu_search_set_perturbed): pair_entry[num_pairs] = i-entry of every pair, interacts 0 = excluded pair;
+ * device-to-device copies on the locality's stream */
+int nbnxm_b200_init_feppairlist_device(nbnxm_b200_t* nb, int iloc, int num_i, int num_pairs, const int* d_iinr,
+                                       const int* d_shift, const int* d_pair_entry, const int* d_jjnr,
+                                       const unsigned char* d_interacts);
 /* gpu_launch_free_energy_kernel, nbnxm_gpu.h:115: adds into the same forces, shift forces and energies as
  * nbnxm_b200_launch_kernel, on the same stream */
 int nbnxm_b200_launch_free_energy_kernel(nbnxm_b200_t* nb, int iloc, int compute_energy, int compute_virial);

@@ -141,6 +141,18 @@ int nbnxm_b200_gpu_search_gather_slab(nbnxm_b200_gpu_search_t* search, nbnxm_b20
                                       int halo_begin, int halo_end);
 int nbnxm_b200_gpu_search_build_slab(nbnxm_b200_gpu_search_t* search, nbnxm_b200_t* target, int iloc, float rlist, int min_sci,
                                      int home_begin, int home_end, int halo_begin, int halo_end, int required_tx);
+/* Perturbed (free-energy) atoms, make_fep_list (pairlist.cpp:1414-1560) on the device: perturbed[natoms] in atom order, host
+ * memory (1 = charge or type differs between the end states; NULL: none).  From then on nbnxm_b200_gpu_search_build moves every
+ * pair with a perturbed atom from the cluster list to an atom-pair list - the list nbnxm_b200_pairlist_split_fep makes on the
+ * host, entry for entry - and installs it as the handle's perturbed list of that locality (nbnxm_b200_init_feppairlist without
+ * the host), and nbnxm_b200_gpu_search_put_atoms_on_grid masks the perturbed atoms out of the cluster kernels' atom data
+ * (charge 0, type ntypes - 1: nbnxm_atomdata_mask_fep, atomdata.cpp:1039).  Not for the slab builds. */
+int nbnxm_b200_gpu_search_set_perturbed(nbnxm_b200_gpu_search_t* search, int natoms, const unsigned char* perturbed);
+/* the perturbed list built last: sizes; copy in the host builder's form (iinr[num_i], jindex[num_i + 1], jjnr / interacts per
+ * j-entry, shift[num_i]; tests) */
+int nbnxm_b200_gpu_search_fep_sizes(const nbnxm_b200_gpu_search_t* search, int* num_i, int* num_j);
+int nbnxm_b200_gpu_search_fep_download(nbnxm_b200_gpu_search_t* search, int* iinr, int* jindex, int* jjnr, int* shift,
+                                       unsigned char* interacts);
 /* sizes of the list built last, cluster pairs in it, device time of the build (ms, CUDA events) */
 int nbnxm_b200_gpu_search_sizes(const nbnxm_b200_gpu_search_t* search, int* nsci, int* ncj_packed, int* nexcl,
                                 long long* ncluster_pairs, float* build_ms);

@@ -143,6 +143,8 @@ int search_emu_set_grid(const float* box, int ncx, int ncy, const int* first_bin
 int search_emu_set_bitonic_column_sort(int on)
 {
     g_st.bitonicColumnSort = on != 0;
+    /* the older forms travel together: bitonic networks with the per-atom global atomics of passes G1 / G3 */
+    g_st.globalColumnAtomics = on != 0;
     return 0;
 }
 
@@ -186,6 +188,35 @@ int search_emu_build(const float* xq, float rlist, int min_sci, int bin_begin, i
     sizes[2]        = g_st.nexcl;
     sizes[3]        = g_st.numBinPairs;
     *ncluster_pairs = g_st.numClusterPairsHost;
+    return 0;
+}
+
+/* perturbed atoms (atom order; null: none) for the builds that follow: pass 8 of buildPairlist */
+int search_emu_set_perturbed(int natoms, const unsigned char* perturbed)
+{
+    return nbs::setPerturbed(g_be, g_st, natoms, perturbed);
+}
+
+int search_emu_fep_sizes(int* num_i, int* num_pairs)
+{
+    *num_i     = g_st.numFepI;
+    *num_pairs = g_st.numFepPairs;
+    return 0;
+}
+
+int search_emu_fep_copy(int* iinr, int* shift, int* pair_entry, int* jjnr, unsigned char* interacts)
+{
+    if (g_st.numFepI)
+    {
+        std::memcpy(iinr, g_st.fepIinr.p, sizeof(int) * g_st.numFepI);
+        std::memcpy(shift, g_st.fepShift.p, sizeof(int) * g_st.numFepI);
+    }
+    if (g_st.numFepPairs)
+    {
+        std::memcpy(pair_entry, g_st.fepPairEntry.p, sizeof(int) * g_st.numFepPairs);
+        std::memcpy(jjnr, g_st.fepJjnr.p, sizeof(int) * g_st.numFepPairs);
+        std::memcpy(interacts, g_st.fepInteracts.p, g_st.numFepPairs);
+    }
     return 0;
 }
 

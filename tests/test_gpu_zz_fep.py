@@ -155,3 +155,109 @@ def test_cluster_and_perturbed_kernels_together_equal_brute_force(oracle):
             assert abs(e_lj - eb[0]) <= 2e-6 * abs(eb[0]) + 2e-6 and abs(e_el - eb[1]) <= 2e-6 * abs(eb[1]), (lam, e_lj, e_el, eb)
     finally:
         nb.gpu_free()
+
+
+def test_device_built_and_split_lists_equal_the_hosts_and_brute_force(oracle):
+    """the perturbed path with nothing of the search on the host: list built on the device, perturbed pairs split off on the device
+    (nbnxm_b200_gpu_search_set_perturbed) and installed device to device - the same cluster and perturbed lists as the host builder +
+    nbnxm_b200_pairlist_split_fep, entry for entry, and masked cluster kernel + perturbed kernel against brute force of the A-state
+    system at lambda = 0 and of the B-state system at lambda = 1; then the same from coordinates gridded on the device"""
+    import torch
+    from gromacs_b200 import LOCAL, NbnxmGpu, StepWorkload
+    from gromacs_b200.pairsearch import Grid, GpuPairSearch, split_fep_pairlist
+    from test_gpusearch_emu import assert_same_list
+    from util import load_golden, oracle_params, product_params, relrms
+    d = load_golden("bench1_ewald_cutnone")
+    x, box = d["sys_x"], d["sys_box"]
+    n = x.shape[0]
+    nt = int(d["nbat_ntypes"][0])
+    q_a, t_a = d["sys_q"].astype(np.float32), d["sys_type"].astype(np.int32)
+    rng = np.random.default_rng(4)
+    perturbed = np.zeros(n, np.uint8)
+    q_b, t_b = q_a.copy(), t_a.copy()
+    for k, m in enumerate(rng.choice(n // 3, size=45, replace=False)):
+        atoms = np.arange(3 * m, 3 * m + 3)
+        perturbed[atoms] = 1
+        q_b[atoms] *= (0.0 if k % 3 == 0 else 0.5)
+        if k % 2 == 0:
+            t_b[atoms] = nt - 1
+    grid = Grid(box, x, nthreads=2)
+    ai = grid.atom_index
+    real = ai >= 0
+    nbat = grid.atomdata(x, np.where(perturbed, 0.0, q_a), np.where(perturbed, nt - 1, t_a), d["nbat_nbfp"], nt,
+                         nbfp_comb=d["nbat_nbfp_comb"])
+    grid.pairlist(1.0, d["sys_excl_index"], d["sys_excl_atoms"], min_sci=200)
+    ref, fep_ref = split_fep_pairlist(grid, perturbed)
+
+    def nbat_order(a, fill):
+        out = np.full(ai.shape[0], fill, np.asarray(a).dtype)
+        out[real] = np.asarray(a)[ai[real]]
+        return out
+    p = oracle_params(oracle, d)
+    sw = StepWorkload(computeEnergy=True, computeVirial=True)
+
+    def end_states(nb):
+        nb.gpu_init_fep_atomdata(nbat_order(q_a, 0.0), nbat_order(q_b, 0.0), nbat_order(t_a, nt - 1), nbat_order(t_b, nt - 1))
+        for lam, q_end, t_end in ((0.0, q_a, t_a), (1.0, q_b, t_b)):
+            nb.copy_gpu_fepparams(True, 0.0, 0.0, 1, 0.3 ** 6, 0.3 ** 6, lam, lam)
+            nb.gpu_clear_outputs(True)
+            nb.gpu_launch_kernel(sw, LOCAL)
+            nb.gpu_launch_free_energy_kernel(sw, LOCAL)
+            nb.gpu_launch_cpyback(nbat, sw, LOCAL)
+            e_lj, e_el = nb.gpu_wait_finish_task(sw, LOCAL)
+            f = oracle.nbat_to_atom_order(nbat.f.astype(np.float64), ai, n)
+            fb, eb = oracle.brute_force(p, x, q_end, t_end, d["nbat_nbfp"], d["nbat_nbfp_comb"], box, d["sys_excl_index"],
+                                        d["sys_excl_atoms"])
+            assert relrms(f, fb) <= 5e-6, (lam, relrms(f, fb))
+            assert abs(e_lj - eb[0]) <= 2e-6 * abs(eb[0]) + 2e-6 and abs(e_el - eb[1]) <= 2e-6 * abs(eb[1]), (lam, e_lj, e_el, eb)
+
+    def same_fep(a, b):
+        for key in ("iinr", "jindex", "jjnr", "shift"):
+            assert np.array_equal(a[key], b[key]), key
+        assert np.array_equal(a["excl_fep"] != 0, b["excl_fep"] != 0)
+
+    # (1) host grid, list and split on the device
+    nb = NbnxmGpu(product_params(d, vdw="Cut"), nbat)
+    try:
+        nb.gpu_init_atomdata(nbat)
+        nb.gpu_upload_shiftvec(nbat)
+        nb.gpu_copy_xq_to_gpu(nbat, LOCAL)
+        search = GpuPairSearch(nb, grid, d["sys_excl_index"], d["sys_excl_atoms"])
+        search.set_perturbed(perturbed)
+        search.build(1.0, LOCAL, min_sci=200)
+        got = search.download()
+        assert_same_list((got.sci, got.cjPacked, got.excl), (ref.sci, ref.cjPacked, ref.excl))
+        same_fep(search.fep_download(), fep_ref)
+        nb.setupGpuShortRangeWork(LOCAL)
+        end_states(nb)
+        # switched off again: the plain list, no perturbed pairs
+        search.set_perturbed(None)
+        search.build(1.0, LOCAL, min_sci=200)
+        plain = grid.pairlist(1.0, d["sys_excl_index"], d["sys_excl_atoms"], min_sci=200)
+        got = search.download()
+        assert_same_list((got.sci, got.cjPacked, got.excl), (plain.sci, plain.cjPacked, plain.excl))
+        assert search.fep_download()["jjnr"].size == 0
+        search.free()
+    finally:
+        nb.gpu_free()
+    # (2) gridding on the device as well: the perturbed atoms are masked out of the cluster kernels' atom data there
+    nb = NbnxmGpu(product_params(d, vdw="Cut"), nbat)
+    try:
+        nb.gpu_upload_shiftvec(nbat)
+        x_dev = torch.from_numpy(np.ascontiguousarray(x, np.float32)).cuda()
+        torch.cuda.synchronize()
+        search = GpuPairSearch(nb)
+        search.set_atoms(q_a, t_a, nt, None, d["sys_excl_index"], d["sys_excl_atoms"])
+        search.set_perturbed(perturbed)
+        search.put_atoms_on_grid(box, x_dev.data_ptr())
+        atom_index, _, _ = search.get_order()
+        assert np.array_equal(atom_index, ai)
+        search.build(1.0, LOCAL, min_sci=200)
+        got = search.download()
+        assert_same_list((got.sci, got.cjPacked, got.excl), (ref.sci, ref.cjPacked, ref.excl))
+        same_fep(search.fep_download(), fep_ref)
+        nb.setupGpuShortRangeWork(LOCAL)
+        end_states(nb)
+        search.free()
+    finally:
+        nb.gpu_free()

@@ -314,3 +314,61 @@ def test_column_sort_corner_cases(emu, kind):
     nbins, atom_index, first_bin = emu_grid(emu, box, x, grid.ncx, grid.ncy)
     assert nbins == grid.nbins and np.array_equal(first_bin, grid.first_bin_of_column)
     assert np.array_equal(atom_index, grid.atom_index)
+
+
+def emu_fep_list(emu):
+    ni, npairs = C.c_int(), C.c_int()
+    emu.search_emu_fep_sizes(C.byref(ni), C.byref(npairs))
+    iinr = np.zeros(ni.value, np.int32)
+    shift = np.zeros(ni.value, np.int32)
+    pair_entry = np.zeros(npairs.value, np.int32)
+    jjnr = np.zeros(npairs.value, np.int32)
+    inter = np.zeros(npairs.value, np.uint8)
+    emu.search_emu_fep_copy(_p(iinr, C.c_int), _p(shift, C.c_int), _p(pair_entry, C.c_int), _p(jjnr, C.c_int), _p(inter, C.c_ubyte))
+    return iinr, shift, pair_entry, jjnr, inter
+
+
+def assert_same_fep_list(dev, host):
+    """device: (iinr, shift, pair_entry, jjnr, interacts); host: dict of split_fep_pairlist"""
+    iinr, shift, pair_entry, jjnr, inter = dev
+    assert np.array_equal(iinr, host["iinr"]) and np.array_equal(shift, host["shift"])
+    assert np.array_equal(jjnr, host["jjnr"]) and np.array_equal(inter != 0, host["excl_fep"] != 0)
+    # pair_entry is jindex expanded
+    want = np.repeat(np.arange(host["iinr"].shape[0], dtype=np.int32), np.diff(host["jindex"]))
+    assert np.array_equal(pair_entry, want)
+
+
+@pytest.mark.parametrize("case,rlist,min_sci,seed", [("bench1_ewald_cutnone", 1.0, 0, 4), ("bench1_ewald_cutnone", 1.05, 500, 5),
+                                                     ("test243_ewald_cutnone", 0.9, 60, 6), ("bench1_rf_cutnone_split", 0.8, 200, 7)])
+def test_perturbed_pair_split_equals_the_host_builders(emu, case, rlist, min_sci, seed):
+    """pass 8 of the device builder (perturbed pairs leave the cluster list for an atom-pair list) against
+    nbnxm_b200_pairlist_split_fep: the same perturbed list entry for entry (i-entries, j-atoms, interacting / excluded), the
+    same cluster list afterwards (masks bit for bit, exclusion words after expansion)"""
+    from gromacs_b200.pairsearch import split_fep_pairlist
+    d = load_golden(case)
+    grid, nbat = host_grid(d)
+    n = d["sys_x"].shape[0]
+    rng = np.random.default_rng(seed)
+    perturbed = np.zeros(n, np.uint8)
+    if n % 3 == 0 and d["sys_excl_index"][1] == 3:          # water: whole molecules
+        for m in rng.choice(n // 3, size=max(3, n // 200), replace=False):
+            perturbed[3 * m:3 * m + 3] = 1
+    else:
+        perturbed[rng.choice(n, size=max(5, n // 40), replace=False)] = 1
+    grid.pairlist(rlist, d["sys_excl_index"], d["sys_excl_atoms"], min_sci=min_sci)
+    ref, fep = split_fep_pairlist(grid, perturbed)
+    assert fep["jjnr"].size > 0 and (fep["excl_fep"] == 0).any() and (fep["excl_fep"] != 0).any()
+    assert emu.search_emu_set_perturbed(n, _p(perturbed, C.c_ubyte)) == 0
+    try:
+        got = emu_pairlist(emu, grid, nbat.xq, rlist, d["sys_excl_index"], d["sys_excl_atoms"], min_sci=min_sci)
+        assert_same_list(got[:3], (ref.sci, ref.cjPacked, ref.excl))
+        assert_same_fep_list(emu_fep_list(emu), fep)
+    finally:
+        emu.search_emu_set_perturbed(0, None)
+    # and without perturbed atoms the passes give the plain list again
+    plain = grid.pairlist(rlist, d["sys_excl_index"], d["sys_excl_atoms"], min_sci=min_sci)
+    got = emu_pairlist(emu, grid, nbat.xq, rlist, d["sys_excl_index"], d["sys_excl_atoms"], min_sci=min_sci)
+    assert_same_list(got[:3], (plain.sci, plain.cjPacked, plain.excl))
+    ni, npairs = C.c_int(), C.c_int()
+    emu.search_emu_fep_sizes(C.byref(ni), C.byref(npairs))
+    assert ni.value == 0 and npairs.value == 0
