@@ -35,3 +35,59 @@ def test_reference_float_kernel_is_not_within_1e6_of_double(oracle, case):
     # ... and its float accumulation of the shift forces sits above 1e-6 on every fixture but the split RF list
     if case != "bench1_rf_cutnone_split":
         assert vir > 1e-6, vir
+
+
+def _erfc_poly_coefficients():
+    """the degree-9 coefficients of erfc_poly as the kernel holds them (nbnxm_force_kernel_packed.cuh), highest first"""
+    import os
+    import re
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    src = open(os.path.join(root, "gromacs_b200", "csrc", "nbnxm_force_kernel_packed.cuh")).read()
+    body = src[src.index("__device__ __forceinline__ V erfc_poly("):]
+    body = body[:body.index("return vmul(q, e);")]
+    c = [float(v) for v in re.findall(r"vbc<V>\((-?\d\.\d+e[+-]\d+)f\)", body)]
+    assert len(c) == 10, c
+    return c
+
+
+def _erfc_poly(x, dtype):
+    """erfc_poly and exp(-x^2) of the packed energy kernels, evaluated in `dtype` (the exp in double: MUFU.EX2 is good to 2 ulp,
+    its error is not what is looked at here)"""
+    c = [dtype(v) for v in _erfc_poly_coefficients()]
+    x = x.astype(dtype)
+    t = dtype(1.0) / (x * dtype(0.5) + dtype(1.0))
+    q = t * c[0] + c[1]
+    for k in c[2:]:
+        q = q * t + k
+    h = x * x
+    nl = (-(x.astype(np.float64)) * x.astype(np.float64) + h.astype(np.float64)).astype(dtype)      # fl(x^2) - x^2, exact in an FMA
+    e = np.exp(-h.astype(np.float64)).astype(dtype)
+    e = e * nl + e
+    return q * e, e
+
+
+@pytest.mark.parametrize("beta,rc", [(3.12341, 1.0), (2.60284, 1.2), (3.47045, 0.9)])
+def test_ewald_force_from_the_energys_erfc_is_the_correction_form(beta, rc):
+    """Energy kernels take the real-space Ewald force of pairs without exclusions from erfc(beta r) and exp(-beta^2 r^2), which
+    they evaluate for the energy anyway: W = qq (erfc(beta r) / r + 2 beta / sqrt(pi) exp(-beta^2 r^2)).  In exact
+    arithmetic this is the correction form qq (1/r + r^2 beta^3 pmeCorrF(beta^2 r^2)) of the force-only kernels; in float32
+    the polynomial erfc keeps it within 4e-7 of the Coulomb force scale qq / r over the range of listed pairs - closer to the
+    exact expression than the rational correction itself."""
+    from math import erfc, exp, pi, sqrt
+    r = np.linspace(0.09, rc, 4000)
+    exact = np.array([erfc(beta * v) / v + 2.0 * beta / sqrt(pi) * exp(-(beta * v) ** 2) for v in r])
+    # the reference's rational correction in double (nbnxm_kernel_utils.h:216-250), as fillParamsDev folds it
+    cn = [-0.75225204789749321333, 0.069670166153766424023, -0.019278317264888380590, 0.0010054721316683106153,
+          -0.000053401640219807709149, 1.4703624142580877519e-6, -1.7357322914161492954e-8]
+    cd = [1.0, 0.50736591960530292870, 0.11583842382862377919, 0.014866955030185295499, 0.0011193462567257629232]
+    z2 = (beta * r) ** 2
+    corr = sum(c * z2 ** k for k, c in enumerate(cn)) / sum(c * z2 ** k for k, c in enumerate(cd))
+    correction_form = 1.0 / r + r * r * beta ** 3 * corr
+    # the two forms are the same function: the rational is the reference's float32-grade fit, up to 6e-7 of qq / r away from
+    # the exact expression near the cut-off (which is why the F+E step's forces moved closer to the double oracle, 5.4e-7 -> 3.9e-7)
+    assert (np.abs(correction_form - exact) * r).max() < 1e-6
+    for dtype, bound in ((np.float64, 5e-9), (np.float32, 4e-7)):
+        ec, ex = _erfc_poly(beta * r, dtype)
+        w = ec.astype(np.float64) / r + 2.0 * beta / sqrt(pi) * ex.astype(np.float64)
+        err = np.abs(w - exact) * r                                                # relative to qq / r
+        assert err.max() < bound, (dtype, err.max())
